@@ -1,0 +1,83 @@
+/* TEST INFRASTRUCTURE ONLY (oracle) -- CLI + C entry points over the CPU restatement in
+ * oracle_*.hpp.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+ * --impl reference legs may run this.  Mirrors the reference driver contract
+ * (app/subcommand/decompose.cpp:94-160: one <component_id>.pvst per component >= 3 vertices). */
+#include <cstring>
+#include <iostream>
+#include "oracle_decompose.hpp"
+
+using namespace oracle;
+
+struct OracleResult {
+	std::vector<u32> comp, a_id, z_id, parent; std::vector<uint8_t> a_fwd, z_fwd;
+	std::vector<u32> comp_ids, comp_nv, comp_nfl;
+};
+
+static OracleResult *pack(const std::vector<DecomposedComponent> &d) {
+	OracleResult *r = new OracleResult();
+	for (auto &c : d) {
+		r->comp_ids.push_back(c.component_id); r->comp_nv.push_back(c.n_vertices); r->comp_nfl.push_back((u32)c.flubbles.size());
+		for (auto &f : c.flubbles) {
+			r->comp.push_back(c.component_id); r->a_id.push_back(f.a_id); r->z_id.push_back(f.z_id);
+			r->a_fwd.push_back(f.a_fwd); r->z_fwd.push_back(f.z_fwd); r->parent.push_back(f.parent);
+		}
+	}
+	return r;
+}
+
+extern "C" {
+/* Graph given as arrays: ids ascending; edges as (v1_idx, side1, v2_idx, side2) in L-line order;
+ * side 0 = left, 1 = right.  Tips are inferred as in from_gfa.cpp:262-277. */
+OracleResult *oracle_decompose_arrays(uint32_t V, const uint32_t *ids, uint64_t E, const uint32_t *v1, const uint8_t *s1,
+				      const uint32_t *v2, const uint8_t *s2) {
+	try {
+		Graph g;
+		for (u32 i = 0; i < V; i++) g.add_vertex(ids[i], "");
+		for (uint64_t e = 0; e < E; e++) g.add_edge(ids[v1[e]], s1[e], ids[v2[e]], s2[e]);
+		for (u32 v = 0; v < V; v++) {
+			if (g.e_l[v].empty() && g.e_r[v].empty()) g.tips.insert({g.ids[v], SIDE_L});
+			else if (g.e_l[v].empty()) g.tips.insert({g.ids[v], SIDE_L});
+			else if (g.e_r[v].empty()) g.tips.insert({g.ids[v], SIDE_R});
+		}
+		return pack(decompose(g));
+	} catch (std::exception &e) { fprintf(stderr, "oracle error: %s\n", e.what()); return nullptr; }
+}
+OracleResult *oracle_decompose_gfa(const char *fp) {
+	try { return pack(decompose(load_gfa(fp, false, false))); }
+	catch (std::exception &e) { fprintf(stderr, "oracle error: %s\n", e.what()); return nullptr; }
+}
+uint64_t oracle_result_flubble_count(const OracleResult *r) { return r->a_id.size(); }
+uint64_t oracle_result_component_count(const OracleResult *r) { return r->comp_ids.size(); }
+void oracle_result_copy(const OracleResult *r, uint32_t *comp, uint32_t *a_id, uint8_t *a_fwd, uint32_t *z_id, uint8_t *z_fwd, uint32_t *parent) {
+	size_t n = r->a_id.size();
+	memcpy(comp, r->comp.data(), 4 * n); memcpy(a_id, r->a_id.data(), 4 * n); memcpy(z_id, r->z_id.data(), 4 * n);
+	memcpy(parent, r->parent.data(), 4 * n); memcpy(a_fwd, r->a_fwd.data(), n); memcpy(z_fwd, r->z_fwd.data(), n);
+}
+void oracle_result_copy_components(const OracleResult *r, uint32_t *ids, uint32_t *nv, uint32_t *nfl) {
+	size_t n = r->comp_ids.size();
+	memcpy(ids, r->comp_ids.data(), 4 * n); memcpy(nv, r->comp_nv.data(), 4 * n); memcpy(nfl, r->comp_nfl.data(), 4 * n);
+}
+void oracle_result_free(OracleResult *r) { delete r; }
+}
+
+#ifndef ORACLE_NO_MAIN
+int main(int argc, char **argv) {
+	if (argc < 2) { fprintf(stderr, "usage: povu_oracle decompose -i gfa -o dir\n"); return 2; }
+	std::string task = argv[1], gfa, out = ".";
+	for (int i = 2; i < argc; i++) {
+		std::string a = argv[i];
+		if (a == "-i" && i + 1 < argc) gfa = argv[++i];
+		else if (a == "-o" && i + 1 < argc) out = argv[++i];
+	}
+	try {
+		if (task == "decompose") {
+			Graph g = load_gfa(gfa, false, false);
+			for (auto &c : decompose(g)) {
+				std::ofstream f(out + "/" + std::to_string(c.component_id) + ".pvst");
+				f << pvst_text(c.flubbles);
+			}
+		} else { fprintf(stderr, "unknown task\n"); return 2; }
+	} catch (std::exception &e) { std::cerr << "[povu::subcommands::do_" << task << "] Error: " << e.what() << std::endl; return 1; }
+	return 0;
+}
+#endif
