@@ -1,0 +1,72 @@
+/* povu_b200 -- C ABI of the B200-native decompose -> call hot path.
+ *
+ * Plain pointers and sizes only (no torch / C++ types).  This is the device layer that sits behind
+ * the reference's in-process operators
+ *     pst::Tree::from_bd + pfl::find_flubbles   (/root/reference/include/povu/algorithms/flubbles.hpp:62,
+ *                                                /root/reference/src/povu/graph/spanning_tree.cpp:262)
+ *     bd::VG::componetize                       (/root/reference/src/povu/graph/bidirected.cpp:477)
+ * and behind the reference's own FFI entry point
+ *     povu_graph_find_flubbles                  (/root/reference/povu-rs/povu-ffi/povu_ffi.h:330-345)
+ * (declared, with identical signatures, in include/povu_ffi.h and implemented on top of these calls).
+ *
+ * Graph encoding: vertices are indices 0..V-1 in ascending segment-id order (the order
+ * mto::from_gfa::to_bd adds them, /root/reference/src/mto/from_gfa.cpp:191-215).  A "port" is
+ * 2*vertex + side with side 0 = left, 1 = right.  Edge e joins ports ep1[e] and ep2[e]; edges are in
+ * L-line order (from_gfa.cpp:223-243).  `L a + b +` is (2a+1, 2b); a '-' flips the respective side.
+ *
+ * Every function returns 0 on success, non-zero on failure (message via pvgpu_last_error).  There is no
+ * CPU fallback: pvgpu_create fails when no CUDA device is usable.
+ */
+#ifndef POVU_B200_H
+#define POVU_B200_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pvgpu_ctx pvgpu_ctx;
+typedef struct pvgpu_flubbles pvgpu_flubbles;
+
+/* device = CUDA ordinal; stream = an existing cudaStream_t (e.g. torch's current stream) or NULL to let
+ * the library create its own non-blocking stream. */
+int pvgpu_create(int device, void *stream, pvgpu_ctx **out);
+void pvgpu_destroy(pvgpu_ctx *ctx);
+const char *pvgpu_last_error(const pvgpu_ctx *ctx);
+/* kernels launched through this context so far (bench.py: gpu_launches) */
+uint64_t pvgpu_launch_count(const pvgpu_ctx *ctx);
+uint64_t pvgpu_peak_device_bytes(const pvgpu_ctx *ctx);
+/* 1 = sm_100a CUDA build, 2 = host debug rehearsal (tests only; never shipped) */
+int pvgpu_build_kind(void);
+
+/* decompose with HOST inputs (pinned or pageable): copies ep1/ep2 to the device on the context's
+ * stream, runs the pipeline, copies the flubble table back.  flags bit0: also return the class stack. */
+int pvgpu_decompose(pvgpu_ctx *ctx, uint32_t n_vertices, uint64_t n_edges, const uint32_t *ep1, const uint32_t *ep2,
+		    uint32_t flags, pvgpu_flubbles **out);
+/* same, inputs already resident in device memory (bench.py `value`) */
+int pvgpu_decompose_dev(pvgpu_ctx *ctx, uint32_t n_vertices, uint64_t n_edges, const uint32_t *d_ep1,
+			const uint32_t *d_ep2, uint32_t flags, pvgpu_flubbles **out);
+
+/* result accessors.  Flubbles are in creation order, components concatenated in component order;
+ * parent / PVST vertex indices are local to the component (0 = dummy root, flubble k of the component
+ * is PVST vertex k+1), exactly the indices the reference writes into <component_id>.pvst. */
+uint64_t pvgpu_flubbles_count(const pvgpu_flubbles *f);
+uint32_t pvgpu_flubbles_component_count(const pvgpu_flubbles *f);
+uint32_t pvgpu_flubbles_dfs_rounds(const pvgpu_flubbles *f);
+uint32_t pvgpu_flubbles_hash_collisions(const pvgpu_flubbles *f);
+/* any pointer may be NULL.  a_v/z_v are vertex indices; a_fwd/z_fwd 1 = '>' 0 = '<'. */
+void pvgpu_flubbles_copy(const pvgpu_flubbles *f, uint32_t *comp, uint32_t *a_v, uint8_t *a_fwd, uint32_t *z_v,
+			 uint8_t *z_fwd, uint32_t *parent, uint32_t *depth);
+/* per component (index k -> component id k+1): lowest vertex index, vertex count, flubble count,
+ * has-tips flag, non-laminar flag */
+void pvgpu_flubbles_copy_components(const pvgpu_flubbles *f, uint32_t *root_v, uint32_t *n_vertices,
+				    uint32_t *n_flubbles, uint32_t *has_tips, uint32_t *nonlaminar);
+/* class stack (only when flags bit0 was set): n_vertices entries */
+uint64_t pvgpu_flubbles_stack_size(const pvgpu_flubbles *f);
+void pvgpu_flubbles_copy_stack(const pvgpu_flubbles *f, uint32_t *v, uint32_t *class_id, uint32_t *fwd);
+void pvgpu_flubbles_free(pvgpu_flubbles *f);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -58,6 +58,39 @@ void oracle_result_copy_components(const OracleResult *r, uint32_t *ids, uint32_
 	memcpy(ids, r->comp_ids.data(), 4 * n); memcpy(nv, r->comp_nv.data(), 4 * n); memcpy(nfl, r->comp_nfl.data(), 4 * n);
 }
 void oracle_result_free(OracleResult *r) { delete r; }
+
+/* class stack of the k-th decomposed component of a GFA: entries (tree_edge_id, class, v_id, forward);
+ * tree_edge_id is the reference's creation-order edge id (spanning_tree.cpp:784-803) that the
+ * conformance cycle oracle (tests/lean4_conformance/src/main.rs:1594-1622) is keyed on.
+ * Returns the number of entries written (<= cap), or -1 on error. */
+int64_t oracle_class_stack_gfa(const char *fp, uint32_t k, uint64_t cap, uint32_t *edge_id, uint32_t *cls, uint32_t *v_id, uint8_t *fwd) {
+	try {
+		Graph g = load_gfa(fp, false, false);
+		std::vector<Component> comps = componetize(g);
+		uint32_t seen = 0;
+		for (auto &c : comps) {
+			if (c.g.ids.size() < 3) continue;
+			if (seen++ != k) continue;
+			STree t = spanning_tree(c.g);
+			cycle_equiv(t);
+			std::vector<StackEntry> s = class_stack(t);
+			uint64_t n = std::min<uint64_t>(cap, s.size());
+			for (uint64_t i = 0; i < n; i++) { edge_id[i] = t.tedges[s[i].tree_edge].id; cls[i] = s[i].cls; v_id[i] = s[i].v_id; fwd[i] = s[i].forward; }
+			return (int64_t)n;
+		}
+		return 0;
+	} catch (std::exception &e) { fprintf(stderr, "oracle error: %s\n", e.what()); return -1; }
+}
+/* decompose without tip inference (a VG assembled in memory, as in tests/integration_tests/pvst_tests.cc:12-39) */
+OracleResult *oracle_decompose_arrays_notips(uint32_t V, const uint32_t *ids, uint64_t E, const uint32_t *v1, const uint8_t *s1,
+					     const uint32_t *v2, const uint8_t *s2) {
+	try {
+		Graph g;
+		for (u32 i = 0; i < V; i++) g.add_vertex(ids[i], "");
+		for (uint64_t e = 0; e < E; e++) g.add_edge(ids[v1[e]], s1[e], ids[v2[e]], s2[e]);
+		return pack(decompose(g));
+	} catch (std::exception &e) { fprintf(stderr, "oracle error: %s\n", e.what()); return nullptr; }
+}
 }
 
 #ifndef ORACLE_NO_MAIN

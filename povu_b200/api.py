@@ -1,0 +1,185 @@
+"""ctypes binding of the povu_b200 C ABI (include/povu_b200.h) and the host-side mirror of the
+reference's operator interface for the decompose -> call path.
+
+The product path loads ONLY the CUDA library (libpovu_b200.so, sm_100a).  There is no CPU fallback:
+if the library or a CUDA device is missing, construction raises.  (tests/emu builds a host debug
+rehearsal of the same kernel sources; it is loaded only by tests that pass `lib_path` explicitly.)
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+DEFAULT_LIB = os.path.join(_HERE, "libpovu_b200.so")
+
+_u32p = np.ctypeslib.ndpointer(dtype=np.uint32, flags="C_CONTIGUOUS")
+
+
+def _as_ptr(a, ct):
+    return a.ctypes.data_as(C.POINTER(ct)) if a is not None else None
+
+
+def load_library(lib_path=None):
+    path = lib_path or DEFAULT_LIB
+    if not os.path.exists(path):
+        raise RuntimeError(
+            f"povu_b200: CUDA library {path} not found. Build it with `python -c 'import __graft_entry__ as g; g.build()'`. "
+            "There is no CPU fallback.")
+    lib = C.CDLL(path)
+    vp, u32, u64 = C.c_void_p, C.c_uint32, C.c_uint64
+    P32, P8 = C.POINTER(C.c_uint32), C.POINTER(C.c_uint8)
+    lib.pvgpu_create.argtypes = [C.c_int, vp, C.POINTER(vp)]
+    lib.pvgpu_create.restype = C.c_int
+    lib.pvgpu_destroy.argtypes = [vp]
+    lib.pvgpu_last_error.argtypes = [vp]
+    lib.pvgpu_last_error.restype = C.c_char_p
+    lib.pvgpu_launch_count.argtypes = [vp]
+    lib.pvgpu_launch_count.restype = u64
+    lib.pvgpu_peak_device_bytes.argtypes = [vp]
+    lib.pvgpu_peak_device_bytes.restype = u64
+    lib.pvgpu_build_kind.restype = C.c_int
+    lib.pvgpu_decompose.argtypes = [vp, u32, u64, vp, vp, u32, C.POINTER(vp)]
+    lib.pvgpu_decompose.restype = C.c_int
+    lib.pvgpu_decompose_dev.argtypes = [vp, u32, u64, vp, vp, u32, C.POINTER(vp)]
+    lib.pvgpu_decompose_dev.restype = C.c_int
+    lib.pvgpu_flubbles_count.argtypes = [vp]
+    lib.pvgpu_flubbles_count.restype = u64
+    lib.pvgpu_flubbles_component_count.argtypes = [vp]
+    lib.pvgpu_flubbles_component_count.restype = u32
+    lib.pvgpu_flubbles_dfs_rounds.argtypes = [vp]
+    lib.pvgpu_flubbles_dfs_rounds.restype = u32
+    lib.pvgpu_flubbles_hash_collisions.argtypes = [vp]
+    lib.pvgpu_flubbles_hash_collisions.restype = u32
+    lib.pvgpu_flubbles_copy.argtypes = [vp, P32, P32, P8, P32, P8, P32, P32]
+    lib.pvgpu_flubbles_copy_components.argtypes = [vp, P32, P32, P32, P32, P32]
+    lib.pvgpu_flubbles_stack_size.argtypes = [vp]
+    lib.pvgpu_flubbles_stack_size.restype = u64
+    lib.pvgpu_flubbles_copy_stack.argtypes = [vp, P32, P32, P32]
+    lib.pvgpu_flubbles_free.argtypes = [vp]
+    return lib
+
+
+def edge_ports(g):
+    """(ep1, ep2) u32 port arrays of a synth/loader graph dict: port = 2*vertex + side."""
+    ep1 = (g["v1"].astype(np.uint32) * 2 + g["s1"].astype(np.uint32)).astype(np.uint32)
+    ep2 = (g["v2"].astype(np.uint32) * 2 + g["s2"].astype(np.uint32)).astype(np.uint32)
+    return np.ascontiguousarray(ep1), np.ascontiguousarray(ep2)
+
+
+class Flubbles:
+    """Result of decompose: flat flubble table + per-component table (see include/povu_b200.h)."""
+
+    def __init__(self, lib, h):
+        n = lib.pvgpu_flubbles_count(h)
+        nc = lib.pvgpu_flubbles_component_count(h)
+        u32, u8 = np.uint32, np.uint8
+        self.comp = np.zeros(n, u32); self.a_v = np.zeros(n, u32); self.z_v = np.zeros(n, u32)
+        self.a_fwd = np.zeros(n, u8); self.z_fwd = np.zeros(n, u8)
+        self.parent = np.zeros(n, u32); self.depth = np.zeros(n, u32)
+        lib.pvgpu_flubbles_copy(h, _as_ptr(self.comp, C.c_uint32), _as_ptr(self.a_v, C.c_uint32), _as_ptr(self.a_fwd, C.c_uint8),
+                                _as_ptr(self.z_v, C.c_uint32), _as_ptr(self.z_fwd, C.c_uint8), _as_ptr(self.parent, C.c_uint32),
+                                _as_ptr(self.depth, C.c_uint32))
+        self.comp_root = np.zeros(nc, u32); self.comp_nv = np.zeros(nc, u32); self.comp_nfl = np.zeros(nc, u32)
+        self.comp_has_tips = np.zeros(nc, u32); self.comp_nonlaminar = np.zeros(nc, u32)
+        lib.pvgpu_flubbles_copy_components(h, _as_ptr(self.comp_root, C.c_uint32), _as_ptr(self.comp_nv, C.c_uint32),
+                                           _as_ptr(self.comp_nfl, C.c_uint32), _as_ptr(self.comp_has_tips, C.c_uint32),
+                                           _as_ptr(self.comp_nonlaminar, C.c_uint32))
+        ns = lib.pvgpu_flubbles_stack_size(h)
+        self.stack_v = np.zeros(ns, u32); self.stack_class = np.zeros(ns, u32); self.stack_fwd = np.zeros(ns, u32)
+        if ns:
+            lib.pvgpu_flubbles_copy_stack(h, _as_ptr(self.stack_v, C.c_uint32), _as_ptr(self.stack_class, C.c_uint32),
+                                          _as_ptr(self.stack_fwd, C.c_uint32))
+        self.dfs_rounds = lib.pvgpu_flubbles_dfs_rounds(h)
+        self.n = int(n)
+
+    def labels(self, ids):
+        """Flubble::as_str (pvst.hpp:408-412): e.g. '>12>17'."""
+        a = ids[self.a_v]; z = ids[self.z_v]
+        return [f"{'>' if af else '<'}{x}{'>' if zf else '<'}{y}" for x, af, y, zf in zip(a, self.a_fwd, z, self.z_fwd)]
+
+    def pvst_texts(self, ids):
+        """{component_id: text} of the .pvst v0.0.3 files the reference would write
+        (to_pvst.cpp:23-109; components with < 3 vertices are skipped, decompose.cpp:135-142)."""
+        out = {}
+        labels = self.labels(ids)
+        base = 0
+        for k in range(len(self.comp_nv)):
+            nfl = int(self.comp_nfl[k])
+            if self.comp_nv[k] >= 3:
+                ch = [[] for _ in range(nfl + 1)]
+                par = self.parent[base:base + nfl]
+                for j in range(nfl):
+                    ch[par[j]].append(j + 1)
+                lines = ["H\t0.0.3\t.\t.\t.\n"]
+                for i in range(nfl + 1):
+                    kids = ", ".join(map(str, ch[i])) if ch[i] else "."
+                    if i == 0:
+                        lines.append(f"D\t0\t.\t{kids}\t.\n")
+                    else:
+                        lines.append(f"F\t{i}\t{labels[base + i - 1]}\t{kids}\tL\n")
+                out[k + 1] = "".join(lines)
+            base += nfl
+        return out
+
+
+class Povu:
+    """One context = one CUDA device + stream."""
+
+    def __init__(self, device=0, stream=None, lib_path=None):
+        self.lib = load_library(lib_path)
+        kind = self.lib.pvgpu_build_kind()
+        if lib_path is None and kind != 1:
+            raise RuntimeError("povu_b200: the default library must be the CUDA build")
+        h = C.c_void_p()
+        rc = self.lib.pvgpu_create(int(device), C.c_void_p(stream) if stream else None, C.byref(h))
+        if rc != 0:
+            raise RuntimeError("povu_b200: pvgpu_create failed (no usable CUDA device; there is no CPU fallback)")
+        self.h = h
+
+    def close(self):
+        if self.h:
+            self.lib.pvgpu_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def launches(self):
+        return int(self.lib.pvgpu_launch_count(self.h))
+
+    @property
+    def peak_bytes(self):
+        return int(self.lib.pvgpu_peak_device_bytes(self.h))
+
+    def _err(self):
+        return self.lib.pvgpu_last_error(self.h).decode()
+
+    def decompose(self, n_vertices, ep1, ep2, want_stack=False):
+        """Host arrays in, Flubbles out (H2D + kernels + D2H)."""
+        ep1 = np.ascontiguousarray(ep1, dtype=np.uint32); ep2 = np.ascontiguousarray(ep2, dtype=np.uint32)
+        out = C.c_void_p()
+        rc = self.lib.pvgpu_decompose(self.h, int(n_vertices), len(ep1), ep1.ctypes.data, ep2.ctypes.data, 1 if want_stack else 0, C.byref(out))
+        if rc != 0:
+            raise RuntimeError("pvgpu_decompose: " + self._err())
+        try:
+            return Flubbles(self.lib, out)
+        finally:
+            self.lib.pvgpu_flubbles_free(out)
+
+    def decompose_dev(self, n_vertices, n_edges, d_ep1, d_ep2, want_stack=False, fetch=True):
+        """Device pointers in (ints)."""
+        out = C.c_void_p()
+        rc = self.lib.pvgpu_decompose_dev(self.h, int(n_vertices), int(n_edges), C.c_void_p(d_ep1), C.c_void_p(d_ep2), 1 if want_stack else 0, C.byref(out))
+        if rc != 0:
+            raise RuntimeError("pvgpu_decompose_dev: " + self._err())
+        try:
+            return Flubbles(self.lib, out) if fetch else int(self.lib.pvgpu_flubbles_count(out))
+        finally:
+            self.lib.pvgpu_flubbles_free(out)

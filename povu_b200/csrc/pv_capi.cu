@@ -1,0 +1,90 @@
+// povu_b200 -- C ABI (include/povu_b200.h) over the device pipelines.
+#include "../../include/povu_b200.h"
+#include "pv_decompose.cuh"
+
+struct pvgpu_ctx { pv::Ctx c; std::string err; };
+struct pvgpu_flubbles { pv::DecompOut o; };
+template <class T> static void cp(T *dst, const std::vector<T> &src) { if (dst && !src.empty()) memcpy(dst, src.data(), src.size() * sizeof(T)); }
+
+extern "C" {
+
+int pvgpu_build_kind(void) {
+#ifndef PV_EMU
+	return 1;
+#else
+	return 2;
+#endif
+}
+
+int pvgpu_create(int device, void *stream, pvgpu_ctx **out) {
+	if (!out) return 1;
+	*out = nullptr;
+	pvgpu_ctx *x = new pvgpu_ctx();
+	try {
+#ifndef PV_EMU
+		int n = 0;
+		if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) throw std::runtime_error("no CUDA device available (povu_b200 has no CPU fallback)");
+		if (device < 0 || device >= n) throw std::runtime_error("invalid CUDA device ordinal");
+#endif
+		x->c.init(device, stream);
+	} catch (std::exception &e) {
+		fprintf(stderr, "pvgpu_create: %s\n", e.what());
+		delete x;
+		return 1;
+	}
+	*out = x;
+	return 0;
+}
+void pvgpu_destroy(pvgpu_ctx *x) { if (x) { x->c.destroy(); delete x; } }
+const char *pvgpu_last_error(const pvgpu_ctx *x) { return x ? x->err.c_str() : "null context"; }
+uint64_t pvgpu_launch_count(const pvgpu_ctx *x) { return x ? x->c.launches : 0; }
+uint64_t pvgpu_peak_device_bytes(const pvgpu_ctx *x) { return x ? x->c.bytes_peak : 0; }
+
+static int run_decompose(pvgpu_ctx *x, uint32_t V, uint64_t E, const uint32_t *d1, const uint32_t *d2, uint32_t flags, pvgpu_flubbles **out) {
+	pvgpu_flubbles *f = new pvgpu_flubbles();
+	pv::DecompOpts opt; opt.want_stack = flags & 1u;
+	pv::decompose_device(x->c, V, E, d1, d2, opt, f->o);
+	if (f->o.collisions) { delete f; throw std::runtime_error("cycle-equivalence label collision detected by the exact bracket-set check"); }
+	*out = f;
+	return 0;
+}
+
+int pvgpu_decompose_dev(pvgpu_ctx *x, uint32_t V, uint64_t E, const uint32_t *d1, const uint32_t *d2, uint32_t flags, pvgpu_flubbles **out) {
+	if (!x || !out) return 1;
+	*out = nullptr;
+	try {
+#ifndef PV_EMU
+		PV_CUDA_CHECK(cudaSetDevice(x->c.device));
+#endif
+		return run_decompose(x, V, E, d1, d2, flags, out);
+	} catch (std::exception &e) { x->err = e.what(); return 1; }
+}
+
+int pvgpu_decompose(pvgpu_ctx *x, uint32_t V, uint64_t E, const uint32_t *ep1, const uint32_t *ep2, uint32_t flags, pvgpu_flubbles **out) {
+	if (!x || !out) return 1;
+	*out = nullptr;
+	try {
+#ifndef PV_EMU
+		PV_CUDA_CHECK(cudaSetDevice(x->c.device));
+#endif
+		pv::Buf<pv::u32> d1(x->c, E ? E : 1), d2(x->c, E ? E : 1);
+		x->c.h2d(d1.p, ep1, E * 4); x->c.h2d(d2.p, ep2, E * 4);
+		return run_decompose(x, V, E, d1.p, d2.p, flags, out);
+	} catch (std::exception &e) { x->err = e.what(); return 1; }
+}
+
+uint64_t pvgpu_flubbles_count(const pvgpu_flubbles *f) { return f->o.a_v.size(); }
+uint32_t pvgpu_flubbles_component_count(const pvgpu_flubbles *f) { return (uint32_t)f->o.comp_root.size(); }
+uint32_t pvgpu_flubbles_dfs_rounds(const pvgpu_flubbles *f) { return f->o.dfs_rounds; }
+uint32_t pvgpu_flubbles_hash_collisions(const pvgpu_flubbles *f) { return f->o.collisions; }
+void pvgpu_flubbles_copy(const pvgpu_flubbles *f, uint32_t *comp, uint32_t *a_v, uint8_t *a_fwd, uint32_t *z_v, uint8_t *z_fwd, uint32_t *parent, uint32_t *depth) {
+	cp(comp, f->o.comp); cp(a_v, f->o.a_v); cp(a_fwd, f->o.a_fwd); cp(z_v, f->o.z_v); cp(z_fwd, f->o.z_fwd); cp(parent, f->o.parent); cp(depth, f->o.depth);
+}
+void pvgpu_flubbles_copy_components(const pvgpu_flubbles *f, uint32_t *root_v, uint32_t *nv, uint32_t *nfl, uint32_t *tips, uint32_t *nonlam) {
+	cp(root_v, f->o.comp_root); cp(nv, f->o.comp_nv); cp(nfl, f->o.comp_nfl); cp(tips, f->o.comp_has_tips); cp(nonlam, f->o.comp_nonlaminar);
+}
+uint64_t pvgpu_flubbles_stack_size(const pvgpu_flubbles *f) { return f->o.stack_v.size(); }
+void pvgpu_flubbles_copy_stack(const pvgpu_flubbles *f, uint32_t *v, uint32_t *cls, uint32_t *fwd) { cp(v, f->o.stack_v); cp(cls, f->o.stack_class); cp(fwd, f->o.stack_fwd); }
+void pvgpu_flubbles_free(pvgpu_flubbles *f) { delete f; }
+
+}

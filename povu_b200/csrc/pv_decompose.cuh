@@ -1,0 +1,622 @@
+// povu_b200 -- decompose: bidirected graph -> flubbles + PVST nesting, every step a data-parallel
+// kernel (no host graph traversal).  Replaces, with identical results, the reference's
+//   VG::componetize            /root/reference/src/povu/graph/bidirected.cpp:477-602
+//   pst::Tree::from_bd         /root/reference/src/povu/graph/spanning_tree.cpp:262-463
+//   simple_cycle_equiv         /root/reference/src/povu/algorithms/flubbles.cpp:503-719
+//   compute_eq_class_stack     flubbles.cpp:412-501 (+ tree_utils.cpp:19-157)
+//   compute_eq_class_metadata  flubbles.cpp:375-410
+//   add_flubbles               flubbles.cpp:295-367
+//
+// Pipeline (DESIGN.md has the full derivation):
+//  D1  CSR of the bi-edged graph whose per-port adjacency order equals the reference's per-component
+//      renumbered edge order (two stable radix sorts).
+//  D2  The reference's lexicographic DFS tree, reproduced exactly but in parallel: rounds of
+//      {union-find over unvisited segments -> per-component claim by the deepest visited neighbour
+//       (64-bit atomicMax) -> "first unvisited edge" functional graph -> pointer-doubling path
+//       marking with rho/self-intersection truncation}.  A chain of bubbles needs 2-3 rounds.
+//  D3  Euler tour + list ranking -> preorder numbers and subtree sizes.
+//  D4  back edges (parallel edges collapse, one back edge per self-looped segment, tips -> dummy root),
+//      bridges -> "simplifying" edges, 128-bit XOR labels, prefix XOR -> class key per black edge,
+//      exact bracket-set verification of every merged pair (count + range-minimum test).
+//  D5  class-stack positions from subtree counts (one scan), radix sort by key -> next/prev seen.
+//  D6  flubbles + PVST parents: laminar components via a max-plus function scan and previous-smaller
+//      queries; non-laminar components replay the reference's stack machine (one thread each).
+#pragma once
+#include "pv_prims.cuh"
+
+namespace pv {
+
+struct DecompOut {
+	// per flubble, in creation order (PVST vertex idx = local position + 1)
+	std::vector<u32> comp;      // 0-based component index (component id = comp + 1)
+	std::vector<u32> a_v, z_v;  // vertex *indices*
+	std::vector<u8> a_fwd, z_fwd;
+	std::vector<u32> parent;    // PVST idx within the component (0 = dummy root)
+	std::vector<u32> depth;     // PVST depth (root = 0)
+	// per component
+	std::vector<u32> comp_root, comp_nv, comp_nfl, comp_has_tips, comp_nonlaminar;
+	// optional debug / parity outputs
+	std::vector<u32> stack_v;       // class stack: vertex idx per position (components concatenated)
+	std::vector<u32> stack_class;   // dense class id per position
+	std::vector<u32> stack_fwd;
+	u32 dfs_rounds = 0;
+	u32 collisions = 0;
+};
+
+struct DecompOpts { bool want_stack = false; u64 seed = 0x706F7675ull; };
+
+// kernel name tags
+struct K_minport {}; struct K_entries {}; struct K_portcount {}; struct K_csr_fill {}; struct K_rev {};
+struct K_tip {}; struct K_uf_init {}; struct K_uf_union {}; struct K_uf_flatten {}; struct K_start {};
+struct K_claim {}; struct K_entry {}; struct K_first_edge {}; struct K_mark {}; struct K_jump {};
+struct K_segconf {}; struct K_finalize {}; struct K_link {}; struct K_visit {}; struct K_active {};
+struct K_compcount {}; struct K_treeslot {}; struct K_euler {}; struct K_pre {}; struct K_backedge {};
+struct K_bridge {}; struct K_simp {}; struct K_key {}; struct K_stackw {}; struct K_stackpos {};
+struct K_gather {}; struct K_seen {}; struct K_verify {}; struct K_arc {}; struct K_lam {};
+struct K_fn {}; struct K_flub {}; struct K_parent {}; struct K_seq {}; struct K_iota {}; struct K_word {};
+struct K_classid {}; struct K_misc {};
+
+struct MP { i32 a, b; };   // x -> max(x + a, b)
+struct OpMP {
+	PV_HD MP operator()(MP f, MP g) const {   // apply f first, then g
+		const i32 BIG = 1 << 29;
+		i32 a = f.a + g.a; if (a < -BIG) a = -BIG;
+		i32 b1 = f.b + g.a; i32 b = b1 > g.b ? b1 : g.b;
+		return MP{a, b};
+	}
+};
+
+PV_DEV u32 uf_find(u32 *uf, u32 x) {
+	u32 p = ld_volatile(uf + x);
+	while (p != x) {
+		u32 gp = ld_volatile(uf + p);
+		if (gp != p) uf[x] = gp;   // path halving (benign race: always points to an ancestor)
+		x = p; p = gp;
+	}
+	return x;
+}
+PV_DEV void uf_union(u32 *uf, u32 a, u32 b) {
+	while (true) {
+		a = uf_find(uf, a); b = uf_find(uf, b);
+		if (a == b) return;
+		if (a < b) { u32 t = a; a = b; b = t; }     // hook the larger root under the smaller: root = min index
+		if (atomic_cas(uf + a, a, b) == a) return;
+	}
+}
+
+inline void decompose_device(Ctx &c, u32 V, u64 E, const u32 *ep1, const u32 *ep2, const DecompOpts &opt, DecompOut &out) {
+	out = DecompOut();
+	if (V == 0) return;
+	const u32 P = 2 * V;            // ports: 2*v + side (0 = left, 1 = right)
+	const u64 M = 2 * E;            // adjacency entries
+	if (M >= 0xFFFFFFF0ull) throw std::runtime_error("graph too large for 32-bit adjacency slots");
+
+	// ------------------------------------------------------------------ D1: CSR in reference edge order
+	Buf<u32> adjOff(c, P + 1), adjNbr(c, M ? M : 1), adjOwner(c, M ? M : 1), rev(c, M ? M : 1), origDeg(c, P);
+	{
+		Buf<u32> ekey(c, E ? E : 1), eord(c, E ? E : 1);
+		u32 *ekey_ = ekey.p, *eord_ = eord.p;
+		origDeg.zero();
+		u32 *origDeg_ = origDeg.p;
+		parallel_for<K_minport>(c, E, PV_LAMBDA(size_t e) {
+			u32 a = ep1[e], b = ep2[e];
+			ekey_[e] = a < b ? a : b; eord_[e] = (u32)e;
+			atomic_add(origDeg_ + a, 1u); atomic_add(origDeg_ + b, 1u);
+		});
+		radix_sort_pairs(c, ekey.p, eord.p, E, bits_for(P));   // stable: (min port, file order) = renumbered edge idx
+		Buf<u32> entPort(c, M ? M : 1), entIdx(c, M ? M : 1), entNbr(c, M ? M : 1);
+		u32 *entPort_ = entPort.p, *entIdx_ = entIdx.p, *entNbr_ = entNbr.p;
+		parallel_for<K_entries>(c, E, PV_LAMBDA(size_t k) {
+			u32 e = eord_[k]; u32 a = ep1[e], b = ep2[e];
+			if ((a >> 1) == (b >> 1)) { a = a & ~1u; b = a | 1u; }   // any self-loop becomes left--right (bidirected.cpp:66-77,526-531)
+			entPort_[2 * k] = a; entNbr_[2 * k] = b; entIdx_[2 * k] = (u32)(2 * k);
+			entPort_[2 * k + 1] = b; entNbr_[2 * k + 1] = a; entIdx_[2 * k + 1] = (u32)(2 * k + 1);
+		});
+		radix_sort_pairs(c, entPort.p, entIdx.p, M, bits_for(P));
+		Buf<u32> slotOf(c, M ? M : 1), cnt(c, P + 1);
+		cnt.zero();
+		u32 *slotOf_ = slotOf.p, *cnt_ = cnt.p, *adjNbr_ = adjNbr.p, *adjOwner_ = adjOwner.p, *rev_ = rev.p;
+		parallel_for<K_csr_fill>(c, M, PV_LAMBDA(size_t s) {
+			u32 j = entIdx_[s]; u32 p = entPort_[s];
+			adjNbr_[s] = entNbr_[j]; adjOwner_[s] = p; slotOf_[j] = (u32)s;
+			atomic_add(cnt_ + p, 1u);
+		});
+		exclusive_scan(c, cnt.p, adjOff.p, (size_t)P + 1, OpAddU32(), 0u);
+		parallel_for<K_rev>(c, M, PV_LAMBDA(size_t s) { rev_[s] = slotOf_[entIdx_[s] ^ 1u]; });
+	}
+	const u32 *adjOff_ = adjOff.p, *adjNbr_ = adjNbr.p, *adjOwner_ = adjOwner.p, *rev_ = rev.p, *origDeg_ = origDeg.p;
+
+	// ------------------------------------------------------------------ D2: exact DFS tree by rounds
+	Buf<u32> visited(c, V), uf(c, V), comp(c, V), gcomp(c, V), entrySide(c, V);
+	Buf<u32> parent(c, P), pslot(c, P), depth(c, P), F(c, P), Fslot(c, P), J(c, P), J2(c, P), rnk(c, P);
+	Buf<u64> claim(c, V);
+	Buf<u32> trunc(c, V), entDepth(c, V), tipPort(c, V), compStart(c, V), flag(c, 4);
+	visited.zero(); parent.fill_ff(); pslot.fill_ff(); depth.zero();
+	u32 *visited_ = visited.p, *uf_ = uf.p, *comp_ = comp.p, *gcomp_ = gcomp.p, *entrySide_ = entrySide.p;
+	u32 *parent_ = parent.p, *pslot_ = pslot.p, *depth_ = depth.p, *F_ = F.p, *Fslot_ = Fslot.p, *rnk_ = rnk.p;
+	u64 *claim_ = claim.p;
+	u32 *trunc_ = trunc.p, *entDepth_ = entDepth.p, *tipPort_ = tipPort.p, *compStart_ = compStart.p, *flag_ = flag.p;
+
+	// tips of the WHOLE graph (from_gfa.cpp:262-277), decided on the original (un-rewritten) endpoints
+	parallel_for<K_tip>(c, V, PV_LAMBDA(size_t v) {
+		u32 dl = origDeg_[2 * v], dr = origDeg_[2 * v + 1];
+		tipPort_[v] = dl == 0 ? (u32)(2 * v) : (dr == 0 ? (u32)(2 * v + 1) : NONE);
+	});
+
+	Buf<u32> active(c, V);
+	u32 nActive = V;
+	{ u32 *a = active.p; parallel_for<K_iota>(c, V, PV_LAMBDA(size_t i) { a[i] = (u32)i; }); }
+
+	u32 round = 0;
+	while (nActive > 0) {
+		const u32 *act = active.p;
+		const u32 nA = nActive;
+#ifdef PV_EMU
+		if (getenv("PV_DEBUG")) { fprintf(stderr, "[dfs] round %u active %u:", round, nA); for (u32 i = 0; i < nA && i < 32; i++) fprintf(stderr, " %u", act[i]); fprintf(stderr, "\n"); }
+#endif
+		// (a,b,c) connected components of the still-unvisited part (segment granularity)
+		parallel_for<K_uf_init>(c, nA, PV_LAMBDA(size_t i) { u32 v = act[i]; uf_[v] = v; claim_[v] = 0; trunc_[v] = NONE; });
+		parallel_for<K_uf_union>(c, (size_t)nA * 2, PV_LAMBDA(size_t i) {
+			u32 v = act[i >> 1]; u32 p = 2 * v + (u32)(i & 1);
+			for (u32 s = adjOff_[p], e = adjOff_[p + 1]; s < e; s++) {
+				u32 w = adjNbr_[s] >> 1;
+				if (w != v && !visited_[w]) uf_union(uf_, v, w);
+			}
+		});
+		parallel_for<K_uf_flatten>(c, nA, PV_LAMBDA(size_t i) { u32 v = act[i]; comp_[v] = uf_find(uf_, v); });
+		if (round == 0) {
+			c.d2d(gcomp.p, comp.p, (size_t)V * 4);
+			// start port: smallest tip (v_id, end) of the component (types.cpp:60-68), else (lowest vertex, left)
+			parallel_for<K_start>(c, V, PV_LAMBDA(size_t v) { compStart_[v] = NONE; rnk_[2 * v] = NONE; rnk_[2 * v + 1] = NONE; });
+			parallel_for<K_start>(c, V, PV_LAMBDA(size_t v) { u32 t = tipPort_[v]; if (t != NONE) atomic_min(compStart_ + comp_[v], t); });
+			parallel_for<K_entry>(c, V, PV_LAMBDA(size_t v) {
+				if (comp_[v] != v) return;
+				u32 q0 = compStart_[v];
+				if (q0 == NONE) q0 = (u32)(2 * v);
+				compStart_[v] = q0;
+				rnk_[q0] = 0; entDepth_[v] = 1;          // virtual root has depth 0
+				parent_[q0] = NONE; pslot_[q0] = NONE;   // parent = the component's virtual root
+			});
+		} else {
+			// (d) every unvisited component is claimed by its deepest visited neighbour, lowest edge first
+			parallel_for<K_claim>(c, (size_t)nA * 2, PV_LAMBDA(size_t i) {
+				u32 v = act[i >> 1]; u32 q = 2 * v + (u32)(i & 1);
+				rnk_[q] = NONE;
+				u64 best = 0;
+				for (u32 s = adjOff_[q], e = adjOff_[q + 1]; s < e; s++) {
+					u32 p = adjNbr_[s];
+					if (!visited_[p >> 1]) continue;
+					u64 key = ((u64)depth_[p] << 32) | (u64)(0xFFFFFFFFu - rev_[s]);
+					if (key > best) best = key;
+				}
+				if (best) atomic_max(claim_ + comp_[v], best);
+			});
+			parallel_for<K_entry>(c, nA, PV_LAMBDA(size_t i) {
+				u32 v = act[i];
+				if (comp_[v] != v) return;
+				u64 k = claim_[v];
+				u32 s = 0xFFFFFFFFu - (u32)(k & 0xFFFFFFFFu);
+				u32 p = adjOwner_[s], q0 = adjNbr_[s];
+				rnk_[q0] = 0; entDepth_[v] = (u32)(k >> 32) + 1;
+				parent_[q0] = p; pslot_[q0] = s;
+			});
+		}
+		// (f) "first unvisited edge" functional graph on entry ports
+		parallel_for<K_first_edge>(c, (size_t)nA * 2, PV_LAMBDA(size_t i) {
+			u32 v = act[i >> 1]; u32 x = 2 * v + (u32)(i & 1); u32 xb = x ^ 1u;
+			u32 f = NONE, fs = NONE;
+			for (u32 s = adjOff_[xb], e = adjOff_[xb + 1]; s < e; s++) {
+				u32 y = adjNbr_[s]; u32 w = y >> 1;
+				if (w != v && !visited_[w]) { f = y; fs = s; break; }
+			}
+			F_[x] = f; Fslot_[x] = fs;
+		});
+		// (g) pointer-doubling path marking from every entry
+		{
+			c.d2d(J.p, F.p, (size_t)P * 4);
+			u32 *Ja = J.p, *Jb = J2.p;
+			int maxIt = bits_for((u64)nA * 2) + 1;
+			for (int it = 0; it < maxIt; it++) {
+				c.memset0(flag.p, 4);
+				const u32 lim = 1u << it;
+				parallel_for<K_mark>(c, (size_t)nA * 2, PV_LAMBDA(size_t i) {
+					u32 v = act[i >> 1]; u32 x = 2 * v + (u32)(i & 1);
+					u32 r = rnk_[x];
+					if (r >= lim) return;                       // NONE or marked in this very iteration
+					u32 y = Ja[x];
+					if (y == NONE) return;
+					u32 rho = r + lim;
+					u32 old = atomic_min(rnk_ + y, rho);
+					if (old != NONE && old != rho) atomic_min(trunc_ + comp_[v], old > rho ? old : rho);
+					flag_[0] = 1;
+				});
+				u32 any = flag.read(0);
+				if (!any) break;
+				parallel_for<K_jump>(c, (size_t)nA * 2, PV_LAMBDA(size_t i) {
+					u32 v = act[i >> 1]; u32 x = 2 * v + (u32)(i & 1);
+					u32 y = Ja[x];
+					Jb[x] = y == NONE ? NONE : Ja[y];
+				});
+				std::swap(Ja, Jb);
+			}
+		}
+		// (h) truncate at the first self-intersection, then fix parents / depths of the stripped paths
+		parallel_for<K_segconf>(c, nA, PV_LAMBDA(size_t i) {
+			u32 v = act[i]; u32 r0 = rnk_[2 * v], r1 = rnk_[2 * v + 1];
+			if (r0 != NONE && r1 != NONE) atomic_min(trunc_ + comp_[v], r0 > r1 ? r0 : r1);
+		});
+		parallel_for<K_finalize>(c, (size_t)nA * 2, PV_LAMBDA(size_t i) {
+			u32 v = act[i >> 1]; u32 x = 2 * v + (u32)(i & 1);
+			u32 r = rnk_[x]; u32 root = comp_[v];
+			if (r == NONE || r >= trunc_[root]) return;
+			u32 d = entDepth_[root] + 2 * r;
+			entrySide_[v] = x & 1u;
+			depth_[x] = d; depth_[x ^ 1u] = d + 1;
+			parent_[x ^ 1u] = x; pslot_[x ^ 1u] = NONE;
+			u32 y = F_[x];
+			if (y != NONE && rnk_[y] == r + 1 && r + 1 < trunc_[root]) { parent_[y] = x ^ 1u; pslot_[y] = Fslot_[x]; }
+		});
+		Buf<u32> still(c, nA);
+		u32 *still_ = still.p;
+		parallel_for<K_visit>(c, nA, PV_LAMBDA(size_t i) {
+			u32 v = act[i]; u32 root = comp_[v]; u32 t = trunc_[root];
+			u32 r0 = rnk_[2 * v], r1 = rnk_[2 * v + 1];
+			bool vis = (r0 != NONE && r0 < t) || (r1 != NONE && r1 < t);
+			still_[i] = vis ? 0u : 1u;
+		});
+		// visited[] is written only after every kernel of this round that reads it has finished
+		parallel_for<K_visit>(c, nA, PV_LAMBDA(size_t i) { if (!still_[i]) visited_[act[i]] = 1; });
+		Buf<u32> idx;
+		u32 nNext = compact_flags(c, still.p, nA, idx);
+		Buf<u32> nextActive(c, nNext ? nNext : 1);
+		{ u32 *na = nextActive.p; const u32 *ix = idx.p; parallel_for<K_active>(c, nNext, PV_LAMBDA(size_t i) { na[i] = act[ix[i]]; }); }
+		active = std::move(nextActive);
+		if (nNext >= nActive) throw std::runtime_error("decompose: DFS round made no progress");
+		nActive = nNext;
+		round++;
+	}
+	out.dfs_rounds = round;
+
+	// ------------------------------------------------------------------ components (dense indices)
+	Buf<u32> isRoot(c, V), compIdxOfRoot(c, V + 1), nvOfRoot(c, V);
+	nvOfRoot.zero();
+	u32 *isRoot_ = isRoot.p, *compIdxOfRoot_ = compIdxOfRoot.p, *nvOfRoot_ = nvOfRoot.p;
+	parallel_for<K_compcount>(c, V, PV_LAMBDA(size_t v) { isRoot_[v] = gcomp_[v] == v ? 1u : 0u; atomic_add(nvOfRoot_ + gcomp_[v], 1u); });
+	Buf<u32> roots;
+	u32 nComp = compact_flags(c, isRoot.p, V, roots);
+	exclusive_scan(c, isRoot.p, compIdxOfRoot.p, V, OpAddU32(), 0u);
+	// per component: nv, node base (2*nv+1 nodes incl. virtual root), segment base
+	Buf<u32> cNv(c, nComp + 1), cNodeBase(c, nComp + 1), cSegBase(c, nComp + 1), cNodes(c, nComp + 1), cHasTips(c, nComp);
+	u32 *cNv_ = cNv.p, *cNodeBase_ = cNodeBase.p, *cSegBase_ = cSegBase.p, *cNodes_ = cNodes.p, *cHasTips_ = cHasTips.p;
+	const u32 *roots_ = roots.p;
+	cHasTips.zero();
+	parallel_for<K_compcount>(c, (size_t)nComp + 1, PV_LAMBDA(size_t k) {
+		u32 nv = k < nComp ? nvOfRoot_[roots_[k]] : 0u;
+		cNv_[k] = nv; cNodes_[k] = k < nComp ? 2 * nv + 1 : 0u;
+	});
+	parallel_for<K_compcount>(c, V, PV_LAMBDA(size_t v) { if (tipPort_[v] != NONE) cHasTips_[compIdxOfRoot_[gcomp_[v]]] = 1; });
+	exclusive_scan(c, cNodes.p, cNodeBase.p, (size_t)nComp + 1, OpAddU32(), 0u);
+	exclusive_scan(c, cNv.p, cSegBase.p, (size_t)nComp + 1, OpAddU32(), 0u);
+	const u32 N = P + nComp;   // nodes in global preorder space
+
+	// ------------------------------------------------------------------ D3: Euler tour + list ranking
+	Buf<u32> treeSlot(c, M ? M : 1);
+	treeSlot.fill_ff();
+	u32 *treeSlot_ = treeSlot.p;
+	parallel_for<K_treeslot>(c, P, PV_LAMBDA(size_t y) { u32 s = pslot_[y]; if (s != NONE) treeSlot_[s] = (u32)y; });
+	Buf<u32> enext(c, (size_t)2 * P), ew(c, (size_t)2 * P), esuf(c, (size_t)2 * P);
+	u32 *enext_ = enext.p, *ew_ = ew.p;
+	parallel_for<K_euler>(c, P, PV_LAMBDA(size_t yy) {
+		u32 y = (u32)yy; u32 v = y >> 1;
+		bool isEntry = (y & 1u) == entrySide_[v];
+		auto firstGray = [&](u32 p, u32 from) -> u32 {
+			for (u32 s = from, e = adjOff_[p + 1]; s < e; s++) { u32 ch = treeSlot_[s]; if (ch != NONE) return ch; }
+			return NONE;
+		};
+		// down(y) = 2y, up(y) = 2y+1
+		u32 fc = isEntry ? (y ^ 1u) : firstGray(y, adjOff_[y]);
+		enext_[2 * y] = fc != NONE ? 2 * fc : 2 * y + 1;
+		u32 par = parent_[y];
+		u32 ns;
+		if (!isEntry) ns = firstGray(par, adjOff_[par]);            // black child: siblings are the entry port's gray children
+		else ns = par == NONE ? NONE : firstGray(par, pslot_[y] + 1);
+		enext_[2 * y + 1] = ns != NONE ? 2 * ns : (par == NONE ? NONE : 2 * par + 1);
+		ew_[2 * y] = 1; ew_[2 * y + 1] = 0;
+	});
+	list_rank_suffix(c, enext.p, ew.p, esuf.p, (size_t)2 * P);
+	Buf<u32> pre(c, P), sz(c, P), pre2node(c, N);
+	u32 *pre_ = pre.p, *sz_ = sz.p, *pre2node_ = pre2node.p;
+	const u32 *esuf_ = esuf.p;
+	parallel_for<K_pre>(c, P, PV_LAMBDA(size_t y) {
+		u32 k = compIdxOfRoot_[gcomp_[y >> 1]];
+		u32 T = 2 * cNv_[k];
+		u32 lp = T - esuf_[2 * y];                   // local preorder, virtual root = 0
+		u32 g = cNodeBase_[k] + lp;
+		pre_[y] = g; sz_[y] = esuf_[2 * y] - esuf_[2 * y + 1] + 1;
+		pre2node_[g] = (u32)y;
+	});
+	parallel_for<K_pre>(c, nComp, PV_LAMBDA(size_t k) { pre2node_[cNodeBase_[k]] = P + (u32)k; });
+
+	// ------------------------------------------------------------------ D4: back edges, bridges, labels, keys
+	Buf<u64> X(c, (size_t)2 * (N + 1));      // 128-bit label accumulators, (lo, hi) interleaved
+	Buf<i32> cd(c, N + 1);
+	Buf<u32> minT(c, N);
+	X.zero(); cd.zero(); minT.fill_ff();
+	u64 *X_ = X.p; i32 *cd_ = cd.p; u32 *minT_ = minT.p;
+	const u64 seed = opt.seed;
+	parallel_for<K_backedge>(c, P, PV_LAMBDA(size_t pp) {
+		u32 p = (u32)pp; u32 v = p >> 1;
+		u32 k = compIdxOfRoot_[gcomp_[v]];
+		u32 myPre = pre_[p];
+		u32 s0 = adjOff_[p], s1 = adjOff_[p + 1];
+		bool isExit = (p & 1u) != entrySide_[v];
+		bool loopDone = false;
+		auto emit = [&](u32 tgtPre, u64 id) {
+			u64 lo = splitmix64(seed ^ (id * 2)), hi = splitmix64((seed * 0x9E3779B97F4A7C15ull) ^ (id * 2 + 1));
+			atomic_xor(X_ + 2 * (size_t)myPre, lo); atomic_xor(X_ + 2 * (size_t)myPre + 1, hi);
+			atomic_xor(X_ + 2 * (size_t)tgtPre, lo); atomic_xor(X_ + 2 * (size_t)tgtPre + 1, hi);
+			atomic_add((u32 *)cd_ + myPre, 1u); atomic_add((u32 *)cd_ + tgtPre, 0xFFFFFFFFu);
+			atomic_min(minT_ + myPre, tgtPre);
+		};
+		if (s0 == s1) {   // tip side: back edge to the dummy root unless the tree already links them (spanning_tree.cpp:431-438)
+			if (parent_[p] != NONE) emit(cNodeBase_[k], (u64)M + p);
+			return;
+		}
+		for (u32 s = s0; s < s1; s++) {
+			u32 q = adjNbr_[s];
+			if (q == (p ^ 1u)) {   // self-loop: one extra back edge per segment, from the child side (spanning_tree.cpp:387-395)
+				if (isExit && !loopDone) { loopDone = true; emit(pre_[q], s); }
+				continue;
+			}
+			u32 qPre = pre_[q];
+			if (qPre > myPre) continue;            // recorded from the deeper endpoint
+			if (parent_[p] == q) continue;          // the tree edge itself, or parallel to it
+			bool dup = false;
+			for (u32 t = s0; t < s; t++) if (adjNbr_[t] == q) { dup = true; break; }   // parallel edges collapse (spanning_tree.cpp:379-386)
+			if (!dup) emit(qPre, s);
+		}
+	});
+	// bridges -> simplifying back edges (flubbles.cpp:621-643): v gets one iff no bracket leaves subtree(v)
+	// upwards and no vertex below v got one
+	Rmq rmq1;
+	rmq_build(c, rmq1, minT.p, N);
+	Buf<u32> bridge(c, N + 1), bsum(c, N + 1);
+	u32 *bridge_ = bridge.p, *bsum_ = bsum.p;
+	{
+		RmqView rv = rmq1.view();
+		parallel_for<K_bridge>(c, (size_t)N + 1, PV_LAMBDA(size_t g) {
+			u32 b = 0;
+			if (g < N) {
+				u32 node = pre2node_[g];
+				if (node < P) {
+					u32 k = compIdxOfRoot_[gcomp_[node >> 1]];
+					bool refRoot = !cHasTips_[k] && g == cNodeBase_[k] + 1;   // without tips the start port is the tree root
+					if (!refRoot) { u32 hi = rv.query((u32)g, (u32)g + sz_[node] - 1); b = hi >= (u32)g ? 1u : 0u; }
+				}
+			}
+			bridge_[g] = b;
+		});
+	}
+	exclusive_scan(c, bridge.p, bsum.p, (size_t)N + 1, OpAddU32(), 0u);
+	parallel_for<K_simp>(c, N, PV_LAMBDA(size_t g) {
+		if (!bridge_[g]) return;
+		u32 node = pre2node_[g];
+		u32 inSub = bsum_[g + sz_[node]] - bsum_[g];
+		if (inSub != 1) return;
+		u32 k = compIdxOfRoot_[gcomp_[node >> 1]];
+		u32 tgt = cHasTips_[k] ? cNodeBase_[k] : cNodeBase_[k] + 1;
+		u64 id = (u64)M + P + node;
+		u64 lo = splitmix64(seed ^ (id * 2)), hi = splitmix64((seed * 0x9E3779B97F4A7C15ull) ^ (id * 2 + 1));
+		atomic_xor(X_ + 2 * g, lo); atomic_xor(X_ + 2 * g + 1, hi);
+		atomic_xor(X_ + 2 * (size_t)tgt, lo); atomic_xor(X_ + 2 * (size_t)tgt + 1, hi);
+		atomic_add((u32 *)cd_ + g, 1u); atomic_add((u32 *)cd_ + tgt, 0xFFFFFFFFu);
+		atomic_min(minT_ + g, tgt);
+	});
+	Rmq rmq2;
+	rmq_build(c, rmq2, minT.p, N);
+	Buf<u128> PX(c, N + 1);
+	Buf<i32> PC(c, N + 1);
+	exclusive_scan(c, (const u128 *)X.p, PX.p, (size_t)N + 1, OpXor128(), u128{0, 0});
+	exclusive_scan(c, cd.p, PC.p, (size_t)N + 1, OpAddI32(), 0);
+	const u128 *PX_ = PX.p; const i32 *PC_ = PC.p;
+
+	// ------------------------------------------------------------------ D5: class stack positions
+	// pos(seg) = #entry ports before + root-path sum of w + G(entry)   (see DESIGN.md "class stack without a second traversal")
+	Buf<u32> isEnt(c, N + 1), S(c, N + 1);
+	Buf<i32> Dw(c, N + 1), PW(c, N + 1);
+	Dw.zero();
+	u32 *isEnt_ = isEnt.p, *S_ = S.p; i32 *Dw_ = Dw.p, *PW_ = PW.p;
+	parallel_for<K_stackw>(c, (size_t)N + 1, PV_LAMBDA(size_t g) {
+		u32 e = 0;
+		if (g < N) { u32 node = pre2node_[g]; if (node < P && (node & 1u) == entrySide_[node >> 1]) e = 1; }
+		isEnt_[g] = e;
+	});
+	exclusive_scan(c, isEnt.p, S.p, (size_t)N + 1, OpAddU32(), 0u);
+	parallel_for<K_stackw>(c, P, PV_LAMBDA(size_t yy) {
+		u32 y = (u32)yy; u32 par = parent_[y];
+		if (par == NONE) return;
+		u32 pv_ = par >> 1;
+		bool parIsEntry = (par & 1u) == entrySide_[pv_];
+		if (!parIsEntry) return;
+		u32 a = par, ab = par ^ 1u;
+		u32 ga = pre_[a], gab = pre_[ab];
+		i32 nsegA = (i32)(S_[ga + sz_[a]] - S_[ga]);
+		i32 nsegAb = (i32)(S_[gab + sz_[ab]] - S_[gab]);
+		i32 w = (y == ab) ? (nsegA - 1 - nsegAb) : -(1 + nsegAb);
+		u32 gy = pre_[y];
+		atomic_add((u32 *)Dw_ + gy, (u32)w); atomic_add((u32 *)Dw_ + gy + sz_[y], (u32)(-w));
+	});
+	inclusive_scan(c, Dw.p, PW.p, (size_t)N + 1, OpAddI32(), 0);
+	const u32 nS = V;   // one stack entry per segment
+	Buf<u32> stV(c, nS), stPre(c, nS), stCnt(c, nS);
+	Buf<u128> stKey(c, nS);
+	u32 *stV_ = stV.p, *stPre_ = stPre.p, *stCnt_ = stCnt.p; u128 *stKey_ = stKey.p;
+	parallel_for<K_stackpos>(c, V, PV_LAMBDA(size_t v) {
+		u32 u = (u32)(2 * v) + entrySide_[v], cx = u ^ 1u;
+		u32 k = compIdxOfRoot_[gcomp_[v]];
+		u32 gu = pre_[u], gc = pre_[cx];
+		i32 segsBefore = (i32)(S_[gu] - S_[cNodeBase_[k]]);
+		i32 nsegU = (i32)(S_[gu + sz_[u]] - S_[gu]);
+		i32 nsegC = (i32)(S_[gc + sz_[cx]] - S_[gc]);
+		i32 G = nsegU - 1 - nsegC;
+		i32 pos = segsBefore + PW_[gu] + G;
+		u32 gp = cSegBase_[k] + (u32)pos;
+		stV_[gp] = (u32)v; stPre_[gp] = gc;
+		u128 a = PX_[gc + sz_[cx]], b = PX_[gc];
+		stKey_[gp] = u128{a.lo ^ b.lo, a.hi ^ b.hi};
+		stCnt_[gp] = (u32)(PC_[gc + sz_[cx]] - PC_[gc]);
+	});
+	// group equal keys: LSD radix sort over the four 32-bit words of the key, stable in stack position
+	Buf<u32> ord(c, nS), wkey(c, nS);
+	u32 *ord_ = ord.p, *wkey_ = wkey.p;
+	parallel_for<K_iota>(c, nS, PV_LAMBDA(size_t i) { ord_[i] = (u32)i; });
+	for (int w = 0; w < 4; w++) {
+		parallel_for<K_word>(c, nS, PV_LAMBDA(size_t i) {
+			u128 kk = stKey_[ord_[i]];
+			u64 h = w < 2 ? kk.lo : kk.hi;
+			wkey_[i] = (u32)(h >> ((w & 1) * 32));
+		});
+		radix_sort_pairs(c, wkey.p, ord.p, nS, 32);
+	}
+	Buf<u32> nxt(c, nS), prv(c, nS), newGrp(c, nS + 1), grpId(c, nS + 1), classOf(c, nS);
+	u32 *nxt_ = nxt.p, *prv_ = prv.p, *newGrp_ = newGrp.p, *grpId_ = grpId.p, *classOf_ = classOf.p;
+	parallel_for<K_seen>(c, nS, PV_LAMBDA(size_t i) {
+		u32 me = ord_[i]; u128 km = stKey_[me];
+		bool sameNext = false, samePrev = false;
+		if (i + 1 < nS) { u128 kn = stKey_[ord_[i + 1]]; sameNext = kn.lo == km.lo && kn.hi == km.hi; }
+		if (i > 0) { u128 kp = stKey_[ord_[i - 1]]; samePrev = kp.lo == km.lo && kp.hi == km.hi; }
+		nxt_[me] = sameNext ? ord_[i + 1] : me;
+		prv_[me] = samePrev ? ord_[i - 1] : NONE;
+		newGrp_[i] = samePrev ? 0u : 1u;
+	});
+	inclusive_scan(c, newGrp.p, grpId.p, nS, OpAddU32(), 0u);
+	parallel_for<K_classid>(c, nS, PV_LAMBDA(size_t i) { classOf_[ord_[i]] = grpId_[i] - 1; });
+
+	// exact verification of every merged pair (bracket sets equal <=> same count, ancestor chain, and no
+	// bracket from subtree(v1) \ subtree(v2) leaves subtree(v1))
+	c.memset0(flag.p, 16);
+	{
+		RmqView rv = rmq2.view();
+		parallel_for<K_verify>(c, nS, PV_LAMBDA(size_t i) {
+			u32 j = nxt_[i];
+			if (j == (u32)i) return;
+			u32 c1 = stPre_[i], c2 = stPre_[j];
+			u32 z1 = sz_[pre2node_[c1]], z2 = sz_[pre2node_[c2]];
+			bool ok = c1 < c2 && c2 + z2 <= c1 + z1 && stCnt_[i] == stCnt_[j];
+			if (ok && c2 > c1) ok = rv.query(c1, c2 - 1) >= c1;
+			if (ok && c2 + z2 < c1 + z1) ok = rv.query(c2 + z2, c1 + z1 - 1) >= c1;
+			if (!ok) atomic_add(flag_ + 1, 1u);
+		});
+	}
+
+	// ------------------------------------------------------------------ D6: flubbles + PVST parents
+	Buf<u32> segComp(c, nS), notNext(c, nS), lamBad(c, nComp ? nComp : 1);
+	u32 *segComp_ = segComp.p, *notNext_ = notNext.p, *lamBad_ = lamBad.p;
+	lamBad.zero();
+	parallel_for<K_arc>(c, nS, PV_LAMBDA(size_t i) { segComp_[i] = compIdxOfRoot_[gcomp_[stV_[i]]]; notNext_[i] = ~nxt_[i]; });
+	Rmq rmq3;
+	rmq_build(c, rmq3, notNext.p, nS);
+	{
+		RmqView rv = rmq3.view();
+		parallel_for<K_lam>(c, nS, PV_LAMBDA(size_t i) {
+			u32 b = nxt_[i];
+			if (b <= (u32)i + 1) return;
+			u32 mx = ~rv.query((u32)i + 1, b - 1);
+			if (mx > b) lamBad_[segComp_[i]] = 1;
+		});
+	}
+	Buf<u32> open(c, nS + 1), flIdx(c, nS + 1);
+	Buf<MP> fn(c, nS), fnS(c, nS);
+	u32 *open_ = open.p, *flIdx_ = flIdx.p; MP *fn_ = fn.p, *fnS_ = fnS.p;
+	parallel_for<K_fn>(c, (size_t)nS + 1, PV_LAMBDA(size_t i) {
+		if (i >= nS) { open_[i] = 0; return; }
+		u32 o = nxt_[i] > (u32)i + 1 ? 1u : 0u;
+		u32 u = prv_[i] != NONE ? 1u : 0u;
+		open_[i] = o;
+		bool first = i == 0 || segComp_[i - 1] != segComp_[i];
+		fn_[i] = MP{first ? -(1 << 29) : (i32)o - (i32)u, (i32)o};
+	});
+	exclusive_scan(c, open.p, flIdx.p, (size_t)nS + 1, OpAddU32(), 0u);
+	inclusive_scan(c, fn.p, fnS.p, nS, OpMP(), MP{0, -(1 << 29)});
+	u32 nFl = flIdx.read(nS);
+	Buf<u32> fA(c, nFl ? nFl : 1), fZ(c, nFl ? nFl : 1), fOr(c, nFl ? nFl : 1), fDepth(c, nFl ? nFl : 1), fPar(c, nFl ? nFl : 1), fComp(c, nFl ? nFl : 1);
+	Buf<u32> cFlBase(c, nComp + 1);
+	u32 *fA_ = fA.p, *fZ_ = fZ.p, *fOr_ = fOr.p, *fDepth_ = fDepth.p, *fPar_ = fPar.p, *fComp_ = fComp.p, *cFlBase_ = cFlBase.p;
+	parallel_for<K_flub>(c, (size_t)nComp + 1, PV_LAMBDA(size_t k) { cFlBase_[k] = flIdx_[cSegBase_[k]]; });
+	parallel_for<K_flub>(c, nS, PV_LAMBDA(size_t i) {
+		if (!open_[i]) return;
+		u32 f = flIdx_[i]; u32 j = nxt_[i];
+		u32 va = stV_[i], vz = stV_[j];
+		u32 oa = entrySide_[va] == 0 ? 1u : 0u, oz = entrySide_[vz] == 0 ? 1u : 0u;   // forward iff the child side is the right one
+		if (!oa && !oz) { u32 t = va; va = vz; vz = t; oa = 1; oz = 1; }             // normalize_endpoints (flubbles.cpp:233-243)
+		fA_[f] = va; fZ_[f] = vz; fOr_[f] = oa | (oz << 1);
+		MP m = fnS_[i];
+		fDepth_[f] = (u32)(m.a > m.b ? m.a : m.b);
+		fComp_[f] = segComp_[i];
+	});
+	Rmq rmq4;
+	if (nFl) {
+		rmq_build(c, rmq4, fDepth.p, nFl);
+		RmqView rv = rmq4.view();
+		parallel_for<K_parent>(c, nFl, PV_LAMBDA(size_t f) {
+			u32 d = fDepth_[f]; u32 k = fComp_[f];
+			if (lamBad_[k]) return;
+			u32 par = 0;
+			if (d > 1 && f > 0) {
+				u32 j = rv.prev_smaller((u32)f - 1, d);
+				if (j != NONE && j >= cFlBase_[k]) par = j - cFlBase_[k] + 1;
+			}
+			fPar_[f] = par;
+		});
+	}
+	// non-laminar components: replay the reference's stack machine, one thread per component
+	Buf<u32> inS(c, nS), stk(c, nS);
+	inS.zero();
+	u32 *inS_ = inS.p, *stk_ = stk.p;
+	parallel_for<K_seq>(c, nComp, PV_LAMBDA(size_t k) {
+		if (!lamBad_[k]) return;
+		u32 b = cSegBase_[k], e = cSegBase_[k + 1], fb = cFlBase_[k];
+		u32 top = b;           // stack occupies stk_[b .. top)
+		u32 prt = 0;           // local PVST idx
+		for (u32 i = b; i < e; i++) {
+			u32 cl = classOf_[i];
+			if (inS_[cl]) {
+				while (top > b) { u32 x = stk_[--top]; inS_[x] = 0; if (x == cl) break; }
+				if (prt != 0) prt = fPar_[fb + prt - 1];
+			}
+			if (open_[i]) {
+				u32 f = flIdx_[i];
+				fPar_[f] = prt;
+				fDepth_[f] = prt == 0 ? 1u : fDepth_[fb + prt - 1] + 1;
+				prt = f - fb + 1;
+			}
+			stk_[top++] = cl; inS_[cl] = 1;
+		}
+	});
+
+	// ------------------------------------------------------------------ results to the host
+	u32 fl[4];
+	c.d2h(fl, flag.p, 16);
+	out.collisions = fl[1];
+	out.a_v = fA.to_host(); out.z_v = fZ.to_host(); out.parent = fPar.to_host(); out.depth = fDepth.to_host(); out.comp = fComp.to_host();
+	out.a_v.resize(nFl); out.z_v.resize(nFl); out.parent.resize(nFl); out.depth.resize(nFl); out.comp.resize(nFl);
+	std::vector<u32> orv = fOr.to_host();
+	out.a_fwd.resize(nFl); out.z_fwd.resize(nFl);
+	for (u32 i = 0; i < nFl; i++) { out.a_fwd[i] = orv[i] & 1u; out.z_fwd[i] = (orv[i] >> 1) & 1u; }
+	out.comp_root = roots.to_host(); out.comp_root.resize(nComp);
+	out.comp_nv = cNv.to_host(); out.comp_nv.resize(nComp);
+	out.comp_has_tips = cHasTips.to_host();
+	out.comp_nonlaminar = lamBad.to_host(); out.comp_nonlaminar.resize(nComp);
+	std::vector<u32> flb = cFlBase.to_host();
+	out.comp_nfl.resize(nComp);
+	for (u32 k = 0; k < nComp; k++) out.comp_nfl[k] = flb[k + 1] - flb[k];
+	if (opt.want_stack) {
+		out.stack_v = stV.to_host(); out.stack_class = classOf.to_host();
+		std::vector<u32> es = entrySide.to_host();
+		out.stack_fwd.resize(nS);
+		for (u32 i = 0; i < nS; i++) out.stack_fwd[i] = es[out.stack_v[i]] == 0;
+	}
+	c.sync();
+}
+
+} // namespace pv

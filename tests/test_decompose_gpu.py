@@ -1,0 +1,71 @@
+"""GPU parity tests proper: the sm_100a pipeline through the C ABI against the CPU oracle (bit-exact:
+integer / index work), the committed golden PVSTs of the compiled reference, and size-independent
+properties at BASELINE.json's cfg2 size."""
+import numpy as np
+import pytest
+
+import helpers
+import oracle_binding as ob
+from povu_b200 import api, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _check(pv, g):
+    ep1, ep2 = api.edge_ports(g)
+    f = pv.decompose(len(g["ids"]), ep1, ep2)
+    assert ob.flubble_rows(f, g["ids"]) == ob.oracle_decompose(g)
+    return f
+
+
+def test_gpu_random_families(gpu):
+    for s in range(60):
+        _check(gpu, synth.nested_bubbles(s, shuffle_links=(s % 2 == 1)))
+    for s in range(120):
+        _check(gpu, synth.wild(s, V=3 + s % 20, E=3 + s % 33, p_loop=0.1, n_comp=1 + s % 3))
+    for s in range(10):
+        _check(gpu, synth.wild(1000 + s, V=200 + s * 10, E=300 + s * 17, p_loop=0.03, n_comp=1 + s % 4))
+        _check(gpu, synth.nested_bubbles(500 + s, n_top=40, max_depth=5, shuffle_links=(s % 2 == 1)))
+
+
+def test_gpu_edge_cases(gpu):
+    one = synth.make_graph([5], ["A"], np.zeros((0, 4)), [])
+    assert gpu.decompose(1, *api.edge_ports(one)).n == 0
+    two = synth.make_graph([1, 2], ["A", "C"], [synth.link(0, "+", 1, "+")], [])
+    assert gpu.decompose(2, *api.edge_ports(two)).n == 0          # < 3 vertices: no PVST (decompose.cpp:135-142)
+    loop = synth.make_graph([1, 2, 3], ["A", "C", "G"], [synth.link(0, "+", 1, "+"), synth.link(1, "+", 1, "+"), synth.link(1, "+", 2, "+")], [])
+    _check(gpu, loop)
+    circ = synth.make_graph([1, 2, 3, 4], ["A"] * 4, [synth.link(0, "+", 1, "+"), synth.link(1, "+", 2, "+"), synth.link(2, "+", 3, "+"), synth.link(3, "+", 0, "+"), synth.link(0, "+", 2, "+")], [])
+    _check(gpu, circ)                                                 # circular component: no tips, no dummy root
+
+
+@pytest.mark.parametrize("name", helpers.POSITIVE + helpers.SYNTHETIC + ["LPA"])
+def test_gpu_golden_pvst(gpu, name, tmp_path):
+    g = helpers.read_gfa(helpers.fixture_path(name, str(tmp_path)))
+    f = gpu.decompose(len(g["ids"]), *api.edge_ports(g))
+    assert f.pvst_texts(g["ids"]) == helpers.expected_pvsts(name)
+
+
+def test_gpu_chain_50k_vs_oracle(gpu):
+    g = synth.snp_indel_chain(50_000, n_paths=2, seed=11, with_seqs=False)
+    f = _check(gpu, g)
+    assert f.n == 50_000 and f.dfs_rounds <= 4
+
+
+def test_gpu_cfg2_full_size_properties(gpu):
+    """cfg2 (1,000,001 segments / 1.4 M links): the oracle takes too long here, so check what the
+    construction guarantees: one flubble per bubble, all at PVST depth 1 under the root, boundaries are
+    consecutive backbone segments in chain order, and the result is deterministic across runs."""
+    n = 400_000
+    g = synth.snp_indel_chain(n, n_paths=1, seed=42, with_seqs=False)
+    assert len(g["ids"]) == 1_000_001 and len(g["v1"]) == 1_400_000
+    ep1, ep2 = api.edge_ports(g)
+    f = gpu.decompose(len(g["ids"]), ep1, ep2)
+    assert f.n == n and (f.parent == 0).all() and (f.depth == 1).all()
+    assert (f.a_fwd == 1).all() and (f.z_fwd == 1).all()
+    per = np.where(np.arange(n) % 2 == 0, 3, 2)
+    base = np.concatenate([[0], np.cumsum(per)])
+    assert (f.a_v == base[:n]).all() and (f.z_v == base[1:]).all()
+    f2 = gpu.decompose(len(g["ids"]), ep1, ep2)
+    for k in ("a_v", "z_v", "parent", "depth", "a_fwd", "z_fwd"):
+        assert (getattr(f, k) == getattr(f2, k)).all()

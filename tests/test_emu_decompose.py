@@ -1,0 +1,52 @@
+"""Host debug rehearsal (tests/emu/libpovu_emu.so = the SAME kernel bodies compiled with -DPV_EMU, one
+logical thread at a time) against the oracle.  This validates the pipeline logic where no GPU exists; the
+GPU parity tests proper are in test_decompose_gpu.py.  Three thread orders expose order dependence."""
+import os
+
+import numpy as np
+import pytest
+
+import helpers
+import oracle_binding as ob
+from povu_b200 import api, synth
+
+
+def _ctx(emu_lib, order):
+    os.environ["PV_EMU_ORDER"] = str(order)
+    return api.Povu(lib_path=emu_lib)
+
+
+def _check(pv, g):
+    ep1, ep2 = api.edge_ports(g)
+    f = pv.decompose(len(g["ids"]), ep1, ep2)
+    assert ob.flubble_rows(f, g["ids"]) == ob.oracle_decompose(g)
+    return f
+
+
+@pytest.mark.parametrize("order", [0, 1, 2])
+def test_emu_random_families(emu_lib, order):
+    pv = _ctx(emu_lib, order)
+    for s in range(40):
+        _check(pv, synth.nested_bubbles(s, shuffle_links=(s % 2 == 1)))
+    for s in range(80):
+        _check(pv, synth.wild(s, V=3 + s % 20, E=3 + s % 33, p_loop=0.1, n_comp=1 + s % 3))
+    for s in range(6):
+        _check(pv, synth.wild(1000 + s, V=200 + s * 10, E=300 + s * 17, p_loop=0.03, n_comp=1 + s % 4))
+        _check(pv, synth.nested_bubbles(500 + s, n_top=40, max_depth=5, shuffle_links=(s % 2 == 1)))
+    _check(pv, synth.snp_indel_chain(2000, n_paths=2, seed=9, with_seqs=False))
+
+
+@pytest.mark.parametrize("name", helpers.POSITIVE + helpers.SYNTHETIC + ["LPA"])
+def test_emu_golden_pvst(emu_lib, name, tmp_path):
+    pv = _ctx(emu_lib, 0)
+    g = helpers.read_gfa(helpers.fixture_path(name, str(tmp_path)))
+    ep1, ep2 = api.edge_ports(g)
+    f = pv.decompose(len(g["ids"]), ep1, ep2)
+    assert f.pvst_texts(g["ids"]) == helpers.expected_pvsts(name)
+
+
+def test_emu_is_not_the_default_library(emu_lib):
+    """The product path refuses anything but the CUDA build."""
+    lib = api.load_library(emu_lib)
+    assert lib.pvgpu_build_kind() == 2
+    assert api.load_library().pvgpu_build_kind() == 1
