@@ -36,6 +36,11 @@ const char *pvgpu_last_error(const pvgpu_ctx *ctx);
 /* kernels launched through this context so far (bench.py: gpu_launches) */
 uint64_t pvgpu_launch_count(const pvgpu_ctx *ctx);
 uint64_t pvgpu_peak_device_bytes(const pvgpu_ctx *ctx);
+/* per-kernel CUDA-event timing (bench.py roofline leg).  While on, every kernel launch is bracketed by
+ * events on the context's stream; pvgpu_profile_json synchronises and writes a JSON array of
+ * {name, launches, items, bytes (algorithmic), ms} (returns the size needed incl. NUL). */
+void pvgpu_set_profiling(pvgpu_ctx *ctx, int on);
+size_t pvgpu_profile_json(pvgpu_ctx *ctx, char *buf, size_t cap);
 /* 1 = sm_100a CUDA build, 2 = host debug rehearsal (tests only; never shipped) */
 int pvgpu_build_kind(void);
 

@@ -41,6 +41,9 @@ def load_library(lib_path=None):
     lib.pvgpu_peak_device_bytes.argtypes = [vp]
     lib.pvgpu_peak_device_bytes.restype = u64
     lib.pvgpu_build_kind.restype = C.c_int
+    lib.pvgpu_set_profiling.argtypes = [vp, C.c_int]
+    lib.pvgpu_profile_json.argtypes = [vp, C.c_char_p, C.c_size_t]
+    lib.pvgpu_profile_json.restype = C.c_size_t
     lib.pvgpu_decompose.argtypes = [vp, u32, u64, vp, vp, u32, C.POINTER(vp)]
     lib.pvgpu_decompose.restype = C.c_int
     lib.pvgpu_decompose_dev.argtypes = [vp, u32, u64, vp, vp, u32, C.POINTER(vp)]
@@ -157,6 +160,17 @@ class Povu:
     @property
     def peak_bytes(self):
         return int(self.lib.pvgpu_peak_device_bytes(self.h))
+
+    def set_profiling(self, on):
+        self.lib.pvgpu_set_profiling(self.h, 1 if on else 0)
+
+    def profile(self):
+        """Per-kernel CUDA-event timings accumulated since set_profiling(True)."""
+        import json
+        n = self.lib.pvgpu_profile_json(self.h, None, 0)
+        buf = C.create_string_buffer(n + 16)
+        self.lib.pvgpu_profile_json(self.h, buf, n + 16)
+        return json.loads(buf.value.decode())
 
     def _err(self):
         return self.lib.pvgpu_last_error(self.h).decode()

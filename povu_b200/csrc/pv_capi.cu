@@ -39,6 +39,22 @@ void pvgpu_destroy(pvgpu_ctx *x) { if (x) { x->c.destroy(); delete x; } }
 const char *pvgpu_last_error(const pvgpu_ctx *x) { return x ? x->err.c_str() : "null context"; }
 uint64_t pvgpu_launch_count(const pvgpu_ctx *x) { return x ? x->c.launches : 0; }
 uint64_t pvgpu_peak_device_bytes(const pvgpu_ctx *x) { return x ? x->c.bytes_peak : 0; }
+void pvgpu_set_profiling(pvgpu_ctx *x, int on) { if (x) { x->c.profiling = on != 0; if (on) x->c.prof_agg.clear(); } }
+size_t pvgpu_profile_json(pvgpu_ctx *x, char *buf, size_t cap) {
+	if (!x) return 0;
+	try { x->c.prof_collect(); } catch (...) {}
+	std::string o = "[";
+	for (size_t i = 0; i < x->c.prof_agg.size(); i++) {
+		auto &a = x->c.prof_agg[i];
+		char tmp[256];
+		snprintf(tmp, sizeof tmp, "%s{\"name\":\"%s\",\"launches\":%llu,\"items\":%llu,\"bytes\":%llu,\"ms\":%.6f}", i ? "," : "", a.name.c_str(),
+			 (unsigned long long)a.launches, (unsigned long long)a.items, (unsigned long long)a.bytes, a.ms);
+		o += tmp;
+	}
+	o += "]";
+	if (buf && cap) { size_t n = o.size() < cap - 1 ? o.size() : cap - 1; memcpy(buf, o.data(), n); buf[n] = 0; }
+	return o.size() + 1;
+}
 
 static int run_decompose(pvgpu_ctx *x, uint32_t V, uint64_t E, const uint32_t *d1, const uint32_t *d2, uint32_t flags, pvgpu_flubbles **out) {
 	pvgpu_flubbles *f = new pvgpu_flubbles();

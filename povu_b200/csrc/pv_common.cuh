@@ -64,6 +64,19 @@ struct Ctx {
 	int device = 0;
 	int sm_count = 148;
 	u64 launches = 0;       // kernels launched through this context (bench.py: gpu_launches)
+	// optional per-kernel CUDA-event timing (bench.py roofline leg): name -> {launches, items, bytes, ms}
+	bool profiling = false;
+	struct ProfRec { const char *name; u64 items; u64 bytes;
+#ifndef PV_EMU
+		cudaEvent_t e0, e1;
+#endif
+	};
+	std::vector<ProfRec> prof;
+	struct ProfAgg { std::string name; u64 launches, items, bytes; double ms; };
+	std::vector<ProfAgg> prof_agg;
+	void prof_begin(const char *name, u64 items, u64 bytes);
+	void prof_end();
+	void prof_collect();
 	u64 bytes_alloc = 0, bytes_peak = 0;
 
 	void init(int dev, void *ext_stream);
@@ -174,6 +187,44 @@ inline void Ctx::d2d(void *d, const void *s, size_t bytes) {
 #endif
 }
 
+inline void Ctx::prof_begin(const char *name, u64 items, u64 bytes) {
+	if (!profiling) return;
+	ProfRec r; r.name = name; r.items = items; r.bytes = bytes;
+#ifndef PV_EMU
+	PV_CUDA_CHECK(cudaEventCreate(&r.e0)); PV_CUDA_CHECK(cudaEventCreate(&r.e1));
+	PV_CUDA_CHECK(cudaEventRecord(r.e0, stream));
+#endif
+	prof.push_back(r);
+}
+inline void Ctx::prof_end() {
+	if (!profiling) return;
+#ifndef PV_EMU
+	PV_CUDA_CHECK(cudaEventRecord(prof.back().e1, stream));
+#endif
+}
+inline void Ctx::prof_collect() {
+	sync();
+	for (auto &r : prof) {
+		float ms = 0;
+#ifndef PV_EMU
+		cudaEventElapsedTime(&ms, r.e0, r.e1);
+		cudaEventDestroy(r.e0); cudaEventDestroy(r.e1);
+#endif
+		bool found = false;
+		for (auto &a : prof_agg) if (a.name == r.name) { a.launches++; a.items += r.items; a.bytes += r.bytes; a.ms += ms; found = true; break; }
+		if (!found) prof_agg.push_back(ProfAgg{r.name, 1, r.items, r.bytes, ms});
+	}
+	prof.clear();
+}
+
+// kernel tags: a name for launch lists / profiles and the ALGORITHMIC bytes one logical item moves
+// (compulsory reads + writes of that kernel, DESIGN.md "per-kernel algorithmic bytes")
+#define PV_KERNEL(tag, bytes_per_item)                                   \
+	struct tag {                                                     \
+		static const char *name() { return #tag; }               \
+		static constexpr u64 bytes = (bytes_per_item);           \
+	}
+
 // RAII device buffer (stream-ordered)
 template <class T> struct Buf {
 	Ctx *c = nullptr;
@@ -238,7 +289,9 @@ template <class Tag, class F> inline void parallel_for(Ctx &c, size_t n, F f) {
 	size_t blocks = (n + 255) / 256;
 	size_t cap = (size_t)c.sm_count * 8;
 	if (blocks > cap) blocks = cap;
+	c.prof_begin(Tag::name(), n, n * Tag::bytes);
 	pf_kernel<Tag, F><<<(unsigned)blocks, 256, 0, c.stream>>>(n, f);
+	c.prof_end();
 	c.launches++;
 #ifdef PV_SYNC_EVERY_LAUNCH
 	PV_CUDA_CHECK(cudaStreamSynchronize(c.stream));

@@ -45,16 +45,45 @@ struct DecompOut {
 
 struct DecompOpts { bool want_stack = false; u64 seed = 0x706F7675ull; };
 
-// kernel name tags
-struct K_minport {}; struct K_entries {}; struct K_portcount {}; struct K_csr_fill {}; struct K_rev {};
-struct K_tip {}; struct K_uf_init {}; struct K_uf_union {}; struct K_uf_flatten {}; struct K_start {};
-struct K_claim {}; struct K_entry {}; struct K_first_edge {}; struct K_mark {}; struct K_jump {};
-struct K_segconf {}; struct K_finalize {}; struct K_link {}; struct K_visit {}; struct K_active {};
-struct K_compcount {}; struct K_treeslot {}; struct K_euler {}; struct K_pre {}; struct K_backedge {};
-struct K_bridge {}; struct K_simp {}; struct K_key {}; struct K_stackw {}; struct K_stackpos {};
-struct K_gather {}; struct K_seen {}; struct K_verify {}; struct K_arc {}; struct K_lam {};
-struct K_fn {}; struct K_flub {}; struct K_parent {}; struct K_seq {}; struct K_iota {}; struct K_word {};
-struct K_classid {}; struct K_misc {};
+// kernel tags with their algorithmic bytes per logical item
+PV_KERNEL(K_minport, 24);      // 2 endpoints in, key + idx out, 2 degree atomics
+PV_KERNEL(K_entries, 36);      // order + 2 endpoints in, 2 x (port, nbr, idx) out
+PV_KERNEL(K_csr_fill, 24);
+PV_KERNEL(K_rev, 12);
+PV_KERNEL(K_tip, 12);
+PV_KERNEL(K_uf_init, 20);
+PV_KERNEL(K_uf_union, 24);     // per port: offsets + ~2 neighbours + visited + uf words
+PV_KERNEL(K_uf_flatten, 12);
+PV_KERNEL(K_start, 12);
+PV_KERNEL(K_claim, 28);
+PV_KERNEL(K_entry, 24);
+PV_KERNEL(K_first_edge, 28);
+PV_KERNEL(K_mark, 16);
+PV_KERNEL(K_jump, 12);         // J[x], J[J[x]] in, J'[x] out
+PV_KERNEL(K_segconf, 12);
+PV_KERNEL(K_finalize, 36);
+PV_KERNEL(K_visit, 16);
+PV_KERNEL(K_active, 12);
+PV_KERNEL(K_compcount, 12);
+PV_KERNEL(K_treeslot, 8);
+PV_KERNEL(K_euler, 48);
+PV_KERNEL(K_pre, 32);
+PV_KERNEL(K_backedge, 64);
+PV_KERNEL(K_bridge, 24);
+PV_KERNEL(K_simp, 12);
+PV_KERNEL(K_stackw, 40);
+PV_KERNEL(K_stackpos, 72);
+PV_KERNEL(K_seen, 44);
+PV_KERNEL(K_verify, 32);
+PV_KERNEL(K_arc, 16);
+PV_KERNEL(K_lam, 16);
+PV_KERNEL(K_fn, 24);
+PV_KERNEL(K_flub, 28);
+PV_KERNEL(K_parent, 16);
+PV_KERNEL(K_seq, 16);
+PV_KERNEL(K_iota, 4);
+PV_KERNEL(K_word, 24);
+PV_KERNEL(K_classid, 12);
 
 struct MP { i32 a, b; };   // x -> max(x + a, b)
 struct OpMP {

@@ -90,16 +90,22 @@ inline void scan_impl(Ctx &c, const T *in, T *out, size_t n, Op op, T identity) 
 	if (n == 0) return;
 	size_t nblocks = (n + SCAN_TILE - 1) / SCAN_TILE;
 	if (nblocks == 1) {
+		c.prof_begin("scan_apply", n, n * 2 * sizeof(T));
 		scan_apply_kernel<T, Op, INCLUSIVE><<<1, SCAN_THREADS, 0, c.stream>>>(in, out, (const T *)nullptr, n, op, identity);
+		c.prof_end();
 		c.launches++;
 		PV_CUDA_CHECK(cudaGetLastError());
 		return;
 	}
 	Buf<T> sums(c, nblocks);
+	c.prof_begin("scan_reduce", n, n * sizeof(T));
 	scan_reduce_kernel<T, Op><<<(unsigned)nblocks, SCAN_THREADS, 0, c.stream>>>(in, sums.p, n, op, identity);
+	c.prof_end();
 	c.launches++;
 	scan_impl<T, Op, false>(c, sums.p, sums.p, nblocks, op, identity);
+	c.prof_begin("scan_apply", n, n * 2 * sizeof(T));
 	scan_apply_kernel<T, Op, INCLUSIVE><<<(unsigned)nblocks, SCAN_THREADS, 0, c.stream>>>(in, out, sums.p, n, op, identity);
+	c.prof_end();
 	c.launches++;
 	PV_CUDA_CHECK(cudaGetLastError());
 }
@@ -191,10 +197,14 @@ inline void radix_sort_pairs(Ctx &c, u32 *keys, u32 *vals, size_t n, int bits) {
 	unsigned blocks = (unsigned)((nsub + RS_WARPS - 1) / RS_WARPS);
 	u32 *ki = keys, *vi = vals, *ko = k2.p, *vo = v2.p;
 	for (int shift = 0; shift < bits; shift += 8) {
+		c.prof_begin("rs_hist", n, n * 4);
 		rs_hist_kernel<<<blocks, RS_WARPS * 32, 0, c.stream>>>(ki, counts.p, n, nsub, shift);
+		c.prof_end();
 		c.launches++;
 		exclusive_scan(c, counts.p, counts.p, 256 * nsub, OpAddU32(), 0u);
+		c.prof_begin("rs_scatter", n, n * 16);
 		rs_scatter_kernel<<<blocks, RS_WARPS * 32, 0, c.stream>>>(ki, vi, ko, vo, counts.p, n, nsub, shift);
+		c.prof_end();
 		c.launches++;
 		PV_CUDA_CHECK(cudaGetLastError());
 		std::swap(ki, ko); std::swap(vi, vo);
@@ -275,8 +285,8 @@ struct Rmq {
 	RmqView view() const { return RmqView{a, pre.p, suf.p, table.p, n, nb, levels}; }
 };
 
-struct K_rmq_blocks {};
-struct K_rmq_level {};
+PV_KERNEL(K_rmq_blocks, 12);   // a in, pre + suf out (+ block min)
+PV_KERNEL(K_rmq_level, 12);
 
 inline void rmq_build(Ctx &c, Rmq &r, const u32 *a, u32 n) {
 	r.a = a; r.n = n; r.nb = (n + 31) / 32;
@@ -309,9 +319,9 @@ inline void rmq_build(Ctx &c, Rmq &r, const u32 *a, u32 n) {
 // Output: rank[i] = sum of weights of the elements strictly AFTER i on its list ... plus nothing;
 // i.e. suffix sums excluding i.  Packed as (next << 32 | acc) so every hop is one 8-byte load.
 // ---------------------------------------------------------------------------------------------
-struct K_lr_init {};
-struct K_lr_jump {};
-struct K_lr_out {};
+PV_KERNEL(K_lr_init, 16);
+PV_KERNEL(K_lr_jump, 24);      // a[i], a[next] in, b[i] out (8 B each)
+PV_KERNEL(K_lr_out, 12);
 
 inline void list_rank_suffix(Ctx &c, const u32 *next, const u32 *weight, u32 *rank_out, size_t n) {
 	if (n == 0) return;
@@ -343,7 +353,7 @@ inline void list_rank_suffix(Ctx &c, const u32 *next, const u32 *weight, u32 *ra
 // ---------------------------------------------------------------------------------------------
 // stream compaction of indices i in [0,n) with flag[i] != 0 -> out (ascending); returns the count
 // ---------------------------------------------------------------------------------------------
-struct K_compact_scatter {};
+PV_KERNEL(K_compact_scatter, 12);
 inline u32 compact_flags(Ctx &c, const u32 *flags, size_t n, Buf<u32> &out) {
 	if (n == 0) { out = Buf<u32>(c, 1); return 0; }
 	Buf<u32> pos(c, n + 1);
