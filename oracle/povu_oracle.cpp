@@ -4,7 +4,7 @@
  * (app/subcommand/decompose.cpp:94-160: one <component_id>.pvst per component >= 3 vertices). */
 #include <cstring>
 #include <iostream>
-#include "oracle_decompose.hpp"
+#include "oracle_call.hpp"
 
 using namespace oracle;
 
@@ -95,12 +95,16 @@ OracleResult *oracle_decompose_arrays_notips(uint32_t V, const uint32_t *ids, ui
 
 #ifndef ORACLE_NO_MAIN
 int main(int argc, char **argv) {
-	if (argc < 2) { fprintf(stderr, "usage: povu_oracle decompose -i gfa -o dir\n"); return 2; }
+	if (argc < 2) { fprintf(stderr, "usage: povu_oracle decompose -i gfa -o dir | gfa2vcf -i gfa -P prefix [-c chunk]\n"); return 2; }
 	std::string task = argv[1], gfa, out = ".";
+	std::vector<std::string> prefixes; size_t chunk = 100;
 	for (int i = 2; i < argc; i++) {
 		std::string a = argv[i];
 		if (a == "-i" && i + 1 < argc) gfa = argv[++i];
 		else if (a == "-o" && i + 1 < argc) out = argv[++i];
+		else if (a == "-P" && i + 1 < argc) prefixes.push_back(argv[++i]);
+		else if (a == "-c" && i + 1 < argc) chunk = (size_t)atol(argv[++i]);
+		else if (a == "-t" && i + 1 < argc) ++i;
 	}
 	try {
 		if (task == "decompose") {
@@ -109,6 +113,15 @@ int main(int argc, char **argv) {
 				std::ofstream f(out + "/" + std::to_string(c.component_id) + ".pvst");
 				f << pvst_text(c.flubbles);
 			}
+		} else if (task == "gfa2vcf") {
+			Graph g = load_gfa(gfa, true, true);
+			std::vector<Pvst> pvsts;
+			for (auto &c : decompose(g)) { Pvst p; p.component_id = c.component_id; p.fl = c.flubbles; p.finish(); pvsts.push_back(std::move(p)); }
+			CallStats st;
+			std::string vcf = call_vcf(g, pvsts, prefixes, chunk, true, st);
+			fwrite(vcf.data(), 1, vcf.size(), stdout);
+			fprintf(stderr, "[oracle] rovs=%llu tangled_skipped=%llu pin_pairs=%llu too_small=%llu hard_errors=%llu\n", (unsigned long long)st.rovs,
+				(unsigned long long)st.tangled_skipped, (unsigned long long)st.pin_pairs, (unsigned long long)st.too_small, (unsigned long long)st.hard_errors);
 		} else { fprintf(stderr, "unknown task\n"); return 2; }
 	} catch (std::exception &e) { std::cerr << "[povu::subcommands::do_" << task << "] Error: " << e.what() << std::endl; return 1; }
 	return 0;

@@ -63,7 +63,7 @@ def main():
     for name, g in cases.items():
         p = os.path.join(syn, name + ".gfa")
         synth.write_gfa(g, p)
-        PREFIX[name] = "S001"
+        PREFIX[name] = "S001#1#chr1" if name == "multi_comp" else "S001"
         run_ref(p, name)
 
 
