@@ -71,6 +71,43 @@ uint64_t pvgpu_flubbles_stack_size(const pvgpu_flubbles *f);
 void pvgpu_flubbles_copy_stack(const pvgpu_flubbles *f, uint32_t *v, uint32_t *class_id, uint32_t *fwd);
 void pvgpu_flubbles_free(pvgpu_flubbles *f);
 
+/* ---------------------------------------------------------------------------------------------------
+ * Sessions: one loaded GFA on one device.  This is the layer behind the `povu` CLI clone
+ * (decompose / call / gfa2vcf: /root/reference/app/subcommand/{decompose,call,gfa2vcf}.cpp) and behind
+ * include/povu_ffi.h.  It replaces the reference's in-process operators
+ *     mto::from_gfa::to_bd        (/root/reference/src/mto/from_gfa.cpp:141)     -> pvgpu_session_open
+ *     do_decompose + write_pvst   (decompose.cpp:94-160, to_pvst.cpp:30)         -> pvgpu_session_decompose / _write_pvst
+ *     read_pvst                   (from_pvst.cpp:162)                            -> pvgpu_session_read_pvst
+ *     ig::gen_vcf_rec_map         (/root/reference/src/ita/genomics/genomics.cpp:69) -> pvgpu_session_call
+ *     to_vcf::init_vcfs/write_vcfs (/root/reference/src/mto/to_vcf.cpp:54,121)   -> pvgpu_session_vcf_text
+ * Errors: non-zero return, message via pvgpu_last_error(ctx) (e.g. "Invalid GFA '<path>': ...").
+ */
+typedef struct pvgpu_session pvgpu_session;
+int pvgpu_session_open(pvgpu_ctx *ctx, const char *gfa_path, int inc_vtx_labels, int inc_refs, pvgpu_session **out);
+void pvgpu_session_close(pvgpu_session *s);
+/* graph sizes: vertices, edges, paths, total path steps */
+void pvgpu_session_sizes(const pvgpu_session *s, uint64_t *n_vertices, uint64_t *n_edges, uint64_t *n_paths, uint64_t *n_steps);
+int pvgpu_session_decompose(pvgpu_session *s);
+uint64_t pvgpu_session_flubble_count(const pvgpu_session *s);
+uint32_t pvgpu_session_tree_count(const pvgpu_session *s);
+/* component id of PVST tree k, and its .pvst v0.0.3 text (malloc'ed; release with pvgpu_free) */
+uint32_t pvgpu_session_tree_component(const pvgpu_session *s, uint32_t k);
+char *pvgpu_session_pvst_text(const pvgpu_session *s, uint32_t k, size_t *len);
+int pvgpu_session_write_pvst(const pvgpu_session *s, const char *dir);
+int pvgpu_session_read_pvst(pvgpu_session *s, const char *dir);
+/* call against the paths selected by the prefixes (refs.hpp:278-301).  Records stay in the session. */
+int pvgpu_session_call(pvgpu_session *s, const char *const *prefixes, size_t n_prefixes);
+uint64_t pvgpu_session_record_count(const pvgpu_session *s);
+/* counters of the last call: [0] regions selected, [1] regions with >= 3 vertices, [2] tangled regions,
+ * [3] inversion pin pairs, [4] regions whose BFS/Kahn order failed, [5] hard errors (the reference would
+ * have exited), [6] device chunks, [7] regions dropped as too small, [8] vertices of the largest region, [9] regions ordered
+ * by a global-arena BFS tier */
+void pvgpu_session_call_stats(const pvgpu_session *s, uint64_t out[10]);
+/* combined VCF text (what `povu gfa2vcf` / `povu call --stdout` print); with_date = 0 drops ##fileDate.
+ * prefix = NULL: combined stream; otherwise the per-prefix file content of `-o dir` (to_vcf.hpp:83-101). */
+char *pvgpu_session_vcf_text(const pvgpu_session *s, size_t chunk_size, int with_date, const char *prefix, size_t *len);
+void pvgpu_free(void *p);
+
 #ifdef __cplusplus
 }
 #endif

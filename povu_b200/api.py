@@ -62,6 +62,33 @@ def load_library(lib_path=None):
     lib.pvgpu_flubbles_stack_size.restype = u64
     lib.pvgpu_flubbles_copy_stack.argtypes = [vp, P32, P32, P32]
     lib.pvgpu_flubbles_free.argtypes = [vp]
+    sz = C.c_size_t
+    lib.pvgpu_session_open.argtypes = [vp, C.c_char_p, C.c_int, C.c_int, C.POINTER(vp)]
+    lib.pvgpu_session_open.restype = C.c_int
+    lib.pvgpu_session_close.argtypes = [vp]
+    lib.pvgpu_session_sizes.argtypes = [vp] + [C.POINTER(u64)] * 4
+    lib.pvgpu_session_decompose.argtypes = [vp]
+    lib.pvgpu_session_decompose.restype = C.c_int
+    lib.pvgpu_session_flubble_count.argtypes = [vp]
+    lib.pvgpu_session_flubble_count.restype = u64
+    lib.pvgpu_session_tree_count.argtypes = [vp]
+    lib.pvgpu_session_tree_count.restype = u32
+    lib.pvgpu_session_tree_component.argtypes = [vp, u32]
+    lib.pvgpu_session_tree_component.restype = u32
+    lib.pvgpu_session_pvst_text.argtypes = [vp, u32, C.POINTER(sz)]
+    lib.pvgpu_session_pvst_text.restype = vp
+    lib.pvgpu_session_write_pvst.argtypes = [vp, C.c_char_p]
+    lib.pvgpu_session_write_pvst.restype = C.c_int
+    lib.pvgpu_session_read_pvst.argtypes = [vp, C.c_char_p]
+    lib.pvgpu_session_read_pvst.restype = C.c_int
+    lib.pvgpu_session_call.argtypes = [vp, C.POINTER(C.c_char_p), sz]
+    lib.pvgpu_session_call.restype = C.c_int
+    lib.pvgpu_session_record_count.argtypes = [vp]
+    lib.pvgpu_session_record_count.restype = u64
+    lib.pvgpu_session_call_stats.argtypes = [vp, C.POINTER(u64)]
+    lib.pvgpu_session_vcf_text.argtypes = [vp, sz, C.c_int, C.c_char_p, C.POINTER(sz)]
+    lib.pvgpu_session_vcf_text.restype = vp
+    lib.pvgpu_free.argtypes = [vp]
     return lib
 
 
@@ -197,3 +224,76 @@ class Povu:
             return Flubbles(self.lib, out) if fetch else int(self.lib.pvgpu_flubbles_count(out))
         finally:
             self.lib.pvgpu_flubbles_free(out)
+
+
+class Session:
+    """One GFA loaded on one device: decompose -> (.pvst) -> call -> VCF text.  Mirrors the reference's
+    `povu decompose / call / gfa2vcf` drivers (app/subcommand/*.cpp) through the pvgpu_session_* C ABI."""
+
+    def __init__(self, pv, gfa_path, inc_vtx_labels=True, inc_refs=True):
+        self.pv, self.lib = pv, pv.lib
+        h = C.c_void_p()
+        rc = self.lib.pvgpu_session_open(pv.h, os.fsencode(gfa_path), int(inc_vtx_labels), int(inc_refs), C.byref(h))
+        if rc != 0:
+            raise RuntimeError(pv._err())
+        self.h = h
+
+    def close(self):
+        if self.h:
+            self.lib.pvgpu_session_close(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise RuntimeError(self.pv._err())
+
+    def _text(self, p, n):
+        if not p:
+            raise RuntimeError(self.pv._err())
+        try:
+            return C.string_at(p, n.value).decode()
+        finally:
+            self.lib.pvgpu_free(p)
+
+    def sizes(self):
+        a = [C.c_uint64() for _ in range(4)]
+        self.lib.pvgpu_session_sizes(self.h, *[C.byref(x) for x in a])
+        return tuple(int(x.value) for x in a)
+
+    def decompose(self):
+        self._check(self.lib.pvgpu_session_decompose(self.h))
+        return int(self.lib.pvgpu_session_flubble_count(self.h))
+
+    def pvst_texts(self):
+        out = {}
+        for k in range(self.lib.pvgpu_session_tree_count(self.h)):
+            n = C.c_size_t()
+            out[int(self.lib.pvgpu_session_tree_component(self.h, k))] = self._text(self.lib.pvgpu_session_pvst_text(self.h, k, C.byref(n)), n)
+        return out
+
+    def write_pvst(self, d):
+        self._check(self.lib.pvgpu_session_write_pvst(self.h, os.fsencode(d)))
+
+    def read_pvst(self, d):
+        self._check(self.lib.pvgpu_session_read_pvst(self.h, os.fsencode(d)))
+
+    def call(self, prefixes):
+        arr = (C.c_char_p * len(prefixes))(*[p.encode() for p in prefixes])
+        self._check(self.lib.pvgpu_session_call(self.h, arr, len(prefixes)))
+        return int(self.lib.pvgpu_session_record_count(self.h))
+
+    def call_stats(self):
+        a = (C.c_uint64 * 10)()
+        self.lib.pvgpu_session_call_stats(self.h, a)
+        k = ["selected", "regions", "tangled", "pin_pairs", "sort_failed", "hard_errors", "chunks", "too_small", "max_region", "big_bfs"]
+        return dict(zip(k, [int(x) for x in a]))
+
+    def vcf_text(self, chunk_size=100, with_date=False, prefix=None):
+        n = C.c_size_t()
+        return self._text(self.lib.pvgpu_session_vcf_text(self.h, chunk_size, int(with_date), prefix.encode() if prefix else None, C.byref(n)), n)

@@ -1,0 +1,752 @@
+// povu_b200 -- call: (graph + haplotype paths + PVST flubbles) -> binary VCF records, every step a
+// data-parallel kernel over flat HBM arrays.  Replaces, with identical results, the reference's
+//   ic::color_pvst              /root/reference/src/ita/variation/color.cpp:15-30,104-163
+//   ir::gen_rov / find_pvst_rovs /root/reference/src/ita/variation/rov.cpp:185-268
+//   bfs_sort / comp_bfs_tree    /root/reference/src/ita/graph/graph.cpp:75-163,557-577
+//   BfsTree::sort (Kahn)        /root/reference/include/ita/graph/bfs_tree.hpp:257-328
+//   depth_matrix::fill          /root/reference/include/ita/genomics/allele.hpp:804-862
+//   gen_race (lap 0)            /root/reference/src/ita/genomics/untangle.cpp:29-103
+//   comp_exps + helpers         /root/reference/src/ita/variation/overlay.cpp:84-588
+//   minimal_rov grouping        /root/reference/include/ita/genomics/allele.hpp:302-475
+//   gen_exp_vcf_recs / gen_gt_data  /root/reference/src/ita/genomics/vcf.cpp:20-121,241-273
+//
+// Device data layout (DESIGN.md "call: HBM layout"):
+//   steps[S]      packed path steps, paths concatenated in P-line order: (vertex idx << 1) | strand
+//   stepOff[H+1]  first step of every path;  loci[S] 1-based start coordinate of every step
+//   vsOff[V+1], vsStep[S], vsHap[S]   per-vertex list of the (global) steps that visit it, ascending --
+//                 since paths are concatenated in hap order this is also (hap, local step) order, i.e. the
+//                 reference's vertex_to_step_matrix_ flattened (bidirected.cpp:347-355)
+//   adjOff[2V+1], adjNbr[..]          per-port neighbour ports in ascending L-line order (bidirected.hpp:68-69)
+//   per region r: verts[rovOff[r] .. +J)  sorted vertices;  depth matrix cells u16 [nh_r x J_r] at matBase[r]
+//                 (rows = the paths of the region's component, ascending path id)
+#pragma once
+#include "pv_decompose.cuh"
+
+namespace pv {
+
+typedef uint16_t u16;
+
+#ifndef PV_EMU
+PV_DEV u64 atomic_cas64(u64 *p, u64 cmp, u64 v) { return (u64)atomicCAS((unsigned long long *)p, (unsigned long long)cmp, (unsigned long long)v); }
+#else
+inline u64 atomic_cas64(u64 *p, u64 cmp, u64 v) { u64 o = *p; if (o == cmp) *p = v; return o; }
+#endif
+
+PV_KERNEL(C_adj_entries, 24);
+PV_KERNEL(C_adj_fill, 16);
+PV_KERNEL(C_loci_len, 12);
+PV_KERNEL(C_loci, 20);
+PV_KERNEL(C_vs_key, 12);
+PV_KERNEL(C_vs_hap, 12);
+PV_KERNEL(C_uf, 16);
+PV_KERNEL(C_color, 32);
+PV_KERNEL(C_child, 12);
+PV_KERNEL(C_bfs, 128);
+PV_KERNEL(C_gather, 16);
+PV_KERNEL(C_rovmeta, 24);
+PV_KERNEL(C_hash, 16);
+PV_KERNEL(C_matfill, 24);       // per (region, column): the vertex's step list in, one cell per visiting path out
+PV_KERNEL(C_lap, 16);
+PV_KERNEL(C_pair_count, 16);    // per (region, path): two matrix rows in, a count out
+PV_KERNEL(C_pair_fill, 64);
+PV_KERNEL(C_group, 64);
+PV_KERNEL(C_emit, 64);
+PV_KERNEL(C_gt_ref, 16);
+PV_KERNEL(C_gt_alt, 16);
+PV_KERNEL(C_fill16, 2);
+
+PV_DEV u32 lb_u32(const u32 *a, u32 lo, u32 hi, u32 key) {   // first index in [lo, hi) with a[idx] >= key
+	while (lo < hi) { u32 m = lo + ((hi - lo) >> 1); if (a[m] < key) lo = m + 1; else hi = m; }
+	return lo;
+}
+PV_DEV u32 ub_u32(const u32 *a, u32 lo, u32 hi, u32 key) {   // first index in [lo, hi) with a[idx] > key
+	while (lo < hi) { u32 m = lo + ((hi - lo) >> 1); if (a[m] <= key) lo = m + 1; else hi = m; }
+	return lo;
+}
+PV_DEV u64 ub_u64(const u64 *a, u64 lo, u64 hi, u64 key) {
+	while (lo < hi) { u64 m = lo + ((hi - lo) >> 1); if (a[m] <= key) lo = m + 1; else hi = m; }
+	return lo;
+}
+
+// ---------------------------------------------------------------------------------------------
+// device-resident graph + paths (built once, used by every call)
+// ---------------------------------------------------------------------------------------------
+struct DevGraph {
+	u32 V = 0, H = 0, S = 0; u64 E = 0;
+	Buf<u32> adjOff, adjNbr;
+	Buf<u32> steps, loci, stepOff, segLen;
+	Buf<u32> vsOff, vsStep, vsHap;
+	Buf<u32> vcomp;
+	// host copies of the small per-path tables
+	std::vector<u32> h_stepOff;
+	std::vector<u32> pathComp;        // dense component index per path (NONE for empty paths)
+	std::vector<u32> cpOff, cpList;   // paths of every component, ascending
+	std::vector<u32> hapLocal;        // index of the path inside its component's list
+	Buf<u32> d_pathComp, d_cpOff, d_cpList, d_hapLocal;
+};
+
+struct GraphView {
+	u32 V, H, S;
+	const u32 *adjOff, *adjNbr, *steps, *loci, *stepOff, *vsOff, *vsStep, *vsHap, *pathComp, *cpOff, *cpList, *hapLocal;
+	// first / last step in [lo, hi) that visits vertex v (NONE if none)
+	PV_DEV u32 occ_first(u32 v, u32 lo, u32 hi) const {
+		u32 a = vsOff[v], b = vsOff[v + 1];
+		u32 k = lb_u32(vsStep, a, b, lo);
+		return (k < b && vsStep[k] < hi) ? vsStep[k] : NONE;
+	}
+	PV_DEV u32 occ_last(u32 v, u32 lo, u32 hi) const {
+		u32 a = vsOff[v], b = vsOff[v + 1];
+		u32 k = lb_u32(vsStep, a, b, hi);
+		return (k > a && vsStep[k - 1] >= lo) ? vsStep[k - 1] : NONE;
+	}
+	PV_DEV bool has_hap(u32 v, u32 h) const {   // any step of path h on vertex v
+		return occ_first(v, stepOff[h], stepOff[h + 1]) != NONE;
+	}
+};
+
+inline GraphView view(const DevGraph &g) {
+	return GraphView{g.V, g.H, g.S, g.adjOff.p, g.adjNbr.p, g.steps.p, g.loci.p, g.stepOff.p, g.vsOff.p, g.vsStep.p, g.vsHap.p,
+			 g.d_pathComp.p, g.d_cpOff.p, g.d_cpList.p, g.d_hapLocal.p};
+}
+
+// d_ep1/d_ep2: E edge endpoint ports (device).  d_steps: S packed steps (device).  d_segLen: V (device).
+inline void graph_build(Ctx &c, u32 V, u64 E, const u32 *ep1, const u32 *ep2, u32 H, const u32 *h_stepOff, const u32 *d_steps,
+			const u32 *d_segLen, DevGraph &g) {
+	g.V = V; g.E = E; g.H = H; g.S = h_stepOff ? h_stepOff[H] : 0;
+	const u32 P = 2 * V; const u64 M = 2 * E; const u32 S = g.S;
+	if (M >= 0xFFFFFFF0ull) throw std::runtime_error("graph too large for 32-bit adjacency slots");
+	// ---- adjacency in whole-graph edge order (what `call` iterates: bidirected.hpp:68-69)
+	g.adjOff = Buf<u32>(c, (size_t)P + 2); g.adjNbr = Buf<u32>(c, M ? M : 1);
+	{
+		Buf<u32> key(c, M ? M : 1), idx(c, M ? M : 1), nbr(c, M ? M : 1), cnt(c, (size_t)P + 2);
+		cnt.zero();
+		u32 *key_ = key.p, *idx_ = idx.p, *nbr_ = nbr.p, *cnt_ = cnt.p;
+		parallel_for<C_adj_entries>(c, E, PV_LAMBDA(size_t e) {
+			u32 a = ep1[e], b = ep2[e];
+			bool self = (a >> 1) == (b >> 1);
+			// Edge::get_other_vtx(v, side) answers the complement side for any self-loop (bidirected.cpp:66-77)
+			key_[2 * e] = a; nbr_[2 * e] = self ? (a ^ 1u) : b; idx_[2 * e] = (u32)(2 * e);
+			bool dup = a == b;   // v+ -> v- style loop: one std::set entry
+			key_[2 * e + 1] = dup ? P : b; nbr_[2 * e + 1] = self ? (b ^ 1u) : a; idx_[2 * e + 1] = (u32)(2 * e + 1);
+			atomic_add(cnt_ + a, 1u);
+			if (!dup) atomic_add(cnt_ + b, 1u);
+		});
+		radix_sort_pairs(c, key.p, idx.p, M, bits_for((u64)P + 1));
+		exclusive_scan(c, cnt.p, g.adjOff.p, (size_t)P + 2, OpAddU32(), 0u);
+		u32 *adjNbr_ = g.adjNbr.p;
+		parallel_for<C_adj_fill>(c, M, PV_LAMBDA(size_t s) { adjNbr_[s] = nbr_[idx_[s]]; });
+	}
+	// ---- paths
+	g.h_stepOff.assign(h_stepOff, h_stepOff + H + 1);
+	g.stepOff = Buf<u32>(c, (size_t)H + 1); c.h2d(g.stepOff.p, h_stepOff, ((size_t)H + 1) * 4);
+	g.steps = Buf<u32>(c, S ? S : 1); c.d2d(g.steps.p, d_steps, (size_t)S * 4);
+	g.segLen = Buf<u32>(c, V ? V : 1); c.d2d(g.segLen.p, d_segLen, (size_t)V * 4);
+	g.loci = Buf<u32>(c, S ? S : 1);
+	g.vsOff = Buf<u32>(c, (size_t)V + 1); g.vsStep = Buf<u32>(c, S ? S : 1); g.vsHap = Buf<u32>(c, S ? S : 1);
+	const u32 *steps_ = g.steps.p, *stepOff_ = g.stepOff.p, *segLen_ = g.segLen.p;
+	{
+		// loci[k] = 1-based start coordinate of step k (liteseq ref_walk::loci)
+		Buf<u64> len(c, (size_t)S + 1), pre(c, (size_t)S + 1);
+		u64 *len_ = len.p, *pre_ = pre.p; u32 *loci_ = g.loci.p;
+		parallel_for<C_loci_len>(c, (size_t)S + 1, PV_LAMBDA(size_t s) { len_[s] = s < S ? (u64)segLen_[steps_[s] >> 1] : 0ull; });
+		exclusive_scan(c, len.p, pre.p, (size_t)S + 1, OpAddU64(), (u64)0);
+		parallel_for<C_loci>(c, S, PV_LAMBDA(size_t s) {
+			u32 h = ub_u32(stepOff_, 0, H + 1, (u32)s) - 1;
+			loci_[s] = (u32)(1ull + pre_[s] - pre_[stepOff_[h]]);
+		});
+	}
+	{
+		// vertex -> steps index: stable sort of the step indices by vertex
+		Buf<u32> key(c, S ? S : 1), cnt(c, (size_t)V + 1);
+		cnt.zero();
+		u32 *key_ = key.p, *cnt_ = cnt.p, *vsStep_ = g.vsStep.p, *vsHap_ = g.vsHap.p;
+		parallel_for<C_vs_key>(c, S, PV_LAMBDA(size_t s) { u32 v = steps_[s] >> 1; key_[s] = v; vsStep_[s] = (u32)s; atomic_add(cnt_ + v, 1u); });
+		radix_sort_pairs(c, key.p, g.vsStep.p, S, bits_for(V));
+		exclusive_scan(c, cnt.p, g.vsOff.p, (size_t)V + 1, OpAddU32(), 0u);
+		parallel_for<C_vs_hap>(c, S, PV_LAMBDA(size_t i) { vsHap_[i] = ub_u32(stepOff_, 0, H + 1, vsStep_[i]) - 1; });
+	}
+	// ---- weakly connected components -> the paths of every component
+	g.vcomp = Buf<u32>(c, V ? V : 1);
+	{
+		u32 *uf_ = g.vcomp.p;
+		parallel_for<C_uf>(c, V, PV_LAMBDA(size_t v) { uf_[v] = (u32)v; });
+		parallel_for<C_uf>(c, E, PV_LAMBDA(size_t e) { uf_union(uf_, ep1[e] >> 1, ep2[e] >> 1); });
+		parallel_for<C_uf>(c, V, PV_LAMBDA(size_t v) { uf_[v] = uf_find(uf_, (u32)v); });
+		Buf<u32> pr(c, H ? H : 1);
+		u32 *pr_ = pr.p;
+		parallel_for<C_uf>(c, H, PV_LAMBDA(size_t h) { pr_[h] = stepOff_[h + 1] > stepOff_[h] ? uf_[steps_[stepOff_[h]] >> 1] : NONE; });
+		std::vector<u32> roots = pr.to_host(); roots.resize(H);
+		std::vector<u32> uniq;
+		for (u32 r : roots) if (r != NONE) uniq.push_back(r);
+		std::sort(uniq.begin(), uniq.end()); uniq.erase(std::unique(uniq.begin(), uniq.end()), uniq.end());
+		g.pathComp.assign(H, NONE); g.hapLocal.assign(H, 0);
+		g.cpOff.assign(uniq.size() + 1, 0);
+		for (u32 h = 0; h < H; h++) if (roots[h] != NONE) { u32 k = (u32)(std::lower_bound(uniq.begin(), uniq.end(), roots[h]) - uniq.begin()); g.pathComp[h] = k; g.cpOff[k + 1]++; }
+		for (size_t k = 0; k < uniq.size(); k++) g.cpOff[k + 1] += g.cpOff[k];
+		g.cpList.assign(g.cpOff.back(), 0);
+		std::vector<u32> fill(g.cpOff.begin(), g.cpOff.end() - 1);
+		for (u32 h = 0; h < H; h++) if (g.pathComp[h] != NONE) { u32 k = g.pathComp[h]; g.hapLocal[h] = fill[k] - g.cpOff[k]; g.cpList[fill[k]++] = h; }
+		auto up = [&](Buf<u32> &b, const std::vector<u32> &h) { b = Buf<u32>(c, h.size() ? h.size() : 1); c.h2d(b.p, h.data(), h.size() * 4); };
+		up(g.d_pathComp, g.pathComp); up(g.d_cpOff, g.cpOff); up(g.d_cpList, g.cpList); up(g.d_hapLocal, g.hapLocal);
+	}
+	c.sync();
+}
+
+// ---------------------------------------------------------------------------------------------
+// region vertex order: BFS tree + Kahn-style sort (graph.cpp:75-163, bfs_tree.hpp:257-328), one thread
+// per region over caller-provided scratch.  Returns the number of sorted vertices, 0 if the sort fails
+// (cycle -> the reference falls back to gen_sort), or NONE on scratch overflow (retry with more).
+// ---------------------------------------------------------------------------------------------
+struct BfsScratch {
+	u32 capV, capE;
+	u32 *tv;      // [capV]   tree vertex -> (vertex idx << 1) | reverse
+	u32 *estart;  // [capV+1] out-edge range of a tree vertex
+	u32 *eto;     // [capE]   (to << 1) | tree-edge flag
+	u32 *deg;     // [capV]
+	u32 *order;   // [capV]   Kahn queue == output order
+	u32 *hkey;    // [hcap]   open-addressing vertex -> tree vertex map (hcap = 0: linear scan of tv)
+	u32 *hval;
+	u32 hcap;
+};
+static const u32 MAX_UNBLOCK_CTR = 10000;   // graph.hpp:22-23
+
+PV_DEV u32 bfs_find(const BfsScratch &s, u32 n, u32 v) {
+	if (s.hcap == 0) { for (u32 t = 0; t < n; t++) if ((s.tv[t] >> 1) == v) return t; return NONE; }
+	u32 m = s.hcap - 1, i = (u32)(splitmix64(v) & m);
+	while (true) { u32 k = s.hkey[i]; if (k == v) return s.hval[i]; if (k == NONE) return NONE; i = (i + 1) & m; }
+}
+PV_DEV void bfs_put(const BfsScratch &s, u32 v, u32 t) {
+	if (s.hcap == 0) return;
+	u32 m = s.hcap - 1, i = (u32)(splitmix64(v) & m);
+	while (s.hkey[i] != NONE) i = (i + 1) & m;
+	s.hkey[i] = v; s.hval[i] = t;
+}
+
+PV_DEV u32 bfs_kahn_sort(const GraphView &g, u32 a_v, u32 a_fwd, u32 z_v, u32 z_fwd, const BfsScratch &s, u32 *out /*[capV]*/) {
+	for (u32 i = 0; i < s.hcap; i++) s.hkey[i] = NONE;
+	u32 n = 0, ne = 0, qh = 0;
+	s.tv[n] = (a_v << 1) | (a_fwd ? 0u : 1u); bfs_put(s, a_v, 0); n = 1;
+	const u32 endKey = (z_v << 1) | (z_fwd ? 0u : 1u);
+	while (qh < n) {
+		u32 t = qh++; u32 cur = s.tv[t];
+		s.estart[t] = ne;
+		if (n - qh > MAX_UNBLOCK_CTR) continue;
+		u32 v = cur >> 1; bool fwd = !(cur & 1u);
+		u32 port = 2 * v + (fwd ? 1u : 0u);       // OUT end: right side when forward
+		for (u32 k = g.adjOff[port], ke = g.adjOff[port + 1]; k < ke; k++) {
+			u32 q = g.adjNbr[k]; u32 w = q >> 1;
+			u32 nb = (w << 1) | ((q & 1u) ? 1u : 0u);   // entering by the left side = forward
+			u32 tw = bfs_find(s, n, w);
+			if (tw != NONE) {
+				if (ne >= s.capE) return NONE;
+				u32 to = s.tv[tw] == nb ? tw : 0u;     // parent_map[] default-inserts tree vertex 0 (graph.cpp:130-136)
+				s.eto[ne++] = to << 1;
+				continue;
+			}
+			if (cur == endKey) continue;
+			if (n >= s.capV || ne >= s.capE) return NONE;
+			s.tv[n] = nb; bfs_put(s, w, n);
+			s.eto[ne++] = (n << 1) | 1u;
+			n++;
+		}
+	}
+	for (u32 t = qh; t <= n; t++) s.estart[t] = ne;   // (qh == n here) closes the last range
+	// Kahn
+	for (u32 t = 0; t < n; t++) s.deg[t] = 0;
+	for (u32 t = 0; t < n; t++)
+		for (u32 e = s.estart[t]; e < s.estart[t + 1]; e++) {
+			u32 x = s.eto[e]; u32 to = x >> 1;
+			if ((x & 1u) || to != t) s.deg[to]++;
+		}
+	// done flags live in the top bit of deg
+	const u32 DONE = 0x80000000u;
+	u32 head = 0, tail = 0;
+	s.order[tail++] = 0; s.deg[0] |= DONE;
+	while (head < tail) {
+		u32 cur = s.order[head++];
+		for (u32 e = s.estart[cur]; e < s.estart[cur + 1]; e++) {
+			u32 x = s.eto[e]; u32 u = x >> 1;
+			if (!(x & 1u) && u == cur) continue;
+			if (s.deg[u] & DONE) continue;
+			s.deg[u]--;
+			if (s.deg[u] > 0) continue;
+			s.order[tail++] = u; s.deg[u] |= DONE;
+		}
+	}
+	if (tail != n) return 0;
+	for (u32 k = 0; k < n; k++) out[k] = s.tv[s.order[k]] >> 1;
+	return n;
+}
+
+// ---------------------------------------------------------------------------------------------
+// results
+// ---------------------------------------------------------------------------------------------
+struct CallIn {            // PVST forest, flubbles of all components concatenated (host arrays)
+	u32 nFl = 0;
+	const u32 *a_v = nullptr, *z_v = nullptr; const u8 *a_fwd = nullptr, *z_fwd = nullptr;
+	const u32 *parent = nullptr;   // PVST idx inside the component (0 = dummy root; flubble k of the component is k+1)
+	const u32 *flBase = nullptr;   // per flubble: index of the first flubble of its component
+	u32 nRefs = 0; const u32 *refs = nullptr;   // ascending path ids to call against
+	const u8 *excluded = nullptr;  // optional: 1 = never selected (sub-flubble clan or below one, color.cpp:117-125)
+};
+
+struct CallOut {
+	// regions (RoVs) in enumeration order: ascending (component file, PVST vertex idx), >= 3 sorted vertices
+	std::vector<u32> rov_fl, rov_J, rov_comp; std::vector<u8> rov_tangled;
+	// records: grouped per (region, ref) in context order, INS / SUB / DEL
+	std::vector<u32> rec_rov, rec_ref, rec_cxtL, rec_cxtR, rec_vt, rec_pos, rec_refStart, rec_refLen, rec_grpOff;
+	std::vector<u64> rec_gtOff;
+	std::vector<u32> grp_hap, grp_start, grp_len, grp_count;   // start = step index inside the path
+	std::vector<u16> gt;           // per record: one code per path of the region's component (0 ref, i alt group, 0xFFFF missing)
+	u64 n_called = 0, n_too_small = 0, n_sort_failed = 0, n_tangled = 0, n_pin_pairs = 0, n_hard_errors = 0, n_chunks = 0, n_big_bfs = 0, max_J = 0;
+};
+enum { VT_DEL = 0, VT_INS = 1, VT_SUB = 2, VT_SUBR = 3 };
+
+struct CallOpts { u64 cell_budget = 1ull << 30; };
+
+struct RovView {
+	const u32 *rovOff, *rovVerts, *rovComp, *rowBase; const u64 *matBase;
+	const u64 *hkey; const u32 *hval; u64 hmask;
+	u32 R; u32 uniformNh; u32 rShift;   // chunk-local region r is global region r + rShift (the hash is keyed globally)
+	PV_DEV u32 J(u32 r) const { return rovOff[r + 1] - rovOff[r]; }
+	PV_DEV u32 find(u32 r, u32 v) const {   // column of vertex v in region r, or NONE
+		u32 a = rovOff[r], n = rovOff[r + 1] - a;
+		if (n <= 16) { for (u32 j = 0; j < n; j++) if (rovVerts[a + j] == v) return j; return NONE; }
+		u64 key = ((u64)(r + rShift) << 32) | v; u64 i = splitmix64(key) & hmask;
+		while (true) { u64 k = hkey[i]; if (k == key) return hval[i]; if (k == ~0ull) return NONE; i = (i + 1) & hmask; }
+	}
+	PV_DEV u32 row2rov(u32 row) const { return uniformNh ? row / uniformNh : ub_u32(rowBase, 0, R + 1, row) - 1; }
+};
+
+struct Lap { u32 lo, hi; };   // global step range [lo, hi)
+
+// hap_sl_from_lap (overlay.cpp:189-246): [first start .. last end] of the context vertices inside a lap
+PV_DEV bool slice_bounds(const GraphView &g, u32 lv, u32 rv, Lap lap, u32 &start, u32 &len) {
+	u32 lf = g.occ_first(lv, lap.lo, lap.hi), rf = g.occ_first(rv, lap.lo, lap.hi);
+	if (lf == NONE || rf == NONE) return false;
+	u32 end;
+	if (lf > rf) { start = rf; end = g.occ_last(lv, lap.lo, lap.hi); }
+	else { start = lf; end = g.occ_last(rv, lap.lo, lap.hi); }
+	len = end - start + 1;
+	return true;
+}
+PV_DEV bool walk_equal(const u32 *steps, u32 a, u32 b, u32 len) {
+	for (u32 i = 0; i < len; i++) if (steps[a + i] != steps[b + i]) return false;
+	return true;
+}
+PV_DEV bool walk_revcomp(const u32 *steps, u32 a, u32 b, u32 len) {   // is_inv_local (overlay.cpp:167-187)
+	for (u32 i = 0; i < len; i++) if (steps[a + i] != (steps[b + len - 1 - i] ^ 1u)) return false;
+	return true;
+}
+// std::vector<id_or_t> operator< (types.cpp:112-120): packed steps compare like (v_id, forward < reverse)
+PV_DEV int walk_cmp(const u32 *steps, u32 a, u32 la, u32 b, u32 lb) {
+	u32 n = la < lb ? la : lb;
+	for (u32 i = 0; i < n; i++) { u32 x = steps[a + i], y = steps[b + i]; if (x != y) return x < y ? -1 : 1; }
+	return la == lb ? 0 : (la < lb ? -1 : 1);
+}
+
+// per-chunk working set shared by the overlay kernels
+struct ChunkView {
+	GraphView g; RovView rv;
+	u16 *mat; u32 *lapStart, *lapLen, *tangled, *hasData, *errs;
+	PV_DEV Lap lap(u32 row) const { u32 s = lapStart[row]; return Lap{s, s + lapLen[row]}; }
+};
+struct CandView { u32 *cL, *cR, *cStart, *cLen, *cRS, *cRL, *cHap, *cCls, *cHead, *gCount, *hsort; };
+
+// comp_bounds + is_inverted over one (region, ref path, other path) pair (overlay.cpp:84-149); with
+// fill = true also gen_cxt, the two hap slices and the classification of every context
+// (overlay.cpp:307-327,189-246,462-530).  Returns the number of contexts.
+PV_DEV u32 scan_pair(const ChunkView &cv, u32 refLocal, u32 k, u32 row, bool fill, const CandView &cd, u32 off) {
+	const RovView &rv = cv.rv; const GraphView &g = cv.g;
+	u32 r = rv.row2rov(row); u32 i = row - rv.rowBase[r];
+	if (i == refLocal || cv.tangled[r]) return 0;
+	if (k > 0 && !cv.hasData[r]) return 0;     // comp_exps returned after the first ref (overlay.cpp:531-532)
+	u32 J = rv.J(r);
+	const u16 *rr = cv.mat + rv.matBase[r] + (u64)refLocal * J, *ar = cv.mat + rv.matBase[r] + (u64)i * J;
+	bool empty = true, inv = true; u32 cnt = 0; u32 prev = NONE; bool diff = false;
+	for (u32 j = 0; j < J; j++) {
+		u32 x = rr[j], y = ar[j];
+		if (y) empty = false;
+		bool ci = (x == 1 && y == 2) || (x == 2 && y == 1);
+		if (!ci && !(x == 0 && y == 0)) inv = false;
+		bool ok = x > 0 && (x == y || ci);
+		if (ok) {
+			if (prev != NONE && diff) {
+				if (fill) {
+					u32 u = rv.rovVerts[rv.rovOff[r] + prev], v = rv.rovVerts[rv.rovOff[r] + j];
+					Lap rl = cv.lap(rv.rowBase[r] + refLocal), al = cv.lap(row);
+					u32 fu = g.occ_first(u, rl.lo, rl.hi), lv = g.occ_last(v, rl.lo, rl.hi);
+					u32 o = off + cnt; cd.cCls[o] = 3;
+					u32 rs = 0, rn = 0, as = 0, an = 0;
+					if (fu == NONE || lv == NONE || !slice_bounds(g, u, v, rl, rs, rn) || !slice_bounds(g, u, v, al, as, an)) atomic_add(cv.errs + 0, 1u);   // the reference exits / crashes here
+					else if (rn == an && walk_revcomp(g.steps, rs, as, rn)) atomic_add(cv.errs + 1, 1u);   // inversion pin pair (SNE)
+					else if (rn == an && walk_equal(g.steps, rs, as, rn)) { }
+					else {
+						cd.cL[o] = g.steps[fu]; cd.cR[o] = g.steps[lv]; cd.cStart[o] = as; cd.cLen[o] = an; cd.cRS[o] = rs; cd.cRL[o] = rn; cd.cHap[o] = i;
+						cd.cCls[o] = an == rn ? 1u : (an > rn ? 0u : 2u);   // 0 INS, 1 SUB, 2 DEL (emission order, vcf.cpp:253-266)
+					}
+				}
+				cnt++;
+			}
+			prev = j; diff = false;
+		} else if (x != y) diff = true;
+	}
+	if (empty) return 0;
+	if (inv) { if (!fill) atomic_add(cv.errs + 1, 1u); return 0; }
+	return cnt;
+}
+
+// order of the reference's nested std::maps: context (l, r), then INS < SUB < DEL, then the walk
+PV_DEV bool head_less(const u32 *steps, const CandView &cd, u32 a, u32 b) {
+	if (cd.cL[a] != cd.cL[b]) return cd.cL[a] < cd.cL[b];
+	if (cd.cR[a] != cd.cR[b]) return cd.cR[a] < cd.cR[b];
+	if (cd.cCls[a] != cd.cCls[b]) return cd.cCls[a] < cd.cCls[b];
+	return walk_cmp(steps, cd.cStart[a], cd.cLen[a], cd.cStart[b], cd.cLen[b]) < 0;
+}
+PV_DEV bool same_record(const CandView &cd, u32 a, u32 b) { return cd.cL[a] == cd.cL[b] && cd.cR[a] == cd.cR[b] && cd.cCls[a] == cd.cCls[b]; }
+
+PV_DEV void sift_down(const u32 *steps, const CandView &cd, u32 *a, u32 root, u32 end) {
+	while (2 * root + 1 < end) {
+		u32 ch = 2 * root + 1;
+		if (ch + 1 < end && head_less(steps, cd, a[ch], a[ch + 1])) ch++;
+		if (!head_less(steps, cd, a[root], a[ch])) return;
+		u32 t = a[root]; a[root] = a[ch]; a[ch] = t; root = ch;
+	}
+}
+
+inline void call_device(Ctx &c, const DevGraph &G, const CallIn &in, const CallOpts &opt, CallOut &out) {
+	out = CallOut();
+	out.rec_grpOff.push_back(0); out.rec_gtOff.push_back(0);
+	const u32 nFl = in.nFl, nRefs = in.nRefs, H = G.H;
+	if (nFl == 0 || nRefs == 0 || H == 0) return;
+	const GraphView g = view(G);
+
+	// ------------------------------------------------------------------ C1: region selection
+	Buf<u32> fa(c, nFl), fz(c, nFl), fpar(c, nFl), fbase(c, nFl), refs(c, nRefs), colored(c, nFl), kid(c, nFl), called(c, nFl);
+	{
+		std::vector<u32> ha(nFl), hz(nFl);
+		for (u32 i = 0; i < nFl; i++) { ha[i] = (in.a_v[i] << 1) | (in.a_fwd[i] ? 0u : 1u); hz[i] = (in.z_v[i] << 1) | (in.z_fwd[i] ? 0u : 1u); }
+		c.h2d(fa.p, ha.data(), (size_t)nFl * 4); c.h2d(fz.p, hz.data(), (size_t)nFl * 4);
+		c.h2d(fpar.p, in.parent, (size_t)nFl * 4); c.h2d(fbase.p, in.flBase, (size_t)nFl * 4); c.h2d(refs.p, in.refs, (size_t)nRefs * 4);
+		if (in.excluded) for (u32 i = 0; i < nFl; i++) if (in.excluded[i]) ha[i] = NONE;
+		if (in.excluded) c.h2d(fa.p, ha.data(), (size_t)nFl * 4);
+		c.sync();   // the staging vectors die here
+	}
+	const u32 *fa_ = fa.p, *fz_ = fz.p, *fpar_ = fpar.p, *fbase_ = fbase.p, *refs_ = refs.p;
+	u32 *colored_ = colored.p, *kid_ = kid.p, *called_ = called.p;
+	kid.zero();
+	parallel_for<C_color>(c, nFl, PV_LAMBDA(size_t f) {   // color.cpp:15-30
+		if (fa_[f] == NONE) { colored_[f] = 0; return; }
+		u32 a = fa_[f] >> 1, z = fz_[f] >> 1; u32 ok = 1;
+		for (u32 k = 0; k < nRefs && ok; k++) { u32 h = refs_[k]; if (!g.has_hap(a, h) || !g.has_hap(z, h)) ok = 0; }
+		colored_[f] = ok;
+	});
+	parallel_for<C_child>(c, nFl, PV_LAMBDA(size_t f) { u32 p = fpar_[f]; if (colored_[f] && p != 0) kid_[fbase_[f] + p - 1] = 1; });
+	parallel_for<C_child>(c, nFl, PV_LAMBDA(size_t f) { called_[f] = (colored_[f] && !kid_[f]) ? 1u : 0u; });   // color.cpp:141-148
+	Buf<u32> rov0;
+	const u32 R0 = compact_flags(c, called.p, nFl, rov0);
+	out.n_called = R0;
+	if (R0 == 0) return;
+
+	// ------------------------------------------------------------------ C2: vertex order per region
+	// tier 0: thread-private scratch; overflowing regions retry with 16x larger slices of a global arena
+	const u32 T0 = 12;
+	Buf<u32> J0(c, R0), vtmp(c, (size_t)R0 * T0);
+	u32 *J0_ = J0.p, *vtmp_ = vtmp.p; const u32 *rov0_ = rov0.p;
+	parallel_for<C_bfs>(c, R0, PV_LAMBDA(size_t r) {
+		u32 tv[12], es[13], et[32], dg[12], od[12], ov[12];
+		BfsScratch s{12, 32, tv, es, et, dg, od, nullptr, nullptr, 0};
+		u32 f = rov0_[r];
+		u32 n = bfs_kahn_sort(g, fa_[f] >> 1, !(fa_[f] & 1u), fz_[f] >> 1, !(fz_[f] & 1u), s, ov);
+		J0_[r] = n;
+		if (n != NONE) for (u32 k = 0; k < n; k++) vtmp_[r * 12 + k] = ov[k];
+	});
+	std::vector<u32> hJ = J0.to_host();
+	struct BigRes { u32 r; std::vector<u32> verts; };
+	std::vector<BigRes> big;
+	{
+		std::vector<u32> todo;
+		for (u32 r = 0; r < R0; r++) if (hJ[r] == NONE) todo.push_back(r);
+		u64 capV64 = 256;
+		while (!todo.empty()) {
+			const bool last = capV64 >= (u64)G.V;
+			const u32 capV = (u32)std::min<u64>(capV64, (u64)G.V + 1);
+			const u32 capE = (u32)std::min<u64>(capV64 * 4, 2 * G.E + 1);
+			u32 hcap = 1; while (hcap < 2 * capV) hcap <<= 1;
+			const u64 per = (u64)capV * 5 + 1 + capE + 2ull * hcap;
+			const u32 slice = (u32)std::max<u64>(1, std::min<u64>(todo.size(), (1ull << 28) / per));
+			std::vector<u32> next;
+			for (size_t b0 = 0; b0 < todo.size(); b0 += slice) {
+				const u32 nb = (u32)std::min<size_t>(slice, todo.size() - b0);
+				Buf<u32> list(c, nb), arena(c, (size_t)nb * per), res(c, nb);
+				c.h2d(list.p, todo.data() + b0, (size_t)nb * 4);
+				u32 *arena_ = arena.p, *res_ = res.p; const u32 *list_ = list.p;
+				parallel_for<C_bfs>(c, nb, PV_LAMBDA(size_t i) {
+					u32 *base = arena_ + i * per;
+					const size_t cv = capV, ce = capE;
+					BfsScratch s{capV, capE, base, base + cv, base + 2 * cv + 1, base + 2 * cv + 1 + ce, base + 3 * cv + 1 + ce,
+						     base + 5 * cv + 1 + ce, base + 5 * cv + 1 + ce + hcap, hcap};
+					u32 f = rov0_[list_[i]];
+					res_[i] = bfs_kahn_sort(g, fa_[f] >> 1, !(fa_[f] & 1u), fz_[f] >> 1, !(fz_[f] & 1u), s, base + 4 * cv + 1 + ce);
+				});
+				std::vector<u32> hres = res.to_host();
+				for (u32 i = 0; i < nb; i++) {
+					u32 r = todo[b0 + i];
+					if (hres[i] == NONE) { next.push_back(r); continue; }
+					BigRes br; br.r = r; br.verts.resize(hres[i]);
+					if (hres[i]) c.d2h(br.verts.data(), arena.p + (size_t)i * per + 4 * (size_t)capV + 1 + capE, (size_t)hres[i] * 4);
+					hJ[r] = hres[i]; out.n_big_bfs++;
+					big.push_back(std::move(br));
+				}
+			}
+			if (!next.empty() && last) throw std::runtime_error("call: region BFS overflow at full-graph capacity");
+			todo.swap(next);
+			capV64 *= 16;
+		}
+	}
+	// keep regions with >= 3 sorted vertices (rov.cpp:208-212); a failed sort (0) needs the reference's
+	// haplotype-lap fallback order (graph.cpp:194-395), which is not on the device yet -> counted, skipped
+	std::vector<u32> keep, hOff{0};
+	for (u32 r = 0; r < R0; r++) {
+		if (hJ[r] == 0) { out.n_sort_failed++; continue; }
+		if (hJ[r] < 3) { out.n_too_small++; continue; }
+		keep.push_back(r); hOff.push_back(hOff.back() + hJ[r]);
+	}
+	const u32 R = (u32)keep.size();
+	if (R == 0) return;
+	const u32 sumJ = hOff.back();
+	Buf<u32> rovOff(c, (size_t)R + 1), rovVerts(c, sumJ), rovSrc(c, R), rovFl(c, R), rovComp(c, R);
+	c.h2d(rovOff.p, hOff.data(), ((size_t)R + 1) * 4); c.h2d(rovSrc.p, keep.data(), (size_t)R * 4);
+	u32 *rovVerts_ = rovVerts.p, *rovFl_ = rovFl.p, *rovComp_ = rovComp.p; const u32 *rovOff_ = rovOff.p, *rovSrc_ = rovSrc.p;
+	parallel_for<C_gather>(c, R, PV_LAMBDA(size_t r) {
+		u32 s = rovSrc_[r]; u32 n = J0_[s]; u32 o = rovOff_[r];
+		rovFl_[r] = rov0_[s];
+		if (n != NONE) for (u32 k = 0; k < n; k++) rovVerts_[o + k] = vtmp_[s * 12 + k];
+		// component of the region = component of any path through its start boundary (a called region is
+		// touched by every reference path)
+		u32 a = fa_[rov0_[s]] >> 1;
+		rovComp_[r] = g.pathComp[g.vsHap[g.vsOff[a]]];
+	});
+	if (!big.empty()) {
+		std::vector<u32> pos(R0, NONE);
+		for (u32 r = 0; r < R; r++) pos[keep[r]] = r;
+		for (auto &b : big) if (pos[b.r] != NONE) c.h2d(rovVerts.p + hOff[pos[b.r]], b.verts.data(), b.verts.size() * 4);
+		c.sync();
+	}
+	out.rov_fl = rovFl.to_host(); out.rov_comp = rovComp.to_host();
+	out.rov_J.resize(R); for (u32 r = 0; r < R; r++) { out.rov_J[r] = hOff[r + 1] - hOff[r]; if (out.rov_J[r] > out.max_J) out.max_J = out.rov_J[r]; }
+	out.rov_tangled.assign(R, 0);
+
+	// hash (region, vertex) -> column for regions with more than 16 vertices
+	u64 bigJ = 0; for (u32 r = 0; r < R; r++) if (out.rov_J[r] > 16) bigJ += out.rov_J[r];
+	u64 hsize = 2; while (hsize < 2 * bigJ + 2) hsize <<= 1;
+	Buf<u64> hkey(c, hsize); Buf<u32> hval(c, hsize);
+	hkey.fill_ff();
+	if (bigJ) {
+		u64 *hkey_ = hkey.p; u32 *hval_ = hval.p; const u64 hmask = hsize - 1;
+		parallel_for<C_hash>(c, sumJ, PV_LAMBDA(size_t x) {
+			u32 r = ub_u32(rovOff_, 0, R + 1, (u32)x) - 1;
+			if (rovOff_[r + 1] - rovOff_[r] <= 16) return;
+			u64 key = ((u64)r << 32) | rovVerts_[x]; u64 i = splitmix64(key) & hmask;
+			while (atomic_cas64(hkey_ + i, ~0ull, key) != ~0ull) i = (i + 1) & hmask;
+			hval_[i] = (u32)x - rovOff_[r];
+		});
+	}
+
+	// ------------------------------------------------------------------ chunks of regions bounded by matrix cells
+	std::vector<u32> nhOf(R);
+	bool uniform = true;
+	for (u32 r = 0; r < R; r++) { u32 k = out.rov_comp[r]; nhOf[r] = G.cpOff[k + 1] - G.cpOff[k]; if (nhOf[r] != nhOf[0]) uniform = false; }
+
+	for (u32 r0 = 0; r0 < R;) {
+		u64 cells = 0, rows = 0; u32 r1 = r0;
+		while (r1 < R) {
+			u64 cc = (u64)nhOf[r1] * out.rov_J[r1];
+			if (r1 > r0 && (cells + cc > opt.cell_budget || rows + nhOf[r1] > 0x7FFFFFF0ull)) break;
+			cells += cc; rows += nhOf[r1]; r1++;
+		}
+		const u32 Rc = r1 - r0; const u32 nRows = (u32)rows;
+		out.n_chunks++;
+		std::vector<u32> hRow(Rc + 1, 0); std::vector<u64> hMat(Rc + 1, 0);
+		for (u32 i = 0; i < Rc; i++) { hRow[i + 1] = hRow[i] + nhOf[r0 + i]; hMat[i + 1] = hMat[i] + (u64)nhOf[r0 + i] * out.rov_J[r0 + i]; }
+		Buf<u32> rowBase(c, (size_t)Rc + 1); Buf<u64> matBase(c, (size_t)Rc + 1);
+		c.h2d(rowBase.p, hRow.data(), ((size_t)Rc + 1) * 4); c.h2d(matBase.p, hMat.data(), ((size_t)Rc + 1) * 8);
+		c.sync();
+		Buf<u16> mat(c, cells ? cells : 1);
+		Buf<u32> lapStart(c, nRows ? nRows : 1), lapLen(c, nRows ? nRows : 1), tangled(c, Rc), hasData(c, Rc), errs(c, 4);
+		c.memset0(mat.p, cells * 2); lapStart.fill_ff(); tangled.zero(); hasData.zero(); errs.zero();
+		// rv.rovOff is shifted to the chunk but still indexes the global vertex array
+		const RovView rv{rovOff.p + r0, rovVerts.p, rovComp.p + r0, rowBase.p, matBase.p, hkey.p, hval.p, hsize - 1, Rc, uniform ? nhOf[0] : 0u, r0};
+		const ChunkView cv{g, rv, mat.p, lapStart.p, lapLen.p, tangled.p, hasData.p, errs.p};
+		// ---- C3: depth matrix (allele.hpp:804-862), one thread per (region, column)
+		const u32 colBase = hOff[r0]; const u32 nCols = hOff[r1] - hOff[r0];
+		parallel_for<C_matfill>(c, nCols, PV_LAMBDA(size_t x) {
+			u32 r = ub_u32(rv.rovOff, 0, Rc + 1, colBase + (u32)x) - 1;
+			u32 J = rv.J(r); u32 j = colBase + (u32)x - rv.rovOff[r];
+			u32 v = rv.rovVerts[colBase + x];
+			u32 comp = rv.rovComp[r];
+			u32 e = g.vsOff[v], ee = g.vsOff[v + 1];
+			while (e < ee) {
+				u32 h = g.vsHap[e]; u32 first = g.vsStep[e]; u32 cnt = 1;
+				while (e + cnt < ee && g.vsHap[e + cnt] == h) cnt++;
+				e += cnt;
+				if (g.pathComp[h] != comp) continue;   // cannot happen for a connected walk; keeps indexing safe
+				u32 i = g.hapLocal[h];
+				if (cnt > 0xFFFEu) { atomic_add(cv.errs + 2, 1u); cnt = 0xFFFEu; }
+				u32 code = cnt == 1 ? ((g.steps[first] & 1u) ? 2u : 1u) : cnt;
+				cv.mat[rv.matBase[r] + (u64)i * J + j] = (u16)code;
+				atomic_min(cv.lapStart + rv.rowBase[r] + i, first);
+				if (cnt > 1 && (j == 0 || j == J - 1)) cv.tangled[r] = 1;
+			}
+		});
+		// ---- C4: lap 0 of every (region, path): the first run of consecutive steps on region vertices (untangle.cpp:29-103)
+		parallel_for<C_lap>(c, nRows, PV_LAMBDA(size_t row) {
+			u32 s = cv.lapStart[row];
+			if (s == NONE) { cv.lapLen[row] = 0; return; }
+			u32 r = rv.row2rov((u32)row);
+			u32 hh = ub_u32(g.stepOff, 0, g.H + 1, s) - 1;
+			u32 end = g.stepOff[hh + 1];
+			u32 len = 1;
+			while (s + len < end && rv.find(r, g.steps[s + len] >> 1) != NONE) len++;
+			cv.lapLen[row] = len;
+		});
+		{
+			std::vector<u32> hT = tangled.to_host();
+			for (u32 i = 0; i < Rc; i++) if (hT[i]) { out.rov_tangled[r0 + i] = 1; out.n_tangled++; }
+		}
+
+		for (u32 k = 0; k < nRefs; k++) {
+			const u32 refH = in.refs[k];
+			const u32 refLocal = G.hapLocal[refH];
+			// ---- C5a: contexts per (region, path) pair
+			Buf<u32> pairCnt(c, (size_t)nRows + 1), candOff(c, (size_t)nRows + 1);
+			u32 *pairCnt_ = pairCnt.p; const u32 *candOff_ = candOff.p;
+			parallel_for<C_pair_count>(c, (size_t)nRows + 1, PV_LAMBDA(size_t row) {
+				pairCnt_[row] = row < nRows ? scan_pair(cv, refLocal, k, (u32)row, false, CandView{}, 0) : 0u;
+			});
+			exclusive_scan(c, pairCnt.p, candOff.p, (size_t)nRows + 1, OpAddU32(), 0u);
+			const u32 nCand = candOff.read(nRows);
+			const size_t nC1 = nCand ? nCand : 1;
+			Buf<u32> cL(c, nC1), cR(c, nC1), cStart(c, nC1), cLen(c, nC1), cRS(c, nC1), cRL(c, nC1), cHap(c, nC1), cCls(c, nC1), cHead(c, nC1), gCount(c, nC1), hsort(c, nC1);
+			const CandView cd{cL.p, cR.p, cStart.p, cLen.p, cRS.p, cRL.p, cHap.p, cCls.p, cHead.p, gCount.p, hsort.p};
+			// ---- C5b: slices per context, classification
+			if (nCand) parallel_for<C_pair_fill>(c, nRows, PV_LAMBDA(size_t row) {
+				if (candOff_[row + 1] == candOff_[row]) return;
+				scan_pair(cv, refLocal, k, (u32)row, true, cd, candOff_[row]);
+			});
+			// ---- C6a: group alt slices by (context, class, walk) per region, order groups like the reference's std::maps
+			Buf<u32> recCnt(c, (size_t)Rc + 1), grpCnt(c, (size_t)Rc + 1), recOff(c, (size_t)Rc + 1), grpOff(c, (size_t)Rc + 1);
+			u32 *recCnt_ = recCnt.p, *grpCnt_ = grpCnt.p;
+			parallel_for<C_group>(c, (size_t)Rc + 1, PV_LAMBDA(size_t rr_) {
+				if (rr_ >= Rc) { recCnt_[rr_] = 0; grpCnt_[rr_] = 0; return; }
+				u32 r = (u32)rr_;
+				u32 b = candOff_[rv.rowBase[r]], e = candOff_[rv.rowBase[r + 1]];
+				u32 *a = cd.hsort + b; u32 nh = 0;
+				for (u32 x = b; x < e; x++) {
+					if (cd.cCls[x] == 3) continue;
+					u32 found = NONE;
+					for (u32 t = 0; t < nh; t++) {
+						u32 y = a[t];
+						if (same_record(cd, x, y) && cd.cLen[y] == cd.cLen[x] && walk_equal(g.steps, cd.cStart[y], cd.cStart[x], cd.cLen[x])) { found = y; break; }
+					}
+					if (found == NONE) { a[nh++] = x; cd.cHead[x] = x; cd.gCount[x] = 1; }
+					else { cd.cHead[x] = found; cd.gCount[found]++; }
+				}
+				for (u32 st = nh / 2; st-- > 0;) sift_down(g.steps, cd, a, st, nh);
+				for (u32 end = nh; end-- > 1;) { u32 t = a[0]; a[0] = a[end]; a[end] = t; sift_down(g.steps, cd, a, 0, end); }
+				u32 nrec = 0;
+				for (u32 t = 0; t < nh; t++) if (t == 0 || !same_record(cd, a[t - 1], a[t])) nrec++;
+				recCnt_[r] = nrec; grpCnt_[r] = nh;
+				if (k == 0) cv.hasData[r] = nh ? 1u : 0u;
+				else if (nh == 0 && cv.hasData[r]) atomic_add(cv.errs + 0, 1u);   // std::map::at throws in the reference
+			});
+			exclusive_scan(c, recCnt.p, recOff.p, (size_t)Rc + 1, OpAddU32(), 0u);
+			exclusive_scan(c, grpCnt.p, grpOff.p, (size_t)Rc + 1, OpAddU32(), 0u);
+			const u32 nRec = recOff.read(Rc), nGrp = grpOff.read(Rc);
+			if (nRec == 0) continue;
+			// ---- C6b: records + groups
+			Buf<u32> oRov(c, nRec), oL(c, nRec), oR(c, nRec), oVt(c, nRec), oPos(c, nRec), oRS(c, nRec), oRL(c, nRec), oGrp(c, (size_t)nRec + 1);
+			Buf<u32> gHap(c, nGrp), gStart(c, nGrp), gLen(c, nGrp), gCnt(c, nGrp), headRec(c, nCand), headOrd(c, nCand);
+			Buf<u64> gtOff(c, (size_t)nRec + 1), recNh(c, (size_t)nRec + 1);
+			u32 *oRov_ = oRov.p, *oL_ = oL.p, *oR_ = oR.p, *oVt_ = oVt.p, *oPos_ = oPos.p, *oRS_ = oRS.p, *oRL_ = oRL.p, *oGrp_ = oGrp.p;
+			u32 *gHap_ = gHap.p, *gStart_ = gStart.p, *gLen_ = gLen.p, *gCnt_ = gCnt.p, *headRec_ = headRec.p, *headOrd_ = headOrd.p;
+			u64 *gtOff_ = gtOff.p, *recNh_ = recNh.p; const u32 *recOff_ = recOff.p, *grpOff_ = grpOff.p;
+			parallel_for<C_emit>(c, Rc, PV_LAMBDA(size_t rr_) {
+				u32 r = (u32)rr_;
+				u32 nh = grpOff_[r + 1] - grpOff_[r];
+				if (!nh) return;
+				const u32 *a = cd.hsort + candOff_[rv.rowBase[r]];
+				u32 rec = recOff_[r], gi = grpOff_[r]; u32 ord = 0;
+				u32 nhaps = rv.rowBase[r + 1] - rv.rowBase[r];
+				for (u32 t = 0; t < nh; t++) {
+					u32 y = a[t];
+					if (t == 0 || !same_record(cd, a[t - 1], y)) {
+						if (t) rec++;
+						ord = 0;
+						u32 cls = cd.cCls[y];
+						oRov_[rec] = r + rv.rShift; oL_[rec] = cd.cL[y]; oR_[rec] = cd.cR[y];
+						oVt_[rec] = cls == 0 ? (u32)VT_INS : (cls == 1 ? (u32)VT_SUB : (u32)VT_DEL);
+						oRS_[rec] = cd.cRS[y]; oRL_[rec] = cd.cRL[y];
+						u32 l = g.loci[cd.cRS[y] + 1];                       // comp_pos (allele.hpp:161-179)
+						oPos_[rec] = cls == 1 ? l : l - 1;
+						oGrp_[rec] = gi; recNh_[rec] = nhaps;
+					}
+					ord++;
+					headRec_[y] = rec; headOrd_[y] = ord;
+					u32 hh = g.cpList[g.cpOff[rv.rovComp[r]] + cd.cHap[y]];
+					gHap_[gi] = hh; gStart_[gi] = cd.cStart[y] - g.stepOff[hh]; gLen_[gi] = cd.cLen[y]; gCnt_[gi] = cd.gCount[y];
+					gi++;
+				}
+			});
+			c.memset0(recNh.p + nRec, 8);
+			exclusive_scan(c, recNh.p, gtOff.p, (size_t)nRec + 1, OpAddU64(), (u64)0);
+			u64 nGt; c.d2h(&nGt, gtOff.p + nRec, 8);
+			Buf<u16> gt(c, nGt ? nGt : 1);
+			c.memset_ff(gt.p, nGt * 2);
+			u16 *gt_ = gt.p;
+			// ---- C7: genotypes.  Paths equal to the ref over the context columns with an identical slice -> 0 (overlay.cpp:534-580)
+			const u32 uniNh = rv.uniformNh;
+			parallel_for<C_gt_ref>(c, nGt, PV_LAMBDA(size_t x) {
+				u32 rec = uniNh ? (u32)(x / uniNh) : (u32)(ub_u64(gtOff_, 0, (u64)nRec + 1, (u64)x) - 1);
+				u32 i = (u32)(x - gtOff_[rec]);
+				u32 r = oRov_[rec] - rv.rShift; u32 J = rv.J(r);
+				u32 lv = oL_[rec] >> 1, rvx = oR_[rec] >> 1;
+				u32 ju = rv.find(r, lv), jv = rv.find(r, rvx);
+				if (ju > jv) { u32 t = ju; ju = jv; jv = t; }
+				const u16 *rr = cv.mat + rv.matBase[r] + (u64)refLocal * J, *ar = cv.mat + rv.matBase[r] + (u64)i * J;
+				for (u32 j = ju; j <= jv; j++) if (rr[j] != ar[j]) return;
+				u32 row = rv.rowBase[r] + i;
+				if (cv.lapStart[row] == NONE) return;
+				u32 as, an;
+				if (!slice_bounds(g, lv, rvx, cv.lap(row), as, an)) return;
+				if (an != oRL_[rec] || !walk_equal(g.steps, oRS_[rec], as, an)) return;
+				gt_[x] = 0;
+			});
+			parallel_for<C_gt_alt>(c, nCand, PV_LAMBDA(size_t x) {
+				if (cd.cCls[x] == 3) return;
+				u32 hd = cd.cHead[x]; u32 rec = headRec_[hd];
+				gt_[gtOff_[rec] + cd.cHap[x]] = (u16)headOrd_[hd];
+			});
+			// ---- results of this (chunk, ref) to the host
+			auto app = [&](std::vector<u32> &dst, const Buf<u32> &src, u32 n) { size_t o = dst.size(); dst.resize(o + n); c.d2h(dst.data() + o, src.p, (size_t)n * 4); };
+			const u32 grpBase = (u32)out.grp_hap.size(); const u64 gtBase = out.gt.size(); const size_t recBase = out.rec_rov.size();
+			app(out.rec_rov, oRov, nRec); app(out.rec_cxtL, oL, nRec); app(out.rec_cxtR, oR, nRec); app(out.rec_vt, oVt, nRec); app(out.rec_pos, oPos, nRec);
+			app(out.rec_refStart, oRS, nRec); app(out.rec_refLen, oRL, nRec);
+			app(out.grp_hap, gHap, nGrp); app(out.grp_start, gStart, nGrp); app(out.grp_len, gLen, nGrp); app(out.grp_count, gCnt, nGrp);
+			std::vector<u32> hg(nRec); c.d2h(hg.data(), oGrp.p, (size_t)nRec * 4);
+			std::vector<u64> hgt((size_t)nRec + 1); c.d2h(hgt.data(), gtOff.p, ((size_t)nRec + 1) * 8);
+			out.rec_grpOff.pop_back(); out.rec_gtOff.pop_back();
+			for (u32 i = 0; i < nRec; i++) { out.rec_grpOff.push_back(grpBase + hg[i]); out.rec_gtOff.push_back(gtBase + hgt[i]); out.rec_ref.push_back(refH); }
+			out.rec_grpOff.push_back(grpBase + nGrp); out.rec_gtOff.push_back(gtBase + nGt);
+			out.gt.resize(gtBase + nGt); c.d2h(out.gt.data() + gtBase, gt.p, nGt * 2);
+			for (size_t i = recBase; i < out.rec_rov.size(); i++) out.rec_refStart[i] -= G.h_stepOff[refH];
+		}
+		u32 he[4]; c.d2h(he, errs.p, 16);
+		out.n_hard_errors += he[0]; out.n_pin_pairs += he[1];
+		if (he[2]) throw std::runtime_error("call: a path visits one vertex more than 65534 times inside a region (u16 depth cell overflow)");
+		r0 = r1;
+	}
+	c.sync();
+}
+
+} // namespace pv

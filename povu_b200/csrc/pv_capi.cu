@@ -1,6 +1,6 @@
 // povu_b200 -- C ABI (include/povu_b200.h) over the device pipelines.
 #include "../../include/povu_b200.h"
-#include "pv_decompose.cuh"
+#include "pv_engine.hpp"
 
 struct pvgpu_ctx { pv::Ctx c; std::string err; };
 struct pvgpu_flubbles { pv::DecompOut o; };
@@ -102,5 +102,59 @@ void pvgpu_flubbles_copy_components(const pvgpu_flubbles *f, uint32_t *root_v, u
 uint64_t pvgpu_flubbles_stack_size(const pvgpu_flubbles *f) { return f->o.stack_v.size(); }
 void pvgpu_flubbles_copy_stack(const pvgpu_flubbles *f, uint32_t *v, uint32_t *cls, uint32_t *fwd) { cp(v, f->o.stack_v); cp(cls, f->o.stack_class); cp(fwd, f->o.stack_fwd); }
 void pvgpu_flubbles_free(pvgpu_flubbles *f) { delete f; }
+
+/* ---------------------------------------------------------------- sessions */
+struct pvgpu_session { pvgpu_ctx *x; pve::Session s; explicit pvgpu_session(pvgpu_ctx *x_) : x(x_), s(x_->c) {} };
+static char *dup_text(const std::string &t, size_t *len) {
+	char *p = (char *)malloc(t.size() + 1);
+	if (!p) return nullptr;
+	memcpy(p, t.data(), t.size()); p[t.size()] = 0;
+	if (len) *len = t.size();
+	return p;
+}
+#ifndef PV_EMU
+#define PV_SET_DEVICE(x) PV_CUDA_CHECK(cudaSetDevice((x)->c.device))
+#else
+#define PV_SET_DEVICE(x) (void)0
+#endif
+#define PV_TRY(x, body) try { PV_SET_DEVICE(x); body; return 0; } catch (std::exception &e) { (x)->err = e.what(); return 1; }
+
+int pvgpu_session_open(pvgpu_ctx *x, const char *gfa, int labels, int refs, pvgpu_session **out) {
+	if (!x || !gfa || !out) return 1;
+	*out = nullptr;
+	pvgpu_session *s = nullptr;
+	try { PV_SET_DEVICE(x); s = new pvgpu_session(x); s->s.load_gfa(gfa, labels != 0, refs != 0); *out = s; return 0; }
+	catch (std::exception &e) { x->err = e.what(); delete s; return 1; }
+}
+void pvgpu_session_close(pvgpu_session *s) { delete s; }
+void pvgpu_session_sizes(const pvgpu_session *s, uint64_t *v, uint64_t *e, uint64_t *h, uint64_t *st) {
+	if (v) *v = s->s.g.V(); if (e) *e = s->s.g.E(); if (h) *h = s->s.g.H(); if (st) *st = s->s.g.steps.size();
+}
+int pvgpu_session_decompose(pvgpu_session *s) { PV_TRY(s->x, s->s.decompose()) }
+uint64_t pvgpu_session_flubble_count(const pvgpu_session *s) { return s->s.forest.n(); }
+uint32_t pvgpu_session_tree_count(const pvgpu_session *s) { return (uint32_t)s->s.forest.comp_id.size(); }
+uint32_t pvgpu_session_tree_component(const pvgpu_session *s, uint32_t k) { return s->s.forest.comp_id[k]; }
+char *pvgpu_session_pvst_text(const pvgpu_session *s, uint32_t k, size_t *len) {
+	try { return dup_text(s->s.pvst_text(k), len); } catch (std::exception &e) { s->x->err = e.what(); return nullptr; }
+}
+int pvgpu_session_write_pvst(const pvgpu_session *s, const char *dir) { PV_TRY(s->x, s->s.write_pvsts(dir)) }
+int pvgpu_session_read_pvst(pvgpu_session *s, const char *dir) { PV_TRY(s->x, s->s.read_pvsts(dir)) }
+int pvgpu_session_call(pvgpu_session *s, const char *const *prefixes, size_t n) {
+	PV_TRY(s->x, { std::vector<std::string> p; for (size_t i = 0; i < n; i++) p.push_back(prefixes[i]); s->s.set_prefixes(p); s->s.call(); })
+}
+uint64_t pvgpu_session_record_count(const pvgpu_session *s) { return s->s.rec.n(); }
+void pvgpu_session_call_stats(const pvgpu_session *s, uint64_t o[10]) {
+	const pv::CallOut &c = s->s.stats;
+	o[0] = c.n_called; o[1] = s->s.rec.rov_fl.size(); o[2] = c.n_tangled; o[3] = c.n_pin_pairs; o[4] = c.n_sort_failed; o[5] = c.n_hard_errors; o[6] = c.n_chunks; o[7] = c.n_too_small; o[8] = c.max_J; o[9] = c.n_big_bfs;
+}
+char *pvgpu_session_vcf_text(const pvgpu_session *s, size_t chunk, int with_date, const char *prefix, size_t *len) {
+	try {
+		const pve::Session &S = s->s;
+		if (!prefix) return dup_text(S.vcf_header(S.prefixes, with_date != 0) + S.vcf_records(chunk, nullptr), len);
+		std::set<pv::u32> only = pvh::refs_in_sample(S.g, prefix);
+		return dup_text(S.vcf_header({std::string(prefix)}, with_date != 0) + S.vcf_records(chunk, &only), len);
+	} catch (std::exception &e) { s->x->err = e.what(); return nullptr; }
+}
+void pvgpu_free(void *p) { free(p); }
 
 }

@@ -1,0 +1,166 @@
+// povu_b200 -- session layer: one loaded graph on one device, tying the host formats (pv_host.hpp) to
+// the device pipelines (pv_decompose.cuh, pv_call.cuh).  This is what the `povu` CLI clone, the povu_ffi
+// C API and the pvgpu_session_* C ABI all sit on; it mirrors the reference's drivers
+//   do_decompose  /root/reference/app/subcommand/decompose.cpp:94-160
+//   do_call       /root/reference/app/subcommand/call.cpp:71-173
+//   do_gfa2vcf    /root/reference/app/subcommand/gfa2vcf.cpp:18-87
+#pragma once
+#include <dirent.h>
+#include <fstream>
+#include "pv_call.cuh"
+#include "pv_host.hpp"
+
+namespace pve {
+
+using pv::u32; using pv::u64; using pv::u8;
+
+struct Session {
+	pv::Ctx *c = nullptr;
+	pvh::HostGraph g;
+	pvh::GtMeta gm; bool gm_ready = false;
+	pv::Buf<u32> d_ep1, d_ep2;
+	pv::DevGraph dg; bool edges_up = false, paths_up = false;
+	pvh::Forest forest; bool forest_ready = false;
+	pv::DecompOut dec;
+	pvh::Records rec;
+	pv::CallOut stats;   // counters of the last call (vectors moved into rec)
+	std::vector<std::string> prefixes;
+	std::set<u32> ref_ids;
+
+	explicit Session(pv::Ctx &ctx) : c(&ctx) {}
+
+	void load_gfa(const std::string &fp, bool labels, bool refs) { g = pvh::load_gfa(fp, labels, refs); }
+
+	void upload_edges() {
+		if (edges_up) return;
+		const u64 E = g.E();
+		d_ep1 = pv::Buf<u32>(*c, E ? E : 1); d_ep2 = pv::Buf<u32>(*c, E ? E : 1);
+		c->h2d(d_ep1.p, g.ep1.data(), E * 4); c->h2d(d_ep2.p, g.ep2.data(), E * 4);
+		c->sync();
+		edges_up = true;
+	}
+	void upload_paths() {
+		if (paths_up) return;
+		upload_edges();
+		const u32 S = g.stepOff.empty() ? 0 : g.stepOff.back();
+		pv::Buf<u32> st(*c, S ? S : 1), sl(*c, g.V() ? g.V() : 1);
+		c->h2d(st.p, g.steps.data(), (size_t)S * 4); c->h2d(sl.p, g.segLen.data(), (size_t)g.V() * 4);
+		if (g.stepOff.empty()) g.stepOff.assign(1, 0);
+		pv::graph_build(*c, g.V(), g.E(), d_ep1.p, d_ep2.p, g.H(), g.stepOff.data(), st.p, sl.p, dg);
+		paths_up = true;
+	}
+
+	// decompose: flubbles + PVST of every component with >= 3 vertices (decompose.cpp:129-142)
+	void decompose() {
+		upload_edges();
+		pv::DecompOpts opt;
+		pv::decompose_device(*c, g.V(), g.E(), d_ep1.p, d_ep2.p, opt, dec);
+		if (dec.collisions) throw std::runtime_error("cycle-equivalence label collision detected by the exact bracket-set check");
+		forest = pvh::Forest();
+		forest.treeOff.push_back(0);
+		u32 base = 0;
+		for (u32 k = 0; k < dec.comp_nv.size(); k++) {
+			const u32 n = dec.comp_nfl[k];
+			if (dec.comp_nv[k] >= 3) {
+				for (u32 j = 0; j < n; j++) {
+					forest.a_v.push_back(dec.a_v[base + j]); forest.z_v.push_back(dec.z_v[base + j]);
+					forest.a_fwd.push_back(dec.a_fwd[base + j]); forest.z_fwd.push_back(dec.z_fwd[base + j]);
+					forest.parent.push_back(dec.parent[base + j]); forest.height.push_back(dec.depth[base + j]);
+					forest.flBase.push_back(forest.treeOff.back()); forest.family.push_back('F');
+				}
+				forest.comp_id.push_back(k + 1); forest.treeOff.push_back(forest.n());
+			}
+			base += n;
+		}
+		forest_ready = true;
+	}
+
+	std::string pvst_text(u32 tree) const {
+		const u32 b = forest.treeOff[tree], n = forest.treeOff[tree + 1] - b;
+		return pvh::pvst_text(g, forest.a_v.data() + b, forest.a_fwd.data() + b, forest.z_v.data() + b, forest.z_fwd.data() + b, forest.parent.data() + b, n);
+	}
+	void write_pvsts(const std::string &dir) const {
+		for (u32 t = 0; t < forest.comp_id.size(); t++) {
+			std::string fp = dir + "/" + std::to_string(forest.comp_id[t]) + ".pvst";
+			std::ofstream f(fp, std::ios::binary);
+			if (!f) throw std::runtime_error("could not open " + fp + " for writing");
+			std::string s = pvst_text(t);
+			f.write(s.data(), (std::streamsize)s.size());
+		}
+	}
+	// every *.pvst of a directory (call.cpp:36-57).  The reference visits them in directory order
+	// (unspecified); here: ascending component id, so the output is reproducible.
+	void read_pvsts(const std::string &dir) {
+		DIR *d = opendir(dir.c_str());
+		if (!d) throw std::runtime_error("Directory does not exist: " + dir);
+		std::vector<std::pair<u64, std::string>> files;
+		while (struct dirent *e = readdir(d)) {
+			std::string n = e->d_name;
+			if (n.size() > 5 && n.compare(n.size() - 5, 5, ".pvst") == 0) files.push_back({strtoull(n.c_str(), nullptr, 10), n});
+		}
+		closedir(d);
+		if (files.empty()) throw std::runtime_error("Could not find pvst files in " + dir);
+		std::sort(files.begin(), files.end());
+		forest = pvh::Forest();
+		for (auto &f : files) pvh::read_pvst(dir + "/" + f.second, g, (u32)f.first, forest);
+		forest_ready = true;
+	}
+
+	void set_prefixes(const std::vector<std::string> &p) {
+		prefixes = p; ref_ids.clear();
+		for (auto &x : p) for (u32 r : pvh::refs_in_sample(g, x)) ref_ids.insert(r);
+		if (!gm_ready) { gm = pvh::genotype_metadata(g); gm_ready = true; }
+	}
+
+	void call() {
+		if (!forest_ready) throw std::runtime_error("call: no PVST forest (run decompose or read .pvst files first)");
+		upload_paths();
+		rec = pvh::Records();
+		std::vector<u32> refs(ref_ids.begin(), ref_ids.end());
+		// sub-flubble families and everything below them are never selected (color.cpp:117-125)
+		std::vector<u8> excl(forest.n(), 0); bool any_excl = false;
+		{
+			std::vector<u32> ord(forest.n());
+			for (u32 i = 0; i < ord.size(); i++) ord[i] = i;
+			std::stable_sort(ord.begin(), ord.end(), [&](u32 a, u32 b) { return forest.height[a] < forest.height[b]; });
+			for (u32 f : ord) {
+				u32 p = forest.parent[f];
+				if (forest.family[f] != 'F' || (p != 0 && excl[forest.flBase[f] + p - 1])) { excl[f] = 1; any_excl = true; }
+			}
+		}
+		pv::CallIn in;
+		if (any_excl) in.excluded = excl.data();
+		in.nFl = forest.n(); in.a_v = forest.a_v.data(); in.z_v = forest.z_v.data(); in.a_fwd = forest.a_fwd.data(); in.z_fwd = forest.z_fwd.data();
+		in.parent = forest.parent.data(); in.flBase = forest.flBase.data(); in.nRefs = (u32)refs.size(); in.refs = refs.data();
+		pv::CallOpts opt;
+		if (const char *e = getenv("POVU_B200_CELL_BUDGET")) opt.cell_budget = strtoull(e, nullptr, 10);
+		pv::CallOut o;
+		pv::call_device(*c, dg, in, opt, o);
+		rec.rov_fl = std::move(o.rov_fl); rec.rov_comp = std::move(o.rov_comp); rec.rov_tangled = std::move(o.rov_tangled);
+		rec.rec_rov = std::move(o.rec_rov); rec.rec_ref = std::move(o.rec_ref); rec.rec_cxtL = std::move(o.rec_cxtL); rec.rec_cxtR = std::move(o.rec_cxtR);
+		rec.rec_vt = std::move(o.rec_vt); rec.rec_pos = std::move(o.rec_pos); rec.rec_refStart = std::move(o.rec_refStart); rec.rec_refLen = std::move(o.rec_refLen);
+		rec.rec_grpOff = std::move(o.rec_grpOff); rec.rec_gtOff = std::move(o.rec_gtOff);
+		rec.grp_hap = std::move(o.grp_hap); rec.grp_start = std::move(o.grp_start); rec.grp_len = std::move(o.grp_len); rec.grp_count = std::move(o.grp_count);
+		rec.gt = std::move(o.gt); rec.cpOff = dg.cpOff; rec.cpList = dg.cpList;
+		stats = std::move(o);
+	}
+
+	// VCF text: header + contig lines of the selected prefixes + records in the reference's chunk order.
+	// only_refs = nullptr: the combined (stdout) stream; otherwise the records of those ref paths only
+	std::string vcf_header(const std::vector<std::string> &for_prefixes, bool with_date) const {
+		std::string o = pvh::vcf_header_common(with_date);
+		for (auto &p : for_prefixes) for (u32 r : pvh::refs_in_sample(g, p)) o += pvh::vcf_contig_line(g.paths[r]);
+		return o + pvh::vcf_col_header(gm);
+	}
+	std::string vcf_records(size_t chunk_size, const std::set<u32> *only_refs) const {
+		std::string o;
+		std::vector<std::string> slots(gm.nSlots);
+		for (size_t i : pvh::record_order(rec, chunk_size)) {
+			if (only_refs && !only_refs->count(rec.rec_ref[i])) continue;
+			pvh::record_text(g, gm, forest, rec, i, slots, o);
+		}
+		return o;
+	}
+};
+
+} // namespace pve

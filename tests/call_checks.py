@@ -1,0 +1,121 @@
+"""Shared parity checks for the call half (used by test_call_emu.py on CPU and test_call_gpu.py on the
+B200): VCF text produced through the pvgpu_session_* C ABI against (a) the committed outputs of the
+compiled reference (tests/golden/expected) and (b) the CPU oracle (oracle/povu_oracle) on seeded synthetic
+graphs.  Bit-exact (text).  Records of tangled regions and SUBR records are compared only where the
+product implements them (see DESIGN.md "call: coverage")."""
+import os
+import subprocess
+import tempfile
+
+import helpers
+from povu_b200 import api, synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE = os.path.join(ROOT, "oracle", "povu_oracle")
+PREFIX = {"hairpin_inversion_subr": "ref", "LPA": "chm13", "multi_comp": "S001#1#chr1"}
+
+
+def prefix_for(name):
+    return PREFIX.get(name, "S001" if name in helpers.SYNTHETIC else "HG1")
+
+
+def split(text, only_plain):
+    lines = text.splitlines()
+    hdr = [l for l in lines if l.startswith("#") and not l.startswith("##fileDate")]
+    rec = [l for l in lines if not l.startswith("#")]
+    if only_plain:
+        rec = [l for l in rec if "TANGLED=F" in l and "VARTYPE=SUBR" not in l]
+    return hdr, rec
+
+
+def gfa2vcf(pv, path, prefixes, chunk=100, via_pvst_dir=None):
+    s = api.Session(pv, path)
+    s.decompose()
+    if via_pvst_dir is not None:        # decompose -> .pvst files -> call, like `povu decompose` + `povu call`
+        s.write_pvst(via_pvst_dir)
+        s.read_pvst(via_pvst_dir)
+    s.call(prefixes)
+    return s.vcf_text(chunk_size=chunk), s.call_stats(), s
+
+
+def check_golden(pv, name, tmp):
+    got, st, _ = gfa2vcf(pv, helpers.fixture_path(name, tmp), [prefix_for(name)])
+    want = open(os.path.join(helpers.GOLDEN, "expected", name + ".vcf")).read()
+    gh, gr = split(got, False)
+    wh, wr = split(want, True)
+    assert gh == wh, "VCF header differs"
+    assert sorted(gr) == sorted(wr), "VCF records differ"
+    if name not in ("LPA", "hairpin_inversion_subr"):
+        assert got == want, "byte-exact (including record order) on single-forest inputs"
+    assert st["hard_errors"] == 0
+    return st
+
+
+def oracle_vcf(gfa, prefixes, chunk=100):
+    cmd = [ORACLE, "gfa2vcf", "-i", gfa, "-c", str(chunk)]
+    for p in prefixes:
+        cmd += ["-P", p]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-300:]
+    return r.stdout
+
+
+def check_vs_oracle(pv, g, prefixes, tmp, chunk=100, exact_order=True):
+    gfa = os.path.join(tmp, "g.gfa")
+    synth.write_gfa(g, gfa)
+    got, st, _ = gfa2vcf(pv, gfa, prefixes, chunk)
+    want = oracle_vcf(gfa, prefixes, chunk)
+    gh, gr = split(got, False)
+    wh, wr = split(want, True)
+    assert gh == wh
+    if exact_order:
+        assert gr == wr
+    else:
+        assert sorted(gr) == sorted(wr)
+    assert st["hard_errors"] == 0
+    return st
+
+
+def run_all_synthetic(pv, tmp, n_seeds=12):
+    seen_big = 0
+    for s in range(n_seeds):
+        g = synth.nested_bubbles(100 + s, n_top=6 + s % 5, max_depth=2 + s % 4, n_paths=2 + s % 7, shuffle_links=(s % 2 == 1))
+        st = check_vs_oracle(pv, g, ["S001"], tmp, chunk=1 + (s * 7) % 50)
+        seen_big += st["big_bfs"]
+    for s in range(4):
+        g = synth.snp_indel_chain(150 + 40 * s, n_paths=4 + 2 * s, seed=20 + s)
+        check_vs_oracle(pv, g, ["S001"], tmp)
+    # two reference paths at once (-P S001 selects both haplotypes of the sample)
+    g = synth.snp_indel_chain(80, n_paths=6, seed=5)
+    check_vs_oracle(pv, g, ["S001", "S002"], tmp)
+    # several components, paths per component
+    g = synth.concat_components([synth.nested_bubbles(41, n_top=5), synth.snp_indel_chain(30, 4, seed=6), synth.nested_bubbles(43, n_top=7, max_depth=4)])
+    check_vs_oracle(pv, g, ["S001#1#chr1"], tmp)
+    check_vs_oracle(pv, g, ["S001"], tmp)
+    return seen_big
+
+
+def run_deep_regions(pv, tmp):
+    """Few paths over deep nesting: parents are selected with large regions, so the global-arena BFS tiers,
+    the (region, vertex) hash and multi-chunk processing (tiny cell budget) are all exercised."""
+    os.environ["POVU_B200_CELL_BUDGET"] = "64"
+    try:
+        big = 0; mx = 0
+        for s in range(6):
+            g = synth.nested_bubbles(300 + s, n_top=4, max_depth=6, n_paths=2 + s % 2, p_multi=0.6)
+            st = check_vs_oracle(pv, g, ["S001"], tmp)
+            big += st["big_bfs"]; mx = max(mx, st["max_region"])
+            assert st["chunks"] >= 1
+        assert big > 0 and mx > 16, (big, mx)
+    finally:
+        del os.environ["POVU_B200_CELL_BUDGET"]
+
+
+def check_pvst_roundtrip(pv, name, tmp):
+    path = helpers.fixture_path(name, tmp)
+    a, _, s = gfa2vcf(pv, path, [prefix_for(name)])
+    d = tempfile.mkdtemp(dir=tmp)
+    b, _, s2 = gfa2vcf(pv, path, [prefix_for(name)], via_pvst_dir=d)
+    assert a == b
+    files = {int(f[:-5]): open(os.path.join(d, f)).read() for f in os.listdir(d)}
+    assert files == helpers.expected_pvsts(name) == s.pvst_texts()

@@ -1,0 +1,33 @@
+"""GPU parity tests proper for the call half: the sm_100a pipeline through the pvgpu_session_* C ABI
+against the committed outputs of the compiled reference and against the CPU oracle (bit-exact text)."""
+import pytest
+
+import call_checks as cc
+import helpers
+from povu_b200 import api
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name", helpers.POSITIVE + helpers.SYNTHETIC + ["LPA"])
+def test_gpu_call_golden(gpu, name, tmp_path):
+    cc.check_golden(gpu, name, str(tmp_path))
+
+
+def test_gpu_call_synthetic_vs_oracle(gpu, tmp_path):
+    cc.run_all_synthetic(gpu, str(tmp_path), n_seeds=16)
+
+
+def test_gpu_call_deep_regions(gpu, tmp_path):
+    cc.run_deep_regions(gpu, str(tmp_path))
+
+
+@pytest.mark.parametrize("name", ["nested_s1", "multi_comp", "two_ordered_substitutions"])
+def test_gpu_pvst_roundtrip(gpu, name, tmp_path):
+    cc.check_pvst_roundtrip(gpu, name, str(tmp_path))
+
+
+@pytest.mark.parametrize("name", helpers.NEGATIVE)
+def test_gpu_rejects_invalid_gfa(gpu, name):
+    with pytest.raises(RuntimeError, match="Invalid GFA"):
+        api.Session(gpu, helpers.fixture_path(name))
