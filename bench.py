@@ -1,15 +1,20 @@
 #!/usr/bin/env python
-"""bench.py -- povu_b200 hot-path benchmark (contract in the task statement / DESIGN.md "Measurement").
+"""bench.py -- povu_b200 hot-path benchmark (contract: task statement / DESIGN.md "Measurement").
 
-One "step" = one pass of the decompose hot path over one synthetic pangenome graph of the shape
-BASELINE.json quotes its metric on (configs[1]: `snp_indel_1M`, V = 1,000,001 segments,
-E = 1,400,000 links, one component).  `value` = graph edges/s with the edge arrays resident in HBM;
-`e2e` = the same through the C ABI with pinned HOST buffers (H2D of the edge arrays and D2H of the
-flubble table inside the timed region).  N > 1: one process per GPU, every rank decomposes its own
-component of that shape (weak scaling, no data-path collective -- components are independent).
+One "step" = one pass of the whole decompose -> call hot path over one synthetic pangenome graph of the
+shape BASELINE.json quotes its metric on (configs[1], `snp_indel_1M`: V = 1,000,001 segments,
+E = 1,400,000 links, one component, 16 haplotype paths, reference path selected with -P 'S001#1'):
+  decompose (components, exact DFS tree, cycle classes, flubbles, PVST)  ->  device index of the paths
+  (adjacency in L-line order, loci, vertex->steps lists)  ->  call (regions, vertex order, depth
+  matrices, contexts, allele groups, genotypes -> binary VCF records on the host).
+`value` = graph edges/s through that whole step with the raw arrays (edge ports, packed path steps,
+segment lengths) resident in HBM; `parts` splits it into BASELINE.json's two figures (decompose edges/s,
+call VCF records/s).  `e2e` = the same step through the C ABI with pinned HOST arrays (H2D of the raw
+arrays and D2H of flubbles + records inside the timed region).  N > 1: one process per GPU, every rank
+runs its own component of that shape (weak scaling, no data-path collective: components are independent).
 
-`--impl reference` times the reference's own CPU implementation (oracle/_ref/povu_ref, the unmodified
-reference sources compiled by oracle/Makefile; falls back to the oracle port) on the host cores.
+`--impl reference` times the reference's own CPU implementation (oracle/_ref/povu_ref = the unmodified
+reference sources compiled by oracle/Makefile) on a bounded sample of the same workload.
 """
 import argparse
 import json
@@ -25,75 +30,98 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 CFG2_BUBBLES = 400_000
+N_PATHS = 16
+REF_PREFIX = "S001#1"
+METRIC = "decompose_call_hot_path_edges_per_sec"
 
 
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--bubbles", type=int, default=CFG2_BUBBLES, help="bubbles in the cfg2-shaped chain (default = cfg2)")
-    ap.add_argument("--cpu-bubbles", type=int, default=CFG2_BUBBLES, help="size of the bounded CPU-baseline sample")
+    ap.add_argument("--paths", type=int, default=N_PATHS)
+    ap.add_argument("--cpu-bubbles", type=int, default=100_000, help="size of the bounded CPU sample (same shape)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-steps", type=int, default=2)
     return ap.parse_args()
 
 
-def workload_name(n):
-    return "snp_indel_1M (cfg2)" if n == CFG2_BUBBLES else f"snp_indel_chain({n} bubbles)"
+def workload_name(n, paths):
+    return f"snp_indel_1M (cfg2), {paths} haplotype paths" if n == CFG2_BUBBLES else f"snp_indel_chain({n} bubbles), {paths} haplotype paths"
 
 
 # ----------------------------------------------------------------------------------------------
 # CPU reference leg
 # ----------------------------------------------------------------------------------------------
-def cpu_reference_run(n_bubbles, seed=42):
-    """Runs the reference decompose on a cfg2-shaped GFA; returns dict(edges, wall_s, stage_s, kind, cores)."""
+def cpu_reference_run(n_bubbles, n_paths, seed=42):
+    """Reference decompose + call on a cfg2-shaped GFA; compute time = the six decompose stage timers +
+    (do_call wall - a stand-alone GFA load with the same configuration)."""
     from povu_b200 import synth
-    g = synth.snp_indel_chain(n_bubbles, n_paths=0, seed=seed, with_seqs=False)
+    g = synth.snp_indel_chain(n_bubbles, n_paths=n_paths, seed=seed, with_seqs=True)
     E = len(g["v1"])
     d = tempfile.mkdtemp(prefix="povu_bench_")
     gfa = os.path.join(d, "g.gfa")
-    synth.write_gfa_fast({**g, "seqs": ["A"] * len(g["ids"])}, gfa)
+    synth.write_gfa_fast(g, gfa)
     ref = os.path.join(ROOT, "oracle", "_ref", "povu_ref")
     port = os.path.join(ROOT, "oracle", "povu_oracle")
-    out = os.path.join(d, "out")
-    os.mkdir(out)
-    if os.path.exists(ref):
-        kind, cmd = "reference", [ref, "decompose", "-i", gfa, "-o", out, "-t", "1"]
-    else:
-        kind, cmd = "port", [port, "decompose", "-i", gfa, "-o", out]
     env = dict(os.environ, POVU_STAGE_COST_TRACE="1")
-    t0 = time.perf_counter()
-    r = subprocess.run(cmd, env=env, capture_output=True, text=True)
-    wall = time.perf_counter() - t0
-    if r.returncode != 0:
-        raise RuntimeError("CPU reference failed: " + r.stderr[-300:])
-    stage_ns = sum(int(x) for x in re.findall(r"povu-stage-cost contract=\S+ .*elapsed_ns=(\d+)", r.stderr))
-    subprocess.run(["rm", "-rf", d])
-    return {"edges": E, "wall_s": wall, "stage_s": stage_ns / 1e9 if stage_ns else None, "kind": kind, "cores": 1}
+    try:
+        if os.path.exists(ref):
+            t0 = time.perf_counter()
+            with open(os.path.join(d, "out.vcf"), "w") as so:
+                r = subprocess.run([ref, "timed-gfa2vcf", "-i", gfa, "-P", REF_PREFIX, "-t", "1"], env=env, stdout=so, stderr=subprocess.PIPE, text=True)
+            wall = time.perf_counter() - t0
+            if r.returncode != 0:
+                raise RuntimeError("CPU reference failed: " + r.stderr[-300:])
+            stage = sum(int(x) for x in re.findall(r"povu-stage-cost contract=\S+ .*elapsed_ns=(\d+)", r.stderr)) / 1e9
+            m = re.search(r"povu-ref-timing decompose_total_s=(\S+) call_load_s=(\S+) call_total_s=(\S+)", r.stderr)
+            dec_total, call_load, call_total = (float(x) for x in m.groups())
+            records = sum(1 for l in open(os.path.join(d, "out.vcf")) if not l.startswith("#"))
+            t_dec = stage if stage > 0 else dec_total
+            t_call = max(call_total - call_load, 1e-9)
+            return {"edges": E, "records": records, "t_dec": t_dec, "t_call": t_call, "wall_s": wall, "kind": "reference", "cores": 2,
+                    "note": "decompose = sum of the reference's six stage timers (1 thread: it parallelises only across components); call = do_call wall minus a stand-alone GFA load (producer thread + VCF text consumer thread)"}
+        t0 = time.perf_counter()
+        r = subprocess.run([port, "gfa2vcf", "-i", gfa, "-P", REF_PREFIX], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+        wall = time.perf_counter() - t0
+        if r.returncode != 0:
+            raise RuntimeError("oracle port failed: " + r.stderr[-300:])
+        records = sum(1 for l in r.stdout.splitlines() if not l.startswith("#"))
+        return {"edges": E, "records": records, "t_dec": wall / 2, "t_call": wall / 2, "wall_s": wall, "kind": "port", "cores": 1, "note": "oracle port, whole-process wall incl. GFA parse"}
+    finally:
+        subprocess.run(["rm", "-rf", d])
+
+
+def cpu_fields(r, n, paths):
+    t = r["t_dec"] + r["t_call"]
+    return {"value": r["edges"] / t, "unit": "edges/s", "cores": r["cores"], "kind": r["kind"],
+            "sample": f"{workload_name(n, paths)}: {r['edges']} edges, {r['records']} records, one pass; {r['note']}; decompose {r['t_dec']:.2f} s + call {r['t_call']:.2f} s (whole process wall {r['wall_s']:.2f} s incl. two GFA parses)",
+            "decompose_edges_per_sec": r["edges"] / r["t_dec"], "call_records_per_sec": r["records"] / r["t_call"], "host_cores_available": os.cpu_count()}
 
 
 def run_reference_arm(args):
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
+    if int(os.environ.get("RANK", "0")) != 0:
         return
-    vals, walls = [], []
     n = args.cpu_bubbles
+    vals, times, last = [], [], None
     for i in range(args.warmup + args.steps):
-        r = cpu_reference_run(n)
+        if i < args.warmup and i > 0:
+            continue          # one untimed warm-up pass is enough for a CPU process (page cache, binary load)
+        last = cpu_reference_run(n, args.paths)
         if i >= args.warmup:
-            t = r["stage_s"] or r["wall_s"]
-            vals.append(r["edges"] / t)
-            walls.append(t)
+            t = last["t_dec"] + last["t_call"]
+            vals.append(last["edges"] / t); times.append(t)
     v = sum(vals) / len(vals)
-    sample = f"{workload_name(n)}: {r['edges']} edges per step, single component => 1 thread (reference parallelises only across components); time = sum of the reference's six decompose stage timers (GFA text parse excluded)"
-    line = {"impl": "reference", "metric": "decompose_graph_edges_per_sec", "value": v, "unit": "edges/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(walls) / len(walls), "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-            "config": {"workload": workload_name(n), "segments": int(2.5 * n) + 1, "links": r["edges"], "components": 1},
-            "cpu_baseline": {"value": v, "unit": "edges/s", "cores": r["cores"], "kind": r["kind"], "sample": sample},
-            "e2e": {"value": v, "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    cpu = cpu_fields(last, n, args.paths)
+    cpu["value"] = v
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "edges/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+            "config": {"workload": workload_name(n, args.paths) + " [bounded CPU sample of cfg2]", "segments": int(2.5 * n) + 1, "links": last["edges"], "paths": args.paths, "components": 1, "ref_prefix": REF_PREFIX},
+            "parts": {"decompose_edges_per_sec": cpu["decompose_edges_per_sec"], "call_records_per_sec": cpu["call_records_per_sec"], "records": last["records"]},
+            "cpu_baseline": cpu, "e2e": {"value": v, "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
 
@@ -149,7 +177,6 @@ class ClockSampler:
 # native arm
 # ----------------------------------------------------------------------------------------------
 def run_native(args):
-    import numpy as np
     import torch
     import torch.distributed as dist
 
@@ -172,20 +199,15 @@ def run_native(args):
     stream = torch.cuda.Stream()
     pv = api.Povu(device=local, stream=stream.cuda_stream)
 
-    # every rank gets its own component of the cfg2 shape (different seed => different alleles/paths)
-    g = synth.snp_indel_chain(args.bubbles, n_paths=0, seed=42 + rank, with_seqs=False)
+    # every rank gets its own component of the cfg2 shape (different seed => different alleles / paths)
+    g = synth.snp_indel_chain(args.bubbles, n_paths=args.paths, seed=42 + rank, with_seqs=True)
     V, E = len(g["ids"]), len(g["v1"])
-    ep1, ep2 = api.edge_ports(g)
-    h1 = torch.from_numpy(ep1.view(np.int32)).pin_memory()
-    h2 = torch.from_numpy(ep2.view(np.int32)).pin_memory()
+    sess = api.Session.from_graph(pv, g, with_labels=True)
+    S = sess.n_steps
+    del g
+    prefixes = [REF_PREFIX]
     with torch.cuda.stream(stream):
-        d1 = h1.to("cuda", non_blocking=True)
-        d2 = h2.to("cuda", non_blocking=True)
         flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2
-    stream.synchronize()
-
-    def step_dev():
-        return pv.decompose_dev(V, E, d1.data_ptr(), d2.data_ptr(), fetch=False)
 
     def barrier():
         if world > 1:
@@ -194,19 +216,19 @@ def run_native(args):
 
     with torch.cuda.stream(stream):
         for _ in range(args.warmup):
-            nfl = step_dev()
+            sess.hot_path(prefixes, keep_resident=True)
         barrier()
         clocks = ClockSampler(local)
         if rank == 0:
             clocks.start()
         launches0 = pv.launches
-        evs = []
+        evs, parts = [], []
         wall0 = time.perf_counter()
         for _ in range(args.steps):
             flush.fill_(1)                      # evict the previous step's working set from L2 (untimed)
             e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
             e0.record(stream)
-            nfl = step_dev()
+            parts.append(sess.hot_path(prefixes, keep_resident=True))
             e1.record(stream)
             evs.append((e0, e1))
         barrier()
@@ -214,34 +236,43 @@ def run_native(args):
         launches = pv.launches - launches0
         dev_ms = sum(a.elapsed_time(b) for a, b in evs)
         clk = clocks.stop() if rank == 0 else None
+        n_rec = int(sess.lib.pvgpu_session_record_count(sess.h))
+        n_fl = int(sess.lib.pvgpu_session_flubble_count(sess.h))
+        stats = sess.call_stats()
 
-        # end-to-end through the C ABI with HOST (pinned) buffers
-        h1n, h2n = h1.numpy().view(np.uint32), h2.numpy().view(np.uint32)
+        # end-to-end through the C ABI from pinned HOST arrays (raw arrays dropped from the device every step)
         for _ in range(min(2, args.warmup)):
-            f = pv.decompose(V, h1n, h2n)
+            sess.hot_path(prefixes, keep_resident=False)
         barrier()
-        t0 = time.perf_counter()
         e2e_steps = max(3, min(args.steps, 10))
+        t0 = time.perf_counter()
         for _ in range(e2e_steps):
-            f = pv.decompose(V, h1n, h2n)
+            sess.hot_path(prefixes, keep_resident=False)
         barrier()
         e2e_s = time.perf_counter() - t0
-        d2h_bytes = int(f.n) * (4 * 5 + 2) + len(f.comp_nv) * 20
+        # VCF text from the binary records (host C++), reported beside e2e
+        t0 = time.perf_counter()
+        text = sess.vcf_text()
+        text_s = time.perf_counter() - t0
+        text_bytes = len(text)
+        del text
 
-        # per-kernel CUDA-event timings for the roofline of the dominant kernel
         prof = None
         if rank == 0 and args.profile_steps > 0:
             pv.set_profiling(True)
             for _ in range(args.profile_steps):
                 flush.fill_(1)
-                step_dev()
+                sess.hot_path(prefixes, keep_resident=True)
             prof = pv.profile()
             pv.set_profiling(False)
 
     t_dev = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
+    cnt = torch.tensor([n_rec, n_fl], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)     # the only exchange: totals of the per-rank record buffers
     dev_ms_max, e2e_ms_max = t_dev.tolist()
+    tot_rec, tot_fl = (int(x) for x in cnt.tolist())
 
     if rank == 0:
         peaks = {}
@@ -250,42 +281,47 @@ def run_native(args):
         except Exception:
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
-        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
         if not prof:
             prof = [{"name": "unprofiled", "ms": 0.0, "bytes": 0, "launches": 1, "items": 0}]
             args.profile_steps = 1
         total_ms = sum(k["ms"] for k in prof) or 1.0
         top = max(prof, key=lambda k: k["ms"])
         ach = top["bytes"] / (top["ms"] * 1e-3) / 1e9 if top["ms"] > 0 else 0.0
-        kernels = sorted(prof, key=lambda k: -k["ms"])[:8]
+        kernels = sorted(prof, key=lambda k: -k["ms"])[:10]
+        ms_per_step = dev_ms_max / args.steps
+        # compulsory bytes of the whole step: decompose 16E + 12V + 16F ; call 8*S + 16F + ~(48 + H + 16) per record
+        comp_dec = 16 * E + 12 * V + 16 * n_fl
+        comp_call = 8 * S + 16 * n_fl + n_rec * (48 + args.paths + 16)
         roofline = {"bound": "hbm", "kernel": top["name"], "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                     "traffic": None, "peak_source": peak_src, "kernel_share_of_step": top["ms"] / total_ms,
                     "avg_launch_us": 1e3 * top["ms"] / top["launches"], "launches_per_step": top["launches"] / args.profile_steps,
                     "algorithmic_bytes_per_launch": top["bytes"] / top["launches"],
-                    "pipeline_compulsory_bytes": 16 * E + 12 * V + 16 * int(nfl),
-                    "pipeline_frac_of_peak": (16 * E + 12 * V + 16 * int(nfl)) / (dev_ms_max / args.steps * 1e-3) / 1e9 / peak,
+                    "pipeline_compulsory_bytes": {"decompose": comp_dec, "call": comp_call},
+                    "pipeline_frac_of_peak": (comp_dec + comp_call) / (ms_per_step * 1e-3) / 1e9 / peak,
                     "top_kernels": [{"name": k["name"], "ms_per_step": k["ms"] / args.profile_steps, "launches_per_step": k["launches"] / args.profile_steps,
                                      "GBps": (k["bytes"] / (k["ms"] * 1e-3) / 1e9) if k["ms"] > 0 else None} for k in kernels]}
         cpu = None
         if not args.no_cpu_baseline and world == 1:
             try:
-                r = cpu_reference_run(args.cpu_bubbles)
-                t = r["stage_s"] or r["wall_s"]
-                cpu = {"value": r["edges"] / t, "unit": "edges/s", "cores": r["cores"], "kind": r["kind"],
-                       "sample": f"{workload_name(args.cpu_bubbles)}, {r['edges']} edges, one pass; time = sum of the reference's six decompose stage timers ({t:.2f} s; whole process wall {r['wall_s']:.2f} s incl. GFA parse); 1 thread because the reference parallelises only across components",
-                       "host_cores_available": os.cpu_count()}
+                cpu = cpu_fields(cpu_reference_run(args.cpu_bubbles, args.paths), args.cpu_bubbles, args.paths)
             except Exception as ex:   # the baseline is reported, never required
                 cpu = {"value": None, "unit": "edges/s", "cores": 0, "kind": "unavailable", "sample": str(ex)[:200]}
-        ms_per_step = dev_ms_max / args.steps
-        line = {"metric": "decompose_graph_edges_per_sec", "value": world * E / (ms_per_step * 1e-3), "unit": "edges/s", "n_gpus": world,
+        pm = [sum(p[i] for p in parts) / len(parts) for i in range(4)]
+        d2h_bytes = n_fl * 22 + n_rec * (9 * 4 + 8) + n_rec * 2 * 16 + n_rec * args.paths * 2
+        line = {"metric": METRIC, "value": world * E / (ms_per_step * 1e-3), "unit": "edges/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-                "config": {"workload": workload_name(args.bubbles), "segments": V, "links": E, "components_per_gpu": 1, "flubbles": int(nfl),
+                "config": {"workload": workload_name(args.bubbles, args.paths), "segments": V, "links": E, "paths": args.paths, "path_steps": S, "components_per_gpu": 1,
+                           "flubbles": n_fl, "records": n_rec, "ref_prefix": REF_PREFIX,
                            "l2": "256 MiB flush write between timed steps (untimed); per-step CUDA events summed",
                            "sharding": "one independent component per rank, no collective on the data path"},
-                "e2e": {"value": world * E / (e2e_ms_max / e2e_steps * 1e-3), "unit": "edges/s", "h2d_bytes_per_step": 8 * E, "d2h_bytes_per_step": d2h_bytes,
-                        "ms_per_step": e2e_ms_max / e2e_steps, "steps": e2e_steps},
-                "gpu_launches": int(launches), "wall_s_timed_region": wall, "dfs_rounds": int(f.dfs_rounds),
+                "parts": {"decompose_edges_per_sec": world * E / (pm[1] * 1e-3), "call_records_per_sec": tot_rec / ((pm[2] + pm[3]) * 1e-3),
+                          "ms": {"decompose": pm[1], "path_index_build": pm[2], "call": pm[3]}, "records_all_ranks": tot_rec, "flubbles_all_ranks": tot_fl, "call_stats": stats},
+                "e2e": {"value": world * E / (e2e_ms_max / e2e_steps * 1e-3), "unit": "edges/s", "h2d_bytes_per_step": 8 * E + 4 * S + 4 * V, "d2h_bytes_per_step": d2h_bytes,
+                        "ms_per_step": e2e_ms_max / e2e_steps, "steps": e2e_steps,
+                        "vcf_text": {"bytes": text_bytes, "ms": text_s * 1e3, "note": "host C++ formatting of the binary records, not inside e2e (SURVEY.md 8f2)"}},
+                "gpu_launches": int(launches), "wall_s_timed_region": wall,
                 "clocks": clk, "roofline": roofline, "cpu_baseline": cpu, "peak_device_bytes": pv.peak_bytes}
         print(json.dumps(line))
     if world > 1:

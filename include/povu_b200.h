@@ -84,7 +84,18 @@ void pvgpu_flubbles_free(pvgpu_flubbles *f);
  */
 typedef struct pvgpu_session pvgpu_session;
 int pvgpu_session_open(pvgpu_ctx *ctx, const char *gfa_path, int inc_vtx_labels, int inc_refs, pvgpu_session **out);
+/* same, from arrays already in memory (the builder path of povu_ffi.h: povu_graph_new / add_vertex / add_edge /
+ * add_path, /root/reference/povu-rs/povu-ffi/povu_ffi.h:147-262).  ids ascending; ep1/ep2 ports as above;
+ * labels optional (label_off[V+1] into labels) -- without them seg_len[V] gives the segment lengths and VCF text is
+ * unavailable; path k has name path_names[k] and packed steps steps[step_off[k] .. step_off[k+1]) = (vertex<<1)|strand. */
+int pvgpu_session_from_arrays(pvgpu_ctx *ctx, uint32_t n_vertices, const uint32_t *ids, const uint32_t *seg_len, const uint64_t *label_off,
+			      const char *labels, uint64_t n_edges, const uint32_t *ep1, const uint32_t *ep2, uint32_t n_paths,
+			      const char *const *path_names, const uint32_t *step_off, const uint32_t *steps, pvgpu_session **out);
 void pvgpu_session_close(pvgpu_session *s);
+/* the whole hot path once: decompose -> device index -> call against the prefixes.  keep_resident != 0: the raw
+ * arrays (edge ports, steps, segment lengths) stay in HBM between calls; 0: they are copied from the host inside the
+ * call.  ms[4] receives the wall time of {upload, decompose, index build, call}. */
+int pvgpu_session_hot_path(pvgpu_session *s, const char *const *prefixes, size_t n_prefixes, int keep_resident, double ms[4]);
 /* graph sizes: vertices, edges, paths, total path steps */
 void pvgpu_session_sizes(const pvgpu_session *s, uint64_t *n_vertices, uint64_t *n_edges, uint64_t *n_paths, uint64_t *n_steps);
 int pvgpu_session_decompose(pvgpu_session *s);

@@ -6,11 +6,15 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <chrono>
 #include <string>
+#include <filesystem>
 #include "povu/common/app.hpp"
 #include "subcommand/call.hpp"
 #include "subcommand/decompose.hpp"
 #include "subcommand/gfa2vcf.hpp"
+#include "mto/from_gfa.hpp"
+#include "povu/graph/bidirected.hpp"
 
 int main(int argc, char **argv)
 {
@@ -35,6 +39,28 @@ int main(int argc, char **argv)
 		else if (a == "-h" || a == "--hairpins") cfg.set_hairpins(true);
 		else if (a == "--stdout") { }
 		else { cfg.set_ref_input_format(core::input_format_e::params); cfg.add_ref_name_prefix(a); }
+	}
+	/* bench.py --impl reference: `timed-gfa2vcf` runs the same two halves as do_gfa2vcf (gfa2vcf.cpp:49-70) with a
+	 * clock around each, plus one stand-alone GFA load with the call configuration, so that the compute time of the
+	 * call half can be reported without the text parse (which is not the reference's own code here: liteseq stand-in). */
+	if (task == "timed-gfa2vcf") {
+		auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+		cfg.set_inc_vtx_labels(true); cfg.set_inc_refs(true); cfg.set_stdout_vcf(true);
+		char tmpl[] = "/tmp/povu_ref_timed_XXXXXX";
+		char *d = mkdtemp(tmpl);
+		if (!d) { perror("mkdtemp"); return 1; }
+		core::config dc = cfg; dc.set_task(core::task_e::decompose); dc.set_inc_vtx_labels(false); dc.set_inc_refs(false); dc.set_output_dir(d);
+		double t0 = now();
+		povu::subcommands::decompose::do_decompose(dc);
+		double t1 = now();
+		{ povu::bidirected::VG *g = mto::from_gfa::to_bd(cfg); delete g; }
+		double t2 = now();
+		core::config cc = cfg; cc.set_task(core::task_e::call); cc.set_forest_dir(d);
+		povu::subcommands::call::do_call(cc);
+		double t3 = now();
+		std::filesystem::remove_all(d);
+		fprintf(stderr, "povu-ref-timing decompose_total_s=%.6f call_load_s=%.6f call_total_s=%.6f\n", t1 - t0, t2 - t1, t3 - t2);
+		return 0;
 	}
 	if (task == "gfa2vcf") {
 		cfg.set_task(core::task_e::gfa2vcf);

@@ -66,6 +66,10 @@ def load_library(lib_path=None):
     lib.pvgpu_session_open.argtypes = [vp, C.c_char_p, C.c_int, C.c_int, C.POINTER(vp)]
     lib.pvgpu_session_open.restype = C.c_int
     lib.pvgpu_session_close.argtypes = [vp]
+    lib.pvgpu_session_from_arrays.argtypes = [vp, u32, vp, vp, vp, vp, u64, vp, vp, u32, C.POINTER(C.c_char_p), vp, vp, C.POINTER(vp)]
+    lib.pvgpu_session_from_arrays.restype = C.c_int
+    lib.pvgpu_session_hot_path.argtypes = [vp, C.POINTER(C.c_char_p), sz, C.c_int, C.POINTER(C.c_double)]
+    lib.pvgpu_session_hot_path.restype = C.c_int
     lib.pvgpu_session_sizes.argtypes = [vp] + [C.POINTER(u64)] * 4
     lib.pvgpu_session_decompose.argtypes = [vp]
     lib.pvgpu_session_decompose.restype = C.c_int
@@ -230,13 +234,53 @@ class Session:
     """One GFA loaded on one device: decompose -> (.pvst) -> call -> VCF text.  Mirrors the reference's
     `povu decompose / call / gfa2vcf` drivers (app/subcommand/*.cpp) through the pvgpu_session_* C ABI."""
 
-    def __init__(self, pv, gfa_path, inc_vtx_labels=True, inc_refs=True):
+    def __init__(self, pv, gfa_path=None, inc_vtx_labels=True, inc_refs=True, _handle=None):
         self.pv, self.lib = pv, pv.lib
+        if _handle is not None:
+            self.h = _handle
+            return
         h = C.c_void_p()
         rc = self.lib.pvgpu_session_open(pv.h, os.fsencode(gfa_path), int(inc_vtx_labels), int(inc_refs), C.byref(h))
         if rc != 0:
             raise RuntimeError(pv._err())
         self.h = h
+
+    @classmethod
+    def from_graph(cls, pv, g, with_labels=True):
+        """Session over a synth/loader graph dict (arrays already in memory; the povu_ffi builder path)."""
+        ids = np.ascontiguousarray(g["ids"], dtype=np.uint32)
+        V = len(ids)
+        ep1, ep2 = edge_ports(g)
+        seqs = g.get("seqs")
+        lens = np.array([len(x) for x in seqs], dtype=np.uint32) if seqs is not None else np.ones(V, np.uint32)
+        lab_off = lab = None
+        if with_labels and seqs is not None:
+            lab_off = np.concatenate([[0], np.cumsum(lens, dtype=np.uint64)]).astype(np.uint64)
+            lab = "".join(seqs).encode()
+        paths = g.get("paths", [])
+        H = len(paths)
+        names = (C.c_char_p * max(H, 1))(*[p[0].encode() for p in paths])
+        off = np.zeros(H + 1, np.uint32)
+        for i, p in enumerate(paths):
+            off[i + 1] = off[i] + len(p[1])
+        steps = np.empty(int(off[-1]), np.uint32)
+        for i, p in enumerate(paths):
+            steps[off[i]:off[i + 1]] = (np.asarray(p[1], np.uint32) << 1) | np.asarray(p[2], np.uint32)
+        h = C.c_void_p()
+        rc = pv.lib.pvgpu_session_from_arrays(pv.h, V, ids.ctypes.data, lens.ctypes.data, lab_off.ctypes.data if lab_off is not None else None,
+                                              lab, len(ep1), ep1.ctypes.data, ep2.ctypes.data, H, names, off.ctypes.data, steps.ctypes.data, C.byref(h))
+        if rc != 0:
+            raise RuntimeError(pv._err())
+        s = cls(pv, _handle=h)
+        s.n_steps = int(off[-1])
+        return s
+
+    def hot_path(self, prefixes, keep_resident=True):
+        """decompose -> device index -> call, once.  Returns ms of (upload, decompose, index, call)."""
+        arr = (C.c_char_p * len(prefixes))(*[p.encode() for p in prefixes])
+        ms = (C.c_double * 4)()
+        self._check(self.lib.pvgpu_session_hot_path(self.h, arr, len(prefixes), int(keep_resident), ms))
+        return [float(x) for x in ms]
 
     def close(self):
         if self.h:

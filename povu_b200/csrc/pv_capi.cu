@@ -1,6 +1,7 @@
 // povu_b200 -- C ABI (include/povu_b200.h) over the device pipelines.
 #include "../../include/povu_b200.h"
 #include "pv_engine.hpp"
+#include "pv_ffi.hpp"
 
 struct pvgpu_ctx { pv::Ctx c; std::string err; };
 struct pvgpu_flubbles { pv::DecompOut o; };
@@ -126,7 +127,49 @@ int pvgpu_session_open(pvgpu_ctx *x, const char *gfa, int labels, int refs, pvgp
 	try { PV_SET_DEVICE(x); s = new pvgpu_session(x); s->s.load_gfa(gfa, labels != 0, refs != 0); *out = s; return 0; }
 	catch (std::exception &e) { x->err = e.what(); delete s; return 1; }
 }
+int pvgpu_session_from_arrays(pvgpu_ctx *x, uint32_t V, const uint32_t *ids, const uint32_t *seg_len, const uint64_t *label_off, const char *labels,
+			      uint64_t E, const uint32_t *ep1, const uint32_t *ep2, uint32_t H, const char *const *names, const uint32_t *step_off,
+			      const uint32_t *steps, pvgpu_session **out) {
+	if (!x || !out) return 1;
+	*out = nullptr;
+	pvgpu_session *s = nullptr;
+	try {
+		PV_SET_DEVICE(x);
+		s = new pvgpu_session(x);
+		pvh::HostGraph &g = s->s.g;
+		g.ids.assign(ids, ids + V);
+		for (uint32_t i = 1; i < V; i++) if (ids[i - 1] >= ids[i]) throw std::runtime_error("segment ids must be strictly ascending");
+		g.lblOff.assign((size_t)V + 1, 0);
+		if (labels && label_off) {
+			g.has_labels = true; g.lblOff.assign(label_off, label_off + V + 1); g.lbl.assign(labels, labels + label_off[V]);
+			g.segLen.resize(V); for (uint32_t i = 0; i < V; i++) g.segLen[i] = (uint32_t)(label_off[i + 1] - label_off[i]);
+		} else if (seg_len) g.segLen.assign(seg_len, seg_len + V);
+		else g.segLen.assign(V, 1);
+		g.build_id_table();
+		g.ep1.assign(ep1, ep1 + E); g.ep2.assign(ep2, ep2 + E);
+		for (uint64_t e = 0; e < E; e++) if (ep1[e] >= 2 * V || ep2[e] >= 2 * V) throw std::runtime_error("edge endpoint out of range");
+		g.stepOff.assign(1, 0);
+		for (uint32_t h = 0; h < H; h++) {
+			pvh::HostPath p = pvh::parse_path_name(names[h]);
+			uint64_t len = 0;
+			for (uint32_t k = step_off[h]; k < step_off[h + 1]; k++) { if ((steps[k] >> 1) >= V) throw std::runtime_error("path step out of range"); len += g.segLen[steps[k] >> 1]; }
+			p.hap_len = (uint32_t)len;
+			g.paths.push_back(std::move(p)); g.stepOff.push_back(step_off[h + 1] - step_off[0]);
+		}
+		if (H) g.steps.assign(steps + step_off[0], steps + step_off[H]);
+		s->s.pin();
+		*out = s; return 0;
+	} catch (std::exception &e) { x->err = e.what(); delete s; return 1; }
+}
 void pvgpu_session_close(pvgpu_session *s) { delete s; }
+int pvgpu_session_hot_path(pvgpu_session *s, const char *const *prefixes, size_t n, int keep, double ms[4]) {
+	PV_TRY(s->x, {
+		std::vector<std::string> p; for (size_t i = 0; i < n; i++) p.push_back(prefixes[i]);
+		if (p != s->s.prefixes || !s->s.gm_ready) s->s.set_prefixes(p);
+		s->s.hot_path(keep != 0);
+		if (ms) { ms[0] = s->s.t_upload_ms; ms[1] = s->s.t_dec_ms; ms[2] = s->s.t_build_ms; ms[3] = s->s.t_call_ms; }
+	})
+}
 void pvgpu_session_sizes(const pvgpu_session *s, uint64_t *v, uint64_t *e, uint64_t *h, uint64_t *st) {
 	if (v) *v = s->s.g.V(); if (e) *e = s->s.g.E(); if (h) *h = s->s.g.H(); if (st) *st = s->s.g.steps.size();
 }

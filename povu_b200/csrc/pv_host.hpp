@@ -89,6 +89,19 @@ inline bool parse_u64(const char *b, const char *e, u64 &out) {
 	out = v; return true;
 }
 
+// PanSN `sample#hap#contig` with a numeric hap -> (sample, hap id); anything else is a raw name whose sample
+// name is the whole tag (liteseq ref_id_type)
+inline HostPath parse_path_name(const std::string &tag) {
+	HostPath p; p.tag = tag;
+	size_t h1 = tag.find('#'), h2 = h1 == std::string::npos ? h1 : tag.find('#', h1 + 1);
+	if (h2 != std::string::npos) {
+		std::string hap = tag.substr(h1 + 1, h2 - h1 - 1);
+		if (!hap.empty() && hap.find_first_not_of("0123456789") == std::string::npos) { p.pansn = true; p.sample = tag.substr(0, h1); p.hap_id = (u32)strtoul(hap.c_str(), nullptr, 10); }
+	}
+	if (!p.pansn) p.sample = tag;
+	return p;
+}
+
 inline HostGraph load_gfa(const std::string &fp, bool inc_labels, bool inc_refs) {
 	auto bad = [&](const std::string &d) { return std::runtime_error("Invalid GFA '" + fp + "': " + d); };
 	MappedFile mf(fp);
@@ -177,14 +190,7 @@ inline HostGraph load_gfa(const std::string &fp, bool inc_labels, bool inc_refs)
 		for (size_t r = 0; r < P.size(); r++) {
 			const char *nb, *ne, *sb, *se, *ob, *oe;
 			if (!field(P[r], 1, nb, ne) || !field(P[r], 2, sb, se) || !field(P[r], 3, ob, oe)) throw lq;
-			HostPath p; p.tag.assign(nb, ne);
-			// PanSN: sample#hap#contig with a numeric hap
-			size_t h1 = p.tag.find('#'), h2 = h1 == std::string::npos ? h1 : p.tag.find('#', h1 + 1);
-			if (h2 != std::string::npos) {
-				std::string hap = p.tag.substr(h1 + 1, h2 - h1 - 1);
-				if (!hap.empty() && hap.find_first_not_of("0123456789") == std::string::npos) { p.pansn = true; p.sample = p.tag.substr(0, h1); p.hap_id = (u32)strtoul(hap.c_str(), nullptr, 10); }
-			}
-			if (!p.pansn) p.sample = p.tag;
+			HostPath p = parse_path_name(std::string(nb, ne));
 			u64 pos = 1;
 			for (const char *q = sb; q <= se;) {
 				const char *cm = (const char *)memchr(q, ',', (size_t)(se - q));

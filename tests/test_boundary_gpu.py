@@ -1,0 +1,18 @@
+"""CLI and povu_ffi.h boundary on the B200: the `povu` binary and libpovu_b200.so (CUDA build)."""
+import os
+
+import pytest
+
+import boundary_checks as bc
+
+pytestmark = pytest.mark.gpu
+
+
+def test_gpu_cli_contract(gpu, tmp_path):
+    bc.check_cli(os.path.join(bc.ROOT, "povu_b200", "bin", "povu"), str(tmp_path))
+
+
+def test_gpu_ffi(gpu, tmp_path):
+    L = bc.ffi(os.path.join(bc.ROOT, "povu_b200", "libpovu_b200.so"))
+    bc.check_ffi_builder(L)
+    bc.check_ffi_compute(L, str(tmp_path))

@@ -22,6 +22,15 @@ def test_povu_b200_h_symbols_exported(built):
     assert lib.pvgpu_build_kind() == 1
 
 
+def test_povu_ffi_h_symbols_exported(built):
+    built.build_cuda()
+    lib = ctypes.CDLL(os.path.join(ROOT, "povu_b200", "libpovu_b200.so"))
+    names = _declared("povu_ffi.h")
+    assert len(names) == 33          # povu_ffi.h:147-437 declares 33 functions
+    for n in names:
+        assert hasattr(lib, n), f"missing export {n}"
+
+
 def test_create_fails_loudly_without_gpu(built):
     """No CPU fallback: without a CUDA device pvgpu_create must fail (skipped on a GPU box)."""
     import pytest
