@@ -117,6 +117,16 @@ void pvgpu_session_call_stats(const pvgpu_session *s, uint64_t out[10]);
 /* combined VCF text (what `povu gfa2vcf` / `povu call --stdout` print); with_date = 0 drops ##fileDate.
  * prefix = NULL: combined stream; otherwise the per-prefix file content of `-o dir` (to_vcf.hpp:83-101). */
 char *pvgpu_session_vcf_text(const pvgpu_session *s, size_t chunk_size, int with_date, const char *prefix, size_t *len);
+/* ---- multi-GPU (one process per GPU): keep only this rank's share of the weakly connected components, balanced by
+ * edges + path steps (greedy LPT).  Component ids, path ids and vertex / edge order stay those of the whole graph, so
+ * the per-rank outputs concatenate into exactly the single-GPU output.  No exchange happens while computing; the only
+ * communication is the final gather of record lines (povu_b200/dist.py does it with torch.distributed). */
+int pvgpu_session_shard(pvgpu_session *s, uint32_t rank, uint32_t world, uint32_t *n_components_total);
+/* after call: per PVST tree of this session its component id and the number of regions that reached the overlay */
+void pvgpu_session_tree_regions(const pvgpu_session *s, uint32_t *comp_id, uint64_t *n_regions);
+/* after call: all records as VCF text lines (malloc'ed, pvgpu_free) with line_off[n+1] and keys[3n] =
+ * (component id, ordinal of the region inside its component, ref path id) per line */
+char *pvgpu_session_record_lines(const pvgpu_session *s, size_t *len, uint64_t **line_off, uint32_t **keys, size_t *n);
 void pvgpu_free(void *p);
 
 #ifdef __cplusplus

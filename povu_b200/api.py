@@ -93,6 +93,11 @@ def load_library(lib_path=None):
     lib.pvgpu_session_vcf_text.argtypes = [vp, sz, C.c_int, C.c_char_p, C.POINTER(sz)]
     lib.pvgpu_session_vcf_text.restype = vp
     lib.pvgpu_free.argtypes = [vp]
+    lib.pvgpu_session_shard.argtypes = [vp, u32, u32, C.POINTER(u32)]
+    lib.pvgpu_session_shard.restype = C.c_int
+    lib.pvgpu_session_tree_regions.argtypes = [vp, vp, vp]
+    lib.pvgpu_session_record_lines.argtypes = [vp, C.POINTER(sz), C.POINTER(vp), C.POINTER(vp), C.POINTER(sz)]
+    lib.pvgpu_session_record_lines.restype = vp
     return lib
 
 
@@ -341,3 +346,33 @@ class Session:
     def vcf_text(self, chunk_size=100, with_date=False, prefix=None):
         n = C.c_size_t()
         return self._text(self.lib.pvgpu_session_vcf_text(self.h, chunk_size, int(with_date), prefix.encode() if prefix else None, C.byref(n)), n)
+
+    def shard(self, rank, world):
+        """Keep only this rank's share of the components (balanced by edges + path steps); returns the total
+        number of components of the whole graph."""
+        n = C.c_uint32()
+        self._check(self.lib.pvgpu_session_shard(self.h, rank, world, C.byref(n)))
+        return int(n.value)
+
+    def tree_regions(self):
+        """{component id: number of regions that reached the overlay} for this session's PVST trees."""
+        k = self.lib.pvgpu_session_tree_count(self.h)
+        comp = np.zeros(k, np.uint32); cnt = np.zeros(k, np.uint64)
+        if k:
+            self.lib.pvgpu_session_tree_regions(self.h, comp.ctypes.data, cnt.ctypes.data)
+        return dict(zip(comp.tolist(), cnt.tolist()))
+
+    def record_lines(self):
+        """(lines, keys) of all records: keys[i] = (component id, region ordinal inside the component, ref path id)."""
+        ln, n = C.c_size_t(), C.c_size_t()
+        off, keys = C.c_void_p(), C.c_void_p()
+        p = self.lib.pvgpu_session_record_lines(self.h, C.byref(ln), C.byref(off), C.byref(keys), C.byref(n))
+        if not p:
+            raise RuntimeError(self.pv._err())
+        try:
+            text = C.string_at(p, ln.value)
+            o = np.ctypeslib.as_array(C.cast(off, C.POINTER(C.c_uint64)), (n.value + 1,)).copy()
+            k = np.ctypeslib.as_array(C.cast(keys, C.POINTER(C.c_uint32)), (max(n.value, 1) * 3,)).copy()[: n.value * 3].reshape(-1, 3)
+        finally:
+            self.lib.pvgpu_free(p); self.lib.pvgpu_free(off); self.lib.pvgpu_free(keys)
+        return [text[o[i]:o[i + 1]].decode() for i in range(n.value)], k

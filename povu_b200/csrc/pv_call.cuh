@@ -109,6 +109,14 @@ inline GraphView view(const DevGraph &g) {
 			 g.d_pathComp.p, g.d_cpOff.p, g.d_cpList.p, g.d_hapLocal.p};
 }
 
+// weakly connected components: label[v] = lowest vertex index of v's component (VG::componetize discovers
+// components in exactly that order, bidirected.cpp:585-596)
+inline void component_labels(Ctx &c, u32 V, u64 E, const u32 *ep1, const u32 *ep2, u32 *label) {
+	parallel_for<C_uf>(c, V, PV_LAMBDA(size_t v) { label[v] = (u32)v; });
+	parallel_for<C_uf>(c, E, PV_LAMBDA(size_t e) { uf_union(label, ep1[e] >> 1, ep2[e] >> 1); });
+	parallel_for<C_uf>(c, V, PV_LAMBDA(size_t v) { label[v] = uf_find(label, (u32)v); });
+}
+
 // d_ep1/d_ep2: E edge endpoint ports (device).  d_steps: S packed steps (device).  d_segLen: V (device).
 inline void graph_build(Ctx &c, u32 V, u64 E, const u32 *ep1, const u32 *ep2, u32 H, const u32 *h_stepOff, const u32 *d_steps,
 			const u32 *d_segLen, DevGraph &g) {
@@ -169,9 +177,7 @@ inline void graph_build(Ctx &c, u32 V, u64 E, const u32 *ep1, const u32 *ep2, u3
 	g.vcomp = Buf<u32>(c, V ? V : 1);
 	{
 		u32 *uf_ = g.vcomp.p;
-		parallel_for<C_uf>(c, V, PV_LAMBDA(size_t v) { uf_[v] = (u32)v; });
-		parallel_for<C_uf>(c, E, PV_LAMBDA(size_t e) { uf_union(uf_, ep1[e] >> 1, ep2[e] >> 1); });
-		parallel_for<C_uf>(c, V, PV_LAMBDA(size_t v) { uf_[v] = uf_find(uf_, (u32)v); });
+		component_labels(c, V, E, ep1, ep2, uf_);
 		Buf<u32> pr(c, H ? H : 1);
 		u32 *pr_ = pr.p;
 		parallel_for<C_uf>(c, H, PV_LAMBDA(size_t h) { pr_[h] = stepOff_[h + 1] > stepOff_[h] ? uf_[steps_[stepOff_[h]] >> 1] : NONE; });

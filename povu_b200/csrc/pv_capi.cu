@@ -198,6 +198,23 @@ char *pvgpu_session_vcf_text(const pvgpu_session *s, size_t chunk, int with_date
 		return dup_text(S.vcf_header({std::string(prefix)}, with_date != 0) + S.vcf_records(chunk, &only), len);
 	} catch (std::exception &e) { s->x->err = e.what(); return nullptr; }
 }
+int pvgpu_session_shard(pvgpu_session *s, uint32_t rank, uint32_t world, uint32_t *n_total) {
+	PV_TRY(s->x, { s->s.shard(rank, world); if (n_total) *n_total = s->s.n_comp_total; })
+}
+void pvgpu_session_tree_regions(const pvgpu_session *s, uint32_t *comp_id, uint64_t *n_regions) {
+	std::vector<uint64_t> n = s->s.regions_per_tree();
+	for (size_t t = 0; t < n.size(); t++) { if (comp_id) comp_id[t] = s->s.forest.comp_id[t]; if (n_regions) n_regions[t] = n[t]; }
+}
+char *pvgpu_session_record_lines(const pvgpu_session *s, size_t *len, uint64_t **line_off, uint32_t **keys, size_t *n) {
+	try {
+		std::string text; std::vector<uint64_t> off; std::vector<uint32_t> k;
+		s->s.record_lines(text, off, k);
+		*n = off.size() - 1;
+		*line_off = (uint64_t *)malloc(off.size() * 8); memcpy(*line_off, off.data(), off.size() * 8);
+		*keys = (uint32_t *)malloc(k.size() * 4 + 4); if (!k.empty()) memcpy(*keys, k.data(), k.size() * 4);
+		return dup_text(text, len);
+	} catch (std::exception &e) { s->x->err = e.what(); return nullptr; }
+}
 void pvgpu_free(void *p) { free(p); }
 
 }

@@ -100,6 +100,58 @@ struct Session {
 		t_upload_ms = t1 - t0; t_dec_ms = t2 - t1; t_build_ms = t3 - t2; t_call_ms = t4 - t3;
 	}
 
+	// ---- multi-GPU: keep only this rank's share of the weakly connected components.
+	// Components are independent units for decompose, and every path lies inside one component, so ranks never
+	// exchange anything while computing.  Balancing: greedy longest-processing-time on (edges + path steps).
+	std::vector<u32> comp_global;          // local component k (ascending lowest vertex) -> global component id (1-based)
+	u32 n_comp_total = 0; bool sharded = false;
+	std::vector<u32> shard_owner;          // per global component (0-based): owning rank
+	void shard(u32 rank, u32 world) {
+		if (world == 0 || rank >= world) throw std::runtime_error("shard: bad rank / world size");
+		upload_edges();
+		const u32 V = g.V(); const u64 E = g.E();
+		pv::Buf<u32> lab(*c, V ? V : 1);
+		pv::component_labels(*c, V, E, d_ep1.p, d_ep2.p, lab.p);
+		std::vector<u32> root = lab.to_host(); root.resize(V);
+		std::vector<u32> comp_of(V), roots;
+		for (u32 v = 0; v < V; v++) if (root[v] == v) roots.push_back(v);          // ascending = discovery order
+		for (u32 v = 0; v < V; v++) comp_of[v] = (u32)(std::lower_bound(roots.begin(), roots.end(), root[v]) - roots.begin());
+		const u32 nC = (u32)roots.size();
+		std::vector<u64> w(nC, 0);
+		for (u64 e = 0; e < E; e++) w[comp_of[g.ep1[e] >> 1]]++;
+		for (u32 st : g.steps) w[comp_of[st >> 1]]++;
+		for (u32 v = 0; v < V; v++) w[comp_of[v]]++;
+		std::vector<u32> order(nC);
+		for (u32 k = 0; k < nC; k++) order[k] = k;
+		std::stable_sort(order.begin(), order.end(), [&](u32 a, u32 b) { return w[a] > w[b]; });
+		std::vector<u64> load(world, 0);
+		shard_owner.assign(nC, 0);
+		for (u32 k : order) { u32 best = 0; for (u32 r = 1; r < world; r++) if (load[r] < load[best]) best = r; shard_owner[k] = best; load[best] += w[k]; }
+		n_comp_total = nC;
+		comp_global.clear();
+		for (u32 k = 0; k < nC; k++) if (shard_owner[k] == rank) comp_global.push_back(k + 1);
+		// filter the host graph (vertex order, edge order and path ids are preserved)
+		pvh::HostGraph n; n.has_labels = g.has_labels; n.paths = g.paths;
+		std::vector<u32> remap(V, pvh::NONE32);
+		n.lblOff.push_back(0);
+		for (u32 v = 0; v < V; v++) if (shard_owner[comp_of[v]] == rank) {
+			remap[v] = (u32)n.ids.size(); n.ids.push_back(g.ids[v]); n.segLen.push_back(g.segLen[v]);
+			if (g.has_labels) n.lbl.append(g.label(v), g.segLen[v]);
+			n.lblOff.push_back(n.lblOff.back() + g.segLen[v]);
+		}
+		for (u64 e = 0; e < E; e++) if (remap[g.ep1[e] >> 1] != pvh::NONE32) { n.ep1.push_back((remap[g.ep1[e] >> 1] << 1) | (g.ep1[e] & 1u)); n.ep2.push_back((remap[g.ep2[e] >> 1] << 1) | (g.ep2[e] & 1u)); }
+		n.stepOff.assign(1, 0);
+		for (u32 h = 0; h < g.H(); h++) {
+			for (u32 k = g.stepOff[h]; k < g.stepOff[h + 1]; k++) { u32 nv = remap[g.steps[k] >> 1]; if (nv != pvh::NONE32) n.steps.push_back((nv << 1) | (g.steps[k] & 1u)); }
+			n.stepOff.push_back((u32)n.steps.size());
+		}
+		n.build_id_table();
+		unpin(); drop_device();
+		g = std::move(n);
+		pin();
+		forest_ready = false; sharded = true;
+	}
+
 	// decompose: flubbles + PVST of every component with >= 3 vertices (decompose.cpp:129-142)
 	void decompose() {
 		upload_edges();
@@ -118,7 +170,7 @@ struct Session {
 					forest.parent.push_back(dec.parent[base + j]); forest.height.push_back(dec.depth[base + j]);
 					forest.flBase.push_back(forest.treeOff.back()); forest.family.push_back('F');
 				}
-				forest.comp_id.push_back(k + 1); forest.treeOff.push_back(forest.n());
+				forest.comp_id.push_back(sharded ? comp_global.at(k) : k + 1); forest.treeOff.push_back(forest.n());
 			}
 			base += n;
 		}
@@ -201,6 +253,27 @@ struct Session {
 		std::string o = pvh::vcf_header_common(with_date);
 		for (auto &p : for_prefixes) for (u32 r : pvh::refs_in_sample(g, p)) o += pvh::vcf_contig_line(g.paths[r]);
 		return o + pvh::vcf_col_header(gm);
+	}
+	// for the multi-GPU merge: every record as a text line plus (component id, ordinal of its region inside that
+	// component, ref path id); lines are in (ref, region, context) order.  regions_per_tree: regions that reached
+	// the overlay, per PVST tree of this session.
+	u32 tree_of_flubble(u32 fl) const { return (u32)(std::upper_bound(forest.treeOff.begin(), forest.treeOff.end(), fl) - forest.treeOff.begin()) - 1; }
+	std::vector<u64> regions_per_tree() const {
+		std::vector<u64> n(forest.comp_id.size(), 0);
+		for (u32 fl : rec.rov_fl) n[tree_of_flubble(fl)]++;
+		return n;
+	}
+	void record_lines(std::string &text, std::vector<u64> &off, std::vector<u32> &keys) const {
+		std::vector<u64> per = regions_per_tree(), first(per.size() + 1, 0);
+		for (size_t t = 0; t < per.size(); t++) first[t + 1] = first[t] + per[t];
+		std::vector<std::string> slots(gm.nSlots);
+		text.clear(); off.assign(1, 0); keys.clear();
+		for (size_t i : pvh::record_order(rec, ~(size_t)0)) {
+			pvh::record_text(g, gm, forest, rec, i, slots, text);
+			off.push_back(text.size());
+			u32 r = rec.rec_rov[i], t = tree_of_flubble(rec.rov_fl[r]);
+			keys.push_back(forest.comp_id[t]); keys.push_back((u32)(r - first[t])); keys.push_back(rec.rec_ref[i]);
+		}
 	}
 	std::string vcf_records(size_t chunk_size, const std::set<u32> *only_refs) const {
 		std::string o;
