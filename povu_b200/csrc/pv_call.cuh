@@ -120,6 +120,7 @@ inline void component_labels(Ctx &c, u32 V, u64 E, const u32 *ep1, const u32 *ep
 // d_ep1/d_ep2: E edge endpoint ports (device).  d_steps: S packed steps (device).  d_segLen: V (device).
 inline void graph_build(Ctx &c, u32 V, u64 E, const u32 *ep1, const u32 *ep2, u32 H, const u32 *h_stepOff, const u32 *d_steps,
 			const u32 *d_segLen, DevGraph &g) {
+	Trace tr(c, "index");
 	g.V = V; g.E = E; g.H = H; g.S = h_stepOff ? h_stepOff[H] : 0;
 	const u32 P = 2 * V; const u64 M = 2 * E; const u32 S = g.S;
 	if (M >= 0xFFFFFFF0ull) throw std::runtime_error("graph too large for 32-bit adjacency slots");
@@ -144,6 +145,7 @@ inline void graph_build(Ctx &c, u32 V, u64 E, const u32 *ep1, const u32 *ep2, u3
 		u32 *adjNbr_ = g.adjNbr.p;
 		parallel_for<C_adj_fill>(c, M, PV_LAMBDA(size_t s) { adjNbr_[s] = nbr_[idx_[s]]; });
 	}
+	tr.mark("adjacency");
 	// ---- paths
 	g.h_stepOff.assign(h_stepOff, h_stepOff + H + 1);
 	g.stepOff = Buf<u32>(c, (size_t)H + 1); c.h2d(g.stepOff.p, h_stepOff, ((size_t)H + 1) * 4);
@@ -173,6 +175,7 @@ inline void graph_build(Ctx &c, u32 V, u64 E, const u32 *ep1, const u32 *ep2, u3
 		exclusive_scan(c, cnt.p, g.vsOff.p, (size_t)V + 1, OpAddU32(), 0u);
 		parallel_for<C_vs_hap>(c, S, PV_LAMBDA(size_t i) { vsHap_[i] = ub_u32(stepOff_, 0, H + 1, vsStep_[i]) - 1; });
 	}
+	tr.mark("loci + vertex->steps");
 	// ---- weakly connected components -> the paths of every component
 	g.vcomp = Buf<u32>(c, V ? V : 1);
 	{
@@ -196,6 +199,7 @@ inline void graph_build(Ctx &c, u32 V, u64 E, const u32 *ep1, const u32 *ep2, u3
 		up(g.d_pathComp, g.pathComp); up(g.d_cpOff, g.cpOff); up(g.d_cpList, g.cpList); up(g.d_hapLocal, g.hapLocal);
 	}
 	c.sync();
+	tr.mark("components");
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -296,32 +300,49 @@ struct CallIn {            // PVST forest, flubbles of all components concatenat
 	const u8 *excluded = nullptr;  // optional: 1 = never selected (sub-flubble clan or below one, color.cpp:117-125)
 };
 
-struct CallOut {
+// binary records, written by the device into page-locked host vectors whose capacity survives across calls
+struct Records {
 	// regions (RoVs) in enumeration order: ascending (component file, PVST vertex idx), >= 3 sorted vertices
-	std::vector<u32> rov_fl, rov_J, rov_comp; std::vector<u8> rov_tangled;
+	hvec<u32> rov_fl, rov_comp, rov_tangled;
 	// records: grouped per (region, ref) in context order, INS / SUB / DEL
-	std::vector<u32> rec_rov, rec_ref, rec_cxtL, rec_cxtR, rec_vt, rec_pos, rec_refStart, rec_refLen, rec_grpOff;
-	std::vector<u64> rec_gtOff;
-	std::vector<u32> grp_hap, grp_start, grp_len, grp_count;   // start = step index inside the path
-	std::vector<u16> gt;           // per record: one code per path of the region's component (0 ref, i alt group, 0xFFFF missing)
+	hvec<u32> rec_rov, rec_ref, rec_cxtL, rec_cxtR, rec_vt, rec_pos, rec_refStart, rec_refLen, rec_grpOff;
+	hvec<u64> rec_gtOff;
+	hvec<u32> grp_hap, grp_start, grp_len, grp_count;   // start = step index inside the path
+	hvec<u16> gt;           // per record: one code per path of the region's component (0 ref, i alt group, 0xFFFF missing)
+	std::vector<u32> cpOff, cpList;   // paths of every component = the columns of `gt`
 	u64 n_called = 0, n_too_small = 0, n_sort_failed = 0, n_tangled = 0, n_pin_pairs = 0, n_hard_errors = 0, n_chunks = 0, n_big_bfs = 0, max_J = 0;
+	size_t n() const { return rec_rov.size(); }
+	void reset() {
+		rov_fl.clear(); rov_comp.clear(); rov_tangled.clear();
+		rec_rov.clear(); rec_ref.clear(); rec_cxtL.clear(); rec_cxtR.clear(); rec_vt.clear(); rec_pos.clear(); rec_refStart.clear(); rec_refLen.clear();
+		rec_grpOff.clear(); rec_gtOff.clear(); grp_hap.clear(); grp_start.clear(); grp_len.clear(); grp_count.clear(); gt.clear();
+		n_called = n_too_small = n_sort_failed = n_tangled = n_pin_pairs = n_hard_errors = n_chunks = n_big_bfs = max_J = 0;
+	}
 };
+typedef Records CallOut;
 enum { VT_DEL = 0, VT_INS = 1, VT_SUB = 2, VT_SUBR = 3 };
 
 struct CallOpts { u64 cell_budget = 1ull << 30; };
 
 struct RovView {
-	const u32 *rovOff, *rovVerts, *rovComp, *rowBase; const u64 *matBase;
+	const u32 *rovOff, *rovVerts, *rovComp; const u64 *rowPre, *cellPre;   // global prefix sums over regions
 	const u64 *hkey; const u32 *hval; u64 hmask;
-	u32 R; u32 uniformNh; u32 rShift;   // chunk-local region r is global region r + rShift (the hash is keyed globally)
-	PV_DEV u32 J(u32 r) const { return rovOff[r + 1] - rovOff[r]; }
+	u32 R; u32 uniformNh; u32 rShift;   // chunk = regions [rShift, rShift + R); region arguments below are chunk-local
+	PV_DEV u32 J(u32 r) const { return rovOff[rShift + r + 1] - rovOff[rShift + r]; }
+	PV_DEV u32 vert(u32 r, u32 j) const { return rovVerts[rovOff[rShift + r] + j]; }
+	PV_DEV u32 comp(u32 r) const { return rovComp[rShift + r]; }
+	PV_DEV u32 rowBase(u32 r) const { return (u32)(rowPre[rShift + r] - rowPre[rShift]); }   // first matrix row of region r (chunk-relative)
+	PV_DEV u64 matBase(u32 r) const { return cellPre[rShift + r] - cellPre[rShift]; }
 	PV_DEV u32 find(u32 r, u32 v) const {   // column of vertex v in region r, or NONE
-		u32 a = rovOff[r], n = rovOff[r + 1] - a;
+		u32 a = rovOff[rShift + r], n = rovOff[rShift + r + 1] - a;
 		if (n <= 16) { for (u32 j = 0; j < n; j++) if (rovVerts[a + j] == v) return j; return NONE; }
 		u64 key = ((u64)(r + rShift) << 32) | v; u64 i = splitmix64(key) & hmask;
 		while (true) { u64 k = hkey[i]; if (k == key) return hval[i]; if (k == ~0ull) return NONE; i = (i + 1) & hmask; }
 	}
-	PV_DEV u32 row2rov(u32 row) const { return uniformNh ? row / uniformNh : ub_u32(rowBase, 0, R + 1, row) - 1; }
+	PV_DEV u32 row2rov(u32 row) const {
+		if (uniformNh) return row / uniformNh;
+		return (u32)(ub_u64(rowPre + rShift, 0, (u64)R + 1, rowPre[rShift] + row) - 1);
+	}
 };
 
 struct Lap { u32 lo, hi; };   // global step range [lo, hi)
@@ -364,11 +385,11 @@ struct CandView { u32 *cL, *cR, *cStart, *cLen, *cRS, *cRL, *cHap, *cCls, *cHead
 // (overlay.cpp:307-327,189-246,462-530).  Returns the number of contexts.
 PV_DEV u32 scan_pair(const ChunkView &cv, u32 refLocal, u32 k, u32 row, bool fill, const CandView &cd, u32 off) {
 	const RovView &rv = cv.rv; const GraphView &g = cv.g;
-	u32 r = rv.row2rov(row); u32 i = row - rv.rowBase[r];
+	u32 r = rv.row2rov(row); u32 i = row - rv.rowBase(r);
 	if (i == refLocal || cv.tangled[r]) return 0;
 	if (k > 0 && !cv.hasData[r]) return 0;     // comp_exps returned after the first ref (overlay.cpp:531-532)
 	u32 J = rv.J(r);
-	const u16 *rr = cv.mat + rv.matBase[r] + (u64)refLocal * J, *ar = cv.mat + rv.matBase[r] + (u64)i * J;
+	const u16 *rr = cv.mat + rv.matBase(r) + (u64)refLocal * J, *ar = cv.mat + rv.matBase(r) + (u64)i * J;
 	bool empty = true, inv = true; u32 cnt = 0; u32 prev = NONE; bool diff = false;
 	for (u32 j = 0; j < J; j++) {
 		u32 x = rr[j], y = ar[j];
@@ -379,8 +400,8 @@ PV_DEV u32 scan_pair(const ChunkView &cv, u32 refLocal, u32 k, u32 row, bool fil
 		if (ok) {
 			if (prev != NONE && diff) {
 				if (fill) {
-					u32 u = rv.rovVerts[rv.rovOff[r] + prev], v = rv.rovVerts[rv.rovOff[r] + j];
-					Lap rl = cv.lap(rv.rowBase[r] + refLocal), al = cv.lap(row);
+					u32 u = rv.vert(r, prev), v = rv.vert(r, j);
+					Lap rl = cv.lap(rv.rowBase(r) + refLocal), al = cv.lap(row);
 					u32 fu = g.occ_first(u, rl.lo, rl.hi), lv = g.occ_last(v, rl.lo, rl.hi);
 					u32 o = off + cnt; cd.cCls[o] = 3;
 					u32 rs = 0, rn = 0, as = 0, an = 0;
@@ -420,23 +441,31 @@ PV_DEV void sift_down(const u32 *steps, const CandView &cd, u32 *a, u32 root, u3
 	}
 }
 
-inline void call_device(Ctx &c, const DevGraph &G, const CallIn &in, const CallOpts &opt, CallOut &out) {
-	out = CallOut();
+PV_KERNEL(C_pack, 24);
+PV_KERNEL(C_keep, 12);
+PV_KERNEL(C_sizes, 24);
+
+inline void call_device(Ctx &c, const DevGraph &G, const CallIn &in, const CallOpts &opt, Records &out) {
+	out.reset();
 	out.rec_grpOff.push_back(0); out.rec_gtOff.push_back(0);
+	out.cpOff = G.cpOff; out.cpList = G.cpList;
 	const u32 nFl = in.nFl, nRefs = in.nRefs, H = G.H;
 	if (nFl == 0 || nRefs == 0 || H == 0) return;
 	const GraphView g = view(G);
+	Trace tr(c, "call");
 
 	// ------------------------------------------------------------------ C1: region selection
 	Buf<u32> fa(c, nFl), fz(c, nFl), fpar(c, nFl), fbase(c, nFl), refs(c, nRefs), colored(c, nFl), kid(c, nFl), called(c, nFl);
 	{
-		std::vector<u32> ha(nFl), hz(nFl);
-		for (u32 i = 0; i < nFl; i++) { ha[i] = (in.a_v[i] << 1) | (in.a_fwd[i] ? 0u : 1u); hz[i] = (in.z_v[i] << 1) | (in.z_fwd[i] ? 0u : 1u); }
-		c.h2d(fa.p, ha.data(), (size_t)nFl * 4); c.h2d(fz.p, hz.data(), (size_t)nFl * 4);
+		Buf<u8> af(c, nFl), zf(c, nFl), ex(c, nFl);
+		c.h2d(fa.p, in.a_v, (size_t)nFl * 4); c.h2d(fz.p, in.z_v, (size_t)nFl * 4); c.h2d(af.p, in.a_fwd, nFl); c.h2d(zf.p, in.z_fwd, nFl);
 		c.h2d(fpar.p, in.parent, (size_t)nFl * 4); c.h2d(fbase.p, in.flBase, (size_t)nFl * 4); c.h2d(refs.p, in.refs, (size_t)nRefs * 4);
-		if (in.excluded) for (u32 i = 0; i < nFl; i++) if (in.excluded[i]) ha[i] = NONE;
-		if (in.excluded) c.h2d(fa.p, ha.data(), (size_t)nFl * 4);
-		c.sync();   // the staging vectors die here
+		if (in.excluded) c.h2d(ex.p, in.excluded, nFl);
+		u32 *fa_w = fa.p, *fz_w = fz.p; const u8 *af_ = af.p, *zf_ = zf.p, *ex_ = in.excluded ? ex.p : nullptr;
+		parallel_for<C_pack>(c, nFl, PV_LAMBDA(size_t f) {   // (vertex << 1) | reverse; NONE hides an excluded flubble
+			fa_w[f] = (ex_ && ex_[f]) ? NONE : ((fa_w[f] << 1) | (af_[f] ? 0u : 1u));
+			fz_w[f] = (fz_w[f] << 1) | (zf_[f] ? 0u : 1u);
+		});
 	}
 	const u32 *fa_ = fa.p, *fz_ = fz.p, *fpar_ = fpar.p, *fbase_ = fbase.p, *refs_ = refs.p;
 	u32 *colored_ = colored.p, *kid_ = kid.p, *called_ = called.p;
@@ -452,26 +481,31 @@ inline void call_device(Ctx &c, const DevGraph &G, const CallIn &in, const CallO
 	Buf<u32> rov0;
 	const u32 R0 = compact_flags(c, called.p, nFl, rov0);
 	out.n_called = R0;
+	tr.mark("C1 select");
 	if (R0 == 0) return;
 
 	// ------------------------------------------------------------------ C2: vertex order per region
 	// tier 0: thread-private scratch; overflowing regions retry with 16x larger slices of a global arena
-	const u32 T0 = 12;
-	Buf<u32> J0(c, R0), vtmp(c, (size_t)R0 * T0);
-	u32 *J0_ = J0.p, *vtmp_ = vtmp.p; const u32 *rov0_ = rov0.p;
+	Buf<u32> J0(c, R0), vtmp(c, (size_t)R0 * 12), cnt(c, 8);
+	cnt.zero();
+	u32 *J0_ = J0.p, *vtmp_ = vtmp.p, *cnt_ = cnt.p; const u32 *rov0_ = rov0.p;
 	parallel_for<C_bfs>(c, R0, PV_LAMBDA(size_t r) {
 		u32 tv[12], es[13], et[32], dg[12], od[12], ov[12];
 		BfsScratch s{12, 32, tv, es, et, dg, od, nullptr, nullptr, 0};
 		u32 f = rov0_[r];
 		u32 n = bfs_kahn_sort(g, fa_[f] >> 1, !(fa_[f] & 1u), fz_[f] >> 1, !(fz_[f] & 1u), s, ov);
 		J0_[r] = n;
-		if (n != NONE) for (u32 k = 0; k < n; k++) vtmp_[r * 12 + k] = ov[k];
+		if (n == NONE) { atomic_add(cnt_ + 0, 1u); return; }
+		for (u32 k = 0; k < n; k++) vtmp_[r * 12 + k] = ov[k];
 	});
-	std::vector<u32> hJ = J0.to_host();
-	struct BigRes { u32 r; std::vector<u32> verts; };
-	std::vector<BigRes> big;
-	{
-		std::vector<u32> todo;
+	u32 hc[8]; c.d2h(hc, cnt.p, 32);
+	// regions that did not fit tier 0: host-driven retries; their orders land in bigVerts[bigOff[r] ..)
+	Buf<u32> bigOff(c, (size_t)R0 + 1), bigVerts;
+	bool haveBig = hc[0] != 0;
+	if (haveBig) {
+		std::vector<u32> hJ = J0.to_host();
+		std::vector<u32> todo, hBigOff((size_t)R0 + 1, 0), hBigVerts;
+		std::vector<std::vector<u32>> res(R0);
 		for (u32 r = 0; r < R0; r++) if (hJ[r] == NONE) todo.push_back(r);
 		u64 capV64 = 256;
 		while (!todo.empty()) {
@@ -484,9 +518,9 @@ inline void call_device(Ctx &c, const DevGraph &G, const CallIn &in, const CallO
 			std::vector<u32> next;
 			for (size_t b0 = 0; b0 < todo.size(); b0 += slice) {
 				const u32 nb = (u32)std::min<size_t>(slice, todo.size() - b0);
-				Buf<u32> list(c, nb), arena(c, (size_t)nb * per), res(c, nb);
+				Buf<u32> list(c, nb), arena(c, (size_t)nb * per), rs(c, nb);
 				c.h2d(list.p, todo.data() + b0, (size_t)nb * 4);
-				u32 *arena_ = arena.p, *res_ = res.p; const u32 *list_ = list.p;
+				u32 *arena_ = arena.p, *res_ = rs.p; const u32 *list_ = list.p;
 				parallel_for<C_bfs>(c, nb, PV_LAMBDA(size_t i) {
 					u32 *base = arena_ + i * per;
 					const size_t cv = capV, ce = capE;
@@ -495,56 +529,77 @@ inline void call_device(Ctx &c, const DevGraph &G, const CallIn &in, const CallO
 					u32 f = rov0_[list_[i]];
 					res_[i] = bfs_kahn_sort(g, fa_[f] >> 1, !(fa_[f] & 1u), fz_[f] >> 1, !(fz_[f] & 1u), s, base + 4 * cv + 1 + ce);
 				});
-				std::vector<u32> hres = res.to_host();
+				std::vector<u32> hres = rs.to_host();
 				for (u32 i = 0; i < nb; i++) {
 					u32 r = todo[b0 + i];
 					if (hres[i] == NONE) { next.push_back(r); continue; }
-					BigRes br; br.r = r; br.verts.resize(hres[i]);
-					if (hres[i]) c.d2h(br.verts.data(), arena.p + (size_t)i * per + 4 * (size_t)capV + 1 + capE, (size_t)hres[i] * 4);
+					res[r].resize(hres[i]);
+					if (hres[i]) c.d2h(res[r].data(), arena.p + (size_t)i * per + 4 * (size_t)capV + 1 + capE, (size_t)hres[i] * 4);
 					hJ[r] = hres[i]; out.n_big_bfs++;
-					big.push_back(std::move(br));
 				}
 			}
 			if (!next.empty() && last) throw std::runtime_error("call: region BFS overflow at full-graph capacity");
 			todo.swap(next);
 			capV64 *= 16;
 		}
-	}
-	// keep regions with >= 3 sorted vertices (rov.cpp:208-212); a failed sort (0) needs the reference's
-	// haplotype-lap fallback order (graph.cpp:194-395), which is not on the device yet -> counted, skipped
-	std::vector<u32> keep, hOff{0};
-	for (u32 r = 0; r < R0; r++) {
-		if (hJ[r] == 0) { out.n_sort_failed++; continue; }
-		if (hJ[r] < 3) { out.n_too_small++; continue; }
-		keep.push_back(r); hOff.push_back(hOff.back() + hJ[r]);
-	}
-	const u32 R = (u32)keep.size();
-	if (R == 0) return;
-	const u32 sumJ = hOff.back();
-	Buf<u32> rovOff(c, (size_t)R + 1), rovVerts(c, sumJ), rovSrc(c, R), rovFl(c, R), rovComp(c, R);
-	c.h2d(rovOff.p, hOff.data(), ((size_t)R + 1) * 4); c.h2d(rovSrc.p, keep.data(), (size_t)R * 4);
-	u32 *rovVerts_ = rovVerts.p, *rovFl_ = rovFl.p, *rovComp_ = rovComp.p; const u32 *rovOff_ = rovOff.p, *rovSrc_ = rovSrc.p;
-	parallel_for<C_gather>(c, R, PV_LAMBDA(size_t r) {
-		u32 s = rovSrc_[r]; u32 n = J0_[s]; u32 o = rovOff_[r];
-		rovFl_[r] = rov0_[s];
-		if (n != NONE) for (u32 k = 0; k < n; k++) rovVerts_[o + k] = vtmp_[s * 12 + k];
-		// component of the region = component of any path through its start boundary (a called region is
-		// touched by every reference path)
-		u32 a = fa_[rov0_[s]] >> 1;
-		rovComp_[r] = g.pathComp[g.vsHap[g.vsOff[a]]];
-	});
-	if (!big.empty()) {
-		std::vector<u32> pos(R0, NONE);
-		for (u32 r = 0; r < R; r++) pos[keep[r]] = r;
-		for (auto &b : big) if (pos[b.r] != NONE) c.h2d(rovVerts.p + hOff[pos[b.r]], b.verts.data(), b.verts.size() * 4);
+		for (u32 r = 0; r < R0; r++) { hBigOff[r + 1] = hBigOff[r] + (u32)res[r].size(); hBigVerts.insert(hBigVerts.end(), res[r].begin(), res[r].end()); }
+		bigVerts = Buf<u32>(c, hBigVerts.size() ? hBigVerts.size() : 1);
+		c.h2d(bigOff.p, hBigOff.data(), ((size_t)R0 + 1) * 4); c.h2d(bigVerts.p, hBigVerts.data(), hBigVerts.size() * 4); c.h2d(J0.p, hJ.data(), (size_t)R0 * 4);
 		c.sync();
 	}
-	out.rov_fl = rovFl.to_host(); out.rov_comp = rovComp.to_host();
-	out.rov_J.resize(R); for (u32 r = 0; r < R; r++) { out.rov_J[r] = hOff[r + 1] - hOff[r]; if (out.rov_J[r] > out.max_J) out.max_J = out.rov_J[r]; }
-	out.rov_tangled.assign(R, 0);
+	tr.mark("C2 bfs");
+	// keep regions with >= 3 sorted vertices (rov.cpp:208-212); a failed sort (0) needs the reference's
+	// haplotype-lap fallback order (graph.cpp:194-395), which is not on the device yet -> counted, skipped
+	Buf<u32> keepF(c, R0), rovSrc;
+	u32 *keepF_ = keepF.p;
+	parallel_for<C_keep>(c, R0, PV_LAMBDA(size_t r) {
+		u32 n = J0_[r];
+		keepF_[r] = n >= 3 ? 1u : 0u;
+		if (n == 0) atomic_add(cnt_ + 1, 1u); else if (n < 3) atomic_add(cnt_ + 2, 1u);
+	});
+	const u32 R = compact_flags(c, keepF.p, R0, rovSrc);
+	if (R == 0) { c.d2h(hc, cnt.p, 32); out.n_sort_failed = hc[1]; out.n_too_small = hc[2]; return; }
+	Buf<u32> rovJ(c, (size_t)R + 1), rovOff(c, (size_t)R + 1), rovFl(c, R), rovComp(c, R), rovTangled(c, R);
+	Buf<u64> rowsOf(c, (size_t)R + 1), cellsOf(c, (size_t)R + 1), rowPre(c, (size_t)R + 1), cellPre(c, (size_t)R + 1), tot(c, 4);
+	tot.zero(); rovTangled.zero();
+	u32 *rovJ_ = rovJ.p, *rovFl_ = rovFl.p, *rovComp_ = rovComp.p, *rovTangled_ = rovTangled.p; const u32 *rovSrc_ = rovSrc.p;
+	u64 *rowsOf_ = rowsOf.p, *cellsOf_ = cellsOf.p, *tot_ = tot.p;
+	parallel_for<C_sizes>(c, (size_t)R + 1, PV_LAMBDA(size_t r) {
+		if (r >= R) { rovJ_[r] = 0; rowsOf_[r] = 0; cellsOf_[r] = 0; return; }
+		u32 s = rovSrc_[r]; u32 n = J0_[s]; u32 f = rov0_[s];
+		rovJ_[r] = n; rovFl_[r] = f;
+		// component of the region = component of any path through its start boundary (a selected region is
+		// touched by every reference path)
+		u32 a = fa_[f] >> 1;
+		u32 comp = g.pathComp[g.vsHap[g.vsOff[a]]];
+		rovComp_[r] = comp;
+		u32 nh = g.cpOff[comp + 1] - g.cpOff[comp];
+		rowsOf_[r] = nh; cellsOf_[r] = (u64)nh * n;
+		atomic_max(tot_ + 0, (u64)n);
+		if (n > 16) atomic_add(tot_ + 1, (u64)n);
+	});
+	exclusive_scan(c, rovJ.p, rovOff.p, (size_t)R + 1, OpAddU32(), 0u);
+	exclusive_scan(c, rowsOf.p, rowPre.p, (size_t)R + 1, OpAddU64(), (u64)0);
+	exclusive_scan(c, cellsOf.p, cellPre.p, (size_t)R + 1, OpAddU64(), (u64)0);
+	u64 ht[4]; c.d2h(ht, tot.p, 32);
+	u64 totRows, totCells; c.d2h(&totRows, rowPre.p + R, 8); c.d2h(&totCells, cellPre.p + R, 8);
+	const u32 sumJ = rovOff.read(R);
+	out.max_J = ht[0];
+	Buf<u32> rovVerts(c, sumJ);
+	u32 *rovVerts_ = rovVerts.p; const u32 *rovOff_ = rovOff.p;
+	{
+		const u32 *bigOff_ = bigOff.p, *bigVerts_ = bigVerts.p;
+		parallel_for<C_gather>(c, R, PV_LAMBDA(size_t r) {
+			u32 s = rovSrc_[r]; u32 n = rovJ_[r]; u32 o = rovOff_[r];
+			if (haveBig && bigOff_[s + 1] > bigOff_[s]) { for (u32 k = 0; k < n; k++) rovVerts_[o + k] = bigVerts_[bigOff_[s] + k]; }
+			else for (u32 k = 0; k < n; k++) rovVerts_[o + k] = vtmp_[s * 12 + k];
+		});
+	}
+	rovFl.to_hvec(out.rov_fl, R); rovComp.to_hvec(out.rov_comp, R);
+	tr.mark("C2 gather");
 
 	// hash (region, vertex) -> column for regions with more than 16 vertices
-	u64 bigJ = 0; for (u32 r = 0; r < R; r++) if (out.rov_J[r] > 16) bigJ += out.rov_J[r];
+	const u64 bigJ = ht[1];
 	u64 hsize = 2; while (hsize < 2 * bigJ + 2) hsize <<= 1;
 	Buf<u64> hkey(c, hsize); Buf<u32> hval(c, hsize);
 	hkey.fill_ff();
@@ -560,49 +615,61 @@ inline void call_device(Ctx &c, const DevGraph &G, const CallIn &in, const CallO
 	}
 
 	// ------------------------------------------------------------------ chunks of regions bounded by matrix cells
-	std::vector<u32> nhOf(R);
-	bool uniform = true;
-	for (u32 r = 0; r < R; r++) { u32 k = out.rov_comp[r]; nhOf[r] = G.cpOff[k + 1] - G.cpOff[k]; if (nhOf[r] != nhOf[0]) uniform = false; }
-
-	for (u32 r0 = 0; r0 < R;) {
-		u64 cells = 0, rows = 0; u32 r1 = r0;
-		while (r1 < R) {
-			u64 cc = (u64)nhOf[r1] * out.rov_J[r1];
-			if (r1 > r0 && (cells + cc > opt.cell_budget || rows + nhOf[r1] > 0x7FFFFFF0ull)) break;
-			cells += cc; rows += nhOf[r1]; r1++;
+	u32 uniformNh = 0;
+	{
+		bool uni = G.cpOff.size() > 1;
+		for (size_t k = 1; k + 1 < G.cpOff.size(); k++) if (G.cpOff[k + 1] - G.cpOff[k] != G.cpOff[1] - G.cpOff[0]) uni = false;
+		if (uni) uniformNh = G.cpOff[1] - G.cpOff[0];
+	}
+	std::vector<u32> chunkEnd;   // exclusive region index of every chunk
+	std::vector<u64> hRowPre, hCellPre;
+	if (totCells <= opt.cell_budget && totRows <= 0x7FFFFFF0ull) chunkEnd.push_back(R);
+	else {
+		hRowPre.resize((size_t)R + 1); hCellPre.resize((size_t)R + 1);
+		c.d2h(hRowPre.data(), rowPre.p, ((size_t)R + 1) * 8); c.d2h(hCellPre.data(), cellPre.p, ((size_t)R + 1) * 8);
+		for (u32 r0 = 0; r0 < R;) {
+			u32 r1 = r0 + 1;
+			while (r1 < R && hCellPre[r1 + 1] - hCellPre[r0] <= opt.cell_budget && hRowPre[r1 + 1] - hRowPre[r0] <= 0x7FFFFFF0ull) r1++;
+			chunkEnd.push_back(r1); r0 = r1;
 		}
-		const u32 Rc = r1 - r0; const u32 nRows = (u32)rows;
+	}
+	Buf<u32> errs(c, 4);
+	errs.zero();
+
+	u32 r0 = 0;
+	for (u32 r1 : chunkEnd) {
+		const u32 Rc = r1 - r0;
+		u64 rows, cells;
+		if (chunkEnd.size() == 1) { rows = totRows; cells = totCells; } else { rows = hRowPre[r1] - hRowPre[r0]; cells = hCellPre[r1] - hCellPre[r0]; }
+		const u32 nRows = (u32)rows;
 		out.n_chunks++;
-		std::vector<u32> hRow(Rc + 1, 0); std::vector<u64> hMat(Rc + 1, 0);
-		for (u32 i = 0; i < Rc; i++) { hRow[i + 1] = hRow[i] + nhOf[r0 + i]; hMat[i + 1] = hMat[i] + (u64)nhOf[r0 + i] * out.rov_J[r0 + i]; }
-		Buf<u32> rowBase(c, (size_t)Rc + 1); Buf<u64> matBase(c, (size_t)Rc + 1);
-		c.h2d(rowBase.p, hRow.data(), ((size_t)Rc + 1) * 4); c.h2d(matBase.p, hMat.data(), ((size_t)Rc + 1) * 8);
-		c.sync();
 		Buf<u16> mat(c, cells ? cells : 1);
-		Buf<u32> lapStart(c, nRows ? nRows : 1), lapLen(c, nRows ? nRows : 1), tangled(c, Rc), hasData(c, Rc), errs(c, 4);
-		c.memset0(mat.p, cells * 2); lapStart.fill_ff(); tangled.zero(); hasData.zero(); errs.zero();
-		// rv.rovOff is shifted to the chunk but still indexes the global vertex array
-		const RovView rv{rovOff.p + r0, rovVerts.p, rovComp.p + r0, rowBase.p, matBase.p, hkey.p, hval.p, hsize - 1, Rc, uniform ? nhOf[0] : 0u, r0};
-		const ChunkView cv{g, rv, mat.p, lapStart.p, lapLen.p, tangled.p, hasData.p, errs.p};
+		Buf<u32> lapStart(c, nRows ? nRows : 1), lapLen(c, nRows ? nRows : 1), hasData(c, Rc);
+		c.memset0(mat.p, cells * 2); lapStart.fill_ff(); hasData.zero();
+		const RovView rv{rovOff.p, rovVerts.p, rovComp.p, rowPre.p, cellPre.p, hkey.p, hval.p, hsize - 1, Rc, uniformNh, r0};
+		const ChunkView cv{g, rv, mat.p, lapStart.p, lapLen.p, rovTangled_ + r0, hasData.p, errs.p};
+		tr.mark("chunk setup");
 		// ---- C3: depth matrix (allele.hpp:804-862), one thread per (region, column)
-		const u32 colBase = hOff[r0]; const u32 nCols = hOff[r1] - hOff[r0];
+		u32 colBase, colEnd;
+		if (chunkEnd.size() == 1) { colBase = 0; colEnd = sumJ; } else { colBase = rovOff.read(r0); colEnd = rovOff.read(r1); }
+		const u32 nCols = colEnd - colBase;
 		parallel_for<C_matfill>(c, nCols, PV_LAMBDA(size_t x) {
-			u32 r = ub_u32(rv.rovOff, 0, Rc + 1, colBase + (u32)x) - 1;
-			u32 J = rv.J(r); u32 j = colBase + (u32)x - rv.rovOff[r];
-			u32 v = rv.rovVerts[colBase + x];
-			u32 comp = rv.rovComp[r];
+			u32 r = ub_u32(rovOff_ + r0, 0, Rc + 1, colBase + (u32)x) - 1;
+			u32 J = rv.J(r); u32 j = colBase + (u32)x - rovOff_[r0 + r];
+			u32 v = rovVerts_[colBase + x];
+			u32 comp = rv.comp(r);
 			u32 e = g.vsOff[v], ee = g.vsOff[v + 1];
 			while (e < ee) {
-				u32 h = g.vsHap[e]; u32 first = g.vsStep[e]; u32 cnt = 1;
-				while (e + cnt < ee && g.vsHap[e + cnt] == h) cnt++;
-				e += cnt;
+				u32 h = g.vsHap[e]; u32 first = g.vsStep[e]; u32 n = 1;
+				while (e + n < ee && g.vsHap[e + n] == h) n++;
+				e += n;
 				if (g.pathComp[h] != comp) continue;   // cannot happen for a connected walk; keeps indexing safe
 				u32 i = g.hapLocal[h];
-				if (cnt > 0xFFFEu) { atomic_add(cv.errs + 2, 1u); cnt = 0xFFFEu; }
-				u32 code = cnt == 1 ? ((g.steps[first] & 1u) ? 2u : 1u) : cnt;
-				cv.mat[rv.matBase[r] + (u64)i * J + j] = (u16)code;
-				atomic_min(cv.lapStart + rv.rowBase[r] + i, first);
-				if (cnt > 1 && (j == 0 || j == J - 1)) cv.tangled[r] = 1;
+				if (n > 0xFFFEu) { atomic_add(cv.errs + 2, 1u); n = 0xFFFEu; }
+				u32 code = n == 1 ? ((g.steps[first] & 1u) ? 2u : 1u) : n;
+				cv.mat[rv.matBase(r) + (u64)i * J + j] = (u16)code;
+				atomic_min(cv.lapStart + rv.rowBase(r) + i, first);
+				if (n > 1 && (j == 0 || j == J - 1)) cv.tangled[r] = 1;
 			}
 		});
 		// ---- C4: lap 0 of every (region, path): the first run of consecutive steps on region vertices (untangle.cpp:29-103)
@@ -616,14 +683,12 @@ inline void call_device(Ctx &c, const DevGraph &G, const CallIn &in, const CallO
 			while (s + len < end && rv.find(r, g.steps[s + len] >> 1) != NONE) len++;
 			cv.lapLen[row] = len;
 		});
-		{
-			std::vector<u32> hT = tangled.to_host();
-			for (u32 i = 0; i < Rc; i++) if (hT[i]) { out.rov_tangled[r0 + i] = 1; out.n_tangled++; }
-		}
+		tr.mark("C3 C4 matrix+laps");
 
 		for (u32 k = 0; k < nRefs; k++) {
 			const u32 refH = in.refs[k];
 			const u32 refLocal = G.hapLocal[refH];
+			const u32 refStep0 = G.h_stepOff[refH];
 			// ---- C5a: contexts per (region, path) pair
 			Buf<u32> pairCnt(c, (size_t)nRows + 1), candOff(c, (size_t)nRows + 1);
 			u32 *pairCnt_ = pairCnt.p; const u32 *candOff_ = candOff.p;
@@ -640,13 +705,14 @@ inline void call_device(Ctx &c, const DevGraph &G, const CallIn &in, const CallO
 				if (candOff_[row + 1] == candOff_[row]) return;
 				scan_pair(cv, refLocal, k, (u32)row, true, cd, candOff_[row]);
 			});
+			tr.mark("C5 pairs");
 			// ---- C6a: group alt slices by (context, class, walk) per region, order groups like the reference's std::maps
 			Buf<u32> recCnt(c, (size_t)Rc + 1), grpCnt(c, (size_t)Rc + 1), recOff(c, (size_t)Rc + 1), grpOff(c, (size_t)Rc + 1);
 			u32 *recCnt_ = recCnt.p, *grpCnt_ = grpCnt.p;
 			parallel_for<C_group>(c, (size_t)Rc + 1, PV_LAMBDA(size_t rr_) {
 				if (rr_ >= Rc) { recCnt_[rr_] = 0; grpCnt_[rr_] = 0; return; }
 				u32 r = (u32)rr_;
-				u32 b = candOff_[rv.rowBase[r]], e = candOff_[rv.rowBase[r + 1]];
+				u32 b = candOff_[rv.rowBase(r)], e = candOff_[rv.rowBase(r + 1)];
 				u32 *a = cd.hsort + b; u32 nh = 0;
 				for (u32 x = b; x < e; x++) {
 					if (cd.cCls[x] == 3) continue;
@@ -670,36 +736,37 @@ inline void call_device(Ctx &c, const DevGraph &G, const CallIn &in, const CallO
 			exclusive_scan(c, grpCnt.p, grpOff.p, (size_t)Rc + 1, OpAddU32(), 0u);
 			const u32 nRec = recOff.read(Rc), nGrp = grpOff.read(Rc);
 			if (nRec == 0) continue;
-			// ---- C6b: records + groups
-			Buf<u32> oRov(c, nRec), oL(c, nRec), oR(c, nRec), oVt(c, nRec), oPos(c, nRec), oRS(c, nRec), oRL(c, nRec), oGrp(c, (size_t)nRec + 1);
+			// ---- C6b: records + groups (offsets already global: the host only appends)
+			const u32 grpBase = (u32)out.grp_hap.size(); const u64 gtBase = out.gt.size(); const size_t recBase = out.rec_rov.size();
+			Buf<u32> oRov(c, nRec), oRef(c, nRec), oL(c, nRec), oR(c, nRec), oVt(c, nRec), oPos(c, nRec), oRS(c, nRec), oRL(c, nRec), oGrp(c, (size_t)nRec + 1);
 			Buf<u32> gHap(c, nGrp), gStart(c, nGrp), gLen(c, nGrp), gCnt(c, nGrp), headRec(c, nCand), headOrd(c, nCand);
 			Buf<u64> gtOff(c, (size_t)nRec + 1), recNh(c, (size_t)nRec + 1);
-			u32 *oRov_ = oRov.p, *oL_ = oL.p, *oR_ = oR.p, *oVt_ = oVt.p, *oPos_ = oPos.p, *oRS_ = oRS.p, *oRL_ = oRL.p, *oGrp_ = oGrp.p;
+			u32 *oRov_ = oRov.p, *oRef_ = oRef.p, *oL_ = oL.p, *oR_ = oR.p, *oVt_ = oVt.p, *oPos_ = oPos.p, *oRS_ = oRS.p, *oRL_ = oRL.p, *oGrp_ = oGrp.p;
 			u32 *gHap_ = gHap.p, *gStart_ = gStart.p, *gLen_ = gLen.p, *gCnt_ = gCnt.p, *headRec_ = headRec.p, *headOrd_ = headOrd.p;
 			u64 *gtOff_ = gtOff.p, *recNh_ = recNh.p; const u32 *recOff_ = recOff.p, *grpOff_ = grpOff.p;
 			parallel_for<C_emit>(c, Rc, PV_LAMBDA(size_t rr_) {
 				u32 r = (u32)rr_;
 				u32 nh = grpOff_[r + 1] - grpOff_[r];
 				if (!nh) return;
-				const u32 *a = cd.hsort + candOff_[rv.rowBase[r]];
+				const u32 *a = cd.hsort + candOff_[rv.rowBase(r)];
 				u32 rec = recOff_[r], gi = grpOff_[r]; u32 ord = 0;
-				u32 nhaps = rv.rowBase[r + 1] - rv.rowBase[r];
+				u32 nhaps = rv.rowBase(r + 1) - rv.rowBase(r);
 				for (u32 t = 0; t < nh; t++) {
 					u32 y = a[t];
 					if (t == 0 || !same_record(cd, a[t - 1], y)) {
 						if (t) rec++;
 						ord = 0;
 						u32 cls = cd.cCls[y];
-						oRov_[rec] = r + rv.rShift; oL_[rec] = cd.cL[y]; oR_[rec] = cd.cR[y];
+						oRov_[rec] = r + rv.rShift; oRef_[rec] = refH; oL_[rec] = cd.cL[y]; oR_[rec] = cd.cR[y];
 						oVt_[rec] = cls == 0 ? (u32)VT_INS : (cls == 1 ? (u32)VT_SUB : (u32)VT_DEL);
 						oRS_[rec] = cd.cRS[y]; oRL_[rec] = cd.cRL[y];
 						u32 l = g.loci[cd.cRS[y] + 1];                       // comp_pos (allele.hpp:161-179)
 						oPos_[rec] = cls == 1 ? l : l - 1;
-						oGrp_[rec] = gi; recNh_[rec] = nhaps;
+						oGrp_[rec] = grpBase + gi; recNh_[rec] = nhaps;
 					}
 					ord++;
 					headRec_[y] = rec; headOrd_[y] = ord;
-					u32 hh = g.cpList[g.cpOff[rv.rovComp[r]] + cd.cHap[y]];
+					u32 hh = g.cpList[g.cpOff[rv.comp(r)] + cd.cHap[y]];
 					gHap_[gi] = hh; gStart_[gi] = cd.cStart[y] - g.stepOff[hh]; gLen_[gi] = cd.cLen[y]; gCnt_[gi] = cd.gCount[y];
 					gi++;
 				}
@@ -710,18 +777,18 @@ inline void call_device(Ctx &c, const DevGraph &G, const CallIn &in, const CallO
 			Buf<u16> gt(c, nGt ? nGt : 1);
 			c.memset_ff(gt.p, nGt * 2);
 			u16 *gt_ = gt.p;
+			tr.mark("C6 group+emit");
 			// ---- C7: genotypes.  Paths equal to the ref over the context columns with an identical slice -> 0 (overlay.cpp:534-580)
-			const u32 uniNh = rv.uniformNh;
 			parallel_for<C_gt_ref>(c, nGt, PV_LAMBDA(size_t x) {
-				u32 rec = uniNh ? (u32)(x / uniNh) : (u32)(ub_u64(gtOff_, 0, (u64)nRec + 1, (u64)x) - 1);
+				u32 rec = uniformNh ? (u32)(x / uniformNh) : (u32)(ub_u64(gtOff_, 0, (u64)nRec + 1, (u64)x) - 1);
 				u32 i = (u32)(x - gtOff_[rec]);
 				u32 r = oRov_[rec] - rv.rShift; u32 J = rv.J(r);
 				u32 lv = oL_[rec] >> 1, rvx = oR_[rec] >> 1;
 				u32 ju = rv.find(r, lv), jv = rv.find(r, rvx);
 				if (ju > jv) { u32 t = ju; ju = jv; jv = t; }
-				const u16 *rr = cv.mat + rv.matBase[r] + (u64)refLocal * J, *ar = cv.mat + rv.matBase[r] + (u64)i * J;
+				const u16 *rr = cv.mat + rv.matBase(r) + (u64)refLocal * J, *ar = cv.mat + rv.matBase(r) + (u64)i * J;
 				for (u32 j = ju; j <= jv; j++) if (rr[j] != ar[j]) return;
-				u32 row = rv.rowBase[r] + i;
+				u32 row = rv.rowBase(r) + i;
 				if (cv.lapStart[row] == NONE) return;
 				u32 as, an;
 				if (!slice_bounds(g, lv, rvx, cv.lap(row), as, an)) return;
@@ -733,25 +800,30 @@ inline void call_device(Ctx &c, const DevGraph &G, const CallIn &in, const CallO
 				u32 hd = cd.cHead[x]; u32 rec = headRec_[hd];
 				gt_[gtOff_[rec] + cd.cHap[x]] = (u16)headOrd_[hd];
 			});
-			// ---- results of this (chunk, ref) to the host
-			auto app = [&](std::vector<u32> &dst, const Buf<u32> &src, u32 n) { size_t o = dst.size(); dst.resize(o + n); c.d2h(dst.data() + o, src.p, (size_t)n * 4); };
-			const u32 grpBase = (u32)out.grp_hap.size(); const u64 gtBase = out.gt.size(); const size_t recBase = out.rec_rov.size();
-			app(out.rec_rov, oRov, nRec); app(out.rec_cxtL, oL, nRec); app(out.rec_cxtR, oR, nRec); app(out.rec_vt, oVt, nRec); app(out.rec_pos, oPos, nRec);
+			// the host sees ref-slice starts relative to the ref path, and global gt offsets
+			parallel_for<C_keep>(c, (size_t)nRec + 1, PV_LAMBDA(size_t i) { if (i < nRec) oRS_[i] -= refStep0; gtOff_[i] += gtBase; });
+			tr.mark("C7 genotypes");
+			// ---- results of this (chunk, ref): asynchronous appends into the pinned host vectors
+			auto app = [&](hvec<u32> &dst, const Buf<u32> &src, u32 n) { size_t o = dst.size(); dst.resize(o + n); c.d2h_async(dst.data() + o, src.p, (size_t)n * 4); };
+			app(out.rec_rov, oRov, nRec); app(out.rec_ref, oRef, nRec); app(out.rec_cxtL, oL, nRec); app(out.rec_cxtR, oR, nRec); app(out.rec_vt, oVt, nRec); app(out.rec_pos, oPos, nRec);
 			app(out.rec_refStart, oRS, nRec); app(out.rec_refLen, oRL, nRec);
 			app(out.grp_hap, gHap, nGrp); app(out.grp_start, gStart, nGrp); app(out.grp_len, gLen, nGrp); app(out.grp_count, gCnt, nGrp);
-			std::vector<u32> hg(nRec); c.d2h(hg.data(), oGrp.p, (size_t)nRec * 4);
-			std::vector<u64> hgt((size_t)nRec + 1); c.d2h(hgt.data(), gtOff.p, ((size_t)nRec + 1) * 8);
-			out.rec_grpOff.pop_back(); out.rec_gtOff.pop_back();
-			for (u32 i = 0; i < nRec; i++) { out.rec_grpOff.push_back(grpBase + hg[i]); out.rec_gtOff.push_back(gtBase + hgt[i]); out.rec_ref.push_back(refH); }
-			out.rec_grpOff.push_back(grpBase + nGrp); out.rec_gtOff.push_back(gtBase + nGt);
-			out.gt.resize(gtBase + nGt); c.d2h(out.gt.data() + gtBase, gt.p, nGt * 2);
-			for (size_t i = recBase; i < out.rec_rov.size(); i++) out.rec_refStart[i] -= G.h_stepOff[refH];
+			out.rec_grpOff.resize(recBase + nRec + 1); c.d2h_async(out.rec_grpOff.data() + recBase, oGrp.p, (size_t)nRec * 4);
+			out.rec_gtOff.resize(recBase + nRec + 1); c.d2h_async(out.rec_gtOff.data() + recBase, gtOff.p, ((size_t)nRec + 1) * 8);
+			out.gt.resize(gtBase + nGt); c.d2h_async(out.gt.data() + gtBase, gt.p, nGt * 2);
+			c.sync();   // the device buffers of this round die at the end of the scope
+			out.rec_grpOff[recBase + nRec] = grpBase + nGrp;
+			tr.mark("records d2h");
 		}
-		u32 he[4]; c.d2h(he, errs.p, 16);
-		out.n_hard_errors += he[0]; out.n_pin_pairs += he[1];
-		if (he[2]) throw std::runtime_error("call: a path visits one vertex more than 65534 times inside a region (u16 depth cell overflow)");
 		r0 = r1;
 	}
+	rovTangled.to_hvec(out.rov_tangled, R);
+	c.d2h(hc, cnt.p, 32);
+	out.n_sort_failed = hc[1]; out.n_too_small = hc[2];
+	u32 he[4]; c.d2h(he, errs.p, 16);
+	out.n_hard_errors = he[0]; out.n_pin_pairs = he[1];
+	if (he[2]) throw std::runtime_error("call: a path visits one vertex more than 65534 times inside a region (u16 depth cell overflow)");
+	for (u32 t : out.rov_tangled) if (t) out.n_tangled++;
 	c.sync();
 }
 

@@ -5,7 +5,7 @@
 
 struct pvgpu_ctx { pv::Ctx c; std::string err; };
 struct pvgpu_flubbles { pv::DecompOut o; };
-template <class T> static void cp(T *dst, const std::vector<T> &src) { if (dst && !src.empty()) memcpy(dst, src.data(), src.size() * sizeof(T)); }
+template <class T, class V> static void cp(T *dst, const V &src) { if (dst && !src.empty()) memcpy(dst, src.data(), src.size() * sizeof(T)); }
 
 extern "C" {
 
@@ -187,7 +187,7 @@ int pvgpu_session_call(pvgpu_session *s, const char *const *prefixes, size_t n) 
 }
 uint64_t pvgpu_session_record_count(const pvgpu_session *s) { return s->s.rec.n(); }
 void pvgpu_session_call_stats(const pvgpu_session *s, uint64_t o[10]) {
-	const pv::CallOut &c = s->s.stats;
+	const pv::Records &c = s->s.rec;
 	o[0] = c.n_called; o[1] = s->s.rec.rov_fl.size(); o[2] = c.n_tangled; o[3] = c.n_pin_pairs; o[4] = c.n_sort_failed; o[5] = c.n_hard_errors; o[6] = c.n_chunks; o[7] = c.n_too_small; o[8] = c.max_J; o[9] = c.n_big_bfs;
 }
 char *pvgpu_session_vcf_text(const pvgpu_session *s, size_t chunk, int with_date, const char *prefix, size_t *len) {

@@ -13,8 +13,11 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <stdexcept>
 #include <string>
+#include <new>
+#include <utility>
 #include <vector>
 
 #ifndef PV_EMU
@@ -88,6 +91,7 @@ struct Ctx {
 	void memset_ff(void *p, size_t bytes);
 	void h2d(void *d, const void *h, size_t bytes);
 	void d2h(void *h, const void *d, size_t bytes);   // synchronous on return
+	void d2h_async(void *h, const void *d, size_t bytes);   // caller syncs before reading h
 	void d2d(void *d, const void *s, size_t bytes);
 };
 
@@ -178,6 +182,14 @@ inline void Ctx::d2h(void *h, const void *d, size_t bytes) {
 	memcpy(h, d, bytes);
 #endif
 }
+inline void Ctx::d2h_async(void *h, const void *d, size_t bytes) {
+	if (!bytes) return;
+#ifndef PV_EMU
+	PV_CUDA_CHECK(cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, stream));
+#else
+	memcpy(h, d, bytes);
+#endif
+}
 inline void Ctx::d2d(void *d, const void *s, size_t bytes) {
 	if (!bytes) return;
 #ifndef PV_EMU
@@ -225,6 +237,45 @@ inline void Ctx::prof_collect() {
 		static constexpr u64 bytes = (bytes_per_item);           \
 	}
 
+// host vectors that receive device results: page-locked storage (D2H at PCIe speed, truly asynchronous) and no
+// zero-fill on resize; capacity is kept across calls by the owners, so steady-state steps allocate nothing.
+template <class T> struct HostAlloc {
+	typedef T value_type;
+	HostAlloc() {}
+	template <class U> HostAlloc(const HostAlloc<U> &) {}
+	T *allocate(size_t n) {
+		size_t bytes = n * sizeof(T) + 64;
+		char *raw = nullptr; u64 kind = 0;
+#ifndef PV_EMU
+		if (cudaHostAlloc((void **)&raw, bytes, cudaHostAllocDefault) == cudaSuccess) kind = 1; else { cudaGetLastError(); raw = nullptr; }
+#endif
+		if (!raw) { raw = (char *)malloc(bytes); kind = 2; }
+		if (!raw) throw std::bad_alloc();
+		*(u64 *)raw = kind;
+		return (T *)(raw + 64);
+	}
+	void deallocate(T *p, size_t) {
+		char *raw = (char *)p - 64;
+#ifndef PV_EMU
+		if (*(u64 *)raw == 1) { cudaFreeHost(raw); return; }
+#endif
+		free(raw);
+	}
+	template <class U> void construct(U *) {}                                   // resize() leaves new elements uninitialised
+	template <class U, class A0, class... A> void construct(U *p, A0 &&a0, A &&...a) { ::new ((void *)p) U(std::forward<A0>(a0), std::forward<A>(a)...); }
+	template <class U> bool operator==(const HostAlloc<U> &) const { return true; }
+	template <class U> bool operator!=(const HostAlloc<U> &) const { return false; }
+};
+template <class T> using hvec = std::vector<T, HostAlloc<T>>;
+
+// coarse phase tracer (PV_TRACE=1): synchronises, so only for finding host-side stalls
+struct Trace {
+	Ctx &c; const char *scope; bool on; double t0;
+	static double now() { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; }
+	Trace(Ctx &ctx, const char *s) : c(ctx), scope(s) { static const bool en = getenv("PV_TRACE") != nullptr; on = en; if (on) { c.sync(); t0 = now(); } }
+	void mark(const char *what) { if (!on) return; c.sync(); double t = now(); fprintf(stderr, "[trace] %s: %-28s %8.3f ms\n", scope, what, t - t0); t0 = t; }
+};
+
 // RAII device buffer (stream-ordered)
 template <class T> struct Buf {
 	Ctx *c = nullptr;
@@ -246,6 +297,8 @@ template <class T> struct Buf {
 	operator T *() const { return p; }
 	T *get() const { return p; }
 	std::vector<T> to_host() const { std::vector<T> h(n); c->d2h(h.data(), p, n * sizeof(T)); return h; }
+	// asynchronous copy of the first m elements into a pinned host vector (capacity reused); sync before reading
+	void to_hvec(hvec<T> &h, size_t m) const { h.resize(m); c->d2h_async(h.data(), p, m * sizeof(T)); }
 	T read(size_t i) const { T v; c->d2h(&v, p + i, sizeof(T)); return v; }
 };
 
@@ -273,6 +326,20 @@ inline u32 atomic_or(u32 *p, u32 v) { u32 o = *p; *p = o | v; return o; }
 inline u64 atomic_xor(u64 *p, u64 v) { u64 o = *p; *p = o ^ v; return o; }
 inline u32 atomic_exch(u32 *p, u32 v) { u32 o = *p; *p = v; return o; }
 inline u32 ld_volatile(const u32 *p) { return *p; }
+#endif
+
+// counter increment where many threads of a warp hit the same counter (e.g. one giant component): lanes with the
+// same index elect a leader that adds the group's size once.  Must be called by converged code (no early return
+// before it inside the warp's iteration).
+#ifndef PV_EMU
+PV_DEV void atomic_inc_aggregated(u32 *base, u32 idx) {
+	u32 active = __activemask();
+	u32 peers = __match_any_sync(active, idx);
+	u32 lane = threadIdx.x & 31u;
+	if ((peers & ((1u << lane) - 1u)) == 0) atomicAdd(base + idx, (u32)__popc(peers));
+}
+#else
+inline void atomic_inc_aggregated(u32 *base, u32 idx) { base[idx]++; }
 #endif
 
 // ---------------------------------------------------------------------------------------------

@@ -28,11 +28,12 @@ namespace pv {
 
 struct DecompOut {
 	// per flubble, in creation order (PVST vertex idx = local position + 1)
-	std::vector<u32> comp;      // 0-based component index (component id = comp + 1)
-	std::vector<u32> a_v, z_v;  // vertex *indices*
-	std::vector<u8> a_fwd, z_fwd;
-	std::vector<u32> parent;    // PVST idx within the component (0 = dummy root)
-	std::vector<u32> depth;     // PVST depth (root = 0)
+	hvec<u32> comp;      // 0-based component index (component id = comp + 1)
+	hvec<u32> a_v, z_v;  // vertex *indices*
+	hvec<u8> a_fwd, z_fwd;
+	hvec<u32> parent;    // PVST idx within the component (0 = dummy root)
+	hvec<u32> depth;     // PVST depth (root = 0)
+	hvec<u32> fl_base;   // index of the first flubble of the flubble's component
 	// per component
 	std::vector<u32> comp_root, comp_nv, comp_nfl, comp_has_tips, comp_nonlaminar;
 	// optional debug / parity outputs
@@ -41,6 +42,11 @@ struct DecompOut {
 	std::vector<u32> stack_fwd;
 	u32 dfs_rounds = 0;
 	u32 collisions = 0;
+	void reset() {   // keeps the (page-locked) capacity of the big arrays
+		comp.clear(); a_v.clear(); z_v.clear(); a_fwd.clear(); z_fwd.clear(); parent.clear(); depth.clear(); fl_base.clear();
+		comp_root.clear(); comp_nv.clear(); comp_nfl.clear(); comp_has_tips.clear(); comp_nonlaminar.clear();
+		stack_v.clear(); stack_class.clear(); stack_fwd.clear(); dfs_rounds = 0; collisions = 0;
+	}
 };
 
 struct DecompOpts { bool want_stack = false; u64 seed = 0x706F7675ull; };
@@ -114,12 +120,13 @@ PV_DEV void uf_union(u32 *uf, u32 a, u32 b) {
 }
 
 inline void decompose_device(Ctx &c, u32 V, u64 E, const u32 *ep1, const u32 *ep2, const DecompOpts &opt, DecompOut &out) {
-	out = DecompOut();
+	out.reset();
 	if (V == 0) return;
 	const u32 P = 2 * V;            // ports: 2*v + side (0 = left, 1 = right)
 	const u64 M = 2 * E;            // adjacency entries
 	if (M >= 0xFFFFFFF0ull) throw std::runtime_error("graph too large for 32-bit adjacency slots");
 
+	Trace tr(c, "decompose");
 	// ------------------------------------------------------------------ D1: CSR in reference edge order
 	Buf<u32> adjOff(c, P + 1), adjNbr(c, M ? M : 1), adjOwner(c, M ? M : 1), rev(c, M ? M : 1), origDeg(c, P);
 	{
@@ -155,6 +162,7 @@ inline void decompose_device(Ctx &c, u32 V, u64 E, const u32 *ep1, const u32 *ep
 	}
 	const u32 *adjOff_ = adjOff.p, *adjNbr_ = adjNbr.p, *adjOwner_ = adjOwner.p, *rev_ = rev.p, *origDeg_ = origDeg.p;
 
+	tr.mark("D1 csr");
 	// ------------------------------------------------------------------ D2: exact DFS tree by rounds
 	Buf<u32> visited(c, V), uf(c, V), comp(c, V), gcomp(c, V), entrySide(c, V);
 	Buf<u32> parent(c, P), pslot(c, P), depth(c, P), F(c, P), Fslot(c, P), J(c, P), J2(c, P), rnk(c, P);
@@ -305,12 +313,13 @@ inline void decompose_device(Ctx &c, u32 V, u64 E, const u32 *ep1, const u32 *ep
 		round++;
 	}
 	out.dfs_rounds = round;
+	tr.mark("D2 dfs rounds");
 
 	// ------------------------------------------------------------------ components (dense indices)
 	Buf<u32> isRoot(c, V), compIdxOfRoot(c, V + 1), nvOfRoot(c, V);
 	nvOfRoot.zero();
 	u32 *isRoot_ = isRoot.p, *compIdxOfRoot_ = compIdxOfRoot.p, *nvOfRoot_ = nvOfRoot.p;
-	parallel_for<K_compcount>(c, V, PV_LAMBDA(size_t v) { isRoot_[v] = gcomp_[v] == v ? 1u : 0u; atomic_add(nvOfRoot_ + gcomp_[v], 1u); });
+	parallel_for<K_compcount>(c, V, PV_LAMBDA(size_t v) { isRoot_[v] = gcomp_[v] == v ? 1u : 0u; atomic_inc_aggregated(nvOfRoot_, gcomp_[v]); });
 	Buf<u32> roots;
 	u32 nComp = compact_flags(c, isRoot.p, V, roots);
 	exclusive_scan(c, isRoot.p, compIdxOfRoot.p, V, OpAddU32(), 0u);
@@ -328,6 +337,7 @@ inline void decompose_device(Ctx &c, u32 V, u64 E, const u32 *ep1, const u32 *ep
 	exclusive_scan(c, cNv.p, cSegBase.p, (size_t)nComp + 1, OpAddU32(), 0u);
 	const u32 N = P + nComp;   // nodes in global preorder space
 
+	tr.mark("components");
 	// ------------------------------------------------------------------ D3: Euler tour + list ranking
 	Buf<u32> treeSlot(c, M ? M : 1);
 	treeSlot.fill_ff();
@@ -366,6 +376,7 @@ inline void decompose_device(Ctx &c, u32 V, u64 E, const u32 *ep1, const u32 *ep
 	});
 	parallel_for<K_pre>(c, nComp, PV_LAMBDA(size_t k) { pre2node_[cNodeBase_[k]] = P + (u32)k; });
 
+	tr.mark("D3 euler+rank");
 	// ------------------------------------------------------------------ D4: back edges, bridges, labels, keys
 	Buf<u64> X(c, (size_t)2 * (N + 1));      // 128-bit label accumulators, (lo, hi) interleaved
 	Buf<i32> cd(c, N + 1);
@@ -449,6 +460,7 @@ inline void decompose_device(Ctx &c, u32 V, u64 E, const u32 *ep1, const u32 *ep
 	exclusive_scan(c, cd.p, PC.p, (size_t)N + 1, OpAddI32(), 0);
 	const u128 *PX_ = PX.p; const i32 *PC_ = PC.p;
 
+	tr.mark("D4 labels");
 	// ------------------------------------------------------------------ D5: class stack positions
 	// pos(seg) = #entry ports before + root-path sum of w + G(entry)   (see DESIGN.md "class stack without a second traversal")
 	Buf<u32> isEnt(c, N + 1), S(c, N + 1);
@@ -499,6 +511,9 @@ inline void decompose_device(Ctx &c, u32 V, u64 E, const u32 *ep1, const u32 *ep
 	Buf<u32> ord(c, nS), wkey(c, nS);
 	u32 *ord_ = ord.p, *wkey_ = wkey.p;
 	parallel_for<K_iota>(c, nS, PV_LAMBDA(size_t i) { ord_[i] = (u32)i; });
+	// Words are sorted least-significant first; after each word a check looks for neighbours that agree on every
+	// word sorted so far but differ in the full key.  None left => equal keys are already adjacent (and still in
+	// stack order, the sort being stable), so the remaining words are skipped: 2 of 4 words in practice.
 	for (int w = 0; w < 4; w++) {
 		parallel_for<K_word>(c, nS, PV_LAMBDA(size_t i) {
 			u128 kk = stKey_[ord_[i]];
@@ -506,6 +521,18 @@ inline void decompose_device(Ctx &c, u32 V, u64 E, const u32 *ep1, const u32 *ep
 			wkey_[i] = (u32)(h >> ((w & 1) * 32));
 		});
 		radix_sort_pairs(c, wkey.p, ord.p, nS, 32);
+		if (w == 3) break;
+		c.memset0(flag.p, 4);
+		parallel_for<K_word>(c, nS, PV_LAMBDA(size_t i) {
+			if (i == 0) return;
+			u128 a = stKey_[ord_[i - 1]], b = stKey_[ord_[i]];
+			if (a.lo == b.lo && a.hi == b.hi) return;
+			bool same = (u32)a.lo == (u32)b.lo;
+			if (w >= 1) same = same && a.lo == b.lo;
+			if (w >= 2) same = same && (u32)a.hi == (u32)b.hi;
+			if (same) flag_[0] = 1;
+		});
+		if (!flag.read(0)) break;
 	}
 	Buf<u32> nxt(c, nS), prv(c, nS), newGrp(c, nS + 1), grpId(c, nS + 1), classOf(c, nS);
 	u32 *nxt_ = nxt.p, *prv_ = prv.p, *newGrp_ = newGrp.p, *grpId_ = grpId.p, *classOf_ = classOf.p;
@@ -538,6 +565,7 @@ inline void decompose_device(Ctx &c, u32 V, u64 E, const u32 *ep1, const u32 *ep
 		});
 	}
 
+	tr.mark("D5 stack+sort");
 	// ------------------------------------------------------------------ D6: flubbles + PVST parents
 	Buf<u32> segComp(c, nS), notNext(c, nS), lamBad(c, nComp ? nComp : 1);
 	u32 *segComp_ = segComp.p, *notNext_ = notNext.p, *lamBad_ = lamBad.p;
@@ -568,6 +596,10 @@ inline void decompose_device(Ctx &c, u32 V, u64 E, const u32 *ep1, const u32 *ep
 	exclusive_scan(c, open.p, flIdx.p, (size_t)nS + 1, OpAddU32(), 0u);
 	inclusive_scan(c, fn.p, fnS.p, nS, OpMP(), MP{0, -(1 << 29)});
 	u32 nFl = flIdx.read(nS);
+	Buf<u8> fAf(c, nFl ? nFl : 1), fZf(c, nFl ? nFl : 1);
+	u8 *fAf_ = fAf.p, *fZf_ = fZf.p;
+	Buf<u32> fBase(c, nFl ? nFl : 1);
+	u32 *fBase_ = fBase.p;
 	Buf<u32> fA(c, nFl ? nFl : 1), fZ(c, nFl ? nFl : 1), fOr(c, nFl ? nFl : 1), fDepth(c, nFl ? nFl : 1), fPar(c, nFl ? nFl : 1), fComp(c, nFl ? nFl : 1);
 	Buf<u32> cFlBase(c, nComp + 1);
 	u32 *fA_ = fA.p, *fZ_ = fZ.p, *fOr_ = fOr.p, *fDepth_ = fDepth.p, *fPar_ = fPar.p, *fComp_ = fComp.p, *cFlBase_ = cFlBase.p;
@@ -578,7 +610,8 @@ inline void decompose_device(Ctx &c, u32 V, u64 E, const u32 *ep1, const u32 *ep
 		u32 va = stV_[i], vz = stV_[j];
 		u32 oa = entrySide_[va] == 0 ? 1u : 0u, oz = entrySide_[vz] == 0 ? 1u : 0u;   // forward iff the child side is the right one
 		if (!oa && !oz) { u32 t = va; va = vz; vz = t; oa = 1; oz = 1; }             // normalize_endpoints (flubbles.cpp:233-243)
-		fA_[f] = va; fZ_[f] = vz; fOr_[f] = oa | (oz << 1);
+		fA_[f] = va; fZ_[f] = vz; fOr_[f] = oa | (oz << 1); fAf_[f] = (u8)oa; fZf_[f] = (u8)oz;
+		fBase_[f] = cFlBase_[segComp_[i]];
 		MP m = fnS_[i];
 		fDepth_[f] = (u32)(m.a > m.b ? m.a : m.b);
 		fComp_[f] = segComp_[i];
@@ -623,15 +656,13 @@ inline void decompose_device(Ctx &c, u32 V, u64 E, const u32 *ep1, const u32 *ep
 		}
 	});
 
+	tr.mark("D6 flubbles");
 	// ------------------------------------------------------------------ results to the host
+	fA.to_hvec(out.a_v, nFl); fZ.to_hvec(out.z_v, nFl); fPar.to_hvec(out.parent, nFl); fDepth.to_hvec(out.depth, nFl); fComp.to_hvec(out.comp, nFl);
+	fAf.to_hvec(out.a_fwd, nFl); fZf.to_hvec(out.z_fwd, nFl); fBase.to_hvec(out.fl_base, nFl);
 	u32 fl[4];
-	c.d2h(fl, flag.p, 16);
+	c.d2h(fl, flag.p, 16);   // synchronises: the asynchronous copies above have landed
 	out.collisions = fl[1];
-	out.a_v = fA.to_host(); out.z_v = fZ.to_host(); out.parent = fPar.to_host(); out.depth = fDepth.to_host(); out.comp = fComp.to_host();
-	out.a_v.resize(nFl); out.z_v.resize(nFl); out.parent.resize(nFl); out.depth.resize(nFl); out.comp.resize(nFl);
-	std::vector<u32> orv = fOr.to_host();
-	out.a_fwd.resize(nFl); out.z_fwd.resize(nFl);
-	for (u32 i = 0; i < nFl; i++) { out.a_fwd[i] = orv[i] & 1u; out.z_fwd[i] = (orv[i] >> 1) & 1u; }
 	out.comp_root = roots.to_host(); out.comp_root.resize(nComp);
 	out.comp_nv = cNv.to_host(); out.comp_nv.resize(nComp);
 	out.comp_has_tips = cHasTips.to_host();
@@ -646,6 +677,7 @@ inline void decompose_device(Ctx &c, u32 V, u64 E, const u32 *ep1, const u32 *ep
 		for (u32 i = 0; i < nS; i++) out.stack_fwd[i] = es[out.stack_v[i]] == 0;
 	}
 	c.sync();
+	tr.mark("results d2h");
 }
 
 } // namespace pv

@@ -23,8 +23,7 @@ struct Session {
 	pv::DevGraph dg; bool edges_up = false, paths_up = false;
 	pvh::Forest forest; bool forest_ready = false;
 	pv::DecompOut dec;
-	pvh::Records rec;
-	pv::CallOut stats;   // counters of the last call (vectors moved into rec)
+	pvh::Records rec;    // binary records + counters of the last call
 	std::vector<std::string> prefixes;
 	std::set<u32> ref_ids;
 
@@ -156,25 +155,24 @@ struct Session {
 	void decompose() {
 		upload_edges();
 		pv::DecompOpts opt;
+		pv::Trace tr(*c, "session");
 		pv::decompose_device(*c, g.V(), g.E(), d_ep1.p, d_ep2.p, opt, dec);
+		tr.mark("decompose_device");
 		if (dec.collisions) throw std::runtime_error("cycle-equivalence label collision detected by the exact bracket-set check");
-		forest = pvh::Forest();
-		forest.treeOff.push_back(0);
+		// the flubble table is already flat in component order: swap the (page-locked) arrays instead of copying.
+		// Components with < 3 vertices own no flubbles and get no tree (decompose.cpp:135-142).
+		forest.a_v.swap(dec.a_v); forest.z_v.swap(dec.z_v); forest.a_fwd.swap(dec.a_fwd); forest.z_fwd.swap(dec.z_fwd);
+		forest.parent.swap(dec.parent); forest.height.swap(dec.depth); forest.flBase.swap(dec.fl_base);
+		forest.family.assign(forest.a_v.size(), 'F');
+		forest.comp_id.clear(); forest.treeOff.assign(1, 0);
 		u32 base = 0;
 		for (u32 k = 0; k < dec.comp_nv.size(); k++) {
-			const u32 n = dec.comp_nfl[k];
-			if (dec.comp_nv[k] >= 3) {
-				for (u32 j = 0; j < n; j++) {
-					forest.a_v.push_back(dec.a_v[base + j]); forest.z_v.push_back(dec.z_v[base + j]);
-					forest.a_fwd.push_back(dec.a_fwd[base + j]); forest.z_fwd.push_back(dec.z_fwd[base + j]);
-					forest.parent.push_back(dec.parent[base + j]); forest.height.push_back(dec.depth[base + j]);
-					forest.flBase.push_back(forest.treeOff.back()); forest.family.push_back('F');
-				}
-				forest.comp_id.push_back(sharded ? comp_global.at(k) : k + 1); forest.treeOff.push_back(forest.n());
-			}
-			base += n;
+			base += dec.comp_nfl[k];
+			if (dec.comp_nv[k] >= 3) { forest.comp_id.push_back(sharded ? comp_global.at(k) : k + 1); forest.treeOff.push_back(base); }
+			else if (dec.comp_nfl[k]) throw std::runtime_error("decompose: flubbles in a component with fewer than 3 vertices");
 		}
 		forest_ready = true;
+		tr.mark("forest conversion");
 	}
 
 	std::string pvst_text(u32 tree) const {
@@ -217,7 +215,6 @@ struct Session {
 	void call() {
 		if (!forest_ready) throw std::runtime_error("call: no PVST forest (run decompose or read .pvst files first)");
 		upload_paths();
-		rec = pvh::Records();
 		std::vector<u32> refs(ref_ids.begin(), ref_ids.end());
 		// sub-flubble families and everything below them are never selected (color.cpp:117-125)
 		std::vector<u8> excl(forest.n(), 0); bool any_excl = false;
@@ -236,15 +233,9 @@ struct Session {
 		in.parent = forest.parent.data(); in.flBase = forest.flBase.data(); in.nRefs = (u32)refs.size(); in.refs = refs.data();
 		pv::CallOpts opt;
 		if (const char *e = getenv("POVU_B200_CELL_BUDGET")) opt.cell_budget = strtoull(e, nullptr, 10);
-		pv::CallOut o;
-		pv::call_device(*c, dg, in, opt, o);
-		rec.rov_fl = std::move(o.rov_fl); rec.rov_comp = std::move(o.rov_comp); rec.rov_tangled = std::move(o.rov_tangled);
-		rec.rec_rov = std::move(o.rec_rov); rec.rec_ref = std::move(o.rec_ref); rec.rec_cxtL = std::move(o.rec_cxtL); rec.rec_cxtR = std::move(o.rec_cxtR);
-		rec.rec_vt = std::move(o.rec_vt); rec.rec_pos = std::move(o.rec_pos); rec.rec_refStart = std::move(o.rec_refStart); rec.rec_refLen = std::move(o.rec_refLen);
-		rec.rec_grpOff = std::move(o.rec_grpOff); rec.rec_gtOff = std::move(o.rec_gtOff);
-		rec.grp_hap = std::move(o.grp_hap); rec.grp_start = std::move(o.grp_start); rec.grp_len = std::move(o.grp_len); rec.grp_count = std::move(o.grp_count);
-		rec.gt = std::move(o.gt); rec.cpOff = dg.cpOff; rec.cpList = dg.cpList;
-		stats = std::move(o);
+		pv::Trace tr(*c, "session");
+		pv::call_device(*c, dg, in, opt, rec);
+		tr.mark("call_device");
 	}
 
 	// VCF text: header + contig lines of the selected prefixes + records in the reference's chunk order.

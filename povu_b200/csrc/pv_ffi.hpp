@@ -216,7 +216,7 @@ PovuVcfOutput *povu_flubbles_call_variants(PovuFlubbles *f, PovuError *error) {
 		s.forest = f->forest; s.forest_ready = true;
 		s.set_prefixes(g->prefixes);
 		s.call();
-		if (s.stats.n_hard_errors) throw std::runtime_error("call: the reference aborts on this input (missing context boundary in a haplotype lap)");
+		if (s.rec.n_hard_errors) throw std::runtime_error("call: the reference aborts on this input (missing context boundary in a haplotype lap)");
 		PovuVcfOutput *o = new PovuVcfOutput();
 		o->vcf_content = s.vcf_header(s.prefixes, true) + s.vcf_records(100, nullptr);
 		return o;

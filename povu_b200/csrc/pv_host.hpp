@@ -25,6 +25,7 @@
 #include <sys/stat.h>
 #include <unistd.h>
 #include <vector>
+#include "pv_common.cuh"
 
 namespace pvh {
 
@@ -263,8 +264,8 @@ inline GtMeta genotype_metadata(const HostGraph &g) {
 struct Forest {
 	std::vector<u32> comp_id;                  // per tree (file): component id
 	std::vector<u32> treeOff;                  // per tree: first flubble (size = trees + 1)
-	std::vector<u32> a_v, z_v, parent, height, flBase; std::vector<u8> a_fwd, z_fwd;   // per flubble; parent/height in PVST indices
-	std::vector<char> family;                  // 'F', 'T', 'O', 'C', 'S', 'M'
+	pv::hvec<u32> a_v, z_v, parent, height, flBase; pv::hvec<u8> a_fwd, z_fwd;   // per flubble; parent/height in PVST indices (page-locked: they are copied to the device)
+	pv::hvec<char> family;                  // 'F', 'T', 'O', 'C', 'S', 'M'
 	u32 n() const { return (u32)a_v.size(); }
 };
 
@@ -415,16 +416,8 @@ inline void slice_dna(const HostGraph &g, u32 hap, u32 start, u32 len, u32 vt, s
 // fmt "{:.1f}" of double(ac)/double(an) (vcf.hpp:310-332): correctly rounded shortest-decimal, ties on the binary value
 inline void append_af(u32 ac, u32 an, std::string &o) { char b[64]; int n = snprintf(b, sizeof b, "%.1f", (double)ac / (double)an); o.append(b, (size_t)n); }
 
-// Binary records as produced by the device (pv_call.cuh CallOut), host copy
-struct Records {
-	std::vector<u32> rov_fl, rov_comp; std::vector<u8> rov_tangled;
-	std::vector<u32> rec_rov, rec_ref, rec_cxtL, rec_cxtR, rec_vt, rec_pos, rec_refStart, rec_refLen, rec_grpOff;
-	std::vector<u64> rec_gtOff;
-	std::vector<u32> grp_hap, grp_start, grp_len, grp_count;
-	std::vector<u16> gt;
-	std::vector<u32> cpOff, cpList;   // paths per component (the columns of `gt`)
-	size_t n() const { return rec_rov.size(); }
-};
+// Binary records as produced by the device (pv_call.cuh)
+typedef pv::Records Records;
 
 inline void record_text(const HostGraph &g, const GtMeta &gm, const Forest &F, const Records &R, size_t i, std::vector<std::string> &slots, std::string &o) {
 	const u32 vt = R.rec_vt[i], ref = R.rec_ref[i], fl = R.rov_fl[R.rec_rov[i]];

@@ -137,19 +137,19 @@ template <class T, class Op> inline void inclusive_scan(Ctx &c, const T *in, T *
 // ---------------------------------------------------------------------------------------------
 #ifndef PV_EMU
 static const int RS_WARPS = 8;
-static const int RS_ROUNDS = 64;
-static const int RS_SUB = 32 * RS_ROUNDS;   // elements per warp sub-tile
+static const int RS_MAX_ROUNDS = 64;        // a warp sub-tile holds 32 * rounds elements; rounds is chosen per sort so that
+                                            // small inputs still spread over every SM (latency-bound otherwise)
 
-__global__ void __launch_bounds__(RS_WARPS * 32) rs_hist_kernel(const u32 *keys, u32 *counts, size_t n, size_t nsub, int shift) {
+__global__ void __launch_bounds__(RS_WARPS * 32) rs_hist_kernel(const u32 *keys, u32 *counts, size_t n, size_t nsub, int shift, int rounds) {
 	__shared__ u32 hist[RS_WARPS][256];
 	int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	for (int d = lane; d < 256; d += 32) hist[w][d] = 0;
 	__syncwarp();
 	size_t sub = (size_t)blockIdx.x * RS_WARPS + w;
 	if (sub < nsub) {
-		size_t base = sub * RS_SUB;
+		size_t base = sub * (size_t)(32 * rounds);
 #pragma unroll 4
-		for (int r = 0; r < RS_ROUNDS; r++) {
+		for (int r = 0; r < rounds; r++) {
 			size_t i = base + (size_t)r * 32 + lane;
 			bool valid = i < n;
 			u32 d = valid ? ((keys[i] >> shift) & 255u) : 256u + lane;   // invalid lanes get unique pseudo-digits
@@ -162,16 +162,16 @@ __global__ void __launch_bounds__(RS_WARPS * 32) rs_hist_kernel(const u32 *keys,
 }
 
 __global__ void __launch_bounds__(RS_WARPS * 32) rs_scatter_kernel(const u32 *keys_in, const u32 *vals_in, u32 *keys_out, u32 *vals_out,
-								   const u32 *offsets, size_t n, size_t nsub, int shift) {
+								   const u32 *offsets, size_t n, size_t nsub, int shift, int rounds) {
 	__shared__ u32 off[RS_WARPS][256];
 	int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	size_t sub = (size_t)blockIdx.x * RS_WARPS + w;
 	if (sub >= nsub) return;
 	for (int d = lane; d < 256; d += 32) off[w][d] = offsets[(size_t)d * nsub + sub];
 	__syncwarp();
-	size_t base = sub * RS_SUB;
+	size_t base = sub * (size_t)(32 * rounds);
 #pragma unroll 4
-	for (int r = 0; r < RS_ROUNDS; r++) {
+	for (int r = 0; r < rounds; r++) {
 		size_t i = base + (size_t)r * 32 + lane;
 		bool valid = i < n;
 		u32 k = valid ? keys_in[i] : 0, v = valid ? vals_in[i] : 0;
@@ -192,18 +192,22 @@ inline void radix_sort_pairs(Ctx &c, u32 *keys, u32 *vals, size_t n, int bits) {
 	if (n <= 1 || bits <= 0) return;
 #ifndef PV_EMU
 	Buf<u32> k2(c, n), v2(c, n);
-	size_t nsub = (n + RS_SUB - 1) / RS_SUB;
+	// about 32 warps per SM: rounds = n / (32 lanes * 32 warps * #SM), clamped to [4, 64]
+	int rounds = (int)(n / ((size_t)1024 * (size_t)c.sm_count));
+	rounds = rounds < 4 ? 4 : (rounds > RS_MAX_ROUNDS ? RS_MAX_ROUNDS : rounds);
+	const size_t sub_elems = (size_t)32 * rounds;
+	size_t nsub = (n + sub_elems - 1) / sub_elems;
 	Buf<u32> counts(c, 256 * nsub);
 	unsigned blocks = (unsigned)((nsub + RS_WARPS - 1) / RS_WARPS);
 	u32 *ki = keys, *vi = vals, *ko = k2.p, *vo = v2.p;
 	for (int shift = 0; shift < bits; shift += 8) {
 		c.prof_begin("rs_hist", n, n * 4);
-		rs_hist_kernel<<<blocks, RS_WARPS * 32, 0, c.stream>>>(ki, counts.p, n, nsub, shift);
+		rs_hist_kernel<<<blocks, RS_WARPS * 32, 0, c.stream>>>(ki, counts.p, n, nsub, shift, rounds);
 		c.prof_end();
 		c.launches++;
 		exclusive_scan(c, counts.p, counts.p, 256 * nsub, OpAddU32(), 0u);
 		c.prof_begin("rs_scatter", n, n * 16);
-		rs_scatter_kernel<<<blocks, RS_WARPS * 32, 0, c.stream>>>(ki, vi, ko, vo, counts.p, n, nsub, shift);
+		rs_scatter_kernel<<<blocks, RS_WARPS * 32, 0, c.stream>>>(ki, vi, ko, vo, counts.p, n, nsub, shift, rounds);
 		c.prof_end();
 		c.launches++;
 		PV_CUDA_CHECK(cudaGetLastError());
