@@ -217,14 +217,16 @@ struct Session {
 		upload_paths();
 		std::vector<u32> refs(ref_ids.begin(), ref_ids.end());
 		// sub-flubble families and everything below them are never selected (color.cpp:117-125)
-		std::vector<u8> excl(forest.n(), 0); bool any_excl = false;
-		{
+		std::vector<u8> excl; bool any_excl = false;
+		for (char f : forest.family) if (f != 'F') { any_excl = true; break; }
+		if (any_excl) {
+			excl.assign(forest.n(), 0);
 			std::vector<u32> ord(forest.n());
 			for (u32 i = 0; i < ord.size(); i++) ord[i] = i;
 			std::stable_sort(ord.begin(), ord.end(), [&](u32 a, u32 b) { return forest.height[a] < forest.height[b]; });
 			for (u32 f : ord) {
 				u32 p = forest.parent[f];
-				if (forest.family[f] != 'F' || (p != 0 && excl[forest.flBase[f] + p - 1])) { excl[f] = 1; any_excl = true; }
+				if (forest.family[f] != 'F' || (p != 0 && excl[forest.flBase[f] + p - 1])) excl[f] = 1;
 			}
 		}
 		pv::CallIn in;
