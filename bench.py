@@ -293,8 +293,13 @@ def run_native(args):
         # compulsory bytes of the whole step: decompose 16E + 12V + 16F ; call 8*S + 16F + ~(48 + H + 16) per record
         comp_dec = 16 * E + 12 * V + 16 * n_fl
         comp_call = 8 * S + 16 * n_fl + n_rec * (48 + args.paths + 16)
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(top["name"], {}).get("dram_bytes_per_launch")
+        except Exception:
+            pass
         roofline = {"bound": "hbm", "kernel": top["name"], "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                    "traffic": None, "peak_source": peak_src, "kernel_share_of_step": top["ms"] / total_ms,
+                    "traffic": traffic, "peak_source": peak_src, "kernel_share_of_step": top["ms"] / total_ms,
                     "avg_launch_us": 1e3 * top["ms"] / top["launches"], "launches_per_step": top["launches"] / args.profile_steps,
                     "algorithmic_bytes_per_launch": top["bytes"] / top["launches"],
                     "pipeline_compulsory_bytes": {"decompose": comp_dec, "call": comp_call},
