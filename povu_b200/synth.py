@@ -259,3 +259,136 @@ def concat_components(graphs):
         off += V
     ids = np.arange(1, off + 1, dtype=np.uint32)
     return make_graph(ids, seqs, np.concatenate(links) if links else np.zeros((0, 4)), paths)
+
+
+# --------------------------------------------------------------------------------------
+# cfg3 / cfg4 / cfg5: large graphs by tiling small templates (vectorised)
+# --------------------------------------------------------------------------------------
+def tower(depth, seed=0, n_walks=8):
+    """PVST depth stress: `depth` bubbles nested inside each other.  Level d: s_d -> x_d -> t_d (alt allele) and
+    s_d -> s_{d+1} ... t_{d+1} -> t_d (the nested allele); innermost s_D -> y -> t_D.  Walk 0 goes all the way in;
+    the others leave at a random level.  Returns a template dict (see `tiled`)."""
+    rng = _rng(seed)
+    D = depth
+    # vertex layout: s_0..s_D, y, t_D..t_0, x_0..x_{D-1}
+    s = np.arange(0, D + 1); y = D + 1; t = (2 * D + 2) - np.arange(0, D + 1); x = 2 * D + 3 + np.arange(0, D)
+    V = 3 * D + 3
+    links = []
+    for d in range(D):
+        links += [link(int(s[d]), "+", int(x[d]), "+"), link(int(x[d]), "+", int(t[d]), "+"),
+                  link(int(s[d]), "+", int(s[d + 1]), "+"), link(int(t[d + 1]), "+", int(t[d]), "+")]
+    links += [link(int(s[D]), "+", y, "+"), link(y, "+", int(t[D]), "+")]
+    seqs = ["".join("ACGT"[int(c)] for c in rng.integers(0, 4, size=int(rng.integers(1, 4)))) for _ in range(V)]
+    walks = []
+    for w in range(n_walks):
+        k = D if w == 0 else int(rng.integers(0, D + 1))
+        mid = [y] if k == D else [int(x[k])]
+        st = list(s[:k + 1]) + mid + list(t[:k + 1][::-1])
+        walks.append((np.array(st, dtype=np.uint32), np.zeros(len(st), dtype=np.uint8)))
+    return {"V": V, "seqs": seqs, "links": np.asarray(links, dtype=np.int64).reshape(-1, 4), "walks": walks}
+
+
+def template_from(g):
+    """A two-tip graph with source-to-sink paths -> tiling template (its paths become the walk choices)."""
+    L = np.stack([g["v1"].astype(np.int64), g["s1"].astype(np.int64), g["v2"].astype(np.int64), g["s2"].astype(np.int64)], 1)
+    return {"V": len(g["ids"]), "seqs": g["seqs"], "links": L, "walks": [(np.asarray(p[1], np.uint32), np.asarray(p[2], np.uint8)) for p in g["paths"]]}
+
+
+def tiled(templates, n_instances, n_paths, seed=42, n_components=1, comp_weights=None, first_id=1, ref_walk0=True):
+    """Chains `n_instances` randomly chosen template instances (sink of one -> source of the next, `+ +`) into
+    `n_components` components (sizes proportional to comp_weights).  Path p of component c picks one of the
+    template's walks per instance (path 0 always walk 0 when ref_walk0).  Paths are named S%03d#{1,2}#chr<c>."""
+    rng = _rng(seed)
+    K = len(templates)
+    tpl = rng.integers(0, K, size=n_instances)
+    tV = np.array([t["V"] for t in templates], dtype=np.int64)
+    base = np.concatenate([[0], np.cumsum(tV[tpl])])            # first vertex of every instance
+    V = int(base[-1])
+    # components: contiguous runs of instances
+    w = np.asarray(comp_weights if comp_weights is not None else np.ones(n_components), dtype=np.float64)
+    cuts = np.round(np.cumsum(w) / w.sum() * n_instances).astype(np.int64)
+    cuts[-1] = n_instances
+    comp_of = np.searchsorted(cuts, np.arange(n_instances), side="right")
+    # vertices / labels
+    seq_pool = [np.array(t["seqs"], dtype=object) for t in templates]
+    seqs = np.empty(V, dtype=object)
+    links = []
+    src = np.array([int(t["walks"][0][0][0]) for t in templates]); snk = np.array([int(t["walks"][0][0][-1]) for t in templates])
+    for k in range(K):
+        inst = np.nonzero(tpl == k)[0]
+        if len(inst) == 0:
+            continue
+        b = base[inst]
+        idx = (b[:, None] + np.arange(tV[k])[None, :]).ravel()
+        seqs[idx] = np.tile(seq_pool[k], len(inst))
+        L = templates[k]["links"]
+        LL = np.repeat(L[None, :, :], len(inst), axis=0).copy()
+        LL[:, :, 0] += b[:, None]; LL[:, :, 2] += b[:, None]
+        links.append((inst.repeat(len(L)), LL.reshape(-1, 4)))
+    # joins between consecutive instances of the same component
+    i = np.arange(n_instances - 1)
+    same = comp_of[i] == comp_of[i + 1]
+    j = i[same]
+    J = np.stack([base[j] + snk[tpl[j]], np.ones(len(j), np.int64), base[j + 1] + src[tpl[j + 1]], np.zeros(len(j), np.int64)], 1)
+    key = np.concatenate([k_ for k_, _ in links] + [j + 0.5])
+    allL = np.concatenate([l_ for _, l_ in links] + [J])
+    allL = allL[np.argsort(key, kind="stable")]                  # L lines follow the chain
+    # paths
+    nW = np.array([len(t["walks"]) for t in templates])
+    wl = [[len(wk[0]) for wk in t["walks"]] for t in templates]
+    paths = []
+    for c in range(n_components):
+        inst = np.nonzero(comp_of == c)[0]
+        if len(inst) == 0:
+            continue
+        for p in range(n_paths):
+            choice = rng.integers(0, 1 << 30, size=len(inst)) % nW[tpl[inst]]
+            if p == 0 and ref_walk0:
+                choice[:] = 0
+            lens = np.array([wl[k][w_] for k, w_ in zip(tpl[inst].tolist(), choice.tolist())], dtype=np.int64) if len(inst) < 2000 else None
+            if lens is None:
+                lens = np.zeros(len(inst), dtype=np.int64)
+                for k in range(K):
+                    for w_ in range(nW[k]):
+                        m = (tpl[inst] == k) & (choice == w_)
+                        lens[m] = wl[k][w_]
+            off = np.concatenate([[0], np.cumsum(lens)])
+            steps = np.empty(int(off[-1]), dtype=np.uint32); strands = np.empty(int(off[-1]), dtype=np.uint8)
+            for k in range(K):
+                for w_ in range(nW[k]):
+                    m = np.nonzero((tpl[inst] == k) & (choice == w_))[0]
+                    if len(m) == 0:
+                        continue
+                    ws, wr = templates[k]["walks"][w_]
+                    pos = (off[m][:, None] + np.arange(len(ws))[None, :]).ravel()
+                    steps[pos] = (base[inst[m]][:, None] + ws[None, :].astype(np.int64)).ravel().astype(np.uint32)
+                    strands[pos] = np.tile(wr, len(m))
+            paths.append((f"S{p // 2 + 1:03d}#{p % 2 + 1}#chr{c + 1}", steps, strands))
+    ids = np.arange(first_id, first_id + V, dtype=np.uint32)
+    return make_graph(ids, seqs.tolist(), allL, paths)
+
+
+def cfg3_templates(seed=7, n_nested=24, tower_depth=64, p_inv=0.0):
+    """nested templates with depth mostly <= 3, some 4-8, plus one tower (inversion bubbles only
+    when p_inv > 0 -- their SUBR records need the SNE pass)."""
+    t = []
+    for k in range(n_nested):
+        depth = 2 + (k % 3) if k % 8 else 5 + (k % 4)
+        t.append(template_from(nested_bubbles(seed * 1000 + k, n_top=4 + k % 5, max_depth=depth, n_paths=8, p_inv=p_inv)))
+    if tower_depth:
+        t.append(tower(tower_depth, seed))
+    return t
+
+
+def truncate(g, n_vertices):
+    """Prefix of a chain-shaped graph: vertices [0, n), the links among them, every path cut at its first step
+    outside.  With n at an instance boundary of `tiled` / a backbone vertex of `snp_indel_chain`, every region
+    strictly inside the prefix is identical to the same region of the whole graph (same ids, same POS)."""
+    keep = (g["v1"] < n_vertices) & (g["v2"] < n_vertices)
+    L = np.stack([g["v1"][keep].astype(np.int64), g["s1"][keep], g["v2"][keep].astype(np.int64), g["s2"][keep]], 1)
+    paths = []
+    for name, st, sr in g["paths"]:
+        out = np.nonzero(st >= n_vertices)[0]
+        k = int(out[0]) if len(out) else len(st)
+        paths.append((name, st[:k], sr[:k]))
+    return make_graph(g["ids"][:n_vertices], g["seqs"][:n_vertices] if g["seqs"] is not None else None, L, paths)
