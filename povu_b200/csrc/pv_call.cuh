@@ -54,6 +54,9 @@ PV_KERNEL(C_emit, 64);
 PV_KERNEL(C_gt_ref, 16);
 PV_KERNEL(C_gt_alt, 16);
 PV_KERNEL(C_fill16, 2);
+PV_KERNEL(C_pack, 24);
+PV_KERNEL(C_keep, 12);
+PV_KERNEL(C_sizes, 24);
 
 PV_DEV u32 lb_u32(const u32 *a, u32 lo, u32 hi, u32 key) {   // first index in [lo, hi) with a[idx] >= key
 	while (lo < hi) { u32 m = lo + ((hi - lo) >> 1); if (a[m] < key) lo = m + 1; else hi = m; }
@@ -325,18 +328,23 @@ enum { VT_DEL = 0, VT_INS = 1, VT_SUB = 2, VT_SUBR = 3 };
 struct CallOpts { u64 cell_budget = 1ull << 30; };
 
 struct RovView {
-	const u32 *rovOff, *rovVerts, *rovComp; const u64 *rowPre, *cellPre;   // global prefix sums over regions
+	const u32 *rovOff, *rovVerts, *rovComp;   // per region (global index): sorted vertices, component
+	const u64 *rowPre, *cellPre;             // prefix sums of matrix rows / cells over the view's items
 	const u64 *hkey; const u32 *hval; u64 hmask;
-	u32 R; u32 uniformNh; u32 rShift;   // chunk = regions [rShift, rShift + R); region arguments below are chunk-local
-	PV_DEV u32 J(u32 r) const { return rovOff[rShift + r + 1] - rovOff[rShift + r]; }
-	PV_DEV u32 vert(u32 r, u32 j) const { return rovVerts[rovOff[rShift + r] + j]; }
-	PV_DEV u32 comp(u32 r) const { return rovComp[rShift + r]; }
-	PV_DEV u32 rowBase(u32 r) const { return (u32)(rowPre[rShift + r] - rowPre[rShift]); }   // first matrix row of region r (chunk-relative)
+	u32 R; u32 uniformNh; u32 rShift;
+	const u32 *map;   // nullptr: item r of the view is region rShift + r (a chunk of regions);
+	                  // else item r is an unrolled matrix of region map[r] (tangled regions) and rShift = 0
+	PV_DEV u32 region(u32 r) const { return map ? map[r] : rShift + r; }
+	PV_DEV u32 J(u32 r) const { u32 q = region(r); return rovOff[q + 1] - rovOff[q]; }
+	PV_DEV u32 vert(u32 r, u32 j) const { return rovVerts[rovOff[region(r)] + j]; }
+	PV_DEV u32 comp(u32 r) const { return rovComp[region(r)]; }
+	PV_DEV u32 rowBase(u32 r) const { return (u32)(rowPre[rShift + r] - rowPre[rShift]); }   // first matrix row of item r (view-relative)
 	PV_DEV u64 matBase(u32 r) const { return cellPre[rShift + r] - cellPre[rShift]; }
-	PV_DEV u32 find(u32 r, u32 v) const {   // column of vertex v in region r, or NONE
-		u32 a = rovOff[rShift + r], n = rovOff[rShift + r + 1] - a;
+	PV_DEV u32 find(u32 r, u32 v) const {   // column of vertex v in item r, or NONE
+		u32 q = region(r);
+		u32 a = rovOff[q], n = rovOff[q + 1] - a;
 		if (n <= 16) { for (u32 j = 0; j < n; j++) if (rovVerts[a + j] == v) return j; return NONE; }
-		u64 key = ((u64)(r + rShift) << 32) | v; u64 i = splitmix64(key) & hmask;
+		u64 key = ((u64)q << 32) | v; u64 i = splitmix64(key) & hmask;
 		while (true) { u64 k = hkey[i]; if (k == key) return hval[i]; if (k == ~0ull) return NONE; i = (i + 1) & hmask; }
 	}
 	PV_DEV u32 row2rov(u32 row) const {
@@ -441,9 +449,341 @@ PV_DEV void sift_down(const u32 *steps, const CandView &cd, u32 *a, u32 root, u3
 	}
 }
 
-PV_KERNEL(C_pack, 24);
-PV_KERNEL(C_keep, 12);
-PV_KERNEL(C_sizes, 24);
+// comp_exps over every matrix of a view (overlay.cpp:348-588) for all ref paths, then records + genotypes
+// (vcf.cpp:20-121,241-273); results are appended to `out`.
+inline void overlay_pass(Ctx &c, const DevGraph &G, const GraphView &g, const CallIn &in, const RovView &rv, const ChunkView &cv, u32 Rc, u32 nRows,
+			 Records &out, Trace &tr) {
+	const u32 nRefs = in.nRefs; const u32 uniformNh = rv.uniformNh;
+	for (u32 k = 0; k < nRefs; k++) {
+		const u32 refH = in.refs[k];
+		const u32 refLocal = G.hapLocal[refH];
+		const u32 refStep0 = G.h_stepOff[refH];
+		// ---- C5a: contexts per (region, path) pair
+		Buf<u32> pairCnt(c, (size_t)nRows + 1), candOff(c, (size_t)nRows + 1);
+		u32 *pairCnt_ = pairCnt.p; const u32 *candOff_ = candOff.p;
+		parallel_for<C_pair_count>(c, (size_t)nRows + 1, PV_LAMBDA(size_t row) {
+			pairCnt_[row] = row < nRows ? scan_pair(cv, refLocal, k, (u32)row, false, CandView{}, 0) : 0u;
+		});
+		exclusive_scan(c, pairCnt.p, candOff.p, (size_t)nRows + 1, OpAddU32(), 0u);
+		const u32 nCand = candOff.read(nRows);
+		const size_t nC1 = nCand ? nCand : 1;
+		Buf<u32> cL(c, nC1), cR(c, nC1), cStart(c, nC1), cLen(c, nC1), cRS(c, nC1), cRL(c, nC1), cHap(c, nC1), cCls(c, nC1), cHead(c, nC1), gCount(c, nC1), hsort(c, nC1);
+		const CandView cd{cL.p, cR.p, cStart.p, cLen.p, cRS.p, cRL.p, cHap.p, cCls.p, cHead.p, gCount.p, hsort.p};
+		// ---- C5b: slices per context, classification
+		if (nCand) parallel_for<C_pair_fill>(c, nRows, PV_LAMBDA(size_t row) {
+			if (candOff_[row + 1] == candOff_[row]) return;
+			scan_pair(cv, refLocal, k, (u32)row, true, cd, candOff_[row]);
+		});
+		tr.mark("C5 pairs");
+		// ---- C6a: group alt slices by (context, class, walk) per region, order groups like the reference's std::maps
+		Buf<u32> recCnt(c, (size_t)Rc + 1), grpCnt(c, (size_t)Rc + 1), recOff(c, (size_t)Rc + 1), grpOff(c, (size_t)Rc + 1);
+		u32 *recCnt_ = recCnt.p, *grpCnt_ = grpCnt.p;
+		parallel_for<C_group>(c, (size_t)Rc + 1, PV_LAMBDA(size_t rr_) {
+			if (rr_ >= Rc) { recCnt_[rr_] = 0; grpCnt_[rr_] = 0; return; }
+			u32 r = (u32)rr_;
+			u32 b = candOff_[rv.rowBase(r)], e = candOff_[rv.rowBase(r + 1)];
+			u32 *a = cd.hsort + b; u32 nh = 0;
+			for (u32 x = b; x < e; x++) {
+				if (cd.cCls[x] == 3) continue;
+				u32 found = NONE;
+				for (u32 t = 0; t < nh; t++) {
+					u32 y = a[t];
+					if (same_record(cd, x, y) && cd.cLen[y] == cd.cLen[x] && walk_equal(g.steps, cd.cStart[y], cd.cStart[x], cd.cLen[x])) { found = y; break; }
+				}
+				if (found == NONE) { a[nh++] = x; cd.cHead[x] = x; cd.gCount[x] = 1; }
+				else { cd.cHead[x] = found; cd.gCount[found]++; }
+			}
+			for (u32 st = nh / 2; st-- > 0;) sift_down(g.steps, cd, a, st, nh);
+			for (u32 end = nh; end-- > 1;) { u32 t = a[0]; a[0] = a[end]; a[end] = t; sift_down(g.steps, cd, a, 0, end); }
+			u32 nrec = 0;
+			for (u32 t = 0; t < nh; t++) if (t == 0 || !same_record(cd, a[t - 1], a[t])) nrec++;
+			recCnt_[r] = nrec; grpCnt_[r] = nh;
+			if (k == 0) cv.hasData[r] = nh ? 1u : 0u;
+			else if (nh == 0 && cv.hasData[r]) atomic_add(cv.errs + 0, 1u);   // std::map::at throws in the reference
+		});
+		exclusive_scan(c, recCnt.p, recOff.p, (size_t)Rc + 1, OpAddU32(), 0u);
+		exclusive_scan(c, grpCnt.p, grpOff.p, (size_t)Rc + 1, OpAddU32(), 0u);
+		const u32 nRec = recOff.read(Rc), nGrp = grpOff.read(Rc);
+		if (nRec == 0) continue;
+		// ---- C6b: records + groups (offsets already global: the host only appends)
+		const u32 grpBase = (u32)out.grp_hap.size(); const u64 gtBase = out.gt.size(); const size_t recBase = out.rec_rov.size();
+		Buf<u32> oLoc(c, nRec); u32 *oLoc_ = oLoc.p;
+		Buf<u32> oRov(c, nRec), oRef(c, nRec), oL(c, nRec), oR(c, nRec), oVt(c, nRec), oPos(c, nRec), oRS(c, nRec), oRL(c, nRec), oGrp(c, (size_t)nRec + 1);
+		Buf<u32> gHap(c, nGrp), gStart(c, nGrp), gLen(c, nGrp), gCnt(c, nGrp), headRec(c, nCand), headOrd(c, nCand);
+		Buf<u64> gtOff(c, (size_t)nRec + 1), recNh(c, (size_t)nRec + 1);
+		u32 *oRov_ = oRov.p, *oRef_ = oRef.p, *oL_ = oL.p, *oR_ = oR.p, *oVt_ = oVt.p, *oPos_ = oPos.p, *oRS_ = oRS.p, *oRL_ = oRL.p, *oGrp_ = oGrp.p;
+		u32 *gHap_ = gHap.p, *gStart_ = gStart.p, *gLen_ = gLen.p, *gCnt_ = gCnt.p, *headRec_ = headRec.p, *headOrd_ = headOrd.p;
+		u64 *gtOff_ = gtOff.p, *recNh_ = recNh.p; const u32 *recOff_ = recOff.p, *grpOff_ = grpOff.p;
+		parallel_for<C_emit>(c, Rc, PV_LAMBDA(size_t rr_) {
+			u32 r = (u32)rr_;
+			u32 nh = grpOff_[r + 1] - grpOff_[r];
+			if (!nh) return;
+			const u32 *a = cd.hsort + candOff_[rv.rowBase(r)];
+			u32 rec = recOff_[r], gi = grpOff_[r]; u32 ord = 0;
+			u32 nhaps = rv.rowBase(r + 1) - rv.rowBase(r);
+			for (u32 t = 0; t < nh; t++) {
+				u32 y = a[t];
+				if (t == 0 || !same_record(cd, a[t - 1], y)) {
+					if (t) rec++;
+					ord = 0;
+					u32 cls = cd.cCls[y];
+					oRov_[rec] = rv.region(r); oLoc_[rec] = r; oRef_[rec] = refH; oL_[rec] = cd.cL[y]; oR_[rec] = cd.cR[y];
+					oVt_[rec] = cls == 0 ? (u32)VT_INS : (cls == 1 ? (u32)VT_SUB : (u32)VT_DEL);
+					oRS_[rec] = cd.cRS[y]; oRL_[rec] = cd.cRL[y];
+					u32 l = g.loci[cd.cRS[y] + 1];                       // comp_pos (allele.hpp:161-179)
+					oPos_[rec] = cls == 1 ? l : l - 1;
+					oGrp_[rec] = grpBase + gi; recNh_[rec] = nhaps;
+				}
+				ord++;
+				headRec_[y] = rec; headOrd_[y] = ord;
+				u32 hh = g.cpList[g.cpOff[rv.comp(r)] + cd.cHap[y]];
+				gHap_[gi] = hh; gStart_[gi] = cd.cStart[y] - g.stepOff[hh]; gLen_[gi] = cd.cLen[y]; gCnt_[gi] = cd.gCount[y];
+				gi++;
+			}
+		});
+		c.memset0(recNh.p + nRec, 8);
+		exclusive_scan(c, recNh.p, gtOff.p, (size_t)nRec + 1, OpAddU64(), (u64)0);
+		u64 nGt; c.d2h(&nGt, gtOff.p + nRec, 8);
+		Buf<u16> gt(c, nGt ? nGt : 1);
+		c.memset_ff(gt.p, nGt * 2);
+		u16 *gt_ = gt.p;
+		tr.mark("C6 group+emit");
+		// ---- C7: genotypes.  Paths equal to the ref over the context columns with an identical slice -> 0 (overlay.cpp:534-580)
+		parallel_for<C_gt_ref>(c, nGt, PV_LAMBDA(size_t x) {
+			u32 rec = uniformNh ? (u32)(x / uniformNh) : (u32)(ub_u64(gtOff_, 0, (u64)nRec + 1, (u64)x) - 1);
+			u32 i = (u32)(x - gtOff_[rec]);
+			u32 r = oLoc_[rec]; u32 J = rv.J(r);
+			u32 lv = oL_[rec] >> 1, rvx = oR_[rec] >> 1;
+			u32 ju = rv.find(r, lv), jv = rv.find(r, rvx);
+			if (ju > jv) { u32 t = ju; ju = jv; jv = t; }
+			const u16 *rr = cv.mat + rv.matBase(r) + (u64)refLocal * J, *ar = cv.mat + rv.matBase(r) + (u64)i * J;
+			for (u32 j = ju; j <= jv; j++) if (rr[j] != ar[j]) return;
+			u32 row = rv.rowBase(r) + i;
+			if (cv.lapStart[row] == NONE) return;
+			u32 as, an;
+			if (!slice_bounds(g, lv, rvx, cv.lap(row), as, an)) return;
+			if (an != oRL_[rec] || !walk_equal(g.steps, oRS_[rec], as, an)) return;
+			gt_[x] = 0;
+		});
+		parallel_for<C_gt_alt>(c, nCand, PV_LAMBDA(size_t x) {
+			if (cd.cCls[x] == 3) return;
+			u32 hd = cd.cHead[x]; u32 rec = headRec_[hd];
+			gt_[gtOff_[rec] + cd.cHap[x]] = (u16)headOrd_[hd];
+		});
+		// the host sees ref-slice starts relative to the ref path, and global gt offsets
+		parallel_for<C_keep>(c, (size_t)nRec + 1, PV_LAMBDA(size_t i) { if (i < nRec) oRS_[i] -= refStep0; gtOff_[i] += gtBase; });
+		tr.mark("C7 genotypes");
+		// ---- results of this (chunk, ref): asynchronous appends into the pinned host vectors
+		auto app = [&](hvec<u32> &dst, const Buf<u32> &src, u32 n) { size_t o = dst.size(); dst.resize(o + n); c.d2h_async(dst.data() + o, src.p, (size_t)n * 4); };
+		app(out.rec_rov, oRov, nRec); app(out.rec_ref, oRef, nRec); app(out.rec_cxtL, oL, nRec); app(out.rec_cxtR, oR, nRec); app(out.rec_vt, oVt, nRec); app(out.rec_pos, oPos, nRec);
+		app(out.rec_refStart, oRS, nRec); app(out.rec_refLen, oRL, nRec);
+		app(out.grp_hap, gHap, nGrp); app(out.grp_start, gStart, nGrp); app(out.grp_len, gLen, nGrp); app(out.grp_count, gCnt, nGrp);
+		out.rec_grpOff.resize(recBase + nRec + 1); c.d2h_async(out.rec_grpOff.data() + recBase, oGrp.p, (size_t)nRec * 4);
+		out.rec_gtOff.resize(recBase + nRec + 1); c.d2h_async(out.rec_gtOff.data() + recBase, gtOff.p, ((size_t)nRec + 1) * 8);
+		out.gt.resize(gtBase + nGt); c.d2h_async(out.gt.data() + gtBase, gt.p, nGt * 2);
+		c.sync();   // the device buffers of this round die at the end of the scope
+		out.rec_grpOff[recBase + nRec] = grpBase + nGrp;
+		tr.mark("records d2h");
+	}
+}
+
+PV_KERNEL(T_rows, 12);
+PV_KERNEL(T_count, 24);
+PV_KERNEL(T_fill, 24);
+PV_KERNEL(T_laps, 24);
+PV_KERNEL(T_sizes, 24);
+PV_KERNEL(T_align, 64);
+PV_KERNEL(T_mismatch, 16);
+PV_KERNEL(T_inst, 24);
+PV_KERNEL(T_matrix, 32);
+
+// Tangled regions (a boundary column visited more than once): ita::untangle::untangle
+// (/root/reference/src/ita/genomics/untangle.cpp:29-247) + ita::align (/root/reference/src/ita/align/align.cpp:71-253).
+// Per tangled region: every path's race (all laps = runs of consecutive steps on region vertices), affine-gap global
+// alignment of the first ref's lap sequence against every other path's (whole laps are the alphabet; u32 arithmetic
+// with INVALID as +inf that wraps, quirk Q12), one unrolled depth matrix per alignment column that holds an 'X', then
+// the ordinary overlay over those matrices with TANGLED = T (overlay.cpp:616-626).  Only the first ref's matrices are
+// used (untangle.cpp:245-246, Q11).
+inline void tangled_pass(Ctx &c, const DevGraph &G, const GraphView &g, const CallIn &in, const RovView &rv, const ChunkView &cv, u32 Rc,
+			 const u32 *tangledFlags, u32 *errs, Records &out, Trace &tr) {
+	Buf<u32> tList;
+	const u32 nT = compact_flags(c, tangledFlags, Rc, tList);
+	if (!nT) return;
+	const u32 ref0Local = G.hapLocal[in.refs[0]];
+	const u32 *tList_ = tList.p;
+	// rows and columns of the tangled regions, flattened
+	Buf<u32> tRows(c, (size_t)nT + 1), tRowPre(c, (size_t)nT + 1), tCols(c, (size_t)nT + 1), tColPre(c, (size_t)nT + 1);
+	u32 *tRows_ = tRows.p, *tCols_ = tCols.p;
+	parallel_for<T_rows>(c, (size_t)nT + 1, PV_LAMBDA(size_t t) {
+		if (t >= nT) { tRows_[t] = 0; tCols_[t] = 0; return; }
+		u32 r = tList_[t];
+		tRows_[t] = rv.rowBase(r + 1) - rv.rowBase(r); tCols_[t] = rv.J(r);
+	});
+	exclusive_scan(c, tRows.p, tRowPre.p, (size_t)nT + 1, OpAddU32(), 0u);
+	exclusive_scan(c, tCols.p, tColPre.p, (size_t)nT + 1, OpAddU32(), 0u);
+	const u32 nTR = tRowPre.read(nT), nTC = tColPre.read(nT);
+	const u32 *tRowPre_ = tRowPre.p, *tColPre_ = tColPre.p;
+	// ---- races: steps of every (region, path) on region vertices, sorted, cut into laps
+	Buf<u32> sCnt(c, (size_t)nTR + 1), sOff(c, (size_t)nTR + 1), cursor(c, nTR ? nTR : 1);
+	sCnt.zero(); cursor.zero();
+	u32 *sCnt_ = sCnt.p, *cursor_ = cursor.p;
+	parallel_for<T_count>(c, nTC, PV_LAMBDA(size_t x) {
+		u32 t = ub_u32(tColPre_, 0, nT + 1, (u32)x) - 1; u32 r = tList_[t]; u32 j = (u32)x - tColPre_[t];
+		u32 v = rv.vert(r, j); u32 comp = rv.comp(r);
+		for (u32 e = g.vsOff[v], ee = g.vsOff[v + 1]; e < ee; e++) {
+			u32 h = g.vsHap[e];
+			if (g.pathComp[h] == comp) atomic_add(sCnt_ + tRowPre_[t] + g.hapLocal[h], 1u);
+		}
+	});
+	exclusive_scan(c, sCnt.p, sOff.p, (size_t)nTR + 1, OpAddU32(), 0u);
+	const u32 TS = sOff.read(nTR);
+	Buf<u32> sList(c, TS ? TS : 1), lapS(c, TS ? TS : 1), lapL(c, TS ? TS : 1), lapCnt(c, nTR ? nTR : 1);
+	u32 *sList_ = sList.p, *lapS_ = lapS.p, *lapL_ = lapL.p, *lapCnt_ = lapCnt.p; const u32 *sOff_ = sOff.p;
+	parallel_for<T_fill>(c, nTC, PV_LAMBDA(size_t x) {
+		u32 t = ub_u32(tColPre_, 0, nT + 1, (u32)x) - 1; u32 r = tList_[t]; u32 j = (u32)x - tColPre_[t];
+		u32 v = rv.vert(r, j); u32 comp = rv.comp(r);
+		for (u32 e = g.vsOff[v], ee = g.vsOff[v + 1]; e < ee; e++) {
+			u32 h = g.vsHap[e];
+			if (g.pathComp[h] != comp) continue;
+			u32 row = tRowPre_[t] + g.hapLocal[h];
+			sList_[sOff_[row] + atomic_add(cursor_ + row, 1u)] = g.vsStep[e];
+		}
+	});
+	parallel_for<T_laps>(c, nTR, PV_LAMBDA(size_t row) {
+		u32 *a = sList_ + sOff_[row]; u32 n = sOff_[row + 1] - sOff_[row];
+		// heap sort ascending (the lists are filled in arbitrary order)
+		for (u32 st = n / 2; st-- > 0;) { u32 root = st; while (2 * root + 1 < n) { u32 ch = 2 * root + 1; if (ch + 1 < n && a[ch] < a[ch + 1]) ch++; if (a[root] >= a[ch]) break; u32 tt = a[root]; a[root] = a[ch]; a[ch] = tt; root = ch; } }
+		for (u32 end = n; end-- > 1;) { u32 tt = a[0]; a[0] = a[end]; a[end] = tt; u32 root = 0; while (2 * root + 1 < end) { u32 ch = 2 * root + 1; if (ch + 1 < end && a[ch] < a[ch + 1]) ch++; if (a[root] >= a[ch]) break; u32 t2 = a[root]; a[root] = a[ch]; a[ch] = t2; root = ch; } }
+		u32 nl = 0, o = sOff_[row];
+		for (u32 k = 0; k < n;) { u32 e = k + 1; while (e < n && a[e] == a[e - 1] + 1) e++; lapS_[o + nl] = a[k]; lapL_[o + nl] = e - k; nl++; k = e; }
+		lapCnt_[row] = nl;
+	});
+	// ---- alignments of the first ref's laps against every other path's
+	Buf<u64> dpSz(c, (size_t)nTR + 1), dpOff(c, (size_t)nTR + 1);
+	Buf<u32> etCap(c, (size_t)nTR + 1), etOff(c, (size_t)nTR + 1), etLen(c, nTR ? nTR : 1);
+	u64 *dpSz_ = dpSz.p; u32 *etCap_ = etCap.p, *etLen_ = etLen.p;
+	parallel_for<T_sizes>(c, (size_t)nTR + 1, PV_LAMBDA(size_t row) {
+		if (row >= nTR) { dpSz_[row] = 0; etCap_[row] = 0; return; }
+		u32 t = ub_u32(tRowPre_, 0, nT + 1, (u32)row) - 1; u32 i = (u32)row - tRowPre_[t];
+		u32 Lr = lapCnt_[tRowPre_[t] + ref0Local], Lh = lapCnt_[row];
+		if (i == ref0Local) { dpSz_[row] = 0; etCap_[row] = 0; return; }
+		dpSz_[row] = (Lr == 1 && Lh == 1) ? 0ull : (u64)(Lr + 1) * (Lh + 1);
+		etCap_[row] = Lr + Lh + 1;
+	});
+	exclusive_scan(c, dpSz.p, dpOff.p, (size_t)nTR + 1, OpAddU64(), (u64)0);
+	exclusive_scan(c, etCap.p, etOff.p, (size_t)nTR + 1, OpAddU32(), 0u);
+	u64 totDP; c.d2h(&totDP, dpOff.p + nTR, 8);
+	const u32 totEt = etOff.read(nTR);
+	if (totDP > (1ull << 31)) throw std::runtime_error("call: tangled regions need more than 24 GB of alignment matrices");
+	Buf<u32> dpM(c, totDP ? totDP : 1), dpI(c, totDP ? totDP : 1), dpD(c, totDP ? totDP : 1);
+	Buf<u8> et(c, totEt ? totEt : 1);
+	u32 *dpM_ = dpM.p, *dpI_ = dpI.p, *dpD_ = dpD.p; u8 *et_ = et.p; const u64 *dpOff_ = dpOff.p; const u32 *etOff_ = etOff.p;
+	parallel_for<T_align>(c, nTR, PV_LAMBDA(size_t row) {
+		u32 t = ub_u32(tRowPre_, 0, nT + 1, (u32)row) - 1; u32 i = (u32)row - tRowPre_[t];
+		if (i == ref0Local) { etLen_[row] = 0; return; }
+		u32 rrow = tRowPre_[t] + ref0Local;
+		u32 Lr = lapCnt_[rrow], Lh = lapCnt_[row];
+		const u32 *rS = lapS_ + sOff_[rrow], *rL = lapL_ + sOff_[rrow], *hS = lapS_ + sOff_[row], *hL = lapL_ + sOff_[row];
+		u8 *e = et_ + etOff_[row];
+		auto eq = [&](u32 a, u32 b) -> bool { return rL[a] == hL[b] && walk_equal(g.steps, rS[a], hS[b], rL[a]); };   // eq_at (align.cpp:37-51)
+		if (Lr == 1 && Lh == 1) { e[0] = eq(0, 0) ? 'M' : 'X'; etLen_[row] = 1; return; }
+		const u32 INV = NONE, ca = 0, cx = 1, co = 2, ce = 1;   // match, mismatch, gap open, gap extend (align.cpp:231)
+		const u32 rows = Lr + 1, cols = Lh + 1;
+		u32 *M = dpM_ + dpOff_[row], *I = dpI_ + dpOff_[row], *D = dpD_ + dpOff_[row];
+#define AT(X, a, b) X[(size_t)(a) * cols + (b)]
+		for (u32 j = 1; j < cols; j++) { AT(D, 0, j) = INV; AT(I, 0, j) = j * ce + co; }
+		for (u32 a = 1; a < rows; a++) { AT(I, a, 0) = INV; AT(D, a, 0) = a * ce + co; }
+		AT(M, 0, 0) = 0; AT(D, 0, 0) = INV; AT(I, 0, 0) = INV;
+		for (u32 a = 1; a < rows; a++) AT(M, a, 0) = INV;
+		for (u32 j = 1; j < cols; j++) AT(M, 0, j) = INV;
+		auto mn = [](u32 x, u32 y) -> u32 { return x < y ? x : y; };
+		for (u32 a = 1; a < rows; a++)
+			for (u32 j = 1; j < cols; j++) {
+				AT(I, a, j) = mn(AT(M, a - 1, j) + co + ce, AT(I, a - 1, j) + ce);      // u32 wrap-around is the reference's behaviour
+				AT(D, a, j) = mn(AT(M, a, j - 1) + co + ce, AT(D, a, j - 1) + ce);
+				bool m = eq(a - 1, j - 1);
+				AT(M, a, j) = mn(AT(M, a - 1, j - 1) + (m ? ca : cx), mn(AT(I, a, j), AT(D, a, j)));
+			}
+		u32 a = Lr, j = Lh, n = 0;
+		while (a > 0 && j > 0) {
+			bool m = eq(a - 1, j - 1);
+			u32 up = AT(M, a - 1, j), lf = AT(M, a, j - 1), dg = AT(M, a - 1, j - 1) + (m ? ca : cx), cur = AT(M, a, j);
+			if (cur == mn(up, mn(lf, dg))) { e[n++] = m ? 'M' : 'X'; a--; j--; }
+			else if (up == mn(up, mn(lf, cur))) { e[n++] = 'I'; a--; }
+			else if (lf == mn(up, mn(lf, cur))) { e[n++] = 'D'; j--; }
+			else { atomic_add(errs + 0, 1u); break; }   // the reference exit(1)s here
+		}
+#undef AT
+		while (a > 0) { e[n++] = 'I'; a--; }
+		while (j > 0) { e[n++] = 'D'; j--; }
+		for (u32 x = 0; x < n / 2; x++) { u8 tt = e[x]; e[x] = e[n - 1 - x]; e[n - 1 - x] = tt; }
+		etLen_[row] = n;
+	});
+	// ---- one unrolled matrix per (region, ref lap j) whose alignment column j holds an 'X' (untangle.cpp:178-209)
+	Buf<u32> LrOf(c, (size_t)nT + 1), jPre(c, (size_t)nT + 1);
+	u32 *LrOf_ = LrOf.p;
+	parallel_for<T_rows>(c, (size_t)nT + 1, PV_LAMBDA(size_t t) { LrOf_[t] = t < nT ? lapCnt_[tRowPre_[t] + ref0Local] : 0u; });
+	exclusive_scan(c, LrOf.p, jPre.p, (size_t)nT + 1, OpAddU32(), 0u);
+	const u32 nJ = jPre.read(nT);
+	if (!nJ) return;
+	Buf<u32> mm(c, nJ), instIdx;
+	u32 *mm_ = mm.p; const u32 *jPre_ = jPre.p;
+	parallel_for<T_mismatch>(c, nJ, PV_LAMBDA(size_t x) {
+		u32 t = ub_u32(jPre_, 0, nT + 1, (u32)x) - 1; u32 j = (u32)x - jPre_[t];
+		u32 hit = 0;
+		for (u32 row = tRowPre_[t]; row < tRowPre_[t + 1] && !hit; row++)
+			if (etLen_[row] > j && et_[etOff_[row] + j] == 'X') hit = 1;
+		mm_[x] = hit;
+	});
+	const u32 nI = compact_flags(c, mm.p, nJ, instIdx);
+	if (!nI) return;
+	Buf<u32> instT(c, nI), instJ(c, nI), instRegion(c, nI), instTangled(c, nI), hasData(c, nI);
+	Buf<u64> iRows(c, (size_t)nI + 1), iCells(c, (size_t)nI + 1), iRowPre(c, (size_t)nI + 1), iCellPre(c, (size_t)nI + 1);
+	instTangled.zero(); hasData.zero();
+	u32 *instT_ = instT.p, *instJ_ = instJ.p, *instRegion_ = instRegion.p; u64 *iRows_ = iRows.p, *iCells_ = iCells.p; const u32 *instIdx_ = instIdx.p;
+	parallel_for<T_inst>(c, (size_t)nI + 1, PV_LAMBDA(size_t n) {
+		if (n >= nI) { iRows_[n] = 0; iCells_[n] = 0; return; }
+		u32 x = instIdx_[n]; u32 t = ub_u32(jPre_, 0, nT + 1, x) - 1;
+		instT_[n] = t; instJ_[n] = x - jPre_[t]; instRegion_[n] = rv.region(tList_[t]);
+		u32 nh = tRowPre_[t + 1] - tRowPre_[t];
+		iRows_[n] = nh; iCells_[n] = (u64)nh * rv.J(tList_[t]);
+	});
+	exclusive_scan(c, iRows.p, iRowPre.p, (size_t)nI + 1, OpAddU64(), (u64)0);
+	exclusive_scan(c, iCells.p, iCellPre.p, (size_t)nI + 1, OpAddU64(), (u64)0);
+	u64 totRows, totCells; c.d2h(&totRows, iRowPre.p + nI, 8); c.d2h(&totCells, iCellPre.p + nI, 8);
+	if (totRows > 0x7FFFFFF0ull) throw std::runtime_error("call: too many unrolled matrix rows in one chunk");
+	Buf<u16> imat(c, totCells ? totCells : 1);
+	Buf<u32> ilapStart(c, totRows ? totRows : 1), ilapLen(c, totRows ? totRows : 1);
+	c.memset0(imat.p, totCells * 2); ilapStart.fill_ff(); ilapLen.zero();
+	const RovView irv{rv.rovOff, rv.rovVerts, rv.rovComp, iRowPre.p, iCellPre.p, rv.hkey, rv.hval, rv.hmask, nI, rv.uniformNh, 0, instRegion.p};
+	const ChunkView icv{g, irv, imat.p, ilapStart.p, ilapLen.p, instTangled.p, hasData.p, errs};
+	parallel_for<T_matrix>(c, (size_t)totRows, PV_LAMBDA(size_t row) {
+		u32 n = irv.row2rov((u32)row); u32 i = (u32)row - irv.rowBase(n);
+		u32 t = instT_[n], j = instJ_[n];
+		u32 x = tRowPre_[t] + i;
+		u32 lapIdx;
+		if (i == ref0Local) lapIdx = j;
+		else {
+			if (etLen_[x] <= j) return;
+			u8 ch = et_[etOff_[x] + j];
+			if (ch == 'D' || ch == 'I') return;
+			u32 ln = 0;
+			for (u32 q = 0; q < j; q++) if (et_[etOff_[x] + q] != 'I') ln++;   // comp_loop_no (untangle.cpp:165-176)
+			lapIdx = ln;
+		}
+		if (lapIdx >= lapCnt_[x]) { atomic_add(errs + 0, 1u); return; }   // out-of-range race index in the reference
+		u32 s0 = lapS_[sOff_[x] + lapIdx], len = lapL_[sOff_[x] + lapIdx];
+		icv.lapStart[row] = s0; icv.lapLen[row] = len;
+		u32 J = irv.J(n); u16 *cells = icv.mat + irv.matBase(n) + (u64)i * J;
+		for (u32 q = 0; q < len; q++) {   // fill_row (untangle.cpp:126-143): later steps overwrite earlier ones
+			u32 st = g.steps[s0 + q]; u32 col = irv.find(n, st >> 1);
+			if (col != NONE) cells[col] = (st & 1u) ? 2 : 1;
+		}
+	});
+	tr.mark("T untangle");
+	overlay_pass(c, G, g, in, irv, icv, nI, (u32)totRows, out, tr);
+}
+
 
 inline void call_device(Ctx &c, const DevGraph &G, const CallIn &in, const CallOpts &opt, Records &out) {
 	out.reset();
@@ -499,14 +839,20 @@ inline void call_device(Ctx &c, const DevGraph &G, const CallIn &in, const CallO
 		for (u32 k = 0; k < n; k++) vtmp_[r * 12 + k] = ov[k];
 	});
 	u32 hc[8]; c.d2h(hc, cnt.p, 32);
-	// regions that did not fit tier 0: host-driven retries; their orders land in bigVerts[bigOff[r] ..)
-	Buf<u32> bigOff(c, (size_t)R0 + 1), bigVerts;
-	bool haveBig = hc[0] != 0;
+	// regions that did not fit tier 0 retry in 16x larger slices of a global arena.  The orders stay where the
+	// kernel wrote them (the arenas live until the gather below); only the per-slice result counts go to the host.
+	std::vector<Buf<u32>> arenas;
+	std::vector<u64> sliceTab;   // per slice: arena base pointer, u32 words per region, offset of the order inside a region's words
+	Buf<u32> bigSlice(c, R0), bigSlot(c, R0);
+	const bool haveBig = hc[0] != 0;
 	if (haveBig) {
-		std::vector<u32> hJ = J0.to_host();
-		std::vector<u32> todo, hBigOff((size_t)R0 + 1, 0), hBigVerts;
-		std::vector<std::vector<u32>> res(R0);
-		for (u32 r = 0; r < R0; r++) if (hJ[r] == NONE) todo.push_back(r);
+		bigSlice.fill_ff();
+		u32 *bigSlice_ = bigSlice.p, *bigSlot_ = bigSlot.p;
+		Buf<u32> ovf(c, R0), todoBuf;
+		u32 *ovf_ = ovf.p;
+		parallel_for<C_keep>(c, R0, PV_LAMBDA(size_t r) { ovf_[r] = J0_[r] == NONE ? 1u : 0u; });
+		u32 nTodo = compact_flags(c, ovf.p, R0, todoBuf);
+		std::vector<u32> todo = todoBuf.to_host(); todo.resize(nTodo);
 		u64 capV64 = 256;
 		while (!todo.empty()) {
 			const bool last = capV64 >= (u64)G.V;
@@ -514,39 +860,38 @@ inline void call_device(Ctx &c, const DevGraph &G, const CallIn &in, const CallO
 			const u32 capE = (u32)std::min<u64>(capV64 * 4, 2 * G.E + 1);
 			u32 hcap = 1; while (hcap < 2 * capV) hcap <<= 1;
 			const u64 per = (u64)capV * 5 + 1 + capE + 2ull * hcap;
+			const u64 ovOff = 4 * (u64)capV + 1 + capE;
 			const u32 slice = (u32)std::max<u64>(1, std::min<u64>(todo.size(), (1ull << 28) / per));
 			std::vector<u32> next;
 			for (size_t b0 = 0; b0 < todo.size(); b0 += slice) {
 				const u32 nb = (u32)std::min<size_t>(slice, todo.size() - b0);
-				Buf<u32> list(c, nb), arena(c, (size_t)nb * per), rs(c, nb);
+				Buf<u32> list(c, nb), rs(c, nb);
+				arenas.emplace_back(c, (size_t)nb * per);
+				const u32 sliceIdx = (u32)(sliceTab.size() / 3);
+				sliceTab.push_back((u64)(uintptr_t)arenas.back().p); sliceTab.push_back(per); sliceTab.push_back(ovOff);
 				c.h2d(list.p, todo.data() + b0, (size_t)nb * 4);
-				u32 *arena_ = arena.p, *res_ = rs.p; const u32 *list_ = list.p;
+				u32 *arena_ = arenas.back().p, *res_ = rs.p; const u32 *list_ = list.p;
 				parallel_for<C_bfs>(c, nb, PV_LAMBDA(size_t i) {
 					u32 *base = arena_ + i * per;
 					const size_t cv = capV, ce = capE;
 					BfsScratch s{capV, capE, base, base + cv, base + 2 * cv + 1, base + 2 * cv + 1 + ce, base + 3 * cv + 1 + ce,
 						     base + 5 * cv + 1 + ce, base + 5 * cv + 1 + ce + hcap, hcap};
-					u32 f = rov0_[list_[i]];
-					res_[i] = bfs_kahn_sort(g, fa_[f] >> 1, !(fa_[f] & 1u), fz_[f] >> 1, !(fz_[f] & 1u), s, base + 4 * cv + 1 + ce);
+					u32 r = list_[i]; u32 f = rov0_[r];
+					u32 n = bfs_kahn_sort(g, fa_[f] >> 1, !(fa_[f] & 1u), fz_[f] >> 1, !(fz_[f] & 1u), s, base + ovOff);
+					res_[i] = n;
+					if (n != NONE) { J0_[r] = n; bigSlice_[r] = sliceIdx; bigSlot_[r] = (u32)i; }
 				});
 				std::vector<u32> hres = rs.to_host();
-				for (u32 i = 0; i < nb; i++) {
-					u32 r = todo[b0 + i];
-					if (hres[i] == NONE) { next.push_back(r); continue; }
-					res[r].resize(hres[i]);
-					if (hres[i]) c.d2h(res[r].data(), arena.p + (size_t)i * per + 4 * (size_t)capV + 1 + capE, (size_t)hres[i] * 4);
-					hJ[r] = hres[i]; out.n_big_bfs++;
-				}
+				for (u32 i = 0; i < nb; i++) { if (hres[i] == NONE) next.push_back(todo[b0 + i]); else out.n_big_bfs++; }
 			}
 			if (!next.empty() && last) throw std::runtime_error("call: region BFS overflow at full-graph capacity");
 			todo.swap(next);
 			capV64 *= 16;
 		}
-		for (u32 r = 0; r < R0; r++) { hBigOff[r + 1] = hBigOff[r] + (u32)res[r].size(); hBigVerts.insert(hBigVerts.end(), res[r].begin(), res[r].end()); }
-		bigVerts = Buf<u32>(c, hBigVerts.size() ? hBigVerts.size() : 1);
-		c.h2d(bigOff.p, hBigOff.data(), ((size_t)R0 + 1) * 4); c.h2d(bigVerts.p, hBigVerts.data(), hBigVerts.size() * 4); c.h2d(J0.p, hJ.data(), (size_t)R0 * 4);
-		c.sync();
 	}
+	Buf<u64> sliceTabD(c, sliceTab.size() ? sliceTab.size() : 1);
+	c.h2d(sliceTabD.p, sliceTab.data(), sliceTab.size() * 8);
+	c.sync();
 	tr.mark("C2 bfs");
 	// keep regions with >= 3 sorted vertices (rov.cpp:208-212); a failed sort (0) needs the reference's
 	// haplotype-lap fallback order (graph.cpp:194-395), which is not on the device yet -> counted, skipped
@@ -588,11 +933,12 @@ inline void call_device(Ctx &c, const DevGraph &G, const CallIn &in, const CallO
 	Buf<u32> rovVerts(c, sumJ);
 	u32 *rovVerts_ = rovVerts.p; const u32 *rovOff_ = rovOff.p;
 	{
-		const u32 *bigOff_ = bigOff.p, *bigVerts_ = bigVerts.p;
+		const u32 *bigSlice_ = bigSlice.p, *bigSlot_ = bigSlot.p; const u64 *tab = sliceTabD.p;
 		parallel_for<C_gather>(c, R, PV_LAMBDA(size_t r) {
 			u32 s = rovSrc_[r]; u32 n = rovJ_[r]; u32 o = rovOff_[r];
-			if (haveBig && bigOff_[s + 1] > bigOff_[s]) { for (u32 k = 0; k < n; k++) rovVerts_[o + k] = bigVerts_[bigOff_[s] + k]; }
-			else for (u32 k = 0; k < n; k++) rovVerts_[o + k] = vtmp_[s * 12 + k];
+			const u32 *src = vtmp_ + (size_t)s * 12;
+			if (haveBig && bigSlice_[s] != NONE) { const u64 *t = tab + 3 * (size_t)bigSlice_[s]; src = (const u32 *)(uintptr_t)t[0] + (size_t)bigSlot_[s] * t[1] + t[2]; }
+			for (u32 k = 0; k < n; k++) rovVerts_[o + k] = src[k];
 		});
 	}
 	rovFl.to_hvec(out.rov_fl, R); rovComp.to_hvec(out.rov_comp, R);
@@ -633,8 +979,9 @@ inline void call_device(Ctx &c, const DevGraph &G, const CallIn &in, const CallO
 			chunkEnd.push_back(r1); r0 = r1;
 		}
 	}
-	Buf<u32> errs(c, 4);
+	Buf<u32> errs(c, 4);   // [0] hard errors, [1] inversion pin pairs, [2] depth overflow, [3] tangled regions
 	errs.zero();
+	u32 seenTangled = 0;
 
 	u32 r0 = 0;
 	for (u32 r1 : chunkEnd) {
@@ -646,7 +993,7 @@ inline void call_device(Ctx &c, const DevGraph &G, const CallIn &in, const CallO
 		Buf<u16> mat(c, cells ? cells : 1);
 		Buf<u32> lapStart(c, nRows ? nRows : 1), lapLen(c, nRows ? nRows : 1), hasData(c, Rc);
 		c.memset0(mat.p, cells * 2); lapStart.fill_ff(); hasData.zero();
-		const RovView rv{rovOff.p, rovVerts.p, rovComp.p, rowPre.p, cellPre.p, hkey.p, hval.p, hsize - 1, Rc, uniformNh, r0};
+		const RovView rv{rovOff.p, rovVerts.p, rovComp.p, rowPre.p, cellPre.p, hkey.p, hval.p, hsize - 1, Rc, uniformNh, r0, nullptr};
 		const ChunkView cv{g, rv, mat.p, lapStart.p, lapLen.p, rovTangled_ + r0, hasData.p, errs.p};
 		tr.mark("chunk setup");
 		// ---- C3: depth matrix (allele.hpp:804-862), one thread per (region, column)
@@ -669,7 +1016,7 @@ inline void call_device(Ctx &c, const DevGraph &G, const CallIn &in, const CallO
 				u32 code = n == 1 ? ((g.steps[first] & 1u) ? 2u : 1u) : n;
 				cv.mat[rv.matBase(r) + (u64)i * J + j] = (u16)code;
 				atomic_min(cv.lapStart + rv.rowBase(r) + i, first);
-				if (n > 1 && (j == 0 || j == J - 1)) cv.tangled[r] = 1;
+				if (n > 1 && (j == 0 || j == J - 1) && atomic_exch(cv.tangled + r, 1u) == 0) atomic_add(cv.errs + 3, 1u);
 			}
 		});
 		// ---- C4: lap 0 of every (region, path): the first run of consecutive steps on region vertices (untangle.cpp:29-103)
@@ -685,135 +1032,10 @@ inline void call_device(Ctx &c, const DevGraph &G, const CallIn &in, const CallO
 		});
 		tr.mark("C3 C4 matrix+laps");
 
-		for (u32 k = 0; k < nRefs; k++) {
-			const u32 refH = in.refs[k];
-			const u32 refLocal = G.hapLocal[refH];
-			const u32 refStep0 = G.h_stepOff[refH];
-			// ---- C5a: contexts per (region, path) pair
-			Buf<u32> pairCnt(c, (size_t)nRows + 1), candOff(c, (size_t)nRows + 1);
-			u32 *pairCnt_ = pairCnt.p; const u32 *candOff_ = candOff.p;
-			parallel_for<C_pair_count>(c, (size_t)nRows + 1, PV_LAMBDA(size_t row) {
-				pairCnt_[row] = row < nRows ? scan_pair(cv, refLocal, k, (u32)row, false, CandView{}, 0) : 0u;
-			});
-			exclusive_scan(c, pairCnt.p, candOff.p, (size_t)nRows + 1, OpAddU32(), 0u);
-			const u32 nCand = candOff.read(nRows);
-			const size_t nC1 = nCand ? nCand : 1;
-			Buf<u32> cL(c, nC1), cR(c, nC1), cStart(c, nC1), cLen(c, nC1), cRS(c, nC1), cRL(c, nC1), cHap(c, nC1), cCls(c, nC1), cHead(c, nC1), gCount(c, nC1), hsort(c, nC1);
-			const CandView cd{cL.p, cR.p, cStart.p, cLen.p, cRS.p, cRL.p, cHap.p, cCls.p, cHead.p, gCount.p, hsort.p};
-			// ---- C5b: slices per context, classification
-			if (nCand) parallel_for<C_pair_fill>(c, nRows, PV_LAMBDA(size_t row) {
-				if (candOff_[row + 1] == candOff_[row]) return;
-				scan_pair(cv, refLocal, k, (u32)row, true, cd, candOff_[row]);
-			});
-			tr.mark("C5 pairs");
-			// ---- C6a: group alt slices by (context, class, walk) per region, order groups like the reference's std::maps
-			Buf<u32> recCnt(c, (size_t)Rc + 1), grpCnt(c, (size_t)Rc + 1), recOff(c, (size_t)Rc + 1), grpOff(c, (size_t)Rc + 1);
-			u32 *recCnt_ = recCnt.p, *grpCnt_ = grpCnt.p;
-			parallel_for<C_group>(c, (size_t)Rc + 1, PV_LAMBDA(size_t rr_) {
-				if (rr_ >= Rc) { recCnt_[rr_] = 0; grpCnt_[rr_] = 0; return; }
-				u32 r = (u32)rr_;
-				u32 b = candOff_[rv.rowBase(r)], e = candOff_[rv.rowBase(r + 1)];
-				u32 *a = cd.hsort + b; u32 nh = 0;
-				for (u32 x = b; x < e; x++) {
-					if (cd.cCls[x] == 3) continue;
-					u32 found = NONE;
-					for (u32 t = 0; t < nh; t++) {
-						u32 y = a[t];
-						if (same_record(cd, x, y) && cd.cLen[y] == cd.cLen[x] && walk_equal(g.steps, cd.cStart[y], cd.cStart[x], cd.cLen[x])) { found = y; break; }
-					}
-					if (found == NONE) { a[nh++] = x; cd.cHead[x] = x; cd.gCount[x] = 1; }
-					else { cd.cHead[x] = found; cd.gCount[found]++; }
-				}
-				for (u32 st = nh / 2; st-- > 0;) sift_down(g.steps, cd, a, st, nh);
-				for (u32 end = nh; end-- > 1;) { u32 t = a[0]; a[0] = a[end]; a[end] = t; sift_down(g.steps, cd, a, 0, end); }
-				u32 nrec = 0;
-				for (u32 t = 0; t < nh; t++) if (t == 0 || !same_record(cd, a[t - 1], a[t])) nrec++;
-				recCnt_[r] = nrec; grpCnt_[r] = nh;
-				if (k == 0) cv.hasData[r] = nh ? 1u : 0u;
-				else if (nh == 0 && cv.hasData[r]) atomic_add(cv.errs + 0, 1u);   // std::map::at throws in the reference
-			});
-			exclusive_scan(c, recCnt.p, recOff.p, (size_t)Rc + 1, OpAddU32(), 0u);
-			exclusive_scan(c, grpCnt.p, grpOff.p, (size_t)Rc + 1, OpAddU32(), 0u);
-			const u32 nRec = recOff.read(Rc), nGrp = grpOff.read(Rc);
-			if (nRec == 0) continue;
-			// ---- C6b: records + groups (offsets already global: the host only appends)
-			const u32 grpBase = (u32)out.grp_hap.size(); const u64 gtBase = out.gt.size(); const size_t recBase = out.rec_rov.size();
-			Buf<u32> oRov(c, nRec), oRef(c, nRec), oL(c, nRec), oR(c, nRec), oVt(c, nRec), oPos(c, nRec), oRS(c, nRec), oRL(c, nRec), oGrp(c, (size_t)nRec + 1);
-			Buf<u32> gHap(c, nGrp), gStart(c, nGrp), gLen(c, nGrp), gCnt(c, nGrp), headRec(c, nCand), headOrd(c, nCand);
-			Buf<u64> gtOff(c, (size_t)nRec + 1), recNh(c, (size_t)nRec + 1);
-			u32 *oRov_ = oRov.p, *oRef_ = oRef.p, *oL_ = oL.p, *oR_ = oR.p, *oVt_ = oVt.p, *oPos_ = oPos.p, *oRS_ = oRS.p, *oRL_ = oRL.p, *oGrp_ = oGrp.p;
-			u32 *gHap_ = gHap.p, *gStart_ = gStart.p, *gLen_ = gLen.p, *gCnt_ = gCnt.p, *headRec_ = headRec.p, *headOrd_ = headOrd.p;
-			u64 *gtOff_ = gtOff.p, *recNh_ = recNh.p; const u32 *recOff_ = recOff.p, *grpOff_ = grpOff.p;
-			parallel_for<C_emit>(c, Rc, PV_LAMBDA(size_t rr_) {
-				u32 r = (u32)rr_;
-				u32 nh = grpOff_[r + 1] - grpOff_[r];
-				if (!nh) return;
-				const u32 *a = cd.hsort + candOff_[rv.rowBase(r)];
-				u32 rec = recOff_[r], gi = grpOff_[r]; u32 ord = 0;
-				u32 nhaps = rv.rowBase(r + 1) - rv.rowBase(r);
-				for (u32 t = 0; t < nh; t++) {
-					u32 y = a[t];
-					if (t == 0 || !same_record(cd, a[t - 1], y)) {
-						if (t) rec++;
-						ord = 0;
-						u32 cls = cd.cCls[y];
-						oRov_[rec] = r + rv.rShift; oRef_[rec] = refH; oL_[rec] = cd.cL[y]; oR_[rec] = cd.cR[y];
-						oVt_[rec] = cls == 0 ? (u32)VT_INS : (cls == 1 ? (u32)VT_SUB : (u32)VT_DEL);
-						oRS_[rec] = cd.cRS[y]; oRL_[rec] = cd.cRL[y];
-						u32 l = g.loci[cd.cRS[y] + 1];                       // comp_pos (allele.hpp:161-179)
-						oPos_[rec] = cls == 1 ? l : l - 1;
-						oGrp_[rec] = grpBase + gi; recNh_[rec] = nhaps;
-					}
-					ord++;
-					headRec_[y] = rec; headOrd_[y] = ord;
-					u32 hh = g.cpList[g.cpOff[rv.comp(r)] + cd.cHap[y]];
-					gHap_[gi] = hh; gStart_[gi] = cd.cStart[y] - g.stepOff[hh]; gLen_[gi] = cd.cLen[y]; gCnt_[gi] = cd.gCount[y];
-					gi++;
-				}
-			});
-			c.memset0(recNh.p + nRec, 8);
-			exclusive_scan(c, recNh.p, gtOff.p, (size_t)nRec + 1, OpAddU64(), (u64)0);
-			u64 nGt; c.d2h(&nGt, gtOff.p + nRec, 8);
-			Buf<u16> gt(c, nGt ? nGt : 1);
-			c.memset_ff(gt.p, nGt * 2);
-			u16 *gt_ = gt.p;
-			tr.mark("C6 group+emit");
-			// ---- C7: genotypes.  Paths equal to the ref over the context columns with an identical slice -> 0 (overlay.cpp:534-580)
-			parallel_for<C_gt_ref>(c, nGt, PV_LAMBDA(size_t x) {
-				u32 rec = uniformNh ? (u32)(x / uniformNh) : (u32)(ub_u64(gtOff_, 0, (u64)nRec + 1, (u64)x) - 1);
-				u32 i = (u32)(x - gtOff_[rec]);
-				u32 r = oRov_[rec] - rv.rShift; u32 J = rv.J(r);
-				u32 lv = oL_[rec] >> 1, rvx = oR_[rec] >> 1;
-				u32 ju = rv.find(r, lv), jv = rv.find(r, rvx);
-				if (ju > jv) { u32 t = ju; ju = jv; jv = t; }
-				const u16 *rr = cv.mat + rv.matBase(r) + (u64)refLocal * J, *ar = cv.mat + rv.matBase(r) + (u64)i * J;
-				for (u32 j = ju; j <= jv; j++) if (rr[j] != ar[j]) return;
-				u32 row = rv.rowBase(r) + i;
-				if (cv.lapStart[row] == NONE) return;
-				u32 as, an;
-				if (!slice_bounds(g, lv, rvx, cv.lap(row), as, an)) return;
-				if (an != oRL_[rec] || !walk_equal(g.steps, oRS_[rec], as, an)) return;
-				gt_[x] = 0;
-			});
-			parallel_for<C_gt_alt>(c, nCand, PV_LAMBDA(size_t x) {
-				if (cd.cCls[x] == 3) return;
-				u32 hd = cd.cHead[x]; u32 rec = headRec_[hd];
-				gt_[gtOff_[rec] + cd.cHap[x]] = (u16)headOrd_[hd];
-			});
-			// the host sees ref-slice starts relative to the ref path, and global gt offsets
-			parallel_for<C_keep>(c, (size_t)nRec + 1, PV_LAMBDA(size_t i) { if (i < nRec) oRS_[i] -= refStep0; gtOff_[i] += gtBase; });
-			tr.mark("C7 genotypes");
-			// ---- results of this (chunk, ref): asynchronous appends into the pinned host vectors
-			auto app = [&](hvec<u32> &dst, const Buf<u32> &src, u32 n) { size_t o = dst.size(); dst.resize(o + n); c.d2h_async(dst.data() + o, src.p, (size_t)n * 4); };
-			app(out.rec_rov, oRov, nRec); app(out.rec_ref, oRef, nRec); app(out.rec_cxtL, oL, nRec); app(out.rec_cxtR, oR, nRec); app(out.rec_vt, oVt, nRec); app(out.rec_pos, oPos, nRec);
-			app(out.rec_refStart, oRS, nRec); app(out.rec_refLen, oRL, nRec);
-			app(out.grp_hap, gHap, nGrp); app(out.grp_start, gStart, nGrp); app(out.grp_len, gLen, nGrp); app(out.grp_count, gCnt, nGrp);
-			out.rec_grpOff.resize(recBase + nRec + 1); c.d2h_async(out.rec_grpOff.data() + recBase, oGrp.p, (size_t)nRec * 4);
-			out.rec_gtOff.resize(recBase + nRec + 1); c.d2h_async(out.rec_gtOff.data() + recBase, gtOff.p, ((size_t)nRec + 1) * 8);
-			out.gt.resize(gtBase + nGt); c.d2h_async(out.gt.data() + gtBase, gt.p, nGt * 2);
-			c.sync();   // the device buffers of this round die at the end of the scope
-			out.rec_grpOff[recBase + nRec] = grpBase + nGrp;
-			tr.mark("records d2h");
+		overlay_pass(c, G, g, in, rv, cv, Rc, nRows, out, tr);
+		{
+			u32 he3 = errs.read(3);
+			if (he3 != seenTangled) { seenTangled = he3; tangled_pass(c, G, g, in, rv, cv, Rc, rovTangled_ + r0, errs.p, out, tr); }
 		}
 		r0 = r1;
 	}

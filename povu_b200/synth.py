@@ -392,3 +392,40 @@ def truncate(g, n_vertices):
         k = int(out[0]) if len(out) else len(st)
         paths.append((name, st[:k], sr[:k]))
     return make_graph(g["ids"][:n_vertices], g["seqs"][:n_vertices] if g["seqs"] is not None else None, L, paths)
+
+
+def repeat_loops(seed, n_units=6, n_paths=6, max_laps=4, first_id=1):
+    """Tangled regions: a backbone whose units `r1 -> (x | y | -) -> r2` carry a back link r2 -> r1, and paths that
+    run through a unit 1..max_laps times picking an allele per lap (a VNTR-like repeat, as in LPA's KIV-2).
+    Path 0 takes one lap of allele x everywhere unless `seed` is odd (then it loops too)."""
+    rng = _rng(seed)
+    seqs, links, units = [], [], []
+
+    def new_v():
+        seqs.append("".join("ACGT"[int(c)] for c in rng.integers(0, 4, size=int(rng.integers(1, 5)))))
+        return len(seqs) - 1
+
+    prev = new_v()
+    for _ in range(n_units):
+        r1, x, y, r2, nxt = new_v(), new_v(), new_v(), new_v(), new_v()
+        links += [link(prev, "+", r1, "+"), link(r1, "+", x, "+"), link(r1, "+", y, "+"), link(x, "+", r2, "+"), link(y, "+", r2, "+"),
+                  link(r2, "+", r1, "+"), link(r2, "+", nxt, "+")]
+        has_del = rng.uniform() < 0.4
+        if has_del:
+            links.append(link(r1, "+", r2, "+"))
+        units.append((prev, r1, x, y, r2, nxt, has_del))
+        prev = nxt
+    paths = []
+    for p in range(n_paths):
+        st = [units[0][0]]
+        for (_, r1, x, y, r2, nxt, has_del) in units:
+            laps = 1 if (p == 0 and seed % 2 == 0) else int(rng.integers(1, max_laps + 1))
+            for _ in range(laps):
+                st.append(r1)
+                c = 0 if (p == 0 and seed % 2 == 0) else int(rng.integers(0, 3 if has_del else 2))
+                if c < 2:
+                    st.append(x if c == 0 else y)
+                st.append(r2)
+            st.append(nxt)
+        paths.append((f"S{p // 2 + 1:03d}#{p % 2 + 1}#chr1", np.array(st, dtype=np.uint32), np.zeros(len(st), dtype=np.uint8)))
+    return make_graph(np.arange(first_id, first_id + len(seqs), dtype=np.uint32), seqs, links, paths)

@@ -1,8 +1,8 @@
 """Shared parity checks for the call half (used by test_call_emu.py on CPU and test_call_gpu.py on the
 B200): VCF text produced through the pvgpu_session_* C ABI against (a) the committed outputs of the
 compiled reference (tests/golden/expected) and (b) the CPU oracle (oracle/povu_oracle) on seeded synthetic
-graphs.  Bit-exact (text).  Records of tangled regions and SUBR records are compared only where the
-product implements them (see DESIGN.md "call: coverage")."""
+graphs.  Bit-exact (text).  SUBR records (inversion / SNE pass) are not produced yet and are excluded from the
+comparison."""
 import os
 import subprocess
 import tempfile
@@ -23,8 +23,8 @@ def split(text, only_plain):
     lines = text.splitlines()
     hdr = [l for l in lines if l.startswith("#") and not l.startswith("##fileDate")]
     rec = [l for l in lines if not l.startswith("#")]
-    if only_plain:
-        rec = [l for l in rec if "TANGLED=F" in l and "VARTYPE=SUBR" not in l]
+    if only_plain:      # what the product does not emit yet: SUBR records of the inversion (SNE) pass
+        rec = [l for l in rec if "VARTYPE=SUBR" not in l]
     return hdr, rec
 
 
@@ -45,8 +45,8 @@ def check_golden(pv, name, tmp):
     wh, wr = split(want, True)
     assert gh == wh, "VCF header differs"
     assert sorted(gr) == sorted(wr), "VCF records differ"
-    if name not in ("LPA", "hairpin_inversion_subr"):
-        assert got == want, "byte-exact (including record order) on single-forest inputs"
+    if name != "hairpin_inversion_subr":
+        assert got == want, "byte-exact, including record order (LPA: all 2238 records, 1270 of them from tangled regions)"
     assert st["hard_errors"] == 0
     return st
 
@@ -67,6 +67,7 @@ def check_vs_oracle(pv, g, prefixes, tmp, chunk=100, exact_order=True):
     want = oracle_vcf(gfa, prefixes, chunk)
     gh, gr = split(got, False)
     wh, wr = split(want, True)
+    gr = [l for l in gr if "TANGLED=T" not in l]      # the oracle restatement skips tangled regions
     assert gh == wh
     if exact_order:
         assert gr == wr
@@ -74,6 +75,40 @@ def check_vs_oracle(pv, g, prefixes, tmp, chunk=100, exact_order=True):
         assert sorted(gr) == sorted(wr)
     assert st["hard_errors"] == 0
     return st
+
+
+REF = os.path.join(ROOT, "oracle", "_ref", "povu_ref")
+
+
+def reference_vcf(gfa, prefixes, chunk=100):
+    """VCF of the compiled, unmodified reference (oracle/_ref: built by oracle/Makefile, travels to the GPU box)."""
+    cmd = [REF, "gfa2vcf", "-i", gfa, "-t", "1", "-c", str(chunk)]
+    for p in prefixes:
+        cmd += ["-P", p]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-300:]
+    return r.stdout
+
+
+def run_tangled_vs_reference(pv, tmp, n_seeds=24):
+    """Tangled regions (untangle + lap alignment): VNTR-like repeat units that paths traverse 1..5 times.  The oracle
+    restatement does not cover this sub-path, so the checker is the compiled reference itself."""
+    import pytest
+    if not os.path.exists(REF):
+        pytest.skip("oracle/_ref/povu_ref not built")
+    tangled = records = 0
+    gfa = os.path.join(tmp, "t.gfa")
+    for seed in range(n_seeds):
+        g = synth.repeat_loops(seed, n_units=3 + seed % 5, n_paths=3 + seed % 6, max_laps=2 + seed % 4)
+        synth.write_gfa(g, gfa)
+        got, st, _ = gfa2vcf(pv, gfa, ["S001#1"], chunk=1 + seed % 7)
+        want = reference_vcf(gfa, ["S001#1"], chunk=1 + seed % 7)
+        gh, gr = split(got, False)
+        wh, wr = split(want, True)
+        assert gh == wh and gr == wr, f"seed {seed}"
+        assert st["hard_errors"] == 0
+        tangled += st["tangled"]; records += sum("TANGLED=T" in l for l in gr)
+    assert tangled > 20 and records > 20, (tangled, records)
 
 
 def run_all_synthetic(pv, tmp, n_seeds=12):

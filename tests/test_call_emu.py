@@ -39,3 +39,7 @@ def test_emu_rejects_invalid_gfa(emu_lib, name):
     pv = _ctx(emu_lib, 0)
     with pytest.raises(RuntimeError, match="Invalid GFA"):
         api.Session(pv, helpers.fixture_path(name))
+
+
+def test_emu_call_tangled_vs_reference(emu_lib, built, tmp_path):
+    cc.run_tangled_vs_reference(_ctx(emu_lib, 1), str(tmp_path), n_seeds=16)

@@ -31,3 +31,7 @@ def test_gpu_pvst_roundtrip(gpu, name, tmp_path):
 def test_gpu_rejects_invalid_gfa(gpu, name):
     with pytest.raises(RuntimeError, match="Invalid GFA"):
         api.Session(gpu, helpers.fixture_path(name))
+
+
+def test_gpu_call_tangled_vs_reference(gpu, tmp_path):
+    cc.run_tangled_vs_reference(gpu, str(tmp_path), n_seeds=32)
