@@ -134,11 +134,11 @@ static void write_vcfs(const Config &c, Dev &d, const std::vector<std::string> &
 	std::vector<const char *> pp;
 	for (auto &p : prefixes) pp.push_back(p.c_str());
 	d.check(pvgpu_session_call(d.s, pp.data(), pp.size()));
-	uint64_t st[10];
+	uint64_t st[12];
 	pvgpu_session_call_stats(d.s, st);
 	if (st[5]) throw Fail{"call: the reference aborts on this input (missing context boundary in a haplotype lap)"};
-	if (st[2] || st[3] || st[4]) fprintf(stderr, "WARN [povu_b200::call] %llu tangled regions, %llu inversion pin pairs and %llu regions needing the haplotype-lap order were skipped (not on the device yet)\n",
-					     (unsigned long long)st[2], (unsigned long long)st[3], (unsigned long long)st[4]);
+	if (st[4]) fprintf(stderr, "WARN [povu_b200::call] %llu regions need the haplotype-lap vertex order (graph.cpp:194-395), which is not on the device yet: skipped\n", (unsigned long long)st[4]);
+	if (st[10]) fprintf(stderr, "WARN [povu_b200::call] %llu SUBR records had a merged length past the end of a walk (undefined in the reference): clamped\n", (unsigned long long)st[10]);
 	const bool to_stdout = !c.have_out || c.stdout_vcf;
 	if (to_stdout) {
 		size_t n = 0; char *t = pvgpu_session_vcf_text(d.s, c.chunk, 1, nullptr, &n);

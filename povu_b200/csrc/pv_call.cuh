@@ -313,13 +313,15 @@ struct Records {
 	hvec<u32> grp_hap, grp_start, grp_len, grp_count;   // start = step index inside the path
 	hvec<u16> gt;           // per record: one code per path of the region's component (0 ref, i alt group, 0xFFFF missing)
 	std::vector<u32> cpOff, cpList;   // paths of every component = the columns of `gt`
+	u64 n_subr_clamped = 0;   // SUBR records whose merged length ran past the end of a walk (the reference reads out of bounds there)
+	u64 n_regions = 0;   // real regions; rov_* entries beyond them are per-ref pseudo regions that carry the SUBR records
 	u64 n_called = 0, n_too_small = 0, n_sort_failed = 0, n_tangled = 0, n_pin_pairs = 0, n_hard_errors = 0, n_chunks = 0, n_big_bfs = 0, max_J = 0;
 	size_t n() const { return rec_rov.size(); }
 	void reset() {
 		rov_fl.clear(); rov_comp.clear(); rov_tangled.clear();
 		rec_rov.clear(); rec_ref.clear(); rec_cxtL.clear(); rec_cxtR.clear(); rec_vt.clear(); rec_pos.clear(); rec_refStart.clear(); rec_refLen.clear();
 		rec_grpOff.clear(); rec_gtOff.clear(); grp_hap.clear(); grp_start.clear(); grp_len.clear(); grp_count.clear(); gt.clear();
-		n_called = n_too_small = n_sort_failed = n_tangled = n_pin_pairs = n_hard_errors = n_chunks = n_big_bfs = max_J = 0;
+		n_regions = 0; n_subr_clamped = 0; n_called = n_too_small = n_sort_failed = n_tangled = n_pin_pairs = n_hard_errors = n_chunks = n_big_bfs = max_J = 0;
 	}
 };
 typedef Records CallOut;
@@ -332,6 +334,7 @@ struct RovView {
 	const u64 *rowPre, *cellPre;             // prefix sums of matrix rows / cells over the view's items
 	const u64 *hkey; const u32 *hval; u64 hmask;
 	u32 R; u32 uniformNh; u32 rShift;
+	const u32 *instJ; // ref lap / alignment column of an unrolled matrix (nullptr for plain regions)
 	const u32 *map;   // nullptr: item r of the view is region rShift + r (a chunk of regions);
 	                  // else item r is an unrolled matrix of region map[r] (tangled regions) and rShift = 0
 	PV_DEV u32 region(u32 r) const { return map ? map[r] : rShift + r; }
@@ -414,7 +417,7 @@ PV_DEV u32 scan_pair(const ChunkView &cv, u32 refLocal, u32 k, u32 row, bool fil
 					u32 o = off + cnt; cd.cCls[o] = 3;
 					u32 rs = 0, rn = 0, as = 0, an = 0;
 					if (fu == NONE || lv == NONE || !slice_bounds(g, u, v, rl, rs, rn) || !slice_bounds(g, u, v, al, as, an)) atomic_add(cv.errs + 0, 1u);   // the reference exits / crashes here
-					else if (rn == an && walk_revcomp(g.steps, rs, as, rn)) atomic_add(cv.errs + 1, 1u);   // inversion pin pair (SNE)
+					else if (rn == an && walk_revcomp(g.steps, rs, as, rn)) { cd.cCls[o] = 4; cd.cRS[o] = rs; cd.cStart[o] = as; cd.cHap[o] = i; }   // inversion pin pair for SNE (overlay.cpp:487-496)
 					else if (rn == an && walk_equal(g.steps, rs, as, rn)) { }
 					else {
 						cd.cL[o] = g.steps[fu]; cd.cR[o] = g.steps[lv]; cd.cStart[o] = as; cd.cLen[o] = an; cd.cRS[o] = rs; cd.cRL[o] = rn; cd.cHap[o] = i;
@@ -427,7 +430,15 @@ PV_DEV u32 scan_pair(const ChunkView &cv, u32 refLocal, u32 k, u32 row, bool fil
 		} else if (x != y) diff = true;
 	}
 	if (empty) return 0;
-	if (inv) { if (!fill) atomic_add(cv.errs + 1, 1u); return 0; }
+	if (inv) {   // every shared column is visited in opposite orientation: one pin pair (ref lap front, alt lap back), overlay.cpp:455-460
+		if (fill) {
+			Lap rl = cv.lap(rv.rowBase(r) + refLocal), al = cv.lap(row);
+			cd.cCls[off] = 3;
+			if (rl.lo == NONE || al.lo == NONE || rl.hi == rl.lo || al.hi == al.lo) atomic_add(cv.errs + 0, 1u);
+			else { cd.cCls[off] = 4; cd.cRS[off] = rl.lo; cd.cStart[off] = al.hi - 1; cd.cHap[off] = i; }
+		}
+		return 1;
+	}
 	return cnt;
 }
 
@@ -449,10 +460,19 @@ PV_DEV void sift_down(const u32 *steps, const CandView &cd, u32 *a, u32 root, u3
 	}
 }
 
+// inversion pin pairs collected while overlaying (ise::pin_cushion, /root/reference/include/ita/variation/sne.hpp:112-170);
+// kept on the device in pieces, one per overlay pass, with the key that restores the reference's insertion order
+struct PinStore {
+	struct Piece { Buf<u32> keyR, keyJ, keyK, keySlot, refStep, altStep; u32 n; };
+	std::vector<Piece> pieces; u64 total = 0;
+};
+PV_KERNEL(S_pinflag, 8);
+PV_KERNEL(S_pinpack, 40);
+
 // comp_exps over every matrix of a view (overlay.cpp:348-588) for all ref paths, then records + genotypes
 // (vcf.cpp:20-121,241-273); results are appended to `out`.
 inline void overlay_pass(Ctx &c, const DevGraph &G, const GraphView &g, const CallIn &in, const RovView &rv, const ChunkView &cv, u32 Rc, u32 nRows,
-			 Records &out, Trace &tr) {
+			 Records &out, Trace &tr, PinStore &pins) {
 	const u32 nRefs = in.nRefs; const u32 uniformNh = rv.uniformNh;
 	for (u32 k = 0; k < nRefs; k++) {
 		const u32 refH = in.refs[k];
@@ -475,6 +495,25 @@ inline void overlay_pass(Ctx &c, const DevGraph &G, const GraphView &g, const Ca
 			scan_pair(cv, refLocal, k, (u32)row, true, cd, candOff_[row]);
 		});
 		tr.mark("C5 pairs");
+		if (nCand) {   // pin pairs sit in candidate slots of class 4: pack them, in slot order
+			Buf<u32> pf(c, nCand), pidx;
+			u32 *pf_ = pf.p;
+			parallel_for<S_pinflag>(c, nCand, PV_LAMBDA(size_t x) { pf_[x] = cd.cCls[x] == 4 ? 1u : 0u; });
+			const u32 np = compact_flags(c, pf.p, nCand, pidx);
+			if (np) {
+				pins.pieces.emplace_back();
+				PinStore::Piece &pc = pins.pieces.back();
+				pc.n = np; pc.keyR = Buf<u32>(c, np); pc.keyJ = Buf<u32>(c, np); pc.keyK = Buf<u32>(c, np); pc.keySlot = Buf<u32>(c, np); pc.refStep = Buf<u32>(c, np); pc.altStep = Buf<u32>(c, np);
+				u32 *kR = pc.keyR.p, *kJ = pc.keyJ.p, *kK = pc.keyK.p, *kS = pc.keySlot.p, *rS = pc.refStep.p, *aS = pc.altStep.p; const u32 *pidx_ = pidx.p;
+				parallel_for<S_pinpack>(c, np, PV_LAMBDA(size_t q) {
+					u32 x = pidx_[q];
+					u32 row = ub_u32(candOff_, 0, nRows + 1, x) - 1; u32 r = rv.row2rov(row);
+					kR[q] = rv.region(r); kJ[q] = rv.instJ ? rv.instJ[r] : 0u; kK[q] = k; kS[q] = x;
+					rS[q] = cd.cRS[x]; aS[q] = cd.cStart[x];
+				});
+				pins.total += np;
+			}
+		}
 		// ---- C6a: group alt slices by (context, class, walk) per region, order groups like the reference's std::maps
 		Buf<u32> recCnt(c, (size_t)Rc + 1), grpCnt(c, (size_t)Rc + 1), recOff(c, (size_t)Rc + 1), grpOff(c, (size_t)Rc + 1);
 		u32 *recCnt_ = recCnt.p, *grpCnt_ = grpCnt.p;
@@ -484,7 +523,7 @@ inline void overlay_pass(Ctx &c, const DevGraph &G, const GraphView &g, const Ca
 			u32 b = candOff_[rv.rowBase(r)], e = candOff_[rv.rowBase(r + 1)];
 			u32 *a = cd.hsort + b; u32 nh = 0;
 			for (u32 x = b; x < e; x++) {
-				if (cd.cCls[x] == 3) continue;
+				if (cd.cCls[x] >= 3) continue;
 				u32 found = NONE;
 				for (u32 t = 0; t < nh; t++) {
 					u32 y = a[t];
@@ -566,7 +605,7 @@ inline void overlay_pass(Ctx &c, const DevGraph &G, const GraphView &g, const Ca
 			gt_[x] = 0;
 		});
 		parallel_for<C_gt_alt>(c, nCand, PV_LAMBDA(size_t x) {
-			if (cd.cCls[x] == 3) return;
+			if (cd.cCls[x] >= 3) return;
 			u32 hd = cd.cHead[x]; u32 rec = headRec_[hd];
 			gt_[gtOff_[rec] + cd.cHap[x]] = (u16)headOrd_[hd];
 		});
@@ -587,6 +626,318 @@ inline void overlay_pass(Ctx &c, const DevGraph &G, const GraphView &g, const Ca
 	}
 }
 
+PV_KERNEL(S_word, 8);
+PV_KERNEL(S_item, 32);
+PV_KERNEL(S_extend, 64);
+PV_KERNEL(S_tree, 64);
+PV_KERNEL(S_gt, 8);
+
+// state of one slice tree (ist::slice_tree, /root/reference/include/ita/graph/slice_tree.hpp:106-848) in flat arenas
+struct SliceTree {
+	// vertices, keyed by ref start
+	u32 *vStart, *vLeft, *vRight, *vAltHead, *vAltTail, *vKeyHead, *vLenHead; u32 nV;
+	u32 *hKey, *hVal; u32 hMask;                 // ref start -> vertex
+	u32 *aHap, *aStart, *aLen, *aNext, *aLive; u32 nA;   // alts of a vertex, in insertion order
+	u32 *kHap, *kNext; u32 nK;                   // alt-hap keys present in a vertex's `alts` map (they survive removals)
+	u32 *lLen, *lHap, *lNext, *lLive; u32 nL;    // (len, hap) members of a vertex's `len_haps`
+	u32 root;
+	PV_DEV u32 lookup(u32 start) const { u32 i = (u32)splitmix64(start) & hMask; while (true) { u32 k = hKey[i]; if (k == start) return hVal[i]; if (k == NONE) return NONE; i = (i + 1) & hMask; } }
+	PV_DEV u32 new_vertex(u32 start) {
+		u32 v = nV++; vStart[v] = start; vLeft[v] = NONE; vRight[v] = NONE; vAltHead[v] = NONE; vAltTail[v] = NONE; vKeyHead[v] = NONE; vLenHead[v] = NONE;
+		u32 i = (u32)splitmix64(start) & hMask; while (hKey[i] != NONE) i = (i + 1) & hMask; hKey[i] = start; hVal[i] = v;
+		return v;
+	}
+	PV_DEV bool has_hap(u32 v, u32 h) const { for (u32 k = vKeyHead[v]; k != NONE; k = kNext[k]) if (kHap[k] == h) return true; return false; }
+	PV_DEV void add_key(u32 v, u32 h) { u32 k = nK++; kHap[k] = h; kNext[k] = vKeyHead[v]; vKeyHead[v] = k; }
+	PV_DEV void push_alt(u32 v, u32 h, u32 st, u32 len) {
+		u32 a = nA++; aHap[a] = h; aStart[a] = st; aLen[a] = len; aNext[a] = NONE; aLive[a] = 1;
+		if (vAltTail[v] == NONE) vAltHead[v] = a; else aNext[vAltTail[v]] = a;
+		vAltTail[v] = a;
+	}
+	PV_DEV void len_insert(u32 v, u32 len, u32 h) {
+		for (u32 l = vLenHead[v]; l != NONE; l = lNext[l]) if (lLive[l] && lLen[l] == len && lHap[l] == h) return;
+		u32 l = nL++; lLen[l] = len; lHap[l] = h; lLive[l] = 1; lNext[l] = vLenHead[v]; vLenHead[v] = l;
+	}
+	PV_DEV void len_erase(u32 v, u32 len, u32 h) { for (u32 l = vLenHead[v]; l != NONE; l = lNext[l]) if (lLive[l] && lLen[l] == len && lHap[l] == h) lLive[l] = 0; }
+	PV_DEV u32 nth_alt(u32 v, u32 h, u32 idx) const { u32 n = 0; for (u32 a = vAltHead[v]; a != NONE; a = aNext[a]) if (aLive[a] && aHap[a] == h) { if (n == idx) return a; n++; } return NONE; }
+	// vertex::insert_alt (slice_tree.hpp:347-356): std::map::insert does nothing when the hap key already exists
+	PV_DEV void insert_alt(u32 v, u32 h, u32 st, u32 len) { if (!has_hap(v, h)) { add_key(v, h); push_alt(v, h, st, len); } len_insert(v, len, h); }
+	PV_DEV void append_alt(u32 v, u32 h, u32 st, u32 len) { if (!has_hap(v, h)) add_key(v, h); push_alt(v, h, st, len); len_insert(v, len, h); }
+	PV_DEV void remove_alt(u32 v, u32 h, u32 idx) { u32 a = nth_alt(v, h, idx); aLive[a] = 0; len_erase(v, aLen[a], h); }
+	// vertex::check_update_type (slice_tree.hpp:284-345): returns comp_type, alt index in *ai
+	PV_DEV u32 check(u32 v, u32 refStart, u32 h, u32 st, u32 len, u32 *ai) const {
+		enum { NO_OVERLAP = 0, EXISTS = 1, REPLACE_ALT = 2, MERGE_EXTEND = 3, MERGE_REPLACE = 4, INSERT_ALT = 5, CONTAINED = 6, EXTEND_ALT = 7 };
+		bool same = vStart[v] == refStart;
+		if (same && !has_hap(v, h)) return INSERT_ALT;
+		u32 n = 0;
+		for (u32 a = vAltHead[v]; a != NONE; a = aNext[a]) {
+			if (!aLive[a] || aHap[a] != h) continue;
+			u32 as = aStart[a], al = aLen[a]; u32 ct = NONE;
+			if (as == st && al == len) ct = EXISTS;
+			else if (as < st && as + al >= st + len) ct = CONTAINED;
+			else if (st < as && st + len >= as + al) ct = REPLACE_ALT;
+			else if (as < st && as + al >= st && st + len >= as + al) ct = MERGE_EXTEND;
+			else if (st < as && st + len >= as && as + al >= st + len) ct = MERGE_REPLACE;
+			if (ct != NONE) { *ai = n; return ct; }
+			n++;
+		}
+		return same ? EXTEND_ALT : NO_OVERLAP;
+	}
+	// slice_tree::add_vertex (slice_tree.hpp:830-846).  Returns false where the reference exits.
+	PV_DEV bool add(u32 refStart, u32 h, u32 st, u32 len) {
+		enum { NO_OVERLAP = 0, EXISTS = 1, REPLACE_ALT = 2, MERGE_EXTEND = 3, MERGE_REPLACE = 4, INSERT_ALT = 5, CONTAINED = 6, EXTEND_ALT = 7 };
+		while (true) {
+			if (nV == 0) { u32 v = new_vertex(refStart); root = v; insert_alt(v, h, st, len); return true; }
+			u32 ct, ai = NONE, target;
+			u32 ex = lookup(refStart);
+			if (ex != NONE) {   // handle_existing_start
+				target = ex; ct = check(ex, refStart, h, st, len, &ai);
+				if (ct == NO_OVERLAP) return false;
+			} else {            // find_insert_point_traverse
+				u32 cur = root, ctr = 0; ct = NONE; target = NONE;
+				while (true) {
+					if (ctr++ >= nV) return false;
+					if (has_hap(cur, h)) {
+						u32 t = check(cur, refStart, h, st, len, &ai);
+						if (t == EXTEND_ALT) return false;
+						if (t != NO_OVERLAP) { ct = t; target = cur; break; }
+					}
+					// right() returns left_ in the reference (slice_tree.hpp:171-174): both directions test and follow the LEFT link
+					if (vLeft[cur] == NONE) {
+						u32 v = new_vertex(refStart);
+						if (refStart < vStart[cur]) vLeft[cur] = v; else vRight[cur] = v;
+						insert_alt(v, h, st, len);
+						return true;
+					}
+					cur = vLeft[cur];
+				}
+			}
+			switch (ct) {
+			case EXISTS: case CONTAINED: return true;
+			case INSERT_ALT: insert_alt(target, h, st, len); return true;
+			case EXTEND_ALT: append_alt(target, h, st, len); return true;
+			case REPLACE_ALT: remove_alt(target, h, ai); insert_alt(target, h, st, len); return true;
+			case MERGE_EXTEND: {
+				u32 a = nth_alt(target, h, ai); u32 oldLen = aLen[a]; u32 newLen = (st + len) - aStart[a];
+				aStart[a] = st; aLen[a] = newLen; len_erase(target, oldLen, h); len_insert(target, newLen, h);
+				return true;
+			}
+			case MERGE_REPLACE: {
+				u32 a = nth_alt(target, h, ai); u32 as = aStart[a], al = aLen[a];
+				remove_alt(target, h, ai);
+				len = (as + al) - st;      // then add_vertex(ref_h_start, alt_h_idx, alt_h_start, new_len) again
+				continue;
+			}
+			default: return false;
+			}
+		}
+	}
+};
+
+PV_DEV u32 half_diff_ceil(u32 a, u32 b) { u32 d = (a > b ? a : b) - (a < b ? a : b); return (d + 1) / 2; }
+
+// Seed-and-extend of the inversion pin pairs into maximal reverse-complement matches, the per-ref slice tree and the
+// SUBR records (ise::sne /root/reference/src/ita/variation/sne.cpp:32-454, gen_inv_recs src/ita/genomics/vcf.cpp:123-239).
+// Chains, limits and extensions are data-parallel; the slice tree is insertion-order dependent (quirk Q20) and is
+// replayed by one thread per ref path.
+inline void sne_pass(Ctx &c, const DevGraph &G, const GraphView &g, const CallIn &in, PinStore &pins, u32 R, u32 *errs, Records &out, Trace &tr) {
+	const u32 nP = (u32)pins.total, nRefs = in.nRefs;
+	Buf<u32> kR(c, nP), kJ(c, nP), kK(c, nP), kS(c, nP), rS(c, nP), aS(c, nP);
+	{
+		size_t o = 0;
+		for (auto &pc : pins.pieces) {
+			c.d2d(kR.p + o, pc.keyR.p, (size_t)pc.n * 4); c.d2d(kJ.p + o, pc.keyJ.p, (size_t)pc.n * 4); c.d2d(kK.p + o, pc.keyK.p, (size_t)pc.n * 4);
+			c.d2d(kS.p + o, pc.keySlot.p, (size_t)pc.n * 4); c.d2d(rS.p + o, pc.refStep.p, (size_t)pc.n * 4); c.d2d(aS.p + o, pc.altStep.p, (size_t)pc.n * 4);
+			o += pc.n;
+		}
+	}
+	// the reference's insertion order: region, unrolled matrix, ref, (path, context) = slot
+	Buf<u32> perm(c, nP), wk(c, nP);
+	u32 *perm_ = perm.p, *wk_ = wk.p;
+	parallel_for<S_word>(c, nP, PV_LAMBDA(size_t i) { perm_[i] = (u32)i; });
+	const u32 *words[4] = {kS.p, kK.p, kJ.p, kR.p};
+	for (int w = 0; w < 4; w++) {
+		const u32 *src = words[w];
+		parallel_for<S_word>(c, nP, PV_LAMBDA(size_t i) { wk_[i] = src[perm_[i]]; });
+		radix_sort_pairs(c, wk.p, perm.p, nP, 32);
+	}
+	// work items: pin pair o seen from ref ordinal kk (a pair between two ref paths belongs to both trees, sne.hpp:128-147)
+	const u32 *refs_ = nullptr;
+	Buf<u32> refsD(c, nRefs); c.h2d(refsD.p, in.refs, (size_t)nRefs * 4); refs_ = refsD.p;
+	const size_t nF = (size_t)nP * nRefs;
+	Buf<u32> fl(c, nF), idx;
+	u32 *fl_ = fl.p; const u32 *rS_ = rS.p, *aS_ = aS.p;
+	parallel_for<S_item>(c, nF, PV_LAMBDA(size_t x) {
+		u32 kk = (u32)(x / nP), o = (u32)(x % nP); u32 p = perm_[o];
+		u32 hr = ub_u32(g.stepOff, 0, g.H + 1, rS_[p]) - 1, ha = ub_u32(g.stepOff, 0, g.H + 1, aS_[p]) - 1;
+		fl_[x] = (hr == refs_[kk] || ha == refs_[kk]) ? 1u : 0u;
+	});
+	const u32 nItems = compact_flags(c, fl.p, nF, idx);
+	if (!nItems) return;
+	Buf<u32> iK(c, nItems), iAlt(c, nItems), iRef(c, nItems), iAltIdx(c, nItems), iperm(c, nItems), iw(c, nItems);
+	u32 *iK_ = iK.p, *iAlt_ = iAlt.p, *iRef_ = iRef.p, *iAltIdx_ = iAltIdx.p, *iperm_ = iperm.p, *iw_ = iw.p; const u32 *idx_ = idx.p;
+	parallel_for<S_item>(c, nItems, PV_LAMBDA(size_t t) {
+		u32 x = idx_[t]; u32 kk = x / nP, o = x % nP; u32 p = perm_[o];
+		u32 hr = ub_u32(g.stepOff, 0, g.H + 1, rS_[p]) - 1, ha = ub_u32(g.stepOff, 0, g.H + 1, aS_[p]) - 1;
+		u32 ri = rS_[p] - g.stepOff[hr], ai = aS_[p] - g.stepOff[ha];
+		iK_[t] = kk; iperm_[t] = (u32)t;
+		if (hr == refs_[kk]) { iAlt_[t] = ha; iRef_[t] = ri; iAltIdx_[t] = ai; }
+		else { iAlt_[t] = hr; iRef_[t] = ai; iAltIdx_[t] = ri; }
+	});
+	// order (ref ordinal, alt path, insertion order): stable sorts by alt path, then by ref ordinal
+	parallel_for<S_word>(c, nItems, PV_LAMBDA(size_t t) { iw_[t] = iAlt_[iperm_[t]]; });
+	radix_sort_pairs(c, iw.p, iperm.p, nItems, bits_for(g.H));
+	parallel_for<S_word>(c, nItems, PV_LAMBDA(size_t t) { iw_[t] = iK_[iperm_[t]]; });
+	radix_sort_pairs(c, iw.p, iperm.p, nItems, bits_for(nRefs));
+	// chain limits (sne.cpp:92-122) + extension of every link (sne.cpp:124-213)
+	Buf<u32> eOk(c, nItems), eRefStart(c, nItems), eAltStart(c, nItems), eLen(c, nItems), eK(c, nItems), eAlt(c, nItems);
+	u32 *eOk_ = eOk.p, *eRefStart_ = eRefStart.p, *eAltStart_ = eAltStart.p, *eLen_ = eLen.p, *eK_ = eK.p, *eAlt_ = eAlt.p;
+	parallel_for<S_extend>(c, nItems, PV_LAMBDA(size_t t) {
+		u32 me = iperm_[t]; u32 kk = iK_[me], alt = iAlt_[me];
+		bool hasPrev = t > 0 && iK_[iperm_[t - 1]] == kk && iAlt_[iperm_[t - 1]] == alt;
+		bool hasNext = t + 1 < nItems && iK_[iperm_[t + 1]] == kk && iAlt_[iperm_[t + 1]] == alt;
+		u32 cur = iRef_[me];
+		u32 limL = NONE, limR = NONE;
+		if (!hasPrev && hasNext) limR = half_diff_ceil(cur, iRef_[iperm_[t + 1]]);
+		else if (!hasNext && hasPrev) limL = half_diff_ceil(cur, iRef_[iperm_[t - 1]]);
+		else if (hasPrev && hasNext) { limL = half_diff_ceil(cur, iRef_[iperm_[t - 1]]); limR = half_diff_ceil(cur, iRef_[iperm_[t + 1]]); }
+		const u32 refH = refs_[kk];
+		const u32 rb = g.stepOff[refH], rn = g.stepOff[refH + 1] - rb, ab = g.stepOff[alt], an = g.stepOff[alt + 1] - ab;
+		const u32 f0 = cur, r0 = iAltIdx_[me];
+		// do_match (sne.cpp:32-57); indices past the end of a walk are undefined behaviour in the reference -> mismatch
+		auto match = [&](u32 i, u32 j) -> int {
+			if (i == NONE || j == NONE) return -1;
+			if (i >= rn || j >= an) return 1;
+			u32 x = g.steps[rb + i], y = g.steps[ab + j];
+			return ((x >> 1) == (y >> 1) && (x & 1u) != (y & 1u)) ? 0 : 1;
+		};
+		u32 S_i = limL == NONE ? f0 : f0 - limL - 1;
+		u32 S_j = limR == NONE ? r0 : r0 - limL - 1;      // (sic) tests the right limit, subtracts the left one (sne.cpp:170-172)
+		u32 E_j = limR == NONE ? NONE : r0 + limR + 1;
+		u32 E_i = limR == NONE ? NONE : f0 + limR + 1;
+		u32 i = f0, j = r0, da = 0, db = 0;
+		for (; i < E_i || j > S_j; ++i, j--) { if (match(i, j) != 0) break; da++; }
+		i = f0; j = r0;
+		for (; i > S_i || j < E_j; --i, ++j) { if (match(i, j) != 0) break; db++; }
+		u32 x = db == 0 ? f0 : (f0 - db) + 1;
+		u32 y = db == 0 ? r0 : r0 + (db - 1);
+		u32 z = da + db;
+		if (db > 0 && da > 0) z--;
+		eK_[t] = kk; eAlt_[t] = alt;
+		if (da == 0 && db == 0) { eOk_[t] = 0; return; }
+		eOk_[t] = 1; eRefStart_[t] = x; eLen_[t] = z; eAltStart_[t] = y - z + 1;
+	});
+	std::vector<u32> hK = eK.to_host();
+	tr.mark("S chains+extend");
+	// one slice tree per ref path, items in (alt path, insertion) order
+	u32 t0 = 0;
+	for (u32 kk = 0; kk < nRefs; kk++) {
+		u32 t1 = t0; while (t1 < nItems && hK[t1] == kk) t1++;
+		const u32 n = t1 - t0;
+		if (!n) continue;
+		u32 hcap = 4; while (hcap < 2 * n + 2) hcap <<= 1;
+		Buf<u32> vA(c, (size_t)n * 7), hT(c, (size_t)hcap * 2), aA(c, (size_t)n * 5), kA(c, (size_t)n * 2), lA(c, (size_t)n * 8);
+		Buf<u32> oRec(c, (size_t)n * 12), oSl(c, (size_t)n * 2), oHap(c, (size_t)n * 2), oCnt(c, 4), ord(c, n);
+		c.memset_ff(hT.p, (size_t)hcap * 4);
+		u32 *vA_ = vA.p, *hT_ = hT.p, *aA_ = aA.p, *kA_ = kA.p, *lA_ = lA.p, *oRec_ = oRec.p, *oSl_ = oSl.p, *oHap_ = oHap.p, *oCnt_ = oCnt.p, *ord_ = ord.p;
+		const u32 refH = in.refs[kk];
+		parallel_for<S_tree>(c, 1, PV_LAMBDA(size_t) {
+			SliceTree T;
+			T.vStart = vA_; T.vLeft = vA_ + n; T.vRight = vA_ + 2 * (size_t)n; T.vAltHead = vA_ + 3 * (size_t)n; T.vAltTail = vA_ + 4 * (size_t)n; T.vKeyHead = vA_ + 5 * (size_t)n; T.vLenHead = vA_ + 6 * (size_t)n; T.nV = 0;
+			T.hKey = hT_; T.hVal = hT_ + hcap; T.hMask = hcap - 1;
+			T.aHap = aA_; T.aStart = aA_ + n; T.aLen = aA_ + 2 * (size_t)n; T.aNext = aA_ + 3 * (size_t)n; T.aLive = aA_ + 4 * (size_t)n; T.nA = 0;
+			T.kHap = kA_; T.kNext = kA_ + n; T.nK = 0;
+			T.lLen = lA_; T.lHap = lA_ + 2 * (size_t)n; T.lNext = lA_ + 4 * (size_t)n; T.lLive = lA_ + 6 * (size_t)n; T.nL = 0;
+			T.root = NONE;
+			for (u32 t = t0; t < t1; t++) {
+				if (!eOk_[t]) continue;
+				if (!T.add(eRefStart_[t], eAlt_[t], eAltStart_[t], eLen_[t])) { atomic_add(errs + 0, 1u); break; }
+			}
+			// records: vertices by ascending ref start (std::map order), per vertex the lengths ascending (vcf.cpp:147-150)
+			u32 nv = T.nV;
+			for (u32 v = 0; v < nv; v++) ord_[v] = v;
+			for (u32 a = 1; a < nv; a++) { u32 x = ord_[a]; u32 b = a; while (b > 0 && T.vStart[ord_[b - 1]] > T.vStart[x]) { ord_[b] = ord_[b - 1]; b--; } ord_[b] = x; }
+			u32 nRec = 0, nSl = 0, nHp = 0;
+			for (u32 q = 0; q < nv; q++) {
+				u32 v = ord_[q];
+				u32 lastLen = 0; bool first = true;
+				while (true) {   // next distinct live length above lastLen
+					u32 best = NONE;
+					for (u32 l = T.vLenHead[v]; l != NONE; l = T.lNext[l]) if (T.lLive[l] && (first || T.lLen[l] > lastLen) && T.lLen[l] < best) best = T.lLen[l];
+					if (best == NONE) break;
+					first = false; lastLen = best;
+					// alt set: haps of the length class ascending, their alts of that length in insertion order
+					u32 sl0 = nSl, hp0 = nHp;
+					u32 lastHap = 0; bool firstH = true;
+					while (true) {
+						u32 bh = NONE;
+						for (u32 l = T.vLenHead[v]; l != NONE; l = T.lNext[l]) if (T.lLive[l] && T.lLen[l] == best && (firstH || T.lHap[l] > lastHap) && T.lHap[l] < bh) bh = T.lHap[l];
+						if (bh == NONE) break;
+						firstH = false; lastHap = bh;
+						oHap_[nHp++] = bh;
+						for (u32 a = T.vAltHead[v]; a != NONE; a = T.aNext[a]) if (T.aLive[a] && T.aHap[a] == bh && T.aLen[a] == best) { oSl_[2 * (size_t)nSl] = bh; oSl_[2 * (size_t)nSl + 1] = T.aStart[a]; nSl++; }
+					}
+					if (nSl == sl0) { nHp = hp0; continue; }   // no alts at that length: no record (vcf.cpp:214-215)
+					u32 *o = oRec_ + 6 * (size_t)nRec;
+					o[0] = T.vStart[v]; o[1] = best; o[2] = sl0; o[3] = nSl - sl0; o[4] = hp0; o[5] = nHp - hp0;
+					nRec++;
+				}
+			}
+			oCnt_[0] = nRec; oCnt_[1] = nSl; oCnt_[2] = nHp;
+		});
+		u32 hc[4]; c.d2h(hc, oCnt.p, 16);
+		const u32 nRec = hc[0], nSl = hc[1];
+		t0 = t1;
+		if (!nRec) continue;
+		// SUBR records of this ref: one pseudo-region after the real ones carries the component (for the genotype columns)
+		const u32 comp = G.pathComp[refH]; const u32 nh = G.cpOff[comp + 1] - G.cpOff[comp];
+		const u32 pseudo = (u32)out.rov_fl.size();
+		out.rov_fl.push_back(NONE); out.rov_comp.push_back(comp);
+		const u32 grpBase = (u32)out.grp_hap.size(); const u64 gtBase = out.gt.size(); const size_t recBase = out.rec_rov.size();
+		Buf<u32> oRov(c, nRec), oRef(c, nRec), oL(c, nRec), oR2(c, nRec), oVt(c, nRec), oPos(c, nRec), oRS(c, nRec), oRL(c, nRec), oGrp(c, nRec);
+		Buf<u32> gHap(c, nRec), gStart(c, nRec), gLen(c, nRec), gCnt(c, nRec);
+		Buf<u64> gtOff(c, (size_t)nRec + 1);
+		Buf<u16> gt(c, (size_t)nRec * nh);
+		c.memset_ff(gt.p, (size_t)nRec * nh * 2);
+		u32 *oRov_ = oRov.p, *oRef_ = oRef.p, *oL_ = oL.p, *oR2_ = oR2.p, *oVt_ = oVt.p, *oPos_ = oPos.p, *oRS_ = oRS.p, *oRL_ = oRL.p, *oGrp_ = oGrp.p;
+		u32 *gHap_ = gHap.p, *gStart_ = gStart.p, *gLen_ = gLen.p, *gCnt_ = gCnt.p; u64 *gtOff_ = gtOff.p; u16 *gt_ = gt.p;
+		const u32 rb = G.h_stepOff[refH], rn = G.h_stepOff[refH + 1] - rb;
+		parallel_for<S_gt>(c, (size_t)nRec + 1, PV_LAMBDA(size_t q) {
+			gtOff_[q] = gtBase + (u64)q * nh;
+			if (q >= nRec) return;
+			const u32 *o = oRec_ + 6 * q;
+			u32 s = o[0], len = o[1];
+			// a merged length is measured on the ALT walk (slice_tree.hpp:378-391) and can run past the end of the ref or
+			// alt walk; the reference then reads beyond its arrays (undefined).  Clamp and count.
+			u32 ah = oSl_[2 * (size_t)o[2]], as0 = oSl_[2 * (size_t)o[2] + 1];
+			u32 an = g.stepOff[ah + 1] - g.stepOff[ah];
+			if (s >= rn || as0 >= an) { atomic_add(errs + 0, 1u); s = 0; as0 = 0; len = 1; }
+			if (s + len > rn || s + len < s) { len = rn - s; atomic_add(errs + 4, 1u); }
+			if (as0 + len > an || as0 + len < as0) { len = an - as0; atomic_add(errs + 4, 1u); }
+			oRov_[q] = pseudo; oRef_[q] = refH; oVt_[q] = (u32)VT_SUBR; oRS_[q] = s; oRL_[q] = len; oGrp_[q] = grpBase + (u32)q;
+			u32 a = g.steps[rb + s], b = g.steps[rb + s + len - 1];
+			if ((a & 1u) && (b & 1u)) { a &= ~1u; b &= ~1u; }   // both reverse: printed forward (vcf.cpp:163-168)
+			oL_[q] = a; oR2_[q] = b;
+			if (s + 1 < rn) oPos_[q] = g.loci[rb + s + 1]; else { oPos_[q] = 0; atomic_add(errs + 4, 1u); }   // comp_pos reads loci[start + 1]
+			gHap_[q] = ah; gStart_[q] = as0; gLen_[q] = len; gCnt_[q] = o[3];
+			u16 *row = gt_ + q * nh;
+			row[g.hapLocal[refH]] = 0;
+			for (u32 x = 0; x < o[5]; x++) { u32 h = oHap_[o[4] + x]; if (g.pathComp[h] == comp) row[g.hapLocal[h]] = 1; }
+		});
+		auto app = [&](hvec<u32> &dst, const Buf<u32> &src, u32 m) { size_t o = dst.size(); dst.resize(o + m); c.d2h_async(dst.data() + o, src.p, (size_t)m * 4); };
+		app(out.rec_rov, oRov, nRec); app(out.rec_ref, oRef, nRec); app(out.rec_cxtL, oL, nRec); app(out.rec_cxtR, oR2, nRec); app(out.rec_vt, oVt, nRec); app(out.rec_pos, oPos, nRec);
+		app(out.rec_refStart, oRS, nRec); app(out.rec_refLen, oRL, nRec);
+		app(out.grp_hap, gHap, nRec); app(out.grp_start, gStart, nRec); app(out.grp_len, gLen, nRec); app(out.grp_count, gCnt, nRec);
+		out.rec_grpOff.resize(recBase + nRec + 1); c.d2h_async(out.rec_grpOff.data() + recBase, oGrp.p, (size_t)nRec * 4);
+		out.rec_gtOff.resize(recBase + nRec + 1); c.d2h_async(out.rec_gtOff.data() + recBase, gtOff.p, ((size_t)nRec + 1) * 8);
+		out.gt.resize(gtBase + (size_t)nRec * nh); c.d2h_async(out.gt.data() + gtBase, gt.p, (size_t)nRec * nh * 2);
+		c.sync();
+		out.rec_grpOff[recBase + nRec] = grpBase + nRec;
+		(void)nSl;
+	}
+	tr.mark("S slice trees");
+}
+
 PV_KERNEL(T_rows, 12);
 PV_KERNEL(T_count, 24);
 PV_KERNEL(T_fill, 24);
@@ -605,7 +956,7 @@ PV_KERNEL(T_matrix, 32);
 // the ordinary overlay over those matrices with TANGLED = T (overlay.cpp:616-626).  Only the first ref's matrices are
 // used (untangle.cpp:245-246, Q11).
 inline void tangled_pass(Ctx &c, const DevGraph &G, const GraphView &g, const CallIn &in, const RovView &rv, const ChunkView &cv, u32 Rc,
-			 const u32 *tangledFlags, u32 *errs, Records &out, Trace &tr) {
+			 const u32 *tangledFlags, u32 *errs, Records &out, Trace &tr, PinStore &pins) {
 	Buf<u32> tList;
 	const u32 nT = compact_flags(c, tangledFlags, Rc, tList);
 	if (!nT) return;
@@ -755,7 +1106,7 @@ inline void tangled_pass(Ctx &c, const DevGraph &G, const GraphView &g, const Ca
 	Buf<u16> imat(c, totCells ? totCells : 1);
 	Buf<u32> ilapStart(c, totRows ? totRows : 1), ilapLen(c, totRows ? totRows : 1);
 	c.memset0(imat.p, totCells * 2); ilapStart.fill_ff(); ilapLen.zero();
-	const RovView irv{rv.rovOff, rv.rovVerts, rv.rovComp, iRowPre.p, iCellPre.p, rv.hkey, rv.hval, rv.hmask, nI, rv.uniformNh, 0, instRegion.p};
+	const RovView irv{rv.rovOff, rv.rovVerts, rv.rovComp, iRowPre.p, iCellPre.p, rv.hkey, rv.hval, rv.hmask, nI, rv.uniformNh, 0, instJ.p, instRegion.p};
 	const ChunkView icv{g, irv, imat.p, ilapStart.p, ilapLen.p, instTangled.p, hasData.p, errs};
 	parallel_for<T_matrix>(c, (size_t)totRows, PV_LAMBDA(size_t row) {
 		u32 n = irv.row2rov((u32)row); u32 i = (u32)row - irv.rowBase(n);
@@ -781,7 +1132,7 @@ inline void tangled_pass(Ctx &c, const DevGraph &G, const GraphView &g, const Ca
 		}
 	});
 	tr.mark("T untangle");
-	overlay_pass(c, G, g, in, irv, icv, nI, (u32)totRows, out, tr);
+	overlay_pass(c, G, g, in, irv, icv, nI, (u32)totRows, out, tr, pins);
 }
 
 
@@ -979,7 +1330,8 @@ inline void call_device(Ctx &c, const DevGraph &G, const CallIn &in, const CallO
 			chunkEnd.push_back(r1); r0 = r1;
 		}
 	}
-	Buf<u32> errs(c, 4);   // [0] hard errors, [1] inversion pin pairs, [2] depth overflow, [3] tangled regions
+	PinStore pins;
+	Buf<u32> errs(c, 8);   // [0] hard errors, [2] depth overflow, [3] tangled regions, [4] SUBR slices clamped to the walk
 	errs.zero();
 	u32 seenTangled = 0;
 
@@ -993,7 +1345,7 @@ inline void call_device(Ctx &c, const DevGraph &G, const CallIn &in, const CallO
 		Buf<u16> mat(c, cells ? cells : 1);
 		Buf<u32> lapStart(c, nRows ? nRows : 1), lapLen(c, nRows ? nRows : 1), hasData(c, Rc);
 		c.memset0(mat.p, cells * 2); lapStart.fill_ff(); hasData.zero();
-		const RovView rv{rovOff.p, rovVerts.p, rovComp.p, rowPre.p, cellPre.p, hkey.p, hval.p, hsize - 1, Rc, uniformNh, r0, nullptr};
+		const RovView rv{rovOff.p, rovVerts.p, rovComp.p, rowPre.p, cellPre.p, hkey.p, hval.p, hsize - 1, Rc, uniformNh, r0, nullptr, nullptr};
 		const ChunkView cv{g, rv, mat.p, lapStart.p, lapLen.p, rovTangled_ + r0, hasData.p, errs.p};
 		tr.mark("chunk setup");
 		// ---- C3: depth matrix (allele.hpp:804-862), one thread per (region, column)
@@ -1032,18 +1384,23 @@ inline void call_device(Ctx &c, const DevGraph &G, const CallIn &in, const CallO
 		});
 		tr.mark("C3 C4 matrix+laps");
 
-		overlay_pass(c, G, g, in, rv, cv, Rc, nRows, out, tr);
+		overlay_pass(c, G, g, in, rv, cv, Rc, nRows, out, tr, pins);
 		{
 			u32 he3 = errs.read(3);
-			if (he3 != seenTangled) { seenTangled = he3; tangled_pass(c, G, g, in, rv, cv, Rc, rovTangled_ + r0, errs.p, out, tr); }
+			if (he3 != seenTangled) { seenTangled = he3; tangled_pass(c, G, g, in, rv, cv, Rc, rovTangled_ + r0, errs.p, out, tr, pins); }
 		}
 		r0 = r1;
 	}
 	rovTangled.to_hvec(out.rov_tangled, R);
+	c.sync();
+	out.n_regions = R;
+	out.n_pin_pairs = pins.total;
+	if (pins.total) sne_pass(c, G, g, in, pins, R, errs.p, out, tr);
+	out.rov_tangled.resize(out.rov_fl.size(), 0);
 	c.d2h(hc, cnt.p, 32);
 	out.n_sort_failed = hc[1]; out.n_too_small = hc[2];
-	u32 he[4]; c.d2h(he, errs.p, 16);
-	out.n_hard_errors = he[0]; out.n_pin_pairs = he[1];
+	u32 he[8]; c.d2h(he, errs.p, 32);
+	out.n_hard_errors = he[0]; out.n_subr_clamped = he[4];
 	if (he[2]) throw std::runtime_error("call: a path visits one vertex more than 65534 times inside a region (u16 depth cell overflow)");
 	for (u32 t : out.rov_tangled) if (t) out.n_tangled++;
 	c.sync();

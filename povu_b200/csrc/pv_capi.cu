@@ -186,9 +186,9 @@ int pvgpu_session_call(pvgpu_session *s, const char *const *prefixes, size_t n) 
 	PV_TRY(s->x, { std::vector<std::string> p; for (size_t i = 0; i < n; i++) p.push_back(prefixes[i]); s->s.set_prefixes(p); s->s.call(); })
 }
 uint64_t pvgpu_session_record_count(const pvgpu_session *s) { return s->s.rec.n(); }
-void pvgpu_session_call_stats(const pvgpu_session *s, uint64_t o[10]) {
+void pvgpu_session_call_stats(const pvgpu_session *s, uint64_t o[12]) {
 	const pv::Records &c = s->s.rec;
-	o[0] = c.n_called; o[1] = s->s.rec.rov_fl.size(); o[2] = c.n_tangled; o[3] = c.n_pin_pairs; o[4] = c.n_sort_failed; o[5] = c.n_hard_errors; o[6] = c.n_chunks; o[7] = c.n_too_small; o[8] = c.max_J; o[9] = c.n_big_bfs;
+	o[0] = c.n_called; o[1] = c.n_regions; o[2] = c.n_tangled; o[3] = c.n_pin_pairs; o[4] = c.n_sort_failed; o[5] = c.n_hard_errors; o[6] = c.n_chunks; o[7] = c.n_too_small; o[8] = c.max_J; o[9] = c.n_big_bfs; o[10] = c.n_subr_clamped; o[11] = 0;
 }
 char *pvgpu_session_vcf_text(const pvgpu_session *s, size_t chunk, int with_date, const char *prefix, size_t *len) {
 	try {

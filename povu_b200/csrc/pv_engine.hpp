@@ -253,7 +253,7 @@ struct Session {
 	u32 tree_of_flubble(u32 fl) const { return (u32)(std::upper_bound(forest.treeOff.begin(), forest.treeOff.end(), fl) - forest.treeOff.begin()) - 1; }
 	std::vector<u64> regions_per_tree() const {
 		std::vector<u64> n(forest.comp_id.size(), 0);
-		for (u32 fl : rec.rov_fl) n[tree_of_flubble(fl)]++;
+		for (size_t r = 0; r < rec.n_regions; r++) n[tree_of_flubble(rec.rov_fl[r])]++;
 		return n;
 	}
 	void record_lines(std::string &text, std::vector<u64> &off, std::vector<u32> &keys) const {
@@ -264,7 +264,9 @@ struct Session {
 		for (size_t i : pvh::record_order(rec, ~(size_t)0)) {
 			pvh::record_text(g, gm, forest, rec, i, slots, text);
 			off.push_back(text.size());
-			u32 r = rec.rec_rov[i], t = tree_of_flubble(rec.rov_fl[r]);
+			u32 r = rec.rec_rov[i];
+			if (r >= rec.n_regions) { keys.push_back(pvh::NONE32); keys.push_back(0); keys.push_back(rec.rec_ref[i]); continue; }   // SUBR: final chunk
+			u32 t = tree_of_flubble(rec.rov_fl[r]);
 			keys.push_back(forest.comp_id[t]); keys.push_back((u32)(r - first[t])); keys.push_back(rec.rec_ref[i]);
 		}
 	}

@@ -481,7 +481,10 @@ inline std::vector<size_t> record_order(const Records &R, size_t chunk_size) {
 	for (size_t i = 0; i < ord.size(); i++) ord[i] = i;
 	if (chunk_size == 0) chunk_size = 1;
 	std::stable_sort(ord.begin(), ord.end(), [&](size_t a, size_t b) {
-		size_t ca = R.rec_rov[a] / chunk_size, cb = R.rec_rov[b] / chunk_size;
+		// SUBR records hang off per-ref pseudo regions after the real ones: they are emitted with the final chunk,
+		// after that chunk's ordinary records of the same ref (genomics.cpp:137-150, vcf.cpp:275-312)
+		const size_t last = R.n_regions ? (size_t)R.n_regions - 1 : 0;
+		size_t ca = std::min<size_t>(R.rec_rov[a], last) / chunk_size, cb = std::min<size_t>(R.rec_rov[b], last) / chunk_size;
 		if (ca != cb) return ca < cb;
 		if (R.rec_ref[a] != R.rec_ref[b]) return R.rec_ref[a] < R.rec_ref[b];
 		return R.rec_rov[a] < R.rec_rov[b];

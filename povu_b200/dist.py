@@ -41,7 +41,13 @@ def gfa2vcf(pv, gfa_path, prefixes, chunk_size=100, with_date=False, pvst_dir=No
     for comp in sorted(merged):          # forest files are visited in ascending component id
         base[comp] = tot
         tot += merged[comp]
-    payload = [((base[int(c)] + int(o)) // chunk_size, int(r), base[int(c)] + int(o), i, lines[i]) for i, (c, o, r) in enumerate(keys.tolist())]
+    last_chunk = max(tot - 1, 0) // chunk_size
+    payload = []
+    for i, (c, o, r) in enumerate(keys.tolist()):
+        if c == 0xFFFFFFFF:      # SUBR records: emitted with the final chunk, after its ordinary records of that ref
+            payload.append((last_chunk, int(r), tot, i, lines[i]))
+        else:
+            payload.append(((base[int(c)] + int(o)) // chunk_size, int(r), base[int(c)] + int(o), i, lines[i]))
     gathered = [None] * world if rank == 0 else None
     dist.gather_object((payload, st), gathered, dst=0)
     if rank != 0:

@@ -429,3 +429,18 @@ def repeat_loops(seed, n_units=6, n_paths=6, max_laps=4, first_id=1):
             st.append(nxt)
         paths.append((f"S{p // 2 + 1:03d}#{p % 2 + 1}#chr1", np.array(st, dtype=np.uint32), np.zeros(len(st), dtype=np.uint8)))
     return make_graph(np.arange(first_id, first_id + len(seqs), dtype=np.uint32), seqs, links, paths)
+
+
+def reverse_paths(g, which):
+    """The same graph with the paths in `which` walked backwards (steps reversed, strands flipped): a path on the
+    reverse strand needs no extra links (`L a + b +` is also `L b - a -`).  Regions such a path traverses with the
+    reference's alleles become whole-region inversions -> SNE pin pairs -> SUBR records."""
+    paths = []
+    for i, (name, st, sr) in enumerate(g["paths"]):
+        if i in which:
+            paths.append((name, np.ascontiguousarray(st[::-1]), np.ascontiguousarray(1 - sr[::-1]).astype(np.uint8)))
+        else:
+            paths.append((name, st, sr))
+    out = dict(g)
+    out["paths"] = paths
+    return out

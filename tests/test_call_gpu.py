@@ -35,3 +35,7 @@ def test_gpu_rejects_invalid_gfa(gpu, name):
 
 def test_gpu_call_tangled_vs_reference(gpu, tmp_path):
     cc.run_tangled_vs_reference(gpu, str(tmp_path), n_seeds=32)
+
+
+def test_gpu_call_inversions_vs_reference(gpu, tmp_path):
+    cc.run_inversions_vs_reference(gpu, str(tmp_path), n_seeds=60)
