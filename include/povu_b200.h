@@ -44,6 +44,11 @@ size_t pvgpu_profile_json(pvgpu_ctx *ctx, char *buf, size_t cap);
 /* 1 = sm_100a CUDA build, 2 = host debug rehearsal (tests only; never shipped) */
 int pvgpu_build_kind(void);
 
+/* test hook (tests/test_prims_gpu.py): runs the device primitives (stable pair sort on `bits` key bits, the scans,
+ * range-minimum / previous-smaller queries) on n seeded elements and counts disagreements with the host's std::
+ * algorithms.  Not part of the reference-facing surface. */
+int pvgpu_selftest_prims(pvgpu_ctx *ctx, uint64_t n, uint64_t seed, int bits, uint64_t *mismatches);
+
 /* decompose with HOST inputs (pinned or pageable): copies ep1/ep2 to the device on the context's
  * stream, runs the pipeline, copies the flubble table back.  flags bit0: also return the class stack. */
 int pvgpu_decompose(pvgpu_ctx *ctx, uint32_t n_vertices, uint64_t n_edges, const uint32_t *ep1, const uint32_t *ep2,

@@ -44,6 +44,8 @@ def load_library(lib_path=None):
     lib.pvgpu_set_profiling.argtypes = [vp, C.c_int]
     lib.pvgpu_profile_json.argtypes = [vp, C.c_char_p, C.c_size_t]
     lib.pvgpu_profile_json.restype = C.c_size_t
+    lib.pvgpu_selftest_prims.argtypes = [vp, u64, u64, C.c_int, C.POINTER(u64)]
+    lib.pvgpu_selftest_prims.restype = C.c_int
     lib.pvgpu_decompose.argtypes = [vp, u32, u64, vp, vp, u32, C.POINTER(vp)]
     lib.pvgpu_decompose.restype = C.c_int
     lib.pvgpu_decompose_dev.argtypes = [vp, u32, u64, vp, vp, u32, C.POINTER(vp)]
@@ -196,6 +198,13 @@ class Povu:
     @property
     def peak_bytes(self):
         return int(self.lib.pvgpu_peak_device_bytes(self.h))
+
+    def selftest_prims(self, n, seed=1, bits=32):
+        """Device primitives (pair sort, scans, RMQ) against the host's std:: algorithms; returns the mismatch count."""
+        bad = C.c_uint64(0)
+        if self.lib.pvgpu_selftest_prims(self.h, int(n), int(seed), int(bits), C.byref(bad)) != 0:
+            raise RuntimeError("povu_b200: " + self.lib.pvgpu_last_error(self.h).decode())
+        return int(bad.value)
 
     def set_profiling(self, on):
         self.lib.pvgpu_set_profiling(self.h, 1 if on else 0)

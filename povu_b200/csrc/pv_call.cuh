@@ -143,7 +143,8 @@ inline void graph_build(Ctx &c, u32 V, u64 E, const u32 *ep1, const u32 *ep2, u3
 			atomic_add(cnt_ + a, 1u);
 			if (!dup) atomic_add(cnt_ + b, 1u);
 		});
-		radix_sort_pairs(c, key.p, idx.p, M, bits_for((u64)P + 1));
+		radix_sort_pairs(c, key, idx, M, bits_for((u64)P + 1));
+		idx_ = idx.p;
 		exclusive_scan(c, cnt.p, g.adjOff.p, (size_t)P + 2, OpAddU32(), 0u);
 		u32 *adjNbr_ = g.adjNbr.p;
 		parallel_for<C_adj_fill>(c, M, PV_LAMBDA(size_t s) { adjNbr_[s] = nbr_[idx_[s]]; });
@@ -174,7 +175,8 @@ inline void graph_build(Ctx &c, u32 V, u64 E, const u32 *ep1, const u32 *ep2, u3
 		cnt.zero();
 		u32 *key_ = key.p, *cnt_ = cnt.p, *vsStep_ = g.vsStep.p, *vsHap_ = g.vsHap.p;
 		parallel_for<C_vs_key>(c, S, PV_LAMBDA(size_t s) { u32 v = steps_[s] >> 1; key_[s] = v; vsStep_[s] = (u32)s; atomic_add(cnt_ + v, 1u); });
-		radix_sort_pairs(c, key.p, g.vsStep.p, S, bits_for(V));
+		radix_sort_pairs(c, key, g.vsStep, S, bits_for(V));
+		vsStep_ = g.vsStep.p;
 		exclusive_scan(c, cnt.p, g.vsOff.p, (size_t)V + 1, OpAddU32(), 0u);
 		parallel_for<C_vs_hap>(c, S, PV_LAMBDA(size_t i) { vsHap_[i] = ub_u32(stepOff_, 0, H + 1, vsStep_[i]) - 1; });
 	}
@@ -759,7 +761,7 @@ inline void sne_pass(Ctx &c, const DevGraph &G, const GraphView &g, const CallIn
 	for (int w = 0; w < 4; w++) {
 		const u32 *src = words[w];
 		parallel_for<S_word>(c, nP, PV_LAMBDA(size_t i) { wk_[i] = src[perm_[i]]; });
-		radix_sort_pairs(c, wk.p, perm.p, nP, 32);
+		radix_sort_pairs_inplace(c, wk.p, perm.p, nP, 32);
 	}
 	// work items: pin pair o seen from ref ordinal kk (a pair between two ref paths belongs to both trees, sne.hpp:128-147)
 	const u32 *refs_ = nullptr;
@@ -786,9 +788,9 @@ inline void sne_pass(Ctx &c, const DevGraph &G, const GraphView &g, const CallIn
 	});
 	// order (ref ordinal, alt path, insertion order): stable sorts by alt path, then by ref ordinal
 	parallel_for<S_word>(c, nItems, PV_LAMBDA(size_t t) { iw_[t] = iAlt_[iperm_[t]]; });
-	radix_sort_pairs(c, iw.p, iperm.p, nItems, bits_for(g.H));
+	radix_sort_pairs_inplace(c, iw.p, iperm.p, nItems, bits_for(g.H));
 	parallel_for<S_word>(c, nItems, PV_LAMBDA(size_t t) { iw_[t] = iK_[iperm_[t]]; });
-	radix_sort_pairs(c, iw.p, iperm.p, nItems, bits_for(nRefs));
+	radix_sort_pairs_inplace(c, iw.p, iperm.p, nItems, bits_for(nRefs));
 	// chain limits (sne.cpp:92-122) + extension of every link (sne.cpp:124-213)
 	Buf<u32> eOk(c, nItems), eRefStart(c, nItems), eAltStart(c, nItems), eLen(c, nItems), eK(c, nItems), eAlt(c, nItems);
 	u32 *eOk_ = eOk.p, *eRefStart_ = eRefStart.p, *eAltStart_ = eAltStart.p, *eLen_ = eLen.p, *eK_ = eK.p, *eAlt_ = eAlt.p;

@@ -7,6 +7,12 @@ struct pvgpu_ctx { pv::Ctx c; std::string err; };
 struct pvgpu_flubbles { pv::DecompOut o; };
 template <class T, class V> static void cp(T *dst, const V &src) { if (dst && !src.empty()) memcpy(dst, src.data(), src.size() * sizeof(T)); }
 
+#ifndef PV_EMU
+#define PV_SET_DEVICE(x) PV_CUDA_CHECK(cudaSetDevice((x)->c.device))
+#else
+#define PV_SET_DEVICE(x) (void)0
+#endif
+
 extern "C" {
 
 int pvgpu_build_kind(void) {
@@ -104,6 +110,105 @@ uint64_t pvgpu_flubbles_stack_size(const pvgpu_flubbles *f) { return f->o.stack_
 void pvgpu_flubbles_copy_stack(const pvgpu_flubbles *f, uint32_t *v, uint32_t *cls, uint32_t *fwd) { cp(v, f->o.stack_v); cp(cls, f->o.stack_class); cp(fwd, f->o.stack_fwd); }
 void pvgpu_flubbles_free(pvgpu_flubbles *f) { delete f; }
 
+/* ---------------------------------------------------------------- primitive self-test (tests/test_prims_gpu.py) */
+int pvgpu_selftest_prims(pvgpu_ctx *x, uint64_t n, uint64_t seed, int bits, uint64_t *mismatches) {
+	if (!x || !mismatches) return 1;
+	*mismatches = 0;
+	try {
+		PV_SET_DEVICE(x);
+		using namespace pv;
+		Ctx &c = x->c;
+		u64 bad = 0, seen = 0;
+		auto section = [&](const char *what) { if (bad != seen) fprintf(stderr, "[selftest n=%llu seed=%llu bits=%d] %s: %llu mismatches\n", (unsigned long long)n, (unsigned long long)seed, bits, what, (unsigned long long)(bad - seen)); seen = bad; };
+		std::vector<u32> hk(n), hv(n);
+		u32 mask = bits >= 32 ? 0xFFFFFFFFu : ((1u << bits) - 1u);
+		for (u64 i = 0; i < n; i++) { hk[i] = (u32)splitmix64(seed + i) & mask; hv[i] = (u32)i; }
+		if (seed & 1) for (u64 i = 0; i < n; i++) hk[i] = (u32)((i * 3) / 2) & mask;   // sorted-ish keys (path steps by vertex)
+		{	// stable sort of pairs
+			Buf<u32> k(c, n ? n : 1), v(c, n ? n : 1);
+			c.h2d(k.p, hk.data(), n * 4); c.h2d(v.p, hv.data(), n * 4);
+			radix_sort_pairs(c, k, v, n, bits);
+			std::vector<u32> gk = k.to_host(), gv = v.to_host();
+			std::vector<u32> idx(n); for (u64 i = 0; i < n; i++) idx[i] = (u32)i;
+			std::stable_sort(idx.begin(), idx.end(), [&](u32 a, u32 b) { return hk[a] < hk[b]; });
+			for (u64 i = 0; i < n; i++) if (gk[i] != hk[idx[i]] || gv[i] != idx[i]) bad++;
+			section("sort");
+			// pointer flavour
+			Buf<u32> k2(c, n ? n : 1), v2(c, n ? n : 1);
+			c.h2d(k2.p, hk.data(), n * 4); c.h2d(v2.p, hv.data(), n * 4);
+			radix_sort_pairs_inplace(c, k2.p, v2.p, n, bits);
+			gk = k2.to_host(); gv = v2.to_host();
+			for (u64 i = 0; i < n; i++) if (gk[i] != hk[idx[i]] || gv[i] != idx[i]) bad++;
+			section("sort (pointer flavour)");
+		}
+		{	// scans: u32 add (exclusive, in place), u64 add, i32 inclusive, u128 xor, max-plus composition (non-commutative)
+			Buf<u32> a(c, n + 1);
+			std::vector<u32> h(n + 1); for (u64 i = 0; i <= n; i++) h[i] = (u32)(splitmix64(seed ^ i) & 1023u);
+			c.h2d(a.p, h.data(), (n + 1) * 4);
+			exclusive_scan(c, a.p, a.p, n + 1, OpAddU32(), 0u);
+			std::vector<u32> g = a.to_host(); u32 run = 0;
+			for (u64 i = 0; i <= n; i++) { if (g[i] != run) bad++; run += h[i]; }
+			section("scan u32 exclusive in place");
+			// misaligned views (scalar path)
+			if (n > 8) {
+				c.h2d(a.p, h.data(), (n + 1) * 4);
+				Buf<u32> o(c, n + 1);
+				inclusive_scan(c, a.p + 1, o.p + 3, n - 4, OpAddU32(), 0u);
+				g = o.to_host(); run = 0;
+				for (u64 i = 0; i + 4 < n; i++) { run += h[i + 1]; if (g[i + 3] != run) bad++; }
+			}
+			section("scan u32 inclusive misaligned");
+			Buf<u64> b(c, n + 1), bo(c, n + 1);
+			std::vector<u64> hb(n + 1); for (u64 i = 0; i <= n; i++) hb[i] = splitmix64(seed + 7 * i) >> 20;
+			c.h2d(b.p, hb.data(), (n + 1) * 8);
+			exclusive_scan(c, b.p, bo.p, n + 1, OpAddU64(), (u64)0);
+			std::vector<u64> gb = bo.to_host(); u64 r64 = 0;
+			for (u64 i = 0; i <= n; i++) { if (gb[i] != r64) bad++; r64 += hb[i]; }
+			section("scan u64");
+			Buf<u128> xk(c, n + 1), xo(c, n + 1);
+			std::vector<u128> hx(n + 1); for (u64 i = 0; i <= n; i++) hx[i] = u128{splitmix64(seed + 2 * i), splitmix64(seed + 2 * i + 1)};
+			c.h2d(xk.p, hx.data(), (n + 1) * 16);
+			exclusive_scan(c, (const u128 *)xk.p, xo.p, n + 1, OpXor128(), u128{0, 0});
+			std::vector<u128> gx = xo.to_host(); u128 rx{0, 0};
+			for (u64 i = 0; i <= n; i++) { if (gx[i].lo != rx.lo || gx[i].hi != rx.hi) bad++; rx.lo ^= hx[i].lo; rx.hi ^= hx[i].hi; }
+			section("scan u128 xor");
+			Buf<MP> m(c, n ? n : 1), mo(c, n ? n : 1);
+			std::vector<MP> hm(n);
+			for (u64 i = 0; i < n; i++) { u64 z = splitmix64(seed + 11 * i); i32 o = (i32)(z & 1), u = (i32)((z >> 1) & 1); hm[i] = MP{(z >> 2) % 97 == 0 ? -(1 << 29) : o - u, o}; }
+			c.h2d(m.p, hm.data(), n * sizeof(MP));
+			inclusive_scan(c, m.p, mo.p, n, OpMP(), MP{0, -(1 << 29)});
+			std::vector<MP> gm = mo.to_host(); MP rm{0, -(1 << 29)}; OpMP op;
+			for (u64 i = 0; i < n; i++) { rm = op(rm, hm[i]); if ((gm[i].a > gm[i].b ? gm[i].a : gm[i].b) != (rm.a > rm.b ? rm.a : rm.b)) bad++; }   // the function applied to 0 (the clamp at -2^29 makes `a` grouping-dependent far below any b)
+			section("scan max-plus");
+		}
+		if (n >= 2) {	// range minimum + previous smaller
+			Buf<u32> a(c, n);
+			std::vector<u32> h(n); for (u64 i = 0; i < n; i++) h[i] = (u32)(splitmix64(seed * 3 + i) % 1000003u);
+			c.h2d(a.p, h.data(), n * 4);
+			Rmq r; rmq_build(c, r, a.p, (u32)n);
+			const u32 Q = 4096;
+			Buf<u32> ql(c, Q), qr(c, Q), out(c, Q), out2(c, Q);
+			std::vector<u32> hl(Q), hr(Q);
+			for (u32 q = 0; q < Q; q++) { u64 z = splitmix64(seed + 99 + q); u32 l = (u32)(z % n), len = (u32)((z >> 32) % ((q & 1) ? 64 : n)); u32 rr = l + len < n ? l + len : (u32)n - 1; hl[q] = l; hr[q] = rr; }
+			c.h2d(ql.p, hl.data(), Q * 4); c.h2d(qr.p, hr.data(), Q * 4);
+			RmqView rv = r.view(); const u32 *ql_ = ql.p, *qr_ = qr.p; u32 *o_ = out.p, *o2_ = out2.p; const u32 *a_ = a.p;
+			parallel_for<K_rmq_blocks>(c, Q, PV_LAMBDA(size_t q) { o_[q] = rv.query(ql_[q], qr_[q]); o2_[q] = rv.prev_smaller(qr_[q], a_[ql_[q]]); });
+			std::vector<u32> g = out.to_host(), g2 = out2.to_host();
+			for (u32 q = 0; q < Q; q++) {
+				u32 mn = 0xFFFFFFFFu; for (u32 i = hl[q]; i <= hr[q]; i++) mn = h[i] < mn ? h[i] : mn;
+				if (g[q] != mn) bad++;
+				section("rmq query");
+				u32 ps = NONE; for (u32 i = hr[q] + 1; i-- > 0;) if (h[i] < h[hl[q]]) { ps = i; break; }
+				if (g2[q] != ps) { bad++; if (bad - seen == 1) fprintf(stderr, "  prev_smaller(r=%u, bound=a[%u]=%u): got %u want %u\n", hr[q], hl[q], h[hl[q]], g2[q], ps); }
+				section("rmq prev_smaller");
+			}
+		}
+		c.sync();
+		*mismatches = bad;
+		return 0;
+	} catch (std::exception &e) { x->err = e.what(); return 1; }
+}
+
 /* ---------------------------------------------------------------- sessions */
 struct pvgpu_session { pvgpu_ctx *x; pve::Session s; explicit pvgpu_session(pvgpu_ctx *x_) : x(x_), s(x_->c) {} };
 static char *dup_text(const std::string &t, size_t *len) {
@@ -113,11 +218,6 @@ static char *dup_text(const std::string &t, size_t *len) {
 	if (len) *len = t.size();
 	return p;
 }
-#ifndef PV_EMU
-#define PV_SET_DEVICE(x) PV_CUDA_CHECK(cudaSetDevice((x)->c.device))
-#else
-#define PV_SET_DEVICE(x) (void)0
-#endif
 #define PV_TRY(x, body) try { PV_SET_DEVICE(x); body; return 0; } catch (std::exception &e) { (x)->err = e.what(); return 1; }
 
 int pvgpu_session_open(pvgpu_ctx *x, const char *gfa, int labels, int refs, pvgpu_session **out) {

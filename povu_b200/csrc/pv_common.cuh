@@ -81,6 +81,16 @@ struct Ctx {
 	void prof_end();
 	void prof_collect();
 	u64 bytes_alloc = 0, bytes_peak = 0;
+	// persistent scratch of the single-pass (decoupled look-back) scan and the onesweep radix sort.  Status words carry
+	// an epoch that grows with every use, so the scratch is never cleared between launches; only these two primitives
+	// ever write it (memory recycled from the pool could alias a live epoch).
+	u32 *lb_flags = nullptr; char *lb_vals = nullptr; size_t lb_cap = 0;     // scan: per tile flag + (aggregate, inclusive) values
+	u64 *rs_status = nullptr; size_t rs_cap = 0;                             // sort: per (tile, digit) status
+	u32 *lb_ticket = nullptr;                                                // [0] scan tile ticket, [1] sort tile ticket (self-resetting)
+	u32 lb_epoch = 0;
+	u32 next_epoch();
+	void lb_reserve(size_t tiles);
+	void rs_reserve(size_t words);
 
 	void init(int dev, void *ext_stream);
 	void destroy();
@@ -114,8 +124,46 @@ inline void Ctx::init(int dev, void *ext_stream) {
 	emu_order = o ? atoi(o) : 0;
 #endif
 }
+inline u32 Ctx::next_epoch() {
+	if (++lb_epoch >= (1u << 30)) {   // wrap: clear the scratch once, start over
+		lb_epoch = 1;
+		if (lb_flags) memset0(lb_flags, lb_cap * 4);
+		if (rs_status) memset0(rs_status, rs_cap * 8);
+	}
+	return lb_epoch;
+}
+inline void Ctx::lb_reserve(size_t tiles) {
+#ifndef PV_EMU
+	if (!lb_ticket) { PV_CUDA_CHECK(cudaMalloc((void **)&lb_ticket, 16)); PV_CUDA_CHECK(cudaMemsetAsync(lb_ticket, 0, 16, stream)); }
+	if (tiles <= lb_cap) return;
+	sync();
+	if (lb_flags) { cudaFree(lb_flags); cudaFree(lb_vals); }
+	lb_cap = tiles * 2 > 4096 ? tiles * 2 : 4096;
+	PV_CUDA_CHECK(cudaMalloc((void **)&lb_flags, lb_cap * 4));
+	PV_CUDA_CHECK(cudaMalloc((void **)&lb_vals, lb_cap * 32));
+	PV_CUDA_CHECK(cudaMemsetAsync(lb_flags, 0, lb_cap * 4, stream));
+#else
+	(void)tiles;
+#endif
+}
+inline void Ctx::rs_reserve(size_t words) {
+#ifndef PV_EMU
+	if (!lb_ticket) { PV_CUDA_CHECK(cudaMalloc((void **)&lb_ticket, 16)); PV_CUDA_CHECK(cudaMemsetAsync(lb_ticket, 0, 16, stream)); }
+	if (words <= rs_cap) return;
+	sync();
+	if (rs_status) cudaFree(rs_status);
+	rs_cap = words > (1u << 16) ? words : (1u << 16);
+	PV_CUDA_CHECK(cudaMalloc((void **)&rs_status, rs_cap * 8));
+	PV_CUDA_CHECK(cudaMemsetAsync(rs_status, 0, rs_cap * 8, stream));
+#else
+	(void)words;
+#endif
+}
 inline void Ctx::destroy() {
 #ifndef PV_EMU
+	if (lb_flags) { cudaFree(lb_flags); cudaFree(lb_vals); lb_flags = nullptr; lb_vals = nullptr; lb_cap = 0; }
+	if (rs_status) { cudaFree(rs_status); rs_status = nullptr; rs_cap = 0; }
+	if (lb_ticket) { cudaFree(lb_ticket); lb_ticket = nullptr; }
 	if (own_stream && stream) cudaStreamDestroy(stream);
 	stream = nullptr;
 #endif

@@ -139,7 +139,8 @@ inline void decompose_device(Ctx &c, u32 V, u64 E, const u32 *ep1, const u32 *ep
 			ekey_[e] = a < b ? a : b; eord_[e] = (u32)e;
 			atomic_add(origDeg_ + a, 1u); atomic_add(origDeg_ + b, 1u);
 		});
-		radix_sort_pairs(c, ekey.p, eord.p, E, bits_for(P));   // stable: (min port, file order) = renumbered edge idx
+		radix_sort_pairs(c, ekey, eord, E, bits_for(P));   // stable: (min port, file order) = renumbered edge idx
+		eord_ = eord.p;
 		Buf<u32> entPort(c, M ? M : 1), entIdx(c, M ? M : 1), entNbr(c, M ? M : 1);
 		u32 *entPort_ = entPort.p, *entIdx_ = entIdx.p, *entNbr_ = entNbr.p;
 		parallel_for<K_entries>(c, E, PV_LAMBDA(size_t k) {
@@ -148,7 +149,8 @@ inline void decompose_device(Ctx &c, u32 V, u64 E, const u32 *ep1, const u32 *ep
 			entPort_[2 * k] = a; entNbr_[2 * k] = b; entIdx_[2 * k] = (u32)(2 * k);
 			entPort_[2 * k + 1] = b; entNbr_[2 * k + 1] = a; entIdx_[2 * k + 1] = (u32)(2 * k + 1);
 		});
-		radix_sort_pairs(c, entPort.p, entIdx.p, M, bits_for(P));
+		radix_sort_pairs(c, entPort, entIdx, M, bits_for(P));
+		entPort_ = entPort.p; entIdx_ = entIdx.p;
 		Buf<u32> slotOf(c, M ? M : 1), cnt(c, P + 1);
 		cnt.zero();
 		u32 *slotOf_ = slotOf.p, *cnt_ = cnt.p, *adjNbr_ = adjNbr.p, *adjOwner_ = adjOwner.p, *rev_ = rev.p;
@@ -520,7 +522,8 @@ inline void decompose_device(Ctx &c, u32 V, u64 E, const u32 *ep1, const u32 *ep
 			u64 h = w < 2 ? kk.lo : kk.hi;
 			wkey_[i] = (u32)(h >> ((w & 1) * 32));
 		});
-		radix_sort_pairs(c, wkey.p, ord.p, nS, 32);
+		radix_sort_pairs(c, wkey, ord, nS, 32);
+		wkey_ = wkey.p; ord_ = ord.p;
 		if (w == 3) break;
 		c.memset0(flag.p, 4);
 		parallel_for<K_word>(c, nS, PV_LAMBDA(size_t i) {

@@ -24,87 +24,148 @@ static const int SCAN_THREADS = 256;
 static const int SCAN_ITEMS = 8;
 static const int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
 
-template <class T, class Op>
-__device__ __forceinline__ T block_exclusive_scan_256(T v, Op op, T identity, T *sm /*[256]*/, T *total) {
-	// Hillis-Steele over 256 thread totals in shared memory (order preserving -> valid for
-	// non-commutative operators such as function composition).
-	int t = threadIdx.x;
-	sm[t] = v;
-	__syncthreads();
-	T acc = v;
+// word-wise helpers for generic (POD, multiple-of-4-byte) scan element types
+template <class T> struct Words { static_assert(sizeof(T) % 4 == 0 && sizeof(T) <= 16, "scan element must be 4..16 bytes"); static const int N = sizeof(T) / 4; };
+template <class T> __device__ __forceinline__ T shfl_up_t(T v, int d) {
+	union { T t; u32 w[Words<T>::N]; } a, b; a.t = v;
 #pragma unroll
-	for (int d = 1; d < 256; d <<= 1) {
-		T other = identity;
-		bool has = t >= d;
-		if (has) other = sm[t - d];
-		__syncthreads();
-		if (has) acc = op(other, acc);
-		sm[t] = acc;
-		__syncthreads();
-	}
-	if (total) *total = sm[255];
-	T excl = t == 0 ? identity : sm[t - 1];
-	__syncthreads();
-	return excl;
+	for (int k = 0; k < Words<T>::N; k++) b.w[k] = __shfl_up_sync(0xFFFFFFFFu, a.w[k], d);
+	return b.t;
 }
-
-template <class T, class Op>
-__global__ void __launch_bounds__(SCAN_THREADS) scan_reduce_kernel(const T *in, T *block_sums, size_t n, Op op, T identity) {
-	__shared__ T sm[SCAN_THREADS];
-	size_t base = (size_t)blockIdx.x * SCAN_TILE + (size_t)threadIdx.x * SCAN_ITEMS;
-	T acc = identity;
+template <class T> __device__ __forceinline__ T shfl_down_t(T v, int d) {
+	union { T t; u32 w[Words<T>::N]; } a, b; a.t = v;
 #pragma unroll
-	for (int k = 0; k < SCAN_ITEMS; k++) {
-		size_t i = base + k;
-		if (i < n) acc = op(acc, in[i]);
-	}
-	T total;
-	block_exclusive_scan_256(acc, op, identity, sm, &total);
-	if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
+	for (int k = 0; k < Words<T>::N; k++) b.w[k] = __shfl_down_sync(0xFFFFFFFFu, a.w[k], d);
+	return b.t;
 }
+template <class T> __device__ __forceinline__ T shfl_t(T v, int src) {
+	union { T t; u32 w[Words<T>::N]; } a, b; a.t = v;
+#pragma unroll
+	for (int k = 0; k < Words<T>::N; k++) b.w[k] = __shfl_sync(0xFFFFFFFFu, a.w[k], src);
+	return b.t;
+}
+template <class T> __device__ __forceinline__ T ld_cg_t(const T *p) {   // L2 load (the value was published by another CTA)
+	union { T t; u32 w[Words<T>::N]; } a;
+#pragma unroll
+	for (int k = 0; k < Words<T>::N; k++) a.w[k] = __ldcg((const u32 *)p + k);
+	return a.t;
+}
+__device__ __forceinline__ void st_flag(u32 *p, u32 v) { *(volatile u32 *)p = v; }
 
-template <class T, class Op, bool INCLUSIVE>
-__global__ void __launch_bounds__(SCAN_THREADS) scan_apply_kernel(const T *in, T *out, const T *block_offsets, size_t n, Op op, T identity) {
-	__shared__ T sm[SCAN_THREADS];
-	size_t base = (size_t)blockIdx.x * SCAN_TILE + (size_t)threadIdx.x * SCAN_ITEMS;
-	T vals[SCAN_ITEMS];
-	T acc = identity;
+// Single-pass scan with decoupled look-back: one launch, every element read once and written once.
+// Tiles are handed out by an atomic ticket (a tile's predecessors have always started, so the look-back cannot
+// dead-lock); a tile publishes its aggregate, warp 0 walks back 32 predecessors at a time until it meets an
+// inclusive prefix, then publishes its own inclusive prefix.  Order of combination is preserved throughout, so
+// non-commutative operators (function composition) are fine.  Flags carry the launch epoch: no clearing between launches.
+template <class T, class Op, bool INCLUSIVE, bool VEC>
+__global__ void __launch_bounds__(SCAN_THREADS) scan_lb_kernel(const T *in, T *out, size_t n, Op op, T identity, u32 *flags, T *agg, T *incl,
+								 u32 *ticket, u32 epoch, u32 ntiles) {
+	__shared__ T warpTot[SCAN_THREADS / 32];
+	__shared__ T s_prefix;
+	__shared__ u32 s_tile;
+	const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+	if (t == 0) { u32 k = atomicAdd(ticket, 1u); if (k == ntiles - 1) atomicExch(ticket, 0u); s_tile = k; }
+	__syncthreads();
+	const u32 tile = s_tile;
+	const size_t base = (size_t)tile * SCAN_TILE + (size_t)t * SCAN_ITEMS;
+	const bool full = (size_t)(tile + 1) * SCAN_TILE <= n;
+	union Items { T v[SCAN_ITEMS]; uint4 q[sizeof(T) * SCAN_ITEMS / 16]; __device__ Items() {} } it;
+	if (full) {
+		if (VEC) {
+			const uint4 *src = reinterpret_cast<const uint4 *>(in + base);
 #pragma unroll
-	for (int k = 0; k < SCAN_ITEMS; k++) {
-		size_t i = base + k;
-		vals[k] = i < n ? in[i] : identity;
-		acc = op(acc, vals[k]);
+			for (int k = 0; k < (int)(sizeof(T) * SCAN_ITEMS / 16); k++) it.q[k] = src[k];
+		} else {
+#pragma unroll
+			for (int k = 0; k < SCAN_ITEMS; k++) it.v[k] = in[base + k];
+		}
+	} else {
+#pragma unroll
+		for (int k = 0; k < SCAN_ITEMS; k++) it.v[k] = base + k < n ? in[base + k] : identity;
 	}
-	T excl = block_exclusive_scan_256(acc, op, identity, sm, (T *)nullptr);
-	T run = block_offsets ? op(block_offsets[blockIdx.x], excl) : excl;
+	T acc = it.v[0];
+#pragma unroll
+	for (int k = 1; k < SCAN_ITEMS; k++) acc = op(acc, it.v[k]);
+	T inc = acc;   // inclusive scan of the thread totals inside the warp
+#pragma unroll
+	for (int d = 1; d < 32; d <<= 1) { T y = shfl_up_t(inc, d); if (lane >= d) inc = op(y, inc); }
+	if (lane == 31) warpTot[w] = inc;
+	__syncthreads();
+	if (w == 0) {
+		T tot = warpTot[0];
+#pragma unroll
+		for (int i = 1; i < SCAN_THREADS / 32; i++) tot = op(tot, warpTot[i]);
+		T prefix = identity;
+		if (tile == 0) {
+			if (lane == 0) { incl[0] = tot; __threadfence(); st_flag(flags, (epoch << 2) | 2u); }
+		} else {
+			if (lane == 0) { agg[tile] = tot; __threadfence(); st_flag(flags + tile, (epoch << 2) | 1u); }
+			T run = identity; bool have = false;
+			int cur = (int)tile - 1;
+			while (true) {
+				int idx = cur - lane;
+				u32 st = 2u; T v = identity;
+				if (idx >= 0) {
+					u32 f;
+					do { f = *(volatile u32 *)(flags + idx); } while ((f >> 2) != epoch);
+					st = f & 3u;
+					__threadfence();
+					v = ld_cg_t(st == 2u ? incl + idx : agg + idx);
+				}
+				u32 inclMask = __ballot_sync(0xFFFFFFFFu, st == 2u);
+				int lim = inclMask ? (__ffs((int)inclMask) - 1) : 31;   // nearest tile that already knows its inclusive prefix
+				if (lane > lim) v = identity;
+				// ordered product v[31] op ... op v[0] (higher lanes = earlier tiles)
+#pragma unroll
+				for (int d = 1; d < 32; d <<= 1) { T y = shfl_down_t(v, d); if (lane + d < 32) v = op(y, v); }
+				v = shfl_t(v, 0);
+				run = have ? op(v, run) : v; have = true;
+				if (inclMask) break;
+				cur -= 32;
+			}
+			prefix = run;
+			if (lane == 0) { incl[tile] = op(prefix, tot); __threadfence(); st_flag(flags + tile, (epoch << 2) | 2u); }
+		}
+		if (lane == 0) s_prefix = prefix;
+	}
+	__syncthreads();
+	T run = s_prefix;
+	for (int i = 0; i < w; i++) run = op(run, warpTot[i]);
+	T prevLane = shfl_up_t(inc, 1);
+	if (lane > 0) run = op(run, prevLane);
+	if (tile == 0 && w == 0 && lane == 0) run = identity;
 #pragma unroll
 	for (int k = 0; k < SCAN_ITEMS; k++) {
-		size_t i = base + k;
-		if (INCLUSIVE) { run = op(run, vals[k]); if (i < n) out[i] = run; }
-		else { if (i < n) out[i] = run; run = op(run, vals[k]); }
+		if (INCLUSIVE) { run = op(run, it.v[k]); it.v[k] = run; }
+		else { T x = it.v[k]; it.v[k] = run; run = op(run, x); }
+	}
+	if (full) {
+		if (VEC) {
+			uint4 *dst = reinterpret_cast<uint4 *>(out + base);
+#pragma unroll
+			for (int k = 0; k < (int)(sizeof(T) * SCAN_ITEMS / 16); k++) dst[k] = it.q[k];
+		} else {
+#pragma unroll
+			for (int k = 0; k < SCAN_ITEMS; k++) out[base + k] = it.v[k];
+		}
+	} else {
+#pragma unroll
+		for (int k = 0; k < SCAN_ITEMS; k++) if (base + k < n) out[base + k] = it.v[k];
 	}
 }
 
 template <class T, class Op, bool INCLUSIVE>
 inline void scan_impl(Ctx &c, const T *in, T *out, size_t n, Op op, T identity) {
 	if (n == 0) return;
-	size_t nblocks = (n + SCAN_TILE - 1) / SCAN_TILE;
-	if (nblocks == 1) {
-		c.prof_begin("scan_apply", n, n * 2 * sizeof(T));
-		scan_apply_kernel<T, Op, INCLUSIVE><<<1, SCAN_THREADS, 0, c.stream>>>(in, out, (const T *)nullptr, n, op, identity);
-		c.prof_end();
-		c.launches++;
-		PV_CUDA_CHECK(cudaGetLastError());
-		return;
-	}
-	Buf<T> sums(c, nblocks);
-	c.prof_begin("scan_reduce", n, n * sizeof(T));
-	scan_reduce_kernel<T, Op><<<(unsigned)nblocks, SCAN_THREADS, 0, c.stream>>>(in, sums.p, n, op, identity);
-	c.prof_end();
-	c.launches++;
-	scan_impl<T, Op, false>(c, sums.p, sums.p, nblocks, op, identity);
-	c.prof_begin("scan_apply", n, n * 2 * sizeof(T));
-	scan_apply_kernel<T, Op, INCLUSIVE><<<(unsigned)nblocks, SCAN_THREADS, 0, c.stream>>>(in, out, sums.p, n, op, identity);
+	size_t ntiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+	if (ntiles >= 0x7FFFFFFFull) throw std::runtime_error("scan: input too large");
+	c.lb_reserve(ntiles);
+	u32 epoch = c.next_epoch();
+	T *agg = (T *)c.lb_vals, *incl = (T *)(c.lb_vals + c.lb_cap * 16);
+	bool vec = (((uintptr_t)in | (uintptr_t)out) & 15u) == 0;
+	c.prof_begin("scan_lb", n, n * 2 * sizeof(T));
+	if (vec) scan_lb_kernel<T, Op, INCLUSIVE, true><<<(unsigned)ntiles, SCAN_THREADS, 0, c.stream>>>(in, out, n, op, identity, c.lb_flags, agg, incl, c.lb_ticket, epoch, (u32)ntiles);
+	else scan_lb_kernel<T, Op, INCLUSIVE, false><<<(unsigned)ntiles, SCAN_THREADS, 0, c.stream>>>(in, out, n, op, identity, c.lb_flags, agg, incl, c.lb_ticket, epoch, (u32)ntiles);
 	c.prof_end();
 	c.launches++;
 	PV_CUDA_CHECK(cudaGetLastError());
@@ -130,100 +191,213 @@ template <class T, class Op> inline void inclusive_scan(Ctx &c, const T *in, T *
 }
 
 // ---------------------------------------------------------------------------------------------
-// stable LSD radix sort of (u32 key, u32 value) pairs on key bits [0, bits)
-// Warp-private sub-tiles: every warp owns RS_ROUNDS*32 consecutive elements, ranks them with
-// __match_any_sync and keeps its 256 running digit offsets in shared memory, so no block barrier is
-// needed inside the scatter loop and stability is by construction.
+// stable LSD radix sort of (u32 key, u32 value) pairs on key bits [0, bits), 8 bits per pass, "onesweep" style:
+//   * ONE histogram kernel reads the keys once and counts the digits of every pass (thread-private run-length
+//     accumulation -> shared-memory atomics -> global atomics);
+//   * ONE kernel per pass: a CTA ranks its tile (warp-private __match_any_sync ranking, in index order, so the sort
+//     is stable by construction), publishes its digit counts, obtains its global offsets by decoupled look-back over
+//     the tiles before it (one thread per digit), stages the tile in digit order in shared memory and writes it out
+//     in coalesced runs.  Every pair is read once and written once per pass; nothing else touches HBM.
+// Tiles are handed out by an atomic ticket; status words carry the launch epoch (no clearing between launches).
 // ---------------------------------------------------------------------------------------------
 #ifndef PV_EMU
-static const int RS_WARPS = 8;
-static const int RS_MAX_ROUNDS = 64;        // a warp sub-tile holds 32 * rounds elements; rounds is chosen per sort so that
-                                            // small inputs still spread over every SM (latency-bound otherwise)
+static const int RS_THREADS = 256;
+static const int RS_WARPS = RS_THREADS / 32;
 
-__global__ void __launch_bounds__(RS_WARPS * 32) rs_hist_kernel(const u32 *keys, u32 *counts, size_t n, size_t nsub, int shift, int rounds) {
-	__shared__ u32 hist[RS_WARPS][256];
-	int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-	for (int d = lane; d < 256; d += 32) hist[w][d] = 0;
-	__syncwarp();
-	size_t sub = (size_t)blockIdx.x * RS_WARPS + w;
-	if (sub < nsub) {
-		size_t base = sub * (size_t)(32 * rounds);
-#pragma unroll 4
-		for (int r = 0; r < rounds; r++) {
-			size_t i = base + (size_t)r * 32 + lane;
-			bool valid = i < n;
-			u32 d = valid ? ((keys[i] >> shift) & 255u) : 256u + lane;   // invalid lanes get unique pseudo-digits
-			u32 peers = __match_any_sync(0xFFFFFFFFu, d);
-			if (valid && (peers & ((1u << lane) - 1u)) == 0) hist[w][d] += __popc(peers);
-			__syncwarp();
+__global__ void __launch_bounds__(RS_THREADS) rs_hist_all_kernel(const u32 *keys, size_t n, u32 *ghist, int passes, int vec) {
+	__shared__ u32 hist[4][256];
+	for (int i = threadIdx.x; i < 4 * 256; i += RS_THREADS) (&hist[0][0])[i] = 0;
+	__syncthreads();
+	const size_t chunk = 16;   // consecutive keys per thread per iteration: runs of equal digits collapse into one atomic
+	size_t nchunks = (n + chunk - 1) / chunk;
+	for (size_t cidx = (size_t)blockIdx.x * RS_THREADS + threadIdx.x; cidx < nchunks; cidx += (size_t)gridDim.x * RS_THREADS) {
+		size_t base = cidx * chunk;
+		u32 k[16]; int m = 16;
+		if (vec && base + 16 <= n) {
+			const uint4 *src = reinterpret_cast<const uint4 *>(keys + base);
+#pragma unroll
+			for (int j = 0; j < 4; j++) { uint4 q = src[j]; k[4 * j] = q.x; k[4 * j + 1] = q.y; k[4 * j + 2] = q.z; k[4 * j + 3] = q.w; }
+		} else {
+			m = (int)(n - base < 16 ? n - base : 16);
+#pragma unroll
+			for (int j = 0; j < 16; j++) k[j] = j < m ? keys[base + j] : 0u;
 		}
-		for (int d = lane; d < 256; d += 32) counts[(size_t)d * nsub + sub] = hist[w][d];
+		for (int p = 0; p < passes; p++) {
+			int sh = 8 * p;
+			u32 cur = (k[0] >> sh) & 255u, cnt = 1;
+#pragma unroll
+			for (int j = 1; j < 16; j++) {
+				if (j < m) {
+					u32 d = (k[j] >> sh) & 255u;
+					if (d == cur) cnt++;
+					else { atomicAdd(&hist[p][cur], cnt); cur = d; cnt = 1; }
+				}
+			}
+			atomicAdd(&hist[p][cur], cnt);
+		}
 	}
+	__syncthreads();
+	for (int i = threadIdx.x; i < passes * 256; i += RS_THREADS) { u32 v = (&hist[0][0])[i]; if (v) atomicAdd(ghist + i, v); }
 }
 
-__global__ void __launch_bounds__(RS_WARPS * 32) rs_scatter_kernel(const u32 *keys_in, const u32 *vals_in, u32 *keys_out, u32 *vals_out,
-								   const u32 *offsets, size_t n, size_t nsub, int shift, int rounds) {
-	__shared__ u32 off[RS_WARPS][256];
-	int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-	size_t sub = (size_t)blockIdx.x * RS_WARPS + w;
-	if (sub >= nsub) return;
-	for (int d = lane; d < 256; d += 32) off[w][d] = offsets[(size_t)d * nsub + sub];
-	__syncwarp();
-	size_t base = sub * (size_t)(32 * rounds);
-#pragma unroll 4
-	for (int r = 0; r < rounds; r++) {
-		size_t i = base + (size_t)r * 32 + lane;
-		bool valid = i < n;
-		u32 k = valid ? keys_in[i] : 0, v = valid ? vals_in[i] : 0;
-		u32 d = valid ? ((k >> shift) & 255u) : 256u + lane;
+__device__ __forceinline__ u32 block_excl_scan_256(u32 v, u32 *warpSum /*[8] shared*/) {
+	const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+	u32 inc = v;
+#pragma unroll
+	for (int d = 1; d < 32; d <<= 1) { u32 y = __shfl_up_sync(0xFFFFFFFFu, inc, d); if (lane >= d) inc += y; }
+	if (lane == 31) warpSum[w] = inc;
+	__syncthreads();
+	u32 base = 0;
+#pragma unroll
+	for (int i = 0; i < RS_WARPS; i++) if (i < w) base += warpSum[i];
+	__syncthreads();
+	return base + inc - v;
+}
+
+template <int ITEMS>
+__global__ void __launch_bounds__(RS_THREADS) rs_onesweep_kernel(const u32 *kin, const u32 *vin, u32 *kout, u32 *vout, size_t n, int shift,
+								   const u32 *ghist, u64 *status, u32 *ticket, u32 epoch, u32 ntiles) {
+	constexpr int TILE = RS_THREADS * ITEMS;
+	__shared__ u32 sKeys[TILE];
+	__shared__ u32 sVals[TILE];
+	__shared__ u32 warpCnt[RS_WARPS][256];
+	__shared__ u32 digStart[256];
+	__shared__ u32 gOff[256];
+	__shared__ u32 warpSum[RS_WARPS];
+	__shared__ u32 s_tile;
+	const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+	if (t == 0) { u32 k = atomicAdd(ticket, 1u); if (k == ntiles - 1) atomicExch(ticket, 0u); s_tile = k; }
+#pragma unroll
+	for (int i = 0; i < RS_WARPS; i++) warpCnt[i][t] = 0;
+	__syncthreads();
+	const u32 tile = s_tile;
+	const size_t tileBase = (size_t)tile * TILE;
+	const u32 tileCount = (u32)(n - tileBase < (size_t)TILE ? n - tileBase : (size_t)TILE);
+	const size_t wbase = tileBase + (size_t)w * (32 * ITEMS) + lane;
+	u32 key[ITEMS], val[ITEMS], pos[ITEMS];
+	const bool full = tileCount == (u32)TILE;
+	if (full) {
+#pragma unroll
+		for (int k = 0; k < ITEMS; k++) { key[k] = kin[wbase + (size_t)k * 32]; val[k] = vin[wbase + (size_t)k * 32]; }
+	} else {
+#pragma unroll
+		for (int k = 0; k < ITEMS; k++) { size_t i = wbase + (size_t)k * 32; bool ok = i < n; key[k] = ok ? kin[i] : 0u; val[k] = ok ? vin[i] : 0u; }
+	}
+	const u32 ltMask = (1u << lane) - 1u;
+#pragma unroll
+	for (int k = 0; k < ITEMS; k++) {
+		bool valid = full || (wbase + (size_t)k * 32 < n);
+		u32 d = valid ? ((key[k] >> shift) & 255u) : 256u + (u32)lane;   // invalid lanes get unique pseudo-digits
 		u32 peers = __match_any_sync(0xFFFFFFFFu, d);
-		u32 rank = __popc(peers & ((1u << lane) - 1u));
-		u32 o = valid ? off[w][d] : 0;
+		u32 r = __popc(peers & ltMask);
+		u32 c0 = valid ? warpCnt[w][d] : 0u;
 		__syncwarp();
-		if (valid && rank == 0) off[w][d] = o + __popc(peers);
+		if (valid && r == 0) warpCnt[w][d] = c0 + __popc(peers);
 		__syncwarp();
-		if (valid) { keys_out[o + rank] = k; vals_out[o + rank] = v; }
+		pos[k] = c0 + r;   // rank among the warp's elements with this digit
+	}
+	__syncthreads();
+	// thread t owns digit t: warp counts -> warp offsets, tile count
+	u32 cnt = 0;
+#pragma unroll
+	for (int i = 0; i < RS_WARPS; i++) { u32 x = warpCnt[i][t]; warpCnt[i][t] = cnt; cnt += x; }
+	u64 *myStatus = status + (size_t)tile * 256 + t;
+	*(volatile u64 *)myStatus = ((u64)epoch << 34) | ((u64)(tile == 0 ? 2u : 1u) << 32) | (u64)cnt;
+	u32 ds = block_excl_scan_256(cnt, warpSum);
+	u32 gbase = block_excl_scan_256(ghist[t], warpSum);
+	u32 excl = 0;
+	if (tile > 0) {
+		for (int i = (int)tile - 1;; i--) {
+			u64 sw;
+			const volatile u64 *sp = (const volatile u64 *)(status + (size_t)i * 256 + t);
+			do { sw = *sp; } while ((u32)(sw >> 34) != epoch);
+			excl += (u32)sw;
+			if (((sw >> 32) & 3u) == 2u) break;
+		}
+		*(volatile u64 *)myStatus = ((u64)epoch << 34) | ((u64)2u << 32) | (u64)(excl + cnt);
+	}
+	digStart[t] = ds;
+	gOff[t] = gbase + excl - ds;
+	__syncthreads();
+#pragma unroll
+	for (int k = 0; k < ITEMS; k++) {
+		bool valid = full || (wbase + (size_t)k * 32 < n);
+		if (valid) {
+			u32 d = (key[k] >> shift) & 255u;
+			u32 p = digStart[d] + warpCnt[w][d] + pos[k];
+			sKeys[p] = key[k]; sVals[p] = val[k];
+		}
+	}
+	__syncthreads();
+#pragma unroll
+	for (int k = 0; k < ITEMS; k++) {
+		u32 j = (u32)t + (u32)k * RS_THREADS;
+		if (j < tileCount) {
+			u32 kk = sKeys[j];
+			u32 dst = gOff[(kk >> shift) & 255u] + j;
+			kout[dst] = kk; vout[dst] = sVals[j];
+		}
 	}
 }
 #endif
 
-// Sorts in place (result ends up back in keys/vals); tmp buffers are allocated internally.
-inline void radix_sort_pairs(Ctx &c, u32 *keys, u32 *vals, size_t n, int bits) {
+// Sorts (keys, vals) by key bits [0, bits); on return keys/vals may have been SWAPPED with the internal double buffers
+// (the Buf objects always own the sorted data; raw pointers taken before the call are stale).
+inline void radix_sort_pairs(Ctx &c, Buf<u32> &keys, Buf<u32> &vals, size_t n, int bits) {
 	if (n <= 1 || bits <= 0) return;
 #ifndef PV_EMU
-	Buf<u32> k2(c, n), v2(c, n);
-	// about 32 warps per SM: rounds = n / (32 lanes * 32 warps * #SM), clamped to [4, 64]
-	int rounds = (int)(n / ((size_t)1024 * (size_t)c.sm_count));
-	rounds = rounds < 4 ? 4 : (rounds > RS_MAX_ROUNDS ? RS_MAX_ROUNDS : rounds);
-	const size_t sub_elems = (size_t)32 * rounds;
-	size_t nsub = (n + sub_elems - 1) / sub_elems;
-	Buf<u32> counts(c, 256 * nsub);
-	unsigned blocks = (unsigned)((nsub + RS_WARPS - 1) / RS_WARPS);
-	u32 *ki = keys, *vi = vals, *ko = k2.p, *vo = v2.p;
-	for (int shift = 0; shift < bits; shift += 8) {
+	if (n >= (1ull << 32)) throw std::runtime_error("radix sort: input too large");
+	if (bits > 32) bits = 32;
+	const int passes = (bits + 7) / 8;
+	Buf<u32> k2(c, keys.n), v2(c, vals.n);
+	Buf<u32> ghist(c, 4 * 256);
+	ghist.zero();
+	bool small = n < (size_t)c.sm_count * 4 * 4096;
+	const size_t tile = small ? RS_THREADS * 8 : RS_THREADS * 16;
+	size_t ntiles = (n + tile - 1) / tile;
+	c.rs_reserve(ntiles * 256);
+	{
+		size_t nchunks = (n + 15) / 16;
+		size_t blocks = (nchunks + RS_THREADS - 1) / RS_THREADS;
+		size_t cap = (size_t)c.sm_count * 8;
+		if (blocks > cap) blocks = cap;
 		c.prof_begin("rs_hist", n, n * 4);
-		rs_hist_kernel<<<blocks, RS_WARPS * 32, 0, c.stream>>>(ki, counts.p, n, nsub, shift, rounds);
+		rs_hist_all_kernel<<<(unsigned)blocks, RS_THREADS, 0, c.stream>>>(keys.p, n, ghist.p, passes, (((uintptr_t)keys.p) & 15u) == 0 ? 1 : 0);
 		c.prof_end();
 		c.launches++;
-		exclusive_scan(c, counts.p, counts.p, 256 * nsub, OpAddU32(), 0u);
-		c.prof_begin("rs_scatter", n, n * 16);
-		rs_scatter_kernel<<<blocks, RS_WARPS * 32, 0, c.stream>>>(ki, vi, ko, vo, counts.p, n, nsub, shift, rounds);
+	}
+	for (int p = 0; p < passes; p++) {
+		u32 epoch = c.next_epoch();
+		c.prof_begin("rs_onesweep", n, n * 16);
+		if (small) rs_onesweep_kernel<8><<<(unsigned)ntiles, RS_THREADS, 0, c.stream>>>(keys.p, vals.p, k2.p, v2.p, n, 8 * p, ghist.p + 256 * p, c.rs_status, c.lb_ticket + 1, epoch, (u32)ntiles);
+		else rs_onesweep_kernel<16><<<(unsigned)ntiles, RS_THREADS, 0, c.stream>>>(keys.p, vals.p, k2.p, v2.p, n, 8 * p, ghist.p + 256 * p, c.rs_status, c.lb_ticket + 1, epoch, (u32)ntiles);
 		c.prof_end();
 		c.launches++;
 		PV_CUDA_CHECK(cudaGetLastError());
-		std::swap(ki, ko); std::swap(vi, vo);
+		std::swap(keys, k2); std::swap(vals, v2);
 	}
-	if (ki != keys) { c.d2d(keys, ki, n * 4); c.d2d(vals, vi, n * 4); }
 #else
 	c.launches++;
 	std::vector<u32> idx(n);
 	std::iota(idx.begin(), idx.end(), 0u);
 	u32 mask = bits >= 32 ? 0xFFFFFFFFu : ((1u << bits) - 1u);
-	std::stable_sort(idx.begin(), idx.end(), [&](u32 a, u32 b) { return (keys[a] & mask) < (keys[b] & mask); });
-	std::vector<u32> k(n), v(n);
-	for (size_t i = 0; i < n; i++) { k[i] = keys[idx[i]]; v[i] = vals[idx[i]]; }
-	memcpy(keys, k.data(), n * 4); memcpy(vals, v.data(), n * 4);
+	u32 *kp = keys.p, *vp = vals.p;
+	std::stable_sort(idx.begin(), idx.end(), [&](u32 a, u32 b) { return (kp[a] & mask) < (kp[b] & mask); });
+	// like the device path with an odd number of passes: the result lives in fresh buffers, the old ones are poisoned
+	Buf<u32> k2(c, keys.n), v2(c, vals.n);
+	for (size_t i = 0; i < n; i++) { k2.p[i] = kp[idx[i]]; v2.p[i] = vp[idx[i]]; }
+	memset(kp, 0xCD, n * 4); memset(vp, 0xCD, n * 4);
+	std::swap(keys, k2); std::swap(vals, v2);
 #endif
+}
+
+// pointer flavour for cold call sites: sorts a copy and writes the result back to keys/vals
+inline void radix_sort_pairs_inplace(Ctx &c, u32 *keys, u32 *vals, size_t n, int bits) {
+	if (n <= 1 || bits <= 0) return;
+	Buf<u32> k(c, n), v(c, n);
+	c.d2d(k.p, keys, n * 4); c.d2d(v.p, vals, n * 4);
+	radix_sort_pairs(c, k, v, n, bits);
+	c.d2d(keys, k.p, n * 4); c.d2d(vals, v.p, n * 4);
 }
 
 inline int bits_for(u64 max_value) { int b = 1; while (b < 64 && (max_value >> b)) b++; return b; }
@@ -290,7 +464,7 @@ struct Rmq {
 };
 
 PV_KERNEL(K_rmq_blocks, 12);   // a in, pre + suf out (+ block min)
-PV_KERNEL(K_rmq_level, 12);
+PV_KERNEL(K_rmq_level, 24);   // one level in, up to five levels out
 
 inline void rmq_build(Ctx &c, Rmq &r, const u32 *a, u32 n) {
 	r.a = a; r.n = n; r.nb = (n + 31) / 32;
@@ -306,14 +480,20 @@ inline void rmq_build(Ctx &c, Rmq &r, const u32 *a, u32 n) {
 		m = NONE;
 		for (u32 i = e; i-- > s;) { u32 x = a[i]; m = x < m ? x : m; suf[i] = m; }
 	});
-	for (u32 k = 1; k < r.levels; k++) {
-		u32 half = 1u << (k - 1);
-		const u32 *prev = table + (size_t)(k - 1) * nb;
-		u32 *cur = table + (size_t)k * nb;
+	// five sparse-table levels per launch: level b+m at j = min over i < 2^m of level b at j + i * 2^b
+	for (u32 b = 0; b + 1 < r.levels; b += 5) {
+		const u32 top = b + 5 < r.levels - 1 ? b + 5 : r.levels - 1;   // highest level written by this launch
+		const u32 stride = 1u << b;
+		const u32 *src = table + (size_t)b * nb;
 		parallel_for<K_rmq_level>(c, nb, PV_LAMBDA(size_t j) {
-			u32 x = prev[j];
-			u32 y = j + half < nb ? prev[j + half] : NONE;
-			cur[j] = x < y ? x : y;
+			u32 m = NONE;
+			u32 lvl = b + 1;
+			for (u32 i = 0; i < 32u && lvl <= top; i++) {
+				size_t q = j + (size_t)i * stride;
+				u32 x = q < nb ? src[q] : NONE;
+				m = x < m ? x : m;
+				if (((i + 1) & i) == 0 && i > 0) { table[(size_t)lvl * nb + j] = m; lvl++; }   // i + 1 = 2, 4, 8, 16, 32
+			}
 		});
 	}
 }
