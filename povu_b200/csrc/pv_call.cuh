@@ -121,8 +121,9 @@ inline void component_labels(Ctx &c, u32 V, u64 E, const u32 *ep1, const u32 *ep
 }
 
 // d_ep1/d_ep2: E edge endpoint ports (device).  d_steps: S packed steps (device).  d_segLen: V (device).
+// labels (optional): component labels already computed on this graph (decompose hands them over on the hot path).
 inline void graph_build(Ctx &c, u32 V, u64 E, const u32 *ep1, const u32 *ep2, u32 H, const u32 *h_stepOff, const u32 *d_steps,
-			const u32 *d_segLen, DevGraph &g) {
+			const u32 *d_segLen, DevGraph &g, Buf<u32> *labels = nullptr) {
 	Trace tr(c, "index");
 	g.V = V; g.E = E; g.H = H; g.S = h_stepOff ? h_stepOff[H] : 0;
 	const u32 P = 2 * V; const u64 M = 2 * E; const u32 S = g.S;
@@ -182,10 +183,10 @@ inline void graph_build(Ctx &c, u32 V, u64 E, const u32 *ep1, const u32 *ep2, u3
 	}
 	tr.mark("loci + vertex->steps");
 	// ---- weakly connected components -> the paths of every component
-	g.vcomp = Buf<u32>(c, V ? V : 1);
+	if (labels && labels->p && labels->n >= V && V) g.vcomp = std::move(*labels);
+	else { g.vcomp = Buf<u32>(c, V ? V : 1); component_labels(c, V, E, ep1, ep2, g.vcomp.p); }
 	{
 		u32 *uf_ = g.vcomp.p;
-		component_labels(c, V, E, ep1, ep2, uf_);
 		Buf<u32> pr(c, H ? H : 1);
 		u32 *pr_ = pr.p;
 		parallel_for<C_uf>(c, H, PV_LAMBDA(size_t h) { pr_[h] = stepOff_[h + 1] > stepOff_[h] ? uf_[steps_[stepOff_[h]] >> 1] : NONE; });
@@ -303,6 +304,7 @@ struct CallIn {            // PVST forest, flubbles of all components concatenat
 	const u32 *flBase = nullptr;   // per flubble: index of the first flubble of its component
 	u32 nRefs = 0; const u32 *refs = nullptr;   // ascending path ids to call against
 	const u8 *excluded = nullptr;  // optional: 1 = never selected (sub-flubble clan or below one, color.cpp:117-125)
+	bool on_device = false;        // a_v .. flBase point into device memory (decompose's table handed over in HBM)
 };
 
 // binary records, written by the device into page-locked host vectors whose capacity survives across calls
@@ -1151,8 +1153,14 @@ inline void call_device(Ctx &c, const DevGraph &G, const CallIn &in, const CallO
 	Buf<u32> fa(c, nFl), fz(c, nFl), fpar(c, nFl), fbase(c, nFl), refs(c, nRefs), colored(c, nFl), kid(c, nFl), called(c, nFl);
 	{
 		Buf<u8> af(c, nFl), zf(c, nFl), ex(c, nFl);
-		c.h2d(fa.p, in.a_v, (size_t)nFl * 4); c.h2d(fz.p, in.z_v, (size_t)nFl * 4); c.h2d(af.p, in.a_fwd, nFl); c.h2d(zf.p, in.z_fwd, nFl);
-		c.h2d(fpar.p, in.parent, (size_t)nFl * 4); c.h2d(fbase.p, in.flBase, (size_t)nFl * 4); c.h2d(refs.p, in.refs, (size_t)nRefs * 4);
+		if (in.on_device) {
+			c.d2d(fa.p, in.a_v, (size_t)nFl * 4); c.d2d(fz.p, in.z_v, (size_t)nFl * 4); c.d2d(af.p, in.a_fwd, nFl); c.d2d(zf.p, in.z_fwd, nFl);
+			c.d2d(fpar.p, in.parent, (size_t)nFl * 4); c.d2d(fbase.p, in.flBase, (size_t)nFl * 4);
+		} else {
+			c.h2d(fa.p, in.a_v, (size_t)nFl * 4); c.h2d(fz.p, in.z_v, (size_t)nFl * 4); c.h2d(af.p, in.a_fwd, nFl); c.h2d(zf.p, in.z_fwd, nFl);
+			c.h2d(fpar.p, in.parent, (size_t)nFl * 4); c.h2d(fbase.p, in.flBase, (size_t)nFl * 4);
+		}
+		c.h2d(refs.p, in.refs, (size_t)nRefs * 4);
 		if (in.excluded) c.h2d(ex.p, in.excluded, nFl);
 		u32 *fa_w = fa.p, *fz_w = fz.p; const u8 *af_ = af.p, *zf_ = zf.p, *ex_ = in.excluded ? ex.p : nullptr;
 		parallel_for<C_pack>(c, nFl, PV_LAMBDA(size_t f) {   // (vertex << 1) | reverse; NONE hides an excluded flubble
@@ -1205,7 +1213,7 @@ inline void call_device(Ctx &c, const DevGraph &G, const CallIn &in, const CallO
 		u32 *ovf_ = ovf.p;
 		parallel_for<C_keep>(c, R0, PV_LAMBDA(size_t r) { ovf_[r] = J0_[r] == NONE ? 1u : 0u; });
 		u32 nTodo = compact_flags(c, ovf.p, R0, todoBuf);
-		std::vector<u32> todo = todoBuf.to_host(); todo.resize(nTodo);
+		std::vector<u32> todo = todoBuf.to_host(nTodo);
 		u64 capV64 = 256;
 		while (!todo.empty()) {
 			const bool last = capV64 >= (u64)G.V;

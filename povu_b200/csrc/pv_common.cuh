@@ -103,6 +103,16 @@ struct Ctx {
 	void d2h(void *h, const void *d, size_t bytes);   // synchronous on return
 	void d2h_async(void *h, const void *d, size_t bytes);   // caller syncs before reading h
 	void d2d(void *d, const void *s, size_t bytes);
+	// background device -> host copies on a second stream, overlapped with later kernels of the main stream:
+	// bg_begin() orders the copy stream after everything issued so far; the SOURCE buffers must stay allocated and
+	// the destinations unread until bg_sync().
+#ifndef PV_EMU
+	cudaStream_t copy_stream = nullptr; cudaEvent_t copy_ev = nullptr;
+#endif
+	bool bg_pending = false;
+	void bg_begin();
+	void d2h_bg(void *h, const void *d, size_t bytes);
+	void bg_sync();
 };
 
 inline void Ctx::init(int dev, void *ext_stream) {
@@ -164,6 +174,7 @@ inline void Ctx::destroy() {
 	if (lb_flags) { cudaFree(lb_flags); cudaFree(lb_vals); lb_flags = nullptr; lb_vals = nullptr; lb_cap = 0; }
 	if (rs_status) { cudaFree(rs_status); rs_status = nullptr; rs_cap = 0; }
 	if (lb_ticket) { cudaFree(lb_ticket); lb_ticket = nullptr; }
+	if (copy_stream) { cudaStreamDestroy(copy_stream); cudaEventDestroy(copy_ev); copy_stream = nullptr; copy_ev = nullptr; }
 	if (own_stream && stream) cudaStreamDestroy(stream);
 	stream = nullptr;
 #endif
@@ -238,6 +249,29 @@ inline void Ctx::d2h_async(void *h, const void *d, size_t bytes) {
 	memcpy(h, d, bytes);
 #endif
 }
+inline void Ctx::bg_begin() {
+#ifndef PV_EMU
+	if (!copy_stream) { PV_CUDA_CHECK(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking)); PV_CUDA_CHECK(cudaEventCreateWithFlags(&copy_ev, cudaEventDisableTiming)); }
+	PV_CUDA_CHECK(cudaEventRecord(copy_ev, stream));
+	PV_CUDA_CHECK(cudaStreamWaitEvent(copy_stream, copy_ev, 0));
+#endif
+	bg_pending = true;
+}
+inline void Ctx::d2h_bg(void *h, const void *d, size_t bytes) {
+	if (!bytes) return;
+#ifndef PV_EMU
+	PV_CUDA_CHECK(cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, copy_stream));
+#else
+	memcpy(h, d, bytes);
+#endif
+}
+inline void Ctx::bg_sync() {
+	if (!bg_pending) return;
+#ifndef PV_EMU
+	PV_CUDA_CHECK(cudaStreamSynchronize(copy_stream));
+#endif
+	bg_pending = false;
+}
 inline void Ctx::d2d(void *d, const void *s, size_t bytes) {
 	if (!bytes) return;
 #ifndef PV_EMU
@@ -270,6 +304,8 @@ inline void Ctx::prof_collect() {
 		cudaEventElapsedTime(&ms, r.e0, r.e1);
 		cudaEventDestroy(r.e0); cudaEventDestroy(r.e1);
 #endif
+		static const bool dump = getenv("PV_PROF_DUMP") != nullptr;
+		if (dump) fprintf(stderr, "[prof] %-16s items %10llu bytes %11llu  %8.2f us\n", r.name, (unsigned long long)r.items, (unsigned long long)r.bytes, ms * 1e3);
 		bool found = false;
 		for (auto &a : prof_agg) if (a.name == r.name) { a.launches++; a.items += r.items; a.bytes += r.bytes; a.ms += ms; found = true; break; }
 		if (!found) prof_agg.push_back(ProfAgg{r.name, 1, r.items, r.bytes, ms});
@@ -345,6 +381,8 @@ template <class T> struct Buf {
 	operator T *() const { return p; }
 	T *get() const { return p; }
 	std::vector<T> to_host() const { std::vector<T> h(n); c->d2h(h.data(), p, n * sizeof(T)); return h; }
+	std::vector<T> to_host(size_t m) const { std::vector<T> h(m); c->d2h(h.data(), p, m * sizeof(T)); return h; }   // first m elements
+	void to_hvec_bg(hvec<T> &h, size_t m) const { h.resize(m); c->d2h_bg(h.data(), p, m * sizeof(T)); }            // on the copy stream
 	// asynchronous copy of the first m elements into a pinned host vector (capacity reused); sync before reading
 	void to_hvec(hvec<T> &h, size_t m) const { h.resize(m); c->d2h_async(h.data(), p, m * sizeof(T)); }
 	T read(size_t i) const { T v; c->d2h(&v, p + i, sizeof(T)); return v; }

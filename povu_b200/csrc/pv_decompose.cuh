@@ -49,7 +49,14 @@ struct DecompOut {
 	}
 };
 
-struct DecompOpts { bool want_stack = false; u64 seed = 0x706F7675ull; };
+struct DecompOpts {
+	bool want_stack = false; u64 seed = 0x706F7675ull;
+	Buf<u32> *keep_labels = nullptr;   // receives label[v] = lowest vertex index of v's component (what pv_call's component_labels computes)
+	struct DevForest *keep_forest = nullptr;   // receives the flubble table on the device (call reads it there instead of re-uploading)
+	bool async_results = false;        // the big result arrays travel on the context's copy stream; the caller must c.bg_sync() before reading them
+};
+// the flubble table as decompose left it in HBM
+struct DevForest { Buf<u32> a_v, z_v, parent, depth, comp, fl_base; Buf<u8> a_fwd, z_fwd; u32 n = 0; bool valid = false; };
 
 // kernel tags with their algorithmic bytes per logical item
 PV_KERNEL(K_minport, 24);      // 2 endpoints in, key + idx out, 2 degree atomics
@@ -199,7 +206,7 @@ inline void decompose_device(Ctx &c, u32 V, u64 E, const u32 *ep1, const u32 *ep
 			u32 v = act[i >> 1]; u32 p = 2 * v + (u32)(i & 1);
 			for (u32 s = adjOff_[p], e = adjOff_[p + 1]; s < e; s++) {
 				u32 w = adjNbr_[s] >> 1;
-				if (w != v && !visited_[w]) uf_union(uf_, v, w);
+				if (w < v && !visited_[w]) uf_union(uf_, v, w);   // an edge between two unvisited segments is seen from both ends: join once
 			}
 		});
 		parallel_for<K_uf_flatten>(c, nA, PV_LAMBDA(size_t i) { u32 v = act[i]; comp_[v] = uf_find(uf_, v); });
@@ -255,10 +262,17 @@ inline void decompose_device(Ctx &c, u32 V, u64 E, const u32 *ep1, const u32 *ep
 			c.d2d(J.p, F.p, (size_t)P * 4);
 			u32 *Ja = J.p, *Jb = J2.p;
 			int maxIt = bits_for((u64)nA * 2) + 1;
+			// itFlag[it] = "iteration it marked something".  Later iterations test the previous flag on the device and fall
+			// through when the marking has converged; the host looks only every 8th iteration (one sync instead of eight).
+			// (flags sit 128 bytes apart: a word that one iteration polls must not share a sector with the word the same
+			// iteration's markers keep storing to)
+			Buf<u32> itFlag(c, ((size_t)maxIt + 1) * 32);
+			itFlag.zero();
+			u32 *itFlag_ = itFlag.p;
 			for (int it = 0; it < maxIt; it++) {
-				c.memset0(flag.p, 4);
 				const u32 lim = 1u << it;
 				parallel_for<K_mark>(c, (size_t)nA * 2, PV_LAMBDA(size_t i) {
+					if (it > 0 && itFlag_[(it - 1) * 32] == 0) return;
 					u32 v = act[i >> 1]; u32 x = 2 * v + (u32)(i & 1);
 					u32 r = rnk_[x];
 					if (r >= lim) return;                       // NONE or marked in this very iteration
@@ -267,11 +281,11 @@ inline void decompose_device(Ctx &c, u32 V, u64 E, const u32 *ep1, const u32 *ep
 					u32 rho = r + lim;
 					u32 old = atomic_min(rnk_ + y, rho);
 					if (old != NONE && old != rho) atomic_min(trunc_ + comp_[v], old > rho ? old : rho);
-					flag_[0] = 1;
+					itFlag_[it * 32] = 1;
 				});
-				u32 any = flag.read(0);
-				if (!any) break;
+				if ((it == 1 || (it & 7) == 7) && !itFlag.read((size_t)it * 32)) break;
 				parallel_for<K_jump>(c, (size_t)nA * 2, PV_LAMBDA(size_t i) {
+					if (itFlag_[it * 32] == 0) return;
 					u32 v = act[i >> 1]; u32 x = 2 * v + (u32)(i & 1);
 					u32 y = Ja[x];
 					Jb[x] = y == NONE ? NONE : Ja[y];
@@ -661,12 +675,19 @@ inline void decompose_device(Ctx &c, u32 V, u64 E, const u32 *ep1, const u32 *ep
 
 	tr.mark("D6 flubbles");
 	// ------------------------------------------------------------------ results to the host
-	fA.to_hvec(out.a_v, nFl); fZ.to_hvec(out.z_v, nFl); fPar.to_hvec(out.parent, nFl); fDepth.to_hvec(out.depth, nFl); fComp.to_hvec(out.comp, nFl);
-	fAf.to_hvec(out.a_fwd, nFl); fZf.to_hvec(out.z_fwd, nFl); fBase.to_hvec(out.fl_base, nFl);
+	const bool bg = opt.async_results && opt.keep_forest;   // (the sources must outlive the copies: only when the caller keeps them)
+	if (bg) {
+		c.bg_begin();
+		fA.to_hvec_bg(out.a_v, nFl); fZ.to_hvec_bg(out.z_v, nFl); fPar.to_hvec_bg(out.parent, nFl); fDepth.to_hvec_bg(out.depth, nFl); fComp.to_hvec_bg(out.comp, nFl);
+		fAf.to_hvec_bg(out.a_fwd, nFl); fZf.to_hvec_bg(out.z_fwd, nFl); fBase.to_hvec_bg(out.fl_base, nFl);
+	} else {
+		fA.to_hvec(out.a_v, nFl); fZ.to_hvec(out.z_v, nFl); fPar.to_hvec(out.parent, nFl); fDepth.to_hvec(out.depth, nFl); fComp.to_hvec(out.comp, nFl);
+		fAf.to_hvec(out.a_fwd, nFl); fZf.to_hvec(out.z_fwd, nFl); fBase.to_hvec(out.fl_base, nFl);
+	}
 	u32 fl[4];
-	c.d2h(fl, flag.p, 16);   // synchronises: the asynchronous copies above have landed
+	c.d2h(fl, flag.p, 16);   // synchronises the main stream
 	out.collisions = fl[1];
-	out.comp_root = roots.to_host(); out.comp_root.resize(nComp);
+	out.comp_root = roots.to_host(nComp);
 	out.comp_nv = cNv.to_host(); out.comp_nv.resize(nComp);
 	out.comp_has_tips = cHasTips.to_host();
 	out.comp_nonlaminar = lamBad.to_host(); out.comp_nonlaminar.resize(nComp);
@@ -681,6 +702,12 @@ inline void decompose_device(Ctx &c, u32 V, u64 E, const u32 *ep1, const u32 *ep
 	}
 	c.sync();
 	tr.mark("results d2h");
+	if (opt.keep_labels) *opt.keep_labels = std::move(gcomp);
+	if (opt.keep_forest) {
+		DevForest &d = *opt.keep_forest;
+		d.a_v = std::move(fA); d.z_v = std::move(fZ); d.parent = std::move(fPar); d.depth = std::move(fDepth); d.comp = std::move(fComp); d.fl_base = std::move(fBase);
+		d.a_fwd = std::move(fAf); d.z_fwd = std::move(fZf); d.n = nFl; d.valid = true;
+	}
 }
 
 } // namespace pv

@@ -50,6 +50,8 @@ struct Session {
 
 	// raw arrays resident in HBM: edge ports, packed steps, segment lengths
 	pv::Buf<u32> d_steps, d_segLen; bool raw_paths_up = false;
+	pv::Buf<u32> d_labels; bool labels_ready = false, want_labels = false;
+	pv::DevForest dforest;   // decompose's flubble table in HBM, alive from decompose to the end of call on the hot path   // whole-graph component labels handed from decompose to the index build (hot path only)
 	double t_upload_ms = 0, t_dec_ms = 0, t_build_ms = 0, t_call_ms = 0;
 	static double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
@@ -74,7 +76,8 @@ struct Session {
 	void upload_paths() {
 		if (paths_up) return;
 		upload_edges(); upload_raw_paths();
-		pv::graph_build(*c, g.V(), g.E(), d_ep1.p, d_ep2.p, g.H(), g.stepOff.data(), d_steps.p, d_segLen.p, dg);
+		pv::graph_build(*c, g.V(), g.E(), d_ep1.p, d_ep2.p, g.H(), g.stepOff.data(), d_steps.p, d_segLen.p, dg, labels_ready ? &d_labels : nullptr);
+		labels_ready = false; d_labels.release();
 		paths_up = true;
 	}
 	// forget everything on the device (the next decompose / call re-uploads from the host arrays)
@@ -89,12 +92,16 @@ struct Session {
 		if (!keep_raw) drop_device();
 		upload_edges(); upload_raw_paths();
 		double t1 = now_ms();
+		want_labels = true;
 		decompose();
+		want_labels = false;
 		double t2 = now_ms();
 		paths_up = false; dg = pv::DevGraph();
 		upload_paths();
 		double t3 = now_ms();
 		call();
+		c->bg_sync();              // the flubble table has reached the host (copied behind the index build and the call)
+		dforest = pv::DevForest();
 		double t4 = now_ms();
 		t_upload_ms = t1 - t0; t_dec_ms = t2 - t1; t_build_ms = t3 - t2; t_call_ms = t4 - t3;
 	}
@@ -153,10 +160,14 @@ struct Session {
 
 	// decompose: flubbles + PVST of every component with >= 3 vertices (decompose.cpp:129-142)
 	void decompose() {
+		c->bg_sync();
 		upload_edges();
 		pv::DecompOpts opt;
+		dforest = pv::DevForest();
+		if (want_labels) { opt.keep_labels = &d_labels; opt.keep_forest = &dforest; opt.async_results = true; }
 		pv::Trace tr(*c, "session");
 		pv::decompose_device(*c, g.V(), g.E(), d_ep1.p, d_ep2.p, opt, dec);
+		labels_ready = want_labels && d_labels.p != nullptr;
 		tr.mark("decompose_device");
 		if (dec.collisions) throw std::runtime_error("cycle-equivalence label collision detected by the exact bracket-set check");
 		// the flubble table is already flat in component order: swap the (page-locked) arrays instead of copying.
@@ -231,8 +242,14 @@ struct Session {
 		}
 		pv::CallIn in;
 		if (any_excl) in.excluded = excl.data();
-		in.nFl = forest.n(); in.a_v = forest.a_v.data(); in.z_v = forest.z_v.data(); in.a_fwd = forest.a_fwd.data(); in.z_fwd = forest.z_fwd.data();
-		in.parent = forest.parent.data(); in.flBase = forest.flBase.data(); in.nRefs = (u32)refs.size(); in.refs = refs.data();
+		in.nFl = forest.n(); in.nRefs = (u32)refs.size(); in.refs = refs.data();
+		if (dforest.valid && dforest.n == in.nFl) {
+			in.on_device = true; in.a_v = dforest.a_v.p; in.z_v = dforest.z_v.p; in.a_fwd = dforest.a_fwd.p; in.z_fwd = dforest.z_fwd.p;
+			in.parent = dforest.parent.p; in.flBase = dforest.fl_base.p;
+		} else {
+			in.a_v = forest.a_v.data(); in.z_v = forest.z_v.data(); in.a_fwd = forest.a_fwd.data(); in.z_fwd = forest.z_fwd.data();
+			in.parent = forest.parent.data(); in.flBase = forest.flBase.data();
+		}
 		pv::CallOpts opt;
 		if (const char *e = getenv("POVU_B200_CELL_BUDGET")) opt.cell_budget = strtoull(e, nullptr, 10);
 		pv::Trace tr(*c, "session");

@@ -20,9 +20,10 @@ struct OpXor128 { PV_HD u128 operator()(u128 a, u128 b) const { return u128{a.lo
 struct OpAddI32 { PV_HD i32 operator()(i32 a, i32 b) const { return a + b; } };
 
 #ifndef PV_EMU
-static const int SCAN_THREADS = 256;
-static const int SCAN_ITEMS = 8;
-static const int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+static const int SCAN_THREADS = 512;
+// items per thread: up to 128 bytes, at most 16 items (u32: 16, u64 / max-plus: 16, u128: 8).  Fat tiles keep the number
+// of tiles -- and with it the length of the look-back chain when every tile of a mid-sized input is resident at once -- small.
+template <class T> struct ScanCfg { static const int ITEMS = sizeof(T) >= 16 ? 8 : 16; static const int TILE = SCAN_THREADS * ITEMS; };
 
 // word-wise helpers for generic (POD, multiple-of-4-byte) scan element types
 template <class T> struct Words { static_assert(sizeof(T) % 4 == 0 && sizeof(T) <= 16, "scan element must be 4..16 bytes"); static const int N = sizeof(T) / 4; };
@@ -60,6 +61,7 @@ __device__ __forceinline__ void st_flag(u32 *p, u32 v) { *(volatile u32 *)p = v;
 template <class T, class Op, bool INCLUSIVE, bool VEC>
 __global__ void __launch_bounds__(SCAN_THREADS) scan_lb_kernel(const T *in, T *out, size_t n, Op op, T identity, u32 *flags, T *agg, T *incl,
 								 u32 *ticket, u32 epoch, u32 ntiles) {
+	constexpr int SCAN_ITEMS = ScanCfg<T>::ITEMS, SCAN_TILE = ScanCfg<T>::TILE;
 	__shared__ T warpTot[SCAN_THREADS / 32];
 	__shared__ T s_prefix;
 	__shared__ u32 s_tile;
@@ -157,6 +159,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_lb_kernel(const T *in, T *o
 template <class T, class Op, bool INCLUSIVE>
 inline void scan_impl(Ctx &c, const T *in, T *out, size_t n, Op op, T identity) {
 	if (n == 0) return;
+	const size_t SCAN_TILE = ScanCfg<T>::TILE;
 	size_t ntiles = (n + SCAN_TILE - 1) / SCAN_TILE;
 	if (ntiles >= 0x7FFFFFFFull) throw std::runtime_error("scan: input too large");
 	c.lb_reserve(ntiles);
@@ -255,8 +258,8 @@ __device__ __forceinline__ u32 block_excl_scan_256(u32 v, u32 *warpSum /*[8] sha
 }
 
 template <int ITEMS>
-__global__ void __launch_bounds__(RS_THREADS) rs_onesweep_kernel(const u32 *kin, const u32 *vin, u32 *kout, u32 *vout, size_t n, int shift,
-								   const u32 *ghist, u64 *status, u32 *ticket, u32 epoch, u32 ntiles) {
+__global__ void __launch_bounds__(RS_THREADS, 4) rs_onesweep_kernel(const u32 *kin, const u32 *vin, u32 *kout, u32 *vout, size_t n, int shift,
+								      const u32 *ghist, u64 *status, u32 *ticket, u32 epoch, u32 ntiles) {
 	constexpr int TILE = RS_THREADS * ITEMS;
 	__shared__ u32 sKeys[TILE];
 	__shared__ u32 sVals[TILE];
@@ -274,27 +277,37 @@ __global__ void __launch_bounds__(RS_THREADS) rs_onesweep_kernel(const u32 *kin,
 	const size_t tileBase = (size_t)tile * TILE;
 	const u32 tileCount = (u32)(n - tileBase < (size_t)TILE ? n - tileBase : (size_t)TILE);
 	const size_t wbase = tileBase + (size_t)w * (32 * ITEMS) + lane;
-	u32 key[ITEMS], val[ITEMS], pos[ITEMS];
 	const bool full = tileCount == (u32)TILE;
+	u32 key[ITEMS], pos[ITEMS];
 	if (full) {
 #pragma unroll
-		for (int k = 0; k < ITEMS; k++) { key[k] = kin[wbase + (size_t)k * 32]; val[k] = vin[wbase + (size_t)k * 32]; }
+		for (int k = 0; k < ITEMS; k++) key[k] = kin[wbase + (size_t)k * 32];
 	} else {
 #pragma unroll
-		for (int k = 0; k < ITEMS; k++) { size_t i = wbase + (size_t)k * 32; bool ok = i < n; key[k] = ok ? kin[i] : 0u; val[k] = ok ? vin[i] : 0u; }
+		for (int k = 0; k < ITEMS; k++) { size_t i = wbase + (size_t)k * 32; key[k] = i < n ? kin[i] : 0u; }
 	}
-	const u32 ltMask = (1u << lane) - 1u;
+	// warp-private ranking in index order (stable).  All the matches are issued first, then the leaders' counter
+	// updates (shared-memory atomics; __syncwarp keeps successive rounds ordered), then the broadcasts: the three
+	// latencies overlap across the ITEMS rounds instead of adding up.
+	{
+		const u32 ltMask = (1u << lane) - 1u;
+		u32 peers[ITEMS];
 #pragma unroll
-	for (int k = 0; k < ITEMS; k++) {
-		bool valid = full || (wbase + (size_t)k * 32 < n);
-		u32 d = valid ? ((key[k] >> shift) & 255u) : 256u + (u32)lane;   // invalid lanes get unique pseudo-digits
-		u32 peers = __match_any_sync(0xFFFFFFFFu, d);
-		u32 r = __popc(peers & ltMask);
-		u32 c0 = valid ? warpCnt[w][d] : 0u;
-		__syncwarp();
-		if (valid && r == 0) warpCnt[w][d] = c0 + __popc(peers);
-		__syncwarp();
-		pos[k] = c0 + r;   // rank among the warp's elements with this digit
+		for (int k = 0; k < ITEMS; k++) {
+			bool valid = full || (wbase + (size_t)k * 32 < n);
+			u32 d = valid ? ((key[k] >> shift) & 255u) : 256u + (u32)lane;   // invalid lanes get unique pseudo-digits
+			peers[k] = __match_any_sync(0xFFFFFFFFu, d);
+		}
+#pragma unroll
+		for (int k = 0; k < ITEMS; k++) {
+			bool valid = full || (wbase + (size_t)k * 32 < n);
+			u32 c0 = 0;
+			if (valid && (peers[k] & ltMask) == 0) c0 = atomicAdd(&warpCnt[w][(key[k] >> shift) & 255u], (u32)__popc(peers[k]));
+			__syncwarp();
+			pos[k] = c0;
+		}
+#pragma unroll
+		for (int k = 0; k < ITEMS; k++) pos[k] = __shfl_sync(0xFFFFFFFFu, pos[k], __ffs((int)peers[k]) - 1) + __popc(peers[k] & ltMask);
 	}
 	__syncthreads();
 	// thread t owns digit t: warp counts -> warp offsets, tile count
@@ -307,26 +320,48 @@ __global__ void __launch_bounds__(RS_THREADS) rs_onesweep_kernel(const u32 *kin,
 	u32 gbase = block_excl_scan_256(ghist[t], warpSum);
 	u32 excl = 0;
 	if (tile > 0) {
-		for (int i = (int)tile - 1;; i--) {
-			u64 sw;
-			const volatile u64 *sp = (const volatile u64 *)(status + (size_t)i * 256 + t);
-			do { sw = *sp; } while ((u32)(sw >> 34) != epoch);
-			excl += (u32)sw;
-			if (((sw >> 32) & 3u) == 2u) break;
+		// look-back, four predecessors' status words in flight at a time (the chain is latency-bound: when every tile of a
+		// mid-sized input is resident at once, tile i walks ~sqrt(2i) predecessors before it meets an inclusive prefix)
+		const u64 done = ((u64)epoch << 34) | ((u64)2u << 32);
+		int i = (int)tile - 1;
+		bool fin = false;
+		while (!fin) {
+			u64 sw[4];
+#pragma unroll
+			for (int q = 0; q < 4; q++) sw[q] = i - q >= 0 ? *(const volatile u64 *)(status + (size_t)(i - q) * 256 + t) : done;
+			int used = 0;
+#pragma unroll
+			for (int q = 0; q < 4; q++) {
+				if (!fin && used == q && (u32)(sw[q] >> 34) == epoch) {
+					excl += (u32)sw[q]; used = q + 1;
+					if (((sw[q] >> 32) & 3u) == 2u) fin = true;
+				}
+			}
+			i -= used;   // the first word that was not ready yet is polled again
 		}
 		*(volatile u64 *)myStatus = ((u64)epoch << 34) | ((u64)2u << 32) | (u64)(excl + cnt);
 	}
 	digStart[t] = ds;
 	gOff[t] = gbase + excl - ds;
 	__syncthreads();
+	// stage the tile in digit order, keys first, then the values (loaded only now: fewer live registers -> 4 CTAs / SM)
 #pragma unroll
 	for (int k = 0; k < ITEMS; k++) {
 		bool valid = full || (wbase + (size_t)k * 32 < n);
 		if (valid) {
 			u32 d = (key[k] >> shift) & 255u;
-			u32 p = digStart[d] + warpCnt[w][d] + pos[k];
-			sKeys[p] = key[k]; sVals[p] = val[k];
+			pos[k] += digStart[d] + warpCnt[w][d];
+			sKeys[pos[k]] = key[k];
 		}
+	}
+	if (full) {
+#pragma unroll
+		for (int k = 0; k < ITEMS; k++) key[k] = vin[wbase + (size_t)k * 32];
+#pragma unroll
+		for (int k = 0; k < ITEMS; k++) sVals[pos[k]] = key[k];
+	} else {
+#pragma unroll
+		for (int k = 0; k < ITEMS; k++) { size_t i = wbase + (size_t)k * 32; if (i < n) sVals[pos[k]] = vin[i]; }
 	}
 	__syncthreads();
 #pragma unroll
@@ -542,14 +577,14 @@ inline u32 compact_flags(Ctx &c, const u32 *flags, size_t n, Buf<u32> &out) {
 	if (n == 0) { out = Buf<u32>(c, 1); return 0; }
 	Buf<u32> pos(c, n + 1);
 	exclusive_scan(c, flags, pos.p, n, OpAddU32(), 0u);
-	u32 last_pos = pos.read(n - 1);
-	u32 last_flag;
-	c.d2h(&last_flag, flags + (n - 1), 4);
-	u32 cnt = last_pos + (last_flag ? 1u : 0u);
-	out = Buf<u32>(c, cnt ? cnt : 1);
-	u32 *o = out.p; const u32 *p = pos.p;
-	parallel_for<K_compact_scatter>(c, n, PV_LAMBDA(size_t i) { if (flags[i]) o[p[i]] = (u32)i; });
-	return cnt;
+	out = Buf<u32>(c, n);     // capacity n: the count is known only after the scatter (one host read instead of two)
+	u32 *o = out.p; u32 *p = pos.p;
+	parallel_for<K_compact_scatter>(c, n, PV_LAMBDA(size_t i) {
+		u32 f = flags[i];
+		if (f) o[p[i]] = (u32)i;
+		if (i == n - 1) p[n] = p[i] + (f ? 1u : 0u);
+	});
+	return pos.read(n);
 }
 
 } // namespace pv
