@@ -250,12 +250,13 @@ def run_native(args):
             sess.hot_path(prefixes, keep_resident=False)
         barrier()
         e2e_s = time.perf_counter() - t0
-        # VCF text from the binary records (host C++), reported beside e2e
+        # VCF text of the records, written on the device (pv_text.cuh) and brought to the host; reported beside e2e
+        devnull = os.path.join(tempfile.gettempdir(), f"povu_bench_{os.getpid()}.vcf")
+        sess.vcf_write(devnull)                    # first call uploads the per-graph text tables
         t0 = time.perf_counter()
-        text = sess.vcf_text()
+        text_bytes = sess.vcf_write("/dev/null")
         text_s = time.perf_counter() - t0
-        text_bytes = len(text)
-        del text
+        os.unlink(devnull)
 
         prof = None
         if rank == 0 and args.profile_steps > 0:
@@ -325,7 +326,7 @@ def run_native(args):
                           "ms": {"decompose": pm[1], "path_index_build": pm[2], "call": pm[3]}, "records_all_ranks": tot_rec, "flubbles_all_ranks": tot_fl, "call_stats": stats},
                 "e2e": {"value": world * E / (e2e_ms_max / e2e_steps * 1e-3), "unit": "edges/s", "h2d_bytes_per_step": 8 * E + 4 * S + 4 * V, "d2h_bytes_per_step": d2h_bytes,
                         "ms_per_step": e2e_ms_max / e2e_steps, "steps": e2e_steps,
-                        "vcf_text": {"bytes": text_bytes, "ms": text_s * 1e3, "note": "host C++ formatting of the binary records, not inside e2e (SURVEY.md 8f2)"}},
+                        "vcf_text": {"bytes": text_bytes, "ms": text_s * 1e3, "note": "record lines written by the device text kernels (X_len, X_write), D2H into a page-locked buffer, write(2) to /dev/null; wall time of one pvgpu_session_vcf_write call, not inside e2e (SURVEY.md 8f2)"}},
                 "gpu_launches": int(launches), "wall_s_timed_region": wall,
                 "clocks": clk, "roofline": roofline, "cpu_baseline": cpu, "peak_device_bytes": pv.peak_bytes}
         print(json.dumps(line))

@@ -49,6 +49,10 @@ int pvgpu_build_kind(void);
  * algorithms.  Not part of the reference-facing surface. */
 int pvgpu_selftest_prims(pvgpu_ctx *ctx, uint64_t n, uint64_t seed, int bits, uint64_t *mismatches);
 
+/* test hook (tests/test_text_emu.py, test_text_gpu.py): formats AF = ac / an for every 0 <= ac <= an <= max_an (and some
+ * integers) with the device text writer and counts disagreements with the C library's "%.1f" / "%u". */
+int pvgpu_selftest_text(pvgpu_ctx *ctx, uint32_t max_an, uint64_t *mismatches);
+
 /* decompose with HOST inputs (pinned or pageable): copies ep1/ep2 to the device on the context's
  * stream, runs the pipeline, copies the flubble table back.  flags bit0: also return the class stack. */
 int pvgpu_decompose(pvgpu_ctx *ctx, uint32_t n_vertices, uint64_t n_edges, const uint32_t *ep1, const uint32_t *ep2,
@@ -123,6 +127,10 @@ void pvgpu_session_call_stats(const pvgpu_session *s, uint64_t out[12]);
 /* combined VCF text (what `povu gfa2vcf` / `povu call --stdout` print); with_date = 0 drops ##fileDate.
  * prefix = NULL: combined stream; otherwise the per-prefix file content of `-o dir` (to_vcf.hpp:83-101). */
 char *pvgpu_session_vcf_text(const pvgpu_session *s, size_t chunk_size, int with_date, const char *prefix, size_t *len);
+/* same text written straight to a file descriptor from the page-locked buffer the device text landed in (what the
+ * CLI uses for stdout / <prefix>.vcf; replaces to_vcf::write_vcfs, /root/reference/src/mto/to_vcf.cpp:121-139).
+ * The record lines themselves are produced on the device (pv_text.cuh); only the '#' header is formatted on the host. */
+int pvgpu_session_vcf_write(const pvgpu_session *s, size_t chunk_size, int with_date, const char *prefix, int fd, uint64_t *bytes_written);
 /* ---- multi-GPU (one process per GPU): keep only this rank's share of the weakly connected components, balanced by
  * edges + path steps (greedy LPT).  Component ids, path ids and vertex / edge order stay those of the whole graph, so
  * the per-rank outputs concatenate into exactly the single-GPU output.  No exchange happens while computing; the only

@@ -46,6 +46,7 @@ def load_library(lib_path=None):
     lib.pvgpu_profile_json.restype = C.c_size_t
     lib.pvgpu_selftest_prims.argtypes = [vp, u64, u64, C.c_int, C.POINTER(u64)]
     lib.pvgpu_selftest_prims.restype = C.c_int
+    lib.pvgpu_selftest_text.argtypes = [vp, u32, C.POINTER(u64)]
     lib.pvgpu_decompose.argtypes = [vp, u32, u64, vp, vp, u32, C.POINTER(vp)]
     lib.pvgpu_decompose.restype = C.c_int
     lib.pvgpu_decompose_dev.argtypes = [vp, u32, u64, vp, vp, u32, C.POINTER(vp)]
@@ -94,6 +95,8 @@ def load_library(lib_path=None):
     lib.pvgpu_session_call_stats.argtypes = [vp, C.POINTER(u64)]
     lib.pvgpu_session_vcf_text.argtypes = [vp, sz, C.c_int, C.c_char_p, C.POINTER(sz)]
     lib.pvgpu_session_vcf_text.restype = vp
+    lib.pvgpu_session_vcf_write.argtypes = [vp, sz, C.c_int, C.c_char_p, C.c_int, C.POINTER(u64)]
+    lib.pvgpu_session_vcf_write.restype = C.c_int
     lib.pvgpu_free.argtypes = [vp]
     lib.pvgpu_session_shard.argtypes = [vp, u32, u32, C.POINTER(u32)]
     lib.pvgpu_session_shard.restype = C.c_int
@@ -198,6 +201,12 @@ class Povu:
     @property
     def peak_bytes(self):
         return int(self.lib.pvgpu_peak_device_bytes(self.h))
+
+    def selftest_text(self, max_an=700):
+        bad = C.c_uint64()
+        if self.lib.pvgpu_selftest_text(self.h, int(max_an), C.byref(bad)) != 0:
+            raise RuntimeError(self._err())
+        return int(bad.value)
 
     def selftest_prims(self, n, seed=1, bits=32):
         """Device primitives (pair sort, scans, RMQ) against the host's std:: algorithms; returns the mismatch count."""
@@ -355,6 +364,16 @@ class Session:
     def vcf_text(self, chunk_size=100, with_date=False, prefix=None):
         n = C.c_size_t()
         return self._text(self.lib.pvgpu_session_vcf_text(self.h, chunk_size, int(with_date), prefix.encode() if prefix else None, C.byref(n)), n)
+
+    def vcf_write(self, path, chunk_size=100, with_date=False, prefix=None):
+        """Header + device-written record text straight to a file; returns the number of bytes."""
+        n = C.c_uint64()
+        fd = os.open(path, os.O_WRONLY | os.O_CREAT | os.O_TRUNC, 0o644)
+        try:
+            self._check(self.lib.pvgpu_session_vcf_write(self.h, chunk_size, int(with_date), prefix.encode() if prefix else None, fd, C.byref(n)))
+        finally:
+            os.close(fd)
+        return int(n.value)
 
     def shard(self, rank, world):
         """Keep only this rank's share of the components (balanced by edges + path steps); returns the total

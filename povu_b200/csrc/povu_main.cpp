@@ -12,6 +12,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <fcntl.h>
 #include <fstream>
 #include <string>
 #include <sys/stat.h>
@@ -141,19 +142,18 @@ static void write_vcfs(const Config &c, Dev &d, const std::vector<std::string> &
 	if (st[10]) fprintf(stderr, "WARN [povu_b200::call] %llu SUBR records had a merged length past the end of a walk (undefined in the reference): clamped\n", (unsigned long long)st[10]);
 	const bool to_stdout = !c.have_out || c.stdout_vcf;
 	if (to_stdout) {
-		size_t n = 0; char *t = pvgpu_session_vcf_text(d.s, c.chunk, 1, nullptr, &n);
-		if (!t) throw Fail{pvgpu_last_error(d.ctx)};
-		fwrite(t, 1, n, stdout); fflush(stdout); pvgpu_free(t);
+		fflush(stdout);
+		d.check(pvgpu_session_vcf_write(d.s, c.chunk, 1, nullptr, STDOUT_FILENO, nullptr));
 		return;
 	}
 	mkdir(c.out_dir.c_str(), 0777);   // create_dir_if_not_exists (to_vcf.hpp:83-101)
 	for (auto &p : prefixes) {
-		size_t n = 0; char *t = pvgpu_session_vcf_text(d.s, c.chunk, 1, p.c_str(), &n);
-		if (!t) throw Fail{pvgpu_last_error(d.ctx)};
 		std::string fp = c.out_dir + "/" + p + ".vcf";
-		FILE *f = fopen(fp.c_str(), "wb");
-		if (!f) { pvgpu_free(t); throw Fail{"Append open failed: " + fp}; }
-		fwrite(t, 1, n, f); fclose(f); pvgpu_free(t);
+		int fd = open(fp.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0666);
+		if (fd < 0) throw Fail{"Append open failed: " + fp};
+		int rc = pvgpu_session_vcf_write(d.s, c.chunk, 1, p.c_str(), fd, nullptr);
+		close(fd);
+		d.check(rc);
 	}
 }
 

@@ -2,6 +2,7 @@
 #include "../../include/povu_b200.h"
 #include "pv_engine.hpp"
 #include "pv_ffi.hpp"
+#include <cerrno>
 
 struct pvgpu_ctx { pv::Ctx c; std::string err; };
 struct pvgpu_flubbles { pv::DecompOut o; };
@@ -209,6 +210,39 @@ int pvgpu_selftest_prims(pvgpu_ctx *x, uint64_t n, uint64_t seed, int bits, uint
 	} catch (std::exception &e) { x->err = e.what(); return 1; }
 }
 
+/* ---------------------------------------------------------------- text formatting self-test (tests/test_text_*.py) */
+namespace pv { PV_KERNEL(X_selftest, 8); }
+int pvgpu_selftest_text(pvgpu_ctx *x, uint32_t max_an, uint64_t *mismatches) {
+	if (!x || !mismatches || max_an == 0) return 1;
+	*mismatches = 0;
+	try {
+		PV_SET_DEVICE(x);
+		using namespace pv;
+		Ctx &c = x->c;
+		// AF of every (ac, an) with 1 <= an <= max_an, 0 <= ac <= an, and plain integers, against the C library
+		const size_t n = (size_t)(max_an + 1) * (max_an + 1);
+		Buf<u8> out(c, n * 16);
+		u8 *out_ = out.p;
+		parallel_for<X_selftest>(c, n, PV_LAMBDA(size_t i) {
+			u32 an = (u32)(i / (max_an + 1)), ac = (u32)(i % (max_an + 1));
+			u8 *o = out_ + i * 16;
+			for (int k = 0; k < 16; k++) o[k] = 0;
+			if (an == 0 || ac > an) return;
+			WriteSink s(o); put_af(s, ac, an); s.ch(' '); put_u32(s, ac * 7919u + an); s.finish();
+		});
+		std::vector<u8> h = out.to_host();
+		u64 bad = 0;
+		for (size_t i = 0; i < n; i++) {
+			u32 an = (u32)(i / (max_an + 1)), ac = (u32)(i % (max_an + 1));
+			if (an == 0 || ac > an) continue;
+			char want[32]; snprintf(want, sizeof want, "%.1f %u", (double)ac / (double)an, ac * 7919u + an);
+			if (strncmp(want, (const char *)&h[i * 16], 16) != 0) { if (bad < 5) fprintf(stderr, "[selftest text] %u/%u: got '%.16s' want '%s'\n", ac, an, (const char *)&h[i * 16], want); bad++; }
+		}
+		*mismatches = bad;
+		return 0;
+	} catch (std::exception &e) { x->err = e.what(); return 1; }
+}
+
 /* ---------------------------------------------------------------- sessions */
 struct pvgpu_session { pvgpu_ctx *x; pve::Session s; explicit pvgpu_session(pvgpu_ctx *x_) : x(x_), s(x_->c) {} };
 static char *dup_text(const std::string &t, size_t *len) {
@@ -290,13 +324,33 @@ void pvgpu_session_call_stats(const pvgpu_session *s, uint64_t o[12]) {
 	const pv::Records &c = s->s.rec;
 	o[0] = c.n_called; o[1] = c.n_regions; o[2] = c.n_tangled; o[3] = c.n_pin_pairs; o[4] = c.n_sort_failed; o[5] = c.n_hard_errors; o[6] = c.n_chunks; o[7] = c.n_too_small; o[8] = c.max_J; o[9] = c.n_big_bfs; o[10] = c.n_subr_clamped; o[11] = 0;
 }
+// header (host strings) + the device-written record text (pv_text.cuh)
+static void vcf_parts(const pve::Session &S, size_t chunk, int with_date, const char *prefix, std::string &header, pv::TextOut &body) {
+	if (!prefix) { header = S.vcf_header(S.prefixes, with_date != 0); S.vcf_records_device(chunk, nullptr, body); return; }
+	std::set<pv::u32> only = pvh::refs_in_sample(S.g, prefix);
+	header = S.vcf_header({std::string(prefix)}, with_date != 0);
+	S.vcf_records_device(chunk, &only, body);
+}
 char *pvgpu_session_vcf_text(const pvgpu_session *s, size_t chunk, int with_date, const char *prefix, size_t *len) {
 	try {
-		const pve::Session &S = s->s;
-		if (!prefix) return dup_text(S.vcf_header(S.prefixes, with_date != 0) + S.vcf_records(chunk, nullptr), len);
-		std::set<pv::u32> only = pvh::refs_in_sample(S.g, prefix);
-		return dup_text(S.vcf_header({std::string(prefix)}, with_date != 0) + S.vcf_records(chunk, &only), len);
+		PV_SET_DEVICE(s->x);
+		std::string header; pv::TextOut body;
+		vcf_parts(s->s, chunk, with_date, prefix, header, body);
+		char *p = (char *)malloc(header.size() + body.text.size() + 1);
+		if (!p) return nullptr;
+		memcpy(p, header.data(), header.size()); memcpy(p + header.size(), body.text.data(), body.text.size()); p[header.size() + body.text.size()] = 0;
+		if (len) *len = header.size() + body.text.size();
+		return p;
 	} catch (std::exception &e) { s->x->err = e.what(); return nullptr; }
+}
+int pvgpu_session_vcf_write(const pvgpu_session *s, size_t chunk, int with_date, const char *prefix, int fd, uint64_t *bytes) {
+	PV_TRY(s->x, {
+		std::string header; pv::TextOut body;
+		vcf_parts(s->s, chunk, with_date, prefix, header, body);
+		auto put = [&](const char *p, size_t n) { while (n) { ssize_t w = write(fd, p, n); if (w < 0) { if (errno == EINTR) continue; throw std::runtime_error(std::string("write failed: ") + strerror(errno)); } p += w; n -= (size_t)w; } };
+		put(header.data(), header.size()); put(body.text.data(), body.text.size());
+		if (bytes) *bytes = header.size() + body.text.size();
+	})
 }
 int pvgpu_session_shard(pvgpu_session *s, uint32_t rank, uint32_t world, uint32_t *n_total) {
 	PV_TRY(s->x, { s->s.shard(rank, world); if (n_total) *n_total = s->s.n_comp_total; })
@@ -307,12 +361,17 @@ void pvgpu_session_tree_regions(const pvgpu_session *s, uint32_t *comp_id, uint6
 }
 char *pvgpu_session_record_lines(const pvgpu_session *s, size_t *len, uint64_t **line_off, uint32_t **keys, size_t *n) {
 	try {
-		std::string text; std::vector<uint64_t> off; std::vector<uint32_t> k;
-		s->s.record_lines(text, off, k);
-		*n = off.size() - 1;
-		*line_off = (uint64_t *)malloc(off.size() * 8); memcpy(*line_off, off.data(), off.size() * 8);
+		PV_SET_DEVICE(s->x);
+		pv::TextOut body; std::vector<uint32_t> k;
+		s->s.record_lines(body, k);
+		*n = body.n;
+		*line_off = (uint64_t *)malloc(body.lineOff.size() * 8); memcpy(*line_off, body.lineOff.data(), body.lineOff.size() * 8);
 		*keys = (uint32_t *)malloc(k.size() * 4 + 4); if (!k.empty()) memcpy(*keys, k.data(), k.size() * 4);
-		return dup_text(text, len);
+		char *p = (char *)malloc(body.text.size() + 1);
+		if (!p) return nullptr;
+		memcpy(p, body.text.data(), body.text.size()); p[body.text.size()] = 0;
+		if (len) *len = body.text.size();
+		return p;
 	} catch (std::exception &e) { s->x->err = e.what(); return nullptr; }
 }
 void pvgpu_free(void *p) { free(p); }

@@ -7,8 +7,10 @@
 #pragma once
 #include <chrono>
 #include <dirent.h>
+#include <array>
 #include <fstream>
-#include "pv_call.cuh"
+#include <type_traits>
+#include "pv_text.cuh"
 #include "pv_host.hpp"
 
 namespace pve {
@@ -46,7 +48,7 @@ struct Session {
 		pinned.clear();
 	}
 
-	void load_gfa(const std::string &fp, bool labels, bool refs) { unpin(); g = pvh::load_gfa(fp, labels, refs); pin(); }
+	void load_gfa(const std::string &fp, bool labels, bool refs) { unpin(); g = pvh::load_gfa(fp, labels, refs); pin(); tt = pv::TextTables(); }
 
 	// raw arrays resident in HBM: edge ports, packed steps, segment lengths
 	pv::Buf<u32> d_steps, d_segLen; bool raw_paths_up = false;
@@ -155,7 +157,7 @@ struct Session {
 		unpin(); drop_device();
 		g = std::move(n);
 		pin();
-		forest_ready = false; sharded = true;
+		forest_ready = false; sharded = true; tt = pv::TextTables(); gm_ready = false;
 	}
 
 	// decompose: flubbles + PVST of every component with >= 3 vertices (decompose.cpp:129-142)
@@ -273,28 +275,78 @@ struct Session {
 		for (size_t r = 0; r < rec.n_regions; r++) n[tree_of_flubble(rec.rov_fl[r])]++;
 		return n;
 	}
-	void record_lines(std::string &text, std::vector<u64> &off, std::vector<u32> &keys) const {
+	// ---- VCF text on the device (pv_text.cuh).  The graph-dependent tables (segment ids, sequences, path names, the
+	// genotype column layout per component) are uploaded once per loaded graph; forest + records travel per request.
+	mutable pv::TextTables tt;
+	void build_text_tables() const {
+		if (tt.ready) return;
+		if (!g.has_labels) throw std::runtime_error("VCF text needs the segment sequences (session opened without labels)");
+		if (!paths_up) throw std::runtime_error("VCF text needs the path index (run call first)");
+		pv::Ctx &cx = *c;
+		auto up32 = [&](pv::Buf<u32> &b, const std::vector<u32> &h) { b = pv::Buf<u32>(cx, h.size() ? h.size() : 1); cx.h2d(b.p, h.data(), h.size() * 4); };
+		up32(tt.ids, g.ids);
+		tt.lblOff = pv::Buf<u64>(cx, g.lblOff.size()); cx.h2d(tt.lblOff.p, g.lblOff.data(), g.lblOff.size() * 8);
+		tt.lbl = pv::Buf<u8>(cx, g.lbl.size() ? g.lbl.size() : 1); cx.h2d(tt.lbl.p, g.lbl.data(), g.lbl.size());
+		std::vector<u32> tagOff(1, 0); std::string tags;
+		for (auto &p : g.paths) { tags += p.tag; tagOff.push_back((u32)tags.size()); }
+		up32(tt.tagOff, tagOff);
+		tt.tags = pv::Buf<u8>(cx, tags.size() ? tags.size() : 1); cx.h2d(tt.tags.p, tags.data(), tags.size());
+		up32(tt.ploidy, gm.ploidy);
+		tt.nCols = (u32)gm.ploidy.size();
+		// per component: (column, phase, local path) of its paths, sorted by (column, phase) -- the merge order of the GT writer
+		std::vector<u32> ceOff(1, 0), ceCol, cePhase, ceLocal;
+		for (size_t k = 0; k + 1 < dg.cpOff.size(); k++) {
+			std::vector<std::array<u32, 3>> e;
+			for (u32 j = dg.cpOff[k]; j < dg.cpOff[k + 1]; j++) { u32 h = dg.cpList[j]; if (gm.col[h] != pvh::NONE32) e.push_back({gm.col[h], gm.phase[h], j - dg.cpOff[k]}); }
+			std::sort(e.begin(), e.end());
+			for (auto &x : e) { ceCol.push_back(x[0]); cePhase.push_back(x[1]); ceLocal.push_back(x[2]); }
+			ceOff.push_back((u32)ceCol.size());
+		}
+		up32(tt.ceOff, ceOff); up32(tt.ceCol, ceCol); up32(tt.cePhase, cePhase); up32(tt.ceLocal, ceLocal);
+		cx.sync();   // the host staging vectors die here
+		tt.ready = true;
+	}
+	// records of the last call as text, in the reference's order; only_refs = nullptr: every record
+	void vcf_records_device(size_t chunk_size, const std::set<u32> *only_refs, pv::TextOut &out) const {
+		out.n = rec.n(); out.text.clear(); out.lineOff.assign(rec.n() + 1, 0);
+		if (!rec.n()) return;
+		if (!gm_ready) throw std::runtime_error("VCF text: no reference prefixes set");
+		build_text_tables();
+		pv::Ctx &cx = *c;
+		pv::Trace tr(cx, "text");
+		const size_t n = rec.n(), nFl = forest.n();
+		auto upv = [&](auto &buf, const auto &h, size_t cnt) { typedef typename std::remove_reference<decltype(*buf.p)>::type T; buf = pv::Buf<T>(cx, cnt ? cnt : 1); cx.h2d(buf.p, h.data(), cnt * sizeof(T)); };
+		pv::Buf<u32> fa, fz, fh, rovFl, rovComp, rovTang, cpOff, rRov, rRef, rL, rR, rVt, rPos, rRS, rRL, rGrp, gHap, gStart, gLen, gCnt;
+		pv::Buf<u8> faf, fzf; pv::Buf<u64> rGt; pv::Buf<pv::u16> gt;
+		upv(fa, forest.a_v, nFl); upv(fz, forest.z_v, nFl); upv(fh, forest.height, nFl); upv(faf, forest.a_fwd, nFl); upv(fzf, forest.z_fwd, nFl);
+		upv(rovFl, rec.rov_fl, rec.rov_fl.size()); upv(rovComp, rec.rov_comp, rec.rov_comp.size()); upv(rovTang, rec.rov_tangled, rec.rov_tangled.size());
+		upv(cpOff, rec.cpOff, rec.cpOff.size());
+		upv(rRov, rec.rec_rov, n); upv(rRef, rec.rec_ref, n); upv(rL, rec.rec_cxtL, n); upv(rR, rec.rec_cxtR, n); upv(rVt, rec.rec_vt, n); upv(rPos, rec.rec_pos, n);
+		upv(rRS, rec.rec_refStart, n); upv(rRL, rec.rec_refLen, n); upv(rGrp, rec.rec_grpOff, n + 1); upv(rGt, rec.rec_gtOff, n + 1);
+		upv(gHap, rec.grp_hap, rec.grp_hap.size()); upv(gStart, rec.grp_start, rec.grp_start.size()); upv(gLen, rec.grp_len, rec.grp_len.size()); upv(gCnt, rec.grp_count, rec.grp_count.size());
+		upv(gt, rec.gt, rec.gt.size());
+		pv::TextView t{tt.ids.p, dg.segLen.p, dg.steps.p, dg.stepOff.p, tt.lblOff.p, tt.lbl.p, tt.tagOff.p, tt.tags.p, tt.ploidy.p, tt.nCols,
+			       tt.ceOff.p, tt.ceCol.p, tt.cePhase.p, tt.ceLocal.p, fa.p, fz.p, fh.p, faf.p, fzf.p, rovFl.p, rovComp.p, rovTang.p, cpOff.p,
+			       rRov.p, rRef.p, rL.p, rR.p, rVt.p, rPos.p, rRS.p, rRL.p, rGrp.p, rGt.p, gHap.p, gStart.p, gLen.p, gCnt.p, gt.p};
+		std::vector<u8> keep;
+		if (only_refs) { keep.assign(g.H(), 0); for (u32 r : *only_refs) if (r < g.H()) keep[r] = 1; }
+		tr.mark("upload records");
+		pv::records_text_device(cx, t, n, rec.n_regions, chunk_size, g.H(), only_refs ? keep.data() : nullptr, out);
+		tr.mark("text kernels + d2h");
+	}
+	// for the multi-GPU merge: every record as a text line plus (component id, ordinal of its region inside that
+	// component, ref path id); lines are in (ref, region, context) order.
+	void record_lines(pv::TextOut &out, std::vector<u32> &keys) const {
 		std::vector<u64> per = regions_per_tree(), first(per.size() + 1, 0);
 		for (size_t t = 0; t < per.size(); t++) first[t + 1] = first[t] + per[t];
-		std::vector<std::string> slots(gm.nSlots);
-		text.clear(); off.assign(1, 0); keys.clear();
-		for (size_t i : pvh::record_order(rec, ~(size_t)0)) {
-			pvh::record_text(g, gm, forest, rec, i, slots, text);
-			off.push_back(text.size());
+		vcf_records_device(~(size_t)0, nullptr, out);
+		keys.clear();
+		for (size_t i : pvh::record_order(rec, ~(size_t)0)) {   // same keys, same stable order as the device permutation
 			u32 r = rec.rec_rov[i];
 			if (r >= rec.n_regions) { keys.push_back(pvh::NONE32); keys.push_back(0); keys.push_back(rec.rec_ref[i]); continue; }   // SUBR: final chunk
 			u32 t = tree_of_flubble(rec.rov_fl[r]);
 			keys.push_back(forest.comp_id[t]); keys.push_back((u32)(r - first[t])); keys.push_back(rec.rec_ref[i]);
 		}
-	}
-	std::string vcf_records(size_t chunk_size, const std::set<u32> *only_refs) const {
-		std::string o;
-		std::vector<std::string> slots(gm.nSlots);
-		for (size_t i : pvh::record_order(rec, chunk_size)) {
-			if (only_refs && !only_refs->count(rec.rec_ref[i])) continue;
-			pvh::record_text(g, gm, forest, rec, i, slots, o);
-		}
-		return o;
 	}
 };
 

@@ -218,7 +218,10 @@ PovuVcfOutput *povu_flubbles_call_variants(PovuFlubbles *f, PovuError *error) {
 		s.call();
 		if (s.rec.n_hard_errors) throw std::runtime_error("call: the reference aborts on this input (missing context boundary in a haplotype lap)");
 		PovuVcfOutput *o = new PovuVcfOutput();
-		o->vcf_content = s.vcf_header(s.prefixes, true) + s.vcf_records(100, nullptr);
+		pv::TextOut body;
+		s.vcf_records_device(100, nullptr, body);
+		o->vcf_content = s.vcf_header(s.prefixes, true);
+		o->vcf_content.append(body.text.data(), body.text.size());
 		return o;
 	} catch (std::exception &e) { ffi_set_error(error, 1, e.what()); return nullptr; }
 }

@@ -391,88 +391,8 @@ inline std::string vcf_col_header(const GtMeta &gm) {
 	return o + "\n";
 }
 
-inline char comp_base(char c) { switch (c) { case 'A': return 'T'; case 'T': return 'A'; case 'C': return 'G'; case 'G': return 'C'; case 'a': return 't'; case 't': return 'a'; case 'c': return 'g'; case 'g': return 'c'; default: return c; } }
-inline void append_step_label(const HostGraph &g, u32 step, std::string &o) {   // utils.cpp:14-45 for '<'
-	u32 v = step >> 1; const char *l = g.label(v); u32 n = g.segLen[v];
-	if (!(step & 1u)) o.append(l, n);
-	else for (u32 i = n; i-- > 0;) o += comp_base(l[i]);
-}
-inline void append_step_str(const HostGraph &g, u32 step, std::string &o) {
-	char b[16]; int n = snprintf(b, sizeof b, "%c%u", (step & 1u) ? '<' : '>', g.ids[step >> 1]); o.append(b, (size_t)n);
-}
-enum { VT_DEL = 0, VT_INS = 1, VT_SUB = 2, VT_SUBR = 3 };
-// hap_slice::as_str / as_dna_str (allele.hpp:134-209); start = step index inside path `hap`
-inline void slice_str(const HostGraph &g, u32 hap, u32 start, u32 len, u32 vt, std::string &o) {
-	u32 i = g.stepOff[hap] + start, N = i + len;
-	if (vt == VT_SUB) { i++; N--; } else if (vt == VT_INS || vt == VT_DEL) N--;
-	for (; i < N; i++) append_step_str(g, g.steps[i], o);
-}
-inline void slice_dna(const HostGraph &g, u32 hap, u32 start, u32 len, u32 vt, std::string &o) {
-	u32 i = g.stepOff[hap] + start, N = i + len;
-	if (vt == VT_INS || vt == VT_DEL) { u32 s = g.steps[i]; u32 v = s >> 1; u32 n = g.segLen[v]; o += !(s & 1u) ? g.label(v)[n - 1] : comp_base(g.label(v)[0]); }
-	if (vt != VT_SUBR) { i++; N--; }
-	for (; i < N; i++) append_step_label(g, g.steps[i], o);
-}
-// fmt "{:.1f}" of double(ac)/double(an) (vcf.hpp:310-332): correctly rounded shortest-decimal, ties on the binary value
-inline void append_af(u32 ac, u32 an, std::string &o) { char b[64]; int n = snprintf(b, sizeof b, "%.1f", (double)ac / (double)an); o.append(b, (size_t)n); }
-
-// Binary records as produced by the device (pv_call.cuh)
+// Binary records as produced by the device (pv_call.cuh); their VCF text is written on the device (pv_text.cuh)
 typedef pv::Records Records;
-
-inline void record_text(const HostGraph &g, const GtMeta &gm, const Forest &F, const Records &R, size_t i, std::vector<std::string> &slots, std::string &o) {
-	const u32 vt = R.rec_vt[i], ref = R.rec_ref[i], fl = R.rov_fl[R.rec_rov[i]];
-	const u32 g0 = R.rec_grpOff[i], g1 = R.rec_grpOff[i + 1];
-	const u32 comp = R.rov_comp[R.rec_rov[i]];
-	const u32 *haps = R.cpList.data() + R.cpOff[comp]; const u32 nh = R.cpOff[comp + 1] - R.cpOff[comp];
-	const u16 *gt = R.gt.data() + R.rec_gtOff[i];
-	u32 nref = 0;
-	for (u32 k = 0; k < nh; k++) if (gt[k] == 0) nref++;
-	u32 an = nref;
-	for (u32 k = g0; k < g1; k++) an += R.grp_count[k];
-	char b[64];
-	o += g.paths[ref].tag; o += '\t';
-	o.append(b, (size_t)snprintf(b, sizeof b, "%u", R.rec_pos[i])); o += '\t';
-	append_step_str(g, R.rec_cxtL[i], o); append_step_str(g, R.rec_cxtR[i], o); o += '\t';
-	slice_dna(g, ref, R.rec_refStart[i], R.rec_refLen[i], vt, o); o += '\t';
-	for (u32 k = g0; k < g1; k++) { if (k > g0) o += ','; slice_dna(g, R.grp_hap[k], R.grp_start[k], R.grp_len[k], vt, o); }
-	o += "\t60\tPASS\tAC=";
-	for (u32 k = g0; k < g1; k++) { if (k > g0) o += ','; o.append(b, (size_t)snprintf(b, sizeof b, "%u", R.grp_count[k])); }
-	o += ";AF=";
-	for (u32 k = g0; k < g1; k++) { if (k > g0) o += ','; append_af(R.grp_count[k], an, o); }
-	// NS = genotype columns with data; GT slots filled in the reference's order: ref matches, then alt groups (vcf.cpp:51-84)
-	for (auto &s : slots) s.clear();
-	std::vector<char> has(gm.ploidy.size(), 0);
-	auto put = [&](u32 h, u32 code) {
-		u32 c = gm.col[h], p = gm.phase[h];
-		if (c == NONE32) return;
-		has[c] = 1;
-		if (p < gm.ploidy[c]) { std::string &s = slots[gm.colOff[c] + p]; s.assign(b, (size_t)snprintf(b, sizeof b, "%u", code)); }   // hap id 0 / gaps: out-of-range write (UB) in the reference
-	};
-	for (u32 k = 0; k < nh; k++) if (gt[k] == 0) put(haps[k], 0);
-	for (u32 a = 1; a <= g1 - g0; a++) for (u32 k = 0; k < nh; k++) if (gt[k] == a) put(haps[k], a);
-	u32 ns = 0; for (char x : has) ns += x;
-	o += ";AN="; o.append(b, (size_t)snprintf(b, sizeof b, "%u", an));
-	o += ";NS="; o.append(b, (size_t)snprintf(b, sizeof b, "%u", ns));
-	o += ";AT="; slice_str(g, ref, R.rec_refStart[i], R.rec_refLen[i], vt, o);
-	o += ',';
-	for (u32 k = g0; k < g1; k++) { if (k > g0) o += ','; slice_str(g, R.grp_hap[k], R.grp_start[k], R.grp_len[k], vt, o); }
-	static const char *VT[] = {"DEL", "INS", "SUB", "SUBR"};
-	o += ";VARTYPE="; o += VT[vt];
-	o += ";TANGLED="; o += R.rov_tangled[R.rec_rov[i]] ? 'T' : 'F';
-	if (vt != VT_SUBR) {
-		o += ";ES="; o += flubble_label(g, F.a_v[fl], F.a_fwd[fl], F.z_v[fl], F.z_fwd[fl]);
-		o += ";LV="; o.append(b, (size_t)snprintf(b, sizeof b, "%u", F.height[fl] - 1));
-	}
-	o += "\tGT\t";
-	for (size_t c = 0; c < gm.ploidy.size(); c++) {
-		if (c) o += '\t';
-		bool all_missing = true;
-		for (u32 p = 0; p < gm.ploidy[c]; p++) if (!slots[gm.colOff[c] + p].empty()) all_missing = false;
-		if (all_missing) { o += '.'; continue; }
-		for (u32 p = 0; p < gm.ploidy[c]; p++) { if (p) o += '|'; const std::string &s = slots[gm.colOff[c] + p]; if (s.empty()) o += '.'; else o += s; }
-	}
-	o += '\n';
-}
 
 // Record order of the reference (genomics.cpp:114-156, to_vcf.cpp:121-139): chunks of `chunk_size` regions,
 // inside a chunk grouped by ref path id ascending, then region order, then context / INS,SUB,DEL order.
