@@ -334,21 +334,23 @@ static void vcf_parts(const pve::Session &S, size_t chunk, int with_date, const 
 char *pvgpu_session_vcf_text(const pvgpu_session *s, size_t chunk, int with_date, const char *prefix, size_t *len) {
 	try {
 		PV_SET_DEVICE(s->x);
-		std::string header; pv::TextOut body;
+		std::string header; pv::TextOut &body = s->s.text_buf;   // page-locked, capacity reused across calls
 		vcf_parts(s->s, chunk, with_date, prefix, header, body);
 		char *p = (char *)malloc(header.size() + body.text.size() + 1);
 		if (!p) return nullptr;
-		memcpy(p, header.data(), header.size()); memcpy(p + header.size(), body.text.data(), body.text.size()); p[header.size() + body.text.size()] = 0;
+		memcpy(p, header.data(), header.size());
+		if (!body.text.empty()) memcpy(p + header.size(), body.text.data(), body.text.size());   // (memcpy from a null pointer, even of 0 bytes, lets the compiler assume non-null)
+		p[header.size() + body.text.size()] = 0;
 		if (len) *len = header.size() + body.text.size();
 		return p;
 	} catch (std::exception &e) { s->x->err = e.what(); return nullptr; }
 }
 int pvgpu_session_vcf_write(const pvgpu_session *s, size_t chunk, int with_date, const char *prefix, int fd, uint64_t *bytes) {
 	PV_TRY(s->x, {
-		std::string header; pv::TextOut body;
+		std::string header; pv::TextOut &body = s->s.text_buf;
 		vcf_parts(s->s, chunk, with_date, prefix, header, body);
 		auto put = [&](const char *p, size_t n) { while (n) { ssize_t w = write(fd, p, n); if (w < 0) { if (errno == EINTR) continue; throw std::runtime_error(std::string("write failed: ") + strerror(errno)); } p += w; n -= (size_t)w; } };
-		put(header.data(), header.size()); put(body.text.data(), body.text.size());
+		put(header.data(), header.size()); if (!body.text.empty()) put(body.text.data(), body.text.size());
 		if (bytes) *bytes = header.size() + body.text.size();
 	})
 }
@@ -362,14 +364,15 @@ void pvgpu_session_tree_regions(const pvgpu_session *s, uint32_t *comp_id, uint6
 char *pvgpu_session_record_lines(const pvgpu_session *s, size_t *len, uint64_t **line_off, uint32_t **keys, size_t *n) {
 	try {
 		PV_SET_DEVICE(s->x);
-		pv::TextOut body; std::vector<uint32_t> k;
+		pv::TextOut &body = s->s.text_buf; std::vector<uint32_t> k;
 		s->s.record_lines(body, k);
 		*n = body.n;
 		*line_off = (uint64_t *)malloc(body.lineOff.size() * 8); memcpy(*line_off, body.lineOff.data(), body.lineOff.size() * 8);
 		*keys = (uint32_t *)malloc(k.size() * 4 + 4); if (!k.empty()) memcpy(*keys, k.data(), k.size() * 4);
 		char *p = (char *)malloc(body.text.size() + 1);
 		if (!p) return nullptr;
-		memcpy(p, body.text.data(), body.text.size()); p[body.text.size()] = 0;
+		if (!body.text.empty()) memcpy(p, body.text.data(), body.text.size());
+		p[body.text.size()] = 0;
 		if (len) *len = body.text.size();
 		return p;
 	} catch (std::exception &e) { s->x->err = e.what(); return nullptr; }

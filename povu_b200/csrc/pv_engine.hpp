@@ -278,6 +278,7 @@ struct Session {
 	// ---- VCF text on the device (pv_text.cuh).  The graph-dependent tables (segment ids, sequences, path names, the
 	// genotype column layout per component) are uploaded once per loaded graph; forest + records travel per request.
 	mutable pv::TextTables tt;
+	mutable pv::TextOut text_buf;   // where the device text lands (page-locked; the allocation survives across requests)
 	void build_text_tables() const {
 		if (tt.ready) return;
 		if (!g.has_labels) throw std::runtime_error("VCF text needs the segment sequences (session opened without labels)");
@@ -308,7 +309,7 @@ struct Session {
 	}
 	// records of the last call as text, in the reference's order; only_refs = nullptr: every record
 	void vcf_records_device(size_t chunk_size, const std::set<u32> *only_refs, pv::TextOut &out) const {
-		out.n = rec.n(); out.text.clear(); out.lineOff.assign(rec.n() + 1, 0);
+		out.n = rec.n(); out.text.clear(); out.lineOff.assign(1, 0);
 		if (!rec.n()) return;
 		if (!gm_ready) throw std::runtime_error("VCF text: no reference prefixes set");
 		build_text_tables();

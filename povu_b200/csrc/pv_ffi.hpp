@@ -221,7 +221,7 @@ PovuVcfOutput *povu_flubbles_call_variants(PovuFlubbles *f, PovuError *error) {
 		pv::TextOut body;
 		s.vcf_records_device(100, nullptr, body);
 		o->vcf_content = s.vcf_header(s.prefixes, true);
-		o->vcf_content.append(body.text.data(), body.text.size());
+		if (!body.text.empty()) o->vcf_content.append(body.text.data(), body.text.size());
 		return o;
 	} catch (std::exception &e) { ffi_set_error(error, 1, e.what()); return nullptr; }
 }

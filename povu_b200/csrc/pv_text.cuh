@@ -227,8 +227,8 @@ inline void record_order_device(Ctx &c, const u32 *rec_rov, const u32 *rec_ref, 
 
 // text of the records selected by keepRef (per ref path id: 1 = print; nullptr = all), in the reference's order
 inline void records_text_device(Ctx &c, const TextView &t, size_t n, u64 n_regions, size_t chunk_size, u32 H, const u8 *keepRef /*host, H entries*/, TextOut &out) {
-	out.n = n; out.text.clear(); out.lineOff.assign(n + 1, 0);
-	if (!n) return;
+	out.n = n; out.text.clear(); out.lineOff.clear(); out.lineOff.resize(n + 1);
+	if (!n) { out.lineOff[0] = 0; return; }
 	Buf<u32> perm;
 	record_order_device(c, t.rec_rov, t.rec_ref, n, n_regions, chunk_size, H, perm);
 	Buf<u8> keep(c, H ? H : 1);
