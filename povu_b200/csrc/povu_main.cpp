@@ -138,7 +138,7 @@ static void write_vcfs(const Config &c, Dev &d, const std::vector<std::string> &
 	uint64_t st[12];
 	pvgpu_session_call_stats(d.s, st);
 	if (st[5]) throw Fail{"call: the reference aborts on this input (missing context boundary in a haplotype lap)"};
-	if (st[4]) fprintf(stderr, "WARN [povu_b200::call] %llu regions need the haplotype-lap vertex order (graph.cpp:194-395), which is not on the device yet: skipped\n", (unsigned long long)st[4]);
+	if (st[4]) fprintf(stderr, "WARN [povu_b200::call] %llu regions have no vertex order (BFS sort and haplotype-lap order both empty): skipped\n", (unsigned long long)st[4]);
 	if (st[10]) fprintf(stderr, "WARN [povu_b200::call] %llu SUBR records had a merged length past the end of a walk (undefined in the reference): clamped\n", (unsigned long long)st[10]);
 	const bool to_stdout = !c.have_out || c.stdout_vcf;
 	if (to_stdout) {

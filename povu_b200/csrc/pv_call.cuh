@@ -295,9 +295,117 @@ PV_DEV u32 bfs_kahn_sort(const GraphView &g, u32 a_v, u32 a_fwd, u32 z_v, u32 z_
 }
 
 // ---------------------------------------------------------------------------------------------
+// fallback vertex order when the BFS/Kahn sort meets a cycle: the reference's haplotype-lap order
+// (find_laps + gen_sort, graph.cpp:165-395).  Inherently sequential (every lap is inserted into the list the
+// earlier laps built), so one thread replays it per failed region; such regions are rare (a repeat unit of two
+// or more vertices inside a bubble).  Scratch: a doubly linked list in arrays + an open-addressing table
+// vertex -> {list node, left / right context of the current lap}.
+// ---------------------------------------------------------------------------------------------
+PV_KERNEL(G_count, 64);
+PV_KERNEL(G_sort, 256);
+struct GsScratch {
+	u32 cap, hcap;
+	u32 *val, *nxt, *prv;                         // [cap]  list nodes
+	u32 *hkey, *hnode, *hlE, *hlV, *hrE, *hrV;   // [hcap] vertex -> node, lap-stamped contexts
+};
+static const u32 GS_CRASH = 0xFFFFFFFEu;   // the reference dereferences an empty optional / map::at throws / reads v_ids[-1] here
+
+// i-th lap of path h between the i-th visits of u and v: [start, start + len) in global step indices
+struct GsLaps {
+	u32 loU, loV, n;
+	PV_DEV GsLaps(const GraphView &g, u32 u, u32 v, u32 h) {
+		u32 s0 = g.stepOff[h], s1 = g.stepOff[h + 1];
+		u32 ua = g.vsOff[u], ub = g.vsOff[u + 1], va = g.vsOff[v], vb = g.vsOff[v + 1];
+		loU = lb_u32(g.vsStep, ua, ub, s0); u32 hiU = lb_u32(g.vsStep, ua, ub, s1);
+		loV = lb_u32(g.vsStep, va, vb, s0); u32 hiV = lb_u32(g.vsStep, va, vb, s1);
+		u32 nu = hiU - loU, nv = hiV - loV;
+		n = nu < nv ? nu : nv;
+	}
+	PV_DEV void lap(const GraphView &g, u32 i, u32 &start, u32 &len) const {
+		u32 s = g.vsStep[loU + i], e = g.vsStep[loV + i];
+		if (s > e) { u32 t = s; s = e; e = t; }
+		start = s; len = e - s + 1;
+	}
+};
+PV_DEV u32 gs_slot(const GsScratch &s, u32 v) {
+	u32 m = s.hcap - 1, i = (u32)(splitmix64(v) & m);
+	while (true) {
+		u32 k = s.hkey[i];
+		if (k == v) return i;
+		if (k == NONE) { s.hkey[i] = v; s.hnode[i] = NONE; s.hlE[i] = 0; s.hrE[i] = 0; return i; }
+		i = (i + 1) & m;
+	}
+}
+// returns the list length (the order in out[]), 0 for an empty list, GS_CRASH where the reference has undefined behaviour
+PV_DEV u32 gen_sort_laps(const GraphView &g, u32 a_v, u32 z_v, const GsScratch &s, u32 *out) {
+	for (u32 i = 0; i < s.hcap; i++) s.hkey[i] = NONE;
+	u32 n = 0, head = NONE, tail = NONE, epoch = 0;
+	for (u32 h = 0; h < g.H; h++) {
+		GsLaps L(g, a_v, z_v, h);
+		for (u32 li = 0; li < L.n; li++) {
+			u32 start, len; L.lap(g, li, start, len);
+			if (n == 0) {   // first lap: the list is the lap's vertices in first-visit order (graph.cpp:282-296)
+				for (u32 j = start; j < start + len; j++) {
+					u32 sl = gs_slot(s, g.steps[j] >> 1);
+					if (s.hnode[sl] != NONE) continue;
+					s.val[n] = g.steps[j] >> 1; s.nxt[n] = NONE; s.prv[n] = tail;
+					if (tail != NONE) s.nxt[tail] = n; else head = n;
+					tail = n; s.hnode[sl] = n; n++;
+				}
+				continue;
+			}
+			if (start == g.stepOff[h]) return GS_CRASH;   // `for (j = start + len - 1; j >= start; j--)` with u32 j and start == 0
+			epoch++;
+			u32 x = NONE;
+			for (u32 j = start; j < start + len; j++) {   // left contexts (graph.cpp:246-262)
+				u32 sl = gs_slot(s, g.steps[j] >> 1);
+				if (s.hlE[sl] == epoch) continue;
+				if (s.hnode[sl] != NONE) { s.hlE[sl] = epoch; s.hlV[sl] = s.hnode[sl]; }
+				else if (j > start) {
+					u32 ps = gs_slot(s, g.steps[j - 1] >> 1);
+					if (s.hnode[ps] != NONE) x = s.hnode[ps];
+					if (x == NONE) return GS_CRASH;
+					s.hlE[sl] = epoch; s.hlV[sl] = x;
+				}
+			}
+			u32 y = NONE;
+			for (u32 j = start + len - 1;; j--) {   // right contexts (graph.cpp:264-280)
+				u32 sl = gs_slot(s, g.steps[j] >> 1);
+				if (s.hrE[sl] != epoch) {
+					if (s.hnode[sl] != NONE) { s.hrE[sl] = epoch; s.hrV[sl] = s.hnode[sl]; }
+					else if (j + 1 < start + len) {
+						u32 ns = gs_slot(s, g.steps[j + 1] >> 1);
+						if (s.hnode[ns] != NONE) y = s.hnode[ns];
+						if (y == NONE) return GS_CRASH;
+						s.hrE[sl] = epoch; s.hrV[sl] = y;
+					}
+				}
+				if (j == start) break;
+			}
+			for (u32 j = start; j < start + len; j++) {   // insert the new vertices (graph.cpp:336-372)
+				u32 sl = gs_slot(s, g.steps[j] >> 1);
+				if (s.hnode[sl] != NONE) continue;
+				if (s.hlE[sl] != epoch || s.hrE[sl] != epoch) return GS_CRASH;   // map::at on a vertex without a context
+				u32 l = s.hlV[sl], r = s.hrV[sl];
+				u32 ip = l;
+				if (l != r) { u32 q = head; while (q != l && q != r) q = s.nxt[q]; if (q == l) ip = r; }   // distance(l) < distance(r) ? r : l
+				if (n >= s.cap) return GS_CRASH;   // cannot happen: cap counts every lap step
+				u32 p = s.prv[ip];
+				s.val[n] = g.steps[j] >> 1; s.nxt[n] = ip; s.prv[n] = p; s.prv[ip] = n;
+				if (p != NONE) s.nxt[p] = n; else head = n;
+				s.hnode[sl] = n; n++;
+			}
+		}
+	}
+	u32 k = 0;
+	for (u32 q = head; q != NONE; q = s.nxt[q]) out[k++] = s.val[q];
+	return n;
+}
+
+// ---------------------------------------------------------------------------------------------
 // results
 // ---------------------------------------------------------------------------------------------
-struct CallIn {            // PVST forest, flubbles of all components concatenated (host arrays)
+struct CallIn {           // PVST forest, flubbles of all components concatenated (host arrays)
 	u32 nFl = 0;
 	const u32 *a_v = nullptr, *z_v = nullptr; const u8 *a_fwd = nullptr, *z_fwd = nullptr;
 	const u32 *parent = nullptr;   // PVST idx inside the component (0 = dummy root; flubble k of the component is k+1)
@@ -1197,6 +1305,7 @@ inline void call_device(Ctx &c, const DevGraph &G, const CallIn &in, const CallO
 		u32 n = bfs_kahn_sort(g, fa_[f] >> 1, !(fa_[f] & 1u), fz_[f] >> 1, !(fz_[f] & 1u), s, ov);
 		J0_[r] = n;
 		if (n == NONE) { atomic_add(cnt_ + 0, 1u); return; }
+		if (n == 0) atomic_add(cnt_ + 3, 1u);
 		for (u32 k = 0; k < n; k++) vtmp_[r * 12 + k] = ov[k];
 	});
 	u32 hc[8]; c.d2h(hc, cnt.p, 32);
@@ -1240,6 +1349,7 @@ inline void call_device(Ctx &c, const DevGraph &G, const CallIn &in, const CallO
 					u32 r = list_[i]; u32 f = rov0_[r];
 					u32 n = bfs_kahn_sort(g, fa_[f] >> 1, !(fa_[f] & 1u), fz_[f] >> 1, !(fz_[f] & 1u), s, base + ovOff);
 					res_[i] = n;
+					if (n == 0) atomic_add(cnt_ + 3, 1u);
 					if (n != NONE) { J0_[r] = n; bigSlice_[r] = sliceIdx; bigSlot_[r] = (u32)i; }
 				});
 				std::vector<u32> hres = rs.to_host();
@@ -1252,10 +1362,53 @@ inline void call_device(Ctx &c, const DevGraph &G, const CallIn &in, const CallO
 	}
 	Buf<u64> sliceTabD(c, sliceTab.size() ? sliceTab.size() : 1);
 	c.h2d(sliceTabD.p, sliceTab.data(), sliceTab.size() * 8);
-	c.sync();
+	c.d2h(hc, cnt.p, 32);
 	tr.mark("C2 bfs");
-	// keep regions with >= 3 sorted vertices (rov.cpp:208-212); a failed sort (0) needs the reference's
-	// haplotype-lap fallback order (graph.cpp:194-395), which is not on the device yet -> counted, skipped
+	// regions whose BFS/Kahn sort failed (a cycle inside the region): the reference's haplotype-lap order
+	// (graph.cpp:194-395), one thread per region over an arena sized by the region's total lap length
+	Buf<u32> gsArena, gsSrc(c, hc[3] ? R0 : 1);
+	Buf<u64> gsMeta;
+	const bool haveGs = hc[3] != 0;
+	if (haveGs) {
+		gsSrc.fill_ff();
+		Buf<u32> failF(c, R0), failList;
+		u32 *failF_ = failF.p;
+		parallel_for<C_keep>(c, R0, PV_LAMBDA(size_t r) { failF_[r] = J0_[r] == 0 ? 1u : 0u; });
+		const u32 nGs = compact_flags(c, failF.p, R0, failList);
+		Buf<u64> capD(c, nGs);
+		u64 *capD_ = capD.p; const u32 *failList_ = failList.p;
+		parallel_for<G_count>(c, nGs, PV_LAMBDA(size_t i) {
+			u32 f = rov0_[failList_[i]]; u64 tot = 0;
+			for (u32 h = 0; h < g.H; h++) { GsLaps L(g, fa_[f] >> 1, fz_[f] >> 1, h); for (u32 li = 0; li < L.n; li++) { u32 st, ln; L.lap(g, li, st, ln); tot += ln; } }
+			capD_[i] = tot;
+		});
+		std::vector<u64> caps = capD.to_host();
+		std::vector<u64> offs(nGs + 1, 0), meta((size_t)nGs * 3);
+		for (u32 i = 0; i < nGs; i++) {
+			u64 cap = std::min<u64>(caps[i], (u64)G.V) + 1;
+			u64 hcap = 2; while (hcap < 2 * cap) hcap <<= 1;
+			meta[3 * (size_t)i] = offs[i]; meta[3 * (size_t)i + 1] = cap; meta[3 * (size_t)i + 2] = hcap;
+			offs[i + 1] = offs[i] + 4 * cap + 6 * hcap;   // out + val + nxt + prv, then the six table columns
+		}
+		if (offs[nGs] > (1ull << 31)) throw std::runtime_error("call: the haplotype-lap vertex order of the cyclic regions needs more than 8 GB of scratch");
+		gsArena = Buf<u32>(c, offs[nGs] ? offs[nGs] : 1);
+		Buf<u64> metaD(c, meta.size() ? meta.size() : 1);
+		c.h2d(metaD.p, meta.data(), meta.size() * 8);
+		u32 *arena_ = gsArena.p, *gsSrc_ = gsSrc.p; const u64 *meta_ = metaD.p;
+		parallel_for<G_sort>(c, nGs, PV_LAMBDA(size_t i) {
+			u32 r = failList_[i]; u32 f = rov0_[r];
+			u32 *b = arena_ + meta_[3 * i]; const u32 cap = (u32)meta_[3 * i + 1], hcap = (u32)meta_[3 * i + 2];
+			u32 *t = b + 4 * (size_t)cap;
+			GsScratch s{cap, hcap, b + cap, b + 2 * (size_t)cap, b + 3 * (size_t)cap, t, t + hcap, t + 2 * (size_t)hcap, t + 3 * (size_t)hcap, t + 4 * (size_t)hcap, t + 5 * (size_t)hcap};
+			u32 n = gen_sort_laps(g, fa_[f] >> 1, fz_[f] >> 1, s, b);
+			if (n == GS_CRASH) { atomic_add(cnt_ + 4, 1u); n = 0; }
+			J0_[r] = n; gsSrc_[r] = (u32)i;
+		});
+		c.sync();   // meta / caps live on the host stack of this block
+		gsMeta = std::move(metaD);
+		tr.mark("C2 lap order");
+	}
+	// keep regions with >= 3 sorted vertices (rov.cpp:208-212); an empty lap order too is skipped there
 	Buf<u32> keepF(c, R0), rovSrc;
 	u32 *keepF_ = keepF.p;
 	parallel_for<C_keep>(c, R0, PV_LAMBDA(size_t r) {
@@ -1264,7 +1417,7 @@ inline void call_device(Ctx &c, const DevGraph &G, const CallIn &in, const CallO
 		if (n == 0) atomic_add(cnt_ + 1, 1u); else if (n < 3) atomic_add(cnt_ + 2, 1u);
 	});
 	const u32 R = compact_flags(c, keepF.p, R0, rovSrc);
-	if (R == 0) { c.d2h(hc, cnt.p, 32); out.n_sort_failed = hc[1]; out.n_too_small = hc[2]; return; }
+	if (R == 0) { c.d2h(hc, cnt.p, 32); out.n_sort_failed = hc[1]; out.n_too_small = hc[2]; out.n_hard_errors = hc[4]; return; }
 	Buf<u32> rovJ(c, (size_t)R + 1), rovOff(c, (size_t)R + 1), rovFl(c, R), rovComp(c, R), rovTangled(c, R);
 	Buf<u64> rowsOf(c, (size_t)R + 1), cellsOf(c, (size_t)R + 1), rowPre(c, (size_t)R + 1), cellPre(c, (size_t)R + 1), tot(c, 4);
 	tot.zero(); rovTangled.zero();
@@ -1295,10 +1448,12 @@ inline void call_device(Ctx &c, const DevGraph &G, const CallIn &in, const CallO
 	u32 *rovVerts_ = rovVerts.p; const u32 *rovOff_ = rovOff.p;
 	{
 		const u32 *bigSlice_ = bigSlice.p, *bigSlot_ = bigSlot.p; const u64 *tab = sliceTabD.p;
+		const u32 *gsSrc_ = gsSrc.p, *gsArena_ = gsArena.p; const u64 *gsMeta_ = gsMeta.p;
 		parallel_for<C_gather>(c, R, PV_LAMBDA(size_t r) {
 			u32 s = rovSrc_[r]; u32 n = rovJ_[r]; u32 o = rovOff_[r];
 			const u32 *src = vtmp_ + (size_t)s * 12;
 			if (haveBig && bigSlice_[s] != NONE) { const u64 *t = tab + 3 * (size_t)bigSlice_[s]; src = (const u32 *)(uintptr_t)t[0] + (size_t)bigSlot_[s] * t[1] + t[2]; }
+			if (haveGs && gsSrc_[s] != NONE) src = gsArena_ + gsMeta_[3 * (size_t)gsSrc_[s]];
 			for (u32 k = 0; k < n; k++) rovVerts_[o + k] = src[k];
 		});
 	}
@@ -1410,7 +1565,7 @@ inline void call_device(Ctx &c, const DevGraph &G, const CallIn &in, const CallO
 	c.d2h(hc, cnt.p, 32);
 	out.n_sort_failed = hc[1]; out.n_too_small = hc[2];
 	u32 he[8]; c.d2h(he, errs.p, 32);
-	out.n_hard_errors = he[0]; out.n_subr_clamped = he[4];
+	out.n_hard_errors = he[0] + hc[4]; out.n_subr_clamped = he[4];
 	if (he[2]) throw std::runtime_error("call: a path visits one vertex more than 65534 times inside a region (u16 depth cell overflow)");
 	for (u32 t : out.rov_tangled) if (t) out.n_tangled++;
 	c.sync();

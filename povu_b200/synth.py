@@ -431,6 +431,50 @@ def repeat_loops(seed, n_units=6, n_paths=6, max_laps=4, first_id=1):
     return make_graph(np.arange(first_id, first_id + len(seqs), dtype=np.uint32), seqs, links, paths)
 
 
+def cyclic_units(seed, n_units=5, n_paths=6, max_laps=3, first_id=1):
+    """Regions whose BFS/Kahn vertex order fails (a cycle strictly inside a bubble), so the reference falls back to
+    its haplotype-lap order (graph.cpp:194-395): units `s -> x1 -> .. -> xk -> t` (k = 2..3) with a back link
+    xk -> x1, an alternative branch `s -> w -> t` and sometimes a chord `x1 -> t`; paths run the cycle 1..max_laps
+    times or take the branch.  A leading backbone vertex keeps every lap away from step 0 (the reference reads
+    v_ids[-1] there)."""
+    rng = _rng(seed)
+    seqs, links, units = [], [], []
+
+    def new_v():
+        seqs.append("".join("ACGT"[int(c)] for c in rng.integers(0, 4, size=int(rng.integers(1, 5)))))
+        return len(seqs) - 1
+
+    prev = new_v()
+    for _ in range(n_units):
+        k = int(rng.integers(2, 4))
+        s_ = new_v(); xs = [new_v() for _ in range(k)]; w = new_v(); t = new_v(); nxt = new_v()
+        links += [link(prev, "+", s_, "+"), link(s_, "+", xs[0], "+")]
+        links += [link(xs[i], "+", xs[i + 1], "+") for i in range(k - 1)]
+        links += [link(xs[-1], "+", xs[0], "+"), link(xs[-1], "+", t, "+"), link(s_, "+", w, "+"), link(w, "+", t, "+"), link(t, "+", nxt, "+")]
+        chord = rng.uniform() < 0.3
+        if chord:
+            links.append(link(xs[0], "+", t, "+"))
+        units.append((s_, xs, w, t, nxt, chord))
+        prev = nxt
+    paths = []
+    for p in range(n_paths):
+        st = [0]
+        for (s_, xs, w, t, nxt, chord) in units:
+            st.append(s_)
+            c = 0 if p == 0 else int(rng.integers(0, 3))
+            if c == 2:
+                st.append(w)
+            else:
+                laps = 1 if (p == 0 and seed % 2 == 0) else int(rng.integers(1, max_laps + 1))
+                for _ in range(laps):
+                    st += xs
+                if chord and c == 1:
+                    st.append(xs[0])
+            st += [t, nxt]
+        paths.append((f"S{p // 2 + 1:03d}#{p % 2 + 1}#chr1", np.array(st, dtype=np.uint32), np.zeros(len(st), dtype=np.uint8)))
+    return make_graph(np.arange(first_id, first_id + len(seqs), dtype=np.uint32), seqs, links, paths)
+
+
 def reverse_paths(g, which):
     """The same graph with the paths in `which` walked backwards (steps reversed, strands flipped): a path on the
     reverse strand needs no extra links (`L a + b +` is also `L b - a -`).  Regions such a path traverses with the

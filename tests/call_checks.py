@@ -105,6 +105,37 @@ def run_tangled_vs_reference(pv, tmp, n_seeds=24):
     assert tangled > 20 and records > 20, (tangled, records)
 
 
+def run_cyclic_vs_reference(pv, tmp, n_seeds=30):
+    """Regions with a cycle inside: the BFS/Kahn sort fails and the vertex order comes from the haplotype laps
+    (find_laps + gen_sort, graph.cpp:165-395).  Checker: the compiled reference; where it crashes (it reads
+    v_ids[-1] / an empty optional on some inputs) the product must report hard errors instead of records."""
+    import pytest
+    if not os.path.exists(REF):
+        pytest.skip("oracle/_ref/povu_ref not built")
+    gfa = os.path.join(tmp, "c.gfa")
+    compared = crashed = records = 0
+    for seed in range(n_seeds):
+        g = synth.cyclic_units(seed, n_units=2 + seed % 5, n_paths=3 + seed % 6, max_laps=1 + seed % 4)
+        synth.write_gfa(g, gfa)
+        cmd = [REF, "gfa2vcf", "-i", gfa, "-t", "1", "-P", "S001#1"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            crashed += 1
+            try:
+                _, st, _ = gfa2vcf(pv, gfa, ["S001#1"])
+            except RuntimeError:
+                continue
+            assert st["hard_errors"] > 0, f"seed {seed}: the reference crashed, the product reported nothing"
+            continue
+        got, st, _ = gfa2vcf(pv, gfa, ["S001#1"])
+        gh, gr = split(got, False)
+        wh, wr = split(r.stdout, False)
+        assert gh == wh and gr == wr, f"seed {seed}"
+        assert st["hard_errors"] == 0 and st["sort_failed"] == 0
+        compared += 1; records += len(gr)
+    assert compared >= n_seeds // 2 and records > 20, (compared, crashed, records)
+
+
 def run_inversions_vs_reference(pv, tmp, n_seeds=45):
     """SNE / SUBR pass: paths walked on the reverse strand turn regions into whole-region inversions (pin pairs ->
     chains -> extensions -> slice tree -> SUBR records), also inside tangled regions and with two ref paths.  Checker:

@@ -47,3 +47,7 @@ def test_emu_call_tangled_vs_reference(emu_lib, built, tmp_path):
 
 def test_emu_call_inversions_vs_reference(emu_lib, built, tmp_path):
     cc.run_inversions_vs_reference(_ctx(emu_lib, 2), str(tmp_path), n_seeds=30)
+
+
+def test_emu_call_cyclic_vs_reference(emu_lib, built, tmp_path):
+    cc.run_cyclic_vs_reference(_ctx(emu_lib, 1), str(tmp_path), n_seeds=24)

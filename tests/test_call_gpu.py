@@ -39,3 +39,7 @@ def test_gpu_call_tangled_vs_reference(gpu, tmp_path):
 
 def test_gpu_call_inversions_vs_reference(gpu, tmp_path):
     cc.run_inversions_vs_reference(gpu, str(tmp_path), n_seeds=60)
+
+
+def test_gpu_call_cyclic_vs_reference(gpu, tmp_path):
+    cc.run_cyclic_vs_reference(gpu, str(tmp_path), n_seeds=40)
