@@ -117,6 +117,13 @@ int pvgpu_session_write_pvst(const pvgpu_session *s, const char *dir);
 int pvgpu_session_read_pvst(pvgpu_session *s, const char *dir);
 /* call against the paths selected by the prefixes (refs.hpp:278-301).  Records stay in the session. */
 int pvgpu_session_call(pvgpu_session *s, const char *const *prefixes, size_t n_prefixes);
+/* selects the reference paths without calling (records of an earlier call are dropped): the VCF header of those prefixes
+ * can then be written on its own (what the reference has printed when its producer thread fails, to_vcf.cpp:54-82) */
+int pvgpu_session_set_prefixes(pvgpu_session *s, const char *const *prefixes, size_t n_prefixes);
+/* -g/--restrict "ref:start-end" of `povu call` (/root/reference/src/ita/variation/rov.cpp:51-183, genomics.cpp:76-88): the next
+ * calls keep only regions with a boundary vertex whose step on path `ref` starts inside [start, end).  NULL clears it.
+ * A malformed string fails with the reference's message (the reference exits with EXIT_FAILURE there). */
+int pvgpu_session_set_restrict(pvgpu_session *s, const char *region);
 uint64_t pvgpu_session_record_count(const pvgpu_session *s);
 /* counters of the last call: [0] regions selected, [1] regions with >= 3 vertices, [2] tangled regions,
  * [3] inversion pin pairs, [4] regions whose BFS/Kahn order failed, [5] hard errors (the reference would

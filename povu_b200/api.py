@@ -90,6 +90,8 @@ def load_library(lib_path=None):
     lib.pvgpu_session_read_pvst.restype = C.c_int
     lib.pvgpu_session_call.argtypes = [vp, C.POINTER(C.c_char_p), sz]
     lib.pvgpu_session_call.restype = C.c_int
+    lib.pvgpu_session_set_restrict.argtypes = [vp, C.c_char_p]
+    lib.pvgpu_session_set_restrict.restype = C.c_int
     lib.pvgpu_session_record_count.argtypes = [vp]
     lib.pvgpu_session_record_count.restype = u64
     lib.pvgpu_session_call_stats.argtypes = [vp, C.POINTER(u64)]
@@ -354,6 +356,10 @@ class Session:
         arr = (C.c_char_p * len(prefixes))(*[p.encode() for p in prefixes])
         self._check(self.lib.pvgpu_session_call(self.h, arr, len(prefixes)))
         return int(self.lib.pvgpu_session_record_count(self.h))
+
+    def set_restrict(self, region):
+        """`povu call -g ref:start-end` (rov.cpp:51-183); None clears the filter."""
+        self._check(self.lib.pvgpu_session_set_restrict(self.h, region.encode() if region is not None else None))
 
     def call_stats(self):
         a = (C.c_uint64 * 12)()

@@ -122,7 +122,6 @@ struct Dev {
 static void unsupported(const Config &c) {
 	if (c.subflubbles) throw Fail{"-s/--subflubbles is not provided by povu_b200 (sub-flubble passes are outside the accelerated hot path)"};
 	if (!c.structure_export.empty()) throw Fail{"--structure-export is not provided by povu_b200"};
-	if (!c.restrict_region.empty()) throw Fail{"-g/--restrict is not provided by povu_b200 yet"};
 }
 
 static void do_decompose(const Config &c, Dev &d, const std::string &out_dir) {
@@ -134,16 +133,25 @@ static void do_decompose(const Config &c, Dev &d, const std::string &out_dir) {
 static void write_vcfs(const Config &c, Dev &d, const std::vector<std::string> &prefixes) {
 	std::vector<const char *> pp;
 	for (auto &p : prefixes) pp.push_back(p.c_str());
-	d.check(pvgpu_session_call(d.s, pp.data(), pp.size()));
-	uint64_t st[12];
-	pvgpu_session_call_stats(d.s, st);
-	if (st[5]) throw Fail{"call: the reference aborts on this input (missing context boundary in a haplotype lap)"};
-	if (st[4]) fprintf(stderr, "WARN [povu_b200::call] %llu regions have no vertex order (BFS sort and haplotype-lap order both empty): skipped\n", (unsigned long long)st[4]);
-	if (st[10]) fprintf(stderr, "WARN [povu_b200::call] %llu SUBR records had a merged length past the end of a walk (undefined in the reference): clamped\n", (unsigned long long)st[10]);
+	bool region_bad = false;   // the reference has printed the VCF header(s) by the time its producer thread rejects the region (genomics.cpp:76-85)
+	if (!c.restrict_region.empty() && pvgpu_session_set_restrict(d.s, c.restrict_region.c_str())) {
+		fprintf(stderr, "ERR [povu::rov::parse_genomic_region] %s\nERR [povu::genomics::gen_vcf_rec_map] Failed to parse genomic region\n", pvgpu_last_error(d.ctx));
+		region_bad = true;
+	}
+	if (region_bad) d.check(pvgpu_session_set_prefixes(d.s, pp.data(), pp.size()));
+	else {
+		d.check(pvgpu_session_call(d.s, pp.data(), pp.size()));
+		uint64_t st[12];
+		pvgpu_session_call_stats(d.s, st);
+		if (st[5]) throw Fail{"call: the reference aborts on this input (missing context boundary in a haplotype lap)"};
+		if (st[4]) fprintf(stderr, "WARN [povu_b200::call] %llu regions have no vertex order (BFS sort and haplotype-lap order both empty): skipped\n", (unsigned long long)st[4]);
+		if (st[10]) fprintf(stderr, "WARN [povu_b200::call] %llu SUBR records had a merged length past the end of a walk (undefined in the reference): clamped\n", (unsigned long long)st[10]);
+	}
 	const bool to_stdout = !c.have_out || c.stdout_vcf;
 	if (to_stdout) {
 		fflush(stdout);
 		d.check(pvgpu_session_vcf_write(d.s, c.chunk, 1, nullptr, STDOUT_FILENO, nullptr));
+		if (region_bad) exit(EXIT_FAILURE);
 		return;
 	}
 	mkdir(c.out_dir.c_str(), 0777);   // create_dir_if_not_exists (to_vcf.hpp:83-101)
@@ -155,6 +163,7 @@ static void write_vcfs(const Config &c, Dev &d, const std::vector<std::string> &
 		close(fd);
 		d.check(rc);
 	}
+	if (region_bad) exit(EXIT_FAILURE);
 }
 
 int main(int argc, char **argv) {

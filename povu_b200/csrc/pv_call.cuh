@@ -41,6 +41,7 @@ PV_KERNEL(C_vs_hap, 12);
 PV_KERNEL(C_uf, 16);
 PV_KERNEL(C_color, 32);
 PV_KERNEL(C_child, 12);
+PV_KERNEL(C_restrict, 24);
 PV_KERNEL(C_bfs, 128);
 PV_KERNEL(C_gather, 16);
 PV_KERNEL(C_rovmeta, 24);
@@ -413,6 +414,9 @@ struct CallIn {           // PVST forest, flubbles of all components concatenate
 	u32 nRefs = 0; const u32 *refs = nullptr;   // ascending path ids to call against
 	const u8 *excluded = nullptr;  // optional: 1 = never selected (sub-flubble clan or below one, color.cpp:117-125)
 	bool on_device = false;        // a_v .. flBase point into device memory (decompose's table handed over in HBM)
+	// -g/--restrict ref:start-end (rov.cpp:137-183): keep a selected flubble only if a step of the named path on one of its
+	// two boundary vertices starts inside [start, end).  restrict_ref == NONE: the path does not exist -> no regions.
+	bool restrict_on = false; u32 restrict_ref = NONE; u64 restrict_start = 0, restrict_end = 0;
 };
 
 // binary records, written by the device into page-locked host vectors whose capacity survives across calls
@@ -1287,6 +1291,22 @@ inline void call_device(Ctx &c, const DevGraph &G, const CallIn &in, const CallO
 	});
 	parallel_for<C_child>(c, nFl, PV_LAMBDA(size_t f) { u32 p = fpar_[f]; if (colored_[f] && p != 0) kid_[fbase_[f] + p - 1] = 1; });
 	parallel_for<C_child>(c, nFl, PV_LAMBDA(size_t f) { called_[f] = (colored_[f] && !kid_[f]) ? 1u : 0u; });   // color.cpp:141-148
+	if (in.restrict_on) {
+		const u32 rh = in.restrict_ref; const u64 lo = in.restrict_start, hi = in.restrict_end;
+		parallel_for<C_restrict>(c, nFl, PV_LAMBDA(size_t f) {
+			if (!called_[f]) return;
+			bool hit = false;
+			if (rh != NONE) {
+				u32 s0 = g.stepOff[rh], s1 = g.stepOff[rh + 1];
+				for (int side = 0; side < 2 && !hit; side++) {
+					u32 v = (side ? fz_[f] : fa_[f]) >> 1;
+					u32 a = g.vsOff[v], b = g.vsOff[v + 1];
+					for (u32 k = lb_u32(g.vsStep, a, b, s0); k < b && g.vsStep[k] < s1; k++) { u64 pos = g.loci[g.vsStep[k]]; if (pos >= lo && pos < hi) { hit = true; break; } }
+				}
+			}
+			if (!hit) called_[f] = 0;
+		});
+	}
 	Buf<u32> rov0;
 	const u32 R0 = compact_flags(c, called.p, nFl, rov0);
 	out.n_called = R0;
@@ -1434,7 +1454,7 @@ inline void call_device(Ctx &c, const DevGraph &G, const CallIn &in, const CallO
 		rovComp_[r] = comp;
 		u32 nh = g.cpOff[comp + 1] - g.cpOff[comp];
 		rowsOf_[r] = nh; cellsOf_[r] = (u64)nh * n;
-		atomic_max(tot_ + 0, (u64)n);
+		if ((u64)n > *(volatile u64 *)(tot_ + 0)) atomic_max(tot_ + 0, (u64)n);   // test first: one contended address otherwise serialises every thread
 		if (n > 16) atomic_add(tot_ + 1, (u64)n);
 	});
 	exclusive_scan(c, rovJ.p, rovOff.p, (size_t)R + 1, OpAddU32(), 0u);

@@ -319,6 +319,10 @@ int pvgpu_session_read_pvst(pvgpu_session *s, const char *dir) { PV_TRY(s->x, s-
 int pvgpu_session_call(pvgpu_session *s, const char *const *prefixes, size_t n) {
 	PV_TRY(s->x, { std::vector<std::string> p; for (size_t i = 0; i < n; i++) p.push_back(prefixes[i]); s->s.set_prefixes(p); s->s.call(); })
 }
+int pvgpu_session_set_prefixes(pvgpu_session *s, const char *const *prefixes, size_t n) {
+	PV_TRY(s->x, { std::vector<std::string> p; for (size_t i = 0; i < n; i++) p.push_back(prefixes[i]); s->s.set_prefixes(p); s->s.rec.reset(); s->s.rec.rec_grpOff.push_back(0); s->s.rec.rec_gtOff.push_back(0); })
+}
+int pvgpu_session_set_restrict(pvgpu_session *s, const char *region) { PV_TRY(s->x, s->s.set_restrict(region)) }
 uint64_t pvgpu_session_record_count(const pvgpu_session *s) { return s->s.rec.n(); }
 void pvgpu_session_call_stats(const pvgpu_session *s, uint64_t o[12]) {
 	const pv::Records &c = s->s.rec;

@@ -5,6 +5,7 @@
 //   do_call       /root/reference/app/subcommand/call.cpp:71-173
 //   do_gfa2vcf    /root/reference/app/subcommand/gfa2vcf.cpp:18-87
 #pragma once
+#include <cerrno>
 #include <chrono>
 #include <dirent.h>
 #include <array>
@@ -225,6 +226,30 @@ struct Session {
 		if (!gm_ready) { gm = pvh::genotype_metadata(g); gm_ready = true; }
 	}
 
+	// -g/--restrict ref:start-end -- parse_genomic_region (/root/reference/src/ita/variation/rov.cpp:51-118), same messages
+	bool restrict_on = false; std::string restrict_ref; u64 restrict_start = 0, restrict_end = 0;
+	void set_restrict(const char *region) {
+		restrict_on = false;
+		if (!region) return;
+		const std::string r = region;
+		auto bad = [&](const std::string &why) { throw std::runtime_error("Invalid region format '" + r + "': " + why); };
+		size_t colon = r.find(':');
+		if (colon == std::string::npos) bad("missing colon separator");
+		std::string name = r.substr(0, colon);
+		if (name.empty()) bad("empty reference name");
+		std::string range = r.substr(colon + 1);
+		size_t dash = range.find('-');
+		if (dash == std::string::npos) bad("missing dash separator in range");
+		std::string a = range.substr(0, dash), b = range.substr(dash + 1);
+		for (char ch : a) if (!isdigit((unsigned char)ch)) bad("non-numeric start position");
+		for (char ch : b) if (!isdigit((unsigned char)ch)) bad("non-numeric end position");
+		errno = 0;
+		u64 st = (u32)strtoull(a.c_str(), nullptr, 10), en = (u32)strtoull(b.c_str(), nullptr, 10);
+		if (a.empty() || b.empty() || errno == ERANGE) throw std::runtime_error("Failed to parse region '" + r + "': stoull");   // std::stoull throws   // pt::idx_t is 32 bits wide: std::stoull's result is truncated
+		if (st >= en) throw std::runtime_error("Invalid region '" + r + "': start position (" + std::to_string(st) + ") must be less than end position (" + std::to_string(en) + ")");
+		restrict_on = true; restrict_ref = name; restrict_start = st; restrict_end = en;
+	}
+
 	void call() {
 		if (!forest_ready) throw std::runtime_error("call: no PVST forest (run decompose or read .pvst files first)");
 		upload_paths();
@@ -251,6 +276,11 @@ struct Session {
 		} else {
 			in.a_v = forest.a_v.data(); in.z_v = forest.z_v.data(); in.a_fwd = forest.a_fwd.data(); in.z_fwd = forest.z_fwd.data();
 			in.parent = forest.parent.data(); in.flBase = forest.flBase.data();
+		}
+		if (restrict_on) {
+			in.restrict_on = true; in.restrict_start = restrict_start; in.restrict_end = restrict_end; in.restrict_ref = pvh::NONE32;
+			for (u32 h = 0; h < g.H(); h++) if (g.paths[h].tag == restrict_ref) { in.restrict_ref = h; break; }   // Refs::get_ref_id (refs.hpp:265-274)
+			if (in.restrict_ref == pvh::NONE32) fprintf(stderr, "ERR [povu::rov::gen_rov] Reference path '%s' not found in graph\n", restrict_ref.c_str());
 		}
 		pv::CallOpts opt;
 		if (const char *e = getenv("POVU_B200_CELL_BUDGET")) opt.cell_budget = strtoull(e, nullptr, 10);

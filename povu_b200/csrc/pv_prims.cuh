@@ -501,12 +501,42 @@ struct Rmq {
 PV_KERNEL(K_rmq_blocks, 12);   // a in, pre + suf out (+ block min)
 PV_KERNEL(K_rmq_level, 24);   // one level in, up to five levels out
 
+#ifndef PV_EMU
+__global__ void __launch_bounds__(256) rmq_blocks_kernel(const u32 *a, u32 *pre, u32 *suf, u32 *table, u32 n, u32 nb) {
+	const u32 lane = threadIdx.x & 31u;
+	const u32 warp = (blockIdx.x * 256u + threadIdx.x) >> 5, nwarps = (gridDim.x * 256u) >> 5;
+	for (u32 b = warp; b < nb; b += nwarps) {
+		u32 i = (b << 5) + lane;
+		u32 x = i < n ? a[i] : NONE;
+		u32 p = x, s = x;
+#pragma unroll
+		for (int d = 1; d < 32; d <<= 1) {
+			u32 y = __shfl_up_sync(0xFFFFFFFFu, p, d); if (lane >= (u32)d && y < p) p = y;
+			u32 z = __shfl_down_sync(0xFFFFFFFFu, s, d); if (lane + d < 32u && z < s) s = z;
+		}
+		if (i < n) { pre[i] = p; suf[i] = s; }
+		if (lane == 0) table[b] = s;
+	}
+}
+#endif
+
 inline void rmq_build(Ctx &c, Rmq &r, const u32 *a, u32 n) {
 	r.a = a; r.n = n; r.nb = (n + 31) / 32;
 	r.levels = 1; while ((1u << r.levels) <= r.nb) r.levels++;
 	r.pre = Buf<u32>(c, n); r.suf = Buf<u32>(c, n); r.table = Buf<u32>(c, (size_t)r.levels * r.nb);
 	u32 *pre = r.pre.p, *suf = r.suf.p, *table = r.table.p; u32 nb = r.nb;
-	// one thread per block of 32: 128 contiguous bytes per thread (4 sectors), sequential scan
+#ifndef PV_EMU
+	{
+		// one warp per block of 32: coalesced 128-byte load, prefix / suffix minima by shuffles, coalesced stores
+		size_t blocks = ((size_t)nb * 32 + 255) / 256, cap = (size_t)c.sm_count * 16;
+		if (blocks > cap) blocks = cap;
+		c.prof_begin(K_rmq_blocks::name(), n, (u64)n * K_rmq_blocks::bytes);
+		rmq_blocks_kernel<<<(unsigned)blocks, 256, 0, c.stream>>>(a, pre, suf, table, n, nb);
+		c.prof_end();
+		c.launches++;
+		PV_CUDA_CHECK(cudaGetLastError());
+	}
+#else
 	parallel_for<K_rmq_blocks>(c, nb, PV_LAMBDA(size_t b) {
 		u32 s = (u32)b << 5, e = s + 32 < n ? s + 32 : n;
 		u32 m = NONE;
@@ -515,6 +545,7 @@ inline void rmq_build(Ctx &c, Rmq &r, const u32 *a, u32 n) {
 		m = NONE;
 		for (u32 i = e; i-- > s;) { u32 x = a[i]; m = x < m ? x : m; suf[i] = m; }
 	});
+#endif
 	// five sparse-table levels per launch: level b+m at j = min over i < 2^m of level b at j + i * 2^b
 	for (u32 b = 0; b + 1 < r.levels; b += 5) {
 		const u32 top = b + 5 < r.levels - 1 ? b + 5 : r.levels - 1;   // highest level written by this launch

@@ -75,6 +75,22 @@ def check_cli(cli, tmp):
     e = os.path.join(tmp, "empty"); os.mkdir(e)
     r = run(cli, "call", "-i", fx("minimal_substitution"), "-f", e, "-P", "HG1")
     assert r.returncode == 1 and "Could not find pvst files" in r.stderr
+    # call -g ref:start-end (rov.cpp:51-183): same records / header / exit code as the compiled reference
+    import call_checks as cc2
+    if os.path.exists(cc2.REF):
+        from povu_b200 import synth
+        gfa = os.path.join(tmp, "restrict.gfa")
+        synth.write_gfa(synth.snp_indel_chain(300, n_paths=6, seed=3, with_seqs=True), gfa)
+        fd = os.path.join(tmp, "rforest"); os.mkdir(fd)
+        assert run(cli, "decompose", "-i", gfa, "-o", fd).returncode == 0
+        for reg in ["S001#1#chr1:100-400", "S002#2#chr1:1-50", "nope:1-5", "S001#1#chr1:5-5", "S001#1#chr1:a-5", "S001#1#chr15",
+                    "S001#1#chr1:-5", "S001#1#chr1:10-4000000000000", "S001#1#chr1:1-99999999999999999999999"]:
+            want = run(cc2.REF, "call", "-i", gfa, "-f", fd, "-P", "S001#1", "-g", reg)
+            got = run(cli, "call", "-i", gfa, "-f", fd, "-P", "S001#1", "-g", reg)
+            assert got.returncode == want.returncode and nodate(got.stdout) == nodate(want.stdout), reg
+            errs = [l[l.index("]") + 1:].split("m", 1)[-1].strip() for l in want.stderr.splitlines() if "ERR" in l]
+            for e in errs:
+                assert e in got.stderr, (reg, e)
     # outside the hot path: loud failure, never a silent no-op
     r = run(cli, "gfa2vcf", "-i", fx("minimal_substitution"), "-P", "HG1", "-s")
     assert r.returncode == 1 and "subflubbles" in r.stderr
