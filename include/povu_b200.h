@@ -93,6 +93,21 @@ void pvgpu_flubbles_free(pvgpu_flubbles *f);
  */
 typedef struct pvgpu_session pvgpu_session;
 int pvgpu_session_open(pvgpu_ctx *ctx, const char *gfa_path, int inc_vtx_labels, int inc_refs, pvgpu_session **out);
+/* pvgpu_session_open parses the GFA text ON THE DEVICE (the file is streamed through page-locked staging
+ * buffers into HBM and split / validated / converted there; replaces the liteseq parse + the pre-scan of
+ * /root/reference/src/mto/from_gfa.cpp:28-113,141-280, same "Invalid GFA '<path>': ..." messages incl. the line number).
+ * Links, walks and sequences then live only in HBM until something on the host asks for them.
+ * text_bytes = size of the file, ms[0] = file -> HBM, ms[1] = device parse (wall, of the last open). */
+void pvgpu_session_gfa_stats(const pvgpu_session *s, uint64_t *text_bytes, double ms[2]);
+/* test hook: the same graph through the host loader (pv_host.hpp), the checker of the device parser's tests */
+int pvgpu_session_open_hostparse(pvgpu_ctx *ctx, const char *gfa_path, int inc_vtx_labels, int inc_refs, pvgpu_session **out);
+/* the loaded graph as flat arrays (any pointer may be NULL): ids[V] ascending segment ids, seg_len[V], ep1/ep2[E] ports in
+ * L-line order, step_off[H+1], steps[S] packed (vertex<<1)|strand in P-line order, hap_len[H] contig lengths,
+ * label_off[V+1] into labels[pvgpu_session_label_bytes] (the concatenated sequences). */
+int pvgpu_session_copy_graph(pvgpu_session *s, uint32_t *ids, uint32_t *seg_len, uint32_t *ep1, uint32_t *ep2, uint32_t *step_off,
+			     uint32_t *steps, uint32_t *hap_len, uint64_t *label_off, char *labels);
+uint64_t pvgpu_session_label_bytes(pvgpu_session *s);
+const char *pvgpu_session_path_name(const pvgpu_session *s, uint32_t k);
 /* same, from arrays already in memory (the builder path of povu_ffi.h: povu_graph_new / add_vertex / add_edge /
  * add_path, /root/reference/povu-rs/povu-ffi/povu_ffi.h:147-262).  ids ascending; ep1/ep2 ports as above;
  * labels optional (label_off[V+1] into labels) -- without them seg_len[V] gives the segment lengths and VCF text is

@@ -69,6 +69,15 @@ def load_library(lib_path=None):
     lib.pvgpu_session_open.argtypes = [vp, C.c_char_p, C.c_int, C.c_int, C.POINTER(vp)]
     lib.pvgpu_session_open.restype = C.c_int
     lib.pvgpu_session_close.argtypes = [vp]
+    lib.pvgpu_session_open_hostparse.argtypes = [vp, C.c_char_p, C.c_int, C.c_int, C.POINTER(vp)]
+    lib.pvgpu_session_open_hostparse.restype = C.c_int
+    lib.pvgpu_session_gfa_stats.argtypes = [vp, C.POINTER(u64), C.POINTER(C.c_double)]
+    lib.pvgpu_session_copy_graph.argtypes = [vp] + [vp] * 9
+    lib.pvgpu_session_copy_graph.restype = C.c_int
+    lib.pvgpu_session_label_bytes.argtypes = [vp]
+    lib.pvgpu_session_label_bytes.restype = u64
+    lib.pvgpu_session_path_name.argtypes = [vp, u32]
+    lib.pvgpu_session_path_name.restype = C.c_char_p
     lib.pvgpu_session_from_arrays.argtypes = [vp, u32, vp, vp, vp, vp, u64, vp, vp, u32, C.POINTER(C.c_char_p), vp, vp, C.POINTER(vp)]
     lib.pvgpu_session_from_arrays.restype = C.c_int
     lib.pvgpu_session_hot_path.argtypes = [vp, C.POINTER(C.c_char_p), sz, C.c_int, C.POINTER(C.c_double)]
@@ -259,16 +268,44 @@ class Session:
     """One GFA loaded on one device: decompose -> (.pvst) -> call -> VCF text.  Mirrors the reference's
     `povu decompose / call / gfa2vcf` drivers (app/subcommand/*.cpp) through the pvgpu_session_* C ABI."""
 
-    def __init__(self, pv, gfa_path=None, inc_vtx_labels=True, inc_refs=True, _handle=None):
+    def __init__(self, pv, gfa_path=None, inc_vtx_labels=True, inc_refs=True, _handle=None, host_parser=False):
+        """The GFA text is parsed on the device (pv_gfa.cuh); host_parser=True is the test hook that loads it with the
+        host loader instead (the checker of the device parser)."""
         self.pv, self.lib = pv, pv.lib
         if _handle is not None:
             self.h = _handle
             return
         h = C.c_void_p()
-        rc = self.lib.pvgpu_session_open(pv.h, os.fsencode(gfa_path), int(inc_vtx_labels), int(inc_refs), C.byref(h))
+        opener = self.lib.pvgpu_session_open_hostparse if host_parser else self.lib.pvgpu_session_open
+        rc = opener(pv.h, os.fsencode(gfa_path), int(inc_vtx_labels), int(inc_refs), C.byref(h))
         if rc != 0:
             raise RuntimeError(pv._err())
         self.h = h
+
+    def gfa_stats(self):
+        """Size of the GFA text and the wall time of (file -> HBM, device parse) of the open."""
+        n, ms = C.c_uint64(), (C.c_double * 2)()
+        self.lib.pvgpu_session_gfa_stats(self.h, C.byref(n), ms)
+        return {"text_bytes": int(n.value), "read_ms": ms[0], "parse_ms": ms[1]}
+
+    def graph_arrays(self, labels=True):
+        """The loaded graph as flat numpy arrays (pvgpu_session_copy_graph)."""
+        V, E, H, S = self.sizes()
+        out = {"ids": np.empty(V, np.uint32), "seg_len": np.empty(V, np.uint32), "ep1": np.empty(E, np.uint32), "ep2": np.empty(E, np.uint32),
+               "step_off": np.empty(H + 1, np.uint32), "steps": np.empty(S, np.uint32), "hap_len": np.empty(H, np.uint32)}
+        lab_off = lab = None
+        if labels:
+            nb = int(self.lib.pvgpu_session_label_bytes(self.h))
+            lab_off, lab = np.empty(V + 1, np.uint64), np.empty(nb, np.uint8)
+        ptr = lambda a: a.ctypes.data if a is not None and a.size else None
+        rc = self.lib.pvgpu_session_copy_graph(self.h, ptr(out["ids"]), ptr(out["seg_len"]), ptr(out["ep1"]), ptr(out["ep2"]), out["step_off"].ctypes.data,
+                                               ptr(out["steps"]), ptr(out["hap_len"]), lab_off.ctypes.data if labels else None, ptr(lab))
+        if rc != 0:
+            raise RuntimeError(self.pv._err())
+        if labels:
+            out["label_off"], out["labels"] = lab_off, lab.tobytes()
+        out["path_names"] = [self.lib.pvgpu_session_path_name(self.h, k).decode() for k in range(H)]
+        return out
 
     @classmethod
     def from_graph(cls, pv, g, with_labels=True):

@@ -261,6 +261,37 @@ int pvgpu_session_open(pvgpu_ctx *x, const char *gfa, int labels, int refs, pvgp
 	try { PV_SET_DEVICE(x); s = new pvgpu_session(x); s->s.load_gfa(gfa, labels != 0, refs != 0); *out = s; return 0; }
 	catch (std::exception &e) { x->err = e.what(); delete s; return 1; }
 }
+int pvgpu_session_open_hostparse(pvgpu_ctx *x, const char *gfa, int labels, int refs, pvgpu_session **out) {
+	if (!x || !gfa || !out) return 1;
+	*out = nullptr;
+	pvgpu_session *s = nullptr;
+	try { PV_SET_DEVICE(x); s = new pvgpu_session(x); s->s.load_gfa(gfa, labels != 0, refs != 0, true); *out = s; return 0; }
+	catch (std::exception &e) { x->err = e.what(); delete s; return 1; }
+}
+void pvgpu_session_gfa_stats(const pvgpu_session *s, uint64_t *text_bytes, double ms[2]) {
+	if (text_bytes) *text_bytes = s->s.gfa_text_bytes;
+	if (ms) { ms[0] = s->s.t_gfa_read_ms; ms[1] = s->s.t_gfa_parse_ms; }
+}
+uint64_t pvgpu_session_label_bytes(pvgpu_session *s) {
+	try { PV_SET_DEVICE(s->x); s->s.ensure_host(false, false, true); return s->s.g.lblOff.empty() ? 0 : s->s.g.lblOff.back(); } catch (std::exception &e) { s->x->err = e.what(); return 0; }
+}
+const char *pvgpu_session_path_name(const pvgpu_session *s, uint32_t k) { return k < s->s.g.H() ? s->s.g.paths[k].tag.c_str() : nullptr; }
+int pvgpu_session_copy_graph(pvgpu_session *s, uint32_t *ids, uint32_t *seg_len, uint32_t *ep1, uint32_t *ep2, uint32_t *step_off, uint32_t *steps,
+			     uint32_t *hap_len, uint64_t *label_off, char *labels) {
+	PV_TRY(s->x, {
+		pvh::HostGraph &g = s->s.g;
+		s->s.ensure_host(ep1 || ep2, steps != nullptr, label_off || labels);
+		if (ids) memcpy(ids, g.ids.data(), g.ids.size() * 4);
+		if (seg_len) memcpy(seg_len, g.segLen.data(), g.segLen.size() * 4);
+		if (ep1) memcpy(ep1, g.ep1.data(), g.ep1.size() * 4);
+		if (ep2) memcpy(ep2, g.ep2.data(), g.ep2.size() * 4);
+		if (step_off) memcpy(step_off, g.stepOff.data(), g.stepOff.size() * 4);
+		if (steps) memcpy(steps, g.steps.data(), g.steps.size() * 4);
+		if (hap_len) for (uint32_t k = 0; k < g.H(); k++) hap_len[k] = g.paths[k].hap_len;
+		if (label_off) memcpy(label_off, g.lblOff.data(), g.lblOff.size() * 8);
+		if (labels && g.has_labels) memcpy(labels, g.lbl.data(), g.lbl.size());
+	})
+}
 int pvgpu_session_from_arrays(pvgpu_ctx *x, uint32_t V, const uint32_t *ids, const uint32_t *seg_len, const uint64_t *label_off, const char *labels,
 			      uint64_t E, const uint32_t *ep1, const uint32_t *ep2, uint32_t H, const char *const *names, const uint32_t *step_off,
 			      const uint32_t *steps, pvgpu_session **out) {
@@ -305,7 +336,7 @@ int pvgpu_session_hot_path(pvgpu_session *s, const char *const *prefixes, size_t
 	})
 }
 void pvgpu_session_sizes(const pvgpu_session *s, uint64_t *v, uint64_t *e, uint64_t *h, uint64_t *st) {
-	if (v) *v = s->s.g.V(); if (e) *e = s->s.g.E(); if (h) *h = s->s.g.H(); if (st) *st = s->s.g.steps.size();
+	if (v) *v = s->s.g.V(); if (e) *e = s->s.g.E(); if (h) *h = s->s.g.H(); if (st) *st = s->s.g.stepOff.empty() ? 0 : s->s.g.stepOff.back();
 }
 int pvgpu_session_decompose(pvgpu_session *s) { PV_TRY(s->x, s->s.decompose()) }
 uint64_t pvgpu_session_flubble_count(const pvgpu_session *s) { return s->s.forest.n(); }

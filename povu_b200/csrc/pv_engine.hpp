@@ -12,6 +12,7 @@
 #include <fstream>
 #include <type_traits>
 #include "pv_text.cuh"
+#include "pv_gfa.cuh"
 #include "pv_host.hpp"
 
 namespace pve {
@@ -49,7 +50,74 @@ struct Session {
 		pinned.clear();
 	}
 
-	void load_gfa(const std::string &fp, bool labels, bool refs) { unpin(); g = pvh::load_gfa(fp, labels, refs); pin(); tt = pv::TextTables(); }
+	// GFA -> graph.  Default: the text is parsed on the device (pv_gfa.cuh); the big arrays (links, walks, sequences)
+	// then exist only in HBM and come to the host on demand (ensure_host).  POVU_B200_HOST_GFA=1 selects the host
+	// loader of pv_host.hpp instead (same results; kept for A/B timing and as the checker in the tests).
+	bool host_edges = true, host_steps = true, host_lbl = true, tt_graph_dev = false;
+	double t_gfa_read_ms = 0, t_gfa_parse_ms = 0; u64 gfa_text_bytes = 0;
+	void load_gfa(const std::string &fp, bool labels, bool refs, bool force_host_parser = false) {
+		unpin(); c->bg_sync();
+		d_ep1.release(); d_ep2.release(); d_steps.release(); d_segLen.release(); dg = pv::DevGraph();
+		edges_up = raw_paths_up = paths_up = false; forest_ready = false; gm_ready = false; sharded = false;
+		tt = pv::TextTables(); tt_graph_dev = false;
+		static const bool env_host_parser = getenv("POVU_B200_HOST_GFA") != nullptr;
+		if (env_host_parser || force_host_parser) { double t0 = now_ms(); g = pvh::load_gfa(fp, labels, refs); t_gfa_read_ms = 0; t_gfa_parse_ms = now_ms() - t0; host_edges = host_steps = host_lbl = true; pin(); return; }
+		load_gfa_device(fp, labels, refs);
+	}
+	void load_gfa_device(const std::string &fp, bool labels, bool refs) {
+		auto bad = [&](const std::string &d) { return std::runtime_error("Invalid GFA '" + fp + "': " + d); };
+		struct Fd { int fd; ~Fd() { if (fd >= 0) close(fd); } } f{open(fp.c_str(), O_RDONLY)};
+		struct stat st;
+		if (f.fd < 0 || fstat(f.fd, &st) != 0 || !S_ISREG(st.st_mode)) throw bad("could not open file");
+		const u64 n = (u64)st.st_size;
+		char last = 0;
+		if (n && pread(f.fd, &last, 1, (off_t)(n - 1)) != 1) throw bad("could not open file");
+		double t0 = now_ms();
+		pv::GfaDev o;
+		gfa_text_bytes = n;
+		{
+			pv::Buf<u8> T;
+			pv::gfa_text_to_device(*c, f.fd, n, T);
+			t_gfa_read_ms = now_ms() - t0;
+			pv::gfa_parse_device(*c, T.p, n, last == '\n', labels, refs, o);
+		}
+		if (o.err != ~0ull) {
+			const std::string line = std::to_string(o.err >> 16); const u32 code = (u32)((o.err >> 8) & 0xFF);
+			if (code == 1) throw bad("S record on line " + line + " is missing a segment id and sequence");
+			if (code == 2) throw bad("S record on line " + line + " is missing a sequence");
+			if (code == 3) throw bad("S record on line " + line + " has an empty sequence");
+			throw bad("unsupported record type '" + std::string(1, (char)(o.err & 0xFF)) + "' on line " + line);
+		}
+		if (o.V == 0) throw bad("liteseq returned no vertices");
+		if (o.lq) throw bad("liteseq could not parse the file");
+		if (o.S >= 0xFFFFFFF0ull) throw std::runtime_error("povu_b200: more than 2^32 path steps in one graph are not supported yet");
+		g = pvh::HostGraph(); g.has_labels = labels;
+		g.ids.swap(o.h_ids); g.segLen.swap(o.h_segLen); g.stepOff = o.h_stepOff; g.devE = o.E;
+		for (u32 r = 0; r < o.H; r++) {
+			std::string tag((size_t)(o.nameE[r] - o.nameB[r]), '\0');
+			if (!tag.empty() && pread(f.fd, &tag[0], tag.size(), (off_t)o.nameB[r]) != (ssize_t)tag.size()) throw bad("could not open file");
+			pvh::HostPath p = pvh::parse_path_name(tag);
+			p.hap_len = (u32)o.hapLen[r];
+			g.paths.push_back(std::move(p));
+		}
+		d_ep1 = std::move(o.ep1); d_ep2 = std::move(o.ep2); edges_up = true;
+		d_steps = o.steps.p ? std::move(o.steps) : pv::Buf<u32>(*c, 1); d_segLen = std::move(o.segLen); raw_paths_up = true;
+		tt.ids = std::move(o.ids); tt.lblOff = std::move(o.lblOff);
+		if (labels) tt.lbl = std::move(o.lbl);
+		tt_graph_dev = true;
+		host_edges = o.E == 0; host_steps = g.stepOff.back() == 0; host_lbl = false;
+		t_gfa_parse_ms = now_ms() - t0 - t_gfa_read_ms;
+	}
+	// bring the arrays that a device-parsed graph keeps only in HBM to the host (sharding, the povu_ffi getters, re-upload)
+	void ensure_host(bool edges, bool steps, bool lbl) {
+		if (edges && !host_edges) { g.ep1.resize(g.devE); g.ep2.resize(g.devE); c->d2h(g.ep1.data(), d_ep1.p, g.devE * 4); c->d2h(g.ep2.data(), d_ep2.p, g.devE * 4); host_edges = true; }
+		if (steps && !host_steps) { g.steps.resize(g.stepOff.back()); c->d2h(g.steps.data(), d_steps.p, g.steps.size() * 4); host_steps = true; }
+		if (lbl && !host_lbl) {
+			g.lblOff.resize((size_t)g.V() + 1); c->d2h(g.lblOff.data(), tt.lblOff.p, g.lblOff.size() * 8);
+			if (g.has_labels) { g.lbl.resize(g.lblOff.back()); c->d2h(&g.lbl[0], tt.lbl.p, g.lbl.size()); }
+			host_lbl = true;
+		}
+	}
 
 	// raw arrays resident in HBM: edge ports, packed steps, segment lengths
 	pv::Buf<u32> d_steps, d_segLen; bool raw_paths_up = false;
@@ -85,6 +153,7 @@ struct Session {
 	}
 	// forget everything on the device (the next decompose / call re-uploads from the host arrays)
 	void drop_device() {
+		ensure_host(true, true, false);
 		d_ep1.release(); d_ep2.release(); d_steps.release(); d_segLen.release(); dg = pv::DevGraph();
 		edges_up = raw_paths_up = paths_up = false;
 	}
@@ -118,6 +187,7 @@ struct Session {
 	void shard(u32 rank, u32 world) {
 		if (world == 0 || rank >= world) throw std::runtime_error("shard: bad rank / world size");
 		upload_edges();
+		ensure_host(true, true, true);
 		const u32 V = g.V(); const u64 E = g.E();
 		pv::Buf<u32> lab(*c, V ? V : 1);
 		pv::component_labels(*c, V, E, d_ep1.p, d_ep2.p, lab.p);
@@ -157,8 +227,9 @@ struct Session {
 		n.build_id_table();
 		unpin(); drop_device();
 		g = std::move(n);
+		host_edges = host_steps = host_lbl = true;
 		pin();
-		forest_ready = false; sharded = true; tt = pv::TextTables(); gm_ready = false;
+		forest_ready = false; sharded = true; tt = pv::TextTables(); tt_graph_dev = false; gm_ready = false;
 	}
 
 	// decompose: flubbles + PVST of every component with >= 3 vertices (decompose.cpp:129-142)
@@ -315,9 +386,11 @@ struct Session {
 		if (!paths_up) throw std::runtime_error("VCF text needs the path index (run call first)");
 		pv::Ctx &cx = *c;
 		auto up32 = [&](pv::Buf<u32> &b, const std::vector<u32> &h) { b = pv::Buf<u32>(cx, h.size() ? h.size() : 1); cx.h2d(b.p, h.data(), h.size() * 4); };
-		up32(tt.ids, g.ids);
-		tt.lblOff = pv::Buf<u64>(cx, g.lblOff.size()); cx.h2d(tt.lblOff.p, g.lblOff.data(), g.lblOff.size() * 8);
-		tt.lbl = pv::Buf<u8>(cx, g.lbl.size() ? g.lbl.size() : 1); cx.h2d(tt.lbl.p, g.lbl.data(), g.lbl.size());
+		if (!tt_graph_dev) {   // a device-parsed graph already left its ids and sequences in HBM
+			up32(tt.ids, g.ids);
+			tt.lblOff = pv::Buf<u64>(cx, g.lblOff.size()); cx.h2d(tt.lblOff.p, g.lblOff.data(), g.lblOff.size() * 8);
+			tt.lbl = pv::Buf<u8>(cx, g.lbl.size() ? g.lbl.size() : 1); cx.h2d(tt.lbl.p, g.lbl.data(), g.lbl.size());
+		}
 		std::vector<u32> tagOff(1, 0); std::string tags;
 		for (auto &p : g.paths) { tags += p.tag; tagOff.push_back((u32)tags.size()); }
 		up32(tt.tagOff, tagOff);

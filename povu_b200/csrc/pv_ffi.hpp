@@ -125,6 +125,7 @@ PovuVertex *povu_graph_get_vertices(const PovuGraph *graph, size_t *count) {
 	if (!graph || !count) { if (count) *count = 0; return nullptr; }
 	const size_t n = povu_graph_vertex_count(graph);
 	*count = n;
+	if (graph->from_gfa) { try { graph->s->ensure_host(false, false, true); } catch (...) { *count = 0; return nullptr; } }
 	PovuVertex *out = new PovuVertex[n];
 	for (size_t i = 0; i < n; i++) {
 		std::string lab = graph->from_gfa ? std::string(graph->s->g.label((uint32_t)i), graph->s->g.segLen[i]) : graph->b_seqs[i];
@@ -137,6 +138,7 @@ PovuEdge *povu_graph_get_edges(const PovuGraph *graph, size_t *count) {
 	if (!graph || !count) { if (count) *count = 0; return nullptr; }
 	const size_t n = povu_graph_edge_count(graph);
 	*count = n;
+	if (graph->from_gfa) { try { graph->s->ensure_host(true, false, false); } catch (...) { *count = 0; return nullptr; } }
 	PovuEdge *out = new PovuEdge[n];
 	for (size_t i = 0; i < n; i++) {
 		uint32_t a = graph->from_gfa ? graph->s->g.ep1[i] : graph->b_ep1[i], b = graph->from_gfa ? graph->s->g.ep2[i] : graph->b_ep2[i];
@@ -150,6 +152,7 @@ PovuPath *povu_graph_get_paths(const PovuGraph *graph, size_t *count) {
 	const size_t n = povu_graph_path_count(graph);
 	*count = n;
 	if (n == 0) return nullptr;
+	if (graph->from_gfa) { try { graph->s->ensure_host(false, true, false); } catch (...) { *count = 0; return nullptr; } }
 	PovuPath *out = new PovuPath[n];
 	for (size_t r = 0; r < n; r++) {
 		const std::string &nm = graph->from_gfa ? graph->s->g.paths[r].tag : graph->b_paths[r].name;

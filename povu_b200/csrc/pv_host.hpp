@@ -47,9 +47,10 @@ struct HostGraph {
 	std::vector<u32> steps;               // (vertex idx << 1) | strand
 	std::vector<u32> id_table;            // dense id -> idx (NONE32 = absent) when ids are dense enough
 	bool has_labels = false;
+	u64 devE = 0;                         // link count when the endpoint arrays live only in HBM (device-parsed GFA)
 
 	u32 V() const { return (u32)ids.size(); }
-	u64 E() const { return ep1.size(); }
+	u64 E() const { return ep1.empty() ? devE : ep1.size(); }
 	u32 H() const { return (u32)paths.size(); }
 	u32 idx_of(u64 id) const {
 		if (!id_table.empty()) return id < id_table.size() ? id_table[id] : NONE32;
