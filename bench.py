@@ -45,6 +45,7 @@ def parse_args():
     ap.add_argument("--paths", type=int, default=N_PATHS)
     ap.add_argument("--cpu-bubbles", type=int, default=100_000, help="size of the bounded CPU sample (same shape)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gfa-leg", action="store_true", help="skip the GFA text -> HBM leg (device parser) reported under gfa_text")
     ap.add_argument("--profile-steps", type=int, default=2)
     return ap.parse_args()
 
@@ -258,6 +259,39 @@ def run_native(args):
         text_s = time.perf_counter() - t0
         os.unlink(devnull)
 
+        # the steps either side of the hot path, on rank 0: GFA text parsed on the device (pv_gfa.cuh) and the
+        # whole file -> file chain (open + decompose + index + call + VCF text) in one process, CUDA context already up
+        gfa_leg = None
+        if rank == 0 and not args.no_gfa_leg:
+            gfa_fp = os.path.join(tempfile.gettempdir(), f"povu_bench_{os.getpid()}.gfa")
+            synth.write_gfa_fast(synth.snp_indel_chain(args.bubbles, n_paths=args.paths, seed=42 + rank, with_seqs=True), gfa_fp)
+            try:
+                opens, chain = [], []
+                for i in range(4):
+                    t0 = time.perf_counter()
+                    s2 = api.Session(pv, gfa_fp)
+                    t1 = time.perf_counter()
+                    s2.hot_path(prefixes, keep_resident=True)
+                    s2.vcf_write("/dev/null")
+                    t2 = time.perf_counter()
+                    st = s2.gfa_stats()
+                    s2.close()
+                    if i:                                   # the first open allocates the page-locked staging pool
+                        opens.append(((t1 - t0) * 1e3, st["read_ms"], st["parse_ms"]))
+                        chain.append((t2 - t0) * 1e3)
+                t0 = time.perf_counter()
+                s2 = api.Session(pv, gfa_fp, host_parser=True)
+                host_ms = (time.perf_counter() - t0) * 1e3
+                s2.close()
+                best = min(opens)
+                gfa_leg = {"text_bytes": st["text_bytes"], "open_ms": best[0], "file_to_hbm_ms": best[1], "device_parse_ms": best[2],
+                           "text_GBps": st["text_bytes"] / best[0] / 1e6, "host_loader_ms": host_ms,
+                           "gfa_file_to_vcf_file_ms": min(chain),
+                           "note": "pvgpu_session_open on the cfg2 GFA text in the page cache: threaded pread -> page-locked staging -> HBM, parsed by the G_* kernels; "
+                                   "host_loader_ms = the sequential host loader on the same file; gfa_file_to_vcf_file_ms = open + decompose + index + call + device VCF text + write(2)"}
+            finally:
+                os.unlink(gfa_fp)
+
         prof = None
         if rank == 0 and args.profile_steps > 0:
             pv.set_profiling(True)
@@ -327,7 +361,7 @@ def run_native(args):
                 "e2e": {"value": world * E / (e2e_ms_max / e2e_steps * 1e-3), "unit": "edges/s", "h2d_bytes_per_step": 8 * E + 4 * S + 4 * V, "d2h_bytes_per_step": d2h_bytes,
                         "ms_per_step": e2e_ms_max / e2e_steps, "steps": e2e_steps,
                         "vcf_text": {"bytes": text_bytes, "ms": text_s * 1e3, "note": "record lines written by the device text kernels (X_len, X_write), D2H into a page-locked buffer, write(2) to /dev/null; wall time of one pvgpu_session_vcf_write call, not inside e2e (SURVEY.md 8f2)"}},
-                "gpu_launches": int(launches), "wall_s_timed_region": wall,
+                "gfa_text": gfa_leg, "gpu_launches": int(launches), "wall_s_timed_region": wall,
                 "clocks": clk, "roofline": roofline, "cpu_baseline": cpu, "peak_device_bytes": pv.peak_bytes}
         print(json.dumps(line))
     if world > 1:

@@ -8,7 +8,8 @@
 // doing anything) and app/subcommand/{gfa2vcf,decompose,call}.cpp (outputs, error text, exit codes).
 // Host code only: all graph work goes through the C ABI of libpovu_b200.so (include/povu_b200.h).
 // Not provided (outside the hot path): info, prune, vcf, --structure-export,
-// -s/--subflubbles, -g/--restrict -- they fail loudly instead of silently doing something else.
+// -s/--subflubbles -- they fail loudly instead of silently doing something else.
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -95,6 +96,7 @@ static int cli(int argc, char **argv, Config &c) {
 }
 
 struct Fail { std::string what; };
+static double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
 static std::vector<std::string> prefixes_of(const Config &c) {
 	if (!c.prefix_file.empty()) {
@@ -108,12 +110,14 @@ static std::vector<std::string> prefixes_of(const Config &c) {
 }
 
 struct Dev {
-	pvgpu_ctx *ctx = nullptr; pvgpu_session *s = nullptr;
+	pvgpu_ctx *ctx = nullptr; pvgpu_session *s = nullptr; double t_create_ms = 0;
 	~Dev() { if (s) pvgpu_session_close(s); if (ctx) pvgpu_destroy(ctx); }
 	void open(const Config &c, bool labels, bool refs) {
 		int dev = 0;
 		if (const char *e = getenv("POVU_B200_DEVICE")) dev = atoi(e);
+		double t0 = now_ms();
 		if (pvgpu_create(dev, nullptr, &ctx) != 0) throw Fail{"no usable CUDA device (povu_b200 has no CPU fallback)"};
+		t_create_ms = now_ms() - t0;
 		if (pvgpu_session_open(ctx, c.gfa.c_str(), labels, refs, &s) != 0) throw Fail{pvgpu_last_error(ctx)};
 	}
 	void check(int rc) { if (rc != 0) throw Fail{pvgpu_last_error(ctx)}; }
@@ -167,6 +171,8 @@ static void write_vcfs(const Config &c, Dev &d, const std::vector<std::string> &
 }
 
 int main(int argc, char **argv) {
+	const double t_main = now_ms();
+	struct AtExit { double t0; ~AtExit() { if (getenv("POVU_B200_TIMING")) fprintf(stderr, "[povu_b200] main() %.1f ms\n", now_ms() - t0); } } at_exit{t_main};
 	Config c;
 	cli(argc, argv, c);
 	if (c.task.empty()) return 0;               // app/main.cpp:15 ignores cli()'s return value
@@ -181,20 +187,25 @@ int main(int argc, char **argv) {
 			Dev d; d.open(c, true, true);
 			if (pvgpu_session_read_pvst(d.s, c.forest_dir.c_str()) != 0) { fprintf(stderr, "ERROR [povu::subcommands::call] %s\n", pvgpu_last_error(d.ctx)); return EXIT_FAILURE; }
 			write_vcfs(c, d, prefixes_of(c));
-		} else {   // gfa2vcf: decompose into a temporary forest directory, then call from it (gfa2vcf.cpp:25-70)
-			char tmpl[] = "/tmp/povu_gfa2vcf_XXXXXX";
-			char *tmp = mkdtemp(tmpl);
-			if (!tmp) { fprintf(stderr, "%s Error: Could not create temporary directory\n", fn.c_str()); return EXIT_FAILURE; }
-			std::string tmp_dir = tmp;
-			auto cleanup = [&]() { std::string cmd = "rm -rf '" + tmp_dir + "'"; if (system(cmd.c_str())) {} };
-			if (c.verbosity > 0) fprintf(stderr, "%s Using temporary directory: %s\n", fn.c_str(), tmp_dir.c_str());
+		} else {
+			// gfa2vcf: the reference decomposes into a temporary forest directory and calls from the .pvst files it reads
+			// back (gfa2vcf.cpp:25-70).  Here the flubble forest goes from decompose to call inside HBM: no text round trip.
 			try {
+				double t0 = now_ms();
 				Dev d; d.open(c, true, true);
-				do_decompose(c, d, tmp_dir);
-				d.check(pvgpu_session_read_pvst(d.s, tmp_dir.c_str()));
+				double t1 = now_ms();
+				d.check(pvgpu_session_decompose(d.s));
+				if (c.verbosity > 1) fprintf(stderr, "INFO [povu::decompose] Found %u components with at least 3 vertices\n", pvgpu_session_tree_count(d.s));
+				double t2 = now_ms();
 				write_vcfs(c, d, prefixes_of(c));
-			} catch (Fail &e) { cleanup(); fprintf(stderr, "%s Error: %s\n", fn.c_str(), e.what.c_str()); return EXIT_FAILURE; }
-			cleanup();
+				double t3 = now_ms();
+				if (getenv("POVU_B200_TIMING")) {
+					uint64_t nb = 0; double ms[2] = {0, 0};
+					pvgpu_session_gfa_stats(d.s, &nb, ms);
+					fprintf(stderr, "[povu_b200] gfa2vcf: CUDA context %.1f ms, GFA open %.1f ms (file -> HBM %.1f, device parse %.1f; %llu bytes), decompose %.1f ms, call + VCF text %.1f ms\n",
+						d.t_create_ms, t1 - t0 - d.t_create_ms, ms[0], ms[1], (unsigned long long)nb, t2 - t1, t3 - t2);
+				}
+			} catch (Fail &e) { fprintf(stderr, "%s Error: %s\n", fn.c_str(), e.what.c_str()); return EXIT_FAILURE; }
 		}
 	} catch (Fail &e) {
 		fprintf(stderr, "%s Error: %s\n", fn.c_str(), e.what.c_str());

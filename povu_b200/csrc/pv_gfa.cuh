@@ -151,14 +151,14 @@ struct GfaDev {
 	double ms_read = 0, ms_parse = 0;
 };
 
-// file -> device memory.  A few host threads pread(2) interleaved 4 MiB blocks of the file into page-locked staging buffers
+// file -> device memory.  A few host threads pread(2) interleaved 1 MiB blocks of the file into page-locked staging buffers
 // (two per thread: the read of one block overlaps the H2D of the previous one) and enqueue the copies on the context's
 // stream, so the page-cache -> staging memcpy (the slow leg, ~3 GB/s per core) runs on several cores while PCIe streams.
 // The staging buffers are pooled per process.  T gets n + 32 bytes, the tail zeroed, so that 16-byte chunk loads never
 // run off the allocation.
 #ifndef PV_EMU
 struct GfaStagePool {
-	static const size_t BLK = 4u << 20;
+	static const size_t BLK = 1u << 20;
 	std::mutex m; std::vector<char *> free_;
 	char *get() {
 		{ std::lock_guard<std::mutex> l(m); if (!free_.empty()) { char *p = free_.back(); free_.pop_back(); return p; } }

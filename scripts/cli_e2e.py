@@ -1,0 +1,41 @@
+#!/usr/bin/env python
+"""`povu gfa2vcf` end to end on the cfg2 GFA text: our CLI (process start -> VCF file on disk) next to the UNMODIFIED
+reference binary (oracle/_ref/povu_ref) on the same file, outputs compared byte for byte (##fileDate aside).
+usage: cli_e2e.py [n_bubbles] [--no-ref]"""
+import json
+import os
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from povu_b200 import synth  # noqa: E402
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 and sys.argv[1].isdigit() else 400_000
+CLI = os.path.join(ROOT, "povu_b200", "bin", "povu")
+REF = os.path.join(ROOT, "oracle", "_ref", "povu_ref")
+fp = "/tmp/cli_e2e.gfa"
+g = synth.snp_indel_chain(n, n_paths=16, seed=42, with_seqs=True)
+synth.write_gfa_fast(g, fp)
+open(fp, "rb").read()
+out = {"workload": f"snp_indel_chain({n} bubbles), 16 haplotype paths", "gfa_bytes": os.path.getsize(fp), "host_cores": os.cpu_count()}
+runs = []
+for i in range(4):
+    t0 = time.perf_counter()
+    with open("/tmp/cli_e2e_ours.vcf", "wb") as f:
+        r = subprocess.run([CLI, "gfa2vcf", "-i", fp, "-P", "S001#1"], stdout=f, stderr=subprocess.PIPE, env=dict(os.environ, POVU_B200_TIMING="1"))
+    runs.append({"wall_s": time.perf_counter() - t0, "phases": r.stderr.decode().strip().splitlines()[-2:] if r.stderr else ""})
+    assert r.returncode == 0, r.stderr.decode()
+out["povu_b200"] = {"wall_s": min(x["wall_s"] for x in runs), "runs": runs, "vcf_bytes": os.path.getsize("/tmp/cli_e2e_ours.vcf")}
+if "--no-ref" not in sys.argv and os.path.exists(REF):
+    t0 = time.perf_counter()
+    with open("/tmp/cli_e2e_ref.vcf", "wb") as f:
+        r = subprocess.run([REF, "gfa2vcf", "-i", fp, "-P", "S001#1", "-t", "1"], stdout=f, stderr=subprocess.PIPE)
+    out["reference"] = {"wall_s": time.perf_counter() - t0, "rc": r.returncode}
+    strip = lambda p: [l for l in open(p, "rb").read().split(b"\n") if not l.startswith(b"##fileDate")]
+    a, b = strip("/tmp/cli_e2e_ours.vcf"), strip("/tmp/cli_e2e_ref.vcf")
+    out["identical_to_reference"] = a == b
+    out["records"] = sum(1 for l in a if l and not l.startswith(b"#"))
+    out["speedup_wall"] = out["reference"]["wall_s"] / out["povu_b200"]["wall_s"]
+print(json.dumps(out, indent=1))
