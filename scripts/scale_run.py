@@ -58,6 +58,15 @@ def main():
         t_sess = time.time() - t0
         ms = s.hot_path([prefix])
         ms = s.hot_path([prefix])
+        prof_top = None
+        if os.environ.get("SCALE_PROF"):
+            pv.set_profiling(True)
+            s.hot_path([prefix])
+            prof = pv.profile()
+            pv.set_profiling(False)
+            tot = sum(k["ms"] for k in prof)
+            prof_top = [{"name": k["name"], "launches": k["launches"], "ms": round(k["ms"], 3), "share": round(k["ms"] / tot, 3),
+                         "GBps": round(k["bytes"] / (k["ms"] * 1e-3) / 1e9, 1) if k["ms"] > 0 else None} for k in sorted(prof, key=lambda k: -k["ms"])[:14]]
         st = s.call_stats()
         nrec = int(s.lib.pvgpu_session_record_count(s.h)); nfl = int(s.lib.pvgpu_session_flubble_count(s.h))
         assert st["hard_errors"] == 0
@@ -85,7 +94,7 @@ def main():
         out[cfg] = {"V": V, "E": E, "paths": len(g["paths"]), "steps": S, "flubbles": nfl, "records": nrec, "ms_upload_dec_index_call": ms, "stats": st,
                     "sample_check": {"prefix_vertices": cut + 1, "reference_records_compared": len(want), "bit_exact": ok, "reference_s": t_ref},
                     "edges_per_s": E / ((ms[1] + ms[2] + ms[3]) * 1e-3), "records_per_s": nrec / ((ms[2] + ms[3]) * 1e-3),
-                    "gen_s": t_gen, "session_s": t_sess, "text_s": t_text, "peak_device_GB": pv.peak_bytes / 1e9}
+                    "top_kernels": prof_top, "gen_s": t_gen, "session_s": t_sess, "text_s": t_text, "peak_device_GB": pv.peak_bytes / 1e9}
         print(cfg, json.dumps(out[cfg]), flush=True)
         assert ok, "sample differs from the reference"
         s.close(); pv.close()
