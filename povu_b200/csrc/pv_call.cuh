@@ -38,6 +38,8 @@ PV_KERNEL(C_loci_len, 12);
 PV_KERNEL(C_loci, 20);
 PV_KERNEL(C_vs_key, 12);
 PV_KERNEL(C_vs_hap, 12);
+PV_KERNEL(C_vs_slot, 16);
+PV_KERNEL(C_vs_sort, 16);
 PV_KERNEL(C_uf, 16);
 PV_KERNEL(C_color, 32);
 PV_KERNEL(C_child, 12);
@@ -172,14 +174,45 @@ inline void graph_build(Ctx &c, u32 V, u64 E, const u32 *ep1, const u32 *ep2, u3
 		});
 	}
 	{
-		// vertex -> steps index: stable sort of the step indices by vertex
-		Buf<u32> key(c, S ? S : 1), cnt(c, (size_t)V + 1);
-		cnt.zero();
-		u32 *key_ = key.p, *cnt_ = cnt.p, *vsStep_ = g.vsStep.p, *vsHap_ = g.vsHap.p;
-		parallel_for<C_vs_key>(c, S, PV_LAMBDA(size_t s) { u32 v = steps_[s] >> 1; key_[s] = v; vsStep_[s] = (u32)s; atomic_add(cnt_ + v, 1u); });
-		radix_sort_pairs(c, key, g.vsStep, S, bits_for(V));
-		vsStep_ = g.vsStep.p;
+		// vertex -> steps index = the step indices grouped by vertex, ascending inside a vertex.  Almost every vertex is
+		// visited a handful of times, so instead of a full stable sort of all S pairs: count, scan, drop every step into a
+		// free slot of its vertex (atomic cursor, arbitrary order) and let one thread per vertex insertion-sort its short
+		// list.  Steps on the few hub vertices (more than VS_SMALL visits) take the stable radix sort, restricted to them.
+		u32 vs_small = 48;
+		if (const char *e = getenv("POVU_B200_VS_SMALL")) vs_small = (u32)strtoul(e, nullptr, 10);   // tests: force the hub path
+		const u32 VS_SMALL = vs_small;
+		Buf<u32> cnt(c, (size_t)V + 1), cur(c, V ? V : 1), nBigBuf(c, 1);
+		cnt.zero(); cur.zero(); nBigBuf.zero();
+		u32 *cnt_ = cnt.p, *cur_ = cur.p, *nBig_ = nBigBuf.p, *vsStep_ = g.vsStep.p, *vsHap_ = g.vsHap.p, *vsOff_ = g.vsOff.p;
+		parallel_for<C_vs_key>(c, S, PV_LAMBDA(size_t s) { atomic_add(cnt_ + (steps_[s] >> 1), 1u); });
 		exclusive_scan(c, cnt.p, g.vsOff.p, (size_t)V + 1, OpAddU32(), 0u);
+		parallel_for<C_vs_slot>(c, S, PV_LAMBDA(size_t s) {
+			u32 v = steps_[s] >> 1;
+			if (cnt_[v] > VS_SMALL) return;
+			vsStep_[vsOff_[v] + atomic_add(cur_ + v, 1u)] = (u32)s;
+		});
+		parallel_for<C_vs_sort>(c, V, PV_LAMBDA(size_t v) {
+			u32 n = cnt_[v];
+			if (n > VS_SMALL) { atomic_add(nBig_, n); return; }
+			u32 *a = vsStep_ + vsOff_[v];
+			for (u32 i = 1; i < n; i++) { u32 x = a[i]; u32 j = i; while (j > 0 && a[j - 1] > x) { a[j] = a[j - 1]; j--; } a[j] = x; }
+		});
+		const u32 nBig = nBigBuf.read(0);
+		if (nBig) {
+			Buf<u32> flag(c, S), idx;
+			u32 *flag_ = flag.p;
+			parallel_for<C_vs_slot>(c, S, PV_LAMBDA(size_t s) { flag_[s] = cnt_[steps_[s] >> 1] > VS_SMALL ? 1u : 0u; });
+			const u32 nb = compact_flags(c, flag.p, S, idx);   // ascending step index
+			flag.release();
+			Buf<u32> key(c, nb), val(c, nb);
+			u32 *key_ = key.p, *val_ = val.p; const u32 *idx_ = idx.p;
+			parallel_for<C_vs_key>(c, nb, PV_LAMBDA(size_t i) { u32 st = idx_[i]; key_[i] = steps_[st] >> 1; val_[i] = st; });
+			radix_sort_pairs(c, key, val, nb, bits_for(V));
+			key_ = key.p; val_ = val.p;
+			// first sorted position of every hub vertex (cur is free again: hubs never touched it)
+			parallel_for<C_vs_key>(c, nb, PV_LAMBDA(size_t i) { if (i == 0 || key_[i - 1] != key_[i]) cur_[key_[i]] = (u32)i; });
+			parallel_for<C_vs_slot>(c, nb, PV_LAMBDA(size_t i) { u32 v = key_[i]; vsStep_[vsOff_[v] + ((u32)i - cur_[v])] = val_[i]; });
+		}
 		parallel_for<C_vs_hap>(c, S, PV_LAMBDA(size_t i) { vsHap_[i] = ub_u32(stepOff_, 0, H + 1, vsStep_[i]) - 1; });
 	}
 	tr.mark("loci + vertex->steps");

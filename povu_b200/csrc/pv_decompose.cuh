@@ -71,8 +71,7 @@ PV_KERNEL(K_start, 12);
 PV_KERNEL(K_claim, 28);
 PV_KERNEL(K_entry, 24);
 PV_KERNEL(K_first_edge, 28);
-PV_KERNEL(K_mark, 16);
-PV_KERNEL(K_jump, 12);         // J[x], J[J[x]] in, J'[x] out
+PV_KERNEL(K_mark, 24);         // J[x], J[J[x]], rnk[x] in, J'[x] out (+ the marks)
 PV_KERNEL(K_segconf, 12);
 PV_KERNEL(K_finalize, 36);
 PV_KERNEL(K_visit, 16);
@@ -271,25 +270,21 @@ inline void decompose_device(Ctx &c, u32 V, u64 E, const u32 *ep1, const u32 *ep
 			u32 *itFlag_ = itFlag.p;
 			for (int it = 0; it < maxIt; it++) {
 				const u32 lim = 1u << it;
+				// one launch per doubling step: mark J^(2^it)-successors of the nodes ranked below 2^it, and square the jump
+				// pointers for the next step (the squaring runs one step past convergence; its result is then unused)
 				parallel_for<K_mark>(c, (size_t)nA * 2, PV_LAMBDA(size_t i) {
 					if (it > 0 && itFlag_[(it - 1) * 32] == 0) return;
 					u32 v = act[i >> 1]; u32 x = 2 * v + (u32)(i & 1);
-					u32 r = rnk_[x];
-					if (r >= lim) return;                       // NONE or marked in this very iteration
 					u32 y = Ja[x];
-					if (y == NONE) return;
+					Jb[x] = y == NONE ? NONE : Ja[y];
+					u32 r = rnk_[x];
+					if (r >= lim || y == NONE) return;          // NONE or marked in this very iteration
 					u32 rho = r + lim;
 					u32 old = atomic_min(rnk_ + y, rho);
 					if (old != NONE && old != rho) atomic_min(trunc_ + comp_[v], old > rho ? old : rho);
 					itFlag_[it * 32] = 1;
 				});
 				if ((it == 1 || (it & 7) == 7) && !itFlag.read((size_t)it * 32)) break;
-				parallel_for<K_jump>(c, (size_t)nA * 2, PV_LAMBDA(size_t i) {
-					if (itFlag_[it * 32] == 0) return;
-					u32 v = act[i >> 1]; u32 x = 2 * v + (u32)(i & 1);
-					u32 y = Ja[x];
-					Jb[x] = y == NONE ? NONE : Ja[y];
-				});
 				std::swap(Ja, Jb);
 			}
 		}

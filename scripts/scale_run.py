@@ -56,8 +56,8 @@ def main():
         t0 = time.time()
         s = api.Session.from_graph(pv, g)
         t_sess = time.time() - t0
-        ms = s.hot_path([prefix])
-        ms = s.hot_path([prefix])
+        for _ in range(4):           # the page-locked result vectors and the device pool reach their steady state after 3 calls
+            ms = s.hot_path([prefix])
         prof_top = None
         if os.environ.get("SCALE_PROF"):
             pv.set_profiling(True)

@@ -51,3 +51,10 @@ def test_emu_call_inversions_vs_reference(emu_lib, built, tmp_path):
 
 def test_emu_call_cyclic_vs_reference(emu_lib, built, tmp_path):
     cc.run_cyclic_vs_reference(_ctx(emu_lib, 1), str(tmp_path), n_seeds=24)
+
+
+@pytest.mark.parametrize("name", ["nested_s1", "hairpin_inversion_subr", "LPA"])
+def test_emu_call_hub_vertices(emu_lib, name, tmp_path, monkeypatch):
+    """vertex -> steps index: every vertex visited more than once takes the hub path (restricted stable sort)"""
+    monkeypatch.setenv("POVU_B200_VS_SMALL", "1")
+    cc.check_golden(_ctx(emu_lib, 2), name, str(tmp_path))

@@ -43,3 +43,10 @@ def test_gpu_call_inversions_vs_reference(gpu, tmp_path):
 
 def test_gpu_call_cyclic_vs_reference(gpu, tmp_path):
     cc.run_cyclic_vs_reference(gpu, str(tmp_path), n_seeds=40)
+
+
+@pytest.mark.parametrize("name", ["nested_s1", "hairpin_inversion_subr", "LPA"])
+def test_gpu_call_hub_vertices(gpu, name, tmp_path, monkeypatch):
+    """vertex -> steps index: every vertex visited more than once takes the hub path (restricted stable sort)"""
+    monkeypatch.setenv("POVU_B200_VS_SMALL", "1")
+    cc.check_golden(gpu, name, str(tmp_path))
