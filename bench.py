@@ -355,7 +355,9 @@ def run_native(args):
                 "config": {"workload": workload_name(args.bubbles, args.paths), "segments": V, "links": E, "paths": args.paths, "path_steps": S, "components_per_gpu": 1,
                            "flubbles": n_fl, "records": n_rec, "ref_prefix": REF_PREFIX,
                            "l2": "256 MiB flush write between timed steps (untimed); per-step CUDA events summed",
-                           "sharding": "one independent component per rank, no collective on the data path"},
+                           "sharding": "one independent component per rank, no collective on the data path",
+                           "outputs": "value: the flubble table reaches the host (copy overlapped), the binary records stay in HBM where the device VCF writer reads them; "
+                                      "e2e: inputs from page-locked host arrays (walks uploaded behind decompose) and the binary records copied to the host as well"},
                 "parts": {"decompose_edges_per_sec": world * E / (pm[1] * 1e-3), "call_records_per_sec": tot_rec / ((pm[2] + pm[3]) * 1e-3),
                           "ms": {"decompose": pm[1], "path_index_build": pm[2], "call": pm[3]}, "records_all_ranks": tot_rec, "flubbles_all_ranks": tot_fl, "call_stats": stats},
                 "e2e": {"value": world * E / (e2e_ms_max / e2e_steps * 1e-3), "unit": "edges/s", "h2d_bytes_per_step": 8 * E + 4 * S + 4 * V, "d2h_bytes_per_step": d2h_bytes,

@@ -38,8 +38,6 @@ PV_KERNEL(C_loci_len, 12);
 PV_KERNEL(C_loci, 20);
 PV_KERNEL(C_vs_key, 12);
 PV_KERNEL(C_vs_hap, 12);
-PV_KERNEL(C_vs_slot, 16);
-PV_KERNEL(C_vs_sort, 16);
 PV_KERNEL(C_uf, 16);
 PV_KERNEL(C_color, 32);
 PV_KERNEL(C_child, 12);
@@ -77,6 +75,8 @@ PV_DEV u64 ub_u64(const u64 *a, u64 lo, u64 hi, u64 key) {
 // ---------------------------------------------------------------------------------------------
 // device-resident graph + paths (built once, used by every call)
 // ---------------------------------------------------------------------------------------------
+struct StepVertex { const u32 *steps; PV_DEV u32 operator()(size_t s) const { return steps[s] >> 1; } };
+
 struct DevGraph {
 	u32 V = 0, H = 0, S = 0; u64 E = 0;
 	Buf<u32> adjOff, adjNbr;
@@ -174,45 +174,11 @@ inline void graph_build(Ctx &c, u32 V, u64 E, const u32 *ep1, const u32 *ep2, u3
 		});
 	}
 	{
-		// vertex -> steps index = the step indices grouped by vertex, ascending inside a vertex.  Almost every vertex is
-		// visited a handful of times, so instead of a full stable sort of all S pairs: count, scan, drop every step into a
-		// free slot of its vertex (atomic cursor, arbitrary order) and let one thread per vertex insertion-sort its short
-		// list.  Steps on the few hub vertices (more than VS_SMALL visits) take the stable radix sort, restricted to them.
+		// vertex -> steps index = the step indices grouped by vertex, ascending inside a vertex (group_indices, pv_prims.cuh)
 		u32 vs_small = 48;
 		if (const char *e = getenv("POVU_B200_VS_SMALL")) vs_small = (u32)strtoul(e, nullptr, 10);   // tests: force the hub path
-		const u32 VS_SMALL = vs_small;
-		Buf<u32> cnt(c, (size_t)V + 1), cur(c, V ? V : 1), nBigBuf(c, 1);
-		cnt.zero(); cur.zero(); nBigBuf.zero();
-		u32 *cnt_ = cnt.p, *cur_ = cur.p, *nBig_ = nBigBuf.p, *vsStep_ = g.vsStep.p, *vsHap_ = g.vsHap.p, *vsOff_ = g.vsOff.p;
-		parallel_for<C_vs_key>(c, S, PV_LAMBDA(size_t s) { atomic_add(cnt_ + (steps_[s] >> 1), 1u); });
-		exclusive_scan(c, cnt.p, g.vsOff.p, (size_t)V + 1, OpAddU32(), 0u);
-		parallel_for<C_vs_slot>(c, S, PV_LAMBDA(size_t s) {
-			u32 v = steps_[s] >> 1;
-			if (cnt_[v] > VS_SMALL) return;
-			vsStep_[vsOff_[v] + atomic_add(cur_ + v, 1u)] = (u32)s;
-		});
-		parallel_for<C_vs_sort>(c, V, PV_LAMBDA(size_t v) {
-			u32 n = cnt_[v];
-			if (n > VS_SMALL) { atomic_add(nBig_, n); return; }
-			u32 *a = vsStep_ + vsOff_[v];
-			for (u32 i = 1; i < n; i++) { u32 x = a[i]; u32 j = i; while (j > 0 && a[j - 1] > x) { a[j] = a[j - 1]; j--; } a[j] = x; }
-		});
-		const u32 nBig = nBigBuf.read(0);
-		if (nBig) {
-			Buf<u32> flag(c, S), idx;
-			u32 *flag_ = flag.p;
-			parallel_for<C_vs_slot>(c, S, PV_LAMBDA(size_t s) { flag_[s] = cnt_[steps_[s] >> 1] > VS_SMALL ? 1u : 0u; });
-			const u32 nb = compact_flags(c, flag.p, S, idx);   // ascending step index
-			flag.release();
-			Buf<u32> key(c, nb), val(c, nb);
-			u32 *key_ = key.p, *val_ = val.p; const u32 *idx_ = idx.p;
-			parallel_for<C_vs_key>(c, nb, PV_LAMBDA(size_t i) { u32 st = idx_[i]; key_[i] = steps_[st] >> 1; val_[i] = st; });
-			radix_sort_pairs(c, key, val, nb, bits_for(V));
-			key_ = key.p; val_ = val.p;
-			// first sorted position of every hub vertex (cur is free again: hubs never touched it)
-			parallel_for<C_vs_key>(c, nb, PV_LAMBDA(size_t i) { if (i == 0 || key_[i - 1] != key_[i]) cur_[key_[i]] = (u32)i; });
-			parallel_for<C_vs_slot>(c, nb, PV_LAMBDA(size_t i) { u32 v = key_[i]; vsStep_[vsOff_[v] + ((u32)i - cur_[v])] = val_[i]; });
-		}
+		u32 *vsStep_ = g.vsStep.p, *vsHap_ = g.vsHap.p;
+		group_indices(c, StepVertex{steps_}, S, V, g.vsOff.p, g.vsStep.p, vs_small);
 		parallel_for<C_vs_hap>(c, S, PV_LAMBDA(size_t i) { vsHap_[i] = ub_u32(stepOff_, 0, H + 1, vsStep_[i]) - 1; });
 	}
 	tr.mark("loci + vertex->steps");
@@ -453,7 +419,16 @@ struct CallIn {           // PVST forest, flubbles of all components concatenate
 };
 
 // binary records, written by the device into page-locked host vectors whose capacity survives across calls
+// the records of one (chunk, ref) emission as they were produced in HBM; offsets (grpOff, gtOff) are already global
+struct RecPiece {
+	Buf<u32> rov, ref, cxtL, cxtR, vt, pos, refStart, refLen, grpOff /* nRec + 1 */, gHap, gStart, gLen, gCnt; Buf<u64> gtOff /* nRec + 1 */; Buf<u16> gt;
+	u32 nRec = 0, nGrp = 0; u64 nGt = 0;
+};
 struct Records {
+	// Records are born in HBM (`dev`) and stay there for the device text writer; the host vectors below are filled on
+	// demand by to_host() (povu_ffi / record_lines / the bench's e2e leg).
+	std::vector<RecPiece> dev; size_t copied = 0;       // pieces [0, copied) are already in the host vectors
+	size_t nRecTot = 0, nGrpTot = 0; u64 nGtTot = 0;
 	// regions (RoVs) in enumeration order: ascending (component file, PVST vertex idx), >= 3 sorted vertices
 	hvec<u32> rov_fl, rov_comp, rov_tangled;
 	// records: grouped per (region, ref) in context order, INS / SUB / DEL
@@ -465,8 +440,54 @@ struct Records {
 	u64 n_subr_clamped = 0;   // SUBR records whose merged length ran past the end of a walk (the reference reads out of bounds there)
 	u64 n_regions = 0;   // real regions; rov_* entries beyond them are per-ref pseudo regions that carry the SUBR records
 	u64 n_called = 0, n_too_small = 0, n_sort_failed = 0, n_tangled = 0, n_pin_pairs = 0, n_hard_errors = 0, n_chunks = 0, n_big_bfs = 0, max_J = 0;
-	size_t n() const { return rec_rov.size(); }
+	size_t n() const { return nRecTot; }
+	void add_piece(RecPiece &&p) { nRecTot += p.nRec; nGrpTot += p.nGrp; nGtTot += p.nGt; dev.push_back(std::move(p)); }
+	// append the device pieces that have not been copied yet to the page-locked host vectors
+	void to_host(Ctx &c) {
+		if (copied == dev.size()) return;
+		rec_rov.reserve(nRecTot); rec_ref.reserve(nRecTot); rec_cxtL.reserve(nRecTot); rec_cxtR.reserve(nRecTot); rec_vt.reserve(nRecTot); rec_pos.reserve(nRecTot);
+		rec_refStart.reserve(nRecTot); rec_refLen.reserve(nRecTot); rec_grpOff.reserve(nRecTot + 1); rec_gtOff.reserve(nRecTot + 1);
+		grp_hap.reserve(nGrpTot); grp_start.reserve(nGrpTot); grp_len.reserve(nGrpTot); grp_count.reserve(nGrpTot); gt.reserve(nGtTot);   // no reallocation under the copies in flight
+		for (; copied < dev.size(); copied++) {
+			const RecPiece &p = dev[copied];
+			const size_t recBase = rec_rov.size(); const u64 gtBase = gt.size();
+			auto app = [&](hvec<u32> &dst, const Buf<u32> &src, u32 m) { size_t o = dst.size(); dst.resize(o + m); c.d2h_async(dst.data() + o, src.p, (size_t)m * 4); };
+			app(rec_rov, p.rov, p.nRec); app(rec_ref, p.ref, p.nRec); app(rec_cxtL, p.cxtL, p.nRec); app(rec_cxtR, p.cxtR, p.nRec); app(rec_vt, p.vt, p.nRec); app(rec_pos, p.pos, p.nRec);
+			app(rec_refStart, p.refStart, p.nRec); app(rec_refLen, p.refLen, p.nRec);
+			app(grp_hap, p.gHap, p.nGrp); app(grp_start, p.gStart, p.nGrp); app(grp_len, p.gLen, p.nGrp); app(grp_count, p.gCnt, p.nGrp);
+			rec_grpOff.resize(recBase + p.nRec + 1); c.d2h_async(rec_grpOff.data() + recBase, p.grpOff.p, ((size_t)p.nRec + 1) * 4);
+			rec_gtOff.resize(recBase + p.nRec + 1); c.d2h_async(rec_gtOff.data() + recBase, p.gtOff.p, ((size_t)p.nRec + 1) * 8);
+			gt.resize(gtBase + p.nGt); c.d2h_async(gt.data() + gtBase, p.gt.p, p.nGt * 2);
+		}
+		c.sync();
+	}
+	// all records as ONE device piece (the text writer reads flat arrays): several pieces are concatenated once
+	const RecPiece &flat(Ctx &c) {
+		if (dev.size() == 1) return dev[0];
+		RecPiece f; f.nRec = (u32)nRecTot; f.nGrp = (u32)nGrpTot; f.nGt = nGtTot;
+		const size_t R1 = nRecTot ? nRecTot : 1, G1 = nGrpTot ? nGrpTot : 1;
+		f.rov = Buf<u32>(c, R1); f.ref = Buf<u32>(c, R1); f.cxtL = Buf<u32>(c, R1); f.cxtR = Buf<u32>(c, R1); f.vt = Buf<u32>(c, R1); f.pos = Buf<u32>(c, R1);
+		f.refStart = Buf<u32>(c, R1); f.refLen = Buf<u32>(c, R1); f.grpOff = Buf<u32>(c, R1 + 1); f.gtOff = Buf<u64>(c, R1 + 1);
+		f.gHap = Buf<u32>(c, G1); f.gStart = Buf<u32>(c, G1); f.gLen = Buf<u32>(c, G1); f.gCnt = Buf<u32>(c, G1); f.gt = Buf<u16>(c, nGtTot ? nGtTot : 1);
+		size_t ro = 0, go = 0; u64 to = 0;
+		if (dev.empty()) { c.memset0(f.grpOff.p, 4); c.memset0(f.gtOff.p, 8); }
+		for (const RecPiece &p : dev) {
+			c.d2d(f.rov.p + ro, p.rov.p, (size_t)p.nRec * 4); c.d2d(f.ref.p + ro, p.ref.p, (size_t)p.nRec * 4); c.d2d(f.cxtL.p + ro, p.cxtL.p, (size_t)p.nRec * 4);
+			c.d2d(f.cxtR.p + ro, p.cxtR.p, (size_t)p.nRec * 4); c.d2d(f.vt.p + ro, p.vt.p, (size_t)p.nRec * 4); c.d2d(f.pos.p + ro, p.pos.p, (size_t)p.nRec * 4);
+			c.d2d(f.refStart.p + ro, p.refStart.p, (size_t)p.nRec * 4); c.d2d(f.refLen.p + ro, p.refLen.p, (size_t)p.nRec * 4);
+			c.d2d(f.grpOff.p + ro, p.grpOff.p, ((size_t)p.nRec + 1) * 4); c.d2d(f.gtOff.p + ro, p.gtOff.p, ((size_t)p.nRec + 1) * 8);
+			c.d2d(f.gHap.p + go, p.gHap.p, (size_t)p.nGrp * 4); c.d2d(f.gStart.p + go, p.gStart.p, (size_t)p.nGrp * 4); c.d2d(f.gLen.p + go, p.gLen.p, (size_t)p.nGrp * 4);
+			c.d2d(f.gCnt.p + go, p.gCnt.p, (size_t)p.nGrp * 4); c.d2d(f.gt.p + to, p.gt.p, p.nGt * 2);
+			ro += p.nRec; go += p.nGrp; to += p.nGt;
+		}
+		if (copied != 0 && copied != dev.size()) to_host(c);   // a host copy that was begun from the pieces is finished from them
+		const bool on_host = copied != 0 || dev.empty();
+		c.sync();
+		dev.clear(); dev.push_back(std::move(f)); copied = on_host ? 1 : 0;
+		return dev[0];
+	}
 	void reset() {
+		dev.clear(); copied = 0; nRecTot = nGrpTot = 0; nGtTot = 0;
 		rov_fl.clear(); rov_comp.clear(); rov_tangled.clear();
 		rec_rov.clear(); rec_ref.clear(); rec_cxtL.clear(); rec_cxtR.clear(); rec_vt.clear(); rec_pos.clear(); rec_refStart.clear(); rec_refLen.clear();
 		rec_grpOff.clear(); rec_gtOff.clear(); grp_hap.clear(); grp_start.clear(); grp_len.clear(); grp_count.clear(); gt.clear();
@@ -694,7 +715,7 @@ inline void overlay_pass(Ctx &c, const DevGraph &G, const GraphView &g, const Ca
 		const u32 nRec = recOff.read(Rc), nGrp = grpOff.read(Rc);
 		if (nRec == 0) continue;
 		// ---- C6b: records + groups (offsets already global: the host only appends)
-		const u32 grpBase = (u32)out.grp_hap.size(); const u64 gtBase = out.gt.size(); const size_t recBase = out.rec_rov.size();
+		const u32 grpBase = (u32)out.nGrpTot; const u64 gtBase = out.nGtTot;
 		Buf<u32> oLoc(c, nRec); u32 *oLoc_ = oLoc.p;
 		Buf<u32> oRov(c, nRec), oRef(c, nRec), oL(c, nRec), oR(c, nRec), oVt(c, nRec), oPos(c, nRec), oRS(c, nRec), oRL(c, nRec), oGrp(c, (size_t)nRec + 1);
 		Buf<u32> gHap(c, nGrp), gStart(c, nGrp), gLen(c, nGrp), gCnt(c, nGrp), headRec(c, nCand), headOrd(c, nCand);
@@ -758,19 +779,15 @@ inline void overlay_pass(Ctx &c, const DevGraph &G, const GraphView &g, const Ca
 			u32 hd = cd.cHead[x]; u32 rec = headRec_[hd];
 			gt_[gtOff_[rec] + cd.cHap[x]] = (u16)headOrd_[hd];
 		});
-		// the host sees ref-slice starts relative to the ref path, and global gt offsets
-		parallel_for<C_keep>(c, (size_t)nRec + 1, PV_LAMBDA(size_t i) { if (i < nRec) oRS_[i] -= refStep0; gtOff_[i] += gtBase; });
+		// ref-slice starts relative to the ref path, global gt offsets, the group sentinel
+		parallel_for<C_keep>(c, (size_t)nRec + 1, PV_LAMBDA(size_t i) { if (i < nRec) oRS_[i] -= refStep0; else oGrp_[i] = grpBase + nGrp; gtOff_[i] += gtBase; });
 		tr.mark("C7 genotypes");
-		// ---- results of this (chunk, ref): asynchronous appends into the pinned host vectors
-		auto app = [&](hvec<u32> &dst, const Buf<u32> &src, u32 n) { size_t o = dst.size(); dst.resize(o + n); c.d2h_async(dst.data() + o, src.p, (size_t)n * 4); };
-		app(out.rec_rov, oRov, nRec); app(out.rec_ref, oRef, nRec); app(out.rec_cxtL, oL, nRec); app(out.rec_cxtR, oR, nRec); app(out.rec_vt, oVt, nRec); app(out.rec_pos, oPos, nRec);
-		app(out.rec_refStart, oRS, nRec); app(out.rec_refLen, oRL, nRec);
-		app(out.grp_hap, gHap, nGrp); app(out.grp_start, gStart, nGrp); app(out.grp_len, gLen, nGrp); app(out.grp_count, gCnt, nGrp);
-		out.rec_grpOff.resize(recBase + nRec + 1); c.d2h_async(out.rec_grpOff.data() + recBase, oGrp.p, (size_t)nRec * 4);
-		out.rec_gtOff.resize(recBase + nRec + 1); c.d2h_async(out.rec_gtOff.data() + recBase, gtOff.p, ((size_t)nRec + 1) * 8);
-		out.gt.resize(gtBase + nGt); c.d2h_async(out.gt.data() + gtBase, gt.p, nGt * 2);
-		c.sync();   // the device buffers of this round die at the end of the scope
-		out.rec_grpOff[recBase + nRec] = grpBase + nGrp;
+		// ---- the records of this (chunk, ref) stay in HBM (Records::dev); Records::to_host copies them out on demand
+		RecPiece pc;
+		pc.rov = std::move(oRov); pc.ref = std::move(oRef); pc.cxtL = std::move(oL); pc.cxtR = std::move(oR); pc.vt = std::move(oVt); pc.pos = std::move(oPos);
+		pc.refStart = std::move(oRS); pc.refLen = std::move(oRL); pc.grpOff = std::move(oGrp); pc.gHap = std::move(gHap); pc.gStart = std::move(gStart); pc.gLen = std::move(gLen);
+		pc.gCnt = std::move(gCnt); pc.gtOff = std::move(gtOff); pc.gt = std::move(gt); pc.nRec = nRec; pc.nGrp = nGrp; pc.nGt = nGt;
+		out.add_piece(std::move(pc));
 		tr.mark("records d2h");
 	}
 }
@@ -1042,8 +1059,8 @@ inline void sne_pass(Ctx &c, const DevGraph &G, const GraphView &g, const CallIn
 		const u32 comp = G.pathComp[refH]; const u32 nh = G.cpOff[comp + 1] - G.cpOff[comp];
 		const u32 pseudo = (u32)out.rov_fl.size();
 		out.rov_fl.push_back(NONE); out.rov_comp.push_back(comp);
-		const u32 grpBase = (u32)out.grp_hap.size(); const u64 gtBase = out.gt.size(); const size_t recBase = out.rec_rov.size();
-		Buf<u32> oRov(c, nRec), oRef(c, nRec), oL(c, nRec), oR2(c, nRec), oVt(c, nRec), oPos(c, nRec), oRS(c, nRec), oRL(c, nRec), oGrp(c, nRec);
+		const u32 grpBase = (u32)out.nGrpTot; const u64 gtBase = out.nGtTot;
+		Buf<u32> oRov(c, nRec), oRef(c, nRec), oL(c, nRec), oR2(c, nRec), oVt(c, nRec), oPos(c, nRec), oRS(c, nRec), oRL(c, nRec), oGrp(c, (size_t)nRec + 1);
 		Buf<u32> gHap(c, nRec), gStart(c, nRec), gLen(c, nRec), gCnt(c, nRec);
 		Buf<u64> gtOff(c, (size_t)nRec + 1);
 		Buf<u16> gt(c, (size_t)nRec * nh);
@@ -1053,7 +1070,7 @@ inline void sne_pass(Ctx &c, const DevGraph &G, const GraphView &g, const CallIn
 		const u32 rb = G.h_stepOff[refH], rn = G.h_stepOff[refH + 1] - rb;
 		parallel_for<S_gt>(c, (size_t)nRec + 1, PV_LAMBDA(size_t q) {
 			gtOff_[q] = gtBase + (u64)q * nh;
-			if (q >= nRec) return;
+			if (q >= nRec) { oGrp_[q] = grpBase + nRec; return; }
 			const u32 *o = oRec_ + 6 * q;
 			u32 s = o[0], len = o[1];
 			// a merged length is measured on the ALT walk (slice_tree.hpp:378-391) and can run past the end of the ref or
@@ -1073,15 +1090,11 @@ inline void sne_pass(Ctx &c, const DevGraph &G, const GraphView &g, const CallIn
 			row[g.hapLocal[refH]] = 0;
 			for (u32 x = 0; x < o[5]; x++) { u32 h = oHap_[o[4] + x]; if (g.pathComp[h] == comp) row[g.hapLocal[h]] = 1; }
 		});
-		auto app = [&](hvec<u32> &dst, const Buf<u32> &src, u32 m) { size_t o = dst.size(); dst.resize(o + m); c.d2h_async(dst.data() + o, src.p, (size_t)m * 4); };
-		app(out.rec_rov, oRov, nRec); app(out.rec_ref, oRef, nRec); app(out.rec_cxtL, oL, nRec); app(out.rec_cxtR, oR2, nRec); app(out.rec_vt, oVt, nRec); app(out.rec_pos, oPos, nRec);
-		app(out.rec_refStart, oRS, nRec); app(out.rec_refLen, oRL, nRec);
-		app(out.grp_hap, gHap, nRec); app(out.grp_start, gStart, nRec); app(out.grp_len, gLen, nRec); app(out.grp_count, gCnt, nRec);
-		out.rec_grpOff.resize(recBase + nRec + 1); c.d2h_async(out.rec_grpOff.data() + recBase, oGrp.p, (size_t)nRec * 4);
-		out.rec_gtOff.resize(recBase + nRec + 1); c.d2h_async(out.rec_gtOff.data() + recBase, gtOff.p, ((size_t)nRec + 1) * 8);
-		out.gt.resize(gtBase + (size_t)nRec * nh); c.d2h_async(out.gt.data() + gtBase, gt.p, (size_t)nRec * nh * 2);
-		c.sync();
-		out.rec_grpOff[recBase + nRec] = grpBase + nRec;
+		RecPiece pc;
+		pc.rov = std::move(oRov); pc.ref = std::move(oRef); pc.cxtL = std::move(oL); pc.cxtR = std::move(oR2); pc.vt = std::move(oVt); pc.pos = std::move(oPos);
+		pc.refStart = std::move(oRS); pc.refLen = std::move(oRL); pc.grpOff = std::move(oGrp); pc.gHap = std::move(gHap); pc.gStart = std::move(gStart); pc.gLen = std::move(gLen);
+		pc.gCnt = std::move(gCnt); pc.gtOff = std::move(gtOff); pc.gt = std::move(gt); pc.nRec = nRec; pc.nGrp = nRec; pc.nGt = (u64)nRec * nh;
+		out.add_piece(std::move(pc));
 		(void)nSl;
 	}
 	tr.mark("S slice trees");

@@ -360,11 +360,17 @@ void pvgpu_session_call_stats(const pvgpu_session *s, uint64_t o[12]) {
 	o[0] = c.n_called; o[1] = c.n_regions; o[2] = c.n_tangled; o[3] = c.n_pin_pairs; o[4] = c.n_sort_failed; o[5] = c.n_hard_errors; o[6] = c.n_chunks; o[7] = c.n_too_small; o[8] = c.max_J; o[9] = c.n_big_bfs; o[10] = c.n_subr_clamped; o[11] = 0;
 }
 // header (host strings) + the device-written record text (pv_text.cuh)
-static void vcf_parts(const pve::Session &S, size_t chunk, int with_date, const char *prefix, std::string &header, pv::TextOut &body) {
-	if (!prefix) { header = S.vcf_header(S.prefixes, with_date != 0); S.vcf_records_device(chunk, nullptr, body); return; }
+static void vcf_parts(const pve::Session &S, size_t chunk, int with_date, const char *prefix, std::string &header, pv::TextOut &body, int fd = -1, pv::u64 *streamed = nullptr) {
+	auto put_header = [&]() {   // streaming: the header goes out before the record text
+		if (fd < 0) return;
+		const char *p = header.data(); size_t n = header.size();
+		while (n) { ssize_t w = write(fd, p, n); if (w < 0) { if (errno == EINTR) continue; throw std::runtime_error(std::string("write failed: ") + strerror(errno)); } p += w; n -= (size_t)w; }
+	};
+	if (!prefix) { header = S.vcf_header(S.prefixes, with_date != 0); put_header(); S.vcf_records_device(chunk, nullptr, body, fd, streamed); return; }
 	std::set<pv::u32> only = pvh::refs_in_sample(S.g, prefix);
 	header = S.vcf_header({std::string(prefix)}, with_date != 0);
-	S.vcf_records_device(chunk, &only, body);
+	put_header();
+	S.vcf_records_device(chunk, &only, body, fd, streamed);
 }
 char *pvgpu_session_vcf_text(const pvgpu_session *s, size_t chunk, int with_date, const char *prefix, size_t *len) {
 	try {
@@ -382,11 +388,9 @@ char *pvgpu_session_vcf_text(const pvgpu_session *s, size_t chunk, int with_date
 }
 int pvgpu_session_vcf_write(const pvgpu_session *s, size_t chunk, int with_date, const char *prefix, int fd, uint64_t *bytes) {
 	PV_TRY(s->x, {
-		std::string header; pv::TextOut &body = s->s.text_buf;
-		vcf_parts(s->s, chunk, with_date, prefix, header, body);
-		auto put = [&](const char *p, size_t n) { while (n) { ssize_t w = write(fd, p, n); if (w < 0) { if (errno == EINTR) continue; throw std::runtime_error(std::string("write failed: ") + strerror(errno)); } p += w; n -= (size_t)w; } };
-		put(header.data(), header.size()); if (!body.text.empty()) put(body.text.data(), body.text.size());
-		if (bytes) *bytes = header.size() + body.text.size();
+		std::string header; pv::TextOut body; pv::u64 streamed = 0;
+		vcf_parts(s->s, chunk, with_date, prefix, header, body, fd, &streamed);   // device text -> ring of page-locked blocks -> write(2)
+		if (bytes) *bytes = header.size() + streamed;
 	})
 }
 int pvgpu_session_shard(pvgpu_session *s, uint32_t rank, uint32_t world, uint32_t *n_total) {

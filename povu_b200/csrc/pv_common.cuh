@@ -19,6 +19,7 @@
 #include <new>
 #include <utility>
 #include <vector>
+#include <mutex>
 
 #ifndef PV_EMU
 #include <cuda_runtime.h>
@@ -109,6 +110,16 @@ struct Ctx {
 #ifndef PV_EMU
 	cudaStream_t copy_stream = nullptr; cudaEvent_t copy_ev = nullptr;
 #endif
+	// background host -> device copies on a third stream (inputs that a later phase needs travel while an earlier phase
+	// computes): up_begin() orders the upload stream after everything issued so far (the destination buffers were allocated
+	// on the main stream), up_join() makes the MAIN STREAM wait for the uploads -- no host synchronisation.
+#ifndef PV_EMU
+	cudaStream_t up_stream = nullptr; cudaEvent_t up_ev = nullptr;
+#endif
+	bool up_pending = false;
+	void up_begin();
+	void h2d_up(void *d, const void *h, size_t bytes);
+	void up_join();
 	bool bg_pending = false;
 	void bg_begin();
 	void d2h_bg(void *h, const void *d, size_t bytes);
@@ -175,6 +186,7 @@ inline void Ctx::destroy() {
 	if (rs_status) { cudaFree(rs_status); rs_status = nullptr; rs_cap = 0; }
 	if (lb_ticket) { cudaFree(lb_ticket); lb_ticket = nullptr; }
 	if (copy_stream) { cudaStreamDestroy(copy_stream); cudaEventDestroy(copy_ev); copy_stream = nullptr; copy_ev = nullptr; }
+	if (up_stream) { cudaStreamDestroy(up_stream); cudaEventDestroy(up_ev); up_stream = nullptr; up_ev = nullptr; }
 	if (own_stream && stream) cudaStreamDestroy(stream);
 	stream = nullptr;
 #endif
@@ -248,6 +260,30 @@ inline void Ctx::d2h_async(void *h, const void *d, size_t bytes) {
 #else
 	memcpy(h, d, bytes);
 #endif
+}
+inline void Ctx::up_begin() {
+#ifndef PV_EMU
+	if (!up_stream) { PV_CUDA_CHECK(cudaStreamCreateWithFlags(&up_stream, cudaStreamNonBlocking)); PV_CUDA_CHECK(cudaEventCreateWithFlags(&up_ev, cudaEventDisableTiming)); }
+	PV_CUDA_CHECK(cudaEventRecord(up_ev, stream));
+	PV_CUDA_CHECK(cudaStreamWaitEvent(up_stream, up_ev, 0));
+#endif
+	up_pending = true;
+}
+inline void Ctx::h2d_up(void *d, const void *h, size_t bytes) {
+	if (!bytes) return;
+#ifndef PV_EMU
+	PV_CUDA_CHECK(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, up_stream));
+#else
+	memcpy(d, h, bytes);
+#endif
+}
+inline void Ctx::up_join() {
+	if (!up_pending) return;
+#ifndef PV_EMU
+	PV_CUDA_CHECK(cudaEventRecord(up_ev, up_stream));
+	PV_CUDA_CHECK(cudaStreamWaitEvent(stream, up_ev, 0));
+#endif
+	up_pending = false;
 }
 inline void Ctx::bg_begin() {
 #ifndef PV_EMU
@@ -359,6 +395,23 @@ struct Trace {
 	Trace(Ctx &ctx, const char *s) : c(ctx), scope(s) { static const bool en = getenv("PV_TRACE") != nullptr; on = en; if (on) { c.sync(); t0 = now(); } }
 	void mark(const char *what) { if (!on) return; c.sync(); double t = now(); fprintf(stderr, "[trace] %s: %-28s %8.3f ms\n", scope, what, t - t0); t0 = t; }
 };
+
+#ifndef PV_EMU
+// per-process pool of 1 MiB page-locked staging blocks (GFA text on its way in, VCF text on its way out): page-locking is
+// slow (~0.3 ms per MiB), so blocks are allocated once and recycled
+struct PinnedPool {
+	static const size_t BLK = 1u << 20;
+	std::mutex m; std::vector<char *> free_;
+	char *get() {
+		{ std::lock_guard<std::mutex> l(m); if (!free_.empty()) { char *p = free_.back(); free_.pop_back(); return p; } }
+		char *p = nullptr;
+		if (cudaHostAlloc((void **)&p, BLK, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+		return p;
+	}
+	void put(char *p) { if (!p) return; std::lock_guard<std::mutex> l(m); free_.push_back(p); }
+	static PinnedPool &inst() { static PinnedPool *g = new PinnedPool(); return *g; }   // never destroyed: outlives the CUDA context teardown order
+};
+#endif
 
 // RAII device buffer (stream-ordered)
 template <class T> struct Buf {

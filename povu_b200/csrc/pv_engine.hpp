@@ -27,7 +27,7 @@ struct Session {
 	pv::DevGraph dg; bool edges_up = false, paths_up = false;
 	pvh::Forest forest; bool forest_ready = false;
 	pv::DecompOut dec;
-	pvh::Records rec;    // binary records + counters of the last call
+	mutable pvh::Records rec;    // binary records + counters of the last call: born in HBM, copied to the host on demand (rec.to_host)
 	std::vector<std::string> prefixes;
 	std::set<u32> ref_ids;
 
@@ -59,7 +59,7 @@ struct Session {
 		unpin(); c->bg_sync();
 		d_ep1.release(); d_ep2.release(); d_steps.release(); d_segLen.release(); dg = pv::DevGraph();
 		edges_up = raw_paths_up = paths_up = false; forest_ready = false; gm_ready = false; sharded = false;
-		tt = pv::TextTables(); tt_graph_dev = false;
+		tt = pv::TextTables(); tt_graph_dev = false; pvst_cache_ok = false;
 		static const bool env_host_parser = getenv("POVU_B200_HOST_GFA") != nullptr;
 		if (env_host_parser || force_host_parser) { double t0 = now_ms(); g = pvh::load_gfa(fp, labels, refs); t_gfa_read_ms = 0; t_gfa_parse_ms = now_ms() - t0; host_edges = host_steps = host_lbl = true; pin(); return; }
 		load_gfa_device(fp, labels, refs);
@@ -143,10 +143,22 @@ struct Session {
 		c->sync();
 		raw_paths_up = true;
 	}
+	// same, but the copies run on the upload stream while the main stream goes on (the walks are first needed by the index
+	// build, after decompose); whoever reads d_steps / d_segLen next calls c->up_join() first
+	void upload_raw_paths_async() {
+		if (raw_paths_up) return;
+		if (g.stepOff.empty()) g.stepOff.assign(1, 0);
+		const u32 S = g.stepOff.back();
+		d_steps = pv::Buf<u32>(*c, S ? S : 1); d_segLen = pv::Buf<u32>(*c, g.V() ? g.V() : 1);
+		c->up_begin();
+		c->h2d_up(d_steps.p, g.steps.data(), (size_t)S * 4); c->h2d_up(d_segLen.p, g.segLen.data(), (size_t)g.V() * 4);
+		raw_paths_up = true;
+	}
 	// derived device index (adjacency in L-line order, loci, vertex -> steps lists, path components)
 	void upload_paths() {
 		if (paths_up) return;
 		upload_edges(); upload_raw_paths();
+		c->up_join();
 		pv::graph_build(*c, g.V(), g.E(), d_ep1.p, d_ep2.p, g.H(), g.stepOff.data(), d_steps.p, d_segLen.p, dg, labels_ready ? &d_labels : nullptr);
 		labels_ready = false; d_labels.release();
 		paths_up = true;
@@ -154,6 +166,7 @@ struct Session {
 	// forget everything on the device (the next decompose / call re-uploads from the host arrays)
 	void drop_device() {
 		ensure_host(true, true, false);
+		c->up_join();
 		d_ep1.release(); d_ep2.release(); d_steps.release(); d_segLen.release(); dg = pv::DevGraph();
 		edges_up = raw_paths_up = paths_up = false;
 	}
@@ -162,7 +175,7 @@ struct Session {
 	void hot_path(bool keep_raw) {
 		double t0 = now_ms();
 		if (!keep_raw) drop_device();
-		upload_edges(); upload_raw_paths();
+		upload_edges(); upload_raw_paths_async();
 		double t1 = now_ms();
 		want_labels = true;
 		decompose();
@@ -172,6 +185,7 @@ struct Session {
 		upload_paths();
 		double t3 = now_ms();
 		call();
+		if (!keep_raw) rec.to_host(*c);   // e2e: the binary records come to the host; otherwise they stay in HBM for the device text writer
 		c->bg_sync();              // the flubble table has reached the host (copied behind the index build and the call)
 		dforest = pv::DevForest();
 		double t4 = now_ms();
@@ -229,7 +243,7 @@ struct Session {
 		g = std::move(n);
 		host_edges = host_steps = host_lbl = true;
 		pin();
-		forest_ready = false; sharded = true; tt = pv::TextTables(); tt_graph_dev = false; gm_ready = false;
+		forest_ready = false; sharded = true; tt = pv::TextTables(); tt_graph_dev = false; gm_ready = false; pvst_cache_ok = false;
 	}
 
 	// decompose: flubbles + PVST of every component with >= 3 vertices (decompose.cpp:129-142)
@@ -256,21 +270,33 @@ struct Session {
 			if (dec.comp_nv[k] >= 3) { forest.comp_id.push_back(sharded ? comp_global.at(k) : k + 1); forest.treeOff.push_back(base); }
 			else if (dec.comp_nfl[k]) throw std::runtime_error("decompose: flubbles in a component with fewer than 3 vertices");
 		}
-		forest_ready = true;
+		forest_ready = true; pvst_cache_ok = false;
 		tr.mark("forest conversion");
 	}
 
+	// .pvst text of every tree, written on the device (pv_text.cuh: pvst_text_device) once per forest
+	mutable pv::PvstTextOut pvst_cache; mutable bool pvst_cache_ok = false;
+	void build_pvst_text() const {
+		if (pvst_cache_ok) return;
+		c->bg_sync();
+		if (!tt.ids.p) { tt.ids = pv::Buf<u32>(*c, g.ids.size() ? g.ids.size() : 1); c->h2d(tt.ids.p, g.ids.data(), g.ids.size() * 4); }
+		pv::pvst_text_device(*c, tt.ids.p, forest.n(), (u32)forest.comp_id.size(), forest.treeOff.data(), forest.a_v.data(), forest.a_fwd.data(),
+				     forest.z_v.data(), forest.z_fwd.data(), forest.parent.data(), forest.family.data(), pvst_cache);
+		pvst_cache_ok = true;
+	}
 	std::string pvst_text(u32 tree) const {
-		const u32 b = forest.treeOff[tree], n = forest.treeOff[tree + 1] - b;
-		return pvh::pvst_text(g, forest.a_v.data() + b, forest.a_fwd.data() + b, forest.z_v.data() + b, forest.z_fwd.data() + b, forest.parent.data() + b, n);
+		build_pvst_text();
+		return std::string(pvst_cache.text.data() + pvst_cache.treeOff[tree], (size_t)(pvst_cache.treeOff[tree + 1] - pvst_cache.treeOff[tree]));
 	}
 	void write_pvsts(const std::string &dir) const {
+		build_pvst_text();
 		for (u32 t = 0; t < forest.comp_id.size(); t++) {
 			std::string fp = dir + "/" + std::to_string(forest.comp_id[t]) + ".pvst";
-			std::ofstream f(fp, std::ios::binary);
-			if (!f) throw std::runtime_error("could not open " + fp + " for writing");
-			std::string s = pvst_text(t);
-			f.write(s.data(), (std::streamsize)s.size());
+			int fd = open(fp.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0666);
+			if (fd < 0) throw std::runtime_error("could not open " + fp + " for writing");
+			const char *p = pvst_cache.text.data() + pvst_cache.treeOff[t]; size_t left = (size_t)(pvst_cache.treeOff[t + 1] - pvst_cache.treeOff[t]);
+			while (left) { ssize_t w = write(fd, p, left); if (w <= 0) { close(fd); throw std::runtime_error("could not write " + fp); } p += w; left -= (size_t)w; }
+			close(fd);
 		}
 	}
 	// every *.pvst of a directory (call.cpp:36-57).  The reference visits them in directory order
@@ -288,7 +314,7 @@ struct Session {
 		std::sort(files.begin(), files.end());
 		forest = pvh::Forest();
 		for (auto &f : files) pvh::read_pvst(dir + "/" + f.second, g, (u32)f.first, forest);
-		forest_ready = true;
+		forest_ready = true; pvst_cache_ok = false;
 	}
 
 	void set_prefixes(const std::vector<std::string> &p) {
@@ -411,8 +437,9 @@ struct Session {
 		tt.ready = true;
 	}
 	// records of the last call as text, in the reference's order; only_refs = nullptr: every record
-	void vcf_records_device(size_t chunk_size, const std::set<u32> *only_refs, pv::TextOut &out) const {
+	void vcf_records_device(size_t chunk_size, const std::set<u32> *only_refs, pv::TextOut &out, int fd = -1, u64 *streamed = nullptr) const {
 		out.n = rec.n(); out.text.clear(); out.lineOff.assign(1, 0);
+		if (streamed) *streamed = 0;
 		if (!rec.n()) return;
 		if (!gm_ready) throw std::runtime_error("VCF text: no reference prefixes set");
 		build_text_tables();
@@ -420,22 +447,19 @@ struct Session {
 		pv::Trace tr(cx, "text");
 		const size_t n = rec.n(), nFl = forest.n();
 		auto upv = [&](auto &buf, const auto &h, size_t cnt) { typedef typename std::remove_reference<decltype(*buf.p)>::type T; buf = pv::Buf<T>(cx, cnt ? cnt : 1); cx.h2d(buf.p, h.data(), cnt * sizeof(T)); };
-		pv::Buf<u32> fa, fz, fh, rovFl, rovComp, rovTang, cpOff, rRov, rRef, rL, rR, rVt, rPos, rRS, rRL, rGrp, gHap, gStart, gLen, gCnt;
-		pv::Buf<u8> faf, fzf; pv::Buf<u64> rGt; pv::Buf<pv::u16> gt;
+		pv::Buf<u32> fa, fz, fh, rovFl, rovComp, rovTang, cpOff;
+		pv::Buf<u8> faf, fzf;
 		upv(fa, forest.a_v, nFl); upv(fz, forest.z_v, nFl); upv(fh, forest.height, nFl); upv(faf, forest.a_fwd, nFl); upv(fzf, forest.z_fwd, nFl);
 		upv(rovFl, rec.rov_fl, rec.rov_fl.size()); upv(rovComp, rec.rov_comp, rec.rov_comp.size()); upv(rovTang, rec.rov_tangled, rec.rov_tangled.size());
 		upv(cpOff, rec.cpOff, rec.cpOff.size());
-		upv(rRov, rec.rec_rov, n); upv(rRef, rec.rec_ref, n); upv(rL, rec.rec_cxtL, n); upv(rR, rec.rec_cxtR, n); upv(rVt, rec.rec_vt, n); upv(rPos, rec.rec_pos, n);
-		upv(rRS, rec.rec_refStart, n); upv(rRL, rec.rec_refLen, n); upv(rGrp, rec.rec_grpOff, n + 1); upv(rGt, rec.rec_gtOff, n + 1);
-		upv(gHap, rec.grp_hap, rec.grp_hap.size()); upv(gStart, rec.grp_start, rec.grp_start.size()); upv(gLen, rec.grp_len, rec.grp_len.size()); upv(gCnt, rec.grp_count, rec.grp_count.size());
-		upv(gt, rec.gt, rec.gt.size());
+		const pv::RecPiece &R = rec.flat(cx);   // the records never left HBM
 		pv::TextView t{tt.ids.p, dg.segLen.p, dg.steps.p, dg.stepOff.p, tt.lblOff.p, tt.lbl.p, tt.tagOff.p, tt.tags.p, tt.ploidy.p, tt.nCols,
 			       tt.ceOff.p, tt.ceCol.p, tt.cePhase.p, tt.ceLocal.p, fa.p, fz.p, fh.p, faf.p, fzf.p, rovFl.p, rovComp.p, rovTang.p, cpOff.p,
-			       rRov.p, rRef.p, rL.p, rR.p, rVt.p, rPos.p, rRS.p, rRL.p, rGrp.p, rGt.p, gHap.p, gStart.p, gLen.p, gCnt.p, gt.p};
+			       R.rov.p, R.ref.p, R.cxtL.p, R.cxtR.p, R.vt.p, R.pos.p, R.refStart.p, R.refLen.p, R.grpOff.p, R.gtOff.p, R.gHap.p, R.gStart.p, R.gLen.p, R.gCnt.p, R.gt.p};
 		std::vector<u8> keep;
 		if (only_refs) { keep.assign(g.H(), 0); for (u32 r : *only_refs) if (r < g.H()) keep[r] = 1; }
 		tr.mark("upload records");
-		pv::records_text_device(cx, t, n, rec.n_regions, chunk_size, g.H(), only_refs ? keep.data() : nullptr, out);
+		pv::records_text_device(cx, t, n, rec.n_regions, chunk_size, g.H(), only_refs ? keep.data() : nullptr, out, fd, streamed);
 		tr.mark("text kernels + d2h");
 	}
 	// for the multi-GPU merge: every record as a text line plus (component id, ordinal of its region inside that
@@ -444,6 +468,7 @@ struct Session {
 		std::vector<u64> per = regions_per_tree(), first(per.size() + 1, 0);
 		for (size_t t = 0; t < per.size(); t++) first[t + 1] = first[t] + per[t];
 		vcf_records_device(~(size_t)0, nullptr, out);
+		rec.to_host(*c);
 		keys.clear();
 		for (size_t i : pvh::record_order(rec, ~(size_t)0)) {   // same keys, same stable order as the device permutation
 			u32 r = rec.rec_rov[i];

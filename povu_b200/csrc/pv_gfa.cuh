@@ -154,27 +154,13 @@ struct GfaDev {
 // file -> device memory.  A few host threads pread(2) interleaved 1 MiB blocks of the file into page-locked staging buffers
 // (two per thread: the read of one block overlaps the H2D of the previous one) and enqueue the copies on the context's
 // stream, so the page-cache -> staging memcpy (the slow leg, ~3 GB/s per core) runs on several cores while PCIe streams.
-// The staging buffers are pooled per process.  T gets n + 32 bytes, the tail zeroed, so that 16-byte chunk loads never
+// The staging buffers come from the per-process pool of pv_common.cuh.  T gets n + 32 bytes, the tail zeroed, so that 16-byte chunk loads never
 // run off the allocation.
-#ifndef PV_EMU
-struct GfaStagePool {
-	static const size_t BLK = 1u << 20;
-	std::mutex m; std::vector<char *> free_;
-	char *get() {
-		{ std::lock_guard<std::mutex> l(m); if (!free_.empty()) { char *p = free_.back(); free_.pop_back(); return p; } }
-		char *p = nullptr;
-		if (cudaHostAlloc((void **)&p, BLK, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
-		return p;
-	}
-	void put(char *p) { if (!p) return; std::lock_guard<std::mutex> l(m); free_.push_back(p); }
-	static GfaStagePool &inst() { static GfaStagePool *g = new GfaStagePool(); return *g; }   // never destroyed: outlives the CUDA context teardown order
-};
-#endif
 inline void gfa_text_to_device(Ctx &c, int fd, u64 n, Buf<u8> &T) {
 	T = Buf<u8>(c, n + 32);
 	c.memset0(T.p + n, 32);
 #ifndef PV_EMU
-	const size_t BLK = GfaStagePool::BLK;
+	const size_t BLK = PinnedPool::BLK;
 	const u64 nBlk = (n + BLK - 1) / BLK;
 	if (nBlk == 0) return;
 	unsigned hw = std::thread::hardware_concurrency();
@@ -185,7 +171,7 @@ inline void gfa_text_to_device(Ctx &c, int fd, u64 n, Buf<u8> &T) {
 	u8 *dst = T.p; cudaStream_t stream = c.stream; const int dev = c.device;
 	auto worker = [&](int tid) {
 		if (cudaSetDevice(dev) != cudaSuccess) { fail = 2; return; }
-		GfaStagePool &pool = GfaStagePool::inst();
+		PinnedPool &pool = PinnedPool::inst();
 		char *st[2] = {pool.get(), pool.get()}; cudaEvent_t ev[2] = {nullptr, nullptr}; bool used[2] = {false, false};
 		if (!st[0] || !st[1] || cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming) != cudaSuccess) fail = 2;
 		for (u64 b = (u64)tid, k = 0; b < nBlk && !fail; b += (u64)NT, k++) {

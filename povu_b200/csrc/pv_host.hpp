@@ -3,7 +3,6 @@
 // Mirrors (same behaviour, own design):
 //   mto::from_gfa::to_bd          /root/reference/src/mto/from_gfa.cpp:28-113,141-280   (liteseq rules: SURVEY.md Appendix A)
 //   pr::Refs                      /root/reference/include/povu/refs/refs.hpp:278-301,359-412
-//   mto::to_pvst::write_pvst      /root/reference/src/mto/to_pvst.cpp:23-109
 //   mto::from_pvst::read_pvst     /root/reference/src/mto/from_pvst.cpp:82-302, comp_heights pvst.hpp:807-836
 //   mto::to_vcf                   /root/reference/src/mto/to_vcf.cpp:19-139, VcfRec text vcf.hpp:295-383
 //   hap_slice::{as_str,as_dna_str} /root/reference/include/ita/genomics/allele.hpp:134-209
@@ -272,26 +271,6 @@ struct Forest {
 
 inline std::string flubble_label(const HostGraph &g, u32 a_v, bool a_fwd, u32 z_v, bool z_fwd) {
 	return std::string(a_fwd ? ">" : "<") + std::to_string(g.ids[a_v]) + (z_fwd ? ">" : "<") + std::to_string(g.ids[z_v]);
-}
-
-// one .pvst text (to_pvst.cpp:23-109) for flubbles [b, e) of a forest-like table
-inline std::string pvst_text(const HostGraph &g, const u32 *a_v, const u8 *a_fwd, const u32 *z_v, const u8 *z_fwd, const u32 *parent, u32 n) {
-	std::vector<u32> cnt(n + 2, 0), off(n + 2, 0), kids(n);
-	for (u32 j = 0; j < n; j++) cnt[parent[j]]++;
-	for (u32 i = 0; i <= n; i++) off[i + 1] = off[i] + cnt[i];
-	std::vector<u32> fill(off.begin(), off.end() - 1);
-	for (u32 j = 0; j < n; j++) kids[fill[parent[j]]++] = j + 1;
-	std::string o = "H\t0.0.3\t.\t.\t.\n";
-	o.reserve(32 + (size_t)n * 40);
-	char buf[32];
-	for (u32 i = 0; i <= n; i++) {
-		if (i == 0) o += "D\t0\t.\t";
-		else { o += "F\t"; snprintf(buf, sizeof buf, "%u", i); o += buf; o += '\t'; o += flubble_label(g, a_v[i - 1], a_fwd[i - 1], z_v[i - 1], z_fwd[i - 1]); o += '\t'; }
-		if (off[i] == off[i + 1]) o += '.';
-		else for (u32 k = off[i]; k < off[i + 1]; k++) { if (k > off[i]) o += ", "; snprintf(buf, sizeof buf, "%u", kids[k]); o += buf; }
-		o += i == 0 ? "\t.\n" : "\tL\n";
-	}
-	return o;
 }
 
 // read one .pvst (from_pvst.cpp:162-302) and append it to the forest.  Throws where the reference exits.

@@ -618,4 +618,50 @@ inline u32 compact_flags(Ctx &c, const u32 *flags, size_t n, Buf<u32> &out) {
 	return pos.read(n);
 }
 
+// ---------------------------------------------------------------------------------------------
+// indices i in [0, n) grouped by key(i) in [0, B), ascending inside a group: off[B + 1] + list[n] (a CSR).
+// Almost every group is small in the graphs this serves (steps per vertex, children per PVST vertex), so instead of a
+// stable sort of all n pairs: count, scan, drop every index into a free slot of its group (atomic cursor, arbitrary order),
+// one thread per group insertion-sorts its short list.  Members of the few large groups (more than `small` entries: hub
+// vertices, a PVST root with a million children) take the stable radix sort, restricted to them.
+// ---------------------------------------------------------------------------------------------
+PV_KERNEL(K_grp_count, 8);
+PV_KERNEL(K_grp_slot, 16);
+PV_KERNEL(K_grp_sort, 16);
+PV_KERNEL(K_grp_big, 12);
+template <class KeyFn> inline void group_indices(Ctx &c, KeyFn key, size_t n, u32 B, u32 *off, u32 *list, u32 small = 48) {
+	if (n >= 0xFFFFFFF0ull) throw std::runtime_error("group_indices: input too large");
+	Buf<u32> cnt(c, (size_t)B + 1), cur(c, B ? B : 1), nBigBuf(c, 1);
+	cnt.zero(); cur.zero(); nBigBuf.zero();
+	u32 *cnt_ = cnt.p, *cur_ = cur.p, *nBig_ = nBigBuf.p;
+	parallel_for<K_grp_count>(c, n, PV_LAMBDA(size_t i) { atomic_add(cnt_ + key(i), 1u); });
+	exclusive_scan(c, cnt.p, off, (size_t)B + 1, OpAddU32(), 0u);
+	parallel_for<K_grp_slot>(c, n, PV_LAMBDA(size_t i) {
+		u32 k = key(i);
+		if (cnt_[k] > small) return;
+		list[off[k] + atomic_add(cur_ + k, 1u)] = (u32)i;
+	});
+	parallel_for<K_grp_sort>(c, B, PV_LAMBDA(size_t k) {
+		u32 m = cnt_[k];
+		if (m > small) { atomic_add(nBig_, m); return; }
+		u32 *a = list + off[k];
+		for (u32 i = 1; i < m; i++) { u32 x = a[i]; u32 j = i; while (j > 0 && a[j - 1] > x) { a[j] = a[j - 1]; j--; } a[j] = x; }
+	});
+	const u32 nBig = nBigBuf.read(0);
+	if (!nBig) return;
+	Buf<u32> flag(c, n), idx;
+	u32 *flag_ = flag.p;
+	parallel_for<K_grp_big>(c, n, PV_LAMBDA(size_t i) { flag_[i] = cnt_[key(i)] > small ? 1u : 0u; });
+	const u32 nb = compact_flags(c, flag.p, n, idx);   // ascending index
+	flag.release();
+	Buf<u32> kk(c, nb), vv(c, nb);
+	u32 *kk_ = kk.p, *vv_ = vv.p; const u32 *idx_ = idx.p;
+	parallel_for<K_grp_big>(c, nb, PV_LAMBDA(size_t j) { u32 i = idx_[j]; kk_[j] = key(i); vv_[j] = i; });
+	radix_sort_pairs(c, kk, vv, nb, bits_for(B));
+	kk_ = kk.p; vv_ = vv.p;
+	// first sorted position of every large group (cur is free again: large groups never touched it)
+	parallel_for<K_grp_big>(c, nb, PV_LAMBDA(size_t j) { if (j == 0 || kk_[j - 1] != kk_[j]) cur_[kk_[j]] = (u32)j; });
+	parallel_for<K_grp_big>(c, nb, PV_LAMBDA(size_t j) { u32 k = kk_[j]; list[off[k] + ((u32)j - cur_[k])] = vv_[j]; });
+}
+
 } // namespace pv

@@ -13,6 +13,8 @@
 // (464 paths) of text; stores leave a thread as aligned 8-byte words.
 #pragma once
 #include <cmath>
+#include <cerrno>
+#include <unistd.h>
 #include "pv_call.cuh"
 
 namespace pv {
@@ -225,10 +227,47 @@ inline void record_order_device(Ctx &c, const u32 *rec_rov, const u32 *rec_ref, 
 	}
 }
 
-// text of the records selected by keepRef (per ref path id: 1 = print; nullptr = all), in the reference's order
-inline void records_text_device(Ctx &c, const TextView &t, size_t n, u64 n_regions, size_t chunk_size, u32 H, const u8 *keepRef /*host, H entries*/, TextOut &out) {
-	out.n = n; out.text.clear(); out.lineOff.clear(); out.lineOff.resize(n + 1);
-	if (!n) { out.lineOff[0] = 0; return; }
+// device text -> file descriptor through a small ring of page-locked blocks: the D2H of block k+1 runs on the copy stream
+// while block k is written with write(2); no text-sized page-locked buffer is ever allocated
+inline void stream_text_to_fd(Ctx &c, const u8 *d_text, u64 total, int fd) {
+	auto put = [&](const char *p, size_t n) { while (n) { ssize_t w = write(fd, p, n); if (w < 0) { if (errno == EINTR) continue; throw std::runtime_error(std::string("write failed: ") + strerror(errno)); } p += w; n -= (size_t)w; } };
+#ifndef PV_EMU
+	const size_t BLK = PinnedPool::BLK; const int NB = 4;
+	PinnedPool &pool = PinnedPool::inst();
+	char *blk[NB]; cudaEvent_t ev[NB]; size_t len[NB];
+	for (int k = 0; k < NB; k++) { blk[k] = pool.get(); if (!blk[k]) throw std::runtime_error("povu_b200: no page-locked memory for the text stream"); PV_CUDA_CHECK(cudaEventCreateWithFlags(&ev[k], cudaEventDisableTiming)); }
+	c.bg_sync(); c.bg_begin();
+	const u64 nBlk = (total + BLK - 1) / BLK;
+	try {
+		for (u64 b = 0; b < nBlk + NB - 1; b++) {
+			if (b < nBlk) {   // issue block b
+				int k = (int)(b % NB); len[k] = (size_t)((total - b * BLK) < BLK ? (total - b * BLK) : BLK);
+				PV_CUDA_CHECK(cudaMemcpyAsync(blk[k], d_text + b * BLK, len[k], cudaMemcpyDeviceToHost, c.copy_stream));
+				PV_CUDA_CHECK(cudaEventRecord(ev[k], c.copy_stream));
+			}
+			if (b >= (u64)NB - 1) {   // drain block b - (NB - 1)
+				int k = (int)((b - (NB - 1)) % NB);
+				PV_CUDA_CHECK(cudaEventSynchronize(ev[k]));
+				put(blk[k], len[k]);
+			}
+		}
+	} catch (...) { cudaStreamSynchronize(c.copy_stream); for (int k = 0; k < NB; k++) { pool.put(blk[k]); cudaEventDestroy(ev[k]); } c.bg_pending = false; throw; }
+	for (int k = 0; k < NB; k++) { pool.put(blk[k]); cudaEventDestroy(ev[k]); }
+	c.bg_sync();
+#else
+	put((const char *)d_text, (size_t)total);
+#endif
+}
+
+// text of the records selected by keepRef (per ref path id: 1 = print; nullptr = all), in the reference's order.
+// fd < 0: the text and its line offsets land in `out`; fd >= 0: the text is streamed to that descriptor instead (out.text stays
+// empty, *streamed = bytes written)
+inline void records_text_device(Ctx &c, const TextView &t, size_t n, u64 n_regions, size_t chunk_size, u32 H, const u8 *keepRef /*host, H entries*/, TextOut &out,
+				int fd = -1, u64 *streamed = nullptr) {
+	out.n = n; out.text.clear(); out.lineOff.clear();
+	if (streamed) *streamed = 0;
+	if (fd < 0) out.lineOff.resize(n + 1);
+	if (!n) { if (fd < 0) out.lineOff[0] = 0; return; }
 	Buf<u32> perm;
 	record_order_device(c, t.rec_rov, t.rec_ref, n, n_regions, chunk_size, H, perm);
 	Buf<u8> keep(c, H ? H : 1);
@@ -250,9 +289,114 @@ inline void records_text_device(Ctx &c, const TextView &t, size_t n, u64 n_regio
 		if (off_[k + 1] == off_[k]) return;
 		WriteSink s(text_ + off_[k]); emit_record(t, perm_[k], s);
 	});
+	if (fd >= 0) {
+		stream_text_to_fd(c, text.p, total, fd);
+		if (streamed) *streamed = total;
+		return;
+	}
 	out.text.resize(total);
 	c.d2h_async(out.text.data(), text.p, total);
 	c.d2h_async(out.lineOff.data(), off.p, (n + 1) * 8);
+	c.sync();
+}
+
+// ---------------------------------------------------------------------------------------------
+// .pvst v0.0.3 text written on the device (second half of SURVEY.md 8 f2; replaces mto::to_pvst::write_pvst,
+// /root/reference/src/mto/to_pvst.cpp:23-109): per component file
+//     H\t0.0.3\t.\t.\t.\n
+//     D\t0\t.\t<children>\t.\n
+//     <family>\t<idx>\t<label>\t<children>\tL\n        children = "." or "c1, c2, ..." in creation order
+// A top-level chain gives the dummy root a million children, so the unit of work is not a line but an ITEM: per PVST
+// vertex a prefix item (everything up to the children column) and a suffix item, plus one item per child entry.  Items
+// are laid out in file order (vertex v owns items 2v + childOff[v] .. 2v + childOff[v+1] + 1), every item computes its
+// length, one u64 scan places them, every item writes its few bytes.
+// ---------------------------------------------------------------------------------------------
+PV_KERNEL(P_node, 12);
+PV_KERNEL(P_len, 40);
+PV_KERNEL(P_write, 64);
+struct PvstView {
+	const u32 *ids, *a_v, *z_v, *parent, *nodeTree, *treeNode0; const u8 *a_fwd, *z_fwd, *family;   // flubble arrays by global flubble index
+	const u32 *childOff, *childList;   // per node (global): its child flubbles (global flubble indices), ascending
+	u32 nNodes, nTrees;
+	// node x of tree t: x == treeNode0[t] is the dummy root, otherwise flubble x - t - 1 (global), local PVST index x - treeNode0[t]
+	template <class Sink> PV_DEV void prefix(u32 x, Sink &o) const {
+		u32 t = nodeTree[x], loc = x - treeNode0[t];
+		if (loc == 0) { put_lit(o, "H\t0.0.3\t.\t.\t.\nD\t0\t.\t"); }
+		else {
+			u32 f = x - t - 1;
+			o.ch((char)family[f]); o.ch('\t'); put_u32(o, loc); o.ch('\t');
+			o.ch(a_fwd[f] ? '>' : '<'); put_u32(o, ids[a_v[f]]); o.ch(z_fwd[f] ? '>' : '<'); put_u32(o, ids[z_v[f]]); o.ch('\t');
+		}
+		if (childOff[x] == childOff[x + 1]) o.ch('.');
+	}
+	template <class Sink> PV_DEV void suffix(u32 x, Sink &o) const { put_lit(o, x == treeNode0[nodeTree[x]] ? "\t.\n" : "\tL\n"); }
+	template <class Sink> PV_DEV void child(u32 x, u32 k, Sink &o) const {   // k-th entry of the global child list, a child of node x
+		if (k > childOff[x]) { o.ch(','); o.ch(' '); }
+		u32 f = childList[k]; u32 t = nodeTree[x];
+		put_u32(o, f + t + 1 - treeNode0[t]);
+	}
+};
+struct PvstParentNode {   // key of flubble f for the children grouping: the global node index of its parent
+	const u32 *parent, *flTree, *treeNode0;
+	PV_DEV u32 operator()(size_t f) const { return treeNode0[flTree[f]] + parent[f]; }
+};
+struct PvstTextOut { hvec<char> text; std::vector<u64> treeOff; };   // treeOff[t] .. treeOff[t+1]: the file of tree t
+
+// forest arrays are HOST arrays (flubbles of all trees concatenated; h_treeOff[T+1] = first flubble of every tree; parent = local
+// PVST index, 0 = root); ids is the device segment-id table
+inline void pvst_text_device(Ctx &c, const u32 *d_ids, u32 nFl, u32 T, const u32 *h_treeOff, const u32 *h_a_v, const u8 *h_a_fwd, const u32 *h_z_v,
+			     const u8 *h_z_fwd, const u32 *h_parent, const char *h_family, PvstTextOut &out) {
+	out.text.clear(); out.treeOff.assign((size_t)T + 1, 0);
+	if (T == 0) return;
+	const u32 N = nFl + T;
+	std::vector<u32> node0((size_t)T + 1);
+	for (u32 t = 0; t <= T; t++) node0[t] = h_treeOff[t] + t;
+	Buf<u32> a_v(c, nFl ? nFl : 1), z_v(c, nFl ? nFl : 1), parent(c, nFl ? nFl : 1), treeOff(c, (size_t)T + 1), treeNode0(c, (size_t)T + 1), nodeTree(c, N), flTree(c, nFl ? nFl : 1);
+	Buf<u8> a_fwd(c, nFl ? nFl : 1), z_fwd(c, nFl ? nFl : 1), family(c, nFl ? nFl : 1);
+	c.h2d(a_v.p, h_a_v, (size_t)nFl * 4); c.h2d(z_v.p, h_z_v, (size_t)nFl * 4); c.h2d(parent.p, h_parent, (size_t)nFl * 4);
+	c.h2d(a_fwd.p, h_a_fwd, nFl); c.h2d(z_fwd.p, h_z_fwd, nFl); c.h2d(family.p, h_family, nFl);
+	c.h2d(treeOff.p, h_treeOff, ((size_t)T + 1) * 4); c.h2d(treeNode0.p, node0.data(), ((size_t)T + 1) * 4);
+	{
+		u32 *nodeTree_ = nodeTree.p, *flTree_ = flTree.p; const u32 *n0 = treeNode0.p;
+		parallel_for<P_node>(c, N, PV_LAMBDA(size_t x) {
+			u32 t = ub_u32(n0, 0, T + 1, (u32)x) - 1;
+			nodeTree_[x] = t;
+			if (x != n0[t]) flTree_[x - t - 1] = t;
+		});
+	}
+	Buf<u32> childOff(c, (size_t)N + 1), childList(c, nFl ? nFl : 1);
+	group_indices(c, PvstParentNode{parent.p, flTree.p, treeNode0.p}, nFl, N, childOff.p, childList.p);
+	PvstView pw{d_ids, a_v.p, z_v.p, parent.p, nodeTree.p, treeNode0.p, a_fwd.p, z_fwd.p, (const u8 *)family.p, childOff.p, childList.p, N, T};
+	const size_t nItems = 2 * (size_t)N + nFl;
+	Buf<u64> len(c, nItems + 1), off(c, nItems + 1);
+	u64 *len_ = len.p; const u32 *childOff_ = childOff.p, *childList_ = childList.p, *parent_ = parent.p, *flTree_ = flTree.p, *n0 = treeNode0.p;
+	parallel_for<P_len>(c, (size_t)N + 1, PV_LAMBDA(size_t x) {
+		if (x == N) { len_[nItems] = 0; return; }
+		CountSink a; pw.prefix((u32)x, a); len_[2 * x + childOff_[x]] = a.n;
+		CountSink b; pw.suffix((u32)x, b); len_[2 * x + childOff_[x + 1] + 1] = b.n;
+	});
+	parallel_for<P_len>(c, nFl, PV_LAMBDA(size_t k) {
+		u32 f = childList_[k]; u32 x = n0[flTree_[f]] + parent_[f];
+		CountSink s; pw.child(x, (u32)k, s); len_[2 * (size_t)x + 1 + k] = s.n;
+	});
+	exclusive_scan(c, len.p, off.p, nItems + 1, OpAddU64(), (u64)0);
+	u64 total; c.d2h(&total, off.p + nItems, 8);
+	Buf<u8> text(c, total + 8);
+	u8 *text_ = text.p; const u64 *off_ = off.p;
+	parallel_for<P_write>(c, N, PV_LAMBDA(size_t x) {
+		WriteSink a(text_ + off_[2 * x + childOff_[x]]); pw.prefix((u32)x, a); a.finish();
+		WriteSink b(text_ + off_[2 * x + childOff_[x + 1] + 1]); pw.suffix((u32)x, b); b.finish();
+	});
+	parallel_for<P_write>(c, nFl, PV_LAMBDA(size_t k) {
+		u32 f = childList_[k]; u32 x = n0[flTree_[f]] + parent_[f];
+		WriteSink s(text_ + off_[2 * (size_t)x + 1 + k]); pw.child(x, (u32)k, s); s.finish();
+	});
+	// file boundaries: the prefix item of every tree's root
+	Buf<u64> tOff(c, (size_t)T + 1);
+	{ u64 *tOff_ = tOff.p; parallel_for<P_node>(c, (size_t)T + 1, PV_LAMBDA(size_t t) { tOff_[t] = t < T ? off_[2 * (size_t)n0[t] + childOff_[n0[t]]] : total; }); }
+	out.text.resize(total);
+	c.d2h_async(out.text.data(), text.p, total);
+	c.d2h_async(out.treeOff.data(), tOff.p, ((size_t)T + 1) * 8);
 	c.sync();
 }
 

@@ -38,4 +38,22 @@ if "--no-ref" not in sys.argv and os.path.exists(REF):
     out["identical_to_reference"] = a == b
     out["records"] = sum(1 for l in a if l and not l.startswith(b"#"))
     out["speedup_wall"] = out["reference"]["wall_s"] / out["povu_b200"]["wall_s"]
+# `povu decompose`: .pvst forest on disk (device decompose + device .pvst text)
+import shutil
+import tempfile
+d_ours, d_ref = tempfile.mkdtemp(), tempfile.mkdtemp()
+runs = []
+for i in range(3):
+    t0 = time.perf_counter()
+    r = subprocess.run([CLI, "decompose", "-i", fp, "-o", d_ours], capture_output=True)
+    runs.append(time.perf_counter() - t0)
+    assert r.returncode == 0, r.stderr.decode()
+out["decompose_cli"] = {"povu_b200_wall_s": min(runs), "runs": runs, "pvst_bytes": sum(os.path.getsize(os.path.join(d_ours, f)) for f in os.listdir(d_ours))}
+if "--no-ref" not in sys.argv and os.path.exists(REF):
+    t0 = time.perf_counter()
+    r = subprocess.run([REF, "decompose", "-i", fp, "-o", d_ref, "-t", "1"], capture_output=True)
+    out["decompose_cli"]["reference_wall_s"] = time.perf_counter() - t0
+    same = sorted(os.listdir(d_ours)) == sorted(os.listdir(d_ref)) and all(open(os.path.join(d_ours, f), "rb").read() == open(os.path.join(d_ref, f), "rb").read() for f in os.listdir(d_ref))
+    out["decompose_cli"]["identical_to_reference"] = same
+shutil.rmtree(d_ours); shutil.rmtree(d_ref)
 print(json.dumps(out, indent=1))
