@@ -49,7 +49,7 @@ PV_KERNEL(C_hash, 16);
 PV_KERNEL(C_matfill, 24);       // per (region, column): the vertex's step list in, one cell per visiting path out
 PV_KERNEL(C_lap, 16);
 PV_KERNEL(C_pair_count, 16);    // per (region, path): two matrix rows in, a count out
-PV_KERNEL(C_pair_fill, 64);
+PV_KERNEL(C_pair_fill, 80);    // per candidate slot: two matrix rows + the steps of both slices in, 9 words out (the row search and the step-list searches are not compulsory traffic)
 PV_KERNEL(C_group, 64);
 PV_KERNEL(C_emit, 64);
 PV_KERNEL(C_gt_ref, 16);
@@ -660,9 +660,12 @@ inline void overlay_pass(Ctx &c, const DevGraph &G, const GraphView &g, const Ca
 		Buf<u32> cL(c, nC1), cR(c, nC1), cStart(c, nC1), cLen(c, nC1), cRS(c, nC1), cRL(c, nC1), cHap(c, nC1), cCls(c, nC1), cHead(c, nC1), gCount(c, nC1), hsort(c, nC1);
 		const CandView cd{cL.p, cR.p, cStart.p, cLen.p, cRS.p, cRL.p, cHap.p, cCls.p, cHead.p, gCount.p, hsort.p};
 		// ---- C5b: slices per context, classification
-		if (nCand) parallel_for<C_pair_fill>(c, nRows, PV_LAMBDA(size_t row) {
-			if (candOff_[row + 1] == candOff_[row]) return;
-			scan_pair(cv, refLocal, k, (u32)row, true, cd, candOff_[row]);
+		// one thread per candidate slot; the thread of a row's FIRST slot fills the whole row.  Rows without a context
+		// (most paths carry the ref allele) cost nothing and the working lanes of a warp are consecutive busy rows.
+		if (nCand) parallel_for<C_pair_fill>(c, nCand, PV_LAMBDA(size_t x) {
+			u32 row = ub_u32(candOff_, 0, nRows + 1, (u32)x) - 1;
+			if (candOff_[row] != (u32)x) return;
+			scan_pair(cv, refLocal, k, row, true, cd, (u32)x);
 		});
 		tr.mark("C5 pairs");
 		if (nCand) {   // pin pairs sit in candidate slots of class 4: pack them, in slot order
