@@ -120,7 +120,13 @@ inline GraphView view(const DevGraph &g) {
 inline void component_labels(Ctx &c, u32 V, u64 E, const u32 *ep1, const u32 *ep2, u32 *label) {
 	parallel_for<C_uf>(c, V, PV_LAMBDA(size_t v) { label[v] = (u32)v; });
 	parallel_for<C_uf>(c, E, PV_LAMBDA(size_t e) { uf_union(label, ep1[e] >> 1, ep2[e] >> 1); });
-	parallel_for<C_uf>(c, V, PV_LAMBDA(size_t v) { label[v] = uf_find(label, (u32)v); });
+	// Flattening in place must not compress paths: a halving store of another thread (a stale ancestor) could land after
+	// the owner's final store and leave a non-root label behind.  Read-only walks see either the old parent or the root.
+	parallel_for<C_uf>(c, V, PV_LAMBDA(size_t v) {
+		u32 x = (u32)v, p = ld_volatile(label + x);
+		while (p != x) { x = p; p = ld_volatile(label + x); }
+		label[v] = x;
+	});
 }
 
 // d_ep1/d_ep2: E edge endpoint ports (device).  d_steps: S packed steps (device).  d_segLen: V (device).

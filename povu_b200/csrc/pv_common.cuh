@@ -499,10 +499,11 @@ template <class Tag, class F> inline void parallel_for(Ctx &c, size_t n, F f) {
 	pf_kernel<Tag, F><<<(unsigned)blocks, 256, 0, c.stream>>>(n, f);
 	c.prof_end();
 	c.launches++;
-#ifdef PV_SYNC_EVERY_LAUNCH
-	PV_CUDA_CHECK(cudaStreamSynchronize(c.stream));
-#endif
-	PV_CUDA_CHECK(cudaGetLastError());
+	// POVU_B200_SYNC_LAUNCHES=1 (debug): synchronise after every launch so that a device fault names its kernel
+	static const bool sync_every = getenv("POVU_B200_SYNC_LAUNCHES") != nullptr;
+	cudaError_t err = sync_every ? cudaStreamSynchronize(c.stream) : cudaSuccess;
+	if (err == cudaSuccess) err = cudaGetLastError();
+	if (err != cudaSuccess) throw std::runtime_error(std::string("CUDA error in kernel ") + Tag::name() + " (" + std::to_string(n) + " items): " + cudaGetErrorString(err));
 }
 #else
 template <class Tag, class F> inline void parallel_for(Ctx &c, size_t n, F f) {

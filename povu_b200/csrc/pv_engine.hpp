@@ -206,6 +206,12 @@ struct Session {
 		pv::Buf<u32> lab(*c, V ? V : 1);
 		pv::component_labels(*c, V, E, d_ep1.p, d_ep2.p, lab.p);
 		std::vector<u32> root = lab.to_host(); root.resize(V);
+		{   // every link must lie inside one component, or the filtered graph below would be cut through a component
+			u64 bad = 0, notroot = 0;
+			for (u64 e = 0; e < E; e++) if (root[g.ep1[e] >> 1] != root[g.ep2[e] >> 1]) bad++;
+			for (u32 v = 0; v < V; v++) if (root[root[v]] != root[v]) notroot++;
+			if (bad || notroot) throw std::runtime_error("shard: inconsistent component labels (" + std::to_string(bad) + " links across components, " + std::to_string(notroot) + " labels that are not roots)");
+		}
 		std::vector<u32> comp_of(V), roots;
 		for (u32 v = 0; v < V; v++) if (root[v] == v) roots.push_back(v);          // ascending = discovery order
 		for (u32 v = 0; v < V; v++) comp_of[v] = (u32)(std::lower_bound(roots.begin(), roots.end(), root[v]) - roots.begin());

@@ -20,3 +20,33 @@ def test_nccl_two_ranks_multi_comp(gpu, tmp_path):
     forest = os.path.join(out, "forest")
     files = {int(f[:-5]): open(os.path.join(forest, f)).read() for f in os.listdir(forest)}
     assert files == helpers.expected_pvsts("multi_comp")
+
+
+def test_gpu_shard_large_graph_on_one_device(gpu, tmp_path):
+    """Sharding a 24-component graph three ways on ONE device: every share is cut along component borders (the session
+    verifies its device component labels against the links) and the records of every component equal those of the
+    unsharded session.  Large enough for long union-find chains (a path-compression race once corrupted the labels)."""
+    from povu_b200 import api, synth
+    W = [248956422, 242193529, 198295559, 190214555, 181538259, 170805979, 159345973, 145138636, 138394717, 133797422, 135086622, 133275309,
+         114364328, 107043718, 101991189, 90338345, 83257441, 80373285, 58617616, 64444167, 46709983, 50818468, 156040895, 57227415, 16569]
+    tpl = [synth.template_from(synth.snp_indel_chain(6, n_paths=6, seed=100 + k)) for k in range(18)] + synth.cfg3_templates(seed=7, n_nested=2, tower_depth=0)
+    g = synth.tiled(tpl, 3000, 8, seed=11, n_components=25, comp_weights=W)
+
+    def records(s, prefix):
+        s.call([prefix])
+        return [l for l in s.vcf_text(with_date=False).splitlines() if not l.startswith("#")]
+
+    whole = api.Session.from_graph(gpu, g)
+    whole.decompose()
+    seen = 0
+    for rank in range(3):
+        s = api.Session.from_graph(gpu, g)
+        assert s.shard(rank, 3) == 24
+        ga = s.graph_arrays(labels=False)
+        own = [n for k, n in enumerate(ga["path_names"]) if n.startswith("S001#1#") and ga["step_off"][k + 1] > ga["step_off"][k]]
+        s.hot_path([own[0]], keep_resident=True)
+        for p in own[:4]:
+            assert records(s, p) == records(whole, p), (rank, p)
+        seen += len(own)
+        s.close()
+    assert seen == 24
