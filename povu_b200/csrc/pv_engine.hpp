@@ -25,7 +25,7 @@ struct Session {
 	pvh::GtMeta gm; bool gm_ready = false;
 	pv::Buf<u32> d_ep1, d_ep2;
 	pv::DevGraph dg; bool edges_up = false, paths_up = false;
-	pvh::Forest forest; bool forest_ready = false;
+	pvh::Forest forest; bool forest_ready = false; int forest_subfl = -1;   // forest_subfl: does the forest hold sub-flubble families (-1 = not looked yet)
 	pv::DecompOut dec;
 	mutable pvh::Records rec;    // binary records + counters of the last call: born in HBM, copied to the host on demand (rec.to_host)
 	std::vector<std::string> prefixes;
@@ -187,8 +187,7 @@ struct Session {
 		call();
 		if (!keep_raw) rec.to_host(*c);   // e2e: the binary records come to the host; otherwise they stay in HBM for the device text writer
 		c->bg_sync();              // the flubble table has reached the host (copied behind the index build and the call)
-		dforest = pv::DevForest();
-		double t4 = now_ms();
+		double t4 = now_ms();      // (the device copy of the forest stays for later calls of this session)
 		t_upload_ms = t1 - t0; t_dec_ms = t2 - t1; t_build_ms = t3 - t2; t_call_ms = t4 - t3;
 	}
 
@@ -250,6 +249,7 @@ struct Session {
 		host_edges = host_steps = host_lbl = true;
 		pin();
 		forest_ready = false; sharded = true; tt = pv::TextTables(); tt_graph_dev = false; gm_ready = false; pvst_cache_ok = false;
+		dforest = pv::DevForest(); labels_ready = false; d_labels.release();
 	}
 
 	// decompose: flubbles + PVST of every component with >= 3 vertices (decompose.cpp:129-142)
@@ -258,10 +258,14 @@ struct Session {
 		upload_edges();
 		pv::DecompOpts opt;
 		dforest = pv::DevForest();
-		if (want_labels) { opt.keep_labels = &d_labels; opt.keep_forest = &dforest; opt.async_results = true; }
+		// the flubble table and the component labels stay in HBM for the calls that follow (no re-upload, no second
+		// connectivity pass); on the hot path the host copies of the results additionally travel behind the next phases
+		opt.keep_labels = &d_labels; opt.keep_forest = &dforest;
+		if (want_labels) opt.async_results = true;
 		pv::Trace tr(*c, "session");
 		pv::decompose_device(*c, g.V(), g.E(), d_ep1.p, d_ep2.p, opt, dec);
-		labels_ready = want_labels && d_labels.p != nullptr;
+		labels_ready = d_labels.p != nullptr && (want_labels || !paths_up);   // (the hot path rebuilds the index right after)
+		if (!labels_ready) d_labels.release();
 		tr.mark("decompose_device");
 		if (dec.collisions) throw std::runtime_error("cycle-equivalence label collision detected by the exact bracket-set check");
 		// the flubble table is already flat in component order: swap the (page-locked) arrays instead of copying.
@@ -276,7 +280,7 @@ struct Session {
 			if (dec.comp_nv[k] >= 3) { forest.comp_id.push_back(sharded ? comp_global.at(k) : k + 1); forest.treeOff.push_back(base); }
 			else if (dec.comp_nfl[k]) throw std::runtime_error("decompose: flubbles in a component with fewer than 3 vertices");
 		}
-		forest_ready = true; pvst_cache_ok = false;
+		forest_ready = true; pvst_cache_ok = false; forest_subfl = 0;
 		tr.mark("forest conversion");
 	}
 
@@ -320,7 +324,7 @@ struct Session {
 		std::sort(files.begin(), files.end());
 		forest = pvh::Forest();
 		for (auto &f : files) pvh::read_pvst(dir + "/" + f.second, g, (u32)f.first, forest);
-		forest_ready = true; pvst_cache_ok = false;
+		forest_ready = true; pvst_cache_ok = false; dforest = pv::DevForest(); forest_subfl = -1;
 	}
 
 	void set_prefixes(const std::vector<std::string> &p) {
@@ -358,8 +362,9 @@ struct Session {
 		upload_paths();
 		std::vector<u32> refs(ref_ids.begin(), ref_ids.end());
 		// sub-flubble families and everything below them are never selected (color.cpp:117-125)
-		std::vector<u8> excl; bool any_excl = false;
-		for (char f : forest.family) if (f != 'F') { any_excl = true; break; }
+		std::vector<u8> excl;
+		if (forest_subfl < 0) { forest_subfl = 0; for (char f : forest.family) if (f != 'F') { forest_subfl = 1; break; } }   // once per forest, not per call
+		const bool any_excl = forest_subfl == 1;
 		if (any_excl) {
 			excl.assign(forest.n(), 0);
 			std::vector<u32> ord(forest.n());

@@ -58,13 +58,18 @@ def main():
     del ga
     nrec = 0
 
+    walls = []
+
     def step():
         n = 0
+        t0 = time.perf_counter()
         s.hot_path([own[0]], keep_resident=True)
         n += int(s.lib.pvgpu_session_record_count(s.h))
+        t1 = time.perf_counter()
         for pfx in own[1:]:
             s.call([pfx])
             n += int(s.lib.pvgpu_session_record_count(s.h))
+        walls.append(((t1 - t0) * 1e3, (time.perf_counter() - t1) * 1e3))
         return n
 
     with torch.cuda.stream(stream):
@@ -97,7 +102,7 @@ def main():
                           "scaling": "strong", "n_gpus": world, "segments": V, "links": E, "path_steps": S, "components": n_comp or 25,
                           "ms_per_step_max_over_ranks": t.item(), "value": E / (t.item() * 1e-3), "unit": "edges/s",
                           "records_all_ranks": int(cnt[0].item()), "flubbles_all_ranks": int(cnt[1].item()), "links_all_ranks": int(cnt[2].item()),
-                          "lpt_load_max_over_mean": max(w) / (sum(w) / len(w)), "steps": a.steps, "warmup": a.warmup}))
+                          "lpt_load_max_over_mean": max(w) / (sum(w) / len(w)), "rank0_host_wall_ms_hot_path_and_calls": [round(x, 2) for x in walls[-1]], "rank0_calls": len(own) - 1, "steps": a.steps, "warmup": a.warmup}))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
