@@ -223,6 +223,8 @@ def run_native(args):
         if rank == 0:
             clocks.start()
         launches0 = pv.launches
+        syncs0 = pv.host_syncs
+        syncs0 = pv.host_syncs
         evs, parts = [], []
         wall0 = time.perf_counter()
         for _ in range(args.steps):
@@ -235,6 +237,7 @@ def run_native(args):
         barrier()
         wall = time.perf_counter() - wall0
         launches = pv.launches - launches0
+        host_syncs = pv.host_syncs - syncs0
         dev_ms = sum(a.elapsed_time(b) for a, b in evs)
         clk = clocks.stop() if rank == 0 else None
         n_rec = int(sess.lib.pvgpu_session_record_count(sess.h))
@@ -363,7 +366,7 @@ def run_native(args):
                 "e2e": {"value": world * E / (e2e_ms_max / e2e_steps * 1e-3), "unit": "edges/s", "h2d_bytes_per_step": 8 * E + 4 * S + 4 * V, "d2h_bytes_per_step": d2h_bytes,
                         "ms_per_step": e2e_ms_max / e2e_steps, "steps": e2e_steps,
                         "vcf_text": {"bytes": text_bytes, "ms": text_s * 1e3, "note": "record lines written by the device text kernels (X_len, X_write), D2H into a page-locked buffer, write(2) to /dev/null; wall time of one pvgpu_session_vcf_write call, not inside e2e (SURVEY.md 8f2)"}},
-                "gfa_text": gfa_leg, "gpu_launches": int(launches), "wall_s_timed_region": wall,
+                "gfa_text": gfa_leg, "gpu_launches": int(launches), "host_syncs_per_step": host_syncs / args.steps, "wall_s_timed_region": wall,
                 "clocks": clk, "roofline": roofline, "cpu_baseline": cpu, "peak_device_bytes": pv.peak_bytes}
         print(json.dumps(line))
     if world > 1:

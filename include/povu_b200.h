@@ -36,6 +36,8 @@ const char *pvgpu_last_error(const pvgpu_ctx *ctx);
 /* kernels launched through this context so far (bench.py: gpu_launches) */
 uint64_t pvgpu_launch_count(const pvgpu_ctx *ctx);
 uint64_t pvgpu_peak_device_bytes(const pvgpu_ctx *ctx);
+/* times the host has waited for the context's stream so far (each wait drains the device queue; bench.py: host_syncs_per_step) */
+uint64_t pvgpu_host_sync_count(const pvgpu_ctx *ctx);
 /* per-kernel CUDA-event timing (bench.py roofline leg).  While on, every kernel launch is bracketed by
  * events on the context's stream; pvgpu_profile_json synchronises and writes a JSON array of
  * {name, launches, items, bytes (algorithmic), ms} (returns the size needed incl. NUL). */

@@ -38,6 +38,8 @@ def load_library(lib_path=None):
     lib.pvgpu_last_error.restype = C.c_char_p
     lib.pvgpu_launch_count.argtypes = [vp]
     lib.pvgpu_launch_count.restype = u64
+    lib.pvgpu_host_sync_count.argtypes = [vp]
+    lib.pvgpu_host_sync_count.restype = u64
     lib.pvgpu_peak_device_bytes.argtypes = [vp]
     lib.pvgpu_peak_device_bytes.restype = u64
     lib.pvgpu_build_kind.restype = C.c_int
@@ -208,6 +210,10 @@ class Povu:
     @property
     def launches(self):
         return int(self.lib.pvgpu_launch_count(self.h))
+
+    @property
+    def host_syncs(self):
+        return int(self.lib.pvgpu_host_sync_count(self.h))
 
     @property
     def peak_bytes(self):

@@ -208,9 +208,8 @@ inline void graph_build(Ctx &c, u32 V, u64 E, const u32 *ep1, const u32 *ep2, u3
 		std::vector<u32> fill(g.cpOff.begin(), g.cpOff.end() - 1);
 		for (u32 h = 0; h < H; h++) if (g.pathComp[h] != NONE) { u32 k = g.pathComp[h]; g.hapLocal[h] = fill[k] - g.cpOff[k]; g.cpList[fill[k]++] = h; }
 		auto up = [&](Buf<u32> &b, const std::vector<u32> &h) { b = Buf<u32>(c, h.size() ? h.size() : 1); c.h2d(b.p, h.data(), h.size() * 4); };
-		up(g.d_pathComp, g.pathComp); up(g.d_cpOff, g.cpOff); up(g.d_cpList, g.cpList); up(g.d_hapLocal, g.hapLocal);
+		up(g.d_pathComp, g.pathComp); up(g.d_cpOff, g.cpOff); up(g.d_cpList, g.cpList); up(g.d_hapLocal, g.hapLocal);   // (sources are members of g: they outlive the copies)
 	}
-	c.sync();
 	tr.mark("components");
 }
 
@@ -565,7 +564,7 @@ struct ChunkView {
 	u16 *mat; u32 *lapStart, *lapLen, *tangled, *hasData, *errs;
 	PV_DEV Lap lap(u32 row) const { u32 s = lapStart[row]; return Lap{s, s + lapLen[row]}; }
 };
-struct CandView { u32 *cL, *cR, *cStart, *cLen, *cRS, *cRL, *cHap, *cCls, *cHead, *gCount, *hsort; };
+struct CandView { u32 *cL, *cR, *cStart, *cLen, *cRS, *cRL, *cHap, *cCls, *cHead, *gCount, *hsort, *pinCount; };
 
 // comp_bounds + is_inverted over one (region, ref path, other path) pair (overlay.cpp:84-149); with
 // fill = true also gen_cxt, the two hap slices and the classification of every context
@@ -593,7 +592,7 @@ PV_DEV u32 scan_pair(const ChunkView &cv, u32 refLocal, u32 k, u32 row, bool fil
 					u32 o = off + cnt; cd.cCls[o] = 3;
 					u32 rs = 0, rn = 0, as = 0, an = 0;
 					if (fu == NONE || lv == NONE || !slice_bounds(g, u, v, rl, rs, rn) || !slice_bounds(g, u, v, al, as, an)) atomic_add(cv.errs + 0, 1u);   // the reference exits / crashes here
-					else if (rn == an && walk_revcomp(g.steps, rs, as, rn)) { cd.cCls[o] = 4; cd.cRS[o] = rs; cd.cStart[o] = as; cd.cHap[o] = i; }   // inversion pin pair for SNE (overlay.cpp:487-496)
+					else if (rn == an && walk_revcomp(g.steps, rs, as, rn)) { cd.cCls[o] = 4; cd.cRS[o] = rs; cd.cStart[o] = as; cd.cHap[o] = i; atomic_add(cd.pinCount, 1u); }   // inversion pin pair for SNE (overlay.cpp:487-496)
 					else if (rn == an && walk_equal(g.steps, rs, as, rn)) { }
 					else {
 						cd.cL[o] = g.steps[fu]; cd.cR[o] = g.steps[lv]; cd.cStart[o] = as; cd.cLen[o] = an; cd.cRS[o] = rs; cd.cRL[o] = rn; cd.cHap[o] = i;
@@ -611,7 +610,7 @@ PV_DEV u32 scan_pair(const ChunkView &cv, u32 refLocal, u32 k, u32 row, bool fil
 			Lap rl = cv.lap(rv.rowBase(r) + refLocal), al = cv.lap(row);
 			cd.cCls[off] = 3;
 			if (rl.lo == NONE || al.lo == NONE || rl.hi == rl.lo || al.hi == al.lo) atomic_add(cv.errs + 0, 1u);
-			else { cd.cCls[off] = 4; cd.cRS[off] = rl.lo; cd.cStart[off] = al.hi - 1; cd.cHap[off] = i; }
+			else { cd.cCls[off] = 4; cd.cRS[off] = rl.lo; cd.cStart[off] = al.hi - 1; cd.cHap[off] = i; atomic_add(cd.pinCount, 1u); }
 		}
 		return 1;
 	}
@@ -664,7 +663,8 @@ inline void overlay_pass(Ctx &c, const DevGraph &G, const GraphView &g, const Ca
 		const u32 nCand = candOff.read(nRows);
 		const size_t nC1 = nCand ? nCand : 1;
 		Buf<u32> cL(c, nC1), cR(c, nC1), cStart(c, nC1), cLen(c, nC1), cRS(c, nC1), cRL(c, nC1), cHap(c, nC1), cCls(c, nC1), cHead(c, nC1), gCount(c, nC1), hsort(c, nC1);
-		const CandView cd{cL.p, cR.p, cStart.p, cLen.p, cRS.p, cRL.p, cHap.p, cCls.p, cHead.p, gCount.p, hsort.p};
+		Buf<u32> pinCount(c, 1); pinCount.zero();
+		const CandView cd{cL.p, cR.p, cStart.p, cLen.p, cRS.p, cRL.p, cHap.p, cCls.p, cHead.p, gCount.p, hsort.p, pinCount.p};
 		// ---- C5b: slices per context, classification
 		// one thread per candidate slot; the thread of a row's FIRST slot fills the whole row.  Rows without a context
 		// (most paths carry the ref allele) cost nothing and the working lanes of a warp are consecutive busy rows.
@@ -674,25 +674,6 @@ inline void overlay_pass(Ctx &c, const DevGraph &G, const GraphView &g, const Ca
 			scan_pair(cv, refLocal, k, row, true, cd, (u32)x);
 		});
 		tr.mark("C5 pairs");
-		if (nCand) {   // pin pairs sit in candidate slots of class 4: pack them, in slot order
-			Buf<u32> pf(c, nCand), pidx;
-			u32 *pf_ = pf.p;
-			parallel_for<S_pinflag>(c, nCand, PV_LAMBDA(size_t x) { pf_[x] = cd.cCls[x] == 4 ? 1u : 0u; });
-			const u32 np = compact_flags(c, pf.p, nCand, pidx);
-			if (np) {
-				pins.pieces.emplace_back();
-				PinStore::Piece &pc = pins.pieces.back();
-				pc.n = np; pc.keyR = Buf<u32>(c, np); pc.keyJ = Buf<u32>(c, np); pc.keyK = Buf<u32>(c, np); pc.keySlot = Buf<u32>(c, np); pc.refStep = Buf<u32>(c, np); pc.altStep = Buf<u32>(c, np);
-				u32 *kR = pc.keyR.p, *kJ = pc.keyJ.p, *kK = pc.keyK.p, *kS = pc.keySlot.p, *rS = pc.refStep.p, *aS = pc.altStep.p; const u32 *pidx_ = pidx.p;
-				parallel_for<S_pinpack>(c, np, PV_LAMBDA(size_t q) {
-					u32 x = pidx_[q];
-					u32 row = ub_u32(candOff_, 0, nRows + 1, x) - 1; u32 r = rv.row2rov(row);
-					kR[q] = rv.region(r); kJ[q] = rv.instJ ? rv.instJ[r] : 0u; kK[q] = k; kS[q] = x;
-					rS[q] = cd.cRS[x]; aS[q] = cd.cStart[x];
-				});
-				pins.total += np;
-			}
-		}
 		// ---- C6a: group alt slices by (context, class, walk) per region, order groups like the reference's std::maps
 		Buf<u32> recCnt(c, (size_t)Rc + 1), grpCnt(c, (size_t)Rc + 1), recOff(c, (size_t)Rc + 1), grpOff(c, (size_t)Rc + 1);
 		u32 *recCnt_ = recCnt.p, *grpCnt_ = grpCnt.p;
@@ -721,7 +702,27 @@ inline void overlay_pass(Ctx &c, const DevGraph &G, const GraphView &g, const Ca
 		});
 		exclusive_scan(c, recCnt.p, recOff.p, (size_t)Rc + 1, OpAddU32(), 0u);
 		exclusive_scan(c, grpCnt.p, grpOff.p, (size_t)Rc + 1, OpAddU32(), 0u);
-		const u32 nRec = recOff.read(Rc), nGrp = grpOff.read(Rc);
+		u32 nRec, nGrp, nPin;
+		{ MultiRead mr(c); mr.add(&nRec, recOff.p + Rc, 4); mr.add(&nGrp, grpOff.p + Rc, 4); mr.add(&nPin, pinCount.p, 4); mr.wait(); }
+		if (nPin) {   // pin pairs sit in candidate slots of class 4 (counted by C_pair_fill): pack them, in slot order
+			Buf<u32> pf(c, nCand), pidx;
+			u32 *pf_ = pf.p;
+			parallel_for<S_pinflag>(c, nCand, PV_LAMBDA(size_t x) { pf_[x] = cd.cCls[x] == 4 ? 1u : 0u; });
+			const u32 np = compact_flags(c, pf.p, nCand, pidx);
+			if (np) {
+				pins.pieces.emplace_back();
+				PinStore::Piece &pc = pins.pieces.back();
+				pc.n = np; pc.keyR = Buf<u32>(c, np); pc.keyJ = Buf<u32>(c, np); pc.keyK = Buf<u32>(c, np); pc.keySlot = Buf<u32>(c, np); pc.refStep = Buf<u32>(c, np); pc.altStep = Buf<u32>(c, np);
+				u32 *kR = pc.keyR.p, *kJ = pc.keyJ.p, *kK = pc.keyK.p, *kS = pc.keySlot.p, *rS = pc.refStep.p, *aS = pc.altStep.p; const u32 *pidx_ = pidx.p;
+				parallel_for<S_pinpack>(c, np, PV_LAMBDA(size_t q) {
+					u32 x = pidx_[q];
+					u32 row = ub_u32(candOff_, 0, nRows + 1, x) - 1; u32 r = rv.row2rov(row);
+					kR[q] = rv.region(r); kJ[q] = rv.instJ ? rv.instJ[r] : 0u; kK[q] = k; kS[q] = x;
+					rS[q] = cd.cRS[x]; aS[q] = cd.cStart[x];
+				});
+				pins.total += np;
+			}
+		}
 		if (nRec == 0) continue;
 		// ---- C6b: records + groups (offsets already global: the host only appends)
 		const u32 grpBase = (u32)out.nGrpTot; const u64 gtBase = out.nGtTot;
@@ -761,7 +762,8 @@ inline void overlay_pass(Ctx &c, const DevGraph &G, const GraphView &g, const Ca
 		});
 		c.memset0(recNh.p + nRec, 8);
 		exclusive_scan(c, recNh.p, gtOff.p, (size_t)nRec + 1, OpAddU64(), (u64)0);
-		u64 nGt; c.d2h(&nGt, gtOff.p + nRec, 8);
+		u64 nGt;
+		if (uniformNh) nGt = (u64)nRec * uniformNh; else c.d2h(&nGt, gtOff.p + nRec, 8);   // every matrix has the same number of rows: no need to ask the device
 		Buf<u16> gt(c, nGt ? nGt : 1);
 		c.memset_ff(gt.p, nGt * 2);
 		u16 *gt_ = gt.p;
@@ -1437,7 +1439,7 @@ inline void call_device(Ctx &c, const DevGraph &G, const CallIn &in, const CallO
 	}
 	Buf<u64> sliceTabD(c, sliceTab.size() ? sliceTab.size() : 1);
 	c.h2d(sliceTabD.p, sliceTab.data(), sliceTab.size() * 8);
-	c.d2h(hc, cnt.p, 32);
+	if (haveBig) c.d2h(hc, cnt.p, 32);   // the arena tiers may have counted more failed sorts; without them the first read still holds
 	tr.mark("C2 bfs");
 	// regions whose BFS/Kahn sort failed (a cycle inside the region): the reference's haplotype-lap order
 	// (graph.cpp:194-395), one thread per region over an arena sized by the region's total lap length
@@ -1515,9 +1517,8 @@ inline void call_device(Ctx &c, const DevGraph &G, const CallIn &in, const CallO
 	exclusive_scan(c, rovJ.p, rovOff.p, (size_t)R + 1, OpAddU32(), 0u);
 	exclusive_scan(c, rowsOf.p, rowPre.p, (size_t)R + 1, OpAddU64(), (u64)0);
 	exclusive_scan(c, cellsOf.p, cellPre.p, (size_t)R + 1, OpAddU64(), (u64)0);
-	u64 ht[4]; c.d2h(ht, tot.p, 32);
-	u64 totRows, totCells; c.d2h(&totRows, rowPre.p + R, 8); c.d2h(&totCells, cellPre.p + R, 8);
-	const u32 sumJ = rovOff.read(R);
+	u64 ht[4]; u64 totRows, totCells; u32 sumJ;
+	{ MultiRead mr(c); mr.add(ht, tot.p, 32); mr.add(&totRows, rowPre.p + R, 8); mr.add(&totCells, cellPre.p + R, 8); mr.add(&sumJ, rovOff.p + R, 4); mr.wait(); }
 	out.max_J = ht[0];
 	Buf<u32> rovVerts(c, sumJ);
 	u32 *rovVerts_ = rovVerts.p; const u32 *rovOff_ = rovOff.p;
@@ -1637,9 +1638,9 @@ inline void call_device(Ctx &c, const DevGraph &G, const CallIn &in, const CallO
 	out.n_pin_pairs = pins.total;
 	if (pins.total) sne_pass(c, G, g, in, pins, R, errs.p, out, tr);
 	out.rov_tangled.resize(out.rov_fl.size(), 0);
-	c.d2h(hc, cnt.p, 32);
+	u32 he[8];
+	{ MultiRead mr(c); mr.add(hc, cnt.p, 32); mr.add(he, errs.p, 32); mr.wait(); }
 	out.n_sort_failed = hc[1]; out.n_too_small = hc[2];
-	u32 he[8]; c.d2h(he, errs.p, 32);
 	out.n_hard_errors = he[0] + hc[4]; out.n_subr_clamped = he[4];
 	if (he[2]) throw std::runtime_error("call: a path visits one vertex more than 65534 times inside a region (u16 depth cell overflow)");
 	for (u32 t : out.rov_tangled) if (t) out.n_tangled++;

@@ -46,6 +46,7 @@ int pvgpu_create(int device, void *stream, pvgpu_ctx **out) {
 void pvgpu_destroy(pvgpu_ctx *x) { if (x) { x->c.destroy(); delete x; } }
 const char *pvgpu_last_error(const pvgpu_ctx *x) { return x ? x->err.c_str() : "null context"; }
 uint64_t pvgpu_launch_count(const pvgpu_ctx *x) { return x ? x->c.launches : 0; }
+uint64_t pvgpu_host_sync_count(const pvgpu_ctx *x) { return x ? x->c.host_syncs : 0; }
 uint64_t pvgpu_peak_device_bytes(const pvgpu_ctx *x) { return x ? x->c.bytes_peak : 0; }
 void pvgpu_set_profiling(pvgpu_ctx *x, int on) { if (x) { x->c.profiling = on != 0; if (on) x->c.prof_agg.clear(); } }
 size_t pvgpu_profile_json(pvgpu_ctx *x, char *buf, size_t cap) {

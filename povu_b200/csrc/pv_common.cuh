@@ -54,6 +54,23 @@ struct u128 { u64 lo, hi; };
 	} while (0)
 #endif
 
+#ifndef PV_EMU
+// per-process pool of 1 MiB page-locked staging blocks (GFA text on its way in, VCF text on its way out): page-locking is
+// slow (~0.3 ms per MiB), so blocks are allocated once and recycled
+struct PinnedPool {
+	static const size_t BLK = 1u << 20;
+	std::mutex m; std::vector<char *> free_;
+	char *get() {
+		{ std::lock_guard<std::mutex> l(m); if (!free_.empty()) { char *p = free_.back(); free_.pop_back(); return p; } }
+		char *p = nullptr;
+		if (cudaHostAlloc((void **)&p, BLK, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+		return p;
+	}
+	void put(char *p) { if (!p) return; std::lock_guard<std::mutex> l(m); free_.push_back(p); }
+	static PinnedPool &inst() { static PinnedPool *g = new PinnedPool(); return *g; }   // never destroyed: outlives the CUDA context teardown order
+};
+#endif
+
 // ---------------------------------------------------------------------------------------------
 // execution context: one CUDA stream, stream-ordered allocations, launch counter
 // ---------------------------------------------------------------------------------------------
@@ -68,6 +85,7 @@ struct Ctx {
 	int device = 0;
 	int sm_count = 148;
 	u64 launches = 0;       // kernels launched through this context (bench.py: gpu_launches)
+	u64 host_syncs = 0;     // times the host waited for the main stream (every one drains the GPU: the launch queue runs dry)
 	// optional per-kernel CUDA-event timing (bench.py roofline leg): name -> {launches, items, bytes, ms}
 	bool profiling = false;
 	struct ProfRec { const char *name; u64 items; u64 bytes;
@@ -116,6 +134,7 @@ struct Ctx {
 #ifndef PV_EMU
 	cudaStream_t up_stream = nullptr; cudaEvent_t up_ev = nullptr;
 #endif
+	char *h_scratch = nullptr;   // page-locked block for MultiRead
 	bool up_pending = false;
 	void up_begin();
 	void h2d_up(void *d, const void *h, size_t bytes);
@@ -187,11 +206,13 @@ inline void Ctx::destroy() {
 	if (lb_ticket) { cudaFree(lb_ticket); lb_ticket = nullptr; }
 	if (copy_stream) { cudaStreamDestroy(copy_stream); cudaEventDestroy(copy_ev); copy_stream = nullptr; copy_ev = nullptr; }
 	if (up_stream) { cudaStreamDestroy(up_stream); cudaEventDestroy(up_ev); up_stream = nullptr; up_ev = nullptr; }
+	if (h_scratch) { PinnedPool::inst().put(h_scratch); h_scratch = nullptr; }
 	if (own_stream && stream) cudaStreamDestroy(stream);
 	stream = nullptr;
 #endif
 }
 inline void Ctx::sync() {
+	host_syncs++;
 #ifndef PV_EMU
 	PV_CUDA_CHECK(cudaStreamSynchronize(stream));
 #endif
@@ -246,6 +267,7 @@ inline void Ctx::h2d(void *d, const void *h, size_t bytes) {
 }
 inline void Ctx::d2h(void *h, const void *d, size_t bytes) {
 	if (!bytes) return;
+	host_syncs++;
 #ifndef PV_EMU
 	PV_CUDA_CHECK(cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, stream));
 	PV_CUDA_CHECK(cudaStreamSynchronize(stream));
@@ -396,23 +418,6 @@ struct Trace {
 	void mark(const char *what) { if (!on) return; c.sync(); double t = now(); fprintf(stderr, "[trace] %s: %-28s %8.3f ms\n", scope, what, t - t0); t0 = t; }
 };
 
-#ifndef PV_EMU
-// per-process pool of 1 MiB page-locked staging blocks (GFA text on its way in, VCF text on its way out): page-locking is
-// slow (~0.3 ms per MiB), so blocks are allocated once and recycled
-struct PinnedPool {
-	static const size_t BLK = 1u << 20;
-	std::mutex m; std::vector<char *> free_;
-	char *get() {
-		{ std::lock_guard<std::mutex> l(m); if (!free_.empty()) { char *p = free_.back(); free_.pop_back(); return p; } }
-		char *p = nullptr;
-		if (cudaHostAlloc((void **)&p, BLK, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
-		return p;
-	}
-	void put(char *p) { if (!p) return; std::lock_guard<std::mutex> l(m); free_.push_back(p); }
-	static PinnedPool &inst() { static PinnedPool *g = new PinnedPool(); return *g; }   // never destroyed: outlives the CUDA context teardown order
-};
-#endif
-
 // RAII device buffer (stream-ordered)
 template <class T> struct Buf {
 	Ctx *c = nullptr;
@@ -439,6 +444,31 @@ template <class T> struct Buf {
 	// asynchronous copy of the first m elements into a pinned host vector (capacity reused); sync before reading
 	void to_hvec(hvec<T> &h, size_t m) const { h.resize(m); c->d2h_async(h.data(), p, m * sizeof(T)); }
 	T read(size_t i) const { T v; c->d2h(&v, p + i, sizeof(T)); return v; }
+};
+
+// several small device -> host reads with ONE host wait: the values land in a page-locked scratch block of the context
+struct MultiRead {
+	Ctx &c; size_t used = 0;
+	struct Item { void *dst; size_t off, bytes; };
+	std::vector<Item> items;
+	explicit MultiRead(Ctx &c_) : c(c_) {}
+	void add(void *dst, const void *src, size_t bytes) {
+#ifndef PV_EMU
+		if (!c.h_scratch) { c.h_scratch = PinnedPool::inst().get(); if (!c.h_scratch) throw std::runtime_error("povu_b200: no page-locked scratch"); }
+		if (used + bytes > PinnedPool::BLK) throw std::runtime_error("MultiRead: too much data for the scratch block");
+		PV_CUDA_CHECK(cudaMemcpyAsync(c.h_scratch + used, src, bytes, cudaMemcpyDeviceToHost, c.stream));
+		items.push_back(Item{dst, used, bytes}); used += (bytes + 7) & ~(size_t)7;
+#else
+		memcpy(dst, src, bytes);
+#endif
+	}
+	void wait() {
+		c.sync();
+#ifndef PV_EMU
+		for (auto &i : items) memcpy(i.dst, c.h_scratch + i.off, i.bytes);
+#endif
+		items.clear(); used = 0;
+	}
 };
 
 // ---------------------------------------------------------------------------------------------

@@ -76,6 +76,7 @@ PV_KERNEL(K_segconf, 12);
 PV_KERNEL(K_finalize, 36);
 PV_KERNEL(K_visit, 16);
 PV_KERNEL(K_active, 12);
+PV_KERNEL(K_pack, 24);
 PV_KERNEL(K_compcount, 12);
 PV_KERNEL(K_treeslot, 8);
 PV_KERNEL(K_euler, 48);
@@ -284,7 +285,9 @@ inline void decompose_device(Ctx &c, u32 V, u64 E, const u32 *ep1, const u32 *ep
 					if (old != NONE && old != rho) atomic_min(trunc_ + comp_[v], old > rho ? old : rho);
 					itFlag_[it * 32] = 1;
 				});
-				if ((it == 1 || (it & 7) == 7) && !itFlag.read((size_t)it * 32)) break;
+				// from round 1 on the host looks at the convergence flag after iteration 1 (later rounds strip short paths and stop
+				// here) and every 8th iteration; round 0 follows a path as long as the graph and runs to the end unobserved
+				if (round > 0 && (it == 1 || (it & 7) == 7) && !itFlag.read((size_t)it * 32)) break;
 				std::swap(Ja, Jb);
 			}
 		}
@@ -534,6 +537,7 @@ inline void decompose_device(Ctx &c, u32 V, u64 E, const u32 *ep1, const u32 *ep
 		radix_sort_pairs(c, wkey, ord, nS, 32);
 		wkey_ = wkey.p; ord_ = ord.p;
 		if (w == 3) break;
+		if (w == 0 && nS > (1u << 16)) continue;   // 32 bits cannot separate that many keys (birthday bound): do not stop to ask
 		c.memset0(flag.p, 4);
 		parallel_for<K_word>(c, nS, PV_LAMBDA(size_t i) {
 			if (i == 0) return;
@@ -679,16 +683,26 @@ inline void decompose_device(Ctx &c, u32 V, u64 E, const u32 *ep1, const u32 *ep
 		fA.to_hvec(out.a_v, nFl); fZ.to_hvec(out.z_v, nFl); fPar.to_hvec(out.parent, nFl); fDepth.to_hvec(out.depth, nFl); fComp.to_hvec(out.comp, nFl);
 		fAf.to_hvec(out.a_fwd, nFl); fZf.to_hvec(out.z_fwd, nFl); fBase.to_hvec(out.fl_base, nFl);
 	}
-	u32 fl[4];
-	c.d2h(fl, flag.p, 16);   // synchronises the main stream
-	out.collisions = fl[1];
-	out.comp_root = roots.to_host(nComp);
-	out.comp_nv = cNv.to_host(); out.comp_nv.resize(nComp);
-	out.comp_has_tips = cHasTips.to_host();
-	out.comp_nonlaminar = lamBad.to_host(); out.comp_nonlaminar.resize(nComp);
-	std::vector<u32> flb = cFlBase.to_host();
-	out.comp_nfl.resize(nComp);
-	for (u32 k = 0; k < nComp; k++) out.comp_nfl[k] = flb[k + 1] - flb[k];
+	// the small per-component tables and the flags travel as ONE packed copy (one host wait instead of six)
+	{
+		const size_t PK = (size_t)nComp + 1;
+		Buf<u32> pack(c, 4 + 5 * PK);
+		u32 *pk = pack.p; const u32 *rt_ = roots.p, *nv_ = cNv.p, *tp_ = cHasTips.p, *lb_ = lamBad.p, *fb_ = cFlBase.p;
+		parallel_for<K_pack>(c, PK > 4 ? PK : 4, PV_LAMBDA(size_t k) {
+			if (k < 4) pk[k] = flag_[k];
+			if (k >= PK) return;
+			const bool in = k < nComp;
+			pk[4 + k] = in ? rt_[k] : 0u; pk[4 + PK + k] = nv_[k]; pk[4 + 2 * PK + k] = in ? tp_[k] : 0u; pk[4 + 3 * PK + k] = in ? lb_[k] : 0u; pk[4 + 4 * PK + k] = fb_[k];
+		});
+		std::vector<u32> h = pack.to_host();   // synchronises the main stream
+		out.collisions = h[1];
+		out.comp_root.assign(h.begin() + 4, h.begin() + 4 + nComp);
+		out.comp_nv.assign(h.begin() + 4 + PK, h.begin() + 4 + PK + nComp);
+		out.comp_has_tips.assign(h.begin() + 4 + 2 * PK, h.begin() + 4 + 2 * PK + nComp);
+		out.comp_nonlaminar.assign(h.begin() + 4 + 3 * PK, h.begin() + 4 + 3 * PK + nComp);
+		out.comp_nfl.resize(nComp);
+		for (u32 k = 0; k < nComp; k++) out.comp_nfl[k] = h[4 + 4 * PK + k + 1] - h[4 + 4 * PK + k];
+	}
 	if (opt.want_stack) {
 		out.stack_v = stV.to_host(); out.stack_class = classOf.to_host();
 		std::vector<u32> es = entrySide.to_host();

@@ -18,11 +18,13 @@ sess = api.Session.from_graph(pv, g, with_labels=True)
 for _ in range(3):
     sess.hot_path(["S001#1"], keep_resident=True)
 torch.cuda.synchronize()
+s0 = pv.host_syncs
 t0 = time.perf_counter()
 for _ in range(5):
     parts = sess.hot_path(["S001#1"], keep_resident=True)
 torch.cuda.synchronize()
 wall = (time.perf_counter() - t0) / 5 * 1e3
+print(f"host waits on the stream per step: {(pv.host_syncs - s0) / 5:.0f}")
 l0 = pv.launches
 pv.set_profiling(True)
 sess.hot_path(["S001#1"], keep_resident=True)
