@@ -3,7 +3,7 @@
 For every configuration: generate the graph, run the whole hot path on the GPU, then cut a prefix of the
 (chain-shaped) graph, run the UNMODIFIED reference (oracle/_ref/povu_ref) on that prefix and require that its
 records are exactly the GPU records whose context lies inside the prefix (same text: ids, POS, alleles, genotypes).
-usage: python scripts/scale_run.py cfg2|cfg3|cfg3s|cfg5s [...]"""
+usage: python scripts/scale_run.py cfg2|cfg3|cfg3s|cfg5s|cfg5h [...]"""
 import json
 import os
 import re
@@ -31,6 +31,9 @@ def build(cfg):
     if cfg == "cfg5s":
         g = synth.snp_indel_chain(200_000, n_paths=232, seed=5)
         return g, "S001#1", 10_000 * 5 // 2
+    if cfg == "cfg5h":   # half of cfg5's flubbles at its full path count: 500 k bubbles x 464 paths, ~0.43 G steps
+        g = synth.snp_indel_chain(500_000, n_paths=464, seed=5)
+        return g, "S001#1", 4_000 * 5 // 2
     raise SystemExit("unknown config " + cfg)
 
 
