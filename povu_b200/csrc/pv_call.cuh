@@ -32,7 +32,6 @@ PV_DEV u64 atomic_cas64(u64 *p, u64 cmp, u64 v) { return (u64)atomicCAS((unsigne
 inline u64 atomic_cas64(u64 *p, u64 cmp, u64 v) { u64 o = *p; if (o == cmp) *p = v; return o; }
 #endif
 
-PV_KERNEL(C_adj_entries, 24);
 PV_KERNEL(C_adj_fill, 16);
 PV_KERNEL(C_loci_len, 12);
 PV_KERNEL(C_loci, 20);
@@ -75,6 +74,10 @@ PV_DEV u64 ub_u64(const u64 *a, u64 lo, u64 hi, u64 key) {
 // ---------------------------------------------------------------------------------------------
 // device-resident graph + paths (built once, used by every call)
 // ---------------------------------------------------------------------------------------------
+struct AdjEntryPort {   // port of adjacency entry j (2e = first end of link e, 2e+1 = second end; P = dropped duplicate)
+	const u32 *ep1, *ep2; u32 P;
+	PV_DEV u32 operator()(size_t j) const { u32 a = ep1[j >> 1], b = ep2[j >> 1]; return (j & 1u) ? (a == b ? P : b) : a; }
+};
 struct StepVertex { const u32 *steps; PV_DEV u32 operator()(size_t s) const { return steps[s] >> 1; } };
 
 struct DevGraph {
@@ -140,24 +143,18 @@ inline void graph_build(Ctx &c, u32 V, u64 E, const u32 *ep1, const u32 *ep2, u3
 	// ---- adjacency in whole-graph edge order (what `call` iterates: bidirected.hpp:68-69)
 	g.adjOff = Buf<u32>(c, (size_t)P + 2); g.adjNbr = Buf<u32>(c, M ? M : 1);
 	{
-		Buf<u32> key(c, M ? M : 1), idx(c, M ? M : 1), nbr(c, M ? M : 1), cnt(c, (size_t)P + 2);
-		cnt.zero();
-		u32 *key_ = key.p, *idx_ = idx.p, *nbr_ = nbr.p, *cnt_ = cnt.p;
-		parallel_for<C_adj_entries>(c, E, PV_LAMBDA(size_t e) {
-			u32 a = ep1[e], b = ep2[e];
+		// entries 2e / 2e+1 = the two ends of link e, grouped by port in link order (group_indices: ports have a handful of
+		// entries; hubs take the restricted stable sort).  Bucket P collects the second end of a v+ -> v+ style loop, which
+		// is one std::set entry in the reference.
+		Buf<u32> list(c, M ? M : 1);
+		group_indices(c, AdjEntryPort{ep1, ep2, P}, M, P + 1, g.adjOff.p, list.p);
+		u32 *adjNbr_ = g.adjNbr.p; const u32 *list_ = list.p;
+		parallel_for<C_adj_fill>(c, M, PV_LAMBDA(size_t s) {
+			u32 j = list_[s]; u32 a = ep1[j >> 1], b = ep2[j >> 1];
 			bool self = (a >> 1) == (b >> 1);
 			// Edge::get_other_vtx(v, side) answers the complement side for any self-loop (bidirected.cpp:66-77)
-			key_[2 * e] = a; nbr_[2 * e] = self ? (a ^ 1u) : b; idx_[2 * e] = (u32)(2 * e);
-			bool dup = a == b;   // v+ -> v- style loop: one std::set entry
-			key_[2 * e + 1] = dup ? P : b; nbr_[2 * e + 1] = self ? (b ^ 1u) : a; idx_[2 * e + 1] = (u32)(2 * e + 1);
-			atomic_add(cnt_ + a, 1u);
-			if (!dup) atomic_add(cnt_ + b, 1u);
+			adjNbr_[s] = (j & 1u) ? (self ? (b ^ 1u) : a) : (self ? (a ^ 1u) : b);
 		});
-		radix_sort_pairs(c, key, idx, M, bits_for((u64)P + 1));
-		idx_ = idx.p;
-		exclusive_scan(c, cnt.p, g.adjOff.p, (size_t)P + 2, OpAddU32(), 0u);
-		u32 *adjNbr_ = g.adjNbr.p;
-		parallel_for<C_adj_fill>(c, M, PV_LAMBDA(size_t s) { adjNbr_[s] = nbr_[idx_[s]]; });
 	}
 	tr.mark("adjacency");
 	// ---- paths

@@ -59,8 +59,7 @@ struct DecompOpts {
 struct DevForest { Buf<u32> a_v, z_v, parent, depth, comp, fl_base; Buf<u8> a_fwd, z_fwd; u32 n = 0; bool valid = false; };
 
 // kernel tags with their algorithmic bytes per logical item
-PV_KERNEL(K_minport, 24);      // 2 endpoints in, key + idx out, 2 degree atomics
-PV_KERNEL(K_entries, 36);      // order + 2 endpoints in, 2 x (port, nbr, idx) out
+PV_KERNEL(K_minport, 16);      // 2 endpoints in, 2 degree atomics
 PV_KERNEL(K_csr_fill, 24);
 PV_KERNEL(K_rev, 12);
 PV_KERNEL(K_tip, 12);
@@ -108,6 +107,17 @@ struct OpMP {
 	}
 };
 
+struct EdgeMinPort { const u32 *ep1, *ep2; PV_DEV u32 operator()(size_t e) const { u32 a = ep1[e], b = ep2[e]; return a < b ? a : b; } };
+// port of adjacency entry j: entries 2k / 2k+1 are the two ends of the k-th edge in renumbered order
+struct EntryPort {
+	const u32 *eord, *ep1, *ep2;
+	PV_DEV u32 operator()(size_t j) const {
+		u32 e = eord[j >> 1]; u32 a = ep1[e], b = ep2[e];
+		if ((a >> 1) == (b >> 1)) { a = a & ~1u; b = a | 1u; }   // any self-loop becomes left--right (bidirected.cpp:66-77,526-531)
+		return (j & 1u) ? b : a;
+	}
+};
+
 PV_DEV u32 uf_find(u32 *uf, u32 x) {
 	u32 p = ld_volatile(uf + x);
 	while (p != x) {
@@ -137,37 +147,25 @@ inline void decompose_device(Ctx &c, u32 V, u64 E, const u32 *ep1, const u32 *ep
 	// ------------------------------------------------------------------ D1: CSR in reference edge order
 	Buf<u32> adjOff(c, P + 1), adjNbr(c, M ? M : 1), adjOwner(c, M ? M : 1), rev(c, M ? M : 1), origDeg(c, P);
 	{
-		Buf<u32> ekey(c, E ? E : 1), eord(c, E ? E : 1);
-		u32 *ekey_ = ekey.p, *eord_ = eord.p;
+		// Both orders are "group by port, keep the input order inside a port", and a port holds a handful of entries:
+		// group_indices (count / slot / per-group insertion sort; hub ports take the restricted stable sort) instead of
+		// two full radix sorts.
+		Buf<u32> eord(c, E ? E : 1), eOff(c, (size_t)P + 1);
 		origDeg.zero();
 		u32 *origDeg_ = origDeg.p;
-		parallel_for<K_minport>(c, E, PV_LAMBDA(size_t e) {
-			u32 a = ep1[e], b = ep2[e];
-			ekey_[e] = a < b ? a : b; eord_[e] = (u32)e;
-			atomic_add(origDeg_ + a, 1u); atomic_add(origDeg_ + b, 1u);
-		});
-		radix_sort_pairs(c, ekey, eord, E, bits_for(P));   // stable: (min port, file order) = renumbered edge idx
-		eord_ = eord.p;
-		Buf<u32> entPort(c, M ? M : 1), entIdx(c, M ? M : 1), entNbr(c, M ? M : 1);
-		u32 *entPort_ = entPort.p, *entIdx_ = entIdx.p, *entNbr_ = entNbr.p;
-		parallel_for<K_entries>(c, E, PV_LAMBDA(size_t k) {
-			u32 e = eord_[k]; u32 a = ep1[e], b = ep2[e];
-			if ((a >> 1) == (b >> 1)) { a = a & ~1u; b = a | 1u; }   // any self-loop becomes left--right (bidirected.cpp:66-77,526-531)
-			entPort_[2 * k] = a; entNbr_[2 * k] = b; entIdx_[2 * k] = (u32)(2 * k);
-			entPort_[2 * k + 1] = b; entNbr_[2 * k + 1] = a; entIdx_[2 * k + 1] = (u32)(2 * k + 1);
-		});
-		radix_sort_pairs(c, entPort, entIdx, M, bits_for(P));
-		entPort_ = entPort.p; entIdx_ = entIdx.p;
-		Buf<u32> slotOf(c, M ? M : 1), cnt(c, P + 1);
-		cnt.zero();
-		u32 *slotOf_ = slotOf.p, *cnt_ = cnt.p, *adjNbr_ = adjNbr.p, *adjOwner_ = adjOwner.p, *rev_ = rev.p;
+		parallel_for<K_minport>(c, E, PV_LAMBDA(size_t e) { atomic_add(origDeg_ + ep1[e], 1u); atomic_add(origDeg_ + ep2[e], 1u); });
+		group_indices(c, EdgeMinPort{ep1, ep2}, E, P, eOff.p, eord.p);   // (min port, file order) = renumbered edge idx
+		eOff.release();
+		// entries 2k / 2k+1 = the two ends of the k-th renumbered edge, grouped by port -> the adjacency and its offsets
+		Buf<u32> list(c, M ? M : 1), slotOf(c, M ? M : 1);
+		const EntryPort EP{eord.p, ep1, ep2};
+		group_indices(c, EP, M, P, adjOff.p, list.p);
+		u32 *slotOf_ = slotOf.p, *adjNbr_ = adjNbr.p, *adjOwner_ = adjOwner.p, *rev_ = rev.p; const u32 *list_ = list.p;
 		parallel_for<K_csr_fill>(c, M, PV_LAMBDA(size_t s) {
-			u32 j = entIdx_[s]; u32 p = entPort_[s];
-			adjNbr_[s] = entNbr_[j]; adjOwner_[s] = p; slotOf_[j] = (u32)s;
-			atomic_add(cnt_ + p, 1u);
+			u32 j = list_[s];
+			adjNbr_[s] = EP(j ^ 1u); adjOwner_[s] = EP(j); slotOf_[j] = (u32)s;
 		});
-		exclusive_scan(c, cnt.p, adjOff.p, (size_t)P + 1, OpAddU32(), 0u);
-		parallel_for<K_rev>(c, M, PV_LAMBDA(size_t s) { rev_[s] = slotOf_[entIdx_[s] ^ 1u]; });
+		parallel_for<K_rev>(c, M, PV_LAMBDA(size_t s) { rev_[s] = slotOf_[list_[s] ^ 1u]; });
 	}
 	const u32 *adjOff_ = adjOff.p, *adjNbr_ = adjNbr.p, *adjOwner_ = adjOwner.p, *rev_ = rev.p, *origDeg_ = origDeg.p;
 
