@@ -20,6 +20,8 @@
 #include <utility>
 #include <vector>
 #include <mutex>
+#include <map>
+#include <unordered_map>
 
 #ifndef PV_EMU
 #include <cuda_runtime.h>
@@ -100,6 +102,16 @@ struct Ctx {
 	void prof_end();
 	void prof_collect();
 	u64 bytes_alloc = 0, bytes_peak = 0;
+	// Block cache in front of cudaMallocAsync: the pipelines allocate ~200 scratch buffers per step, the big graphs
+	// multi-GB ones, and the driver pool's split / merge / remap work showed up as erratic 10-1000 ms stalls.  Freed
+	// blocks are kept by size (8 size classes per octave) and handed to the next request of a fitting class; everything
+	// runs on the context's stream, so reuse is ordered like the stream.  cache_limit bounds the idle bytes.
+#ifndef PV_EMU
+	std::multimap<size_t, void *> cache_free; std::unordered_map<void *, size_t> cache_live;
+	u64 cache_idle = 0, cache_limit = 0, cache_hits = 0, cache_misses = 0;
+	static size_t size_class(size_t bytes);
+	void cache_trim(u64 keep);
+#endif
 	// persistent scratch of the single-pass (decoupled look-back) scan and the onesweep radix sort.  Status words carry
 	// an epoch that grows with every use, so the scratch is never cleared between launches; only these two primitives
 	// ever write it (memory recycled from the pool could alias a live epoch).
@@ -158,6 +170,8 @@ inline void Ctx::init(int dev, void *ext_stream) {
 	PV_CUDA_CHECK(cudaDeviceGetDefaultMemPool(&pool, dev));
 	u64 thr = ~0ull;   // keep freed blocks cached in the pool between calls
 	PV_CUDA_CHECK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+	cache_limit = (u64)(p.totalGlobalMem / 2);   // idle blocks may hold up to half of the device memory
+	if (const char *e = getenv("POVU_B200_CACHE_LIMIT_MB")) cache_limit = strtoull(e, nullptr, 10) << 20;
 #else
 	(void)ext_stream;
 	const char *o = getenv("PV_EMU_ORDER");
@@ -201,6 +215,7 @@ inline void Ctx::rs_reserve(size_t words) {
 }
 inline void Ctx::destroy() {
 #ifndef PV_EMU
+	if (stream) { cache_trim(0); cudaStreamSynchronize(stream); }
 	if (lb_flags) { cudaFree(lb_flags); cudaFree(lb_vals); lb_flags = nullptr; lb_vals = nullptr; lb_cap = 0; }
 	if (rs_status) { cudaFree(rs_status); rs_status = nullptr; rs_cap = 0; }
 	if (lb_ticket) { cudaFree(lb_ticket); lb_ticket = nullptr; }
@@ -217,13 +232,39 @@ inline void Ctx::sync() {
 	PV_CUDA_CHECK(cudaStreamSynchronize(stream));
 #endif
 }
+#ifndef PV_EMU
+inline size_t Ctx::size_class(size_t bytes) {
+	if (bytes <= 512) return 512;
+	int hb = 63 - __builtin_clzll((unsigned long long)bytes);   // highest set bit
+	size_t step = (size_t)1 << (hb - 3);                          // 8 classes per octave: at most 12.5 % slack
+	return (bytes + step - 1) & ~(step - 1);
+}
+inline void Ctx::cache_trim(u64 keep) {
+	while (cache_idle > keep && !cache_free.empty()) {
+		auto it = std::prev(cache_free.end());   // largest first
+		cache_idle -= it->first;
+		cudaFreeAsync(it->second, stream);
+		cache_free.erase(it);
+	}
+}
+#endif
 inline void *Ctx::raw_alloc(size_t bytes) {
 	if (bytes == 0) bytes = 16;
 	bytes_alloc += bytes;
 	if (bytes_alloc > bytes_peak) bytes_peak = bytes_alloc;
 #ifndef PV_EMU
+	const size_t cls = size_class(bytes);
+	auto it = cache_free.lower_bound(cls);
+	if (it != cache_free.end() && it->first <= cls + cls / 4) {   // a block of this class, or at most two classes up
+		void *p = it->second; const size_t sz = it->first;
+		cache_free.erase(it); cache_idle -= sz; cache_live[p] = sz; cache_hits++;
+		return p;
+	}
 	void *p = nullptr;
-	PV_CUDA_CHECK(cudaMallocAsync(&p, bytes, stream));
+	cudaError_t e = cudaMallocAsync(&p, cls, stream);
+	if (e == cudaErrorMemoryAllocation) { cudaGetLastError(); cache_trim(0); cudaStreamSynchronize(stream); e = cudaMallocAsync(&p, cls, stream); }   // give the idle blocks back and retry
+	PV_CUDA_CHECK(e);
+	cache_live[p] = cls; cache_misses++;
 	return p;
 #else
 	void *p = malloc(bytes);
@@ -236,7 +277,12 @@ inline void Ctx::raw_free(void *p, size_t bytes) {
 	if (!p) return;
 	bytes_alloc -= bytes ? bytes : 16;
 #ifndef PV_EMU
-	cudaFreeAsync(p, stream);
+	auto it = cache_live.find(p);
+	if (it == cache_live.end()) { cudaFreeAsync(p, stream); return; }
+	const size_t sz = it->second;
+	cache_live.erase(it);
+	cache_free.emplace(sz, p); cache_idle += sz;
+	if (cache_limit && cache_idle > cache_limit) cache_trim(cache_limit / 2);
 #else
 	free(p);
 #endif

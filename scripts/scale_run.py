@@ -59,7 +59,7 @@ def main():
         t0 = time.time()
         s = api.Session.from_graph(pv, g)
         t_sess = time.time() - t0
-        for _ in range(4):           # the page-locked result vectors and the device pool reach their steady state after 3 calls
+        for _ in range(int(os.environ.get("SCALE_ITERS", "4"))):           # the page-locked result vectors and the device pool reach their steady state after 3 calls
             ms = s.hot_path([prefix])
         prof_top = None
         if os.environ.get("SCALE_PROF"):
