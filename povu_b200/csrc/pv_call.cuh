@@ -1590,16 +1590,24 @@ inline void call_device(Ctx &c, const DevGraph &G, const CallIn &in, const CallO
 		u32 colBase, colEnd;
 		if (chunkEnd.size() == 1) { colBase = 0; colEnd = sumJ; } else { colBase = rovOff.read(r0); colEnd = rovOff.read(r1); }
 		const u32 nCols = colEnd - colBase;
-		parallel_for<C_matfill>(c, nCols, PV_LAMBDA(size_t x) {
-			u32 r = ub_u32(rovOff_ + r0, 0, Rc + 1, colBase + (u32)x) - 1;
-			u32 J = rv.J(r); u32 j = colBase + (u32)x - rovOff_[r0 + r];
+		// LW logical lanes share one column and stride over the vertex's step list (coalesced when LW = 32); a lane owns the
+		// runs (consecutive steps of one path) whose first entry it meets.  LW follows the mean list length: with 16 paths
+		// a list has ~12 entries, with 464 paths ~350.
+		u32 LW = 1;
+		{ const u64 meanList = G.V ? (u64)G.S / G.V : 0; while (LW < 32 && (u64)LW * 8 < meanList) LW <<= 1; }
+		if (const char *e = getenv("POVU_B200_MATFILL_LANES")) { u32 v = (u32)strtoul(e, nullptr, 10); if (v >= 1 && v <= 32) LW = v; }   // tests: force the multi-lane path
+		parallel_for<C_matfill>(c, (size_t)nCols * LW, PV_LAMBDA(size_t t) {
+			const u32 x = (u32)(t / LW), lane = (u32)(t % LW);
+			u32 r = ub_u32(rovOff_ + r0, 0, Rc + 1, colBase + x) - 1;
+			u32 J = rv.J(r); u32 j = colBase + x - rovOff_[r0 + r];
 			u32 v = rovVerts_[colBase + x];
 			u32 comp = rv.comp(r);
-			u32 e = g.vsOff[v], ee = g.vsOff[v + 1];
-			while (e < ee) {
-				u32 h = g.vsHap[e]; u32 first = g.vsStep[e]; u32 n = 1;
+			const u32 a = g.vsOff[v], ee = g.vsOff[v + 1];
+			for (u32 e = a + lane; e < ee; e += LW) {
+				u32 h = g.vsHap[e];
+				if (e > a && g.vsHap[e - 1] == h) continue;   // not the head of its run
+				u32 first = g.vsStep[e]; u32 n = 1;
 				while (e + n < ee && g.vsHap[e + n] == h) n++;
-				e += n;
 				if (g.pathComp[h] != comp) continue;   // cannot happen for a connected walk; keeps indexing safe
 				u32 i = g.hapLocal[h];
 				if (n > 0xFFFEu) { atomic_add(cv.errs + 2, 1u); n = 0xFFFEu; }

@@ -643,7 +643,7 @@ template <class KeyFn> inline void group_indices(Ctx &c, KeyFn key, size_t n, u3
 	});
 	parallel_for<K_grp_sort>(c, B, PV_LAMBDA(size_t k) {
 		u32 m = cnt_[k];
-		if (m > small) { atomic_add(nBig_, m); return; }
+		if (m > small) { nBig_[0] = 1; return; }   // (a flag, not a sum: with many paths every group is large and a counter would serialise)
 		u32 *a = list + off[k];
 		for (u32 i = 1; i < m; i++) { u32 x = a[i]; u32 j = i; while (j > 0 && a[j - 1] > x) { a[j] = a[j - 1]; j--; } a[j] = x; }
 	});

@@ -58,3 +58,10 @@ def test_emu_call_hub_vertices(emu_lib, name, tmp_path, monkeypatch):
     """vertex -> steps index: every vertex visited more than once takes the hub path (restricted stable sort)"""
     monkeypatch.setenv("POVU_B200_VS_SMALL", "1")
     cc.check_golden(_ctx(emu_lib, 2), name, str(tmp_path))
+
+
+@pytest.mark.parametrize("name", ["nested_s1", "LPA"])
+def test_emu_call_matfill_lanes(emu_lib, name, tmp_path, monkeypatch):
+    """depth matrix: 32 logical lanes per column stride over the vertex's step list (the many-paths configuration)"""
+    monkeypatch.setenv("POVU_B200_MATFILL_LANES", "32")
+    cc.check_golden(_ctx(emu_lib, 2), name, str(tmp_path))

@@ -50,3 +50,10 @@ def test_gpu_call_hub_vertices(gpu, name, tmp_path, monkeypatch):
     """vertex -> steps index: every vertex visited more than once takes the hub path (restricted stable sort)"""
     monkeypatch.setenv("POVU_B200_VS_SMALL", "1")
     cc.check_golden(gpu, name, str(tmp_path))
+
+
+@pytest.mark.parametrize("name", ["nested_s1", "LPA"])
+def test_gpu_call_matfill_lanes(gpu, name, tmp_path, monkeypatch):
+    """depth matrix: 32 logical lanes per column stride over the vertex's step list (the many-paths configuration)"""
+    monkeypatch.setenv("POVU_B200_MATFILL_LANES", "32")
+    cc.check_golden(gpu, name, str(tmp_path))
