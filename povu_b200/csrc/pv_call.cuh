@@ -1592,9 +1592,9 @@ inline void call_device(Ctx &c, const DevGraph &G, const CallIn &in, const CallO
 		const u32 nCols = colEnd - colBase;
 		// LW logical lanes share one column and stride over the vertex's step list (coalesced when LW = 32); a lane owns the
 		// runs (consecutive steps of one path) whose first entry it meets.  LW follows the mean list length: with 16 paths
-		// a list has ~12 entries, with 464 paths ~350.
+		// a list has ~12 entries (one lane: 189 us at cfg2, two lanes would take 384 us), with 464 paths ~350 (32 lanes).
 		u32 LW = 1;
-		{ const u64 meanList = G.V ? (u64)G.S / G.V : 0; while (LW < 32 && (u64)LW * 8 < meanList) LW <<= 1; }
+		{ const u64 meanList = G.V ? (u64)G.S / G.V : 0; LW = meanList >= 64 ? 32u : (meanList >= 32 ? 8u : 1u); }   // (every lane repeats the column setup: short lists keep one lane)
 		if (const char *e = getenv("POVU_B200_MATFILL_LANES")) { u32 v = (u32)strtoul(e, nullptr, 10); if (v >= 1 && v <= 32) LW = v; }   // tests: force the multi-lane path
 		parallel_for<C_matfill>(c, (size_t)nCols * LW, PV_LAMBDA(size_t t) {
 			const u32 x = (u32)(t / LW), lane = (u32)(t % LW);
