@@ -1596,7 +1596,26 @@ inline void call_device(Ctx &c, const DevGraph &G, const CallIn &in, const CallO
 		u32 LW = 1;
 		{ const u64 meanList = G.V ? (u64)G.S / G.V : 0; LW = meanList >= 64 ? 32u : (meanList >= 32 ? 8u : 1u); }   // (every lane repeats the column setup: short lists keep one lane)
 		if (const char *e = getenv("POVU_B200_MATFILL_LANES")) { u32 v = (u32)strtoul(e, nullptr, 10); if (v >= 1 && v <= 32) LW = v; }   // tests: force the multi-lane path
-		parallel_for<C_matfill>(c, (size_t)nCols * LW, PV_LAMBDA(size_t t) {
+		if (LW == 1) parallel_for<C_matfill>(c, nCols, PV_LAMBDA(size_t x) {   // short lists: one thread walks the list run by run
+			u32 r = ub_u32(rovOff_ + r0, 0, Rc + 1, colBase + (u32)x) - 1;
+			u32 J = rv.J(r); u32 j = colBase + (u32)x - rovOff_[r0 + r];
+			u32 v = rovVerts_[colBase + x];
+			u32 comp = rv.comp(r);
+			u32 e = g.vsOff[v], ee = g.vsOff[v + 1];
+			while (e < ee) {
+				u32 h = g.vsHap[e]; u32 first = g.vsStep[e]; u32 n = 1;
+				while (e + n < ee && g.vsHap[e + n] == h) n++;
+				e += n;
+				if (g.pathComp[h] != comp) continue;   // cannot happen for a connected walk; keeps indexing safe
+				u32 i = g.hapLocal[h];
+				if (n > 0xFFFEu) { atomic_add(cv.errs + 2, 1u); n = 0xFFFEu; }
+				u32 code = n == 1 ? ((g.steps[first] & 1u) ? 2u : 1u) : n;
+				cv.mat[rv.matBase(r) + (u64)i * J + j] = (u16)code;
+				atomic_min(cv.lapStart + rv.rowBase(r) + i, first);
+				if (n > 1 && (j == 0 || j == J - 1) && atomic_exch(cv.tangled + r, 1u) == 0) atomic_add(cv.errs + 3, 1u);
+			}
+		});
+		else parallel_for<C_matfill>(c, (size_t)nCols * LW, PV_LAMBDA(size_t t) {
 			const u32 x = (u32)(t / LW), lane = (u32)(t % LW);
 			u32 r = ub_u32(rovOff_ + r0, 0, Rc + 1, colBase + x) - 1;
 			u32 J = rv.J(r); u32 j = colBase + x - rovOff_[r0 + r];

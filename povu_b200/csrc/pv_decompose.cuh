@@ -66,6 +66,7 @@ PV_KERNEL(K_tip, 12);
 PV_KERNEL(K_uf_init, 20);
 PV_KERNEL(K_uf_union, 24);     // per port: offsets + ~2 neighbours + visited + uf words
 PV_KERNEL(K_uf_flatten, 12);
+PV_KERNEL(K_uf_min, 12);
 PV_KERNEL(K_start, 12);
 PV_KERNEL(K_claim, 28);
 PV_KERNEL(K_entry, 24);
@@ -132,6 +133,18 @@ PV_DEV void uf_union(u32 *uf, u32 a, u32 b) {
 		a = uf_find(uf, a); b = uf_find(uf, b);
 		if (a == b) return;
 		if (a < b) { u32 t = a; a = b; b = t; }     // hook the larger root under the smaller: root = min index
+		if (atomic_cas(uf + a, a, b) == a) return;
+	}
+}
+// Hooking by a hashed priority instead of by index: on chain-shaped graphs (vertex ids ascending along the backbone) hooking
+// by index first builds one long list that every later find has to halve; a random priority keeps the trees shallow.  The
+// root is then an arbitrary member of the component (callers that need the lowest vertex index fix it up afterwards).
+PV_DEV u64 uf_priority(u32 x) { return ((u64)(u32)splitmix64(x) << 32) | x; }
+PV_DEV void uf_union_hashed(u32 *uf, u32 a, u32 b) {
+	while (true) {
+		a = uf_find(uf, a); b = uf_find(uf, b);
+		if (a == b) return;
+		if (uf_priority(a) > uf_priority(b)) { u32 t = a; a = b; b = t; }     // a = lower priority: it goes under b
 		if (atomic_cas(uf + a, a, b) == a) return;
 	}
 }
@@ -204,11 +217,28 @@ inline void decompose_device(Ctx &c, u32 V, u64 E, const u32 *ep1, const u32 *ep
 			u32 v = act[i >> 1]; u32 p = 2 * v + (u32)(i & 1);
 			for (u32 s = adjOff_[p], e = adjOff_[p + 1]; s < e; s++) {
 				u32 w = adjNbr_[s] >> 1;
-				if (w < v && !visited_[w]) uf_union(uf_, v, w);   // an edge between two unvisited segments is seen from both ends: join once
+				if (w < v && !visited_[w]) uf_union_hashed(uf_, v, w);   // an edge between two unvisited segments is seen from both ends: join once
 			}
 		});
+		// a few rounds of plain pointer doubling first (every store is an ancestor, so they can run in place): the finds of the
+		// flatten then start from short chains instead of chasing them one dependent load at a time
+		for (int jmp = 0; jmp < 3; jmp++)
+			parallel_for<K_uf_flatten>(c, nA, PV_LAMBDA(size_t i) { u32 v = act[i]; u32 p = ld_volatile(uf_ + v); u32 gp = ld_volatile(uf_ + p); if (gp != p) uf_[v] = gp; });
 		parallel_for<K_uf_flatten>(c, nA, PV_LAMBDA(size_t i) { u32 v = act[i]; comp_[v] = uf_find(uf_, v); });
 		if (round == 0) {
+			// round 0's labels name the whole-graph components and must be the LOWEST vertex index of each (component order =
+			// ascending lowest vertex, bidirected.cpp:585-596): representative -> minimum.  Runs of 32 consecutive vertices mostly
+			// share a representative, so a thread issues one atomicMin per run.
+			Buf<u32> minIdx(c, V);
+			minIdx.fill_ff();
+			u32 *minIdx_ = minIdx.p;
+			parallel_for<K_uf_min>(c, ((size_t)V + 31) / 32, PV_LAMBDA(size_t t) {
+				u32 v0 = (u32)t * 32, v1 = v0 + 32 < V ? v0 + 32 : V;
+				u32 rep = comp_[v0], lo = v0;
+				for (u32 v = v0 + 1; v < v1; v++) { u32 r = comp_[v]; if (r != rep) { atomic_min(minIdx_ + rep, lo); rep = r; lo = v; } }
+				atomic_min(minIdx_ + rep, lo);
+			});
+			parallel_for<K_uf_min>(c, V, PV_LAMBDA(size_t v) { comp_[v] = minIdx_[comp_[v]]; });
 			c.d2d(gcomp.p, comp.p, (size_t)V * 4);
 			// start port: smallest tip (v_id, end) of the component (types.cpp:60-68), else (lowest vertex, left)
 			parallel_for<K_start>(c, V, PV_LAMBDA(size_t v) { compStart_[v] = NONE; rnk_[2 * v] = NONE; rnk_[2 * v + 1] = NONE; });
