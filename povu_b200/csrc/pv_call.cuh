@@ -166,14 +166,15 @@ inline void graph_build(Ctx &c, u32 V, u64 E, const u32 *ep1, const u32 *ep2, u3
 	g.vsOff = Buf<u32>(c, (size_t)V + 1); g.vsStep = Buf<u32>(c, S ? S : 1); g.vsHap = Buf<u32>(c, S ? S : 1);
 	const u32 *steps_ = g.steps.p, *stepOff_ = g.stepOff.p, *segLen_ = g.segLen.p;
 	{
-		// loci[k] = 1-based start coordinate of step k (liteseq ref_walk::loci)
-		Buf<u64> len(c, (size_t)S + 1), pre(c, (size_t)S + 1);
-		u64 *len_ = len.p, *pre_ = pre.p; u32 *loci_ = g.loci.p;
-		parallel_for<C_loci_len>(c, (size_t)S + 1, PV_LAMBDA(size_t s) { len_[s] = s < S ? (u64)segLen_[steps_[s] >> 1] : 0ull; });
-		exclusive_scan(c, len.p, pre.p, (size_t)S + 1, OpAddU64(), (u64)0);
+		// loci[k] = 1-based start coordinate of step k (liteseq ref_walk::loci).  One u32 scan over all
+		// walks: the coordinate is a difference of two prefixes, so 32-bit wrap-around cancels (loci itself is 32 bits wide).
+		Buf<u32> len(c, (size_t)S + 1), pre(c, (size_t)S + 1);
+		u32 *len_ = len.p, *pre_ = pre.p; u32 *loci_ = g.loci.p;
+		parallel_for<C_loci_len>(c, (size_t)S + 1, PV_LAMBDA(size_t s) { len_[s] = s < S ? segLen_[steps_[s] >> 1] : 0u; });
+		exclusive_scan(c, len.p, pre.p, (size_t)S + 1, OpAddU32(), 0u);
 		parallel_for<C_loci>(c, S, PV_LAMBDA(size_t s) {
 			u32 h = ub_u32(stepOff_, 0, H + 1, (u32)s) - 1;
-			loci_[s] = (u32)(1ull + pre_[s] - pre_[stepOff_[h]]);
+			loci_[s] = 1u + pre_[s] - pre_[stepOff_[h]];
 		});
 	}
 	{

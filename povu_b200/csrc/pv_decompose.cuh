@@ -363,8 +363,8 @@ inline void decompose_device(Ctx &c, u32 V, u64 E, const u32 *ep1, const u32 *ep
 	u32 *isRoot_ = isRoot.p, *compIdxOfRoot_ = compIdxOfRoot.p, *nvOfRoot_ = nvOfRoot.p;
 	parallel_for<K_compcount>(c, V, PV_LAMBDA(size_t v) { isRoot_[v] = gcomp_[v] == v ? 1u : 0u; atomic_inc_aggregated(nvOfRoot_, gcomp_[v]); });
 	Buf<u32> roots;
-	u32 nComp = compact_flags(c, isRoot.p, V, roots);
-	exclusive_scan(c, isRoot.p, compIdxOfRoot.p, V, OpAddU32(), 0u);
+	u32 nComp = compact_flags(c, isRoot.p, V, roots, &compIdxOfRoot);   // (the compaction's own scan is the dense component index)
+	compIdxOfRoot_ = compIdxOfRoot.p;
 	// per component: nv, node base (2*nv+1 nodes incl. virtual root), segment base
 	Buf<u32> cNv(c, nComp + 1), cNodeBase(c, nComp + 1), cSegBase(c, nComp + 1), cNodes(c, nComp + 1), cHasTips(c, nComp);
 	u32 *cNv_ = cNv.p, *cNodeBase_ = cNodeBase.p, *cSegBase_ = cSegBase.p, *cNodes_ = cNodes.p, *cHasTips_ = cHasTips.p;
@@ -375,8 +375,15 @@ inline void decompose_device(Ctx &c, u32 V, u64 E, const u32 *ep1, const u32 *ep
 		cNv_[k] = nv; cNodes_[k] = k < nComp ? 2 * nv + 1 : 0u;
 	});
 	parallel_for<K_compcount>(c, V, PV_LAMBDA(size_t v) { if (tipPort_[v] != NONE) cHasTips_[compIdxOfRoot_[gcomp_[v]]] = 1; });
-	exclusive_scan(c, cNodes.p, cNodeBase.p, (size_t)nComp + 1, OpAddU32(), 0u);
-	exclusive_scan(c, cNv.p, cSegBase.p, (size_t)nComp + 1, OpAddU32(), 0u);
+	if (nComp <= 2048) {   // a handful of components: one thread adds them up instead of two scan launches
+		parallel_for<K_compcount>(c, 1, PV_LAMBDA(size_t) {
+			u32 a = 0, b = 0;
+			for (u32 k = 0; k <= nComp; k++) { u32 x = cNodes_[k], y = cNv_[k]; cNodeBase_[k] = a; cSegBase_[k] = b; a += x; b += y; }
+		});
+	} else {
+		exclusive_scan(c, cNodes.p, cNodeBase.p, (size_t)nComp + 1, OpAddU32(), 0u);
+		exclusive_scan(c, cNv.p, cSegBase.p, (size_t)nComp + 1, OpAddU32(), 0u);
+	}
 	const u32 N = P + nComp;   // nodes in global preorder space
 
 	tr.mark("components");

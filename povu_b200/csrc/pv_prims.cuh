@@ -604,8 +604,9 @@ inline void list_rank_suffix(Ctx &c, const u32 *next, const u32 *weight, u32 *ra
 // stream compaction of indices i in [0,n) with flag[i] != 0 -> out (ascending); returns the count
 // ---------------------------------------------------------------------------------------------
 PV_KERNEL(K_compact_scatter, 12);
-inline u32 compact_flags(Ctx &c, const u32 *flags, size_t n, Buf<u32> &out) {
-	if (n == 0) { out = Buf<u32>(c, 1); return 0; }
+// keep_pos (optional) receives the exclusive scan of the flags (n + 1 entries): rank of every index among the kept ones
+inline u32 compact_flags(Ctx &c, const u32 *flags, size_t n, Buf<u32> &out, Buf<u32> *keep_pos = nullptr) {
+	if (n == 0) { out = Buf<u32>(c, 1); if (keep_pos) { *keep_pos = Buf<u32>(c, 1); keep_pos->zero(); } return 0; }
 	Buf<u32> pos(c, n + 1);
 	exclusive_scan(c, flags, pos.p, n, OpAddU32(), 0u);
 	out = Buf<u32>(c, n);     // capacity n: the count is known only after the scatter (one host read instead of two)
@@ -615,7 +616,9 @@ inline u32 compact_flags(Ctx &c, const u32 *flags, size_t n, Buf<u32> &out) {
 		if (f) o[p[i]] = (u32)i;
 		if (i == n - 1) p[n] = p[i] + (f ? 1u : 0u);
 	});
-	return pos.read(n);
+	const u32 cnt = pos.read(n);
+	if (keep_pos) *keep_pos = std::move(pos);
+	return cnt;
 }
 
 // ---------------------------------------------------------------------------------------------
