@@ -51,8 +51,9 @@ struct Session {
 	}
 
 	// GFA -> graph.  Default: the text is parsed on the device (pv_gfa.cuh); the big arrays (links, walks, sequences)
-	// then exist only in HBM and come to the host on demand (ensure_host).  POVU_B200_HOST_GFA=1 selects the host
-	// loader of pv_host.hpp instead (same results; kept for A/B timing and as the checker in the tests).
+	// then exist only in HBM and come to the host on demand (ensure_host).  The sequential host loader of pv_host.hpp is
+	// reachable only through the test hook pvgpu_session_open_hostparse (same results; the checker of the parser's tests
+	// and the "host_loader_ms" figure of the bench).
 	bool host_edges = true, host_steps = true, host_lbl = true, tt_graph_dev = false;
 	double t_gfa_read_ms = 0, t_gfa_parse_ms = 0; u64 gfa_text_bytes = 0;
 	void load_gfa(const std::string &fp, bool labels, bool refs, bool force_host_parser = false) {
@@ -60,8 +61,7 @@ struct Session {
 		d_ep1.release(); d_ep2.release(); d_steps.release(); d_segLen.release(); dg = pv::DevGraph();
 		edges_up = raw_paths_up = paths_up = false; forest_ready = false; gm_ready = false; sharded = false;
 		tt = pv::TextTables(); tt_graph_dev = false; pvst_cache_ok = false;
-		static const bool env_host_parser = getenv("POVU_B200_HOST_GFA") != nullptr;
-		if (env_host_parser || force_host_parser) { double t0 = now_ms(); g = pvh::load_gfa(fp, labels, refs); t_gfa_read_ms = 0; t_gfa_parse_ms = now_ms() - t0; host_edges = host_steps = host_lbl = true; pin(); return; }
+		if (force_host_parser) {   // test hook only (pvgpu_session_open_hostparse): the checker of the device parser double t0 = now_ms(); g = pvh::load_gfa(fp, labels, refs); t_gfa_read_ms = 0; t_gfa_parse_ms = now_ms() - t0; host_edges = host_steps = host_lbl = true; pin(); return; }
 		load_gfa_device(fp, labels, refs);
 	}
 	void load_gfa_device(const std::string &fp, bool labels, bool refs) {
