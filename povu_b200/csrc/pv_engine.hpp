@@ -61,7 +61,8 @@ struct Session {
 		d_ep1.release(); d_ep2.release(); d_steps.release(); d_segLen.release(); dg = pv::DevGraph();
 		edges_up = raw_paths_up = paths_up = false; forest_ready = false; gm_ready = false; sharded = false;
 		tt = pv::TextTables(); tt_graph_dev = false; pvst_cache_ok = false;
-		if (force_host_parser) {   // test hook only (pvgpu_session_open_hostparse): the checker of the device parser double t0 = now_ms(); g = pvh::load_gfa(fp, labels, refs); t_gfa_read_ms = 0; t_gfa_parse_ms = now_ms() - t0; host_edges = host_steps = host_lbl = true; pin(); return; }
+		// force_host_parser: test hook only (pvgpu_session_open_hostparse), the checker of the device parser
+		if (force_host_parser) { double t0 = now_ms(); g = pvh::load_gfa(fp, labels, refs); t_gfa_read_ms = 0; t_gfa_parse_ms = now_ms() - t0; host_edges = host_steps = host_lbl = true; pin(); return; }
 		load_gfa_device(fp, labels, refs);
 	}
 	void load_gfa_device(const std::string &fp, bool labels, bool refs) {
