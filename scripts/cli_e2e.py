@@ -15,23 +15,32 @@ from povu_b200 import synth  # noqa: E402
 n = int(sys.argv[1]) if len(sys.argv) > 1 and sys.argv[1].isdigit() else 400_000
 CLI = os.path.join(ROOT, "povu_b200", "bin", "povu")
 REF = os.path.join(ROOT, "oracle", "_ref", "povu_ref")
-fp = "/tmp/cli_e2e.gfa"
-g = synth.snp_indel_chain(n, n_paths=16, seed=42, with_seqs=True)
-synth.write_gfa_fast(g, fp)
+PREFIX = "S001#1"
+if "--lpa" in sys.argv:      # the reference's own real-data fixture (tests/data/LPA.gfa: 57 % of its regions are tangled)
+    import gzip
+    fp = "/tmp/cli_e2e_LPA.gfa"
+    with gzip.open(os.path.join(ROOT, "tests", "golden", "fixtures", "LPA.gfa.gz"), "rb") as i, open(fp, "wb") as o:
+        o.write(i.read())
+    PREFIX = "chm13"
+    out = {"workload": "tests/data/LPA.gfa (real data, tangled regions), -P chm13", "gfa_bytes": os.path.getsize(fp), "host_cores": os.cpu_count()}
+else:
+    fp = "/tmp/cli_e2e.gfa"
+    g = synth.snp_indel_chain(n, n_paths=16, seed=42, with_seqs=True)
+    synth.write_gfa_fast(g, fp)
+    out = {"workload": f"snp_indel_chain({n} bubbles), 16 haplotype paths", "gfa_bytes": os.path.getsize(fp), "host_cores": os.cpu_count()}
 open(fp, "rb").read()
-out = {"workload": f"snp_indel_chain({n} bubbles), 16 haplotype paths", "gfa_bytes": os.path.getsize(fp), "host_cores": os.cpu_count()}
 runs = []
 for i in range(4):
     t0 = time.perf_counter()
     with open("/tmp/cli_e2e_ours.vcf", "wb") as f:
-        r = subprocess.run([CLI, "gfa2vcf", "-i", fp, "-P", "S001#1"], stdout=f, stderr=subprocess.PIPE, env=dict(os.environ, POVU_B200_TIMING="1"))
+        r = subprocess.run([CLI, "gfa2vcf", "-i", fp, "-P", PREFIX], stdout=f, stderr=subprocess.PIPE, env=dict(os.environ, POVU_B200_TIMING="1"))
     runs.append({"wall_s": time.perf_counter() - t0, "phases": r.stderr.decode().strip().splitlines()[-2:] if r.stderr else ""})
     assert r.returncode == 0, r.stderr.decode()
 out["povu_b200"] = {"wall_s": min(x["wall_s"] for x in runs), "runs": runs, "vcf_bytes": os.path.getsize("/tmp/cli_e2e_ours.vcf")}
 if "--no-ref" not in sys.argv and os.path.exists(REF):
     t0 = time.perf_counter()
     with open("/tmp/cli_e2e_ref.vcf", "wb") as f:
-        r = subprocess.run([REF, "gfa2vcf", "-i", fp, "-P", "S001#1", "-t", "1"], stdout=f, stderr=subprocess.PIPE)
+        r = subprocess.run([REF, "gfa2vcf", "-i", fp, "-P", PREFIX, "-t", "1"], stdout=f, stderr=subprocess.PIPE)
     out["reference"] = {"wall_s": time.perf_counter() - t0, "rc": r.returncode}
     strip = lambda p: [l for l in open(p, "rb").read().split(b"\n") if not l.startswith(b"##fileDate")]
     a, b = strip("/tmp/cli_e2e_ours.vcf"), strip("/tmp/cli_e2e_ref.vcf")
