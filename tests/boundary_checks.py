@@ -192,6 +192,18 @@ def check_ffi_compute(L, tmp):
     name = "nested_s1"
     g = L.povu_graph_from_gfa(helpers.fixture_path(name).encode(), None)
     assert g
+    # a graph loaded from GFA keeps its links / walks / sequences in HBM (device parser): the getters bring them to the host
+    src = helpers.read_gfa(helpers.fixture_path(name))
+    n = C.c_size_t()
+    v = L.povu_graph_get_vertices(g, C.byref(n))
+    assert n.value == len(src["ids"]) and all(v[i].id == int(src["ids"][i]) and v[i].sequence == src["seqs"][i].encode() for i in range(n.value))
+    L.povu_vertices_free(v, n)
+    e = L.povu_graph_get_edges(g, C.byref(n))
+    assert n.value == len(src["v1"])
+    for i in range(n.value):       # PovuOrientation names the vertex END for both endpoints (povu_ffi.cpp:148-156): 0 = left, 1 = right
+        assert (e[i].from_id, e[i].from_orientation, e[i].to_id, e[i].to_orientation) == (int(src["ids"][src["v1"][i]]), int(src["s1"][i]), int(src["ids"][src["v2"][i]]), int(src["s2"][i])), i
+    L.povu_edges_free(e, n)
+    assert L.povu_graph_path_count(g) == len(src["paths"])
     f, text = _vcf_via_ffi(L, g, ["S001"])
     assert nodate(text) == golden(name)
     nfl = L.povu_flubbles_count(f)
