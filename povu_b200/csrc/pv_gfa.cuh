@@ -163,6 +163,13 @@ inline void gfa_text_to_device(Ctx &c, int fd, u64 n, Buf<u8> &T) {
 	const size_t BLK = PinnedPool::BLK;
 	const u64 nBlk = (n + BLK - 1) / BLK;
 	if (nBlk == 0) return;
+	if (n <= (8u << 20)) {   // small file: page-locking staging blocks (~0.3 ms per MiB, cold) would cost more than the copy itself
+		std::vector<char> tmp((size_t)n);
+		for (u64 got = 0; got < n;) { ssize_t r = pread(fd, tmp.data() + got, (size_t)(n - got), (off_t)got); if (r <= 0) throw std::runtime_error("read error"); got += (u64)r; }
+		PV_CUDA_CHECK(cudaMemcpyAsync(T.p, tmp.data(), (size_t)n, cudaMemcpyHostToDevice, c.stream));
+		PV_CUDA_CHECK(cudaStreamSynchronize(c.stream));
+		return;
+	}
 	unsigned hw = std::thread::hardware_concurrency();
 	int NT = (int)(hw / 2 > 8 ? 8 : (hw / 2 < 1 ? 1 : hw / 2));
 	if (const char *e = getenv("POVU_B200_READ_THREADS")) { int v = atoi(e); if (v >= 1 && v <= 64) NT = v; }
