@@ -415,6 +415,10 @@ struct CallIn {           // PVST forest, flubbles of all components concatenate
 	const u32 *flBase = nullptr;   // per flubble: index of the first flubble of its component
 	u32 nRefs = 0; const u32 *refs = nullptr;   // ascending path ids to call against
 	const u8 *excluded = nullptr;  // optional: 1 = never selected (sub-flubble clan or below one, color.cpp:117-125)
+	// The arrays may be a SLICE of the forest: the flubbles of the one component that holds every selected reference path
+	// (no flubble of another component can be selected: both boundaries must lie on every reference path).  fl_offset =
+	// global index of the slice's first flubble; flBase values stay global, region -> flubble indices come out global.
+	u32 fl_offset = 0;
 	bool on_device = false;        // a_v .. flBase point into device memory (decompose's table handed over in HBM)
 	// -g/--restrict ref:start-end (rov.cpp:137-183): keep a selected flubble only if a step of the named path on one of its
 	// two boundary vertices starts inside [start, end).  restrict_ref == NONE: the path does not exist -> no regions.
@@ -1311,7 +1315,7 @@ inline void call_device(Ctx &c, const DevGraph &G, const CallIn &in, const CallO
 	out.reset();
 	out.rec_grpOff.push_back(0); out.rec_gtOff.push_back(0);
 	out.cpOff = G.cpOff; out.cpList = G.cpList;
-	const u32 nFl = in.nFl, nRefs = in.nRefs, H = G.H;
+	const u32 nFl = in.nFl, nRefs = in.nRefs, H = G.H; const u32 flOff = in.fl_offset;
 	if (nFl == 0 || nRefs == 0 || H == 0) return;
 	const GraphView g = view(G);
 	Trace tr(c, "call");
@@ -1330,9 +1334,11 @@ inline void call_device(Ctx &c, const DevGraph &G, const CallIn &in, const CallO
 		c.h2d(refs.p, in.refs, (size_t)nRefs * 4);
 		if (in.excluded) c.h2d(ex.p, in.excluded, nFl);
 		u32 *fa_w = fa.p, *fz_w = fz.p; const u8 *af_ = af.p, *zf_ = zf.p, *ex_ = in.excluded ? ex.p : nullptr;
+		u32 *fbase_w = fbase.p; const u32 flOff0 = in.fl_offset;
 		parallel_for<C_pack>(c, nFl, PV_LAMBDA(size_t f) {   // (vertex << 1) | reverse; NONE hides an excluded flubble
 			fa_w[f] = (ex_ && ex_[f]) ? NONE : ((fa_w[f] << 1) | (af_[f] ? 0u : 1u));
 			fz_w[f] = (fz_w[f] << 1) | (zf_[f] ? 0u : 1u);
+			fbase_w[f] -= flOff0;   // slice-relative from here on
 		});
 	}
 	const u32 *fa_ = fa.p, *fz_ = fz.p, *fpar_ = fpar.p, *fbase_ = fbase.p, *refs_ = refs.p;
@@ -1501,7 +1507,7 @@ inline void call_device(Ctx &c, const DevGraph &G, const CallIn &in, const CallO
 	parallel_for<C_sizes>(c, (size_t)R + 1, PV_LAMBDA(size_t r) {
 		if (r >= R) { rovJ_[r] = 0; rowsOf_[r] = 0; cellsOf_[r] = 0; return; }
 		u32 s = rovSrc_[r]; u32 n = J0_[s]; u32 f = rov0_[s];
-		rovJ_[r] = n; rovFl_[r] = f;
+		rovJ_[r] = n; rovFl_[r] = f + flOff;   // global flubble index
 		// component of the region = component of any path through its start boundary (a selected region is
 		// touched by every reference path)
 		u32 a = fa_[f] >> 1;

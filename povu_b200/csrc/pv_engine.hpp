@@ -25,7 +25,7 @@ struct Session {
 	pvh::GtMeta gm; bool gm_ready = false;
 	pv::Buf<u32> d_ep1, d_ep2;
 	pv::DevGraph dg; bool edges_up = false, paths_up = false;
-	pvh::Forest forest; bool forest_ready = false; int forest_subfl = -1;   // forest_subfl: does the forest hold sub-flubble families (-1 = not looked yet)
+	pvh::Forest forest; bool forest_ready = false; int forest_subfl = -1; std::vector<u32> tree_label;   // tree_label: component label per tree (call slices the forest by it)   // forest_subfl: does the forest hold sub-flubble families (-1 = not looked yet)
 	pv::DecompOut dec;
 	mutable pvh::Records rec;    // binary records + counters of the last call: born in HBM, copied to the host on demand (rec.to_host)
 	std::vector<std::string> prefixes;
@@ -281,7 +281,7 @@ struct Session {
 			if (dec.comp_nv[k] >= 3) { forest.comp_id.push_back(sharded ? comp_global.at(k) : k + 1); forest.treeOff.push_back(base); }
 			else if (dec.comp_nfl[k]) throw std::runtime_error("decompose: flubbles in a component with fewer than 3 vertices");
 		}
-		forest_ready = true; pvst_cache_ok = false; forest_subfl = 0;
+		forest_ready = true; pvst_cache_ok = false; forest_subfl = 0; tree_label.clear();
 		tr.mark("forest conversion");
 	}
 
@@ -325,7 +325,7 @@ struct Session {
 		std::sort(files.begin(), files.end());
 		forest = pvh::Forest();
 		for (auto &f : files) pvh::read_pvst(dir + "/" + f.second, g, (u32)f.first, forest);
-		forest_ready = true; pvst_cache_ok = false; dforest = pv::DevForest(); forest_subfl = -1;
+		forest_ready = true; pvst_cache_ok = false; dforest = pv::DevForest(); forest_subfl = -1; tree_label.clear();
 	}
 
 	void set_prefixes(const std::vector<std::string> &p) {
@@ -377,14 +377,38 @@ struct Session {
 			}
 		}
 		pv::CallIn in;
-		if (any_excl) in.excluded = excl.data();
 		in.nFl = forest.n(); in.nRefs = (u32)refs.size(); in.refs = refs.data();
-		if (dforest.valid && dforest.n == in.nFl) {
-			in.on_device = true; in.a_v = dforest.a_v.p; in.z_v = dforest.z_v.p; in.a_fwd = dforest.a_fwd.p; in.z_fwd = dforest.z_fwd.p;
-			in.parent = dforest.parent.p; in.flBase = dforest.fl_base.p;
+		// A flubble is selectable only if every reference path visits both of its boundaries (color.cpp:15-30), so when all
+		// reference paths lie in ONE component only that component's flubbles can be called: hand call_device that slice of
+		// the forest (the usual whole-genome case: one run per chromosome reference over a graph of 25 components).
+		u32 slice_b = 0, slice_n = forest.n();
+		if (!refs.empty() && forest.comp_id.size() > 1 && dg.pathComp.size() == g.H()) {
+			u32 pc = dg.pathComp[refs[0]]; bool one = pc != pvh::NONE32;
+			for (u32 r : refs) if (dg.pathComp[r] != pc) one = false;
+			if (one) {
+				// the component's flubbles = the tree whose first flubble lies in the component of the reference path's first vertex
+				if (tree_label.size() != forest.comp_id.size()) {   // once per forest: component label (lowest vertex index) of every tree
+					tree_label.assign(forest.comp_id.size(), pvh::NONE32);
+					const bool dev = dforest.valid && dforest.n == forest.n();
+					for (u32 t = 0; t < forest.comp_id.size(); t++) {
+						const u32 b = forest.treeOff[t], e = forest.treeOff[t + 1];
+						if (e > b) tree_label[t] = dg.vcomp.read(dev ? dforest.a_v.read(b) : forest.a_v[b]);
+					}
+				}
+				const u32 label = dg.vcomp.read(d_steps.read(g.stepOff[refs[0]]) >> 1);   // lowest vertex index of the references' component
+				slice_n = 0;                                                              // no tree: the component owns no flubbles
+				for (u32 t = 0; t < forest.comp_id.size(); t++)
+					if (tree_label[t] == label) { slice_b = forest.treeOff[t]; slice_n = forest.treeOff[t + 1] - slice_b; break; }
+			}
+		}
+		in.nFl = slice_n; in.fl_offset = slice_b;
+		if (any_excl) in.excluded = excl.data() + slice_b;
+		if (dforest.valid && dforest.n == forest.n()) {
+			in.on_device = true; in.a_v = dforest.a_v.p + slice_b; in.z_v = dforest.z_v.p + slice_b; in.a_fwd = dforest.a_fwd.p + slice_b; in.z_fwd = dforest.z_fwd.p + slice_b;
+			in.parent = dforest.parent.p + slice_b; in.flBase = dforest.fl_base.p + slice_b;
 		} else {
-			in.a_v = forest.a_v.data(); in.z_v = forest.z_v.data(); in.a_fwd = forest.a_fwd.data(); in.z_fwd = forest.z_fwd.data();
-			in.parent = forest.parent.data(); in.flBase = forest.flBase.data();
+			in.a_v = forest.a_v.data() + slice_b; in.z_v = forest.z_v.data() + slice_b; in.a_fwd = forest.a_fwd.data() + slice_b; in.z_fwd = forest.z_fwd.data() + slice_b;
+			in.parent = forest.parent.data() + slice_b; in.flBase = forest.flBase.data() + slice_b;
 		}
 		if (restrict_on) {
 			in.restrict_on = true; in.restrict_start = restrict_start; in.restrict_end = restrict_end; in.restrict_ref = pvh::NONE32;
