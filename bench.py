@@ -139,7 +139,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -148,7 +148,13 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
+
+    def mark_begin(self):
+        self.t0 = time.perf_counter()
+
+    def mark_end(self):
+        self.t1 = time.perf_counter()
 
     def stop(self):
         if not self.proc:
@@ -160,7 +166,13 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        # the sampler runs from before the warm-up (nvidia-smi needs ~50 ms to deliver its first row); keep the rows that arrived
+        # inside the timed region, widened by one sampling period on both sides
+        t0, t1 = getattr(self, "t0", None), getattr(self, "t1", None)
+        rows = [r for t, r in self.rows if t0 is None or t1 is None or (t0 - 0.06 <= t <= t1 + 0.06)]
+        if not rows:
+            rows = [r for _, r in self.rows]
+        for r in rows:
             if len(r) < 7:
                 continue
             try:
@@ -215,15 +227,15 @@ def run_native(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
     with torch.cuda.stream(stream):
         for _ in range(args.warmup):
             sess.hot_path(prefixes, keep_resident=True)
         barrier()
-        clocks = ClockSampler(local)
-        if rank == 0:
-            clocks.start()
+        clocks.mark_begin()
         launches0 = pv.launches
-        syncs0 = pv.host_syncs
         syncs0 = pv.host_syncs
         evs, parts = [], []
         wall0 = time.perf_counter()
@@ -235,6 +247,7 @@ def run_native(args):
             e1.record(stream)
             evs.append((e0, e1))
         barrier()
+        clocks.mark_end()
         wall = time.perf_counter() - wall0
         launches = pv.launches - launches0
         host_syncs = pv.host_syncs - syncs0
