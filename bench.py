@@ -43,7 +43,8 @@ def parse_args():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--bubbles", type=int, default=CFG2_BUBBLES, help="bubbles in the cfg2-shaped chain (default = cfg2)")
     ap.add_argument("--paths", type=int, default=N_PATHS)
-    ap.add_argument("--cpu-bubbles", type=int, default=100_000, help="size of the bounded CPU sample (same shape)")
+    ap.add_argument("--cpu-bubbles", type=int, default=0, help="bubbles of the CPU arm's graph (default 0 = the same graph as the GPU arm: same config)")
+    ap.add_argument("--ref-budget-s", type=float, default=1500.0, help="reference arm: stop adding timed passes when the run would exceed this wall time (the line then says how many were timed)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gfa-leg", action="store_true", help="skip the GFA text -> HBM leg (device parser) reported under gfa_text")
     ap.add_argument("--profile-steps", type=int, default=2)
@@ -57,43 +58,54 @@ def workload_name(n, paths):
 # ----------------------------------------------------------------------------------------------
 # CPU reference leg
 # ----------------------------------------------------------------------------------------------
+_GFA_CACHE = {}
+
+
+def cpu_gfa(n_bubbles, n_paths, seed=42):
+    """The workload as GFA text for the CPU arm (written once per process: the generator and the 141 MB text are not the thing timed)."""
+    key = (n_bubbles, n_paths, seed)
+    if key not in _GFA_CACHE:
+        from povu_b200 import synth
+        g = synth.snp_indel_chain(n_bubbles, n_paths=n_paths, seed=seed, with_seqs=True)
+        d = tempfile.mkdtemp(prefix="povu_bench_")
+        gfa = os.path.join(d, "g.gfa")
+        synth.write_gfa_fast(g, gfa)
+        _GFA_CACHE[key] = (d, gfa, len(g["v1"]))
+        import atexit
+        atexit.register(lambda d=d: subprocess.run(["rm", "-rf", d]))
+    return _GFA_CACHE[key]
+
+
 def cpu_reference_run(n_bubbles, n_paths, seed=42):
     """Reference decompose + call on a cfg2-shaped GFA; compute time = the six decompose stage timers +
     (do_call wall - a stand-alone GFA load with the same configuration)."""
-    from povu_b200 import synth
-    g = synth.snp_indel_chain(n_bubbles, n_paths=n_paths, seed=seed, with_seqs=True)
-    E = len(g["v1"])
-    d = tempfile.mkdtemp(prefix="povu_bench_")
-    gfa = os.path.join(d, "g.gfa")
-    synth.write_gfa_fast(g, gfa)
+    d, gfa, E = cpu_gfa(n_bubbles, n_paths, seed)
     ref = os.path.join(ROOT, "oracle", "_ref", "povu_ref")
     port = os.path.join(ROOT, "oracle", "povu_oracle")
     env = dict(os.environ, POVU_STAGE_COST_TRACE="1")
-    try:
-        if os.path.exists(ref):
-            t0 = time.perf_counter()
-            with open(os.path.join(d, "out.vcf"), "w") as so:
-                r = subprocess.run([ref, "timed-gfa2vcf", "-i", gfa, "-P", REF_PREFIX, "-t", "1"], env=env, stdout=so, stderr=subprocess.PIPE, text=True)
-            wall = time.perf_counter() - t0
-            if r.returncode != 0:
-                raise RuntimeError("CPU reference failed: " + r.stderr[-300:])
-            stage = sum(int(x) for x in re.findall(r"povu-stage-cost contract=\S+ .*elapsed_ns=(\d+)", r.stderr)) / 1e9
-            m = re.search(r"povu-ref-timing decompose_total_s=(\S+) call_load_s=(\S+) call_total_s=(\S+)", r.stderr)
-            dec_total, call_load, call_total = (float(x) for x in m.groups())
-            records = sum(1 for l in open(os.path.join(d, "out.vcf")) if not l.startswith("#"))
-            t_dec = stage if stage > 0 else dec_total
-            t_call = max(call_total - call_load, 1e-9)
-            return {"edges": E, "records": records, "t_dec": t_dec, "t_call": t_call, "wall_s": wall, "kind": "reference", "cores": 2,
-                    "note": "decompose = sum of the reference's six stage timers (1 thread: it parallelises only across components); call = do_call wall minus a stand-alone GFA load (producer thread + VCF text consumer thread)"}
+    threads = str(min(os.cpu_count() or 1, 255))      # the reference parallelises decompose across components only (one here); call = producer + writer thread
+    if os.path.exists(ref):
         t0 = time.perf_counter()
-        r = subprocess.run([port, "gfa2vcf", "-i", gfa, "-P", REF_PREFIX], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+        with open(os.path.join(d, "out.vcf"), "w") as so:
+            r = subprocess.run([ref, "timed-gfa2vcf", "-i", gfa, "-P", REF_PREFIX, "-t", threads], env=env, stdout=so, stderr=subprocess.PIPE, text=True)
         wall = time.perf_counter() - t0
         if r.returncode != 0:
-            raise RuntimeError("oracle port failed: " + r.stderr[-300:])
-        records = sum(1 for l in r.stdout.splitlines() if not l.startswith("#"))
-        return {"edges": E, "records": records, "t_dec": wall / 2, "t_call": wall / 2, "wall_s": wall, "kind": "port", "cores": 1, "note": "oracle port, whole-process wall incl. GFA parse"}
-    finally:
-        subprocess.run(["rm", "-rf", d])
+            raise RuntimeError("CPU reference failed: " + r.stderr[-300:])
+        stage = sum(int(x) for x in re.findall(r"povu-stage-cost contract=\S+ .*elapsed_ns=(\d+)", r.stderr)) / 1e9
+        m = re.search(r"povu-ref-timing decompose_total_s=(\S+) call_load_s=(\S+) call_total_s=(\S+)", r.stderr)
+        dec_total, call_load, call_total = (float(x) for x in m.groups())
+        records = sum(1 for l in open(os.path.join(d, "out.vcf")) if not l.startswith("#"))
+        t_dec = stage if stage > 0 else dec_total
+        t_call = max(call_total - call_load, 1e-9)
+        return {"edges": E, "records": records, "t_dec": t_dec, "t_call": t_call, "wall_s": wall, "kind": "reference", "cores": 2,
+                "note": f"-t {threads}; decompose = sum of the reference's six stage timers (1 busy thread: it parallelises only across components, and this graph is one); call = do_call wall minus a stand-alone GFA load (producer thread + VCF text consumer thread = the 2 cores counted)"}
+    t0 = time.perf_counter()
+    r = subprocess.run([port, "gfa2vcf", "-i", gfa, "-P", REF_PREFIX], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    wall = time.perf_counter() - t0
+    if r.returncode != 0:
+        raise RuntimeError("oracle port failed: " + r.stderr[-300:])
+    records = sum(1 for l in r.stdout.splitlines() if not l.startswith("#"))
+    return {"edges": E, "records": records, "t_dec": wall / 2, "t_call": wall / 2, "wall_s": wall, "kind": "port", "cores": 1, "note": "oracle port, whole-process wall incl. GFA parse"}
 
 
 def cpu_fields(r, n, paths):
@@ -103,24 +115,41 @@ def cpu_fields(r, n, paths):
             "decompose_edges_per_sec": r["edges"] / r["t_dec"], "call_records_per_sec": r["records"] / r["t_call"], "host_cores_available": os.cpu_count()}
 
 
+def base_config(n, paths):
+    """config keys shared by both arms (the driver compares them): the workload both arms run"""
+    n_snp, n_ind = (n + 1) // 2, n // 2
+    return {"workload": workload_name(n, paths), "segments": (n + 1) + 2 * n_snp + n_ind, "links": 4 * n_snp + 3 * n_ind, "paths": paths, "components_per_gpu": 1, "ref_prefix": REF_PREFIX}
+
+
 def run_reference_arm(args):
+    """The reference's own CPU implementation on the SAME graph as the GPU arm (full cfg2 by default: ~17 s per pass).  One
+    untimed warm-up pass (page cache, binary load), then --steps timed passes; if the whole run would exceed --ref-budget-s
+    the remaining passes are dropped and the line says how many were timed (never fewer than 3)."""
     if int(os.environ.get("RANK", "0")) != 0:
         return
-    n = args.cpu_bubbles
+    n = args.cpu_bubbles or args.bubbles
+    t_start = time.perf_counter()
+    cpu_gfa(n, args.paths)
     vals, times, last = [], [], None
-    for i in range(args.warmup + args.steps):
-        if i < args.warmup and i > 0:
-            continue          # one untimed warm-up pass is enough for a CPU process (page cache, binary load)
+    if args.warmup > 0:
+        cpu_reference_run(n, args.paths)
+    per_pass = None
+    for i in range(args.steps):
+        t0 = time.perf_counter()
         last = cpu_reference_run(n, args.paths)
-        if i >= args.warmup:
-            t = last["t_dec"] + last["t_call"]
-            vals.append(last["edges"] / t); times.append(t)
-    v = sum(vals) / len(vals)
+        per_pass = time.perf_counter() - t0
+        t = last["t_dec"] + last["t_call"]
+        vals.append(last["edges"] / t); times.append(t)
+        if len(vals) >= 3 and (time.perf_counter() - t_start) + per_pass > args.ref_budget_s:
+            break
+    v = len(vals) * last["edges"] / sum(times)
     cpu = cpu_fields(last, n, args.paths)
     cpu["value"] = v
+    cfg = base_config(n, args.paths)
+    cfg.update({"records": last["records"], "timed_passes": len(vals), "same_graph_as_gpu_arm": n == args.bubbles})
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "edges/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-            "config": {"workload": workload_name(n, args.paths) + " [bounded CPU sample of cfg2]", "segments": int(2.5 * n) + 1, "links": last["edges"], "paths": args.paths, "components": 1, "ref_prefix": REF_PREFIX},
+            "config": cfg,
             "parts": {"decompose_edges_per_sec": cpu["decompose_edges_per_sec"], "call_records_per_sec": cpu["call_records_per_sec"], "records": last["records"]},
             "cpu_baseline": cpu, "e2e": {"value": v, "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
@@ -360,7 +389,9 @@ def run_native(args):
         cpu = None
         if not args.no_cpu_baseline and world == 1:
             try:
-                cpu = cpu_fields(cpu_reference_run(args.cpu_bubbles, args.paths), args.cpu_bubbles, args.paths)
+                nb = args.cpu_bubbles or args.bubbles
+                cpu = cpu_fields(cpu_reference_run(nb, args.paths), nb, args.paths)
+                cpu["same_config"] = nb == args.bubbles
             except Exception as ex:   # the baseline is reported, never required
                 cpu = {"value": None, "unit": "edges/s", "cores": 0, "kind": "unavailable", "sample": str(ex)[:200]}
         pm = [sum(p[i] for p in parts) / len(parts) for i in range(4)]
@@ -368,8 +399,7 @@ def run_native(args):
         line = {"metric": METRIC, "value": world * E / (ms_per_step * 1e-3), "unit": "edges/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-                "config": {"workload": workload_name(args.bubbles, args.paths), "segments": V, "links": E, "paths": args.paths, "path_steps": S, "components_per_gpu": 1,
-                           "flubbles": n_fl, "records": n_rec, "ref_prefix": REF_PREFIX,
+                "config": {**base_config(args.bubbles, args.paths), "path_steps": S, "flubbles": n_fl, "records": n_rec,
                            "l2": "256 MiB flush write between timed steps (untimed); per-step CUDA events summed",
                            "sharding": "one independent component per rank, no collective on the data path",
                            "outputs": "value: the flubble table reaches the host (copy overlapped), the binary records stay in HBM where the device VCF writer reads them; "

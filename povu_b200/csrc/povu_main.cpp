@@ -126,6 +126,7 @@ struct Dev {
 static void unsupported(const Config &c) {
 	if (c.subflubbles) throw Fail{"-s/--subflubbles is not provided by povu_b200 (sub-flubble passes are outside the accelerated hot path)"};
 	if (!c.structure_export.empty()) throw Fail{"--structure-export is not provided by povu_b200"};
+	if (c.hairpins) throw Fail{"-h/--hairpins is not provided by povu_b200 (the reference's stderr report of hairpin boundaries, flubbles.cpp:711-717)"};
 }
 
 static void do_decompose(const Config &c, Dev &d, const std::string &out_dir) {

@@ -89,6 +89,7 @@ struct DevGraph {
 	// host copies of the small per-path tables
 	std::vector<u32> h_stepOff;
 	std::vector<u32> pathComp;        // dense component index per path (NONE for empty paths)
+	std::vector<u32> pathLabel;       // component label (lowest vertex index of the component) per path (NONE for empty paths)
 	std::vector<u32> cpOff, cpList;   // paths of every component, ascending
 	std::vector<u32> hapLocal;        // index of the path inside its component's list
 	Buf<u32> d_pathComp, d_cpOff, d_cpList, d_hapLocal;
@@ -195,6 +196,7 @@ inline void graph_build(Ctx &c, u32 V, u64 E, const u32 *ep1, const u32 *ep2, u3
 		u32 *pr_ = pr.p;
 		parallel_for<C_uf>(c, H, PV_LAMBDA(size_t h) { pr_[h] = stepOff_[h + 1] > stepOff_[h] ? uf_[steps_[stepOff_[h]] >> 1] : NONE; });
 		std::vector<u32> roots = pr.to_host(); roots.resize(H);
+		g.pathLabel = roots;
 		std::vector<u32> uniq;
 		for (u32 r : roots) if (r != NONE) uniq.push_back(r);
 		std::sort(uniq.begin(), uniq.end()); uniq.erase(std::unique(uniq.begin(), uniq.end()), uniq.end());

@@ -59,8 +59,8 @@ struct Session {
 	void load_gfa(const std::string &fp, bool labels, bool refs, bool force_host_parser = false) {
 		unpin(); c->bg_sync();
 		d_ep1.release(); d_ep2.release(); d_steps.release(); d_segLen.release(); dg = pv::DevGraph();
-		edges_up = raw_paths_up = paths_up = false; forest_ready = false; gm_ready = false; sharded = false;
-		tt = pv::TextTables(); tt_graph_dev = false; pvst_cache_ok = false;
+		edges_up = raw_paths_up = paths_up = false; sharded = false;
+		invalidate_graph_state();
 		// force_host_parser: test hook only (pvgpu_session_open_hostparse), the checker of the device parser
 		if (force_host_parser) { double t0 = now_ms(); g = pvh::load_gfa(fp, labels, refs); t_gfa_read_ms = 0; t_gfa_parse_ms = now_ms() - t0; host_edges = host_steps = host_lbl = true; pin(); return; }
 		load_gfa_device(fp, labels, refs);
@@ -164,6 +164,13 @@ struct Session {
 		labels_ready = false; d_labels.release();
 		paths_up = true;
 	}
+	// the loaded graph changed (new file, shard, builder mutation): nothing derived from the previous graph may survive
+	void invalidate_graph_state() {
+		forest_ready = false; gm_ready = false; forest_subfl = -1; tree_label.clear();
+		tt = pv::TextTables(); tt_graph_dev = false; pvst_cache_ok = false;
+		dforest = pv::DevForest(); labels_ready = false; d_labels.release();
+		rec.reset();
+	}
 	// forget everything on the device (the next decompose / call re-uploads from the host arrays)
 	void drop_device() {
 		ensure_host(true, true, false);
@@ -249,8 +256,7 @@ struct Session {
 		g = std::move(n);
 		host_edges = host_steps = host_lbl = true;
 		pin();
-		forest_ready = false; sharded = true; tt = pv::TextTables(); tt_graph_dev = false; gm_ready = false; pvst_cache_ok = false;
-		dforest = pv::DevForest(); labels_ready = false; d_labels.release();
+		invalidate_graph_state(); sharded = true;
 	}
 
 	// decompose: flubbles + PVST of every component with >= 3 vertices (decompose.cpp:129-142)
@@ -387,15 +393,18 @@ struct Session {
 			for (u32 r : refs) if (dg.pathComp[r] != pc) one = false;
 			if (one) {
 				// the component's flubbles = the tree whose first flubble lies in the component of the reference path's first vertex
-				if (tree_label.size() != forest.comp_id.size()) {   // once per forest: component label (lowest vertex index) of every tree
-					tree_label.assign(forest.comp_id.size(), pvh::NONE32);
+				if (tree_label.size() != forest.comp_id.size()) {   // once per forest: component label (lowest vertex index) of every tree,
+					const u32 T = (u32)forest.comp_id.size();       // gathered by one kernel and one copy (a whole-genome graph has thousands of trees)
 					const bool dev = dforest.valid && dforest.n == forest.n();
-					for (u32 t = 0; t < forest.comp_id.size(); t++) {
-						const u32 b = forest.treeOff[t], e = forest.treeOff[t + 1];
-						if (e > b) tree_label[t] = dg.vcomp.read(dev ? dforest.a_v.read(b) : forest.a_v[b]);
-					}
+					std::vector<u32> first(T, pvh::NONE32);
+					for (u32 t = 0; t < T; t++) { const u32 b = forest.treeOff[t], e = forest.treeOff[t + 1]; if (e > b) first[t] = dev ? b : forest.a_v[b]; }
+					pv::Buf<u32> dFirst(*c, T), dLab(*c, T);
+					c->h2d(dFirst.p, first.data(), (size_t)T * 4);
+					const u32 *first_ = dFirst.p, *av_ = dev ? dforest.a_v.p : nullptr, *vcomp_ = dg.vcomp.p; u32 *lab_ = dLab.p;
+					pv::parallel_for<pv::C_keep>(*c, T, PV_LAMBDA(size_t t) { u32 x = first_[t]; lab_[t] = x == pv::NONE ? pv::NONE : vcomp_[av_ ? av_[x] : x]; });
+					tree_label = dLab.to_host();
 				}
-				const u32 label = dg.vcomp.read(d_steps.read(g.stepOff[refs[0]]) >> 1);   // lowest vertex index of the references' component
+				const u32 label = dg.pathLabel[refs[0]];   // lowest vertex index of the references' component (graph_build)
 				slice_n = 0;                                                              // no tree: the component owns no flubbles
 				for (u32 t = 0; t < forest.comp_id.size(); t++)
 					if (tree_label[t] == label) { slice_b = forest.treeOff[t]; slice_n = forest.treeOff[t + 1] - slice_b; break; }

@@ -10,6 +10,7 @@ struct PovuGraph {
 	pve::Session *s = nullptr;
 	// builder state (povu_graph_new / add_*): vertex idx = insertion order, like bd::VG::add_vertex
 	std::vector<uint64_t> b_ids; std::vector<std::string> b_seqs;
+	std::unordered_map<uint64_t, size_t> b_index;  // id -> builder vertex idx (add_edge resolves ids in O(1); duplicates are rejected)
 	std::vector<uint32_t> b_ep1, b_ep2;            // by builder vertex idx
 	struct BPath { std::string name; std::vector<PovuStep> steps; };
 	std::vector<BPath> b_paths;
@@ -27,18 +28,29 @@ struct PovuGraph {
 #endif
 		ctx.init(dev, nullptr); ctx_ready = true;
 	}
-	// materialise the builder arrays as a HostGraph (the device encoding wants vertex idx order == id order,
-	// which is also what mto::from_gfa::to_bd produces)
+	// materialise the builder arrays as a HostGraph.  The device encoding wants vertex idx order == ascending id order
+	// (what mto::from_gfa::to_bd produces), so vertices added in any order are sorted by id here and the builder's
+	// edge ports are remapped; the getters keep answering in insertion order.
 	void sync() {
 		if (from_gfa || synced) return;
-		for (size_t i = 1; i < b_ids.size(); i++) if (b_ids[i - 1] >= b_ids[i]) throw std::runtime_error("povu_b200: vertices must be added in strictly ascending id order");
+		const uint32_t V = (uint32_t)b_ids.size();
+		std::vector<uint32_t> ord(V), rank(V);
+		for (uint32_t i = 0; i < V; i++) ord[i] = i;
+		bool sorted = true;
+		for (size_t i = 1; i < b_ids.size(); i++) if (b_ids[i - 1] >= b_ids[i]) { sorted = false; break; }
+		if (!sorted) std::sort(ord.begin(), ord.end(), [&](uint32_t a, uint32_t b) { return b_ids[a] < b_ids[b]; });
+		for (uint32_t i = 0; i < V; i++) rank[ord[i]] = i;
 		pvh::HostGraph &g = s->g;
 		g = pvh::HostGraph(); g.has_labels = true;
-		const uint32_t V = (uint32_t)b_ids.size();
 		g.ids.resize(V); g.segLen.resize(V); g.lblOff.assign((size_t)V + 1, 0);
-		for (uint32_t i = 0; i < V; i++) { if (b_ids[i] > 0xFFFFFFFFull) throw std::runtime_error("povu_b200: vertex id does not fit 32 bits"); g.ids[i] = (uint32_t)b_ids[i]; g.segLen[i] = (uint32_t)b_seqs[i].size(); g.lblOff[i + 1] = g.lblOff[i] + b_seqs[i].size(); g.lbl += b_seqs[i]; }
+		for (uint32_t i = 0; i < V; i++) {
+			const uint32_t b = ord[i];
+			if (b_ids[b] > 0xFFFFFFFFull) throw std::runtime_error("povu_b200: vertex id does not fit 32 bits");
+			g.ids[i] = (uint32_t)b_ids[b]; g.segLen[i] = (uint32_t)b_seqs[b].size(); g.lblOff[i + 1] = g.lblOff[i] + b_seqs[b].size(); g.lbl += b_seqs[b];
+		}
 		g.build_id_table();
-		g.ep1 = b_ep1; g.ep2 = b_ep2;
+		g.ep1.resize(b_ep1.size()); g.ep2.resize(b_ep2.size());
+		for (size_t e = 0; e < b_ep1.size(); e++) { g.ep1[e] = (rank[b_ep1[e] >> 1] << 1) | (b_ep1[e] & 1u); g.ep2[e] = (rank[b_ep2[e] >> 1] << 1) | (b_ep2[e] & 1u); }
 		g.stepOff.assign(1, 0);
 		for (auto &p : b_paths) {
 			pvh::HostPath hp = pvh::parse_path_name(p.name);
@@ -47,7 +59,9 @@ struct PovuGraph {
 			hp.hap_len = (uint32_t)len;
 			g.paths.push_back(std::move(hp)); g.stepOff.push_back((uint32_t)g.steps.size());
 		}
-		s->drop_device(); s->gm_ready = false; s->forest_ready = false;
+		// the graph changed: nothing derived from the previous one may survive (device arrays, text tables, forest, labels, records)
+		s->host_edges = s->host_steps = s->host_lbl = true;
+		s->drop_device(); s->invalidate_graph_state();
 		synced = true;
 	}
 };
@@ -97,13 +111,15 @@ void povu_graph_free(PovuGraph *graph) { delete graph; }
 
 size_t povu_graph_add_vertex(PovuGraph *graph, uint64_t id, const char *sequence) {
 	if (!graph || !sequence || graph->from_gfa) return (size_t)-1;
-	try { graph->b_ids.push_back(id); graph->b_seqs.emplace_back(sequence); graph->synced = false; return graph->b_ids.size() - 1; } catch (...) { return (size_t)-1; }
+	try {
+		if (!graph->b_index.emplace(id, graph->b_ids.size()).second) return (size_t)-1;   // duplicate id
+		graph->b_ids.push_back(id); graph->b_seqs.emplace_back(sequence); graph->synced = false; return graph->b_ids.size() - 1;
+	} catch (...) { return (size_t)-1; }
 }
 size_t povu_graph_add_edge(PovuGraph *graph, uint64_t from_id, PovuOrientation fo, uint64_t to_id, PovuOrientation to) {
 	if (!graph || graph->from_gfa) return (size_t)-1;
 	try {
-		// ids -> builder vertex idx (linear probe from the back: builders add edges right after their vertices)
-		auto find = [&](uint64_t id) -> size_t { for (size_t i = graph->b_ids.size(); i-- > 0;) if (graph->b_ids[i] == id) return i; return (size_t)-1; };
+		auto find = [&](uint64_t id) -> size_t { auto it = graph->b_index.find(id); return it == graph->b_index.end() ? (size_t)-1 : it->second; };
 		size_t a = find(from_id), b = find(to_id);
 		if (a == (size_t)-1 || b == (size_t)-1) return (size_t)-1;
 		graph->b_ep1.push_back((uint32_t)(2 * a + (fo == POVU_ORIENTATION_FORWARD ? 0u : 1u)));

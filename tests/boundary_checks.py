@@ -152,6 +152,7 @@ def check_ffi_builder(L):
     assert L.povu_graph_add_edge(g, 2, 1, 3, 0) == 2
     assert L.povu_graph_add_edge(g, 9, 0, 1, 0) == C.c_size_t(-1).value   # unknown vertex
     assert L.povu_graph_add_vertex(g, 7, None) == C.c_size_t(-1).value
+    assert L.povu_graph_add_vertex(g, 2, b"C") == C.c_size_t(-1).value          # duplicate id
     L.povu_graph_finalize(g)
     assert (L.povu_graph_vertex_count(g), L.povu_graph_edge_count(g), L.povu_graph_path_count(g)) == (3, 3, 0)
     n = C.c_size_t()
@@ -233,7 +234,39 @@ def check_ffi_compute(L, tmp):
     assert L.povu_graph_path_count(b) == len(src["paths"])
     f, text = _vcf_via_ffi(L, b, ["HG1"])
     assert nodate(text) == golden("minimal_substitution")
-    L.povu_flubbles_free(f); L.povu_graph_free(b)
+    nfl1 = L.povu_flubbles_count(f)
+    L.povu_flubbles_free(f)
+    # mutating a graph after a call: a second component is added, every table derived from the old graph must be rebuilt
+    # (the text tables / forest / labels of the previous graph used to survive: out-of-bounds reads in the text kernels)
+    V0 = max(int(i) for i in src["ids"]) + 1
+    for i, sq in zip(src["ids"], src["seqs"]):
+        assert L.povu_graph_add_vertex(b, V0 + int(i), sq.encode()) != C.c_size_t(-1).value
+    for v1, s1, v2, s2 in zip(src["v1"], src["s1"], src["v2"], src["s2"]):
+        assert L.povu_graph_add_edge(b, V0 + int(src["ids"][v1]), int(s1), V0 + int(src["ids"][v2]), int(s2)) != C.c_size_t(-1).value
+    for nm, steps, strands in src["paths"]:
+        arr = (PovuStep * len(steps))(*[PovuStep(V0 + int(src["ids"][v]), int(o)) for v, o in zip(steps, strands)])
+        assert L.povu_graph_add_path(b, ("ZZ" + nm[2:]).replace("chr1", "chr2").encode(), arr, len(steps))
+    f2, text2 = _vcf_via_ffi(L, b, ["HG1"])
+    body = lambda t: [l.split("\t")[3:5] for l in t.splitlines() if not l.startswith("#")]
+    assert L.povu_graph_vertex_count(b) == 2 * len(src["ids"]) and L.povu_flubbles_count(f2) == 2 * nfl1
+    assert body(text2) == body(golden("minimal_substitution"))       # a flubble is called only where every reference path runs: component 1
+    L.povu_flubbles_free(f2)
+    f2, text2 = _vcf_via_ffi(L, b, ["ZZ1"])
+    assert body(text2) == body(golden("minimal_substitution"))       # the new component, against its own reference
+    L.povu_flubbles_free(f2); L.povu_graph_free(b)
+    # vertices added in any order (sorted by id at finalize): same VCF as the id-ordered build
+    b = L.povu_graph_new(0, 0, 0)
+    order = list(range(len(src["ids"])))[::-1]
+    for k in order:
+        assert L.povu_graph_add_vertex(b, int(src["ids"][k]), src["seqs"][k].encode()) != C.c_size_t(-1).value
+    for v1, s1, v2, s2 in zip(src["v1"], src["s1"], src["v2"], src["s2"]):
+        assert L.povu_graph_add_edge(b, int(src["ids"][v1]), int(s1), int(src["ids"][v2]), int(s2)) != C.c_size_t(-1).value
+    for nm, steps, strands in src["paths"]:
+        arr = (PovuStep * len(steps))(*[PovuStep(int(src["ids"][v]), int(o)) for v, o in zip(steps, strands)])
+        assert L.povu_graph_add_path(b, nm.encode(), arr, len(steps))
+    f3, text3 = _vcf_via_ffi(L, b, ["HG1"])
+    assert nodate(text3) == golden("minimal_substitution")
+    L.povu_flubbles_free(f3); L.povu_graph_free(b)
     # one-shot file API
     out = os.path.join(tmp, "o.vcf"); refs = os.path.join(tmp, "r.txt"); open(refs, "w").write("HG1\n")
     err = PovuError()

@@ -74,6 +74,12 @@ def check_vs_oracle(pv, g, prefixes, tmp, chunk=100, exact_order=True):
 REF = os.path.join(ROOT, "oracle", "_ref", "povu_ref")
 
 
+def require_ref():
+    """The compiled reference is the checker of the tangled / SNE / cyclic sub-paths: without it those tests FAIL (a skip
+    would silently drop that parity).  It is built by oracle/Makefile (`__graft_entry__.build()`) and travels to the GPU box."""
+    assert os.path.exists(REF), "oracle/_ref/povu_ref is missing: run `python -c 'import __graft_entry__ as g; g.build()'` where /root/reference exists"
+
+
 def reference_vcf(gfa, prefixes, chunk=100):
     """VCF of the compiled, unmodified reference (oracle/_ref: built by oracle/Makefile, travels to the GPU box)."""
     cmd = [REF, "gfa2vcf", "-i", gfa, "-t", "1", "-c", str(chunk)]
@@ -87,9 +93,7 @@ def reference_vcf(gfa, prefixes, chunk=100):
 def run_tangled_vs_reference(pv, tmp, n_seeds=24):
     """Tangled regions (untangle + lap alignment): VNTR-like repeat units that paths traverse 1..5 times.  The oracle
     restatement does not cover this sub-path, so the checker is the compiled reference itself."""
-    import pytest
-    if not os.path.exists(REF):
-        pytest.skip("oracle/_ref/povu_ref not built")
+    require_ref()
     tangled = records = 0
     gfa = os.path.join(tmp, "t.gfa")
     for seed in range(n_seeds):
@@ -109,9 +113,7 @@ def run_cyclic_vs_reference(pv, tmp, n_seeds=30):
     """Regions with a cycle inside: the BFS/Kahn sort fails and the vertex order comes from the haplotype laps
     (find_laps + gen_sort, graph.cpp:165-395).  Checker: the compiled reference; where it crashes (it reads
     v_ids[-1] / an empty optional on some inputs) the product must report hard errors instead of records."""
-    import pytest
-    if not os.path.exists(REF):
-        pytest.skip("oracle/_ref/povu_ref not built")
+    require_ref()
     gfa = os.path.join(tmp, "c.gfa")
     compared = crashed = records = 0
     for seed in range(n_seeds):
@@ -141,11 +143,9 @@ def run_inversions_vs_reference(pv, tmp, n_seeds=45):
     chains -> extensions -> slice tree -> SUBR records), also inside tangled regions and with two ref paths.  Checker:
     the compiled reference.  Seeds where a merged slice length runs past the end of a walk are skipped: the reference
     reads beyond its arrays there (undefined behaviour), the product clamps and counts (`subr_clamped`)."""
-    import pytest
-    if not os.path.exists(REF):
-        pytest.skip("oracle/_ref/povu_ref not built")
+    require_ref()
     gfa = os.path.join(tmp, "i.gfa")
-    subr = pins = compared = 0
+    subr = pins = compared = clamped_compared = 0
     for seed in range(n_seeds):
         kind = seed % 3
         if kind == 0:
@@ -165,12 +165,20 @@ def run_inversions_vs_reference(pv, tmp, n_seeds=45):
         assert st["hard_errors"] == 0
         pins += st["pin_pairs"]
         if st["subr_clamped"]:
+            # a merged slice ran past the end of a walk: the reference reads beyond its arrays there (undefined behaviour), so
+            # its SUBR lines cannot be compared -- every other record still must agree (unless the reference crashed outright)
+            cmd = [REF, "gfa2vcf", "-i", gfa, "-t", "1", "-c", str(chunk)] + [x for p_ in pref for x in ("-P", p_)]
+            r = subprocess.run(cmd, capture_output=True, text=True)
+            if r.returncode == 0:
+                nosubr = lambda t: [l for l in split(t, False)[1] if "VARTYPE=SUBR" not in l]
+                assert nosubr(got) == nosubr(r.stdout), f"seed {seed} (clamped)"
+                clamped_compared += 1
             continue
         want = reference_vcf(gfa, pref, chunk)
         assert split(got, False) == split(want, False), f"seed {seed}"
         compared += 1
         subr += sum("VARTYPE=SUBR" in l for l in got.splitlines())
-    assert compared >= n_seeds * 0.7 and subr > 50 and pins > 100, (compared, subr, pins)
+    assert compared >= n_seeds * 0.7 and subr > 50 and pins > 100, (compared, clamped_compared, subr, pins)
 
 
 def run_all_synthetic(pv, tmp, n_seeds=12):

@@ -47,3 +47,33 @@ def test_oracle_pvst_known_answer(built):
         labels = [f"{'>' if af else '<'}{a}{'>' if zf else '<'}{z}" for _, a, af, z, zf, _ in rows]
         parents = ["." if p == 0 else labels[p - 1] for *_, p in rows]
         assert sorted(zip(labels, parents)) == sorted(map(tuple, t["expected"]))
+
+
+def _vcf_rows(text):
+    """VCF text -> rows shaped like tests/golden/doc_rows.json (the columns the reference's documents pin)."""
+    samples, rows = [], []
+    for l in text.splitlines():
+        f = l.split("\t")
+        if l.startswith("#CHROM"):
+            samples = f[9:]
+        elif not l.startswith("#"):
+            rows.append({"CHROM": f[0], "POS": int(f[1]), "ID": f[2], "REF": f[3], "ALT": f[4], "INFO": f[7], "GT": f[9:]})
+    return samples, rows
+
+
+DOC = {k: v for k, v in helpers.load_json("doc_rows.json").items() if not k.startswith("_")}
+
+
+@pytest.mark.parametrize("name", sorted(DOC))
+def test_documented_golden_rows(built, name):
+    """The golden VCF rows the reference documents (docs/vcf-modernization/practical_vcf_conformance.md:82-300, the same
+    strings as povu-rs/tests/native_gfa_vcf_tests.rs:141-258) pin BOTH checkers: the committed outputs of the compiled
+    reference (tests/golden/expected, what the CUDA path is compared with byte for byte) and the CPU oracle restatement."""
+    import call_checks
+    want = DOC[name]
+    exp = open(helpers.GOLDEN + "/expected/" + name + ".vcf").read()
+    samples, rows = _vcf_rows(exp)
+    assert samples == want["samples"] and rows == want["rows"], "compiled reference output differs from the documented rows"
+    if all("VARTYPE=SUBR" not in r["INFO"] for r in want["rows"]):      # the restatement does not cover the SNE pass
+        samples, rows = _vcf_rows(call_checks.oracle_vcf(helpers.fixture_path(name), [want["prefix"]]))
+        assert samples == want["samples"] and rows == want["rows"], "oracle restatement differs from the documented rows"
