@@ -146,7 +146,7 @@ uint64_t pvgpu_session_record_count(const pvgpu_session *s);
  * [3] inversion pin pairs, [4] regions whose BFS/Kahn order failed, [5] hard errors (the reference would
  * have exited), [6] device chunks, [7] regions dropped as too small, [8] vertices of the largest region, [9] regions ordered
  * by a global-arena BFS tier, [10] SUBR records whose merged length ran past the end of a walk (undefined in the
- * reference; clamped here), [11] reserved */
+ * reference; clamped here), [11] slice trees of the SNE pass replayed sequentially (0 = all took the sorted fast path) */
 void pvgpu_session_call_stats(const pvgpu_session *s, uint64_t out[12]);
 /* combined VCF text (what `povu gfa2vcf` / `povu call --stdout` print); with_date = 0 drops ##fileDate.
  * prefix = NULL: combined stream; otherwise the per-prefix file content of `-o dir` (to_vcf.hpp:83-101). */

@@ -407,7 +407,7 @@ class Session:
     def call_stats(self):
         a = (C.c_uint64 * 12)()
         self.lib.pvgpu_session_call_stats(self.h, a)
-        k = ["selected", "regions", "tangled", "pin_pairs", "sort_failed", "hard_errors", "chunks", "too_small", "max_region", "big_bfs", "subr_clamped", "reserved"]
+        k = ["selected", "regions", "tangled", "pin_pairs", "sort_failed", "hard_errors", "chunks", "too_small", "max_region", "big_bfs", "subr_clamped", "slice_tree_replays"]
         return dict(zip(k, [int(x) for x in a]))
 
     def vcf_text(self, chunk_size=100, with_date=False, prefix=None):

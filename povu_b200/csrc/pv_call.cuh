@@ -449,6 +449,7 @@ struct Records {
 	u64 n_subr_clamped = 0;   // SUBR records whose merged length ran past the end of a walk (the reference reads out of bounds there)
 	u64 n_regions = 0;   // real regions; rov_* entries beyond them are per-ref pseudo regions that carry the SUBR records
 	u64 n_called = 0, n_too_small = 0, n_sort_failed = 0, n_tangled = 0, n_pin_pairs = 0, n_hard_errors = 0, n_chunks = 0, n_big_bfs = 0, max_J = 0;
+	u64 n_slice_tree_replays = 0;   // ref paths whose slice tree was replayed sequentially (slices of one alt path overlap); 0 = every tree took the sorted fast path
 	size_t n() const { return nRecTot; }
 	void add_piece(RecPiece &&p) { nRecTot += p.nRec; nGrpTot += p.nGrp; nGtTot += p.nGt; dev.push_back(std::move(p)); }
 	// append the device pieces that have not been copied yet to the page-locked host vectors
@@ -500,7 +501,7 @@ struct Records {
 		rov_fl.clear(); rov_comp.clear(); rov_tangled.clear();
 		rec_rov.clear(); rec_ref.clear(); rec_cxtL.clear(); rec_cxtR.clear(); rec_vt.clear(); rec_pos.clear(); rec_refStart.clear(); rec_refLen.clear();
 		rec_grpOff.clear(); rec_gtOff.clear(); grp_hap.clear(); grp_start.clear(); grp_len.clear(); grp_count.clear(); gt.clear();
-		n_regions = 0; n_subr_clamped = 0; n_called = n_too_small = n_sort_failed = n_tangled = n_pin_pairs = n_hard_errors = n_chunks = n_big_bfs = max_J = 0;
+		n_regions = 0; n_subr_clamped = 0; n_slice_tree_replays = 0; n_called = n_too_small = n_sort_failed = n_tangled = n_pin_pairs = n_hard_errors = n_chunks = n_big_bfs = max_J = 0;
 	}
 };
 typedef Records CallOut;
@@ -915,6 +916,9 @@ struct SliceTree {
 	}
 };
 
+// segmented running maximum over (segment key << 32 | value) words whose keys are sorted: a new key restarts the maximum
+struct SegMax { PV_HD u64 operator()(u64 a, u64 b) const { return (a >> 32) == (b >> 32) ? (a > b ? a : b) : b; } };
+
 PV_DEV u32 half_diff_ceil(u32 a, u32 b) { u32 d = (a > b ? a : b) - (a < b ? a : b); return (d + 1) / 2; }
 
 // Seed-and-extend of the inversion pin pairs into maximal reverse-complement matches, the per-ref slice tree and the
@@ -1016,12 +1020,93 @@ inline void sne_pass(Ctx &c, const DevGraph &G, const GraphView &g, const CallIn
 		u32 t1 = t0; while (t1 < nItems && hK[t1] == kk) t1++;
 		const u32 n = t1 - t0;
 		if (!n) continue;
-		u32 hcap = 4; while (hcap < 2 * n + 2) hcap <<= 1;
-		Buf<u32> vA(c, (size_t)n * 7), hT(c, (size_t)hcap * 2), aA(c, (size_t)n * 5), kA(c, (size_t)n * 2), lA(c, (size_t)n * 8);
-		Buf<u32> oRec(c, (size_t)n * 12), oSl(c, (size_t)n * 2), oHap(c, (size_t)n * 2), oCnt(c, 4), ord(c, n);
-		c.memset_ff(hT.p, (size_t)hcap * 4);
-		u32 *vA_ = vA.p, *hT_ = hT.p, *aA_ = aA.p, *kA_ = kA.p, *lA_ = lA.p, *oRec_ = oRec.p, *oSl_ = oSl.p, *oHap_ = oHap.p, *oCnt_ = oCnt.p, *ord_ = ord.p;
+		Buf<u32> oRec(c, (size_t)n * 12), oSl(c, (size_t)n * 2), oHap(c, (size_t)n * 2), oCnt(c, 4);
+		u32 *oRec_ = oRec.p, *oSl_ = oSl.p, *oHap_ = oHap.p, *oCnt_ = oCnt.p;
 		const u32 refH = in.refs[kk];
+		// ---- conflict-free fast path.  Two slices interact in the slice tree only when they belong to the same alt path and
+		// their ALT intervals overlap, touch or coincide (vertex::check_update_type, slice_tree.hpp:284-345); whether such a pair
+		// meets at all depends on the tree's shape (quirk Q20: the traversal only follows left links), i.e. on the whole
+		// insertion history.  Without such a pair every insertion is INSERT_ALT / EXTEND_ALT / EXISTS or a new vertex, the tree's
+		// content is just "slices grouped by ref start" and the records follow from sorts: vertices by ref start, lengths
+		// ascending, paths ascending, slices of a path in insertion order (vcf.cpp:147-215).  Any suspicious pair -> the
+		// sequential replay below, unchanged.
+		bool fast = false;
+		{
+			Buf<u32> okF(c, n), okIdx;
+			u32 *okF_ = okF.p;
+			parallel_for<S_word>(c, n, PV_LAMBDA(size_t i) { okF_[i] = eOk_[t0 + i] ? 1u : 0u; });
+			const u32 m = compact_flags(c, okF.p, n, okIdx);
+			if (m == 0) { t0 = t1; continue; }
+			Buf<u32> perm2(c, m), wk2(c, m), dup(c, m), cflag(c, 1);
+			Buf<u64> sv(c, m), sm(c, m);
+			u32 *perm2_ = perm2.p, *wk2_ = wk2.p, *dup_ = dup.p, *cflag_ = cflag.p; u64 *sv_ = sv.p, *sm_ = sm.p; const u32 *okIdx_ = okIdx.p;
+			cflag.zero();
+			parallel_for<S_word>(c, m, PV_LAMBDA(size_t i) { perm2_[i] = t0 + okIdx_[i]; });
+			const u32 *keys4[4] = {eRefStart_, eLen_, eAltStart_, eAlt_};   // LSD: sorted by (alt path, alt start, len, ref start), stable in insertion order
+			for (int w = 0; w < 4; w++) {
+				const u32 *src = keys4[w];
+				parallel_for<S_word>(c, m, PV_LAMBDA(size_t i) { wk2_[i] = src[perm2_[i]]; });
+				radix_sort_pairs_inplace(c, wk2.p, perm2.p, m, w == 3 ? bits_for(g.H) : 32);
+			}
+			parallel_for<S_item>(c, m, PV_LAMBDA(size_t i) {
+				u32 t = perm2_[i]; bool d = false;
+				if (i > 0) { u32 p = perm2_[i - 1]; d = eAlt_[p] == eAlt_[t] && eAltStart_[p] == eAltStart_[t] && eLen_[p] == eLen_[t] && eRefStart_[p] == eRefStart_[t]; }
+				dup_[i] = d ? 1u : 0u;       // the same slice at the same ref start again: EXISTS, dropped (the first one stays)
+				sv_[i] = ((u64)eAlt_[t] << 32) | (d ? 0ull : (u64)(eAltStart_[t] + eLen_[t]));
+			});
+			inclusive_scan(c, sv.p, sm.p, m, SegMax(), (u64)0);
+			parallel_for<S_item>(c, m, PV_LAMBDA(size_t i) {
+				if (i == 0 || dup_[i]) return;
+				u32 t = perm2_[i]; u64 pm = sm_[i - 1];
+				if ((u32)(pm >> 32) == eAlt_[t] && (u32)pm >= eAltStart_[t]) cflag_[0] = 1;   // overlaps / touches / coincides with an earlier slice of the path
+			});
+			if (cflag.read(0) == 0) {
+				fast = true;
+				// kept slices in insertion order, then sorted by (ref start, len, path) -- stable, so a path's slices keep their order
+				Buf<u32> keepI(c, n), kIdx;
+				u32 *keepI_ = keepI.p;
+				keepI.zero();
+				parallel_for<S_word>(c, m, PV_LAMBDA(size_t i) { if (!dup_[i]) keepI_[perm2_[i] - t0] = 1; });
+				const u32 kN = compact_flags(c, keepI.p, n, kIdx);
+				Buf<u32> perm3(c, kN), wk3(c, kN), nr(c, (size_t)kN + 1), nh(c, (size_t)kN + 1), nrS(c, (size_t)kN + 1), nhS(c, (size_t)kN + 1);
+				u32 *perm3_ = perm3.p, *wk3_ = wk3.p, *nr_ = nr.p, *nh_ = nh.p; const u32 *kIdx_ = kIdx.p;
+				parallel_for<S_word>(c, kN, PV_LAMBDA(size_t i) { perm3_[i] = t0 + kIdx_[i]; });
+				const u32 *keys3[3] = {eAlt_, eLen_, eRefStart_};
+				for (int w = 0; w < 3; w++) {
+					const u32 *src = keys3[w];
+					parallel_for<S_word>(c, kN, PV_LAMBDA(size_t i) { wk3_[i] = src[perm3_[i]]; });
+					radix_sort_pairs_inplace(c, wk3.p, perm3.p, kN, w == 0 ? bits_for(g.H) : 32);
+				}
+				parallel_for<S_item>(c, (size_t)kN + 1, PV_LAMBDA(size_t i) {
+					if (i >= kN) { nr_[i] = 0; nh_[i] = 0; return; }
+					u32 t = perm3_[i]; bool r = i == 0, h = i == 0;
+					if (i > 0) { u32 p = perm3_[i - 1]; r = eRefStart_[p] != eRefStart_[t] || eLen_[p] != eLen_[t]; h = r || eAlt_[p] != eAlt_[t]; }
+					nr_[i] = r ? 1u : 0u; nh_[i] = h ? 1u : 0u;
+				});
+				exclusive_scan(c, nr.p, nrS.p, (size_t)kN + 1, OpAddU32(), 0u);
+				exclusive_scan(c, nh.p, nhS.p, (size_t)kN + 1, OpAddU32(), 0u);
+				const u32 *nrS_ = nrS.p, *nhS_ = nhS.p;
+				parallel_for<S_item>(c, kN, PV_LAMBDA(size_t i) {
+					u32 t = perm3_[i];
+					oSl_[2 * i] = eAlt_[t]; oSl_[2 * i + 1] = eAltStart_[t];
+					if (nh_[i]) oHap_[nhS_[i]] = eAlt_[t];
+					if (nr_[i]) { u32 *o = oRec_ + 6 * (size_t)nrS_[i]; o[0] = eRefStart_[t]; o[1] = eLen_[t]; o[2] = (u32)i; o[4] = nhS_[i]; }
+					if (i == kN - 1) { oCnt_[0] = nrS_[kN]; oCnt_[1] = kN; oCnt_[2] = nhS_[kN]; }
+				});
+				parallel_for<S_item>(c, kN, PV_LAMBDA(size_t i) {   // counts = distance to the next record's first slice / path
+					if (!nr_[i]) return;
+					u32 r = nrS_[i]; u32 *o = oRec_ + 6 * (size_t)r;
+					u32 j = (u32)i + 1; while (j < kN && !nr_[j]) j++;
+					o[3] = j - (u32)i; o[5] = (j < kN ? nhS_[j] : nhS_[kN]) - nhS_[i];
+				});
+			}
+		}
+		if (!fast) {
+		u32 hcap = 4; while (hcap < 2 * n + 2) hcap <<= 1;
+		Buf<u32> vA(c, (size_t)n * 7), hT(c, (size_t)hcap * 2), aA(c, (size_t)n * 5), kA(c, (size_t)n * 2), lA(c, (size_t)n * 8), ord(c, n);
+		c.memset_ff(hT.p, (size_t)hcap * 4);
+		u32 *vA_ = vA.p, *hT_ = hT.p, *aA_ = aA.p, *kA_ = kA.p, *lA_ = lA.p, *ord_ = ord.p;
+		out.n_slice_tree_replays++;
 		parallel_for<S_tree>(c, 1, PV_LAMBDA(size_t) {
 			SliceTree T;
 			T.vStart = vA_; T.vLeft = vA_ + n; T.vRight = vA_ + 2 * (size_t)n; T.vAltHead = vA_ + 3 * (size_t)n; T.vAltTail = vA_ + 4 * (size_t)n; T.vKeyHead = vA_ + 5 * (size_t)n; T.vLenHead = vA_ + 6 * (size_t)n; T.nV = 0;
@@ -1037,7 +1122,11 @@ inline void sne_pass(Ctx &c, const DevGraph &G, const GraphView &g, const CallIn
 			// records: vertices by ascending ref start (std::map order), per vertex the lengths ascending (vcf.cpp:147-150)
 			u32 nv = T.nV;
 			for (u32 v = 0; v < nv; v++) ord_[v] = v;
-			for (u32 a = 1; a < nv; a++) { u32 x = ord_[a]; u32 b = a; while (b > 0 && T.vStart[ord_[b - 1]] > T.vStart[x]) { ord_[b] = ord_[b - 1]; b--; } ord_[b] = x; }
+			{   // heap sort by ref start (starts are distinct: one vertex per start)
+				auto sift = [&](u32 root, u32 end) { while (2 * root + 1 < end) { u32 ch = 2 * root + 1; if (ch + 1 < end && T.vStart[ord_[ch]] < T.vStart[ord_[ch + 1]]) ch++; if (T.vStart[ord_[root]] >= T.vStart[ord_[ch]]) return; u32 t = ord_[root]; ord_[root] = ord_[ch]; ord_[ch] = t; root = ch; } };
+				for (u32 st = nv / 2; st-- > 0;) sift(st, nv);
+				for (u32 end = nv; end-- > 1;) { u32 t = ord_[0]; ord_[0] = ord_[end]; ord_[end] = t; sift(0, end); }
+			}
 			u32 nRec = 0, nSl = 0, nHp = 0;
 			for (u32 q = 0; q < nv; q++) {
 				u32 v = ord_[q];
@@ -1066,6 +1155,8 @@ inline void sne_pass(Ctx &c, const DevGraph &G, const GraphView &g, const CallIn
 			}
 			oCnt_[0] = nRec; oCnt_[1] = nSl; oCnt_[2] = nHp;
 		});
+		c.sync();   // (the replay's scratch dies with this block)
+		}
 		u32 hc[4]; c.d2h(hc, oCnt.p, 16);
 		const u32 nRec = hc[0], nSl = hc[1];
 		t0 = t1;

@@ -182,6 +182,15 @@ int pvgpu_selftest_prims(pvgpu_ctx *x, uint64_t n, uint64_t seed, int bits, uint
 			std::vector<MP> gm = mo.to_host(); MP rm{0, -(1 << 29)}; OpMP op;
 			for (u64 i = 0; i < n; i++) { rm = op(rm, hm[i]); if ((gm[i].a > gm[i].b ? gm[i].a : gm[i].b) != (rm.a > rm.b ? rm.a : rm.b)) bad++; }   // the function applied to 0 (the clamp at -2^29 makes `a` grouping-dependent far below any b)
 			section("scan max-plus");
+			// segmented running maximum (an operator whose `identity` only works on the left)
+			Buf<u64> sg(c, n ? n : 1), sgo(c, n ? n : 1);
+			std::vector<u64> hs(n); u64 key = 0;
+			for (u64 i = 0; i < n; i++) { u64 z = splitmix64(seed + 13 * i); if (z % 37 == 0) key += 1 + (z >> 8) % 3; hs[i] = (key << 32) | (u32)(z >> 40); }
+			c.h2d(sg.p, hs.data(), n * 8);
+			inclusive_scan(c, sg.p, sgo.p, n, SegMax(), (u64)0);
+			std::vector<u64> gs = sgo.to_host(); u64 rs = 0; SegMax sop;
+			for (u64 i = 0; i < n; i++) { rs = i ? sop(rs, hs[i]) : hs[i]; if (gs[i] != rs) bad++; }
+			section("scan segmented max");
 		}
 		if (n >= 2) {	// range minimum + previous smaller
 			Buf<u32> a(c, n);
@@ -358,7 +367,7 @@ int pvgpu_session_set_restrict(pvgpu_session *s, const char *region) { PV_TRY(s-
 uint64_t pvgpu_session_record_count(const pvgpu_session *s) { return s->s.rec.n(); }
 void pvgpu_session_call_stats(const pvgpu_session *s, uint64_t o[12]) {
 	const pv::Records &c = s->s.rec;
-	o[0] = c.n_called; o[1] = c.n_regions; o[2] = c.n_tangled; o[3] = c.n_pin_pairs; o[4] = c.n_sort_failed; o[5] = c.n_hard_errors; o[6] = c.n_chunks; o[7] = c.n_too_small; o[8] = c.max_J; o[9] = c.n_big_bfs; o[10] = c.n_subr_clamped; o[11] = 0;
+	o[0] = c.n_called; o[1] = c.n_regions; o[2] = c.n_tangled; o[3] = c.n_pin_pairs; o[4] = c.n_sort_failed; o[5] = c.n_hard_errors; o[6] = c.n_chunks; o[7] = c.n_too_small; o[8] = c.max_J; o[9] = c.n_big_bfs; o[10] = c.n_subr_clamped; o[11] = c.n_slice_tree_replays;
 }
 // header (host strings) + the device-written record text (pv_text.cuh)
 static void vcf_parts(const pve::Session &S, size_t chunk, int with_date, const char *prefix, std::string &header, pv::TextOut &body, int fd = -1, pv::u64 *streamed = nullptr) {

@@ -116,6 +116,7 @@ struct Ctx {
 	// an epoch that grows with every use, so the scratch is never cleared between launches; only these two primitives
 	// ever write it (memory recycled from the pool could alias a live epoch).
 	u32 *lb_flags = nullptr; char *lb_vals = nullptr; size_t lb_cap = 0;     // scan: per tile flag + (aggregate, inclusive) values
+	u64 *lb_pack = nullptr;                                                  // flat scan of 4-byte elements: (epoch << 32 | aggregate) per tile, written by that kernel only
 	u64 *rs_status = nullptr; size_t rs_cap = 0;                             // sort: per (tile, digit) status
 	u32 *lb_ticket = nullptr;                                                // [0] scan tile ticket, [1] sort tile ticket (self-resetting)
 	u32 lb_epoch = 0;
@@ -176,12 +177,13 @@ inline void Ctx::init(int dev, void *ext_stream) {
 	(void)ext_stream;
 	const char *o = getenv("PV_EMU_ORDER");
 	emu_order = o ? atoi(o) : 0;
+	if (const char *sd = getenv("PV_EMU_SEED")) emu_seed = strtoull(sd, nullptr, 10);
 #endif
 }
 inline u32 Ctx::next_epoch() {
 	if (++lb_epoch >= (1u << 30)) {   // wrap: clear the scratch once, start over
 		lb_epoch = 1;
-		if (lb_flags) memset0(lb_flags, lb_cap * 4);
+		if (lb_flags) { memset0(lb_flags, lb_cap * 4); memset0(lb_pack, lb_cap * 8); }
 		if (rs_status) memset0(rs_status, rs_cap * 8);
 	}
 	return lb_epoch;
@@ -191,11 +193,13 @@ inline void Ctx::lb_reserve(size_t tiles) {
 	if (!lb_ticket) { PV_CUDA_CHECK(cudaMalloc((void **)&lb_ticket, 16)); PV_CUDA_CHECK(cudaMemsetAsync(lb_ticket, 0, 16, stream)); }
 	if (tiles <= lb_cap) return;
 	sync();
-	if (lb_flags) { cudaFree(lb_flags); cudaFree(lb_vals); }
+	if (lb_flags) { cudaFree(lb_flags); cudaFree(lb_vals); cudaFree(lb_pack); }
 	lb_cap = tiles * 2 > 4096 ? tiles * 2 : 4096;
 	PV_CUDA_CHECK(cudaMalloc((void **)&lb_flags, lb_cap * 4));
 	PV_CUDA_CHECK(cudaMalloc((void **)&lb_vals, lb_cap * 32));
+	PV_CUDA_CHECK(cudaMalloc((void **)&lb_pack, lb_cap * 8));
 	PV_CUDA_CHECK(cudaMemsetAsync(lb_flags, 0, lb_cap * 4, stream));
+	PV_CUDA_CHECK(cudaMemsetAsync(lb_pack, 0, lb_cap * 8, stream));
 #else
 	(void)tiles;
 #endif
@@ -216,7 +220,7 @@ inline void Ctx::rs_reserve(size_t words) {
 inline void Ctx::destroy() {
 #ifndef PV_EMU
 	if (stream) { cache_trim(0); cudaStreamSynchronize(stream); }
-	if (lb_flags) { cudaFree(lb_flags); cudaFree(lb_vals); lb_flags = nullptr; lb_vals = nullptr; lb_cap = 0; }
+	if (lb_flags) { cudaFree(lb_flags); cudaFree(lb_vals); cudaFree(lb_pack); lb_flags = nullptr; lb_vals = nullptr; lb_pack = nullptr; lb_cap = 0; }
 	if (rs_status) { cudaFree(rs_status); rs_status = nullptr; rs_cap = 0; }
 	if (lb_ticket) { cudaFree(lb_ticket); lb_ticket = nullptr; }
 	if (copy_stream) { cudaStreamDestroy(copy_stream); cudaEventDestroy(copy_ev); copy_stream = nullptr; copy_ev = nullptr; }
@@ -584,7 +588,9 @@ template <class Tag, class F> inline void parallel_for(Ctx &c, size_t n, F f) {
 #else
 template <class Tag, class F> inline void parallel_for(Ctx &c, size_t n, F f) {
 	c.launches++;
-	if (c.emu_order == 0) { for (size_t i = 0; i < n; i++) f(i); }
+	static const char *fwd = getenv("PV_EMU_FWD");   // debug: kernels named here run in forward order (bisecting an order dependence)
+	if (c.emu_order == 2 && fwd && strstr(fwd, Tag::name())) { c.emu_seed++; for (size_t i = 0; i < n; i++) f(i); }   // (the other kernels keep their permutations)
+	else if (c.emu_order == 0) { for (size_t i = 0; i < n; i++) f(i); }
 	else if (c.emu_order == 1) { for (size_t i = n; i-- > 0;) f(i); }
 	else {
 		// deterministic pseudo-random order: i -> (a*i + b) mod n with a coprime to n

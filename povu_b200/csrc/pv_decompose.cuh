@@ -96,7 +96,6 @@ PV_KERNEL(K_parent, 16);
 PV_KERNEL(K_seq, 16);
 PV_KERNEL(K_iota, 4);
 PV_KERNEL(K_word, 24);
-PV_KERNEL(K_classid, 12);
 
 struct MP { i32 a, b; };   // x -> max(x + a, b)
 struct OpMP {
@@ -556,48 +555,24 @@ inline void decompose_device(Ctx &c, u32 V, u64 E, const u32 *ep1, const u32 *ep
 		stKey_[gp] = u128{a.lo ^ b.lo, a.hi ^ b.hi};
 		stCnt_[gp] = (u32)(PC_[gc + sz_[cx]] - PC_[gc]);
 	});
-	// group equal keys: LSD radix sort over the four 32-bit words of the key, stable in stack position
+	// group equal keys: ONE stable radix sort by a 32-bit word of the 128-bit key (4 onesweep passes instead of 8-16).  Keys
+	// that agree on that word but differ elsewhere (a few dozen pairs per million classes, by the birthday bound) interleave
+	// inside a run of equal words; the neighbour search below steps over them, which costs the length of the foreign stretch.
+	// The sort is stable in stack position, so "next / previous in the run with my key" is next / previous seen in the stack.
 	Buf<u32> ord(c, nS), wkey(c, nS);
 	u32 *ord_ = ord.p, *wkey_ = wkey.p;
-	parallel_for<K_iota>(c, nS, PV_LAMBDA(size_t i) { ord_[i] = (u32)i; });
-	// Words are sorted least-significant first; after each word a check looks for neighbours that agree on every
-	// word sorted so far but differ in the full key.  None left => equal keys are already adjacent (and still in
-	// stack order, the sort being stable), so the remaining words are skipped: 2 of 4 words in practice.
-	for (int w = 0; w < 4; w++) {
-		parallel_for<K_word>(c, nS, PV_LAMBDA(size_t i) {
-			u128 kk = stKey_[ord_[i]];
-			u64 h = w < 2 ? kk.lo : kk.hi;
-			wkey_[i] = (u32)(h >> ((w & 1) * 32));
-		});
-		radix_sort_pairs(c, wkey, ord, nS, 32);
-		wkey_ = wkey.p; ord_ = ord.p;
-		if (w == 3) break;
-		if (w == 0 && nS > (1u << 16)) continue;   // 32 bits cannot separate that many keys (birthday bound): do not stop to ask
-		c.memset0(flag.p, 4);
-		parallel_for<K_word>(c, nS, PV_LAMBDA(size_t i) {
-			if (i == 0) return;
-			u128 a = stKey_[ord_[i - 1]], b = stKey_[ord_[i]];
-			if (a.lo == b.lo && a.hi == b.hi) return;
-			bool same = (u32)a.lo == (u32)b.lo;
-			if (w >= 1) same = same && a.lo == b.lo;
-			if (w >= 2) same = same && (u32)a.hi == (u32)b.hi;
-			if (same) flag_[0] = 1;
-		});
-		if (!flag.read(0)) break;
-	}
-	Buf<u32> nxt(c, nS), prv(c, nS), newGrp(c, nS + 1), grpId(c, nS + 1), classOf(c, nS);
-	u32 *nxt_ = nxt.p, *prv_ = prv.p, *newGrp_ = newGrp.p, *grpId_ = grpId.p, *classOf_ = classOf.p;
+	parallel_for<K_word>(c, nS, PV_LAMBDA(size_t i) { ord_[i] = (u32)i; wkey_[i] = (u32)stKey_[i].lo; });
+	radix_sort_pairs(c, wkey, ord, nS, 32);
+	wkey_ = wkey.p; ord_ = ord.p;
+	Buf<u32> nxt(c, nS), prv(c, nS);
+	u32 *nxt_ = nxt.p, *prv_ = prv.p;
 	parallel_for<K_seen>(c, nS, PV_LAMBDA(size_t i) {
-		u32 me = ord_[i]; u128 km = stKey_[me];
-		bool sameNext = false, samePrev = false;
-		if (i + 1 < nS) { u128 kn = stKey_[ord_[i + 1]]; sameNext = kn.lo == km.lo && kn.hi == km.hi; }
-		if (i > 0) { u128 kp = stKey_[ord_[i - 1]]; samePrev = kp.lo == km.lo && kp.hi == km.hi; }
-		nxt_[me] = sameNext ? ord_[i + 1] : me;
-		prv_[me] = samePrev ? ord_[i - 1] : NONE;
-		newGrp_[i] = samePrev ? 0u : 1u;
+		const u32 me = ord_[i], w = wkey_[i]; const u128 km = stKey_[me];
+		u32 nx = me, pv_ = NONE;
+		for (size_t j = i + 1; j < nS && wkey_[j] == w; j++) { u32 o = ord_[j]; u128 k = stKey_[o]; if (k.lo == km.lo && k.hi == km.hi) { nx = o; break; } }
+		for (size_t j = i; j-- > 0 && wkey_[j] == w;) { u32 o = ord_[j]; u128 k = stKey_[o]; if (k.lo == km.lo && k.hi == km.hi) { pv_ = o; break; } }
+		nxt_[me] = nx; prv_[me] = pv_;
 	});
-	inclusive_scan(c, newGrp.p, grpId.p, nS, OpAddU32(), 0u);
-	parallel_for<K_classid>(c, nS, PV_LAMBDA(size_t i) { classOf_[ord_[i]] = grpId_[i] - 1; });
 
 	// exact verification of every merged pair (bracket sets equal <=> same count, ancestor chain, and no
 	// bracket from subtree(v1) \ subtree(v2) leaves subtree(v1))
@@ -682,7 +657,9 @@ inline void decompose_device(Ctx &c, u32 V, u64 E, const u32 *ep1, const u32 *ep
 			fPar_[f] = par;
 		});
 	}
-	// non-laminar components: replay the reference's stack machine, one thread per component
+	// non-laminar components: replay the reference's stack machine, one thread per component.  The stack holds at most one
+	// entry per class (a re-encountered class pops down to its previous entry first), so "is my class on the stack" is "is my
+	// previous occurrence still on the stack": positions stand in for class ids.
 	Buf<u32> inS(c, nS), stk(c, nS);
 	inS.zero();
 	u32 *inS_ = inS.p, *stk_ = stk.p;
@@ -692,9 +669,9 @@ inline void decompose_device(Ctx &c, u32 V, u64 E, const u32 *ep1, const u32 *ep
 		u32 top = b;           // stack occupies stk_[b .. top)
 		u32 prt = 0;           // local PVST idx
 		for (u32 i = b; i < e; i++) {
-			u32 cl = classOf_[i];
-			if (inS_[cl]) {
-				while (top > b) { u32 x = stk_[--top]; inS_[x] = 0; if (x == cl) break; }
+			u32 p = prv_[i];
+			if (p != NONE && inS_[p]) {
+				while (top > b) { u32 x = stk_[--top]; inS_[x] = 0; if (x == p) break; }
 				if (prt != 0) prt = fPar_[fb + prt - 1];
 			}
 			if (open_[i]) {
@@ -703,7 +680,7 @@ inline void decompose_device(Ctx &c, u32 V, u64 E, const u32 *ep1, const u32 *ep
 				fDepth_[f] = prt == 0 ? 1u : fDepth_[fb + prt - 1] + 1;
 				prt = f - fb + 1;
 			}
-			stk_[top++] = cl; inS_[cl] = 1;
+			stk_[top++] = i; inS_[i] = 1;
 		}
 	});
 
@@ -739,7 +716,11 @@ inline void decompose_device(Ctx &c, u32 V, u64 E, const u32 *ep1, const u32 *ep
 		for (u32 k = 0; k < nComp; k++) out.comp_nfl[k] = h[4 + 4 * PK + k + 1] - h[4 + 4 * PK + k];
 	}
 	if (opt.want_stack) {
-		out.stack_v = stV.to_host(); out.stack_class = classOf.to_host();
+		out.stack_v = stV.to_host();
+		{   // dense class ids in order of first appearance on the stack (debug output only: derived from the previous-seen links)
+			std::vector<u32> hp = prv.to_host(); out.stack_class.resize(nS); u32 next_id = 0;
+			for (u32 i = 0; i < nS; i++) out.stack_class[i] = hp[i] == NONE ? next_id++ : out.stack_class[hp[i]];
+		}
 		std::vector<u32> es = entrySide.to_host();
 		out.stack_fwd.resize(nS);
 		for (u32 i = 0; i < nS; i++) out.stack_fwd[i] = es[out.stack_v[i]] == 0;

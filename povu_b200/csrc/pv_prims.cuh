@@ -156,6 +156,114 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_lb_kernel(const T *in, T *o
 	}
 }
 
+// Mid-sized inputs (every tile resident at once: up to a few million elements, the regime of cfg2) are latency-bound in the
+// look-back above: tile i walks back through its predecessors 32 at a time, one dependent round trip to L2 per window.  Here a
+// tile publishes its aggregate and then fetches the aggregates of ALL its predecessors at once: lane L of warp 0 owns a
+// contiguous block of ceil(i / 32) predecessors (independent loads, combined in order), then one ordered warp reduction.  One
+// round trip instead of i / 32.  4-byte elements travel with their epoch in one 64-bit word (no fence, no second load).
+template <class T> struct ScanPack { static const bool value = sizeof(T) == 4; };
+template <class T, class Op, bool INCLUSIVE, bool VEC>
+__global__ void __launch_bounds__(SCAN_THREADS) scan_flat_kernel(const T *in, T *out, size_t n, Op op, T identity, u32 *flags, T *agg, u64 *pack,
+								   u32 *ticket, u32 epoch, u32 ntiles) {
+	constexpr int SCAN_ITEMS = ScanCfg<T>::ITEMS, SCAN_TILE = ScanCfg<T>::TILE;
+	__shared__ T warpTot[SCAN_THREADS / 32];
+	__shared__ T s_prefix;
+	__shared__ u32 s_tile;
+	const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+	if (t == 0) { u32 k = atomicAdd(ticket, 1u); if (k == ntiles - 1) atomicExch(ticket, 0u); s_tile = k; }
+	__syncthreads();
+	const u32 tile = s_tile;
+	const size_t base = (size_t)tile * SCAN_TILE + (size_t)t * SCAN_ITEMS;
+	const bool full = (size_t)(tile + 1) * SCAN_TILE <= n;
+	union Items { T v[SCAN_ITEMS]; uint4 q[sizeof(T) * SCAN_ITEMS / 16]; __device__ Items() {} } it;
+	if (full) {
+		if (VEC) {
+			const uint4 *src = reinterpret_cast<const uint4 *>(in + base);
+#pragma unroll
+			for (int k = 0; k < (int)(sizeof(T) * SCAN_ITEMS / 16); k++) it.q[k] = src[k];
+		} else {
+#pragma unroll
+			for (int k = 0; k < SCAN_ITEMS; k++) it.v[k] = in[base + k];
+		}
+	} else {
+#pragma unroll
+		for (int k = 0; k < SCAN_ITEMS; k++) it.v[k] = base + k < n ? in[base + k] : identity;
+	}
+	T acc = it.v[0];
+#pragma unroll
+	for (int k = 1; k < SCAN_ITEMS; k++) acc = op(acc, it.v[k]);
+	T inc = acc;
+#pragma unroll
+	for (int d = 1; d < 32; d <<= 1) { T y = shfl_up_t(inc, d); if (lane >= d) inc = op(y, inc); }
+	if (lane == 31) warpTot[w] = inc;
+	__syncthreads();
+	if (w == 0) {
+		T tot = warpTot[0];
+#pragma unroll
+		for (int i = 1; i < SCAN_THREADS / 32; i++) tot = op(tot, warpTot[i]);
+		if (lane == 0 && tile + 1 < ntiles) {   // (nobody reads the last tile's aggregate)
+			if (ScanPack<T>::value) { union { T t; u32 u; } cv; cv.u = 0; cv.t = tot; *(volatile u64 *)(pack + tile) = ((u64)epoch << 32) | cv.u; }
+			else { agg[tile] = tot; __threadfence(); st_flag(flags + tile, (epoch << 2) | 1u); }
+		}
+		// predecessors [0, tile): lane L combines [L * k, (L + 1) * k) in order
+		const u32 k = (tile + 31u) / 32u;
+		const u32 j0 = (u32)lane * k, j1 = j0 + k < tile ? j0 + k : tile;
+		T v = identity; bool have = false;   // (never combine with `identity` on the right: segmented operators only honour it on the left)
+		for (u32 j = j0; j < j1; j += 4) {
+			T x[4];
+#pragma unroll
+			for (int q = 0; q < 4; q++) {
+				if (j + q < j1) {
+					if (ScanPack<T>::value) {
+						u64 wd;
+						do { wd = *(const volatile u64 *)(pack + j + q); } while ((u32)(wd >> 32) != epoch);
+						union { T t; u32 u; } cv; cv.u = (u32)wd; x[q] = cv.t;
+					} else {
+						u32 f;
+						do { f = *(const volatile u32 *)(flags + j + q); } while ((f >> 2) != epoch);
+						__threadfence();
+						x[q] = ld_cg_t(agg + j + q);
+					}
+				}
+			}
+#pragma unroll
+			for (int q = 0; q < 4; q++) if (j + q < j1) { v = have ? op(v, x[q]) : x[q]; have = true; }
+		}
+		// ordered product over the lanes that hold something (lower lanes = earlier tiles)
+#pragma unroll
+		for (int d = 1; d < 32; d <<= 1) {
+			T y = shfl_up_t(v, d); bool hy = __shfl_up_sync(0xFFFFFFFFu, have ? 1 : 0, d) != 0;
+			if (lane >= d && hy) { v = have ? op(y, v) : y; have = true; }
+		}
+		if (!have) v = identity;
+		if (lane == 31) s_prefix = v;
+	}
+	__syncthreads();
+	T run = s_prefix;
+	for (int i = 0; i < w; i++) run = op(run, warpTot[i]);
+	T prevLane = shfl_up_t(inc, 1);
+	if (lane > 0) run = op(run, prevLane);
+	if (tile == 0 && w == 0 && lane == 0) run = identity;
+#pragma unroll
+	for (int k = 0; k < SCAN_ITEMS; k++) {
+		if (INCLUSIVE) { run = op(run, it.v[k]); it.v[k] = run; }
+		else { T x = it.v[k]; it.v[k] = run; run = op(run, x); }
+	}
+	if (full) {
+		if (VEC) {
+			uint4 *dst = reinterpret_cast<uint4 *>(out + base);
+#pragma unroll
+			for (int k = 0; k < (int)(sizeof(T) * SCAN_ITEMS / 16); k++) dst[k] = it.q[k];
+		} else {
+#pragma unroll
+			for (int k = 0; k < SCAN_ITEMS; k++) out[base + k] = it.v[k];
+		}
+	} else {
+#pragma unroll
+		for (int k = 0; k < SCAN_ITEMS; k++) if (base + k < n) out[base + k] = it.v[k];
+	}
+}
+
 template <class T, class Op, bool INCLUSIVE>
 inline void scan_impl(Ctx &c, const T *in, T *out, size_t n, Op op, T identity) {
 	if (n == 0) return;
@@ -166,6 +274,16 @@ inline void scan_impl(Ctx &c, const T *in, T *out, size_t n, Op op, T identity) 
 	u32 epoch = c.next_epoch();
 	T *agg = (T *)c.lb_vals, *incl = (T *)(c.lb_vals + c.lb_cap * 16);
 	bool vec = (((uintptr_t)in | (uintptr_t)out) & 15u) == 0;
+	static const u32 flat_max = getenv("POVU_B200_SCAN_FLAT_MAX") ? (u32)strtoul(getenv("POVU_B200_SCAN_FLAT_MAX"), nullptr, 10) : 1024u;
+	if (ntiles <= flat_max) {   // every predecessor's aggregate is fetched at once (see scan_flat_kernel)
+		c.prof_begin("scan_flat", n, n * 2 * sizeof(T));
+		if (vec) scan_flat_kernel<T, Op, INCLUSIVE, true><<<(unsigned)ntiles, SCAN_THREADS, 0, c.stream>>>(in, out, n, op, identity, c.lb_flags, agg, c.lb_pack, c.lb_ticket, epoch, (u32)ntiles);
+		else scan_flat_kernel<T, Op, INCLUSIVE, false><<<(unsigned)ntiles, SCAN_THREADS, 0, c.stream>>>(in, out, n, op, identity, c.lb_flags, agg, c.lb_pack, c.lb_ticket, epoch, (u32)ntiles);
+		c.prof_end();
+		c.launches++;
+		PV_CUDA_CHECK(cudaGetLastError());
+		return;
+	}
 	c.prof_begin("scan_lb", n, n * 2 * sizeof(T));
 	if (vec) scan_lb_kernel<T, Op, INCLUSIVE, true><<<(unsigned)ntiles, SCAN_THREADS, 0, c.stream>>>(in, out, n, op, identity, c.lb_flags, agg, incl, c.lb_ticket, epoch, (u32)ntiles);
 	else scan_lb_kernel<T, Op, INCLUSIVE, false><<<(unsigned)ntiles, SCAN_THREADS, 0, c.stream>>>(in, out, n, op, identity, c.lb_flags, agg, incl, c.lb_ticket, epoch, (u32)ntiles);
@@ -447,9 +565,18 @@ PV_DEV u32 pv_clz(u32 x) { return (u32)__clz((int)x); }
 inline u32 pv_clz(u32 x) { return (u32)__builtin_clz(x); }
 #endif
 
+// Two levels of blocking so that a build is ONE launch (the sparse table over all block minima took one launch per five levels:
+// 12 launches for the four RMQs of a cfg2 decompose, all latency):
+//   block      = 32 elements: prefix / suffix minima inside the block (pre, suf)
+//   superblock = 32 blocks (1024 elements, one CTA): per block a 6-level table of minima over the next 1, 2, 4, 8, 16, 32 blocks of its
+//                superblock (bt), prefix / suffix minima of the block minima inside the superblock (pre2, suf2)
+//   a sparse table over the superblock minima (st), built by the last CTA to finish (n / 1024 entries per level).
 struct RmqView {
-	const u32 *a; const u32 *pre; const u32 *suf; const u32 *table; u32 n; u32 nb;
+	const u32 *a; const u32 *pre; const u32 *suf; const u32 *bt; const u32 *pre2; const u32 *suf2; const u32 *st; u32 n; u32 nb; u32 ns; u32 levels;
 	PV_DEV u32 query(u32 l, u32 r) const {
+#ifdef PV_EMU
+		if (l > r || r >= n) { fprintf(stderr, "RmqView::query(%u, %u) outside [0, %u)\n", l, r, n); abort(); }
+#endif
 		u32 bl = l >> 5, br = r >> 5;
 		if (bl == br) {
 			u32 m = a[l];
@@ -458,16 +585,32 @@ struct RmqView {
 		}
 		u32 m = suf[l]; u32 x = pre[r]; m = x < m ? x : m;
 		if (br > bl + 1) {
-			u32 len = br - bl - 1;
-			u32 k = 31u - pv_clz(len);
-			const u32 *row = table + (size_t)k * nb;
-			x = row[bl + 1]; m = x < m ? x : m;
-			x = row[br - (1u << k)]; m = x < m ? x : m;
+			const u32 p = bl + 1, q = br - 1;      // whole blocks in between
+			const u32 sp = p >> 5, sq = q >> 5;
+			if (sp == sq) {
+				u32 k = 31u - pv_clz(q - p + 1);
+				x = bt[(size_t)k * nb + p]; m = x < m ? x : m;
+				x = bt[(size_t)k * nb + (q + 1 - (1u << k))]; m = x < m ? x : m;
+			} else {
+				x = suf2[p]; m = x < m ? x : m;
+				x = pre2[q]; m = x < m ? x : m;
+				if (sq > sp + 1) {
+					u32 k = 31u - pv_clz(sq - sp - 1);
+					const u32 *row = st + (size_t)k * ns;
+					x = row[sp + 1]; m = x < m ? x : m;
+					x = row[sq - (1u << k)]; m = x < m ? x : m;
+				}
+			}
 		}
 		return m;
 	}
-	// largest index j <= r with a[j] < bound, or NONE ("previous smaller value"): scan r's block, then
-	// skip candidate-free block spans by descending the sparse table, then scan the hit block.
+	PV_DEV u32 scan_block_down(u32 blk, u32 bound) const {   // largest index of block blk with a value below bound (the block holds one)
+		u32 s = blk << 5; u32 i = s + 31u < n ? s + 31u : n - 1;
+		for (;; i--) { if (a[i] < bound) return i; if (i == s) break; }
+		return NONE;   // unreachable when the tables are consistent
+	}
+	// largest index j <= r with a[j] < bound, or NONE ("previous smaller value"): r's block, then the earlier blocks of its
+	// superblock, then whole superblocks by descending the sparse table, then the hit superblock's blocks.
 	PV_DEV u32 prev_smaller(u32 r, u32 bound) const {
 		u32 j = r;
 		while (true) {
@@ -475,93 +618,120 @@ struct RmqView {
 			if ((j & 31u) == 0) break;
 			j--;
 		}
-		u32 pos = j >> 5;   // blocks [pos, block(r)] hold no candidate
+		const u32 b = r >> 5, sb = b >> 5;
+		for (u32 blk = b; blk-- > (sb << 5);) if (bt[blk] < bound) return scan_block_down(blk, bound);
+		u32 pos = sb;   // superblocks [pos, sb] hold no candidate
 		for (u32 k = levels; k-- > 0;) {
 			u32 span = 1u << k;
-			if (pos >= span && table[(size_t)k * nb + (pos - span)] >= bound) pos -= span;
+			if (pos >= span && st[(size_t)k * ns + (pos - span)] >= bound) pos -= span;
 		}
 		if (pos == 0) return NONE;
-		u32 b = pos - 1, s = b << 5;
-		for (u32 i = s + 31u;; i--) {
-			if (a[i] < bound) return i;
-			if (i == s) break;
-		}
-		return NONE;   // unreachable when the table is consistent
+		const u32 s = pos - 1;
+		u32 top = (s << 5) + 31u; if (top >= nb) top = nb - 1;
+		for (u32 blk = top + 1; blk-- > (s << 5);) if (bt[blk] < bound) return scan_block_down(blk, bound);
+		return NONE;   // unreachable when the tables are consistent
 	}
-	u32 levels;
 };
 
 struct Rmq {
-	Buf<u32> pre, suf, table;
-	u32 n = 0, nb = 0, levels = 0;
+	Buf<u32> pre, suf, bt, pre2, suf2, st;
+	u32 n = 0, nb = 0, ns = 0, levels = 0;
 	const u32 *a = nullptr;
-	RmqView view() const { return RmqView{a, pre.p, suf.p, table.p, n, nb, levels}; }
+	RmqView view() const { return RmqView{a, pre.p, suf.p, bt.p, pre2.p, suf2.p, st.p, n, nb, ns, levels}; }
 };
 
-PV_KERNEL(K_rmq_blocks, 12);   // a in, pre + suf out (+ block min)
-PV_KERNEL(K_rmq_level, 24);   // one level in, up to five levels out
+PV_KERNEL(K_rmq_blocks, 12);   // a in, pre + suf out (+ the block tables: 8 words per 32 elements)
+PV_KERNEL(K_rmq_level, 8);
 
 #ifndef PV_EMU
-__global__ void __launch_bounds__(256) rmq_blocks_kernel(const u32 *a, u32 *pre, u32 *suf, u32 *table, u32 n, u32 nb) {
-	const u32 lane = threadIdx.x & 31u;
-	const u32 warp = (blockIdx.x * 256u + threadIdx.x) >> 5, nwarps = (gridDim.x * 256u) >> 5;
-	for (u32 b = warp; b < nb; b += nwarps) {
+__global__ void __launch_bounds__(1024) rmq_build_kernel(const u32 *a, u32 *pre, u32 *suf, u32 *bt, u32 *pre2, u32 *suf2, u32 *st, u32 n, u32 nb, u32 ns, u32 levels, u32 *ticket) {
+	__shared__ u32 bm[32];
+	__shared__ u32 s_last;
+	const u32 lane = threadIdx.x & 31u, w = threadIdx.x >> 5, s = blockIdx.x;
+	const u32 b = (s << 5) + w;
+	{
 		u32 i = (b << 5) + lane;
 		u32 x = i < n ? a[i] : NONE;
-		u32 p = x, s = x;
+		u32 p = x, q = x;
 #pragma unroll
 		for (int d = 1; d < 32; d <<= 1) {
 			u32 y = __shfl_up_sync(0xFFFFFFFFu, p, d); if (lane >= (u32)d && y < p) p = y;
-			u32 z = __shfl_down_sync(0xFFFFFFFFu, s, d); if (lane + d < 32u && z < s) s = z;
+			u32 z = __shfl_down_sync(0xFFFFFFFFu, q, d); if (lane + d < 32u && z < q) q = z;
 		}
-		if (i < n) { pre[i] = p; suf[i] = s; }
-		if (lane == 0) table[b] = s;
+		if (i < n) { pre[i] = p; suf[i] = q; }
+		if (lane == 0) bm[w] = q;      // NONE for blocks past the end
+	}
+	__syncthreads();
+	if (w < 6) {   // warp k: level k of the block table (minimum over the next 2^k blocks of this superblock)
+		const u32 k = w, span = 1u << k;
+		u32 m = NONE;
+		for (u32 i = 0; i < span && lane + i < 32u; i++) { u32 x = bm[lane + i]; m = x < m ? x : m; }
+		if ((s << 5) + lane < nb) bt[(size_t)k * nb + (s << 5) + lane] = m;
+	} else if (w == 6) {
+		u32 x = bm[lane], p = x, q = x;
+#pragma unroll
+		for (int d = 1; d < 32; d <<= 1) {
+			u32 y = __shfl_up_sync(0xFFFFFFFFu, p, d); if (lane >= (u32)d && y < p) p = y;
+			u32 z = __shfl_down_sync(0xFFFFFFFFu, q, d); if (lane + d < 32u && z < q) q = z;
+		}
+		if ((s << 5) + lane < nb) { pre2[(s << 5) + lane] = p; suf2[(s << 5) + lane] = q; }
+		if (lane == 0) { st[s] = q; __threadfence(); u32 k = atomicAdd(ticket, 1u); s_last = (k == gridDim.x - 1) ? 1u : 0u; if (s_last) atomicExch(ticket, 0u); }
+	}
+	__syncthreads();
+	if (!s_last) return;
+	__threadfence();
+	// the last CTA: sparse table over the superblock minima, level by level
+	for (u32 k = 1; k < levels; k++) {
+		const u32 half = 1u << (k - 1);
+		const u32 *src = st + (size_t)(k - 1) * ns; u32 *dst = st + (size_t)k * ns;
+		for (u32 i = threadIdx.x; i < ns; i += 1024u) {
+			u32 x = __ldcg(src + i), y = i + half < ns ? __ldcg(src + i + half) : NONE;
+			dst[i] = x < y ? x : y;
+		}
+		__syncthreads();
 	}
 }
 #endif
 
 inline void rmq_build(Ctx &c, Rmq &r, const u32 *a, u32 n) {
-	r.a = a; r.n = n; r.nb = (n + 31) / 32;
-	r.levels = 1; while ((1u << r.levels) <= r.nb) r.levels++;
-	r.pre = Buf<u32>(c, n); r.suf = Buf<u32>(c, n); r.table = Buf<u32>(c, (size_t)r.levels * r.nb);
-	u32 *pre = r.pre.p, *suf = r.suf.p, *table = r.table.p; u32 nb = r.nb;
+	r.a = a; r.n = n; r.nb = (n + 31) / 32; r.ns = (r.nb + 31) / 32;
+	r.levels = 1; while ((1u << r.levels) <= r.ns) r.levels++;
+	r.pre = Buf<u32>(c, n); r.suf = Buf<u32>(c, n); r.bt = Buf<u32>(c, (size_t)6 * r.nb); r.pre2 = Buf<u32>(c, r.nb); r.suf2 = Buf<u32>(c, r.nb);
+	r.st = Buf<u32>(c, (size_t)r.levels * r.ns);
+	u32 *pre = r.pre.p, *suf = r.suf.p, *bt = r.bt.p, *pre2 = r.pre2.p, *suf2 = r.suf2.p, *st = r.st.p; const u32 nb = r.nb, ns = r.ns, levels = r.levels;
 #ifndef PV_EMU
-	{
-		// one warp per block of 32: coalesced 128-byte load, prefix / suffix minima by shuffles, coalesced stores
-		size_t blocks = ((size_t)nb * 32 + 255) / 256, cap = (size_t)c.sm_count * 16;
-		if (blocks > cap) blocks = cap;
-		c.prof_begin(K_rmq_blocks::name(), n, (u64)n * K_rmq_blocks::bytes);
-		rmq_blocks_kernel<<<(unsigned)blocks, 256, 0, c.stream>>>(a, pre, suf, table, n, nb);
-		c.prof_end();
-		c.launches++;
-		PV_CUDA_CHECK(cudaGetLastError());
-	}
+	c.lb_reserve(1);
+	c.prof_begin(K_rmq_blocks::name(), n, (u64)n * K_rmq_blocks::bytes);
+	rmq_build_kernel<<<ns, 1024, 0, c.stream>>>(a, pre, suf, bt, pre2, suf2, st, n, nb, ns, levels, c.lb_ticket + 2);
+	c.prof_end();
+	c.launches++;
+	PV_CUDA_CHECK(cudaGetLastError());
 #else
-	parallel_for<K_rmq_blocks>(c, nb, PV_LAMBDA(size_t b) {
-		u32 s = (u32)b << 5, e = s + 32 < n ? s + 32 : n;
-		u32 m = NONE;
-		for (u32 i = s; i < e; i++) { u32 x = a[i]; m = x < m ? x : m; pre[i] = m; }
-		table[b] = m;
-		m = NONE;
-		for (u32 i = e; i-- > s;) { u32 x = a[i]; m = x < m ? x : m; suf[i] = m; }
+	parallel_for<K_rmq_blocks>(c, ns, PV_LAMBDA(size_t s) {
+		u32 bm[32];
+		for (u32 w = 0; w < 32; w++) {
+			u32 b = ((u32)s << 5) + w; u32 lo = b << 5, hi = lo + 32 < n ? lo + 32 : n;
+			u32 m = NONE;
+			for (u32 i = lo; i < hi && i >= lo; i++) { u32 x = a[i]; m = x < m ? x : m; pre[i] = m; }
+			m = NONE;
+			if (lo < n) for (u32 i = hi; i-- > lo;) { u32 x = a[i]; m = x < m ? x : m; suf[i] = m; }
+			bm[w] = m;
+		}
+		for (u32 w = 0; w < 32; w++) {
+			u32 b = ((u32)s << 5) + w;
+			if (b >= nb) break;
+			for (u32 k = 0; k < 6; k++) { u32 m = NONE; for (u32 i = 0; i < (1u << k) && w + i < 32; i++) m = bm[w + i] < m ? bm[w + i] : m; bt[(size_t)k * nb + b] = m; }
+			u32 p = NONE; for (u32 i = 0; i <= w; i++) p = bm[i] < p ? bm[i] : p;
+			u32 q = NONE; for (u32 i = w; i < 32; i++) q = bm[i] < q ? bm[i] : q;
+			pre2[b] = p; suf2[b] = q;
+			if (w == 0) st[s] = q;
+		}
+	});
+	parallel_for<K_rmq_level>(c, 1, PV_LAMBDA(size_t) {
+		for (u32 k = 1; k < levels; k++)
+			for (u32 i = 0; i < ns; i++) { u32 x = st[(size_t)(k - 1) * ns + i]; u32 j = i + (1u << (k - 1)); u32 y = j < ns ? st[(size_t)(k - 1) * ns + j] : NONE; st[(size_t)k * ns + i] = x < y ? x : y; }
 	});
 #endif
-	// five sparse-table levels per launch: level b+m at j = min over i < 2^m of level b at j + i * 2^b
-	for (u32 b = 0; b + 1 < r.levels; b += 5) {
-		const u32 top = b + 5 < r.levels - 1 ? b + 5 : r.levels - 1;   // highest level written by this launch
-		const u32 stride = 1u << b;
-		const u32 *src = table + (size_t)b * nb;
-		parallel_for<K_rmq_level>(c, nb, PV_LAMBDA(size_t j) {
-			u32 m = NONE;
-			u32 lvl = b + 1;
-			for (u32 i = 0; i < 32u && lvl <= top; i++) {
-				size_t q = j + (size_t)i * stride;
-				u32 x = q < nb ? src[q] : NONE;
-				m = x < m ? x : m;
-				if (((i + 1) & i) == 0 && i > 0) { table[(size_t)lvl * nb + j] = m; lvl++; }   // i + 1 = 2, 4, 8, 16, 32
-			}
-		});
-	}
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -146,6 +146,7 @@ def snp_indel_chain(n_bubbles=400_000, n_paths=16, seed=42, with_seqs=True, firs
         hap = p % 2 + 1
         paths.append((f"S{sample:03d}#{hap}#chr1", steps, np.zeros(len(steps), dtype=np.uint8)))
     g = make_graph(ids, seqs, allL, paths)
+    g["inst_base"] = base.astype(np.int64)      # backbone vertex of every bubble (+ the last one): where the chain can be cut
     return g
 
 
@@ -294,13 +295,17 @@ def template_from(g):
     return {"V": len(g["ids"]), "seqs": g["seqs"], "links": L, "walks": [(np.asarray(p[1], np.uint32), np.asarray(p[2], np.uint8)) for p in g["paths"]]}
 
 
-def tiled(templates, n_instances, n_paths, seed=42, n_components=1, comp_weights=None, first_id=1, ref_walk0=True):
+def tiled(templates, n_instances, n_paths, seed=42, n_components=1, comp_weights=None, first_id=1, ref_walk0=True, tpl_weights=None):
     """Chains `n_instances` randomly chosen template instances (sink of one -> source of the next, `+ +`) into
     `n_components` components (sizes proportional to comp_weights).  Path p of component c picks one of the
     template's walks per instance (path 0 always walk 0 when ref_walk0).  Paths are named S%03d#{1,2}#chr<c>."""
     rng = _rng(seed)
     K = len(templates)
-    tpl = rng.integers(0, K, size=n_instances)
+    if tpl_weights is None:
+        tpl = rng.integers(0, K, size=n_instances)
+    else:                                                        # templates drawn with the given relative frequencies
+        w_ = np.asarray(tpl_weights, dtype=np.float64)
+        tpl = np.minimum(np.searchsorted(np.cumsum(w_) / w_.sum(), rng.uniform(size=n_instances), side="right"), K - 1)
     tV = np.array([t["V"] for t in templates], dtype=np.int64)
     base = np.concatenate([[0], np.cumsum(tV[tpl])])            # first vertex of every instance
     V = int(base[-1])
@@ -365,19 +370,91 @@ def tiled(templates, n_instances, n_paths, seed=42, n_components=1, comp_weights
                     strands[pos] = np.tile(wr, len(m))
             paths.append((f"S{p // 2 + 1:03d}#{p % 2 + 1}#chr{c + 1}", steps, strands))
     ids = np.arange(first_id, first_id + V, dtype=np.uint32)
-    return make_graph(ids, seqs.tolist(), allL, paths)
+    g = make_graph(ids, seqs.tolist(), allL, paths)
+    g["inst_base"] = base.astype(np.int64)      # first vertex of every template instance (+ V): where the chain can be cut
+    return g
 
 
-def cfg3_templates(seed=7, n_nested=24, tower_depth=64, p_inv=0.0):
+def inversion_unit(seed=0, inner=1):
+    """A block that paths may traverse on the reverse strand: u -> [s -> (x | y) -> t] -> v plus the two links of the
+    inverted traversal (u+ -> t-, s- -> v+).  A path that walks t-, x-, s- crosses the region (s, t) as a whole-region
+    inversion of the reference's s+, x+, t+: an SNE pin pair, a reverse-complement match, one SUBR record.  `inner` chains
+    that many bubbles inside the block.  Walk 0 (the reference) is forward; 1 walk in 5 is inverted (p = 0.2)."""
+    rng = _rng(1000 + seed)
+    seqs, links = [], []
+
+    def new_v():
+        seqs.append("".join("ACGT"[int(c)] for c in rng.integers(0, 4, size=int(rng.integers(1, 5)))))
+        return len(seqs) - 1
+
+    u = new_v()
+    chain = [new_v()]
+    alleles = []
+    for _ in range(inner):
+        s_ = chain[-1]; x, y, t = new_v(), new_v(), new_v()
+        links += [link(s_, "+", x, "+"), link(s_, "+", y, "+"), link(x, "+", t, "+"), link(y, "+", t, "+")]
+        alleles.append((x, y)); chain.append(t)
+    v = new_v()
+    first, last = chain[0], chain[-1]
+    links += [link(u, "+", first, "+"), link(last, "+", v, "+"), link(u, "+", last, "-"), link(first, "-", v, "+")]
+
+    def walk(pick, inverted):
+        mid = [chain[0]]
+        for k, (x, y) in enumerate(alleles):
+            mid += [x if pick[k] == 0 else y, chain[k + 1]]
+        st = [(m, 0) for m in mid]
+        if inverted:
+            st = [(m, 1) for m, _ in reversed(st)]
+        st = [(u, 0)] + st + [(v, 0)]
+        return np.array([a for a, _ in st], dtype=np.uint32), np.array([b for _, b in st], dtype=np.uint8)
+
+    zeros = [0] * inner
+    walks = [walk(zeros, False), walk([1] * inner, False), walk([int(c) for c in rng.integers(0, 2, size=inner)], False),
+             walk([int(c) for c in rng.integers(0, 2, size=inner)], False), walk(zeros if seed % 2 == 0 else [1] * inner, True)]
+    return {"V": len(seqs), "seqs": seqs, "links": np.asarray(links, dtype=np.int64).reshape(-1, 4), "walks": walks}
+
+
+def cfg3_templates(seed=7, n_nested=24, tower_depth=64, p_inv=0.0, n_repeat=0):
     """nested templates with depth mostly <= 3, some 4-8, plus one tower (inversion bubbles only
-    when p_inv > 0 -- their SUBR records need the SNE pass)."""
+    when p_inv > 0 -- their SUBR records need the SNE pass; n_repeat VNTR-like repeat-unit templates give tangled regions)."""
     t = []
     for k in range(n_nested):
         depth = 2 + (k % 3) if k % 8 else 5 + (k % 4)
         t.append(template_from(nested_bubbles(seed * 1000 + k, n_top=4 + k % 5, max_depth=depth, n_paths=8, p_inv=p_inv)))
+    for k in range(n_repeat):
+        t.append(template_from(repeat_loops(2 * (seed * 100 + k), n_units=2, n_paths=8, max_laps=3)))       # even seed: walk 0 (the reference) takes one lap
     if tower_depth:
         t.append(tower(tower_depth, seed))
     return t
+
+
+def window(g, lo, hi):
+    """Vertices [lo, hi) of a chain-shaped graph with their ORIGINAL ids, the links among them and, of every path, its steps
+    inside the window (a chain-shaped walk crosses the window once, so they are one run).  With lo / hi at instance
+    boundaries of `tiled` (or backbone vertices of `snp_indel_chain`) every region strictly inside the window is the same
+    region as in the whole graph: same ids, same alleles, same genotypes; POS is shifted by the bases of the reference walk
+    before the window (`window_pos_shift`)."""
+    keep = (g["v1"] >= lo) & (g["v1"] < hi) & (g["v2"] >= lo) & (g["v2"] < hi)
+    L = np.stack([g["v1"][keep].astype(np.int64) - lo, g["s1"][keep], g["v2"][keep].astype(np.int64) - lo, g["s2"][keep]], 1)
+    paths = []
+    for name, st, sr in g["paths"]:
+        m = np.nonzero((st >= lo) & (st < hi))[0]
+        if len(m) == 0:
+            paths.append((name, st[:0], sr[:0])); continue
+        a, b = int(m[0]), int(m[-1]) + 1
+        assert b - a == len(m), "the walk leaves and re-enters the window"
+        paths.append((name, (st[a:b].astype(np.int64) - lo).astype(np.uint32), sr[a:b]))
+    return make_graph(g["ids"][lo:hi], g["seqs"][lo:hi] if g["seqs"] is not None else None, L, paths)
+
+
+def window_pos_shift(g, lo, hi, path=0):
+    """bases of path `path`'s walk before its first step inside [lo, hi): POS(whole graph) = POS(window) + shift"""
+    _, st, _ = g["paths"][path]
+    m = np.nonzero((st >= lo) & (st < hi))[0]
+    if len(m) == 0:
+        return 0
+    lens = np.fromiter((len(g["seqs"][v]) for v in st[:int(m[0])].tolist()), dtype=np.int64, count=int(m[0])) if g["seqs"] is not None else np.ones(int(m[0]), np.int64)
+    return int(lens.sum())
 
 
 def truncate(g, n_vertices):

@@ -1,0 +1,59 @@
+"""Parity at size on the B200, against the compiled reference (oracle/_ref/povu_ref -- missing binary = failure):
+  * cfg2 at its full size (1,000,001 segments / 1.4 M links / 16 paths) through the `povu` CLI: VCF and .pvst byte-identical;
+  * the cfg3 mix (nested bubbles, PVST tower, inversion bubbles, reverse-strand blocks -> SNE / SUBR, repeat units -> tangled)
+    at >= 1 M segments and 90 paths: 8 windows spread over the graph, every record type compared."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+import call_checks
+from povu_b200 import api, synth
+
+pytestmark = pytest.mark.gpu
+ROOT = call_checks.ROOT
+sys.path.insert(0, os.path.join(ROOT, "scripts"))
+
+
+def test_gpu_cfg2_full_size_bytes(gpu, tmp_path):
+    call_checks.require_ref()
+    cli = os.path.join(ROOT, "povu_b200", "bin", "povu")
+    gfa = str(tmp_path / "cfg2.gfa")
+    g = synth.snp_indel_chain(400_000, n_paths=16, seed=42, with_seqs=True)
+    assert len(g["ids"]) == 1_000_001 and len(g["v1"]) == 1_400_000
+    synth.write_gfa_fast(g, gfa)
+    del g
+    ours, ref = str(tmp_path / "ours.vcf"), str(tmp_path / "ref.vcf")
+    with open(ours, "wb") as f:
+        r = subprocess.run([cli, "gfa2vcf", "-i", gfa, "-P", "S001#1"], stdout=f, stderr=subprocess.PIPE)
+    assert r.returncode == 0, r.stderr.decode()[-400:]
+    with open(ref, "wb") as f:
+        r = subprocess.run([call_checks.REF, "gfa2vcf", "-i", gfa, "-P", "S001#1", "-t", "1"], stdout=f, stderr=subprocess.PIPE)
+    assert r.returncode == 0, r.stderr.decode()[-400:]
+    strip = lambda p: [l for l in open(p, "rb").read().split(b"\n") if not l.startswith(b"##fileDate")]
+    a, b = strip(ours), strip(ref)
+    assert len(a) > 375_000 and a == b, "cfg2 VCF differs from the reference"
+    d1, d2 = str(tmp_path / "p1"), str(tmp_path / "p2")
+    os.makedirs(d1); os.makedirs(d2)
+    assert subprocess.run([cli, "decompose", "-i", gfa, "-o", d1], capture_output=True).returncode == 0
+    assert subprocess.run([call_checks.REF, "decompose", "-i", gfa, "-o", d2, "-t", "1"], capture_output=True).returncode == 0
+    assert sorted(os.listdir(d1)) == sorted(os.listdir(d2)) == ["1.pvst"]
+    assert open(os.path.join(d1, "1.pvst"), "rb").read() == open(os.path.join(d2, "1.pvst"), "rb").read()
+
+
+def test_gpu_cfg3_mix_with_inversions_windows(gpu):
+    call_checks.require_ref()
+    import scale_run
+    g, prefix, width = scale_run.build("cfg3m")
+    assert len(g["ids"]) >= 1_000_000 and len(g["paths"]) == 90
+    s = api.Session.from_graph(gpu, g)
+    s.hot_path([prefix])
+    st = s.call_stats()
+    assert st["hard_errors"] == 0 and st["pin_pairs"] > 0 and st["tangled"] > 0, st
+    lines, _ = s.record_lines()
+    wins = scale_run.check_windows(g, lines, prefix, width, n_windows=8)
+    s.close()
+    assert all(w["bit_exact"] for w in wins), [w for w in wins if not w["bit_exact"]]
+    assert sum(w["tangled"] for w in wins) > 0 and sum(w["records_compared"] for w in wins) > 5_000
+    assert sum("VARTYPE=SUBR" in l for l in lines) > 0
