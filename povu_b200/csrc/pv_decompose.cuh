@@ -71,6 +71,8 @@ PV_KERNEL(K_start, 12);
 PV_KERNEL(K_claim, 28);
 PV_KERNEL(K_entry, 24);
 PV_KERNEL(K_first_edge, 28);
+PV_KERNEL(K_skip, 40);          // per port: its candidates + a bounded walk of the first-edge chain from each
+PV_KERNEL(K_skipcheck, 28);
 PV_KERNEL(K_mark, 24);         // J[x], J[J[x]], rnk[x] in, J'[x] out (+ the marks)
 PV_KERNEL(K_segconf, 12);
 PV_KERNEL(K_finalize, 36);
@@ -186,12 +188,12 @@ inline void decompose_device(Ctx &c, u32 V, u64 E, const u32 *ep1, const u32 *ep
 	Buf<u32> visited(c, V), uf(c, V), comp(c, V), gcomp(c, V), entrySide(c, V);
 	Buf<u32> parent(c, P), pslot(c, P), depth(c, P), F(c, P), Fslot(c, P), J(c, P), J2(c, P), rnk(c, P);
 	Buf<u64> claim(c, V);
-	Buf<u32> trunc(c, V), entDepth(c, V), tipPort(c, V), compStart(c, V), flag(c, 4);
+	Buf<u32> trunc(c, V), entDepth(c, V), entV(c, V), tipPort(c, V), compStart(c, V), flag(c, 4);
 	visited.zero(); parent.fill_ff(); pslot.fill_ff(); depth.zero();
 	u32 *visited_ = visited.p, *uf_ = uf.p, *comp_ = comp.p, *gcomp_ = gcomp.p, *entrySide_ = entrySide.p;
 	u32 *parent_ = parent.p, *pslot_ = pslot.p, *depth_ = depth.p, *F_ = F.p, *Fslot_ = Fslot.p, *rnk_ = rnk.p;
 	u64 *claim_ = claim.p;
-	u32 *trunc_ = trunc.p, *entDepth_ = entDepth.p, *tipPort_ = tipPort.p, *compStart_ = compStart.p, *flag_ = flag.p;
+	u32 *trunc_ = trunc.p, *entDepth_ = entDepth.p, *entV_ = entV.p, *tipPort_ = tipPort.p, *compStart_ = compStart.p, *flag_ = flag.p;
 
 	// tips of the WHOLE graph (from_gfa.cpp:262-277), decided on the original (un-rewritten) endpoints
 	parallel_for<K_tip>(c, V, PV_LAMBDA(size_t v) {
@@ -204,6 +206,8 @@ inline void decompose_device(Ctx &c, u32 V, u64 E, const u32 *ep1, const u32 *ep
 	{ u32 *a = active.p; parallel_for<K_iota>(c, V, PV_LAMBDA(size_t i) { a[i] = (u32)i; }); }
 
 	u32 round = 0;
+	bool repair = false;   // set by a round whose stripped path was cut short (see f')
+	static const u32 skip_walk = getenv("POVU_B200_SKIP_WALK") ? (u32)strtoul(getenv("POVU_B200_SKIP_WALK"), nullptr, 10) : 32u;   // 0 = never predict
 	while (nActive > 0) {
 		const u32 *act = active.p;
 		const u32 nA = nActive;
@@ -247,7 +251,7 @@ inline void decompose_device(Ctx &c, u32 V, u64 E, const u32 *ep1, const u32 *ep
 				u32 q0 = compStart_[v];
 				if (q0 == NONE) q0 = (u32)(2 * v);
 				compStart_[v] = q0;
-				rnk_[q0] = 0; entDepth_[v] = 1;          // virtual root has depth 0
+				rnk_[q0] = 0; entDepth_[v] = 1; entV_[v] = q0 >> 1;          // virtual root has depth 0
 				parent_[q0] = NONE; pslot_[q0] = NONE;   // parent = the component's virtual root
 			});
 		} else {
@@ -270,7 +274,7 @@ inline void decompose_device(Ctx &c, u32 V, u64 E, const u32 *ep1, const u32 *ep
 				u64 k = claim_[v];
 				u32 s = 0xFFFFFFFFu - (u32)(k & 0xFFFFFFFFu);
 				u32 p = adjOwner_[s], q0 = adjNbr_[s];
-				rnk_[q0] = 0; entDepth_[v] = (u32)(k >> 32) + 1;
+				rnk_[q0] = 0; entDepth_[v] = (u32)(k >> 32) + 1; entV_[v] = q0 >> 1;
 				parent_[q0] = p; pslot_[q0] = s;
 			});
 		}
@@ -284,9 +288,44 @@ inline void decompose_device(Ctx &c, u32 V, u64 E, const u32 *ep1, const u32 *ep
 			}
 			F_[x] = f; Fslot_[x] = fs;
 		});
+		// (f') repair mode.  The DFS takes the first edge to a segment that is unvisited WHEN IT GETS THERE; F above only knows
+		// what was unvisited when the round began, so an edge back to a segment earlier on the very path being stripped (the back
+		// link of a repeat unit, the far link of an inversion) makes the stripped path run into itself and the round ends there.
+		// A graph with thousands of such structures along one chain then needs thousands of rounds, each O(remaining graph).
+		// After a round that was cut short this way, the next rounds PREDICT those edges: candidate w of port x is skipped when a
+		// bounded walk of the first-edge chain from w reaches x (w comes before x on that chain) and w's index lies between the
+		// path's entry vertex and x (chains of several ports can merge: a walk from the far side of an inversion also reaches x;
+		// segment ids of real graphs follow the backbone, so the side the path came from is the one between entry and x).  The
+		// prediction only decides how far a round gets: every skipped candidate of every stripped node is verified afterwards (K_skipcheck: it
+		// really is earlier on the path), a failed check cuts the path right after that node, and an edge that should have been
+		// skipped but was not still ends the path at the self-intersection, exactly as before.
+		const u32 *Fuse_ = F_, *Fsuse_ = Fslot_;
+		Buf<u32> F1, Fslot1;
+		if (repair) {
+			F1 = Buf<u32>(c, P); Fslot1 = Buf<u32>(c, P);
+			u32 *F1_ = F1.p, *Fslot1_ = Fslot1.p;
+			const u32 WALK = skip_walk;
+			parallel_for<K_skip>(c, (size_t)nA * 2, PV_LAMBDA(size_t i) {
+				u32 v = act[i >> 1]; u32 x = 2 * v + (u32)(i & 1); u32 xb = x ^ 1u;
+				u32 f = NONE, fs = NONE;
+				const u32 q = entV_[comp_[v]]; const u32 lo = q < v ? q : v, hi = q < v ? v : q;
+				for (u32 s = adjOff_[xb], e = adjOff_[xb + 1]; s < e; s++) {
+					u32 y = adjNbr_[s]; u32 w = y >> 1;
+					if (w == v || visited_[w]) continue;
+					bool before = false;
+					for (u32 side = 0; side < 2 && !before && w >= lo && w <= hi; side++) {
+						u32 z = 2 * w + side;
+						for (u32 k = 0; k < WALK; k++) { z = F_[z]; if (z == NONE) break; if (z == x) { before = true; break; } }
+					}
+					if (!before) { f = y; fs = s; break; }
+				}
+				F1_[x] = f; Fslot1_[x] = fs;
+			});
+			Fuse_ = F1_; Fsuse_ = Fslot1_;
+		}
 		// (g) pointer-doubling path marking from every entry
 		{
-			c.d2d(J.p, F.p, (size_t)P * 4);
+			c.d2d(J.p, Fuse_, (size_t)P * 4);
 			u32 *Ja = J.p, *Jb = J2.p;
 			int maxIt = bits_for((u64)nA * 2) + 1;
 			// itFlag[it] = "iteration it marked something".  Later iterations test the previous flag on the device and fall
@@ -323,6 +362,20 @@ inline void decompose_device(Ctx &c, u32 V, u64 E, const u32 *ep1, const u32 *ep
 			u32 v = act[i]; u32 r0 = rnk_[2 * v], r1 = rnk_[2 * v + 1];
 			if (r0 != NONE && r1 != NONE) atomic_min(trunc_ + comp_[v], r0 > r1 ? r0 : r1);
 		});
+		if (repair) {   // every candidate that a stripped node skipped must lie earlier on the stripped path
+			parallel_for<K_skipcheck>(c, (size_t)nA * 2, PV_LAMBDA(size_t i) {
+				u32 v = act[i >> 1]; u32 x = 2 * v + (u32)(i & 1); u32 xb = x ^ 1u;
+				u32 r = rnk_[x]; u32 root = comp_[v];
+				if (r == NONE || r >= trunc_[root]) return;
+				const u32 fs = Fsuse_[x];
+				for (u32 s = adjOff_[xb], e = adjOff_[xb + 1]; s < e && s != fs; s++) {
+					u32 w = adjNbr_[s] >> 1;
+					if (w == v || visited_[w]) continue;
+					u32 r0 = rnk_[2 * w], r1 = rnk_[2 * w + 1]; u32 m = r0 < r1 ? r0 : r1;
+					if (!(m < r)) { atomic_min(trunc_ + root, r + 1); break; }   // wrong guess: x stays, its successor does not
+				}
+			});
+		}
 		parallel_for<K_finalize>(c, (size_t)nA * 2, PV_LAMBDA(size_t i) {
 			u32 v = act[i >> 1]; u32 x = 2 * v + (u32)(i & 1);
 			u32 r = rnk_[x]; u32 root = comp_[v];
@@ -331,21 +384,33 @@ inline void decompose_device(Ctx &c, u32 V, u64 E, const u32 *ep1, const u32 *ep
 			entrySide_[v] = x & 1u;
 			depth_[x] = d; depth_[x ^ 1u] = d + 1;
 			parent_[x ^ 1u] = x; pslot_[x ^ 1u] = NONE;
-			u32 y = F_[x];
-			if (y != NONE && rnk_[y] == r + 1 && r + 1 < trunc_[root]) { parent_[y] = x ^ 1u; pslot_[y] = Fslot_[x]; }
+			u32 y = Fuse_[x];
+			if (y != NONE && rnk_[y] == r + 1 && r + 1 < trunc_[root]) { parent_[y] = x ^ 1u; pslot_[y] = Fsuse_[x]; }
 		});
 		Buf<u32> still(c, nA);
 		u32 *still_ = still.p;
+		c.memset0(flag.p + 2, 4);
 		parallel_for<K_visit>(c, nA, PV_LAMBDA(size_t i) {
 			u32 v = act[i]; u32 root = comp_[v]; u32 t = trunc_[root];
 			u32 r0 = rnk_[2 * v], r1 = rnk_[2 * v + 1];
 			bool vis = (r0 != NONE && r0 < t) || (r1 != NONE && r1 < t);
 			still_[i] = vis ? 0u : 1u;
+			if (root == v && t != NONE) flag_[2] = 1;   // a stripped path was cut short
 		});
 		// visited[] is written only after every kernel of this round that reads it has finished
 		parallel_for<K_visit>(c, nA, PV_LAMBDA(size_t i) { if (!still_[i]) visited_[act[i]] = 1; });
-		Buf<u32> idx;
-		u32 nNext = compact_flags(c, still.p, nA, idx);
+		Buf<u32> idx, idxPos;
+		u32 nNext = 0, cut = 0;
+		{ MultiRead mr(c); compact_flags(c, still.p, nA, idx, &idxPos, &mr, &nNext); mr.add(&cut, flag.p + 2, 4); mr.wait(); }
+#ifdef PV_EMU
+		if (getenv("PV_DEBUG")) {
+			fprintf(stderr, "[dfs] round %u: active %u -> %u, repair %d, cut %u;", round, nA, nNext, (int)repair, cut);
+			for (u32 i = 0; i < nA && i < 48; i++) { u32 v = act[i]; if (comp_[v] == v && trunc_[v] != NONE) fprintf(stderr, " comp %u trunc %u", v, trunc_[v]); }
+			fprintf(stderr, "\n");
+			if (nA <= 40) for (u32 i = 0; i < nA; i++) { u32 v = act[i]; fprintf(stderr, "   v%u: rnkL %d rnkR %d F0L %d F0R %d FL %d FR %d comp %u\n", v, (int)rnk_[2 * v], (int)rnk_[2 * v + 1], (int)F_[2 * v], (int)F_[2 * v + 1], (int)Fuse_[2 * v], (int)Fuse_[2 * v + 1], comp_[v]); }
+		}
+#endif
+		repair = cut != 0 && skip_walk != 0;
 		Buf<u32> nextActive(c, nNext ? nNext : 1);
 		{ u32 *na = nextActive.p; const u32 *ix = idx.p; parallel_for<K_active>(c, nNext, PV_LAMBDA(size_t i) { na[i] = act[ix[i]]; }); }
 		active = std::move(nextActive);

@@ -775,8 +775,10 @@ inline void list_rank_suffix(Ctx &c, const u32 *next, const u32 *weight, u32 *ra
 // ---------------------------------------------------------------------------------------------
 PV_KERNEL(K_compact_scatter, 12);
 // keep_pos (optional) receives the exclusive scan of the flags (n + 1 entries): rank of every index among the kept ones
-inline u32 compact_flags(Ctx &c, const u32 *flags, size_t n, Buf<u32> &out, Buf<u32> *keep_pos = nullptr) {
-	if (n == 0) { out = Buf<u32>(c, 1); if (keep_pos) { *keep_pos = Buf<u32>(c, 1); keep_pos->zero(); } return 0; }
+// mr (optional): the count is not read here but queued on the caller's MultiRead into *cnt_dst (valid after mr->wait(); keep_pos
+// must be given and stay alive until then) -- several small results then share one host wait
+inline u32 compact_flags(Ctx &c, const u32 *flags, size_t n, Buf<u32> &out, Buf<u32> *keep_pos = nullptr, MultiRead *mr = nullptr, u32 *cnt_dst = nullptr) {
+	if (n == 0) { out = Buf<u32>(c, 1); if (keep_pos) { *keep_pos = Buf<u32>(c, 1); keep_pos->zero(); } if (cnt_dst) *cnt_dst = 0; return 0; }
 	Buf<u32> pos(c, n + 1);
 	exclusive_scan(c, flags, pos.p, n, OpAddU32(), 0u);
 	out = Buf<u32>(c, n);     // capacity n: the count is known only after the scatter (one host read instead of two)
@@ -786,6 +788,12 @@ inline u32 compact_flags(Ctx &c, const u32 *flags, size_t n, Buf<u32> &out, Buf<
 		if (f) o[p[i]] = (u32)i;
 		if (i == n - 1) p[n] = p[i] + (f ? 1u : 0u);
 	});
+	if (mr) {
+		if (!keep_pos || !cnt_dst) throw std::runtime_error("compact_flags: a deferred count needs keep_pos and cnt_dst");
+		*keep_pos = std::move(pos);
+		mr->add(cnt_dst, keep_pos->p + n, 4);
+		return 0;
+	}
 	const u32 cnt = pos.read(n);
 	if (keep_pos) *keep_pos = std::move(pos);
 	return cnt;

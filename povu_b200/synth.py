@@ -565,3 +565,16 @@ def reverse_paths(g, which):
     out = dict(g)
     out["paths"] = paths
     return out
+
+
+def permute_vertices(g, seed):
+    """The same graph with its vertices renumbered at random (ids stay 1..V in index order): segment ids then no longer follow
+    the backbone -- the decompose heuristics that look at id order must stay exact (they may only cost extra rounds)."""
+    rng = _rng(seed)
+    V = len(g["ids"])
+    perm = rng.permutation(V).astype(np.int64)          # old index -> new index
+    inv = np.empty(V, dtype=np.int64); inv[perm] = np.arange(V)
+    seqs = [g["seqs"][int(i)] for i in inv] if g["seqs"] is not None else None
+    L = np.stack([perm[g["v1"].astype(np.int64)], g["s1"].astype(np.int64), perm[g["v2"].astype(np.int64)], g["s2"].astype(np.int64)], 1)
+    paths = [(n, perm[st.astype(np.int64)].astype(np.uint32), sr) for n, st, sr in g["paths"]]
+    return make_graph(g["ids"], seqs, L, paths)

@@ -28,6 +28,17 @@ def test_gpu_random_families(gpu):
         _check(gpu, synth.nested_bubbles(500 + s, n_top=40, max_depth=5, shuffle_links=(s % 2 == 1)))
 
 
+def test_gpu_dfs_repair_mode(gpu):
+    """Repeat units / inversion bubbles / reverse-strand blocks along one chain (see tests/test_emu_decompose.py): exact vs the
+    oracle with ids that follow the backbone (few DFS rounds) and with the vertices renumbered at random (any number)."""
+    T = synth.cfg3_templates(seed=7, n_nested=6, tower_depth=8, p_inv=0.1, n_repeat=2) + [synth.inversion_unit(k, inner=1 + k % 3) for k in range(4)]
+    for seed in range(4):
+        g = synth.tiled(T, 150, 4, seed=seed)
+        f = _check(gpu, g)
+        assert f.dfs_rounds <= 12, f.dfs_rounds
+        _check(gpu, synth.permute_vertices(g, 100 + seed))
+
+
 def test_gpu_edge_cases(gpu):
     one = synth.make_graph([5], ["A"], np.zeros((0, 4)), [])
     assert gpu.decompose(1, *api.edge_ports(one)).n == 0

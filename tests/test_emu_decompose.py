@@ -36,6 +36,25 @@ def test_emu_random_families(emu_lib, order):
     _check(pv, synth.snp_indel_chain(2000, n_paths=2, seed=9, with_seqs=False))
 
 
+def _cyclic_mix(n_inst, seed):
+    T = synth.cfg3_templates(seed=7, n_nested=6, tower_depth=8, p_inv=0.1, n_repeat=2) + [synth.inversion_unit(k, inner=1 + k % 3) for k in range(4)]
+    return synth.tiled(T, n_inst, 4, seed=seed)
+
+
+@pytest.mark.parametrize("order", [0, 2])
+def test_emu_dfs_repair_mode(emu_lib, order):
+    """Repeat units, inversion bubbles and reverse-strand blocks along one chain: a stripped DFS path runs into itself at every
+    one of them, so without the skip prediction (pv_decompose.cuh, f') the tree takes one round per structure.  Exact either
+    way; with ids that follow the backbone a handful of rounds must do.  With the vertices renumbered at random the id-order
+    part of the prediction is useless or wrong -- results must still be exact (the verification cuts wrong guesses)."""
+    pv = _ctx(emu_lib, order)
+    for seed in range(3):
+        g = _cyclic_mix(40, seed)
+        f = _check(pv, g)
+        assert f.dfs_rounds <= 12, f.dfs_rounds
+        _check(pv, synth.permute_vertices(g, 100 + seed))
+
+
 @pytest.mark.parametrize("name", helpers.POSITIVE + helpers.SYNTHETIC + ["LPA"])
 def test_emu_golden_pvst(emu_lib, name, tmp_path):
     pv = _ctx(emu_lib, 0)
