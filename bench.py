@@ -48,6 +48,9 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gfa-leg", action="store_true", help="skip the GFA text -> HBM leg (device parser) reported under gfa_text")
     ap.add_argument("--profile-steps", type=int, default=2)
+    ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling leg (whole-genome-shaped graph sharded over the ranks)")
+    ap.add_argument("--wg-instances", type=int, default=300_000, help="template instances of the whole-genome-shaped graph (300 k = 14.3 M segments / 20.2 M links)")
+    ap.add_argument("--wg-paths", type=int, default=24, help="haplotype paths per component of that graph")
     return ap.parse_args()
 
 
@@ -216,6 +219,134 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------------
+# strong scaling: ONE whole-genome-shaped graph, its components partitioned over the ranks (north_star / SURVEY.md 8e)
+# ----------------------------------------------------------------------------------------------
+GRCH38 = [248956422, 242193529, 198295559, 190214555, 181538259, 170805979, 159345973, 145138636, 138394717, 133797422, 135086622, 133275309,
+          114364328, 107043718, 101991189, 90338345, 83257441, 80373285, 58617616, 64444167, 46709983, 50818468, 156040895, 57227415, 16569]
+
+
+def wg_graph(instances, paths):
+    """cfg4's shape: 25 weakly connected components with sizes proportional to GRCh38 chr1-22, X, Y, M; SNP / indel
+    runs with ~10 % nested templates; `paths` haplotype paths per component.  Deterministic: every rank builds the same graph."""
+    from povu_b200 import synth
+    tpl = [synth.template_from(synth.snp_indel_chain(6, n_paths=6, seed=100 + k)) for k in range(18)] + synth.cfg3_templates(seed=7, n_nested=2, tower_depth=0)
+    return synth.tiled(tpl, instances, paths, seed=11, n_components=25, comp_weights=GRCH38)
+
+
+def run_strong(args, pv, stream, rank, world, torch, dist):
+    """value: device-timed step on the resident shard (one decompose + index per step, then one call per owned component against
+    that component's reference path -- a region is only called where EVERY selected reference runs, so the reference too needs one
+    run per chromosome).  e2e: the same from the page-locked host arrays of the WHOLE graph: host -> HBM, partition on the device
+    (pvgpu_session_reshard), hot path, the binary records packed in HBM and gathered to rank 0 over NCCL."""
+    from povu_b200 import api
+    t0 = time.perf_counter()
+    g = wg_graph(args.wg_instances, args.wg_paths)
+    V, E = len(g["ids"]), len(g["v1"])
+    S = sum(len(p[1]) for p in g["paths"])
+    gen_s = time.perf_counter() - t0
+    sess = api.Session.from_graph(pv, g, with_labels=False)
+    del g
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def owned_refs():
+        ga = sess.graph_arrays(labels=False)
+        return [n for k, n in enumerate(ga["path_names"]) if n.startswith("S001#1#") and ga["step_off"][k + 1] > ga["step_off"][k]]
+
+    n_comp, shard_ms0 = sess.reshard(rank, world)
+    v_, e_, h_, st_ = sess.sizes()
+    own = owned_refs()
+    buf = torch.empty(64 << 20, dtype=torch.uint8, device="cuda")
+
+    def step(keep, pack):
+        nonlocal buf
+        nrec = used = 0
+        for i, pfx in enumerate(own):
+            if i == 0:
+                sess.hot_path([pfx], keep_resident=keep)
+            else:
+                sess.call([pfx])
+            nrec += int(sess.lib.pvgpu_session_record_count(sess.h))
+            if pack:
+                need = sess.records_packed_bytes()
+                if used + need > buf.numel():
+                    nb = torch.empty(max(2 * buf.numel(), used + need), dtype=torch.uint8, device="cuda")
+                    nb[:used] = buf[:used]; buf = nb
+                used += sess.records_pack(buf.data_ptr() + used, buf.numel() - used)
+        return nrec, used
+
+    with torch.cuda.stream(stream):
+        for _ in range(args.warmup):
+            step(True, False)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(args.steps):
+            nrec, _ = step(True, False)
+        e1.record(stream)
+        barrier()
+        dev_ms = e0.elapsed_time(e1) / args.steps
+        nfl = int(sess.lib.pvgpu_session_flubble_count(sess.h))
+
+        # end to end: whole graph on the host -> partition -> hot path -> packed records -> gather on rank 0
+        def e2e_step():
+            t_sh = 0.0
+            if world > 1:
+                _, t_sh = sess.reshard(rank, world, from_host=True)
+            nrec, used = step(world > 1, True) if world > 1 else step(False, True)
+            sizes = torch.tensor([used], dtype=torch.int64, device="cuda")
+            gathered = 0
+            if world > 1:
+                all_sizes = [torch.zeros_like(sizes) for _ in range(world)]
+                dist.all_gather(all_sizes, sizes)
+                mx = int(max(int(x.item()) for x in all_sizes))
+                send = buf[:mx] if buf.numel() >= mx else torch.cat([buf, torch.empty(mx - buf.numel(), dtype=torch.uint8, device="cuda")])
+                recv = [torch.empty(mx, dtype=torch.uint8, device="cuda") for _ in range(world)] if rank == 0 else None
+                dist.gather(send, recv, dst=0)
+                gathered = sum(int(x.item()) for x in all_sizes)
+            else:
+                gathered = used
+            return t_sh, used, gathered
+        for _ in range(min(2, args.warmup)):
+            e2e_step()
+        barrier()
+        n_e2e = max(3, min(args.steps, 5))
+        t0 = time.perf_counter()
+        sh = []
+        for _ in range(n_e2e):
+            t_sh, used, gathered = e2e_step()
+            sh.append(t_sh)
+        barrier()
+        e2e_ms = (time.perf_counter() - t0) * 1e3 / n_e2e
+
+    t = torch.tensor([dev_ms, e2e_ms, sum(sh) / len(sh)], dtype=torch.float64, device="cuda")
+    cnt = torch.tensor([nrec, nfl, e_], dtype=torch.float64, device="cuda")
+    share = torch.tensor([float(e_ + st_ + v_)], dtype=torch.float64, device="cuda")
+    shares = [torch.zeros_like(share) for _ in range(world)]
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+        dist.all_gather(shares, share)
+    else:
+        shares = [share]
+    sess.close()
+    w = [float(x.item()) for x in shares]
+    dev_ms, e2e_ms, shard_ms = t.tolist()
+    return {"workload": f"wg_25c (cfg4 shape): 25 components ~ GRCh38 chromosome sizes, {args.wg_instances} template instances, {args.wg_paths} paths per component",
+            "scaling": "strong", "n_gpus": world, "segments": V, "links": E, "path_steps": S, "components": n_comp,
+            "value": E / (dev_ms * 1e-3), "unit": "edges/s", "ms_per_step": dev_ms, "steps": args.steps,
+            "records_all_ranks": int(cnt[0].item()), "flubbles_all_ranks": int(cnt[1].item()), "links_all_ranks": int(cnt[2].item()),
+            "lpt_load_max_over_mean": max(w) / (sum(w) / len(w)), "calls_per_step_rank0": len(own),
+            "e2e": {"value": E / (e2e_ms * 1e-3), "unit": "edges/s", "ms_per_step": e2e_ms, "steps": n_e2e, "shard_ms_max_over_ranks": shard_ms,
+                    "h2d_bytes_per_step_per_rank": 8 * E + 4 * S + 8 * V, "gathered_record_bytes": int(gathered),
+                    "note": "per step and rank: whole graph host -> HBM, device partition (labels, weights, compaction), decompose + index + one call per owned component, binary records packed in HBM; then all ranks' streams gathered on rank 0 over NCCL (N = 1: no partition, no gather)"},
+            "graph_generation_s": gen_s}
+
+
+# ----------------------------------------------------------------------------------------------
 # native arm
 # ----------------------------------------------------------------------------------------------
 def run_native(args):
@@ -346,6 +477,13 @@ def run_native(args):
             prof = pv.profile()
             pv.set_profiling(False)
 
+    strong = None
+    if not args.no_strong:
+        sess.close()
+        try:
+            strong = run_strong(args, pv, stream, rank, world, torch, dist)
+        except Exception as ex:      # reported, never fatal for the headline line
+            strong = {"error": str(ex)[:300]}
     t_dev = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
     cnt = torch.tensor([n_rec, n_fl], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -410,7 +548,7 @@ def run_native(args):
                         "ms_per_step": e2e_ms_max / e2e_steps, "steps": e2e_steps,
                         "vcf_text": {"bytes": text_bytes, "ms": text_s * 1e3, "note": "record lines written by the device text kernels (X_len, X_write), D2H into a page-locked buffer, write(2) to /dev/null; wall time of one pvgpu_session_vcf_write call, not inside e2e (SURVEY.md 8f2)"}},
                 "gfa_text": gfa_leg, "gpu_launches": int(launches), "host_syncs_per_step": host_syncs / args.steps, "wall_s_timed_region": wall,
-                "clocks": clk, "roofline": roofline, "cpu_baseline": cpu, "peak_device_bytes": pv.peak_bytes}
+                "clocks": clk, "roofline": roofline, "cpu_baseline": cpu, "strong_scaling": strong, "peak_device_bytes": pv.peak_bytes}
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

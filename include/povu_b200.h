@@ -160,6 +160,16 @@ int pvgpu_session_vcf_write(const pvgpu_session *s, size_t chunk_size, int with_
  * the per-rank outputs concatenate into exactly the single-GPU output.  No exchange happens while computing; the only
  * communication is the final gather of record lines (povu_b200/dist.py does it with torch.distributed). */
 int pvgpu_session_shard(pvgpu_session *s, uint32_t rank, uint32_t world, uint32_t *n_components_total);
+/* The same, repeatable: the first call sets the whole graph aside (host arrays + a copy in HBM); every call cuts this rank's share
+ * out of it ON THE DEVICE (component labels, per-component weights, compaction of segments / links / walks; only the handful of
+ * component weights visit the host for the greedy balance).  from_host != 0 drops the device copy of the whole graph first, so
+ * that the call also pays its host -> HBM transfer from the page-locked arrays (the end-to-end step of bench.py).  ms = wall time. */
+/* The binary records of the last call as one self-describing stream written into caller-provided DEVICE memory (layout:
+ * pv_engine.hpp "records_pack"; context steps carry segment ids, so streams of different shards can be concatenated).  This is
+ * what a rank hands to the final NCCL gather of a multi-GPU run. */
+uint64_t pvgpu_session_records_packed_bytes(const pvgpu_session *s);
+int pvgpu_session_records_pack(pvgpu_session *s, void *dst_device, uint64_t capacity, uint64_t *bytes);
+int pvgpu_session_reshard(pvgpu_session *s, uint32_t rank, uint32_t world, int from_host, uint32_t *n_components_total, double *ms);
 /* after call: per PVST tree of this session its component id and the number of regions that reached the overlay */
 void pvgpu_session_tree_regions(const pvgpu_session *s, uint32_t *comp_id, uint64_t *n_regions);
 /* after call: all records as VCF text lines (malloc'ed, pvgpu_free) with line_off[n+1] and keys[3n] =

@@ -113,6 +113,12 @@ def load_library(lib_path=None):
     lib.pvgpu_free.argtypes = [vp]
     lib.pvgpu_session_shard.argtypes = [vp, u32, u32, C.POINTER(u32)]
     lib.pvgpu_session_shard.restype = C.c_int
+    lib.pvgpu_session_records_packed_bytes.argtypes = [vp]
+    lib.pvgpu_session_records_packed_bytes.restype = u64
+    lib.pvgpu_session_records_pack.argtypes = [vp, vp, u64, C.POINTER(u64)]
+    lib.pvgpu_session_records_pack.restype = C.c_int
+    lib.pvgpu_session_reshard.argtypes = [vp, u32, u32, C.c_int, C.POINTER(u32), C.POINTER(C.c_double)]
+    lib.pvgpu_session_reshard.restype = C.c_int
     lib.pvgpu_session_tree_regions.argtypes = [vp, vp, vp]
     lib.pvgpu_session_record_lines.argtypes = [vp, C.POINTER(sz), C.POINTER(vp), C.POINTER(vp), C.POINTER(sz)]
     lib.pvgpu_session_record_lines.restype = vp
@@ -430,6 +436,22 @@ class Session:
         n = C.c_uint32()
         self._check(self.lib.pvgpu_session_shard(self.h, rank, world, C.byref(n)))
         return int(n.value)
+
+    def records_packed_bytes(self):
+        return int(self.lib.pvgpu_session_records_packed_bytes(self.h))
+
+    def records_pack(self, dst_device_ptr, capacity):
+        """The binary records of the last call as one stream in caller-provided device memory; returns the byte count."""
+        n = C.c_uint64()
+        self._check(self.lib.pvgpu_session_records_pack(self.h, C.c_void_p(dst_device_ptr), int(capacity), C.byref(n)))
+        return int(n.value)
+
+    def reshard(self, rank, world, from_host=False):
+        """Repeatable shard(): cuts this rank's share out of the whole graph on the device; from_host=True re-uploads the whole
+        graph from the page-locked host arrays first.  Returns (components of the whole graph, wall ms)."""
+        n, ms = C.c_uint32(), C.c_double()
+        self._check(self.lib.pvgpu_session_reshard(self.h, rank, world, int(from_host), C.byref(n), C.byref(ms)))
+        return int(n.value), float(ms.value)
 
     def tree_regions(self):
         """{component id: number of regions that reached the overlay} for this session's PVST trees."""

@@ -13,7 +13,7 @@
 // Device data layout (DESIGN.md "call: HBM layout"):
 //   steps[S]      packed path steps, paths concatenated in P-line order: (vertex idx << 1) | strand
 //   stepOff[H+1]  first step of every path;  loci[S] 1-based start coordinate of every step
-//   vsOff[V+1], vsStep[S], vsHap[S]   per-vertex list of the (global) steps that visit it, ascending --
+//   vsOff[V+1], vsStep[S], vsHap[S]   per-vertex list of the (global) steps that visit it, ascending; vsHap = (path << 1) | strand --
 //                 since paths are concatenated in hap order this is also (hap, local step) order, i.e. the
 //                 reference's vertex_to_step_matrix_ flattened (bidirected.cpp:347-355)
 //   adjOff[2V+1], adjNbr[..]          per-port neighbour ports in ascending L-line order (bidirected.hpp:68-69)
@@ -184,7 +184,9 @@ inline void graph_build(Ctx &c, u32 V, u64 E, const u32 *ep1, const u32 *ep2, u3
 		if (const char *e = getenv("POVU_B200_VS_SMALL")) vs_small = (u32)strtoul(e, nullptr, 10);   // tests: force the hub path
 		u32 *vsStep_ = g.vsStep.p, *vsHap_ = g.vsHap.p;
 		group_indices(c, StepVertex{steps_}, S, V, g.vsOff.p, g.vsStep.p, vs_small);
-		parallel_for<C_vs_hap>(c, S, PV_LAMBDA(size_t i) { vsHap_[i] = ub_u32(stepOff_, 0, H + 1, vsStep_[i]) - 1; });
+		// (path << 1) | strand next to every entry: the depth matrix needs the strand per visit, and reading it here (one pass, the
+		// step index at hand) is cheaper than a random access per matrix cell later
+		parallel_for<C_vs_hap>(c, S, PV_LAMBDA(size_t i) { u32 st = vsStep_[i]; vsHap_[i] = ((ub_u32(stepOff_, 0, H + 1, st) - 1) << 1) | (steps_[st] & 1u); });
 	}
 	tr.mark("loci + vertex->steps");
 	// ---- weakly connected components -> the paths of every component
@@ -1250,7 +1252,7 @@ inline void tangled_pass(Ctx &c, const DevGraph &G, const GraphView &g, const Ca
 		u32 t = ub_u32(tColPre_, 0, nT + 1, (u32)x) - 1; u32 r = tList_[t]; u32 j = (u32)x - tColPre_[t];
 		u32 v = rv.vert(r, j); u32 comp = rv.comp(r);
 		for (u32 e = g.vsOff[v], ee = g.vsOff[v + 1]; e < ee; e++) {
-			u32 h = g.vsHap[e];
+			u32 h = g.vsHap[e] >> 1;
 			if (g.pathComp[h] == comp) atomic_add(sCnt_ + tRowPre_[t] + g.hapLocal[h], 1u);
 		}
 	});
@@ -1262,7 +1264,7 @@ inline void tangled_pass(Ctx &c, const DevGraph &G, const GraphView &g, const Ca
 		u32 t = ub_u32(tColPre_, 0, nT + 1, (u32)x) - 1; u32 r = tList_[t]; u32 j = (u32)x - tColPre_[t];
 		u32 v = rv.vert(r, j); u32 comp = rv.comp(r);
 		for (u32 e = g.vsOff[v], ee = g.vsOff[v + 1]; e < ee; e++) {
-			u32 h = g.vsHap[e];
+			u32 h = g.vsHap[e] >> 1;
 			if (g.pathComp[h] != comp) continue;
 			u32 row = tRowPre_[t] + g.hapLocal[h];
 			sList_[sOff_[row] + atomic_add(cursor_ + row, 1u)] = g.vsStep[e];
@@ -1604,7 +1606,7 @@ inline void call_device(Ctx &c, const DevGraph &G, const CallIn &in, const CallO
 		// component of the region = component of any path through its start boundary (a selected region is
 		// touched by every reference path)
 		u32 a = fa_[f] >> 1;
-		u32 comp = g.pathComp[g.vsHap[g.vsOff[a]]];
+		u32 comp = g.pathComp[g.vsHap[g.vsOff[a]] >> 1];
 		rovComp_[r] = comp;
 		u32 nh = g.cpOff[comp + 1] - g.cpOff[comp];
 		rowsOf_[r] = nh; cellsOf_[r] = (u64)nh * n;
@@ -1703,13 +1705,13 @@ inline void call_device(Ctx &c, const DevGraph &G, const CallIn &in, const CallO
 			u32 comp = rv.comp(r);
 			u32 e = g.vsOff[v], ee = g.vsOff[v + 1];
 			while (e < ee) {
-				u32 h = g.vsHap[e]; u32 first = g.vsStep[e]; u32 n = 1;
-				while (e + n < ee && g.vsHap[e + n] == h) n++;
+				const u32 hs = g.vsHap[e]; u32 h = hs >> 1; u32 first = g.vsStep[e]; u32 n = 1;
+				while (e + n < ee && (g.vsHap[e + n] >> 1) == h) n++;
 				e += n;
 				if (g.pathComp[h] != comp) continue;   // cannot happen for a connected walk; keeps indexing safe
 				u32 i = g.hapLocal[h];
 				if (n > 0xFFFEu) { atomic_add(cv.errs + 2, 1u); n = 0xFFFEu; }
-				u32 code = n == 1 ? ((g.steps[first] & 1u) ? 2u : 1u) : n;
+				u32 code = n == 1 ? ((hs & 1u) ? 2u : 1u) : n;
 				cv.mat[rv.matBase(r) + (u64)i * J + j] = (u16)code;
 				atomic_min(cv.lapStart + rv.rowBase(r) + i, first);
 				if (n > 1 && (j == 0 || j == J - 1) && atomic_exch(cv.tangled + r, 1u) == 0) atomic_add(cv.errs + 3, 1u);
@@ -1723,14 +1725,14 @@ inline void call_device(Ctx &c, const DevGraph &G, const CallIn &in, const CallO
 			u32 comp = rv.comp(r);
 			const u32 a = g.vsOff[v], ee = g.vsOff[v + 1];
 			for (u32 e = a + lane; e < ee; e += LW) {
-				u32 h = g.vsHap[e];
-				if (e > a && g.vsHap[e - 1] == h) continue;   // not the head of its run
+				const u32 hs = g.vsHap[e]; u32 h = hs >> 1;
+				if (e > a && (g.vsHap[e - 1] >> 1) == h) continue;   // not the head of its run
 				u32 first = g.vsStep[e]; u32 n = 1;
-				while (e + n < ee && g.vsHap[e + n] == h) n++;
+				while (e + n < ee && (g.vsHap[e + n] >> 1) == h) n++;
 				if (g.pathComp[h] != comp) continue;   // cannot happen for a connected walk; keeps indexing safe
 				u32 i = g.hapLocal[h];
 				if (n > 0xFFFEu) { atomic_add(cv.errs + 2, 1u); n = 0xFFFEu; }
-				u32 code = n == 1 ? ((g.steps[first] & 1u) ? 2u : 1u) : n;
+				u32 code = n == 1 ? ((hs & 1u) ? 2u : 1u) : n;
 				cv.mat[rv.matBase(r) + (u64)i * J + j] = (u16)code;
 				atomic_min(cv.lapStart + rv.rowBase(r) + i, first);
 				if (n > 1 && (j == 0 || j == J - 1) && atomic_exch(cv.tangled + r, 1u) == 0) atomic_add(cv.errs + 3, 1u);

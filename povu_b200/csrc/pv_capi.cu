@@ -406,6 +406,13 @@ int pvgpu_session_vcf_write(const pvgpu_session *s, size_t chunk, int with_date,
 int pvgpu_session_shard(pvgpu_session *s, uint32_t rank, uint32_t world, uint32_t *n_total) {
 	PV_TRY(s->x, { s->s.shard(rank, world); if (n_total) *n_total = s->s.n_comp_total; })
 }
+int pvgpu_session_reshard(pvgpu_session *s, uint32_t rank, uint32_t world, int from_host, uint32_t *n_total, double *ms) {
+	PV_TRY(s->x, { s->s.shard(rank, world, from_host != 0); if (n_total) *n_total = s->s.n_comp_total; if (ms) *ms = s->s.t_shard_ms; })
+}
+uint64_t pvgpu_session_records_packed_bytes(const pvgpu_session *s) { return s->s.records_packed_bytes(); }
+int pvgpu_session_records_pack(pvgpu_session *s, void *dst_device, uint64_t capacity, uint64_t *bytes) {
+	PV_TRY(s->x, { pv::u64 b = 0; s->s.records_pack(dst_device, capacity, &b); if (bytes) *bytes = b; })
+}
 void pvgpu_session_tree_regions(const pvgpu_session *s, uint32_t *comp_id, uint64_t *n_regions) {
 	std::vector<uint64_t> n = s->s.regions_per_tree();
 	for (size_t t = 0; t < n.size(); t++) { if (comp_id) comp_id[t] = s->s.forest.comp_id[t]; if (n_regions) n_regions[t] = n[t]; }

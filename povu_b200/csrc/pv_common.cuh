@@ -119,6 +119,7 @@ struct Ctx {
 	u64 *lb_pack = nullptr;                                                  // flat scan of 4-byte elements: (epoch << 32 | aggregate) per tile, written by that kernel only
 	u64 *rs_status = nullptr; size_t rs_cap = 0;                             // sort: per (tile, digit) status
 	u32 *lb_ticket = nullptr;                                                // [0] scan tile ticket, [1] sort tile ticket (self-resetting)
+	u32 *grid_bar = nullptr;                                                 // grid-wide barrier of the cooperative kernels: arrivals, generation
 	u32 lb_epoch = 0;
 	u32 next_epoch();
 	void lb_reserve(size_t tiles);
@@ -223,6 +224,7 @@ inline void Ctx::destroy() {
 	if (lb_flags) { cudaFree(lb_flags); cudaFree(lb_vals); cudaFree(lb_pack); lb_flags = nullptr; lb_vals = nullptr; lb_pack = nullptr; lb_cap = 0; }
 	if (rs_status) { cudaFree(rs_status); rs_status = nullptr; rs_cap = 0; }
 	if (lb_ticket) { cudaFree(lb_ticket); lb_ticket = nullptr; }
+	if (grid_bar) { cudaFree(grid_bar); grid_bar = nullptr; }
 	if (copy_stream) { cudaStreamDestroy(copy_stream); cudaEventDestroy(copy_ev); copy_stream = nullptr; copy_ev = nullptr; }
 	if (up_stream) { cudaStreamDestroy(up_stream); cudaEventDestroy(up_ev); up_stream = nullptr; up_ev = nullptr; }
 	if (h_scratch) { PinnedPool::inst().put(h_scratch); h_scratch = nullptr; }
@@ -536,6 +538,9 @@ PV_DEV u32 atomic_or(u32 *p, u32 v) { return atomicOr(p, v); }
 PV_DEV u64 atomic_xor(u64 *p, u64 v) { return (u64)atomicXor((unsigned long long *)p, (unsigned long long)v); }
 PV_DEV u32 atomic_exch(u32 *p, u32 v) { return atomicExch(p, v); }
 PV_DEV u32 ld_volatile(const u32 *p) { return *(const volatile u32 *)p; }
+// L2 loads for data that another CTA wrote earlier in the SAME kernel (sweeps of parallel_iter): never served from this SM's L1
+PV_DEV u32 ld_cg(const u32 *p) { return __ldcg(p); }
+PV_DEV u64 ld_cg(const u64 *p) { return (u64)__ldcg((const unsigned long long *)p); }
 #else
 template <class T> inline T atomic_add(T *p, T v) { T o = *p; *p = o + v; return o; }
 template <class T> inline T atomic_min(T *p, T v) { T o = *p; if (v < o) *p = v; return o; }
@@ -545,6 +550,8 @@ inline u32 atomic_or(u32 *p, u32 v) { u32 o = *p; *p = o | v; return o; }
 inline u64 atomic_xor(u64 *p, u64 v) { u64 o = *p; *p = o ^ v; return o; }
 inline u32 atomic_exch(u32 *p, u32 v) { u32 o = *p; *p = v; return o; }
 inline u32 ld_volatile(const u32 *p) { return *p; }
+inline u32 ld_cg(const u32 *p) { return *p; }
+inline u64 ld_cg(const u64 *p) { return *p; }
 #endif
 
 // counter increment where many threads of a warp hit the same counter (e.g. one giant component): lanes with the
@@ -600,6 +607,57 @@ template <class Tag, class F> inline void parallel_for(Ctx &c, size_t n, F f) {
 		while (gcd(a, n) != 1) a++;
 		u64 b = (c.emu_seed++ * 0xD1B54A32D192ED03ull) % n;
 		for (size_t i = 0; i < n; i++) f((size_t)(((unsigned __int128)a * i + b) % n));
+	}
+}
+#endif
+
+// ---------------------------------------------------------------------------------------------
+// parallel_iter: up to `iters` dependent sweeps over [0, n) in ONE cooperative launch, a grid-wide barrier between sweeps
+// (pointer doubling: every sweep is one doubling step; as separate launches each step pays launch + drain, ~4 us of a ~13 us
+// step at cfg2).  f(i, it) does the work of item i in sweep it; `live` (optional, device, iters words, zeroed by the caller):
+// a sweep that did something sets live[it]; the loop ends after the first sweep that leaves its word zero.
+// The grid is sized to what is co-resident (occupancy query), as cudaLaunchCooperativeKernel requires.
+// ---------------------------------------------------------------------------------------------
+#ifndef PV_EMU
+__device__ __forceinline__ void grid_barrier(u32 *bar /* [0] arrivals, [1] generation */, u32 nblocks) {
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		__threadfence();
+		const u32 g = *(volatile u32 *)(bar + 1);
+		if (atomicAdd(bar, 1u) == nblocks - 1) { atomicExch(bar, 0u); __threadfence(); atomicAdd(bar + 1, 1u); }
+		else { while (*(volatile u32 *)(bar + 1) == g) { } }
+		__threadfence();
+	}
+	__syncthreads();
+}
+template <class Tag, class F> __global__ void __launch_bounds__(256) pi_kernel(size_t n, int iters, F f, const u32 *live, u32 *bar) {
+	const size_t stride = (size_t)gridDim.x * blockDim.x;
+	for (int it = 0; it < iters; it++) {
+		for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) f(i, it);
+		if (it + 1 == iters) break;
+		grid_barrier(bar, gridDim.x);
+		if (live && *(volatile const u32 *)(live + it) == 0) break;   // (every thread reads the same word after the barrier)
+	}
+}
+template <class Tag, class F> inline void parallel_iter(Ctx &c, size_t n, int iters, F f, const u32 *live = nullptr) {
+	if (n == 0 || iters <= 0) return;
+	static int per_sm = 0;
+	if (!per_sm) { PV_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pi_kernel<Tag, F>, 256, 0)); if (per_sm < 1) throw std::runtime_error("parallel_iter: kernel does not fit an SM"); }
+	size_t blocks = (n + 255) / 256, cap = (size_t)per_sm * c.sm_count;
+	if (blocks > cap) blocks = cap;
+	if (!c.grid_bar) { PV_CUDA_CHECK(cudaMalloc((void **)&c.grid_bar, 8)); PV_CUDA_CHECK(cudaMemsetAsync(c.grid_bar, 0, 8, c.stream)); }
+	c.prof_begin(Tag::name(), n * (u64)iters, n * (u64)iters * Tag::bytes);
+	u32 *bar = c.grid_bar;
+	void *args[] = {(void *)&n, (void *)&iters, (void *)&f, (void *)&live, (void *)&bar};
+	PV_CUDA_CHECK(cudaLaunchCooperativeKernel((const void *)pi_kernel<Tag, F>, dim3((unsigned)blocks), dim3(256), args, 0, c.stream));
+	c.prof_end();
+	c.launches++;
+}
+#else
+template <class Tag, class F> inline void parallel_iter(Ctx &c, size_t n, int iters, F f, const u32 *live = nullptr) {
+	for (int it = 0; it < iters; it++) {
+		parallel_for<Tag>(c, n, [=](size_t i) { f(i, it); });
+		if (live && it + 1 < iters && live[it] == 0) break;
 	}
 }
 #endif

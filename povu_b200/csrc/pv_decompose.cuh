@@ -331,14 +331,16 @@ inline void decompose_device(Ctx &c, u32 V, u64 E, const u32 *ep1, const u32 *ep
 			// itFlag[it] = "iteration it marked something".  Later iterations test the previous flag on the device and fall
 			// through when the marking has converged; the host looks only every 8th iteration (one sync instead of eight).
 			// (flags sit 128 bytes apart: a word that one iteration polls must not share a sector with the word the same
-			// iteration's markers keep storing to)
+			// iteration's markers keep storing to.)  One launch per doubling step: all steps in one cooperative launch with
+			// grid barriers (parallel_iter) was measured 3x SLOWER here -- the sweeps must then read the jump pointers and ranks
+			// from L2 (another SM wrote them one sweep earlier), and this kernel lives on L1 hits (947 vs 312 us at cfg2).
 			Buf<u32> itFlag(c, ((size_t)maxIt + 1) * 32);
 			itFlag.zero();
 			u32 *itFlag_ = itFlag.p;
 			for (int it = 0; it < maxIt; it++) {
 				const u32 lim = 1u << it;
-				// one launch per doubling step: mark J^(2^it)-successors of the nodes ranked below 2^it, and square the jump
-				// pointers for the next step (the squaring runs one step past convergence; its result is then unused)
+				// mark the J^(2^it)-successors of the nodes ranked below 2^it, and square the jump pointers for the next step
+				// (the squaring runs one step past convergence; its result is then unused)
 				parallel_for<K_mark>(c, (size_t)nA * 2, PV_LAMBDA(size_t i) {
 					if (it > 0 && itFlag_[(it - 1) * 32] == 0) return;
 					u32 v = act[i >> 1]; u32 x = 2 * v + (u32)(i & 1);

@@ -13,6 +13,7 @@
 #include <type_traits>
 #include "pv_text.cuh"
 #include "pv_gfa.cuh"
+#include "pv_shard.cuh"
 #include "pv_host.hpp"
 
 namespace pve {
@@ -32,7 +33,7 @@ struct Session {
 	std::set<u32> ref_ids;
 
 	explicit Session(pv::Ctx &ctx) : c(&ctx) {}
-	~Session() { unpin(); }
+	~Session() { unpin(); pinned.swap(full_pinned); unpin(); }
 	Session(const Session &) = delete;
 	Session &operator=(const Session &) = delete;
 	// page-lock the host arrays that are copied to the device (so H2D runs at PCIe speed, asynchronously)
@@ -205,58 +206,63 @@ struct Session {
 	std::vector<u32> comp_global;          // local component k (ascending lowest vertex) -> global component id (1-based)
 	u32 n_comp_total = 0; bool sharded = false;
 	std::vector<u32> shard_owner;          // per global component (0-based): owning rank
-	void shard(u32 rank, u32 world) {
-		if (world == 0 || rank >= world) throw std::runtime_error("shard: bad rank / world size");
-		upload_edges();
-		ensure_host(true, true, true);
-		const u32 V = g.V(); const u64 E = g.E();
-		pv::Buf<u32> lab(*c, V ? V : 1);
-		pv::component_labels(*c, V, E, d_ep1.p, d_ep2.p, lab.p);
-		std::vector<u32> root = lab.to_host(); root.resize(V);
-		{   // every link must lie inside one component, or the filtered graph below would be cut through a component
-			u64 bad = 0, notroot = 0;
-			for (u64 e = 0; e < E; e++) if (root[g.ep1[e] >> 1] != root[g.ep2[e] >> 1]) bad++;
-			for (u32 v = 0; v < V; v++) if (root[root[v]] != root[v]) notroot++;
-			if (bad || notroot) throw std::runtime_error("shard: inconsistent component labels (" + std::to_string(bad) + " links across components, " + std::to_string(notroot) + " labels that are not roots)");
+	// The whole graph, kept aside by the first shard() so that the partitioning can be repeated (the multi-GPU end-to-end
+	// step re-shards from the page-locked host arrays every time): host side in `full`, device side in f_*.
+	pvh::HostGraph full; bool have_full = false, full_dev = false;
+	pv::Buf<u32> f_ep1, f_ep2, f_steps, f_segLen, f_ids; pv::Buf<u64> f_lblOff; pv::Buf<u8> f_lbl;
+	std::vector<void *> full_pinned;
+	double t_shard_ms = 0;
+	// from_host: forget the device copy of the whole graph first, so that this call uploads it from the host arrays again
+	void shard(u32 rank, u32 world, bool from_host = false) {
+		const double t0 = now_ms();
+		if (!have_full) {
+			upload_edges(); upload_raw_paths(); c->up_join();
+			if (from_host) ensure_host(true, true, true);
+			const bool dev_tables = tt_graph_dev && tt.ids.p;
+			f_ep1 = std::move(d_ep1); f_ep2 = std::move(d_ep2); f_steps = std::move(d_steps); f_segLen = std::move(d_segLen);
+			if (dev_tables) { f_ids = std::move(tt.ids); if (g.has_labels) { f_lblOff = std::move(tt.lblOff); f_lbl = std::move(tt.lbl); } }
+			else {
+				f_ids = pv::Buf<u32>(*c, g.V() ? g.V() : 1); c->h2d(f_ids.p, g.ids.data(), (size_t)g.V() * 4);
+				if (g.has_labels) { f_lblOff = pv::Buf<u64>(*c, g.lblOff.size()); c->h2d(f_lblOff.p, g.lblOff.data(), g.lblOff.size() * 8); f_lbl = pv::Buf<u8>(*c, g.lbl.size() ? g.lbl.size() : 1); c->h2d(f_lbl.p, g.lbl.data(), g.lbl.size()); }
+				c->sync();
+			}
+			full_pinned.swap(pinned);      // (the page-locked registrations belong to the whole graph's arrays)
+			full = std::move(g);
+			full.devE = full.ep1.empty() ? full.devE : full.ep1.size();
+			have_full = true; full_dev = true;
 		}
-		std::vector<u32> comp_of(V), roots;
-		for (u32 v = 0; v < V; v++) if (root[v] == v) roots.push_back(v);          // ascending = discovery order
-		for (u32 v = 0; v < V; v++) comp_of[v] = (u32)(std::lower_bound(roots.begin(), roots.end(), root[v]) - roots.begin());
-		const u32 nC = (u32)roots.size();
-		std::vector<u64> w(nC, 0);
-		for (u64 e = 0; e < E; e++) w[comp_of[g.ep1[e] >> 1]]++;
-		for (u32 st : g.steps) w[comp_of[st >> 1]]++;
-		for (u32 v = 0; v < V; v++) w[comp_of[v]]++;
-		std::vector<u32> order(nC);
-		for (u32 k = 0; k < nC; k++) order[k] = k;
-		std::stable_sort(order.begin(), order.end(), [&](u32 a, u32 b) { return w[a] > w[b]; });
-		std::vector<u64> load(world, 0);
-		shard_owner.assign(nC, 0);
-		for (u32 k : order) { u32 best = 0; for (u32 r = 1; r < world; r++) if (load[r] < load[best]) best = r; shard_owner[k] = best; load[best] += w[k]; }
-		n_comp_total = nC;
-		comp_global.clear();
-		for (u32 k = 0; k < nC; k++) if (shard_owner[k] == rank) comp_global.push_back(k + 1);
-		// filter the host graph (vertex order, edge order and path ids are preserved)
-		pvh::HostGraph n; n.has_labels = g.has_labels; n.paths = g.paths;
-		std::vector<u32> remap(V, pvh::NONE32);
-		n.lblOff.push_back(0);
-		for (u32 v = 0; v < V; v++) if (shard_owner[comp_of[v]] == rank) {
-			remap[v] = (u32)n.ids.size(); n.ids.push_back(g.ids[v]); n.segLen.push_back(g.segLen[v]);
-			if (g.has_labels) n.lbl.append(g.label(v), g.segLen[v]);
-			n.lblOff.push_back(n.lblOff.back() + g.segLen[v]);
+		if (from_host && full_dev) { f_ep1.release(); f_ep2.release(); f_steps.release(); f_segLen.release(); f_ids.release(); f_lblOff.release(); f_lbl.release(); full_dev = false; }
+		const u32 V = full.V(), H = full.H(); const u64 E = full.E(); const u64 S = full.stepOff.empty() ? 0 : full.stepOff.back();
+		if (!full_dev) {   // the whole graph travels host -> HBM again (page-locked arrays: PCIe speed)
+			if ((E && full.ep1.empty()) || (S && full.steps.empty())) throw std::runtime_error("shard: the whole graph is no longer on the host");
+			f_ep1 = pv::Buf<u32>(*c, E ? E : 1); f_ep2 = pv::Buf<u32>(*c, E ? E : 1); f_steps = pv::Buf<u32>(*c, S ? S : 1); f_segLen = pv::Buf<u32>(*c, V ? V : 1); f_ids = pv::Buf<u32>(*c, V ? V : 1);
+			c->h2d(f_ep1.p, full.ep1.data(), E * 4); c->h2d(f_ep2.p, full.ep2.data(), E * 4); c->h2d(f_steps.p, full.steps.data(), S * 4);
+			c->h2d(f_segLen.p, full.segLen.data(), (size_t)V * 4); c->h2d(f_ids.p, full.ids.data(), (size_t)V * 4);
+			if (full.has_labels) { f_lblOff = pv::Buf<u64>(*c, full.lblOff.size()); c->h2d(f_lblOff.p, full.lblOff.data(), full.lblOff.size() * 8); f_lbl = pv::Buf<u8>(*c, full.lbl.size() ? full.lbl.size() : 1); c->h2d(f_lbl.p, full.lbl.data(), full.lbl.size()); }
+			full_dev = true;
 		}
-		for (u64 e = 0; e < E; e++) if (remap[g.ep1[e] >> 1] != pvh::NONE32) { n.ep1.push_back((remap[g.ep1[e] >> 1] << 1) | (g.ep1[e] & 1u)); n.ep2.push_back((remap[g.ep2[e] >> 1] << 1) | (g.ep2[e] & 1u)); }
-		n.stepOff.assign(1, 0);
-		for (u32 h = 0; h < g.H(); h++) {
-			for (u32 k = g.stepOff[h]; k < g.stepOff[h + 1]; k++) { u32 nv = remap[g.steps[k] >> 1]; if (nv != pvh::NONE32) n.steps.push_back((nv << 1) | (g.steps[k] & 1u)); }
-			n.stepOff.push_back((u32)n.steps.size());
-		}
-		n.build_id_table();
-		unpin(); drop_device();
-		g = std::move(n);
-		host_edges = host_steps = host_lbl = true;
-		pin();
-		invalidate_graph_state(); sharded = true;
+		pv::ShardIn in; in.V = V; in.H = H; in.E = E; in.S = S; in.ep1 = f_ep1.p; in.ep2 = f_ep2.p; in.steps = f_steps.p; in.segLen = f_segLen.p; in.ids = f_ids.p;
+		if (full.has_labels) { in.lblOff = f_lblOff.p; in.lbl = f_lbl.p; }
+		if (full.stepOff.empty()) full.stepOff.assign(1, 0);
+		in.h_stepOff = full.stepOff.data();
+		pv::ShardOut o;
+		pv::shard_device(*c, in, rank, world, o);
+		// install the share as the session's graph: the big arrays exist only in HBM (ensure_host brings them on demand)
+		c->bg_sync(); c->up_join();
+		invalidate_graph_state();
+		dg = pv::DevGraph(); paths_up = false;
+		g = pvh::HostGraph(); g.has_labels = full.has_labels; g.paths = full.paths;
+		g.ids.swap(o.h_ids); g.segLen.swap(o.h_segLen); g.stepOff = o.h_stepOff; g.devE = o.E;
+		g.build_id_table();
+		d_ep1 = std::move(o.ep1); d_ep2 = std::move(o.ep2); d_steps = std::move(o.steps); d_segLen = std::move(o.segLen);
+		edges_up = true; raw_paths_up = true;
+		tt.ids = std::move(o.ids);
+		if (full.has_labels) { tt.lblOff = std::move(o.lblOff); tt.lbl = std::move(o.lbl); }
+		tt_graph_dev = true;
+		host_edges = o.E == 0; host_steps = o.S == 0; host_lbl = false;
+		comp_global = o.comp_global; shard_owner = o.owner; n_comp_total = o.n_comp_total;
+		sharded = true;
+		t_shard_ms = now_ms() - t0;
 	}
 
 	// decompose: flubbles + PVST of every component with >= 3 vertices (decompose.cpp:129-142)
@@ -429,6 +435,45 @@ struct Session {
 		pv::Trace tr(*c, "session");
 		pv::call_device(*c, dg, in, opt, rec);
 		tr.mark("call_device");
+	}
+
+	// ---- the records of the last call as ONE self-describing binary stream in HBM: what a rank contributes to the final
+	// gather of a multi-GPU run (NCCL moves the bytes; nothing is converted on the host).  Layout (little endian, every array
+	// 8-byte aligned): u64 header[8] = {magic "PVREC001", nRec, nGrp, nGt, H, 0, 0, 0}; then u32[nRec] region, ref path, left and
+	// right context step ((SEGMENT ID << 1) | strand -- ids, not shard-local indices), VARTYPE, POS, ref slice start, ref slice
+	// length; u32[nRec + 1] first alt group; u64[nRec + 1] first genotype cell; u32[nGrp] alt path, start, length, count;
+	// u16[nGt] genotype cells.
+	static u64 pad8(u64 x) { return (x + 7) & ~(u64)7; }
+	u64 records_packed_bytes() const {
+		const u64 R = rec.nRecTot, G = rec.nGrpTot, T = rec.nGtTot;
+		return 64 + 8 * pad8(R * 4) + pad8((R + 1) * 4) + (R + 1) * 8 + 4 * pad8(G * 4) + pad8(T * 2);
+	}
+	void records_pack(void *dst, u64 cap, u64 *bytes) {
+		const u64 need = records_packed_bytes();
+		if (bytes) *bytes = need;
+		if (cap < need) throw std::runtime_error("records_pack: destination too small");
+		pv::Ctx &cx = *c;
+		const pv::RecPiece *Rp = rec.nRecTot ? &rec.flat(cx) : nullptr;
+		const u64 R = rec.nRecTot, G = rec.nGrpTot, T = rec.nGtTot;
+		u64 hdr[8] = {0x3130304345525650ull, R, G, T, (u64)g.H(), 0, 0, 0};
+		char *d = (char *)dst; u64 o = 0;
+		cx.h2d(d, hdr, 64); o = 64;
+		if (!tt.ids.p) { tt.ids = pv::Buf<u32>(cx, g.ids.size() ? g.ids.size() : 1); cx.h2d(tt.ids.p, g.ids.data(), g.ids.size() * 4); }
+		auto put = [&](const void *src, u64 n) { if (n) cx.d2d(d + o, src, n); o += pad8(n); };
+		if (Rp) {
+			const pv::RecPiece &P = *Rp;
+			put(P.rov.p, R * 4); put(P.ref.p, R * 4);
+			for (int side = 0; side < 2; side++) {
+				const u32 *src = side ? P.cxtR.p : P.cxtL.p; u32 *out = (u32 *)(d + o); const u32 *ids = tt.ids.p;
+				pv::parallel_for<pv::C_keep>(cx, R, PV_LAMBDA(size_t i) { u32 x = src[i]; out[i] = (ids[x >> 1] << 1) | (x & 1u); });
+				o += pad8(R * 4);
+			}
+			put(P.vt.p, R * 4); put(P.pos.p, R * 4); put(P.refStart.p, R * 4); put(P.refLen.p, R * 4);
+			put(P.grpOff.p, (R + 1) * 4); put(P.gtOff.p, (R + 1) * 8);
+			put(P.gHap.p, G * 4); put(P.gStart.p, G * 4); put(P.gLen.p, G * 4); put(P.gCnt.p, G * 4);
+			put(P.gt.p, T * 2);
+		} else { cx.memset0(d + o, need - o); }
+		cx.sync();   // (the header lives on this stack frame)
 	}
 
 	// VCF text: header + contig lines of the selected prefixes + records in the reference's chunk order.

@@ -754,19 +754,19 @@ inline void list_rank_suffix(Ctx &c, const u32 *next, const u32 *weight, u32 *ra
 		u32 w = nx == NONE ? 0u : weight[nx];
 		a[i] = ((u64)nx << 32) | w;
 	});
-	int iters = bits_for(n);
-	for (int it = 0; it < iters; it++) {
-		parallel_for<K_lr_jump>(c, n, PV_LAMBDA(size_t i) {
-			u64 x = a[i];
-			u32 nx = (u32)(x >> 32);
-			if (nx != NONE) {
-				u64 y = a[nx];
-				x = (y & 0xFFFFFFFF00000000ull) | (u32)((u32)x + (u32)y);
-			}
-			b[i] = x;
-		});
-		std::swap(a, b);
-	}
+	const int iters = bits_for(n);
+	// every doubling step of the list in ONE cooperative launch (sweep `it` reads buffer it & 1, writes the other)
+	parallel_iter<K_lr_jump>(c, n, iters, PV_LAMBDA(size_t i, int it) {
+		const u64 *src = (it & 1) ? b : a; u64 *dst = (it & 1) ? a : b;
+		u64 x = ld_cg(src + i);
+		u32 nx = (u32)(x >> 32);
+		if (nx != NONE) {
+			u64 y = ld_cg(src + nx);
+			x = (y & 0xFFFFFFFF00000000ull) | (u32)((u32)x + (u32)y);
+		}
+		dst[i] = x;
+	});
+	if (iters & 1) std::swap(a, b);
 	parallel_for<K_lr_out>(c, n, PV_LAMBDA(size_t i) { rank_out[i] = (u32)a[i]; });
 }
 
