@@ -684,6 +684,53 @@ inline void overlay_pass(Ctx &c, const DevGraph &G, const GraphView &g, const Ca
 		// ---- C6a: group alt slices by (context, class, walk) per region, order groups like the reference's std::maps
 		Buf<u32> recCnt(c, (size_t)Rc + 1), grpCnt(c, (size_t)Rc + 1), recOff(c, (size_t)Rc + 1), grpOff(c, (size_t)Rc + 1);
 		u32 *recCnt_ = recCnt.p, *grpCnt_ = grpCnt.p;
+		bool group_by_warp = false;
+#ifndef PV_EMU
+		// hundreds of paths: a region has ~100+ candidates that one thread would compare one by one (1.7 GB/s of algorithmic
+		// traffic at 464 paths).  One warp per region instead: repeatedly take the first ungrouped candidate as the next head
+		// (lanes stride over the candidates, warp minimum), let every lane compare its candidates with it, count the members
+		// with a warp sum.  Heads come out in order of first occurrence and every candidate joins the first head it matches --
+		// exactly the sequential grouping; the few heads are then ordered by lane 0.
+		group_by_warp = (u64)nCand >= 24ull * Rc || getenv("POVU_B200_GROUP_WARP") != nullptr;
+		if (group_by_warp && !getenv("POVU_B200_GROUP_THREAD")) {
+			u32 *cHead_ = cd.cHead;
+			parallel_for<C_fill16>(c, nC1, PV_LAMBDA(size_t x) { cHead_[x] = NONE; });
+			parallel_for<C_group>(c, ((size_t)Rc + 1) * 32, PV_LAMBDA(size_t t) {
+				const u32 r = (u32)(t >> 5), lane = (u32)(t & 31);
+				if (r >= Rc) { if (lane == 0) { recCnt_[r] = 0; grpCnt_[r] = 0; } return; }
+				const u32 b = candOff_[rv.rowBase(r)], e = candOff_[rv.rowBase(r + 1)];
+				u32 *a = cd.hsort + b; u32 nh = 0;
+				u32 next = b + lane;          // this lane's first candidate that may still be ungrouped
+				while (true) {
+					while (next < e && (cd.cCls[next] >= 3 || cd.cHead[next] != NONE)) next += 32;
+					u32 h = next < e ? next : NONE;
+#pragma unroll
+					for (int d = 16; d > 0; d >>= 1) { u32 o = __shfl_xor_sync(0xFFFFFFFFu, h, d); h = o < h ? o : h; }
+					if (h == NONE) break;
+					const u32 hL = cd.cL[h], hR = cd.cR[h], hC = cd.cCls[h], hLen = cd.cLen[h], hSt = cd.cStart[h];
+					u32 mine = 0;
+					for (u32 x = next; x < e; x += 32) {
+						if (x == h) { cd.cHead[x] = h; mine++; continue; }
+						if (cd.cCls[x] >= 3 || cd.cHead[x] != NONE) continue;
+						if (cd.cL[x] == hL && cd.cR[x] == hR && cd.cCls[x] == hC && cd.cLen[x] == hLen && walk_equal(g.steps, hSt, cd.cStart[x], hLen)) { cd.cHead[x] = h; mine++; }
+					}
+#pragma unroll
+					for (int d = 16; d > 0; d >>= 1) mine += __shfl_xor_sync(0xFFFFFFFFu, mine, d);
+					if (lane == 0) { a[nh] = h; cd.gCount[h] = mine; }
+					nh++;
+				}
+				if (lane != 0) return;
+				for (u32 st = nh / 2; st-- > 0;) sift_down(g.steps, cd, a, st, nh);
+				for (u32 end = nh; end-- > 1;) { u32 t2 = a[0]; a[0] = a[end]; a[end] = t2; sift_down(g.steps, cd, a, 0, end); }
+				u32 nrec = 0;
+				for (u32 q = 0; q < nh; q++) if (q == 0 || !same_record(cd, a[q - 1], a[q])) nrec++;
+				recCnt_[r] = nrec; grpCnt_[r] = nh;
+				if (k == 0) cv.hasData[r] = nh ? 1u : 0u;
+				else if (nh == 0 && cv.hasData[r]) atomic_add(cv.errs + 0, 1u);   // std::map::at throws in the reference
+			});
+		} else group_by_warp = false;
+#endif
+		if (!group_by_warp)
 		parallel_for<C_group>(c, (size_t)Rc + 1, PV_LAMBDA(size_t rr_) {
 			if (rr_ >= Rc) { recCnt_[rr_] = 0; grpCnt_[rr_] = 0; return; }
 			u32 r = (u32)rr_;

@@ -573,7 +573,22 @@ inline void atomic_inc_aggregated(u32 *base, u32 idx) { base[idx]++; }
 // The Tag type only names the kernel instantiation (so ncu launch lists read `pf_kernel<K_claim,...>`).
 // ---------------------------------------------------------------------------------------------
 #ifndef PV_EMU
+// Programmatic dependent launch: a kernel launched with launch_pdl may be scheduled while its predecessor in the stream is
+// still draining (its launch latency hides behind the predecessor's tail); it must not touch memory before pdl_wait(), which
+// returns once every earlier grid has completed and flushed.  A step here is a chain of ~140 short dependent kernels, so the
+// launch + drain gap between two of them is a visible share of the step.  POVU_B200_NO_PDL=1 launches the plain way.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+template <class... KArgs, class... Args> inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+	static const bool off = getenv("POVU_B200_NO_PDL") != nullptr;
+	cudaLaunchConfig_t cfg = {};
+	cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+	cudaLaunchAttribute attr[1];
+	attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[0].val.programmaticStreamSerializationAllowed = 1;
+	cfg.attrs = attr; cfg.numAttrs = off ? 0 : 1;
+	return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
 template <class Tag, class F> __global__ void __launch_bounds__(256) pf_kernel(size_t n, F f) {
+	pdl_wait();
 	size_t stride = (size_t)gridDim.x * blockDim.x;
 	for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) f(i);
 }
@@ -583,12 +598,12 @@ template <class Tag, class F> inline void parallel_for(Ctx &c, size_t n, F f) {
 	size_t cap = (size_t)c.sm_count * 8;
 	if (blocks > cap) blocks = cap;
 	c.prof_begin(Tag::name(), n, n * Tag::bytes);
-	pf_kernel<Tag, F><<<(unsigned)blocks, 256, 0, c.stream>>>(n, f);
+	cudaError_t lerr = launch_pdl(pf_kernel<Tag, F>, dim3((unsigned)blocks), dim3(256), 0, c.stream, n, f);
 	c.prof_end();
 	c.launches++;
 	// POVU_B200_SYNC_LAUNCHES=1 (debug): synchronise after every launch so that a device fault names its kernel
 	static const bool sync_every = getenv("POVU_B200_SYNC_LAUNCHES") != nullptr;
-	cudaError_t err = sync_every ? cudaStreamSynchronize(c.stream) : cudaSuccess;
+	cudaError_t err = lerr != cudaSuccess ? lerr : (sync_every ? cudaStreamSynchronize(c.stream) : cudaSuccess);
 	if (err == cudaSuccess) err = cudaGetLastError();
 	if (err != cudaSuccess) throw std::runtime_error(std::string("CUDA error in kernel ") + Tag::name() + " (" + std::to_string(n) + " items): " + cudaGetErrorString(err));
 }

@@ -99,6 +99,68 @@ PV_KERNEL(K_seq, 16);
 PV_KERNEL(K_iota, 4);
 PV_KERNEL(K_word, 24);
 
+// The reference's stage-cost trace (POVU_STAGE_COST_TRACE=1, /root/reference/src/povu/common/stage_cost.cpp:59-94): six named
+// decompose stages with calls / input items / output items / elapsed ns, printed to stderr at exit in the same line format, so
+// CPU and GPU stage times line up.  Here the stage boundaries are CUDA events on the pipeline's stream; the mapping:
+//   componentDecomposition     D1 (CSR in reference edge order) + dense component tables   [VG::componetize]
+//   tipDummyAugmentation       D2 + D3: the exact DFS tree, Euler tour, pre / post order    [pst::Tree::from_bd carries this stage]
+//   cycleClassAssignment       D4: back edges, bridges, labels, class keys                  [simple_cycle_equiv]
+//   traversalFrameConstruction D5a: class-stack positions                                    [compute_eq_class_stack]
+//   boundaryEmission           D5b: sort by class key, next / previous seen, exact check    [compute_eq_class_metadata]
+//   hierarchyConstruction      D6: flubbles, PVST depths and parents                        [add_flubbles]
+// calls counts components (the reference runs every stage but the first once per component).
+struct StageCost {
+	static const int N = 6;
+	u64 calls[N] = {0}, in_items[N] = {0}, out_items[N] = {0}; double ns[N] = {0};
+	bool on = false, registered = false;
+	static StageCost &inst() { static StageCost s; return s; }
+	static bool enabled() { const char *v = getenv("POVU_STAGE_COST_TRACE"); return v && v[0] && v[0] != '0'; }
+	static void report() {
+		StageCost &s = inst();
+		static const char *contract[N] = {"componentDecomposition", "tipDummyAugmentation", "traversalFrameConstruction", "cycleClassAssignment", "boundaryEmission", "hierarchyConstruction"};
+		static const char *trace[N] = {"component-decomposition", "tip-dummy-augmentation", "traversal-frame-construction", "cycle-class-assignment", "flubble-boundary-extraction", "flubble-hierarchy-construction"};
+		fprintf(stderr, "povu-stage-cost-trace schema=povu.stage-cost.v1\n");
+		for (int i = 0; i < N; i++)
+			fprintf(stderr, "povu-stage-cost contract=%s trace=%s calls=%llu input_items=%llu output_items=%llu elapsed_ns=%llu\n", contract[i], trace[i],
+				(unsigned long long)s.calls[i], (unsigned long long)s.in_items[i], (unsigned long long)s.out_items[i], (unsigned long long)s.ns[i]);
+	}
+	void add(int stage, u64 c, u64 in, u64 out, double nanos) {
+		if (!registered) { registered = true; atexit(report); }
+		calls[stage] += c; in_items[stage] += in; out_items[stage] += out; ns[stage] += nanos;
+	}
+};
+// stage boundaries of one decompose call (events only exist when the trace is on)
+struct StageMarks {
+	Ctx &c; bool on; int n = 0;
+#ifndef PV_EMU
+	cudaEvent_t ev[12];
+#else
+	double t[12];
+#endif
+	explicit StageMarks(Ctx &ctx) : c(ctx), on(StageCost::enabled()) {}
+	void mark() {
+		if (!on || n >= 12) return;
+#ifndef PV_EMU
+		PV_CUDA_CHECK(cudaEventCreate(&ev[n])); PV_CUDA_CHECK(cudaEventRecord(ev[n], c.stream));
+#else
+		t[n] = Trace::now();
+#endif
+		n++;
+	}
+	double ns_between(int a, int b) {   // after the stream was synchronised
+#ifndef PV_EMU
+		float ms = 0; cudaEventElapsedTime(&ms, ev[a], ev[b]); return (double)ms * 1e6;
+#else
+		return (t[b] - t[a]) * 1e6;
+#endif
+	}
+	~StageMarks() {
+#ifndef PV_EMU
+		for (int i = 0; i < n; i++) cudaEventDestroy(ev[i]);
+#endif
+	}
+};
+
 struct MP { i32 a, b; };   // x -> max(x + a, b)
 struct OpMP {
 	PV_HD MP operator()(MP f, MP g) const {   // apply f first, then g
@@ -158,6 +220,8 @@ inline void decompose_device(Ctx &c, u32 V, u64 E, const u32 *ep1, const u32 *ep
 	if (M >= 0xFFFFFFF0ull) throw std::runtime_error("graph too large for 32-bit adjacency slots");
 
 	Trace tr(c, "decompose");
+	StageMarks sm(c);
+	sm.mark();   // 0
 	// ------------------------------------------------------------------ D1: CSR in reference edge order
 	Buf<u32> adjOff(c, P + 1), adjNbr(c, M ? M : 1), adjOwner(c, M ? M : 1), rev(c, M ? M : 1), origDeg(c, P);
 	{
@@ -184,6 +248,7 @@ inline void decompose_device(Ctx &c, u32 V, u64 E, const u32 *ep1, const u32 *ep
 	const u32 *adjOff_ = adjOff.p, *adjNbr_ = adjNbr.p, *adjOwner_ = adjOwner.p, *rev_ = rev.p, *origDeg_ = origDeg.p;
 
 	tr.mark("D1 csr");
+	sm.mark();   // 1
 	// ------------------------------------------------------------------ D2: exact DFS tree by rounds
 	Buf<u32> visited(c, V), uf(c, V), comp(c, V), gcomp(c, V), entrySide(c, V);
 	Buf<u32> parent(c, P), pslot(c, P), depth(c, P), F(c, P), Fslot(c, P), J(c, P), J2(c, P), rnk(c, P);
@@ -422,6 +487,7 @@ inline void decompose_device(Ctx &c, u32 V, u64 E, const u32 *ep1, const u32 *ep
 	}
 	out.dfs_rounds = round;
 	tr.mark("D2 dfs rounds");
+	sm.mark();   // 2
 
 	// ------------------------------------------------------------------ components (dense indices)
 	Buf<u32> isRoot(c, V), compIdxOfRoot(c, V + 1), nvOfRoot(c, V);
@@ -453,6 +519,7 @@ inline void decompose_device(Ctx &c, u32 V, u64 E, const u32 *ep1, const u32 *ep
 	const u32 N = P + nComp;   // nodes in global preorder space
 
 	tr.mark("components");
+	sm.mark();   // 3
 	// ------------------------------------------------------------------ D3: Euler tour + list ranking
 	Buf<u32> treeSlot(c, M ? M : 1);
 	treeSlot.fill_ff();
@@ -492,6 +559,7 @@ inline void decompose_device(Ctx &c, u32 V, u64 E, const u32 *ep1, const u32 *ep
 	parallel_for<K_pre>(c, nComp, PV_LAMBDA(size_t k) { pre2node_[cNodeBase_[k]] = P + (u32)k; });
 
 	tr.mark("D3 euler+rank");
+	sm.mark();   // 4
 	// ------------------------------------------------------------------ D4: back edges, bridges, labels, keys
 	Buf<u64> X(c, (size_t)2 * (N + 1));      // 128-bit label accumulators, (lo, hi) interleaved
 	Buf<i32> cd(c, N + 1);
@@ -576,6 +644,7 @@ inline void decompose_device(Ctx &c, u32 V, u64 E, const u32 *ep1, const u32 *ep
 	const u128 *PX_ = PX.p; const i32 *PC_ = PC.p;
 
 	tr.mark("D4 labels");
+	sm.mark();   // 5
 	// ------------------------------------------------------------------ D5: class stack positions
 	// pos(seg) = #entry ports before + root-path sum of w + G(entry)   (see DESIGN.md "class stack without a second traversal")
 	Buf<u32> isEnt(c, N + 1), S(c, N + 1);
@@ -622,6 +691,7 @@ inline void decompose_device(Ctx &c, u32 V, u64 E, const u32 *ep1, const u32 *ep
 		stKey_[gp] = u128{a.lo ^ b.lo, a.hi ^ b.hi};
 		stCnt_[gp] = (u32)(PC_[gc + sz_[cx]] - PC_[gc]);
 	});
+	sm.mark();   // 6
 	// group equal keys: ONE stable radix sort by a 32-bit word of the 128-bit key (4 onesweep passes instead of 8-16).  Keys
 	// that agree on that word but differ elsewhere (a few dozen pairs per million classes, by the birthday bound) interleave
 	// inside a run of equal words; the neighbour search below steps over them, which costs the length of the foreign stretch.
@@ -659,6 +729,7 @@ inline void decompose_device(Ctx &c, u32 V, u64 E, const u32 *ep1, const u32 *ep
 	}
 
 	tr.mark("D5 stack+sort");
+	sm.mark();   // 7
 	// ------------------------------------------------------------------ D6: flubbles + PVST parents
 	Buf<u32> segComp(c, nS), notNext(c, nS), lamBad(c, nComp ? nComp : 1);
 	u32 *segComp_ = segComp.p, *notNext_ = notNext.p, *lamBad_ = lamBad.p;
@@ -752,6 +823,7 @@ inline void decompose_device(Ctx &c, u32 V, u64 E, const u32 *ep1, const u32 *ep
 	});
 
 	tr.mark("D6 flubbles");
+	sm.mark();   // 8
 	// ------------------------------------------------------------------ results to the host
 	const bool bg = opt.async_results && opt.keep_forest;   // (the sources must outlive the copies: only when the caller keeps them)
 	if (bg) {
@@ -794,6 +866,17 @@ inline void decompose_device(Ctx &c, u32 V, u64 E, const u32 *ep1, const u32 *ep
 	}
 	c.sync();
 	tr.mark("results d2h");
+	if (sm.on && sm.n == 9) {
+		StageCost &sc = StageCost::inst();
+		u64 tips = 0; for (u32 k = 0; k < nComp; k++) tips += out.comp_has_tips[k] ? 1 : 0;   // (components with tips; the exact tip count stays on the device)
+		const u64 treeE = (u64)N - nComp, nodes = N;
+		sc.add(0, 1, (u64)V + E, nComp, sm.ns_between(0, 1) + sm.ns_between(2, 3));
+		sc.add(1, nComp, (u64)V + E + tips, nodes + treeE, sm.ns_between(1, 2) + sm.ns_between(3, 4));
+		sc.add(3, nComp, nodes + treeE, treeE, sm.ns_between(4, 5));
+		sc.add(2, nComp, nodes + treeE, nS, sm.ns_between(5, 6));
+		sc.add(4, nComp, nS, nFl, sm.ns_between(6, 7));
+		sc.add(5, nComp, nS, (u64)nFl + nComp, sm.ns_between(7, 8));
+	}
 	if (opt.keep_labels) *opt.keep_labels = std::move(gcomp);
 	if (opt.keep_forest) {
 		DevForest &d = *opt.keep_forest;

@@ -66,6 +66,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_lb_kernel(const T *in, T *o
 	__shared__ T s_prefix;
 	__shared__ u32 s_tile;
 	const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+	pdl_wait();
 	if (t == 0) { u32 k = atomicAdd(ticket, 1u); if (k == ntiles - 1) atomicExch(ticket, 0u); s_tile = k; }
 	__syncthreads();
 	const u32 tile = s_tile;
@@ -170,6 +171,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_flat_kernel(const T *in, T 
 	__shared__ T s_prefix;
 	__shared__ u32 s_tile;
 	const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+	pdl_wait();
 	if (t == 0) { u32 k = atomicAdd(ticket, 1u); if (k == ntiles - 1) atomicExch(ticket, 0u); s_tile = k; }
 	__syncthreads();
 	const u32 tile = s_tile;
@@ -277,16 +279,16 @@ inline void scan_impl(Ctx &c, const T *in, T *out, size_t n, Op op, T identity) 
 	static const u32 flat_max = getenv("POVU_B200_SCAN_FLAT_MAX") ? (u32)strtoul(getenv("POVU_B200_SCAN_FLAT_MAX"), nullptr, 10) : 1024u;
 	if (ntiles <= flat_max) {   // every predecessor's aggregate is fetched at once (see scan_flat_kernel)
 		c.prof_begin("scan_flat", n, n * 2 * sizeof(T));
-		if (vec) scan_flat_kernel<T, Op, INCLUSIVE, true><<<(unsigned)ntiles, SCAN_THREADS, 0, c.stream>>>(in, out, n, op, identity, c.lb_flags, agg, c.lb_pack, c.lb_ticket, epoch, (u32)ntiles);
-		else scan_flat_kernel<T, Op, INCLUSIVE, false><<<(unsigned)ntiles, SCAN_THREADS, 0, c.stream>>>(in, out, n, op, identity, c.lb_flags, agg, c.lb_pack, c.lb_ticket, epoch, (u32)ntiles);
+		if (vec) PV_CUDA_CHECK(launch_pdl(scan_flat_kernel<T, Op, INCLUSIVE, true>, dim3((unsigned)ntiles), dim3(SCAN_THREADS), 0, c.stream, in, out, n, op, identity, c.lb_flags, agg, c.lb_pack, c.lb_ticket, epoch, (u32)ntiles));
+		else PV_CUDA_CHECK(launch_pdl(scan_flat_kernel<T, Op, INCLUSIVE, false>, dim3((unsigned)ntiles), dim3(SCAN_THREADS), 0, c.stream, in, out, n, op, identity, c.lb_flags, agg, c.lb_pack, c.lb_ticket, epoch, (u32)ntiles));
 		c.prof_end();
 		c.launches++;
 		PV_CUDA_CHECK(cudaGetLastError());
 		return;
 	}
 	c.prof_begin("scan_lb", n, n * 2 * sizeof(T));
-	if (vec) scan_lb_kernel<T, Op, INCLUSIVE, true><<<(unsigned)ntiles, SCAN_THREADS, 0, c.stream>>>(in, out, n, op, identity, c.lb_flags, agg, incl, c.lb_ticket, epoch, (u32)ntiles);
-	else scan_lb_kernel<T, Op, INCLUSIVE, false><<<(unsigned)ntiles, SCAN_THREADS, 0, c.stream>>>(in, out, n, op, identity, c.lb_flags, agg, incl, c.lb_ticket, epoch, (u32)ntiles);
+	if (vec) PV_CUDA_CHECK(launch_pdl(scan_lb_kernel<T, Op, INCLUSIVE, true>, dim3((unsigned)ntiles), dim3(SCAN_THREADS), 0, c.stream, in, out, n, op, identity, c.lb_flags, agg, incl, c.lb_ticket, epoch, (u32)ntiles));
+	else PV_CUDA_CHECK(launch_pdl(scan_lb_kernel<T, Op, INCLUSIVE, false>, dim3((unsigned)ntiles), dim3(SCAN_THREADS), 0, c.stream, in, out, n, op, identity, c.lb_flags, agg, incl, c.lb_ticket, epoch, (u32)ntiles));
 	c.prof_end();
 	c.launches++;
 	PV_CUDA_CHECK(cudaGetLastError());
@@ -649,6 +651,7 @@ __global__ void __launch_bounds__(1024) rmq_build_kernel(const u32 *a, u32 *pre,
 	__shared__ u32 s_last;
 	const u32 lane = threadIdx.x & 31u, w = threadIdx.x >> 5, s = blockIdx.x;
 	const u32 b = (s << 5) + w;
+	pdl_wait();
 	{
 		u32 i = (b << 5) + lane;
 		u32 x = i < n ? a[i] : NONE;
@@ -702,7 +705,7 @@ inline void rmq_build(Ctx &c, Rmq &r, const u32 *a, u32 n) {
 #ifndef PV_EMU
 	c.lb_reserve(1);
 	c.prof_begin(K_rmq_blocks::name(), n, (u64)n * K_rmq_blocks::bytes);
-	rmq_build_kernel<<<ns, 1024, 0, c.stream>>>(a, pre, suf, bt, pre2, suf2, st, n, nb, ns, levels, c.lb_ticket + 2);
+	PV_CUDA_CHECK(launch_pdl(rmq_build_kernel, dim3(ns), dim3(1024), 0, c.stream, a, pre, suf, bt, pre2, suf2, st, n, nb, ns, levels, c.lb_ticket + 2));
 	c.prof_end();
 	c.launches++;
 	PV_CUDA_CHECK(cudaGetLastError());

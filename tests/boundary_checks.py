@@ -44,6 +44,25 @@ def check_cli(cli, tmp):
     assert files == helpers.expected_pvsts("multi_comp")
     r = run(cli, "call", "-i", fx("multi_comp"), "-f", d, "-P", "S001#1#chr1")
     assert r.returncode == 0 and nodate(r.stdout) == golden("multi_comp")
+    # POVU_STAGE_COST_TRACE=1: the reference's six stage lines (stage_cost.cpp:59-94), same names / order / fields; the item
+    # counts it defines on the inputs agree with the compiled reference where one exists
+    d2 = os.path.join(tmp, "forest2"); os.mkdir(d2)
+    r = run(cli, "decompose", "-i", fx("multi_comp"), "-o", d2, env={"POVU_STAGE_COST_TRACE": "1"})
+    assert r.returncode == 0
+    lines = [l for l in r.stderr.splitlines() if l.startswith("povu-stage-cost")]
+    assert lines[0] == "povu-stage-cost-trace schema=povu.stage-cost.v1"
+    names = [re.match(r"povu-stage-cost contract=(\w+) trace=([\w-]+) calls=(\d+) input_items=(\d+) output_items=(\d+) elapsed_ns=(\d+)$", l).groups() for l in lines[1:]]
+    assert [(n[0], n[1]) for n in names] == [("componentDecomposition", "component-decomposition"), ("tipDummyAugmentation", "tip-dummy-augmentation"),
+                                              ("traversalFrameConstruction", "traversal-frame-construction"), ("cycleClassAssignment", "cycle-class-assignment"),
+                                              ("boundaryEmission", "flubble-boundary-extraction"), ("hierarchyConstruction", "flubble-hierarchy-construction")]
+    import call_checks as cc0
+    if os.path.exists(cc0.REF):
+        rr = subprocess.run([cc0.REF, "decompose", "-i", fx("multi_comp"), "-o", d2, "-t", "1"], capture_output=True, text=True, env=dict(os.environ, POVU_STAGE_COST_TRACE="1"))
+        ref = {m[0]: m for m in re.findall(r"povu-stage-cost contract=(\w+) trace=[\w-]+ calls=(\d+) input_items=(\d+) output_items=(\d+)", rr.stderr)}
+        got = {n[0]: n for n in names}
+        assert got["componentDecomposition"][3:5] == ref["componentDecomposition"][2:4]                 # V + E in, components out
+        assert got["boundaryEmission"][4] == ref["boundaryEmission"][3]                                  # flubble boundaries found
+        assert got["traversalFrameConstruction"][4] == ref["traversalFrameConstruction"][3]              # class-stack entries
     # -o dir: one <prefix>.vcf per prefix (to_vcf.hpp:83-101); -r file
     out = os.path.join(tmp, "vcfs")
     pf = os.path.join(tmp, "refs.txt"); open(pf, "w").write("S001\n")
