@@ -293,10 +293,14 @@ def run_strong(args, pv, stream, rank, world, torch, dist):
 
         # end to end: whole graph on the host -> partition -> hot path -> packed records -> gather on rank 0
         def e2e_step():
+            t_a = time.perf_counter()
             t_sh = 0.0
             if world > 1:
                 _, t_sh = sess.reshard(rank, world, from_host=True)
+            t_b = time.perf_counter()
             nrec, used = step(world > 1, True) if world > 1 else step(False, True)
+            torch.cuda.synchronize()
+            t_c = time.perf_counter()
             sizes = torch.tensor([used], dtype=torch.int64, device="cuda")
             gathered = 0
             if world > 1:
@@ -306,23 +310,25 @@ def run_strong(args, pv, stream, rank, world, torch, dist):
                 send = buf[:mx] if buf.numel() >= mx else torch.cat([buf, torch.empty(mx - buf.numel(), dtype=torch.uint8, device="cuda")])
                 recv = [torch.empty(mx, dtype=torch.uint8, device="cuda") for _ in range(world)] if rank == 0 else None
                 dist.gather(send, recv, dst=0)
+                torch.cuda.synchronize()
                 gathered = sum(int(x.item()) for x in all_sizes)
             else:
                 gathered = used
-            return t_sh, used, gathered
+            t_d = time.perf_counter()
+            return (t_b - t_a) * 1e3, used, gathered, (t_c - t_b) * 1e3, (t_d - t_c) * 1e3
         for _ in range(min(2, args.warmup)):
             e2e_step()
         barrier()
         n_e2e = max(3, min(args.steps, 5))
         t0 = time.perf_counter()
-        sh = []
+        sh, hp, ga = [], [], []
         for _ in range(n_e2e):
-            t_sh, used, gathered = e2e_step()
-            sh.append(t_sh)
+            t_sh, used, gathered, t_hot, t_ga = e2e_step()
+            sh.append(t_sh); hp.append(t_hot); ga.append(t_ga)
         barrier()
         e2e_ms = (time.perf_counter() - t0) * 1e3 / n_e2e
 
-    t = torch.tensor([dev_ms, e2e_ms, sum(sh) / len(sh)], dtype=torch.float64, device="cuda")
+    t = torch.tensor([dev_ms, e2e_ms, sum(sh) / len(sh), sum(hp) / len(hp), sum(ga) / len(ga)], dtype=torch.float64, device="cuda")
     cnt = torch.tensor([nrec, nfl, e_], dtype=torch.float64, device="cuda")
     share = torch.tensor([float(e_ + st_ + v_)], dtype=torch.float64, device="cuda")
     shares = [torch.zeros_like(share) for _ in range(world)]
@@ -334,15 +340,15 @@ def run_strong(args, pv, stream, rank, world, torch, dist):
         shares = [share]
     sess.close()
     w = [float(x.item()) for x in shares]
-    dev_ms, e2e_ms, shard_ms = t.tolist()
+    dev_ms, e2e_ms, shard_ms, hot_ms, gather_ms = t.tolist()
     return {"workload": f"wg_25c (cfg4 shape): 25 components ~ GRCh38 chromosome sizes, {args.wg_instances} template instances, {args.wg_paths} paths per component",
             "scaling": "strong", "n_gpus": world, "segments": V, "links": E, "path_steps": S, "components": n_comp,
             "value": E / (dev_ms * 1e-3), "unit": "edges/s", "ms_per_step": dev_ms, "steps": args.steps,
             "records_all_ranks": int(cnt[0].item()), "flubbles_all_ranks": int(cnt[1].item()), "links_all_ranks": int(cnt[2].item()),
             "lpt_load_max_over_mean": max(w) / (sum(w) / len(w)), "calls_per_step_rank0": len(own),
-            "e2e": {"value": E / (e2e_ms * 1e-3), "unit": "edges/s", "ms_per_step": e2e_ms, "steps": n_e2e, "shard_ms_max_over_ranks": shard_ms,
-                    "h2d_bytes_per_step_per_rank": 8 * E + 4 * S + 8 * V, "gathered_record_bytes": int(gathered),
-                    "note": "per step and rank: whole graph host -> HBM, device partition (labels, weights, compaction), decompose + index + one call per owned component, binary records packed in HBM; then all ranks' streams gathered on rank 0 over NCCL (N = 1: no partition, no gather)"},
+            "e2e": {"value": E / (e2e_ms * 1e-3), "unit": "edges/s", "ms_per_step": e2e_ms, "steps": n_e2e, "breakdown_ms_max_over_ranks": {"h2d_whole_graph_links_and_segments_plus_device_partition": shard_ms, "hot_path_calls_and_record_packing": hot_ms, "size_exchange_and_nccl_gather": gather_ms},
+                    "h2d_bytes_per_step_per_rank": (8 * E + 8 * V + (4 * S) // world) if world > 1 else 8 * E + 4 * S + 4 * V, "gathered_record_bytes": int(gathered),
+                    "note": "per step and rank: whole graph host -> HBM, device partition (labels, weights, compaction), decompose + index + one call per owned component, binary records packed in HBM; then all ranks' streams gathered on rank 0 over NCCL (N = 1: no partition, no gather).  Every rank needs ALL links to label the components, so that part of the ingest does not shrink with N; the walks (the bulk) travel only for the paths a rank owns"},
             "graph_generation_s": gen_s}
 
 

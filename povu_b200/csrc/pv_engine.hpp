@@ -208,7 +208,7 @@ struct Session {
 	std::vector<u32> shard_owner;          // per global component (0-based): owning rank
 	// The whole graph, kept aside by the first shard() so that the partitioning can be repeated (the multi-GPU end-to-end
 	// step re-shards from the page-locked host arrays every time): host side in `full`, device side in f_*.
-	pvh::HostGraph full; bool have_full = false, full_dev = false;
+	pvh::HostGraph full; bool have_full = false, full_dev = false, full_steps_dev = false;
 	pv::Buf<u32> f_ep1, f_ep2, f_steps, f_segLen, f_ids; pv::Buf<u64> f_lblOff; pv::Buf<u8> f_lbl;
 	std::vector<void *> full_pinned;
 	double t_shard_ms = 0;
@@ -229,19 +229,21 @@ struct Session {
 			full_pinned.swap(pinned);      // (the page-locked registrations belong to the whole graph's arrays)
 			full = std::move(g);
 			full.devE = full.ep1.empty() ? full.devE : full.ep1.size();
-			have_full = true; full_dev = true;
+			have_full = true; full_dev = true; full_steps_dev = true;
 		}
 		if (from_host && full_dev) { f_ep1.release(); f_ep2.release(); f_steps.release(); f_segLen.release(); f_ids.release(); f_lblOff.release(); f_lbl.release(); full_dev = false; }
 		const u32 V = full.V(), H = full.H(); const u64 E = full.E(); const u64 S = full.stepOff.empty() ? 0 : full.stepOff.back();
 		if (!full_dev) {   // the whole graph travels host -> HBM again (page-locked arrays: PCIe speed)
 			if ((E && full.ep1.empty()) || (S && full.steps.empty())) throw std::runtime_error("shard: the whole graph is no longer on the host");
-			f_ep1 = pv::Buf<u32>(*c, E ? E : 1); f_ep2 = pv::Buf<u32>(*c, E ? E : 1); f_steps = pv::Buf<u32>(*c, S ? S : 1); f_segLen = pv::Buf<u32>(*c, V ? V : 1); f_ids = pv::Buf<u32>(*c, V ? V : 1);
-			c->h2d(f_ep1.p, full.ep1.data(), E * 4); c->h2d(f_ep2.p, full.ep2.data(), E * 4); c->h2d(f_steps.p, full.steps.data(), S * 4);
+			// links and segments of the whole graph (the component labels need every link); of the walks only this rank's own
+			// paths will travel (shard_device, host-walk mode): f_steps stays empty
+			f_ep1 = pv::Buf<u32>(*c, E ? E : 1); f_ep2 = pv::Buf<u32>(*c, E ? E : 1); f_segLen = pv::Buf<u32>(*c, V ? V : 1); f_ids = pv::Buf<u32>(*c, V ? V : 1);
+			c->h2d(f_ep1.p, full.ep1.data(), E * 4); c->h2d(f_ep2.p, full.ep2.data(), E * 4);
 			c->h2d(f_segLen.p, full.segLen.data(), (size_t)V * 4); c->h2d(f_ids.p, full.ids.data(), (size_t)V * 4);
 			if (full.has_labels) { f_lblOff = pv::Buf<u64>(*c, full.lblOff.size()); c->h2d(f_lblOff.p, full.lblOff.data(), full.lblOff.size() * 8); f_lbl = pv::Buf<u8>(*c, full.lbl.size() ? full.lbl.size() : 1); c->h2d(f_lbl.p, full.lbl.data(), full.lbl.size()); }
-			full_dev = true;
+			full_dev = true; full_steps_dev = false;
 		}
-		pv::ShardIn in; in.V = V; in.H = H; in.E = E; in.S = S; in.ep1 = f_ep1.p; in.ep2 = f_ep2.p; in.steps = f_steps.p; in.segLen = f_segLen.p; in.ids = f_ids.p;
+		pv::ShardIn in; in.V = V; in.H = H; in.E = E; in.S = S; in.ep1 = f_ep1.p; in.ep2 = f_ep2.p; in.steps = full_steps_dev ? f_steps.p : nullptr; in.h_steps = full.steps.data(); in.segLen = f_segLen.p; in.ids = f_ids.p;
 		if (full.has_labels) { in.lblOff = f_lblOff.p; in.lbl = f_lbl.p; }
 		if (full.stepOff.empty()) full.stepOff.assign(1, 0);
 		in.h_stepOff = full.stepOff.data();

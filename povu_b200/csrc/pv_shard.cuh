@@ -24,6 +24,9 @@ struct ShardIn {      // the whole graph in HBM
 	const u32 *ep1 = nullptr, *ep2 = nullptr, *steps = nullptr, *segLen = nullptr, *ids = nullptr;
 	const u64 *lblOff = nullptr; const u8 *lbl = nullptr;      // optional (sessions opened with labels)
 	const u32 *h_stepOff = nullptr;                            // host, H + 1
+	// walks still on the host (page-locked): with `steps` == nullptr only the walks of the paths this rank ends up owning
+	// are uploaded -- a path lies inside one component, and the walks are the bulk of a pangenome (S >> E)
+	const u32 *h_steps = nullptr;
 };
 struct ShardOut {     // this rank's share, in HBM (+ the small host tables)
 	u32 V = 0; u64 E = 0, S = 0;
@@ -75,11 +78,24 @@ inline void shard_device(Ctx &c, const ShardIn &in, u32 rank, u32 world, ShardOu
 	u64 *w_ = w.p;
 	{
 		shard_weights(c, E, CompOfPort{in.ep1, lab_, compIdx_}, w_);
-		shard_weights(c, S, CompOfPort{in.steps, lab_, compIdx_}, w_);
+		if (in.steps) shard_weights(c, S, CompOfPort{in.steps, lab_, compIdx_}, w_);
 		shard_weights(c, V, CompOfVertex{lab_, compIdx_}, w_);
 	}
 	out.weight.resize(nC);
 	c.d2h(out.weight.data(), w.p, (size_t)nC * 8);
+	// walks on the host: the component of a path is the component of its first step (one small gather), its weight its length
+	std::vector<u32> pathCompH;
+	if (!in.steps) {
+		if (S && !in.h_steps) throw std::runtime_error("shard: no walks given");
+		std::vector<u32> firstV((size_t)H, NONE);
+		for (u32 h = 0; h < H; h++) if (in.h_stepOff[h + 1] > in.h_stepOff[h]) firstV[h] = in.h_steps[in.h_stepOff[h]] >> 1;
+		Buf<u32> fv(c, H ? H : 1), pc(c, H ? H : 1);
+		c.h2d(fv.p, firstV.data(), (size_t)H * 4);
+		const u32 *fv_ = fv.p; u32 *pc_ = pc.p;
+		parallel_for<P_step>(c, H, PV_LAMBDA(size_t h) { u32 v = fv_[h]; pc_[h] = v == NONE ? NONE : compIdx_[lab_[v]]; });
+		pathCompH = pc.to_host(); pathCompH.resize(H);
+		for (u32 h = 0; h < H; h++) if (pathCompH[h] != NONE) out.weight[pathCompH[h]] += in.h_stepOff[h + 1] - in.h_stepOff[h];
+	}
 	tr.mark("labels + weights");
 	// ---- the one host step: greedy longest-processing-time over nC numbers
 	std::vector<u32> order(nC);
@@ -101,23 +117,35 @@ inline void shard_device(Ctx &c, const ShardIn &in, u32 rank, u32 world, ShardOu
 	parallel_for<P_keep>(c, (size_t)V + 1, PV_LAMBDA(size_t v) { keepV_[v] = v < V ? mine_[compIdx_[lab_[v]]] : 0u; });
 	exclusive_scan(c, keepV.p, remap.p, (size_t)V + 1, OpAddU32(), 0u);
 	// ---- links and steps: keep flags, positions
-	Buf<u32> keepE(c, E + 1), posE(c, E + 1), keepS(c, S + 1), posS(c, S + 1);
-	u32 *keepE_ = keepE.p, *keepS_ = keepS.p; const u32 *posE_ = posE.p, *posS_ = posS.p;
-	{
-		const u32 *ep1 = in.ep1, *steps = in.steps;
-		parallel_for<P_keep>(c, E + 1, PV_LAMBDA(size_t e) { keepE_[e] = e < E ? keepV_[ep1[e] >> 1] : 0u; });
-		parallel_for<P_keep>(c, S + 1, PV_LAMBDA(size_t s) { keepS_[s] = s < S ? keepV_[steps[s] >> 1] : 0u; });
-	}
+	Buf<u32> keepE(c, E + 1), posE(c, E + 1), keepS, posS;
+	u32 *keepE_ = keepE.p; const u32 *posE_ = posE.p;
+	{ const u32 *ep1 = in.ep1; parallel_for<P_keep>(c, E + 1, PV_LAMBDA(size_t e) { keepE_[e] = e < E ? keepV_[ep1[e] >> 1] : 0u; }); }
 	exclusive_scan(c, keepE.p, posE.p, E + 1, OpAddU32(), 0u);
-	exclusive_scan(c, keepS.p, posS.p, S + 1, OpAddU32(), 0u);
-	// sizes + the new path offsets in ONE host wait
-	Buf<u32> offIn(c, (size_t)H + 1), offOut(c, (size_t)H + 1);
-	c.h2d(offIn.p, in.h_stepOff, ((size_t)H + 1) * 4);
-	{ const u32 *oi = offIn.p; u32 *oo = offOut.p; parallel_for<P_step>(c, (size_t)H + 1, PV_LAMBDA(size_t h) { oo[h] = posS_[oi[h]]; }); }
 	u32 nV = 0, nE = 0, nS = 0;
-	out.h_stepOff.resize((size_t)H + 1);
-	{ MultiRead mr(c); mr.add(&nV, remap.p + V, 4); mr.add(&nE, posE.p + E, 4); mr.add(&nS, posS.p + S, 4); mr.wait(); }
-	c.d2h(out.h_stepOff.data(), offOut.p, ((size_t)H + 1) * 4);
+	out.h_stepOff.assign((size_t)H + 1, 0);
+	Buf<u32> rawOwn;      // host-walk mode: the owned paths' steps as uploaded (whole-graph vertex indices)
+	if (in.steps) {
+		keepS = Buf<u32>(c, S + 1); posS = Buf<u32>(c, S + 1);
+		u32 *keepS_ = keepS.p; const u32 *posS_ = posS.p; const u32 *steps = in.steps;
+		parallel_for<P_keep>(c, S + 1, PV_LAMBDA(size_t s) { keepS_[s] = s < S ? keepV_[steps[s] >> 1] : 0u; });
+		exclusive_scan(c, keepS.p, posS.p, S + 1, OpAddU32(), 0u);
+		// sizes + the new path offsets in ONE host wait
+		Buf<u32> offIn(c, (size_t)H + 1), offOut(c, (size_t)H + 1);
+		c.h2d(offIn.p, in.h_stepOff, ((size_t)H + 1) * 4);
+		{ const u32 *oi = offIn.p; u32 *oo = offOut.p; parallel_for<P_step>(c, (size_t)H + 1, PV_LAMBDA(size_t h) { oo[h] = posS_[oi[h]]; }); }
+		{ MultiRead mr(c); mr.add(&nV, remap.p + V, 4); mr.add(&nE, posE.p + E, 4); mr.add(&nS, posS.p + S, 4); mr.wait(); }
+		c.d2h(out.h_stepOff.data(), offOut.p, ((size_t)H + 1) * 4);
+	} else {
+		u64 tot = 0;
+		for (u32 h = 0; h < H; h++) { out.h_stepOff[h] = (u32)tot; if (pathCompH[h] != NONE && mine[pathCompH[h]]) tot += in.h_stepOff[h + 1] - in.h_stepOff[h]; }
+		out.h_stepOff[H] = (u32)tot; nS = (u32)tot;
+		rawOwn = Buf<u32>(c, nS ? nS : 1);
+		for (u32 h = 0; h < H; h++) {   // one copy per owned path, straight from the page-locked walks
+			const u32 len = out.h_stepOff[h + 1] - out.h_stepOff[h];
+			if (len) c.h2d(rawOwn.p + out.h_stepOff[h], in.h_steps + in.h_stepOff[h], (size_t)len * 4);
+		}
+		{ MultiRead mr(c); mr.add(&nV, remap.p + V, 4); mr.add(&nE, posE.p + E, 4); mr.wait(); }
+	}
 	out.V = nV; out.E = nE; out.S = nS;
 	tr.mark("flags + scans");
 	// ---- compaction
@@ -132,8 +160,15 @@ inline void shard_device(Ctx &c, const ShardIn &in, u32 rank, u32 world, ShardOu
 			u32 a = ep1[e], b = ep2[e]; u32 p = posE_[e];
 			o1[p] = (remap_[a >> 1] << 1) | (a & 1u); o2[p] = (remap_[b >> 1] << 1) | (b & 1u);
 		});
-		u32 *os = out.steps.p; const u32 *steps = in.steps;
-		parallel_for<P_step>(c, S, PV_LAMBDA(size_t s) { if (keepS_[s]) { u32 x = steps[s]; os[posS_[s]] = (remap_[x >> 1] << 1) | (x & 1u); } });
+		u32 *os = out.steps.p;
+		if (in.steps) {
+			const u32 *steps = in.steps, *keepS_ = keepS.p, *posS_ = posS.p;
+			parallel_for<P_step>(c, S, PV_LAMBDA(size_t s) { if (keepS_[s]) { u32 x = steps[s]; os[posS_[s]] = (remap_[x >> 1] << 1) | (x & 1u); } });
+		} else {
+			const u32 *raw = rawOwn.p; Buf<u32> bad(c, 1); bad.zero(); u32 *bad_ = bad.p;
+			parallel_for<P_step>(c, nS, PV_LAMBDA(size_t s) { u32 x = raw[s]; if (!keepV_[x >> 1]) atomic_add(bad_, 1u); os[s] = (remap_[x >> 1] << 1) | (x & 1u); });
+			if (bad.read(0)) throw std::runtime_error("shard: a path leaves the component of its first step");
+		}
 	}
 	if (in.lblOff && in.lbl) {
 		Buf<u64> len(c, (size_t)nV + 1);

@@ -67,3 +67,41 @@ def test_shard_balance_and_coverage(emu_lib, tmp_path):
         loads.append(v + e + st)
     assert tot == [V, E, S]
     assert max(loads) <= 1.35 * (sum(loads) / 3)
+
+
+def check_reshard_repeatable(pv, n_ranks=3):
+    """pvgpu_session_reshard on ONE session, again and again: every share equals the share of a one-shot shard(), whether the
+    whole graph is still in HBM or comes from the page-locked host arrays again (then only the owned paths' walks travel);
+    the binary record stream of a share has the advertised size."""
+    g = synth.concat_components([synth.nested_bubbles(81, n_top=5), synth.snp_indel_chain(20, 4, seed=3), synth.nested_bubbles(83, n_top=4, max_depth=2),
+                                 synth.snp_indel_chain(35, 4, seed=4), synth.snp_indel_chain(12, 4, seed=5)])
+    s = api.Session.from_graph(pv, g)
+
+    def share_vcfs(sess):
+        ga = sess.graph_arrays(labels=False)
+        own = [n for k, n in enumerate(ga["path_names"]) if n.startswith("S001#1#") and ga["step_off"][k + 1] > ga["step_off"][k]]
+        sess.decompose()
+        out = {}
+        for p in own:
+            sess.call([p])
+            out[p] = sess.vcf_text(with_date=False)
+        return out, ga
+    want = []
+    for r in range(n_ranks):
+        one = api.Session.from_graph(pv, g)
+        assert one.shard(r, n_ranks) == 5
+        want.append(share_vcfs(one))
+    for from_host in (False, True, True, False):
+        for r in range(n_ranks):
+            n, _ = s.reshard(r, n_ranks, from_host=from_host)
+            assert n == 5
+            got, ga = share_vcfs(s)
+            assert got == want[r][0], (from_host, r)
+            for k in ("ids", "ep1", "ep2", "steps", "step_off"):
+                assert (ga[k] == want[r][1][k]).all(), (k, from_host, r)
+    assert s.records_packed_bytes() >= 64
+    assert sum(len(w[0]) for w in want) == 5
+
+
+def test_emu_reshard_repeatable(emu_lib):
+    check_reshard_repeatable(api.Povu(lib_path=emu_lib))

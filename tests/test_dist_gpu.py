@@ -50,3 +50,31 @@ def test_gpu_shard_large_graph_on_one_device(gpu, tmp_path):
         seen += len(own)
         s.close()
     assert seen == 24
+
+
+def test_gpu_reshard_repeatable_and_record_stream(gpu):
+    """The repeatable device-side partition (resident and from-host modes) and the packed binary record stream in HBM."""
+    import torch
+    import test_dist_emu
+    test_dist_emu.check_reshard_repeatable(gpu)
+    from povu_b200 import api, synth
+    g = synth.concat_components([synth.snp_indel_chain(60, 6, seed=1), synth.snp_indel_chain(40, 6, seed=2)])
+    s = api.Session.from_graph(gpu, g)
+    s.reshard(0, 1)
+    s.hot_path(["S001#1#chr1"])
+    need = s.records_packed_bytes()
+    buf = torch.zeros(need + 64, dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    assert s.records_pack(buf.data_ptr(), buf.numel()) == need
+    torch.cuda.synchronize()
+    h = buf.cpu().numpy()
+    hdr = h[:64].view("<u8")
+    nrec = int(s.lib.pvgpu_session_record_count(s.h))
+    assert bytes(h[:8]) == b"PVREC001" and hdr[1] == nrec and hdr[4] == len(g["paths"])
+    # left context steps carry segment ids: compare with the ids named in the VCF ID column
+    import re
+    R = nrec; pad = lambda x: (x + 7) & ~7
+    cxtL = h[64 + 2 * pad(R * 4): 64 + 2 * pad(R * 4) + R * 4].view("<u4")
+    ids_vcf = [int(re.findall(r"\d+", l.split("\t")[2])[0]) for l in s.vcf_text(with_date=False).splitlines() if not l.startswith("#")]
+    assert set((cxtL >> 1).tolist()) <= set(int(x) for x in g["ids"]) and len(ids_vcf) == nrec
+    assert set((cxtL >> 1).tolist()) == set(ids_vcf)      # the left context of a record is the first id of its ID column here (forward bubbles)
