@@ -50,6 +50,9 @@ int pvgpu_build_kind(void);
  * range-minimum / previous-smaller queries) on n seeded elements and counts disagreements with the host's std::
  * algorithms.  Not part of the reference-facing surface. */
 int pvgpu_selftest_prims(pvgpu_ctx *ctx, uint64_t n, uint64_t seed, int bits, uint64_t *mismatches);
+/* fired-arc fixpoint (decompose, D6) on a random class sequence with crossing arcs against the reference's stack machine run on
+ * the host; *rounds = fixpoint rounds (-1: not settled within 64, nothing compared) */
+int pvgpu_selftest_arcs(pvgpu_ctx *ctx, uint32_t n, uint32_t n_classes, uint64_t seed, uint64_t *mismatches, int *rounds);
 
 /* test hook (tests/test_text_emu.py, test_text_gpu.py): formats AF = ac / an for every 0 <= ac <= an <= max_an (and some
  * integers) with the device text writer and counts disagreements with the C library's "%.1f" / "%u". */
@@ -70,6 +73,9 @@ uint64_t pvgpu_flubbles_count(const pvgpu_flubbles *f);
 uint32_t pvgpu_flubbles_component_count(const pvgpu_flubbles *f);
 uint32_t pvgpu_flubbles_dfs_rounds(const pvgpu_flubbles *f);
 uint32_t pvgpu_flubbles_hash_collisions(const pvgpu_flubbles *f);
+/* rounds of the fired-arc fixpoint that decides which class re-encounters still find their previous occurrence on the reference's
+ * stack (0 = every component laminar; more than 64 = the sequential replay ran instead) */
+uint32_t pvgpu_flubbles_arc_rounds(const pvgpu_flubbles *f);
 /* any pointer may be NULL.  a_v/z_v are vertex indices; a_fwd/z_fwd 1 = '>' 0 = '<'. */
 void pvgpu_flubbles_copy(const pvgpu_flubbles *f, uint32_t *comp, uint32_t *a_v, uint8_t *a_fwd, uint32_t *z_v,
 			 uint8_t *z_fwd, uint32_t *parent, uint32_t *depth);

@@ -48,6 +48,8 @@ def load_library(lib_path=None):
     lib.pvgpu_profile_json.restype = C.c_size_t
     lib.pvgpu_selftest_prims.argtypes = [vp, u64, u64, C.c_int, C.POINTER(u64)]
     lib.pvgpu_selftest_prims.restype = C.c_int
+    lib.pvgpu_selftest_arcs.argtypes = [vp, u32, u32, u64, C.POINTER(u64), C.POINTER(C.c_int)]
+    lib.pvgpu_selftest_arcs.restype = C.c_int
     lib.pvgpu_selftest_text.argtypes = [vp, u32, C.POINTER(u64)]
     lib.pvgpu_decompose.argtypes = [vp, u32, u64, vp, vp, u32, C.POINTER(vp)]
     lib.pvgpu_decompose.restype = C.c_int
@@ -61,6 +63,8 @@ def load_library(lib_path=None):
     lib.pvgpu_flubbles_dfs_rounds.restype = u32
     lib.pvgpu_flubbles_hash_collisions.argtypes = [vp]
     lib.pvgpu_flubbles_hash_collisions.restype = u32
+    lib.pvgpu_flubbles_arc_rounds.argtypes = [vp]
+    lib.pvgpu_flubbles_arc_rounds.restype = u32
     lib.pvgpu_flubbles_copy.argtypes = [vp, P32, P32, P8, P32, P8, P32, P32]
     lib.pvgpu_flubbles_copy_components.argtypes = [vp, P32, P32, P32, P32, P32]
     lib.pvgpu_flubbles_stack_size.argtypes = [vp]
@@ -156,6 +160,7 @@ class Flubbles:
             lib.pvgpu_flubbles_copy_stack(h, _as_ptr(self.stack_v, C.c_uint32), _as_ptr(self.stack_class, C.c_uint32),
                                           _as_ptr(self.stack_fwd, C.c_uint32))
         self.dfs_rounds = lib.pvgpu_flubbles_dfs_rounds(h)
+        self.arc_rounds = lib.pvgpu_flubbles_arc_rounds(h)
         self.n = int(n)
 
     def labels(self, ids):
@@ -230,6 +235,13 @@ class Povu:
         if self.lib.pvgpu_selftest_text(self.h, int(max_an), C.byref(bad)) != 0:
             raise RuntimeError(self._err())
         return int(bad.value)
+
+    def selftest_arcs(self, n, n_classes, seed=1):
+        """Fired-arc fixpoint vs the reference's stack machine on a random class sequence; returns (mismatches, rounds)."""
+        bad, rounds = C.c_uint64(0), C.c_int(0)
+        if self.lib.pvgpu_selftest_arcs(self.h, int(n), int(n_classes), int(seed), C.byref(bad), C.byref(rounds)) != 0:
+            raise RuntimeError("povu_b200: " + self.lib.pvgpu_last_error(self.h).decode())
+        return int(bad.value), int(rounds.value)
 
     def selftest_prims(self, n, seed=1, bits=32):
         """Device primitives (pair sort, scans, RMQ) against the host's std:: algorithms; returns the mismatch count."""

@@ -102,6 +102,7 @@ uint64_t pvgpu_flubbles_count(const pvgpu_flubbles *f) { return f->o.a_v.size();
 uint32_t pvgpu_flubbles_component_count(const pvgpu_flubbles *f) { return (uint32_t)f->o.comp_root.size(); }
 uint32_t pvgpu_flubbles_dfs_rounds(const pvgpu_flubbles *f) { return f->o.dfs_rounds; }
 uint32_t pvgpu_flubbles_hash_collisions(const pvgpu_flubbles *f) { return f->o.collisions; }
+uint32_t pvgpu_flubbles_arc_rounds(const pvgpu_flubbles *f) { return f->o.arc_rounds; }
 void pvgpu_flubbles_copy(const pvgpu_flubbles *f, uint32_t *comp, uint32_t *a_v, uint8_t *a_fwd, uint32_t *z_v, uint8_t *z_fwd, uint32_t *parent, uint32_t *depth) {
 	cp(comp, f->o.comp); cp(a_v, f->o.a_v); cp(a_fwd, f->o.a_fwd); cp(z_v, f->o.z_v); cp(z_fwd, f->o.z_fwd); cp(parent, f->o.parent); cp(depth, f->o.depth);
 }
@@ -215,6 +216,41 @@ int pvgpu_selftest_prims(pvgpu_ctx *x, uint64_t n, uint64_t seed, int bits, uint
 			}
 		}
 		c.sync();
+		*mismatches = bad;
+		return 0;
+	} catch (std::exception &e) { x->err = e.what(); return 1; }
+}
+
+/* ---------------------------------------------------------------- fired-arc fixpoint self-test (tests/test_prims_*.py)
+ * a random class sequence with crossing arcs; device fixpoint vs the reference's stack machine (flubbles.cpp:295-367) on the host */
+int pvgpu_selftest_arcs(pvgpu_ctx *x, uint32_t n, uint32_t n_classes, uint64_t seed, uint64_t *mismatches, int *rounds) {
+	if (!x || !mismatches || n == 0 || n_classes == 0) return 1;
+	*mismatches = 0;
+	try {
+		PV_SET_DEVICE(x);
+		using namespace pv;
+		Ctx &c = x->c;
+		std::vector<u32> cls(n), prv(n, NONE), last(n_classes, NONE);
+		for (u32 i = 0; i < n; i++) {
+			u64 z = splitmix64(seed + i);
+			// mostly fresh classes with bursts of re-encounters of recent ones: nested AND crossing arcs
+			cls[i] = (z % 3 == 0) ? (u32)((z >> 8) % n_classes) : (u32)(((z >> 8) % 7 + i / 5) % n_classes);
+			prv[i] = last[cls[i]]; last[cls[i]] = i;
+		}
+		// the reference's stack machine
+		std::vector<u32> want(n, 2), stk; std::vector<u8> on(n, 0);
+		for (u32 i = 0; i < n; i++) {
+			u32 p = prv[i];
+			if (p != NONE && on[p]) { want[i] = 1; while (!stk.empty()) { u32 q = stk.back(); stk.pop_back(); on[q] = 0; if (q == p) break; } }
+			stk.push_back(i); on[i] = 1;
+		}
+		Buf<u32> dprv(c, n), fire(c, n);
+		c.h2d(dprv.p, prv.data(), (size_t)n * 4);
+		int r = fired_arcs(c, dprv.p, n, fire.p, nullptr, nullptr, nullptr, nullptr);
+		if (rounds) *rounds = r;
+		std::vector<u32> got = fire.to_host();
+		u64 bad = 0;
+		if (r >= 0) for (u32 i = 0; i < n; i++) if (got[i] != want[i]) bad++;
 		*mismatches = bad;
 		return 0;
 	} catch (std::exception &e) { x->err = e.what(); return 1; }

@@ -41,11 +41,12 @@ struct DecompOut {
 	std::vector<u32> stack_class;   // dense class id per position
 	std::vector<u32> stack_fwd;
 	u32 dfs_rounds = 0;
+	u32 arc_rounds = 0;      // rounds of the fired-arc fixpoint (0 = every component laminar; > 64 = the sequential replay ran)
 	u32 collisions = 0;
 	void reset() {   // keeps the (page-locked) capacity of the big arrays
 		comp.clear(); a_v.clear(); z_v.clear(); a_fwd.clear(); z_fwd.clear(); parent.clear(); depth.clear(); fl_base.clear();
 		comp_root.clear(); comp_nv.clear(); comp_nfl.clear(); comp_has_tips.clear(); comp_nonlaminar.clear();
-		stack_v.clear(); stack_class.clear(); stack_fwd.clear(); dfs_rounds = 0; collisions = 0;
+		stack_v.clear(); stack_class.clear(); stack_fwd.clear(); dfs_rounds = 0; arc_rounds = 0; collisions = 0;
 	}
 };
 
@@ -210,6 +211,54 @@ PV_DEV void uf_union_hashed(u32 *uf, u32 a, u32 b) {
 		if (uf_priority(a) > uf_priority(b)) { u32 t = a; a = b; b = t; }     // a = lower priority: it goes under b
 		if (atomic_cas(uf + a, a, b) == a) return;
 	}
+}
+
+// Which class re-encounters still find their previous occurrence on the reference's stack?  (see D6 in decompose_device)
+// prv[i] = previous stack position of i's class or NONE.  fire[i]: 1 = the arc (prv[i], i) fires, 2 = dead or no arc.
+// Returns the number of fixpoint rounds after the laminarity pass (0 = no two arcs cross), -1 if undecided arcs remain after
+// 64 rounds (fire[] then holds 0 for them).  segComp / lamBad (optional): component of every position -> "has crossing arcs".
+// extra_src / extra_dst (optional): one more device word read with the first host wait (the caller's flubble count).
+inline int fired_arcs(Ctx &c, const u32 *prv_, u32 nS, u32 *fire_, const u32 *segComp_, u32 *lamBad_, const u32 *extra_src, u32 *extra_dst) {
+	Buf<u32> arcA(c, nS ? nS : 1), fl(c, 1);
+	u32 *arcA_ = arcA.p, *fl_ = fl.p;
+	fl.zero();
+	parallel_for<K_arc>(c, nS, PV_LAMBDA(size_t i) { arcA_[i] = prv_[i]; });   // NONE = no arc = +inf
+	{
+		Rmq rmqA;
+		rmq_build(c, rmqA, arcA.p, nS);
+		RmqView rv = rmqA.view();
+		parallel_for<K_lam>(c, nS, PV_LAMBDA(size_t i) {
+			u32 p = prv_[i];
+			if (p == NONE) { fire_[i] = 2; return; }
+			bool crossed = (u32)i > p + 1 && rv.query(p + 1, (u32)i - 1) < p;
+			fire_[i] = crossed ? 0u : 1u;
+			if (crossed) { fl_[0] = 1; if (lamBad_) lamBad_[segComp_[i]] = 1; }
+		});
+	}
+	u32 undecided = 0;
+	{ MultiRead mr(c); if (extra_src) mr.add(extra_dst, extra_src, 4); mr.add(&undecided, fl.p, 4); mr.wait(); }
+	int rounds = 0;
+	if (undecided) {
+		Buf<u32> arcF(c, nS);
+		u32 *arcF_ = arcF.p;
+		while (undecided) {
+			if (++rounds > 64) return -1;
+			parallel_for<K_arc>(c, nS, PV_LAMBDA(size_t i) { u32 st = fire_[i]; u32 p = prv_[i]; arcA_[i] = st == 2 ? NONE : p; arcF_[i] = st == 1 ? p : NONE; });
+			Rmq rmqA, rmqF;
+			rmq_build(c, rmqA, arcA.p, nS); rmq_build(c, rmqF, arcF.p, nS);
+			RmqView ra = rmqA.view(), rf = rmqF.view();
+			fl.zero();
+			parallel_for<K_lam>(c, nS, PV_LAMBDA(size_t i) {
+				if (fire_[i] != 0) return;
+				u32 p = prv_[i];
+				if (ra.query(p + 1, (u32)i - 1) >= p) { fire_[i] = 1; return; }      // nothing left that could cross it
+				if (rf.query(p + 1, (u32)i - 1) < p) { fire_[i] = 2; return; }       // crossed by an arc that fires: p was popped
+				fl_[0] = 1;
+			});
+			undecided = fl.read(0);
+		}
+	}
+	return rounds;
 }
 
 inline void decompose_device(Ctx &c, u32 V, u64 E, const u32 *ep1, const u32 *ep2, const DecompOpts &opt, DecompOut &out) {
@@ -731,35 +780,34 @@ inline void decompose_device(Ctx &c, u32 V, u64 E, const u32 *ep1, const u32 *ep
 	tr.mark("D5 stack+sort");
 	sm.mark();   // 7
 	// ------------------------------------------------------------------ D6: flubbles + PVST parents
-	Buf<u32> segComp(c, nS), notNext(c, nS), lamBad(c, nComp ? nComp : 1);
-	u32 *segComp_ = segComp.p, *notNext_ = notNext.p, *lamBad_ = lamBad.p;
+	// A class met again at stack position i closes what was opened since its previous occurrence p = prv[i] -- IF p is still on
+	// the reference's stack: an earlier re-encounter (p', j) with p' < p < j < i has popped p with everything above p'
+	// (add_flubbles, flubbles.cpp:295-367).  "Arc (p, i) fires" is therefore: no FIRED arc crosses it from the left.  In a
+	// laminar component no arcs cross at all and every arc fires (one range-minimum pass shows it); otherwise the fired set is the
+	// fixpoint of: an arc with no possible crosser fires, an arc crossed by a fired arc is dead -- the undecided arc with the
+	// smallest right end is always decidable, and real graphs (LPA's repeat loop) settle in a few rounds.  Every round is one
+	// range-minimum structure per status plus one kernel; the stack machine itself (one thread walking a whole chromosome) is
+	// only the fallback for inputs that do not settle within 64 rounds.
+	Buf<u32> segComp(c, nS), fire(c, nS), lamBad(c, nComp ? nComp : 1);
+	u32 *segComp_ = segComp.p, *fire_ = fire.p, *lamBad_ = lamBad.p;
 	lamBad.zero();
-	parallel_for<K_arc>(c, nS, PV_LAMBDA(size_t i) { segComp_[i] = compIdxOfRoot_[gcomp_[stV_[i]]]; notNext_[i] = ~nxt_[i]; });
-	Rmq rmq3;
-	rmq_build(c, rmq3, notNext.p, nS);
-	{
-		RmqView rv = rmq3.view();
-		parallel_for<K_lam>(c, nS, PV_LAMBDA(size_t i) {
-			u32 b = nxt_[i];
-			if (b <= (u32)i + 1) return;
-			u32 mx = ~rv.query((u32)i + 1, b - 1);
-			if (mx > b) lamBad_[segComp_[i]] = 1;
-		});
-	}
+	parallel_for<K_arc>(c, nS, PV_LAMBDA(size_t i) { segComp_[i] = compIdxOfRoot_[gcomp_[stV_[i]]]; });
 	Buf<u32> open(c, nS + 1), flIdx(c, nS + 1);
 	Buf<MP> fn(c, nS), fnS(c, nS);
 	u32 *open_ = open.p, *flIdx_ = flIdx.p; MP *fn_ = fn.p, *fnS_ = fnS.p;
-	parallel_for<K_fn>(c, (size_t)nS + 1, PV_LAMBDA(size_t i) {
-		if (i >= nS) { open_[i] = 0; return; }
-		u32 o = nxt_[i] > (u32)i + 1 ? 1u : 0u;
-		u32 u = prv_[i] != NONE ? 1u : 0u;
-		open_[i] = o;
+	parallel_for<K_fn>(c, (size_t)nS + 1, PV_LAMBDA(size_t i) { open_[i] = i < nS && nxt_[i] > (u32)i + 1 ? 1u : 0u; });
+	exclusive_scan(c, open.p, flIdx.p, (size_t)nS + 1, OpAddU32(), 0u);
+	u32 nFl = 0;
+	const int arcRounds = fired_arcs(c, prv.p, nS, fire.p, segComp.p, lamBad.p, flIdx.p + nS, &nFl);
+	out.arc_rounds = arcRounds < 0 ? 65u : (u32)arcRounds;
+	const bool replay = arcRounds < 0;      // the sequential fallback
+	parallel_for<K_fn>(c, nS, PV_LAMBDA(size_t i) {
+		u32 o = open_[i];
+		u32 u = fire_[i] == 1 ? 1u : 0u;
 		bool first = i == 0 || segComp_[i - 1] != segComp_[i];
 		fn_[i] = MP{first ? -(1 << 29) : (i32)o - (i32)u, (i32)o};
 	});
-	exclusive_scan(c, open.p, flIdx.p, (size_t)nS + 1, OpAddU32(), 0u);
 	inclusive_scan(c, fn.p, fnS.p, nS, OpMP(), MP{0, -(1 << 29)});
-	u32 nFl = flIdx.read(nS);
 	Buf<u8> fAf(c, nFl ? nFl : 1), fZf(c, nFl ? nFl : 1);
 	u8 *fAf_ = fAf.p, *fZf_ = fZf.p;
 	Buf<u32> fBase(c, nFl ? nFl : 1);
@@ -786,7 +834,7 @@ inline void decompose_device(Ctx &c, u32 V, u64 E, const u32 *ep1, const u32 *ep
 		RmqView rv = rmq4.view();
 		parallel_for<K_parent>(c, nFl, PV_LAMBDA(size_t f) {
 			u32 d = fDepth_[f]; u32 k = fComp_[f];
-			if (lamBad_[k]) return;
+			if (replay && lamBad_[k]) return;
 			u32 par = 0;
 			if (d > 1 && f > 0) {
 				u32 j = rv.prev_smaller((u32)f - 1, d);
@@ -798,10 +846,10 @@ inline void decompose_device(Ctx &c, u32 V, u64 E, const u32 *ep1, const u32 *ep
 	// non-laminar components: replay the reference's stack machine, one thread per component.  The stack holds at most one
 	// entry per class (a re-encountered class pops down to its previous entry first), so "is my class on the stack" is "is my
 	// previous occurrence still on the stack": positions stand in for class ids.
-	Buf<u32> inS(c, nS), stk(c, nS);
-	inS.zero();
+	Buf<u32> inS(c, replay ? nS : 1), stk(c, replay ? nS : 1);
+	if (replay) inS.zero();
 	u32 *inS_ = inS.p, *stk_ = stk.p;
-	parallel_for<K_seq>(c, nComp, PV_LAMBDA(size_t k) {
+	if (replay) parallel_for<K_seq>(c, nComp, PV_LAMBDA(size_t k) {
 		if (!lamBad_[k]) return;
 		u32 b = cSegBase_[k], e = cSegBase_[k + 1], fb = cFlBase_[k];
 		u32 top = b;           // stack occupies stk_[b .. top)

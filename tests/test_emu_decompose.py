@@ -69,3 +69,8 @@ def test_emu_is_not_the_default_library(emu_lib):
     lib = api.load_library(emu_lib)
     assert lib.pvgpu_build_kind() == 2
     assert api.load_library().pvgpu_build_kind() == 1
+
+
+def test_emu_fired_arcs_fixpoint(emu_lib):
+    import test_prims_gpu
+    test_prims_gpu.check_fired_arcs(_ctx(emu_lib, 2))

@@ -19,3 +19,20 @@ def test_prims_large(gpu):
     assert gpu.selftest_prims(5_000_000, seed=10, bits=32) == 0
     for rep in range(20):                                           # repeated launches reuse the epoch-tagged scratch
         assert gpu.selftest_prims(300_000 + rep, seed=100 + rep, bits=32) == 0
+
+
+def check_fired_arcs(pv):
+    """Which class re-encounters still find their previous occurrence on the reference's stack (decompose D6): the device
+    fixpoint against the stack machine itself on random class sequences full of crossing arcs.  Real class stacks have no
+    crossing arcs at all (LPA, every fixture, thousands of random graphs: 0 rounds), so this is the only place the rounds run."""
+    settled = 0
+    for n, k in [(10, 3), (50, 10), (200, 30), (1000, 100), (3000, 1500)]:
+        for seed in range(12):
+            bad, rounds = pv.selftest_arcs(n, k, seed * 977 + n)
+            assert bad == 0, (n, k, seed, bad, rounds)
+            settled += rounds >= 0
+    assert settled >= 40
+
+
+def test_gpu_fired_arcs_fixpoint(gpu):
+    check_fired_arcs(gpu)
