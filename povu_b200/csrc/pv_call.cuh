@@ -45,6 +45,7 @@ PV_KERNEL(C_bfs, 128);
 PV_KERNEL(C_gather, 16);
 PV_KERNEL(C_rovmeta, 24);
 PV_KERNEL(C_hash, 16);
+PV_KERNEL(C_region, 72);        // per region lane: its share of the step lists in, cells + laps + context counts out (C3 + C4 + C5a fused)
 PV_KERNEL(C_matfill, 24);       // per (region, column): the vertex's step list in, one cell per visiting path out
 PV_KERNEL(C_lap, 16);
 PV_KERNEL(C_pair_count, 16);    // per (region, path): two matrix rows in, a count out
@@ -579,7 +580,7 @@ struct CandView { u32 *cL, *cR, *cStart, *cLen, *cRS, *cRL, *cHap, *cCls, *cHead
 PV_DEV u32 scan_pair(const ChunkView &cv, u32 refLocal, u32 k, u32 row, bool fill, const CandView &cd, u32 off) {
 	const RovView &rv = cv.rv; const GraphView &g = cv.g;
 	u32 r = rv.row2rov(row); u32 i = row - rv.rowBase(r);
-	if (i == refLocal || cv.tangled[r]) return 0;
+	if (i == refLocal || ld_volatile(cv.tangled + r)) return 0;      // (volatile: in the fused region kernel another lane's atomic set it moments ago)
 	if (k > 0 && !cv.hasData[r]) return 0;     // comp_exps returned after the first ref (overlay.cpp:531-532)
 	u32 J = rv.J(r);
 	const u16 *rr = cv.mat + rv.matBase(r) + (u64)refLocal * J, *ar = cv.mat + rv.matBase(r) + (u64)i * J;
@@ -653,21 +654,28 @@ PV_KERNEL(S_pinpack, 40);
 
 // comp_exps over every matrix of a view (overlay.cpp:348-588) for all ref paths, then records + genotypes
 // (vcf.cpp:20-121,241-273); results are appended to `out`.
+// tangled_seen (optional): receives errs[3] (tangled regions counted so far) with the first host wait of the pass
 inline void overlay_pass(Ctx &c, const DevGraph &G, const GraphView &g, const CallIn &in, const RovView &rv, const ChunkView &cv, u32 Rc, u32 nRows,
-			 Records &out, Trace &tr, PinStore &pins) {
+			 Records &out, Trace &tr, PinStore &pins, u32 *tangled_seen = nullptr, Buf<u32> *pairCnt0 = nullptr) {
 	const u32 nRefs = in.nRefs; const u32 uniformNh = rv.uniformNh;
 	for (u32 k = 0; k < nRefs; k++) {
 		const u32 refH = in.refs[k];
 		const u32 refLocal = G.hapLocal[refH];
 		const u32 refStep0 = G.h_stepOff[refH];
 		// ---- C5a: contexts per (region, path) pair
-		Buf<u32> pairCnt(c, (size_t)nRows + 1), candOff(c, (size_t)nRows + 1);
-		u32 *pairCnt_ = pairCnt.p; const u32 *candOff_ = candOff.p;
-		parallel_for<C_pair_count>(c, (size_t)nRows + 1, PV_LAMBDA(size_t row) {
-			pairCnt_[row] = row < nRows ? scan_pair(cv, refLocal, k, (u32)row, false, CandView{}, 0) : 0u;
-		});
+		Buf<u32> pairCnt, candOff(c, (size_t)nRows + 1);
+		if (k == 0 && pairCnt0) pairCnt = std::move(*pairCnt0);      // counted by the fused region kernel
+		else {
+			pairCnt = Buf<u32>(c, (size_t)nRows + 1);
+			u32 *pairCnt_ = pairCnt.p;
+			parallel_for<C_pair_count>(c, (size_t)nRows + 1, PV_LAMBDA(size_t row) {
+				pairCnt_[row] = row < nRows ? scan_pair(cv, refLocal, k, (u32)row, false, CandView{}, 0) : 0u;
+			});
+		}
+		const u32 *candOff_ = candOff.p;
 		exclusive_scan(c, pairCnt.p, candOff.p, (size_t)nRows + 1, OpAddU32(), 0u);
-		const u32 nCand = candOff.read(nRows);
+		u32 nCand = 0;
+		{ MultiRead mr(c); mr.add(&nCand, candOff.p + nRows, 4); if (tangled_seen && k == 0) mr.add(tangled_seen, cv.errs + 3, 4); mr.wait(); }
 		const size_t nC1 = nCand ? nCand : 1;
 		Buf<u32> cL(c, nC1), cR(c, nC1), cStart(c, nC1), cLen(c, nC1), cRS(c, nC1), cRL(c, nC1), cHap(c, nC1), cCls(c, nC1), cHead(c, nC1), gCount(c, nC1), hsort(c, nC1);
 		Buf<u32> pinCount(c, 1); pinCount.zero();
@@ -1735,6 +1743,58 @@ inline void call_device(Ctx &c, const DevGraph &G, const CallIn &in, const CallO
 		const RovView rv{rovOff.p, rovVerts.p, rovComp.p, rowPre.p, cellPre.p, hkey.p, hval.p, hsize - 1, Rc, uniformNh, r0, nullptr, nullptr};
 		const ChunkView cv{g, rv, mat.p, lapStart.p, lapLen.p, rovTangled_ + r0, hasData.p, errs.p};
 		tr.mark("chunk setup");
+		// ---- C3 + C4 + the first pass of C5 as ONE kernel, one warp per region (GPU build): the lanes stride over the step lists of
+		// the region's vertices (depth cells, first steps), then over its rows (lap 0), then over its rows again (contexts of every
+		// path against the first reference path) -- the three kernels below run back to back on data the same SM just wrote,
+		// and the per-row index arithmetic (region of a row, matrix base, row base) is done once per region.
+		Buf<u32> pairCnt0;
+		bool fused = false;
+#ifndef PV_EMU
+		// Measured: with 16 paths a warp per region idles half its lanes and loses (703 vs 405 us for the three kernels at cfg2);
+		// with 464 paths it wins (4.7 vs 7.7 ms at 200 k bubbles).  Regions with >= 48 rows on average take the fused kernel.
+		fused = (getenv("POVU_B200_FUSED_REGION") != nullptr || (u64)nRows >= 48ull * Rc) && getenv("POVU_B200_NO_FUSED_REGION") == nullptr && nRows > 0;
+		if (fused) {
+			pairCnt0 = Buf<u32>(c, (size_t)nRows + 1);
+			u32 *pc0 = pairCnt0.p;
+			const u32 ref0Local = G.hapLocal[in.refs[0]];
+			parallel_for<C_region>(c, (size_t)Rc * 32, PV_LAMBDA(size_t t) {
+				const u32 r = (u32)(t >> 5), lane = (u32)(t & 31);
+				const u32 J = rv.J(r), comp = rv.comp(r), rb = rv.rowBase(r), nh = rv.rowBase(r + 1) - rb;
+				const u64 mb = rv.matBase(r);
+				for (u32 j = 0; j < J; j++) {
+					const u32 v = rv.vert(r, j);
+					const u32 a = g.vsOff[v], ee = g.vsOff[v + 1];
+					for (u32 e = a + lane; e < ee; e += 32) {
+						const u32 hs = g.vsHap[e]; u32 h = hs >> 1;
+						if (e > a && (g.vsHap[e - 1] >> 1) == h) continue;   // not the head of its run
+						u32 first = g.vsStep[e]; u32 n = 1;
+						while (e + n < ee && (g.vsHap[e + n] >> 1) == h) n++;
+						if (g.pathComp[h] != comp) continue;   // cannot happen for a connected walk; keeps indexing safe
+						u32 i = g.hapLocal[h];
+						if (n > 0xFFFEu) { atomic_add(cv.errs + 2, 1u); n = 0xFFFEu; }
+						u32 code = n == 1 ? ((hs & 1u) ? 2u : 1u) : n;
+						cv.mat[mb + (u64)i * J + j] = (u16)code;
+						atomic_min(cv.lapStart + rb + i, first);
+						if (n > 1 && (j == 0 || j == J - 1) && atomic_exch(cv.tangled + r, 1u) == 0) atomic_add(cv.errs + 3, 1u);
+					}
+				}
+				__threadfence_block(); __syncwarp();
+				for (u32 i = lane; i < nh; i += 32) {
+					const u32 row = rb + i;
+					u32 s0 = ld_cg(cv.lapStart + row);
+					if (s0 == NONE) { cv.lapLen[row] = 0; continue; }
+					u32 hh = ub_u32(g.stepOff, 0, g.H + 1, s0) - 1;
+					u32 end = g.stepOff[hh + 1];
+					u32 len = 1;
+					while (s0 + len < end && rv.find(r, g.steps[s0 + len] >> 1) != NONE) len++;
+					cv.lapLen[row] = len;
+				}
+				__threadfence_block(); __syncwarp();
+				for (u32 i = lane; i < nh; i += 32) pc0[rb + i] = scan_pair(cv, ref0Local, 0, rb + i, false, CandView{}, 0);
+				if (r == Rc - 1 && lane == 0) pc0[nRows] = 0;
+			});
+		}
+#endif
 		// ---- C3: depth matrix (allele.hpp:804-862), one thread per (region, column)
 		u32 colBase, colEnd;
 		if (chunkEnd.size() == 1) { colBase = 0; colEnd = sumJ; } else { colBase = rovOff.read(r0); colEnd = rovOff.read(r1); }
@@ -1745,7 +1805,8 @@ inline void call_device(Ctx &c, const DevGraph &G, const CallIn &in, const CallO
 		u32 LW = 1;
 		{ const u64 meanList = G.V ? (u64)G.S / G.V : 0; LW = meanList >= 64 ? 32u : (meanList >= 32 ? 8u : 1u); }   // (every lane repeats the column setup: short lists keep one lane)
 		if (const char *e = getenv("POVU_B200_MATFILL_LANES")) { u32 v = (u32)strtoul(e, nullptr, 10); if (v >= 1 && v <= 32) LW = v; }   // tests: force the multi-lane path
-		if (LW == 1) parallel_for<C_matfill>(c, nCols, PV_LAMBDA(size_t x) {   // short lists: one thread walks the list run by run
+		if (fused) { }
+		else if (LW == 1) parallel_for<C_matfill>(c, nCols, PV_LAMBDA(size_t x) {   // short lists: one thread walks the list run by run
 			u32 r = ub_u32(rovOff_ + r0, 0, Rc + 1, colBase + (u32)x) - 1;
 			u32 J = rv.J(r); u32 j = colBase + (u32)x - rovOff_[r0 + r];
 			u32 v = rovVerts_[colBase + x];
@@ -1786,7 +1847,7 @@ inline void call_device(Ctx &c, const DevGraph &G, const CallIn &in, const CallO
 			}
 		});
 		// ---- C4: lap 0 of every (region, path): the first run of consecutive steps on region vertices (untangle.cpp:29-103)
-		parallel_for<C_lap>(c, nRows, PV_LAMBDA(size_t row) {
+		if (!fused) parallel_for<C_lap>(c, nRows, PV_LAMBDA(size_t row) {
 			u32 s = cv.lapStart[row];
 			if (s == NONE) { cv.lapLen[row] = 0; return; }
 			u32 r = rv.row2rov((u32)row);
@@ -1798,26 +1859,22 @@ inline void call_device(Ctx &c, const DevGraph &G, const CallIn &in, const CallO
 		});
 		tr.mark("C3 C4 matrix+laps");
 
-		overlay_pass(c, G, g, in, rv, cv, Rc, nRows, out, tr, pins);
-		{
-			u32 he3 = errs.read(3);
-			if (he3 != seenTangled) { seenTangled = he3; tangled_pass(c, G, g, in, rv, cv, Rc, rovTangled_ + r0, errs.p, out, tr, pins); }
-		}
+		u32 he3 = seenTangled;
+		overlay_pass(c, G, g, in, rv, cv, Rc, nRows, out, tr, pins, &he3, fused ? &pairCnt0 : nullptr);      // (the tangled flags were set by C_matfill above)
+		if (he3 != seenTangled) { seenTangled = he3; tangled_pass(c, G, g, in, rv, cv, Rc, rovTangled_ + r0, errs.p, out, tr, pins); }
 		r0 = r1;
 	}
-	rovTangled.to_hvec(out.rov_tangled, R);
-	c.sync();
+	rovTangled.to_hvec(out.rov_tangled, R);      // (asynchronous: complete after the wait below)
 	out.n_regions = R;
 	out.n_pin_pairs = pins.total;
 	if (pins.total) sne_pass(c, G, g, in, pins, R, errs.p, out, tr);
-	out.rov_tangled.resize(out.rov_fl.size(), 0);
 	u32 he[8];
-	{ MultiRead mr(c); mr.add(hc, cnt.p, 32); mr.add(he, errs.p, 32); mr.wait(); }
+	{ MultiRead mr(c); mr.add(hc, cnt.p, 32); mr.add(he, errs.p, 32); mr.wait(); }      // one wait: counters + every copy queued above
+	out.rov_tangled.resize(out.rov_fl.size(), 0);
 	out.n_sort_failed = hc[1]; out.n_too_small = hc[2];
 	out.n_hard_errors = he[0] + hc[4]; out.n_subr_clamped = he[4];
 	if (he[2]) throw std::runtime_error("call: a path visits one vertex more than 65534 times inside a region (u16 depth cell overflow)");
 	for (u32 t : out.rov_tangled) if (t) out.n_tangled++;
-	c.sync();
 }
 
 } // namespace pv

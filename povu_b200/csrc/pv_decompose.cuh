@@ -172,12 +172,13 @@ struct OpMP {
 	}
 };
 
-struct EdgeMinPort { const u32 *ep1, *ep2; PV_DEV u32 operator()(size_t e) const { u32 a = ep1[e], b = ep2[e]; return a < b ? a : b; } };
-// port of adjacency entry j: entries 2k / 2k+1 are the two ends of the k-th edge in renumbered order
+// lower (raw) port of the link that entry x = 2e + end belongs to: the major key of the reference's renumbered edge order
+struct EntryMinPort { const u32 *ep1, *ep2; PV_DEV u32 operator()(size_t x) const { u32 a = ep1[x >> 1], b = ep2[x >> 1]; return a < b ? a : b; } };
+// port of adjacency entry x: entries 2e / 2e+1 are the two ends of link e (file order)
 struct EntryPort {
-	const u32 *eord, *ep1, *ep2;
+	const u32 *ep1, *ep2;
 	PV_DEV u32 operator()(size_t j) const {
-		u32 e = eord[j >> 1]; u32 a = ep1[e], b = ep2[e];
+		u32 e = (u32)(j >> 1); u32 a = ep1[e], b = ep2[e];
 		if ((a >> 1) == (b >> 1)) { a = a & ~1u; b = a | 1u; }   // any self-loop becomes left--right (bidirected.cpp:66-77,526-531)
 		return (j & 1u) ? b : a;
 	}
@@ -274,19 +275,16 @@ inline void decompose_device(Ctx &c, u32 V, u64 E, const u32 *ep1, const u32 *ep
 	// ------------------------------------------------------------------ D1: CSR in reference edge order
 	Buf<u32> adjOff(c, P + 1), adjNbr(c, M ? M : 1), adjOwner(c, M ? M : 1), rev(c, M ? M : 1), origDeg(c, P);
 	{
-		// Both orders are "group by port, keep the input order inside a port", and a port holds a handful of entries:
-		// group_indices (count / slot / per-group insertion sort; hub ports take the restricted stable sort) instead of
-		// two full radix sorts.
-		Buf<u32> eord(c, E ? E : 1), eOff(c, (size_t)P + 1);
+		// The adjacency of a port lists its links in the reference's per-component RENUMBERED edge order = (lower port of the
+		// link, file order).  Entry x = 2e + end of link e therefore sorts, inside its port's group, by (min port of e, x): one
+		// grouping of the 2E entries with that secondary key (count / slot / per-group insertion sort; hub ports take the two-key
+		// radix sort) -- the renumbered edge index itself is never needed.
 		origDeg.zero();
 		u32 *origDeg_ = origDeg.p;
 		parallel_for<K_minport>(c, E, PV_LAMBDA(size_t e) { atomic_add(origDeg_ + ep1[e], 1u); atomic_add(origDeg_ + ep2[e], 1u); });
-		group_indices(c, EdgeMinPort{ep1, ep2}, E, P, eOff.p, eord.p);   // (min port, file order) = renumbered edge idx
-		eOff.release();
-		// entries 2k / 2k+1 = the two ends of the k-th renumbered edge, grouped by port -> the adjacency and its offsets
 		Buf<u32> list(c, M ? M : 1), slotOf(c, M ? M : 1);
-		const EntryPort EP{eord.p, ep1, ep2};
-		group_indices(c, EP, M, P, adjOff.p, list.p);
+		const EntryPort EP{ep1, ep2};
+		group_indices_ord<EntryPort, EntryMinPort, true>(c, EP, EntryMinPort{ep1, ep2}, M, P, adjOff.p, list.p);
 		u32 *slotOf_ = slotOf.p, *adjNbr_ = adjNbr.p, *adjOwner_ = adjOwner.p, *rev_ = rev.p; const u32 *list_ = list.p;
 		parallel_for<K_csr_fill>(c, M, PV_LAMBDA(size_t s) {
 			u32 j = list_[s];
@@ -319,12 +317,17 @@ inline void decompose_device(Ctx &c, u32 V, u64 E, const u32 *ep1, const u32 *ep
 	u32 nActive = V;
 	{ u32 *a = active.p; parallel_for<K_iota>(c, V, PV_LAMBDA(size_t i) { a[i] = (u32)i; }); }
 
+	// dense component tables: the flags and their compaction are queued in round 0 (as soon as the labels exist) so that the
+	// component count arrives with that round's own host wait
+	Buf<u32> isRoot(c, V), compIdxOfRoot(c, V + 1), nvOfRoot(c, V), roots;
+	u32 nComp = 0;
 	u32 round = 0;
 	bool repair = false;   // set by a round whose stripped path was cut short (see f')
 	static const u32 skip_walk = getenv("POVU_B200_SKIP_WALK") ? (u32)strtoul(getenv("POVU_B200_SKIP_WALK"), nullptr, 10) : 32u;   // 0 = never predict
 	while (nActive > 0) {
 		const u32 *act = active.p;
 		const u32 nA = nActive;
+		MultiRead mrRound(c);
 #ifdef PV_EMU
 		if (getenv("PV_DEBUG")) { fprintf(stderr, "[dfs] round %u active %u:", round, nA); for (u32 i = 0; i < nA && i < 32; i++) fprintf(stderr, " %u", act[i]); fprintf(stderr, "\n"); }
 #endif
@@ -357,6 +360,12 @@ inline void decompose_device(Ctx &c, u32 V, u64 E, const u32 *ep1, const u32 *ep
 			});
 			parallel_for<K_uf_min>(c, V, PV_LAMBDA(size_t v) { comp_[v] = minIdx_[comp_[v]]; });
 			c.d2d(gcomp.p, comp.p, (size_t)V * 4);
+			{
+				nvOfRoot.zero();
+				u32 *isRoot_ = isRoot.p, *nvOfRoot_ = nvOfRoot.p;
+				parallel_for<K_compcount>(c, V, PV_LAMBDA(size_t v) { isRoot_[v] = comp_[v] == v ? 1u : 0u; atomic_inc_aggregated(nvOfRoot_, comp_[v]); });
+				compact_flags(c, isRoot.p, V, roots, &compIdxOfRoot, &mrRound, &nComp);   // (the compaction's own scan is the dense component index)
+			}
 			// start port: smallest tip (v_id, end) of the component (types.cpp:60-68), else (lowest vertex, left)
 			parallel_for<K_start>(c, V, PV_LAMBDA(size_t v) { compStart_[v] = NONE; rnk_[2 * v] = NONE; rnk_[2 * v + 1] = NONE; });
 			parallel_for<K_start>(c, V, PV_LAMBDA(size_t v) { u32 t = tipPort_[v]; if (t != NONE) atomic_min(compStart_ + comp_[v], t); });
@@ -517,7 +526,7 @@ inline void decompose_device(Ctx &c, u32 V, u64 E, const u32 *ep1, const u32 *ep
 		parallel_for<K_visit>(c, nA, PV_LAMBDA(size_t i) { if (!still_[i]) visited_[act[i]] = 1; });
 		Buf<u32> idx, idxPos;
 		u32 nNext = 0, cut = 0;
-		{ MultiRead mr(c); compact_flags(c, still.p, nA, idx, &idxPos, &mr, &nNext); mr.add(&cut, flag.p + 2, 4); mr.wait(); }
+		compact_flags(c, still.p, nA, idx, &idxPos, &mrRound, &nNext); mrRound.add(&cut, flag.p + 2, 4); mrRound.wait();
 #ifdef PV_EMU
 		if (getenv("PV_DEBUG")) {
 			fprintf(stderr, "[dfs] round %u: active %u -> %u, repair %d, cut %u;", round, nA, nNext, (int)repair, cut);
@@ -539,13 +548,7 @@ inline void decompose_device(Ctx &c, u32 V, u64 E, const u32 *ep1, const u32 *ep
 	sm.mark();   // 2
 
 	// ------------------------------------------------------------------ components (dense indices)
-	Buf<u32> isRoot(c, V), compIdxOfRoot(c, V + 1), nvOfRoot(c, V);
-	nvOfRoot.zero();
-	u32 *isRoot_ = isRoot.p, *compIdxOfRoot_ = compIdxOfRoot.p, *nvOfRoot_ = nvOfRoot.p;
-	parallel_for<K_compcount>(c, V, PV_LAMBDA(size_t v) { isRoot_[v] = gcomp_[v] == v ? 1u : 0u; atomic_inc_aggregated(nvOfRoot_, gcomp_[v]); });
-	Buf<u32> roots;
-	u32 nComp = compact_flags(c, isRoot.p, V, roots, &compIdxOfRoot);   // (the compaction's own scan is the dense component index)
-	compIdxOfRoot_ = compIdxOfRoot.p;
+	u32 *compIdxOfRoot_ = compIdxOfRoot.p, *nvOfRoot_ = nvOfRoot.p;
 	// per component: nv, node base (2*nv+1 nodes incl. virtual root), segment base
 	Buf<u32> cNv(c, nComp + 1), cNodeBase(c, nComp + 1), cSegBase(c, nComp + 1), cNodes(c, nComp + 1), cHasTips(c, nComp);
 	u32 *cNv_ = cNv.p, *cNodeBase_ = cNodeBase.p, *cSegBase_ = cSegBase.p, *cNodes_ = cNodes.p, *cHasTips_ = cHasTips.p;
@@ -912,8 +915,7 @@ inline void decompose_device(Ctx &c, u32 V, u64 E, const u32 *ep1, const u32 *ep
 		out.stack_fwd.resize(nS);
 		for (u32 i = 0; i < nS; i++) out.stack_fwd[i] = es[out.stack_v[i]] == 0;
 	}
-	c.sync();
-	tr.mark("results d2h");
+	tr.mark("results d2h");   // (pack.to_host() above waited for the stream: every copy queued on it before has landed)
 	if (sm.on && sm.n == 9) {
 		StageCost &sc = StageCost::inst();
 		u64 tips = 0; for (u32 k = 0; k < nComp; k++) tips += out.comp_has_tips[k] ? 1 : 0;   // (components with tips; the exact tip count stays on the device)

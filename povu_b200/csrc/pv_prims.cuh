@@ -163,14 +163,41 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_lb_kernel(const T *in, T *o
 // contiguous block of ceil(i / 32) predecessors (independent loads, combined in order), then one ordered warp reduction.  One
 // round trip instead of i / 32.  4-byte elements travel with their epoch in one 64-bit word (no fence, no second load).
 template <class T> struct ScanPack { static const bool value = sizeof(T) == 4; };
-template <class T, class Op, bool INCLUSIVE, bool VEC>
+
+// Bulk asynchronous copies (the TMA unit's 1-D path, UBLKCP in SASS): one elected thread moves a whole scan tile between
+// global and shared memory; completion of the load is signalled on an mbarrier (transaction bytes), the store is a bulk group.
+__device__ __forceinline__ u32 smem_u32(const void *p) { return (u32)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(u64 *bar, u32 count) {
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+	asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(u64 *bar, u32 bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src, u32 bytes, u64 *bar) {
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(u64 *bar, u32 parity) {
+	asm volatile("{\n\t.reg .pred p;\n\tLAB_WAIT:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra LAB_DONE;\n\tbra LAB_WAIT;\n\tLAB_DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void *dst, const void *src_smem, u32 bytes) {
+	asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src_smem)), "r"(bytes) : "memory");
+	asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+	asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+// TMA = true (16-byte aligned input and output): full tiles are staged through shared memory by bulk asynchronous copies --
+// thread 0 arms an mbarrier with the tile's byte count and issues ONE cp.async.bulk for the tile, the CTA waits on the barrier
+// and reads its items with 128-bit shared loads; the scanned tile goes back the same way (items to shared memory, one bulk
+// store).  The partial last tile takes the register path.
+template <class T, class Op, bool INCLUSIVE, bool VEC, bool TMA>
 __global__ void __launch_bounds__(SCAN_THREADS) scan_flat_kernel(const T *in, T *out, size_t n, Op op, T identity, u32 *flags, T *agg, u64 *pack,
 								   u32 *ticket, u32 epoch, u32 ntiles) {
 	constexpr int SCAN_ITEMS = ScanCfg<T>::ITEMS, SCAN_TILE = ScanCfg<T>::TILE;
+	extern __shared__ __align__(128) unsigned char scan_dsm[];      // TMA: the tile (SCAN_TILE * sizeof(T) bytes)
 	__shared__ T warpTot[SCAN_THREADS / 32];
 	__shared__ T s_prefix;
 	__shared__ u32 s_tile;
+	__shared__ __align__(8) u64 s_bar;
 	const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+	if (TMA && t == 0) mbar_init(&s_bar, 1);
 	pdl_wait();
 	if (t == 0) { u32 k = atomicAdd(ticket, 1u); if (k == ntiles - 1) atomicExch(ticket, 0u); s_tile = k; }
 	__syncthreads();
@@ -178,7 +205,14 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_flat_kernel(const T *in, T 
 	const size_t base = (size_t)tile * SCAN_TILE + (size_t)t * SCAN_ITEMS;
 	const bool full = (size_t)(tile + 1) * SCAN_TILE <= n;
 	union Items { T v[SCAN_ITEMS]; uint4 q[sizeof(T) * SCAN_ITEMS / 16]; __device__ Items() {} } it;
-	if (full) {
+	if (TMA && full) {
+		constexpr u32 TILE_BYTES = (u32)(SCAN_TILE * sizeof(T));
+		if (t == 0) { mbar_expect_tx(&s_bar, TILE_BYTES); bulk_g2s(scan_dsm, in + (size_t)tile * SCAN_TILE, TILE_BYTES, &s_bar); }
+		mbar_wait(&s_bar, 0);
+		const uint4 *src = reinterpret_cast<const uint4 *>(scan_dsm) + (size_t)t * (sizeof(T) * SCAN_ITEMS / 16);
+#pragma unroll
+		for (int k = 0; k < (int)(sizeof(T) * SCAN_ITEMS / 16); k++) it.q[k] = src[k];
+	} else if (full) {
 		if (VEC) {
 			const uint4 *src = reinterpret_cast<const uint4 *>(in + base);
 #pragma unroll
@@ -251,7 +285,15 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_flat_kernel(const T *in, T 
 		if (INCLUSIVE) { run = op(run, it.v[k]); it.v[k] = run; }
 		else { T x = it.v[k]; it.v[k] = run; run = op(run, x); }
 	}
-	if (full) {
+	if (TMA && full) {
+		constexpr u32 TILE_BYTES = (u32)(SCAN_TILE * sizeof(T));
+		uint4 *dsts = reinterpret_cast<uint4 *>(scan_dsm) + (size_t)t * (sizeof(T) * SCAN_ITEMS / 16);
+#pragma unroll
+		for (int k = 0; k < (int)(sizeof(T) * SCAN_ITEMS / 16); k++) dsts[k] = it.q[k];
+		asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // the generic-proxy writes above become visible to the bulk copy
+		__syncthreads();
+		if (t == 0) bulk_s2g(out + (size_t)tile * SCAN_TILE, scan_dsm, TILE_BYTES);
+	} else if (full) {
 		if (VEC) {
 			uint4 *dst = reinterpret_cast<uint4 *>(out + base);
 #pragma unroll
@@ -279,8 +321,15 @@ inline void scan_impl(Ctx &c, const T *in, T *out, size_t n, Op op, T identity) 
 	static const u32 flat_max = getenv("POVU_B200_SCAN_FLAT_MAX") ? (u32)strtoul(getenv("POVU_B200_SCAN_FLAT_MAX"), nullptr, 10) : 1024u;
 	if (ntiles <= flat_max) {   // every predecessor's aggregate is fetched at once (see scan_flat_kernel)
 		c.prof_begin("scan_flat", n, n * 2 * sizeof(T));
-		if (vec) PV_CUDA_CHECK(launch_pdl(scan_flat_kernel<T, Op, INCLUSIVE, true>, dim3((unsigned)ntiles), dim3(SCAN_THREADS), 0, c.stream, in, out, n, op, identity, c.lb_flags, agg, c.lb_pack, c.lb_ticket, epoch, (u32)ntiles));
-		else PV_CUDA_CHECK(launch_pdl(scan_flat_kernel<T, Op, INCLUSIVE, false>, dim3((unsigned)ntiles), dim3(SCAN_THREADS), 0, c.stream, in, out, n, op, identity, c.lb_flags, agg, c.lb_pack, c.lb_ticket, epoch, (u32)ntiles));
+		static const bool no_tma = getenv("POVU_B200_SCAN_NO_TMA") != nullptr;
+		if (vec && !no_tma && ntiles > 1) {
+			static bool attr_set = false;      // (per instantiation: this is a function template)
+			const size_t smem = SCAN_TILE * sizeof(T);
+			if (!attr_set) { PV_CUDA_CHECK(cudaFuncSetAttribute(scan_flat_kernel<T, Op, INCLUSIVE, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_set = true; }
+			PV_CUDA_CHECK(launch_pdl(scan_flat_kernel<T, Op, INCLUSIVE, true, true>, dim3((unsigned)ntiles), dim3(SCAN_THREADS), smem, c.stream, in, out, n, op, identity, c.lb_flags, agg, c.lb_pack, c.lb_ticket, epoch, (u32)ntiles));
+		}
+		else if (vec) PV_CUDA_CHECK(launch_pdl(scan_flat_kernel<T, Op, INCLUSIVE, true, false>, dim3((unsigned)ntiles), dim3(SCAN_THREADS), 0, c.stream, in, out, n, op, identity, c.lb_flags, agg, c.lb_pack, c.lb_ticket, epoch, (u32)ntiles));
+		else PV_CUDA_CHECK(launch_pdl(scan_flat_kernel<T, Op, INCLUSIVE, false, false>, dim3((unsigned)ntiles), dim3(SCAN_THREADS), 0, c.stream, in, out, n, op, identity, c.lb_flags, agg, c.lb_pack, c.lb_ticket, epoch, (u32)ntiles));
 		c.prof_end();
 		c.launches++;
 		PV_CUDA_CHECK(cudaGetLastError());
@@ -813,7 +862,10 @@ PV_KERNEL(K_grp_count, 8);
 PV_KERNEL(K_grp_slot, 16);
 PV_KERNEL(K_grp_sort, 16);
 PV_KERNEL(K_grp_big, 12);
-template <class KeyFn> inline void group_indices(Ctx &c, KeyFn key, size_t n, u32 B, u32 *off, u32 *list, u32 small = 48) {
+// ord (optional): a secondary key -- inside a group the indices come out ascending by (ord(i), i) instead of by i alone.
+struct NoOrd { PV_DEV u32 operator()(size_t) const { return 0u; } };
+template <class KeyFn, class OrdFn = NoOrd, bool HAS_ORD = false>
+inline void group_indices_ord(Ctx &c, KeyFn key, OrdFn ord, size_t n, u32 B, u32 *off, u32 *list, u32 small = 48) {
 	if (n >= 0xFFFFFFF0ull) throw std::runtime_error("group_indices: input too large");
 	Buf<u32> cnt(c, (size_t)B + 1), cur(c, B ? B : 1), nBigBuf(c, 1);
 	cnt.zero(); cur.zero(); nBigBuf.zero();
@@ -829,7 +881,12 @@ template <class KeyFn> inline void group_indices(Ctx &c, KeyFn key, size_t n, u3
 		u32 m = cnt_[k];
 		if (m > small) { nBig_[0] = 1; return; }   // (a flag, not a sum: with many paths every group is large and a counter would serialise)
 		u32 *a = list + off[k];
-		for (u32 i = 1; i < m; i++) { u32 x = a[i]; u32 j = i; while (j > 0 && a[j - 1] > x) { a[j] = a[j - 1]; j--; } a[j] = x; }
+		for (u32 i = 1; i < m; i++) {
+			u32 x = a[i]; u32 j = i;
+			if (HAS_ORD) { const u64 kx = ((u64)ord(x) << 32) | x; while (j > 0 && (((u64)ord(a[j - 1]) << 32) | a[j - 1]) > kx) { a[j] = a[j - 1]; j--; } }
+			else { while (j > 0 && a[j - 1] > x) { a[j] = a[j - 1]; j--; } }
+			a[j] = x;
+		}
 	});
 	const u32 nBig = nBigBuf.read(0);
 	if (!nBig) return;
@@ -840,12 +897,22 @@ template <class KeyFn> inline void group_indices(Ctx &c, KeyFn key, size_t n, u3
 	flag.release();
 	Buf<u32> kk(c, nb), vv(c, nb);
 	u32 *kk_ = kk.p, *vv_ = vv.p; const u32 *idx_ = idx.p;
-	parallel_for<K_grp_big>(c, nb, PV_LAMBDA(size_t j) { u32 i = idx_[j]; kk_[j] = key(i); vv_[j] = i; });
+	if (HAS_ORD) {   // stable by the secondary key first (the members are in index order), then by group
+		parallel_for<K_grp_big>(c, nb, PV_LAMBDA(size_t j) { u32 i = idx_[j]; kk_[j] = ord(i); vv_[j] = i; });
+		radix_sort_pairs(c, kk, vv, nb, 32);
+		kk_ = kk.p; vv_ = vv.p;
+		parallel_for<K_grp_big>(c, nb, PV_LAMBDA(size_t j) { kk_[j] = key(vv_[j]); });
+	} else {
+		parallel_for<K_grp_big>(c, nb, PV_LAMBDA(size_t j) { u32 i = idx_[j]; kk_[j] = key(i); vv_[j] = i; });
+	}
 	radix_sort_pairs(c, kk, vv, nb, bits_for(B));
 	kk_ = kk.p; vv_ = vv.p;
 	// first sorted position of every large group (cur is free again: large groups never touched it)
 	parallel_for<K_grp_big>(c, nb, PV_LAMBDA(size_t j) { if (j == 0 || kk_[j - 1] != kk_[j]) cur_[kk_[j]] = (u32)j; });
 	parallel_for<K_grp_big>(c, nb, PV_LAMBDA(size_t j) { u32 k = kk_[j]; list[off[k] + ((u32)j - cur_[k])] = vv_[j]; });
+}
+template <class KeyFn> inline void group_indices(Ctx &c, KeyFn key, size_t n, u32 B, u32 *off, u32 *list, u32 small = 48) {
+	group_indices_ord<KeyFn, NoOrd, false>(c, key, NoOrd(), n, B, off, list, small);
 }
 
 } // namespace pv

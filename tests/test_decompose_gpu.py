@@ -39,6 +39,18 @@ def test_gpu_dfs_repair_mode(gpu):
         _check(gpu, synth.permute_vertices(g, 100 + seed))
 
 
+def test_gpu_hub_ports(gpu):
+    """Ports with more than 48 links: the two-key radix path of the adjacency grouping (see tests/test_emu_decompose.py)."""
+    for s in range(8):
+        _check(gpu, synth.wild(7000 + s, V=3 + s % 4, E=150 + 40 * s, p_loop=0.1, n_comp=1))
+    links = []
+    for k in range(1, 120):
+        links.append(synth.link(0, "+", k, "+" if k % 3 else "-"))
+        if k % 2:
+            links.append(synth.link(k, "+", 120, "+"))
+    _check(gpu, synth.make_graph(list(range(1, 122)), ["A"] * 121, links, []))
+
+
 def test_gpu_edge_cases(gpu):
     one = synth.make_graph([5], ["A"], np.zeros((0, 4)), [])
     assert gpu.decompose(1, *api.edge_ports(one)).n == 0

@@ -74,3 +74,19 @@ def test_emu_is_not_the_default_library(emu_lib):
 def test_emu_fired_arcs_fixpoint(emu_lib):
     import test_prims_gpu
     test_prims_gpu.check_fired_arcs(_ctx(emu_lib, 2))
+
+
+@pytest.mark.parametrize("order", [0, 2])
+def test_emu_hub_ports(emu_lib, order):
+    """Ports with more than 48 links take the two-key radix path of the adjacency grouping (lower port of the link, then file
+    order): tiny vertex sets with hundreds of (parallel, looping) links, and a star around one hub segment."""
+    pv = _ctx(emu_lib, order)
+    for s in range(8):
+        _check(pv, synth.wild(7000 + s, V=3 + s % 4, E=150 + 40 * s, p_loop=0.1, n_comp=1))
+    links = []
+    for k in range(1, 120):
+        links.append(synth.link(0, "+", k, "+" if k % 3 else "-"))
+        if k % 2:
+            links.append(synth.link(k, "+", 120, "+"))
+    g = synth.make_graph(list(range(1, 122)), ["A"] * 121, links, [])
+    _check(pv, g)
