@@ -795,7 +795,7 @@ PV_KERNEL(K_lr_init, 16);
 PV_KERNEL(K_lr_jump, 24);      // a[i], a[next] in, b[i] out (8 B each)
 PV_KERNEL(K_lr_out, 12);
 
-inline void list_rank_suffix(Ctx &c, const u32 *next, const u32 *weight, u32 *rank_out, size_t n) {
+inline void list_rank_wyllie(Ctx &c, const u32 *next, const u32 *weight, u32 *rank_out, size_t n) {
 	if (n == 0) return;
 	Buf<u64> A(c, n), B(c, n);
 	u64 *a = A.p, *b = B.p;
@@ -822,6 +822,78 @@ inline void list_rank_suffix(Ctx &c, const u32 *next, const u32 *weight, u32 *ra
 	parallel_for<K_lr_out>(c, n, PV_LAMBDA(size_t i) { rank_out[i] = (u32)a[i]; });
 }
 
+inline u32 compact_flags(Ctx &c, const u32 *flags, size_t n, Buf<u32> &out, Buf<u32> *keep_pos = nullptr, MultiRead *mr = nullptr, u32 *cnt_dst = nullptr);
+
+// Block-local list ranking.  The lists ranked here are Euler tours of DFS trees whose vertices are numbered along the chain
+// (segment ids follow the backbone), so a list element's successor is almost always a few indices away.  Every CTA takes 2048
+// consecutive elements, cuts the list where it leaves the block and ranks the pieces inside shared memory (11 pointer-jumping
+// steps, no global traffic); what is left for the global Wyllie pass is one node per piece -- a few thousand instead of four
+// million at cfg2.  Without locality every element is its own piece and this degenerates to the plain pass plus one sweep.
+PV_KERNEL(K_lr_local, 20);     // next + weight in, tail + partial sum + flag out
+PV_KERNEL(K_lr_reduce, 24);
+PV_KERNEL(K_lr_expand, 16);
+#ifndef PV_EMU
+static const int LR_BLOCK = 2048, LR_THREADS = 512;
+__global__ void __launch_bounds__(LR_THREADS) lr_local_kernel(const u32 *next, const u32 *weight, u32 n, u32 *tailOf, u32 *sumTo, u32 *isTail) {
+	__shared__ u32 P[2][LR_BLOCK];      // next element of the piece inside the block (local index), NONE = none
+	__shared__ u32 A[2][LR_BLOCK];      // weights of the elements in (l, P(l)]
+	pdl_wait();
+	const u32 base = blockIdx.x * LR_BLOCK;
+	for (u32 l = threadIdx.x; l < LR_BLOCK; l += LR_THREADS) {
+		const u32 i = base + l;
+		u32 p = NONE, a = 0;
+		if (i < n) { u32 nx = next[i]; if (nx != NONE && nx >= base && nx - base < LR_BLOCK) { p = nx - base; a = weight[nx]; } }
+		P[0][l] = p; A[0][l] = a;
+	}
+	__syncthreads();
+	int cur = 0;
+#pragma unroll 1
+	for (int it = 0; it < 11; it++) {      // 2^11 = LR_BLOCK
+		for (u32 l = threadIdx.x; l < LR_BLOCK; l += LR_THREADS) {
+			u32 q = P[cur][l], a = A[cur][l];
+			if (q != NONE) { u32 qq = P[cur][q]; if (qq != NONE) { a += A[cur][q]; q = qq; } }      // never jump past the piece's last element
+			P[cur ^ 1][l] = q; A[cur ^ 1][l] = a;
+		}
+		__syncthreads();
+		cur ^= 1;
+	}
+	for (u32 l = threadIdx.x; l < LR_BLOCK; l += LR_THREADS) {
+		const u32 i = base + l;
+		if (i >= n) continue;
+		const u32 q = P[cur][l];
+		tailOf[i] = q == NONE ? i : base + q; sumTo[i] = q == NONE ? 0u : A[cur][l]; isTail[i] = q == NONE ? 1u : 0u;
+	}
+}
+#endif
+
+inline void list_rank_suffix(Ctx &c, const u32 *next, const u32 *weight, u32 *rank_out, size_t n) {
+	if (n == 0) return;
+#ifdef PV_EMU
+	list_rank_wyllie(c, next, weight, rank_out, n);
+#else
+	static const bool plain = getenv("POVU_B200_LR_PLAIN") != nullptr;
+	if (plain || n < 4 * (size_t)LR_BLOCK || n >= 0xFFFFFFF0ull) { list_rank_wyllie(c, next, weight, rank_out, n); return; }
+	Buf<u32> tailOf(c, n), sumTo(c, n), isTail(c, n), tails, tid;
+	c.prof_begin(K_lr_local::name(), n, n * K_lr_local::bytes);
+	PV_CUDA_CHECK(launch_pdl(lr_local_kernel, dim3((unsigned)((n + LR_BLOCK - 1) / LR_BLOCK)), dim3(LR_THREADS), 0, c.stream, next, weight, (u32)n, tailOf.p, sumTo.p, isTail.p));
+	c.prof_end();
+	c.launches++;
+	const u32 m = compact_flags(c, isTail.p, n, tails, &tid);      // tails ascending; tid[i] = dense id of tail i
+	Buf<u32> rnext(c, m), rw(c, m), rrank(c, m);
+	rw.zero();
+	u32 *rnext_ = rnext.p, *rw_ = rw.p; const u32 *tails_ = tails.p, *tid_ = tid.p, *tailOf_ = tailOf.p, *sumTo_ = sumTo.p;
+	parallel_for<K_lr_reduce>(c, m, PV_LAMBDA(size_t k) {
+		const u32 t = tails_[k]; const u32 nx = next[t];
+		if (nx == NONE) { rnext_[k] = NONE; return; }
+		const u32 k2 = tid_[tailOf_[nx]];            // the piece that starts at nx: its weight = every element from nx to its tail
+		rnext_[k] = k2; rw_[k2] = weight[nx] + sumTo_[nx];
+	});
+	list_rank_wyllie(c, rnext.p, rw.p, rrank.p, m);
+	const u32 *rrank_ = rrank.p;
+	parallel_for<K_lr_expand>(c, n, PV_LAMBDA(size_t i) { rank_out[i] = sumTo_[i] + rrank_[tid_[tailOf_[i]]]; });
+#endif
+}
+
 // ---------------------------------------------------------------------------------------------
 // stream compaction of indices i in [0,n) with flag[i] != 0 -> out (ascending); returns the count
 // ---------------------------------------------------------------------------------------------
@@ -829,7 +901,7 @@ PV_KERNEL(K_compact_scatter, 12);
 // keep_pos (optional) receives the exclusive scan of the flags (n + 1 entries): rank of every index among the kept ones
 // mr (optional): the count is not read here but queued on the caller's MultiRead into *cnt_dst (valid after mr->wait(); keep_pos
 // must be given and stay alive until then) -- several small results then share one host wait
-inline u32 compact_flags(Ctx &c, const u32 *flags, size_t n, Buf<u32> &out, Buf<u32> *keep_pos = nullptr, MultiRead *mr = nullptr, u32 *cnt_dst = nullptr) {
+inline u32 compact_flags(Ctx &c, const u32 *flags, size_t n, Buf<u32> &out, Buf<u32> *keep_pos, MultiRead *mr, u32 *cnt_dst) {
 	if (n == 0) { out = Buf<u32>(c, 1); if (keep_pos) { *keep_pos = Buf<u32>(c, 1); keep_pos->zero(); } if (cnt_dst) *cnt_dst = 0; return 0; }
 	Buf<u32> pos(c, n + 1);
 	exclusive_scan(c, flags, pos.p, n, OpAddU32(), 0u);

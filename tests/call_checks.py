@@ -106,7 +106,7 @@ def run_tangled_vs_reference(pv, tmp, n_seeds=24):
         assert gh == wh and gr == wr, f"seed {seed}"
         assert st["hard_errors"] == 0
         tangled += st["tangled"]; records += sum("TANGLED=T" in l for l in gr)
-    assert tangled > 20 and records > 20, (tangled, records)
+    assert tangled > n_seeds and records > n_seeds, (tangled, records)
 
 
 def run_cyclic_vs_reference(pv, tmp, n_seeds=30):
@@ -178,7 +178,7 @@ def run_inversions_vs_reference(pv, tmp, n_seeds=45):
         assert split(got, False) == split(want, False), f"seed {seed}"
         compared += 1
         subr += sum("VARTYPE=SUBR" in l for l in got.splitlines())
-    assert compared >= n_seeds * 0.7 and subr > 50 and pins > 100, (compared, clamped_compared, subr, pins)
+    assert compared >= n_seeds * 0.7 and subr > n_seeds and pins > 2 * n_seeds, (compared, clamped_compared, subr, pins)
 
 
 def run_all_synthetic(pv, tmp, n_seeds=12):

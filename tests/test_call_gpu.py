@@ -57,3 +57,20 @@ def test_gpu_call_matfill_lanes(gpu, name, tmp_path, monkeypatch):
     """depth matrix: 32 logical lanes per column stride over the vertex's step list (the many-paths configuration)"""
     monkeypatch.setenv("POVU_B200_MATFILL_LANES", "32")
     cc.check_golden(gpu, name, str(tmp_path))
+
+
+@pytest.mark.parametrize("name", ["nested_s1", "nested_s2_shuffled", "hairpin_inversion_subr", "multi_comp", "LPA"])
+def test_gpu_call_many_path_kernels(gpu, name, tmp_path, monkeypatch):
+    """The kernels that take over when regions have dozens of rows / candidates (hundreds of paths), forced on the fixtures:
+    one warp per region for depth cells + lap 0 + context counts (C_region) and for the allele grouping (C_group)."""
+    monkeypatch.setenv("POVU_B200_FUSED_REGION", "1")
+    monkeypatch.setenv("POVU_B200_GROUP_WARP", "1")
+    cc.check_golden(gpu, name, str(tmp_path))
+
+
+def test_gpu_call_many_path_kernels_families(gpu, tmp_path, monkeypatch):
+    monkeypatch.setenv("POVU_B200_FUSED_REGION", "1")
+    monkeypatch.setenv("POVU_B200_GROUP_WARP", "1")
+    cc.run_all_synthetic(gpu, str(tmp_path), n_seeds=8)
+    cc.run_tangled_vs_reference(gpu, str(tmp_path), n_seeds=10)
+    cc.run_inversions_vs_reference(gpu, str(tmp_path), n_seeds=15)
