@@ -142,23 +142,18 @@ inline void graph_build(Ctx &c, u32 V, u64 E, const u32 *ep1, const u32 *ep2, u3
 	g.V = V; g.E = E; g.H = H; g.S = h_stepOff ? h_stepOff[H] : 0;
 	const u32 P = 2 * V; const u64 M = 2 * E; const u32 S = g.S;
 	if (M >= 0xFFFFFFF0ull) throw std::runtime_error("graph too large for 32-bit adjacency slots");
+	// Two groupings (adjacency by port, steps by vertex) and the component label of every path are all queued before the ONE
+	// host wait of the index build: their "has large groups" flags and the path labels arrive together.
 	// ---- adjacency in whole-graph edge order (what `call` iterates: bidirected.hpp:68-69)
 	g.adjOff = Buf<u32>(c, (size_t)P + 2); g.adjNbr = Buf<u32>(c, M ? M : 1);
-	{
-		// entries 2e / 2e+1 = the two ends of link e, grouped by port in link order (group_indices: ports have a handful of
-		// entries; hubs take the restricted stable sort).  Bucket P collects the second end of a v+ -> v+ style loop, which
-		// is one std::set entry in the reference.
-		Buf<u32> list(c, M ? M : 1);
-		group_indices(c, AdjEntryPort{ep1, ep2, P}, M, P + 1, g.adjOff.p, list.p);
-		u32 *adjNbr_ = g.adjNbr.p; const u32 *list_ = list.p;
-		parallel_for<C_adj_fill>(c, M, PV_LAMBDA(size_t s) {
-			u32 j = list_[s]; u32 a = ep1[j >> 1], b = ep2[j >> 1];
-			bool self = (a >> 1) == (b >> 1);
-			// Edge::get_other_vtx(v, side) answers the complement side for any self-loop (bidirected.cpp:66-77)
-			adjNbr_[s] = (j & 1u) ? (self ? (b ^ 1u) : a) : (self ? (a ^ 1u) : b);
-		});
-	}
-	tr.mark("adjacency");
+	// entries 2e / 2e+1 = the two ends of link e, grouped by port in link order (group_indices: ports have a handful of
+	// entries; hubs take the restricted stable sort).  Bucket P collects the second end of a v+ -> v+ style loop, which
+	// is one std::set entry in the reference.
+	Buf<u32> alist(c, M ? M : 1);
+	const AdjEntryPort AEP{ep1, ep2, P};
+	GroupState gsAdj, gsVs;
+	MultiRead mr(c);
+	group_begin(c, AEP, NoOrd(), M, P + 1, g.adjOff.p, alist.p, 48u, gsAdj, &mr);
 	// ---- paths
 	g.h_stepOff.assign(h_stepOff, h_stepOff + H + 1);
 	g.stepOff = Buf<u32>(c, (size_t)H + 1); c.h2d(g.stepOff.p, h_stepOff, ((size_t)H + 1) * 4);
@@ -179,26 +174,45 @@ inline void graph_build(Ctx &c, u32 V, u64 E, const u32 *ep1, const u32 *ep2, u3
 			loci_[s] = 1u + pre_[s] - pre_[stepOff_[h]];
 		});
 	}
+	// vertex -> steps index = the step indices grouped by vertex, ascending inside a vertex (group_indices, pv_prims.cuh)
+	u32 vs_small = 48;
+	if (const char *e = getenv("POVU_B200_VS_SMALL")) vs_small = (u32)strtoul(e, nullptr, 10);   // tests: force the hub path
+	const StepVertex SV{steps_};
+	group_begin(c, SV, NoOrd(), S, V, g.vsOff.p, g.vsStep.p, vs_small, gsVs, &mr);
+	// ---- weakly connected components -> the component label of every path
+	if (labels && labels->p && labels->n >= V && V) g.vcomp = std::move(*labels);
+	else { g.vcomp = Buf<u32>(c, V ? V : 1); component_labels(c, V, E, ep1, ep2, g.vcomp.p); }
+	Buf<u32> pr(c, H ? H : 1);
+	std::vector<u32> roots(H ? H : 1, NONE);
 	{
-		// vertex -> steps index = the step indices grouped by vertex, ascending inside a vertex (group_indices, pv_prims.cuh)
-		u32 vs_small = 48;
-		if (const char *e = getenv("POVU_B200_VS_SMALL")) vs_small = (u32)strtoul(e, nullptr, 10);   // tests: force the hub path
-		u32 *vsStep_ = g.vsStep.p, *vsHap_ = g.vsHap.p;
-		group_indices(c, StepVertex{steps_}, S, V, g.vsOff.p, g.vsStep.p, vs_small);
+		u32 *uf_ = g.vcomp.p; u32 *pr_ = pr.p;
+		parallel_for<C_uf>(c, H, PV_LAMBDA(size_t h) { pr_[h] = stepOff_[h + 1] > stepOff_[h] ? uf_[steps_[stepOff_[h]] >> 1] : NONE; });
+		if ((size_t)H * 4 + 64 < ((size_t)1 << 20)) mr.add(roots.data(), pr.p, (size_t)H * 4);
+	}
+	mr.wait();
+	if ((size_t)H * 4 + 64 >= ((size_t)1 << 20)) roots = pr.to_host();
+	roots.resize(H);
+	tr.mark("groupings queued");
+	group_finish(c, AEP, NoOrd(), gsAdj);
+	{
+		u32 *adjNbr_ = g.adjNbr.p; const u32 *list_ = alist.p;
+		parallel_for<C_adj_fill>(c, M, PV_LAMBDA(size_t s) {
+			u32 j = list_[s]; u32 a = ep1[j >> 1], b = ep2[j >> 1];
+			bool self = (a >> 1) == (b >> 1);
+			// Edge::get_other_vtx(v, side) answers the complement side for any self-loop (bidirected.cpp:66-77)
+			adjNbr_[s] = (j & 1u) ? (self ? (b ^ 1u) : a) : (self ? (a ^ 1u) : b);
+		});
+	}
+	tr.mark("adjacency");
+	group_finish(c, SV, NoOrd(), gsVs);
+	{
 		// (path << 1) | strand next to every entry: the depth matrix needs the strand per visit, and reading it here (one pass, the
 		// step index at hand) is cheaper than a random access per matrix cell later
+		u32 *vsStep_ = g.vsStep.p, *vsHap_ = g.vsHap.p;
 		parallel_for<C_vs_hap>(c, S, PV_LAMBDA(size_t i) { u32 st = vsStep_[i]; vsHap_[i] = ((ub_u32(stepOff_, 0, H + 1, st) - 1) << 1) | (steps_[st] & 1u); });
 	}
 	tr.mark("loci + vertex->steps");
-	// ---- weakly connected components -> the paths of every component
-	if (labels && labels->p && labels->n >= V && V) g.vcomp = std::move(*labels);
-	else { g.vcomp = Buf<u32>(c, V ? V : 1); component_labels(c, V, E, ep1, ep2, g.vcomp.p); }
 	{
-		u32 *uf_ = g.vcomp.p;
-		Buf<u32> pr(c, H ? H : 1);
-		u32 *pr_ = pr.p;
-		parallel_for<C_uf>(c, H, PV_LAMBDA(size_t h) { pr_[h] = stepOff_[h + 1] > stepOff_[h] ? uf_[steps_[stepOff_[h]] >> 1] : NONE; });
-		std::vector<u32> roots = pr.to_host(); roots.resize(H);
 		g.pathLabel = roots;
 		std::vector<u32> uniq;
 		for (u32 r : roots) if (r != NONE) uniq.push_back(r);
@@ -570,6 +584,7 @@ PV_DEV int walk_cmp(const u32 *steps, u32 a, u32 la, u32 b, u32 lb) {
 struct ChunkView {
 	GraphView g; RovView rv;
 	u16 *mat; u32 *lapStart, *lapLen, *tangled, *hasData, *errs;
+
 	PV_DEV Lap lap(u32 row) const { u32 s = lapStart[row]; return Lap{s, s + lapLen[row]}; }
 };
 struct CandView { u32 *cL, *cR, *cStart, *cLen, *cRS, *cRL, *cHap, *cCls, *cHead, *gCount, *hsort, *pinCount; };

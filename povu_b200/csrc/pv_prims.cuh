@@ -936,14 +936,19 @@ PV_KERNEL(K_grp_sort, 16);
 PV_KERNEL(K_grp_big, 12);
 // ord (optional): a secondary key -- inside a group the indices come out ascending by (ord(i), i) instead of by i alone.
 struct NoOrd { PV_DEV u32 operator()(size_t) const { return 0u; } };
+// Two halves, so that a caller can queue several groupings and learn all their "has large groups" flags with ONE host wait:
+// group_begin runs count / scan / slot / small-group sort and queues the flag on the caller's MultiRead (or reads it at once);
+// group_finish takes the large groups through the radix path.
+struct GroupState { Buf<u32> cnt, cur, nBigBuf; size_t n = 0; u32 B = 0; u32 *off = nullptr, *list = nullptr; u32 small = 48; u32 nBig = 0; };
 template <class KeyFn, class OrdFn = NoOrd, bool HAS_ORD = false>
-inline void group_indices_ord(Ctx &c, KeyFn key, OrdFn ord, size_t n, u32 B, u32 *off, u32 *list, u32 small = 48) {
+inline void group_begin(Ctx &c, KeyFn key, OrdFn ord, size_t n, u32 B, u32 *off, u32 *list, u32 small, GroupState &st, MultiRead *mr = nullptr) {
 	if (n >= 0xFFFFFFF0ull) throw std::runtime_error("group_indices: input too large");
-	Buf<u32> cnt(c, (size_t)B + 1), cur(c, B ? B : 1), nBigBuf(c, 1);
-	cnt.zero(); cur.zero(); nBigBuf.zero();
-	u32 *cnt_ = cnt.p, *cur_ = cur.p, *nBig_ = nBigBuf.p;
+	st.n = n; st.B = B; st.off = off; st.list = list; st.small = small; st.nBig = 0;
+	st.cnt = Buf<u32>(c, (size_t)B + 1); st.cur = Buf<u32>(c, B ? B : 1); st.nBigBuf = Buf<u32>(c, 1);
+	st.cnt.zero(); st.cur.zero(); st.nBigBuf.zero();
+	u32 *cnt_ = st.cnt.p, *cur_ = st.cur.p, *nBig_ = st.nBigBuf.p;
 	parallel_for<K_grp_count>(c, n, PV_LAMBDA(size_t i) { atomic_add(cnt_ + key(i), 1u); });
-	exclusive_scan(c, cnt.p, off, (size_t)B + 1, OpAddU32(), 0u);
+	exclusive_scan(c, st.cnt.p, off, (size_t)B + 1, OpAddU32(), 0u);
 	parallel_for<K_grp_slot>(c, n, PV_LAMBDA(size_t i) {
 		u32 k = key(i);
 		if (cnt_[k] > small) return;
@@ -960,8 +965,14 @@ inline void group_indices_ord(Ctx &c, KeyFn key, OrdFn ord, size_t n, u32 B, u32
 			a[j] = x;
 		}
 	});
-	const u32 nBig = nBigBuf.read(0);
-	if (!nBig) return;
+	if (mr) mr->add(&st.nBig, st.nBigBuf.p, 4);
+	else st.nBig = st.nBigBuf.read(0);
+}
+template <class KeyFn, class OrdFn = NoOrd, bool HAS_ORD = false>
+inline void group_finish(Ctx &c, KeyFn key, OrdFn ord, GroupState &st) {
+	if (!st.nBig) { st.cnt.release(); st.cur.release(); return; }
+	const size_t n = st.n; const u32 B = st.B, small = st.small; u32 *off = st.off, *list = st.list;
+	u32 *cnt_ = st.cnt.p, *cur_ = st.cur.p;
 	Buf<u32> flag(c, n), idx;
 	u32 *flag_ = flag.p;
 	parallel_for<K_grp_big>(c, n, PV_LAMBDA(size_t i) { flag_[i] = cnt_[key(i)] > small ? 1u : 0u; });
@@ -982,6 +993,12 @@ inline void group_indices_ord(Ctx &c, KeyFn key, OrdFn ord, size_t n, u32 B, u32
 	// first sorted position of every large group (cur is free again: large groups never touched it)
 	parallel_for<K_grp_big>(c, nb, PV_LAMBDA(size_t j) { if (j == 0 || kk_[j - 1] != kk_[j]) cur_[kk_[j]] = (u32)j; });
 	parallel_for<K_grp_big>(c, nb, PV_LAMBDA(size_t j) { u32 k = kk_[j]; list[off[k] + ((u32)j - cur_[k])] = vv_[j]; });
+}
+template <class KeyFn, class OrdFn = NoOrd, bool HAS_ORD = false>
+inline void group_indices_ord(Ctx &c, KeyFn key, OrdFn ord, size_t n, u32 B, u32 *off, u32 *list, u32 small = 48) {
+	GroupState st;
+	group_begin<KeyFn, OrdFn, HAS_ORD>(c, key, ord, n, B, off, list, small, st);
+	group_finish<KeyFn, OrdFn, HAS_ORD>(c, key, ord, st);
 }
 template <class KeyFn> inline void group_indices(Ctx &c, KeyFn key, size_t n, u32 B, u32 *off, u32 *list, u32 small = 48) {
 	group_indices_ord<KeyFn, NoOrd, false>(c, key, NoOrd(), n, B, off, list, small);
