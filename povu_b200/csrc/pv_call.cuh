@@ -592,9 +592,14 @@ struct CandView { u32 *cL, *cR, *cStart, *cLen, *cRS, *cRL, *cHap, *cCls, *cHead
 // comp_bounds + is_inverted over one (region, ref path, other path) pair (overlay.cpp:84-149); with
 // fill = true also gen_cxt, the two hap slices and the classification of every context
 // (overlay.cpp:307-327,189-246,462-530).  Returns the number of contexts.
+PV_DEV u32 scan_pair_ri(const ChunkView &cv, u32 refLocal, u32 k, u32 r, u32 i, u32 row, bool fill, const CandView &cd, u32 off);
 PV_DEV u32 scan_pair(const ChunkView &cv, u32 refLocal, u32 k, u32 row, bool fill, const CandView &cd, u32 off) {
+	u32 r = cv.rv.row2rov(row);
+	return scan_pair_ri(cv, refLocal, k, r, row - cv.rv.rowBase(r), row, fill, cd, off);
+}
+// the same with the region item r and the row's index i inside it already known (row = rowBase(r) + i)
+PV_DEV u32 scan_pair_ri(const ChunkView &cv, u32 refLocal, u32 k, u32 r, u32 i, u32 row, bool fill, const CandView &cd, u32 off) {
 	const RovView &rv = cv.rv; const GraphView &g = cv.g;
-	u32 r = rv.row2rov(row); u32 i = row - rv.rowBase(r);
 	if (i == refLocal || ld_volatile(cv.tangled + r)) return 0;      // (volatile: in the fused region kernel another lane's atomic set it moments ago)
 	if (k > 0 && !cv.hasData[r]) return 0;     // comp_exps returned after the first ref (overlay.cpp:531-532)
 	u32 J = rv.J(r);
@@ -683,6 +688,15 @@ inline void overlay_pass(Ctx &c, const DevGraph &G, const GraphView &g, const Ca
 		else {
 			pairCnt = Buf<u32>(c, (size_t)nRows + 1);
 			u32 *pairCnt_ = pairCnt.p;
+			if ((u64)nRows <= 32ull * Rc) {
+				// few rows per region (a handful of samples): one thread per REGION walks its rows -- the region's geometry (row base,
+				// matrix base, width) is looked up once instead of once per row, and its rows are one contiguous block of the matrix
+				parallel_for<C_pair_count>(c, (size_t)Rc + 1, PV_LAMBDA(size_t rr_) {
+					if (rr_ >= Rc) { pairCnt_[nRows] = 0; return; }
+					const u32 r = (u32)rr_, rb = rv.rowBase(r), nh = rv.rowBase(r + 1) - rb;
+					for (u32 i = 0; i < nh; i++) pairCnt_[rb + i] = scan_pair_ri(cv, refLocal, k, r, i, rb + i, false, CandView{}, 0);
+				});
+			} else
 			parallel_for<C_pair_count>(c, (size_t)nRows + 1, PV_LAMBDA(size_t row) {
 				pairCnt_[row] = row < nRows ? scan_pair(cv, refLocal, k, (u32)row, false, CandView{}, 0) : 0u;
 			});
@@ -846,6 +860,7 @@ inline void overlay_pass(Ctx &c, const DevGraph &G, const GraphView &g, const Ca
 		u16 *gt_ = gt.p;
 		tr.mark("C6 group+emit");
 		// ---- C7: genotypes.  Paths equal to the ref over the context columns with an identical slice -> 0 (overlay.cpp:534-580)
+		// (one thread per RECORD walking its rows was measured slower at 16 paths: 256 vs 180 us -- too few threads to hide the loads)
 		parallel_for<C_gt_ref>(c, nGt, PV_LAMBDA(size_t x) {
 			u32 rec = uniformNh ? (u32)(x / uniformNh) : (u32)(ub_u64(gtOff_, 0, (u64)nRec + 1, (u64)x) - 1);
 			u32 i = (u32)(x - gtOff_[rec]);

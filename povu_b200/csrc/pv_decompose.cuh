@@ -214,6 +214,45 @@ PV_DEV void uf_union_hashed(u32 *uf, u32 a, u32 b) {
 	}
 }
 
+// Round 0 of the DFS labels the components of the WHOLE graph.  Segment ids of real graphs follow the backbone, so most edges
+// join two segments a few indices apart: a CTA first unites its own span of UF_SPAN consecutive segments in shared memory
+// (the same hashed hooking, shared-memory atomics), writes every segment's local root, and the global pass that follows
+// only sees the edges that leave a span.  Without locality the pre-pass finds nothing to join and costs one sweep.
+PV_KERNEL(K_uf_local, 28);
+#ifndef PV_EMU
+static const int UF_SPAN = 2048, UF_THREADS = 512;
+__device__ __forceinline__ u32 ufl_find(volatile u32 *s, u32 x) {
+	u32 p = s[x];
+	while (p != x) { u32 gp = s[p]; if (gp != p) s[x] = gp; x = p; p = gp; }
+	return x;
+}
+__global__ void __launch_bounds__(UF_THREADS) uf_local_kernel(const u32 *adjOff, const u32 *adjNbr, u32 V, u32 *uf) {
+	__shared__ u32 s[UF_SPAN];
+	pdl_wait();
+	const u32 base = blockIdx.x * UF_SPAN;
+	for (u32 l = threadIdx.x; l < UF_SPAN; l += UF_THREADS) s[l] = l;
+	__syncthreads();
+	for (u32 t = threadIdx.x; t < 2 * UF_SPAN; t += UF_THREADS) {      // one port per step
+		const u32 l = t >> 1, v = base + l;
+		if (v >= V) continue;
+		const u32 p = 2 * v + (t & 1u);
+		for (u32 e = adjOff[p], ee = adjOff[p + 1]; e < ee; e++) {
+			const u32 w = adjNbr[e] >> 1;
+			if (w >= v || w < base) continue;      // each edge inside the span once, from its higher end
+			u32 a = l, b = w - base;
+			while (true) {
+				a = ufl_find(s, a); b = ufl_find(s, b);
+				if (a == b) break;
+				if (uf_priority(base + a) > uf_priority(base + b)) { u32 x = a; a = b; b = x; }
+				if (atomicCAS(s + a, a, b) == a) break;
+			}
+		}
+	}
+	__syncthreads();
+	for (u32 l = threadIdx.x; l < UF_SPAN; l += UF_THREADS) if (base + l < V) uf[base + l] = base + ufl_find(s, l);
+}
+#endif
+
 // Which class re-encounters still find their previous occurrence on the reference's stack?  (see D6 in decompose_device)
 // prv[i] = previous stack position of i's class or NONE.  fire[i]: 1 = the arc (prv[i], i) fires, 2 = dead or no arc.
 // Returns the number of fixpoint rounds after the laminarity pass (0 = no two arcs cross), -1 if undecided arcs remain after
@@ -333,10 +372,22 @@ inline void decompose_device(Ctx &c, u32 V, u64 E, const u32 *ep1, const u32 *ep
 #endif
 		// (a,b,c) connected components of the still-unvisited part (segment granularity)
 		parallel_for<K_uf_init>(c, nA, PV_LAMBDA(size_t i) { u32 v = act[i]; uf_[v] = v; claim_[v] = 0; trunc_[v] = NONE; });
+		u32 span = 0;      // > 0: segments of one span of `span` consecutive indices are already united (round 0, see uf_local_kernel)
+#ifndef PV_EMU
+		static const bool no_local = getenv("POVU_B200_UF_NO_LOCAL") != nullptr;
+		if (round == 0 && !no_local && V >= 4u * UF_SPAN) {
+			span = UF_SPAN;
+			c.prof_begin(K_uf_local::name(), V, (size_t)V * K_uf_local::bytes);
+			PV_CUDA_CHECK(launch_pdl(uf_local_kernel, dim3((unsigned)((V + UF_SPAN - 1) / UF_SPAN)), dim3(UF_THREADS), 0, c.stream, adjOff_, adjNbr_, V, uf_));
+			c.prof_end();
+			c.launches++;
+		}
+#endif
 		parallel_for<K_uf_union>(c, (size_t)nA * 2, PV_LAMBDA(size_t i) {
 			u32 v = act[i >> 1]; u32 p = 2 * v + (u32)(i & 1);
 			for (u32 s = adjOff_[p], e = adjOff_[p + 1]; s < e; s++) {
 				u32 w = adjNbr_[s] >> 1;
+				if (span && w / span == v / span) continue;
 				if (w < v && !visited_[w]) uf_union_hashed(uf_, v, w);   // an edge between two unvisited segments is seen from both ends: join once
 			}
 		});

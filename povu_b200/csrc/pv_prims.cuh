@@ -159,9 +159,9 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_lb_kernel(const T *in, T *o
 
 // Mid-sized inputs (every tile resident at once: up to a few million elements, the regime of cfg2) are latency-bound in the
 // look-back above: tile i walks back through its predecessors 32 at a time, one dependent round trip to L2 per window.  Here a
-// tile publishes its aggregate and then fetches the aggregates of ALL its predecessors at once: lane L of warp 0 owns a
-// contiguous block of ceil(i / 32) predecessors (independent loads, combined in order), then one ordered warp reduction.  One
-// round trip instead of i / 32.  4-byte elements travel with their epoch in one 64-bit word (no fence, no second load).
+// tile publishes its aggregate and then fetches the aggregates of ALL its predecessors at once: thread t of the CTA owns a
+// contiguous block of ceil(i / 512) predecessors (independent loads, combined in order), then an ordered warp and CTA reduction.
+// One round trip instead of i / 32.  4-byte elements travel with their epoch in one 64-bit word (no fence, no second load).
 template <class T> struct ScanPack { static const bool value = sizeof(T) == 4; };
 
 // Bulk asynchronous copies (the TMA unit's 1-D path, UBLKCP in SASS): one elected thread moves a whole scan tile between
@@ -192,8 +192,8 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_flat_kernel(const T *in, T 
 								   u32 *ticket, u32 epoch, u32 ntiles) {
 	constexpr int SCAN_ITEMS = ScanCfg<T>::ITEMS, SCAN_TILE = ScanCfg<T>::TILE;
 	extern __shared__ __align__(128) unsigned char scan_dsm[];      // TMA: the tile (SCAN_TILE * sizeof(T) bytes)
-	__shared__ T warpTot[SCAN_THREADS / 32];
-	__shared__ T s_prefix;
+	__shared__ T warpTot[SCAN_THREADS / 32], warpPre[SCAN_THREADS / 32];
+	__shared__ u32 warpHave[SCAN_THREADS / 32];
 	__shared__ u32 s_tile;
 	__shared__ __align__(8) u64 s_bar;
 	const int t = threadIdx.x, lane = t & 31, w = t >> 5;
@@ -233,49 +233,58 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_flat_kernel(const T *in, T 
 	for (int d = 1; d < 32; d <<= 1) { T y = shfl_up_t(inc, d); if (lane >= d) inc = op(y, inc); }
 	if (lane == 31) warpTot[w] = inc;
 	__syncthreads();
-	if (w == 0) {
+	if (w == 0 && lane == 0 && tile + 1 < ntiles) {   // publish the tile's aggregate first (nobody reads the last tile's)
 		T tot = warpTot[0];
 #pragma unroll
 		for (int i = 1; i < SCAN_THREADS / 32; i++) tot = op(tot, warpTot[i]);
-		if (lane == 0 && tile + 1 < ntiles) {   // (nobody reads the last tile's aggregate)
-			if (ScanPack<T>::value) { union { T t; u32 u; } cv; cv.u = 0; cv.t = tot; *(volatile u64 *)(pack + tile) = ((u64)epoch << 32) | cv.u; }
-			else { agg[tile] = tot; __threadfence(); st_flag(flags + tile, (epoch << 2) | 1u); }
-		}
-		// predecessors [0, tile): lane L combines [L * k, (L + 1) * k) in order
-		const u32 k = (tile + 31u) / 32u;
-		const u32 j0 = (u32)lane * k, j1 = j0 + k < tile ? j0 + k : tile;
+		if (ScanPack<T>::value) { union { T t; u32 u; } cv; cv.u = 0; cv.t = tot; *(volatile u64 *)(pack + tile) = ((u64)epoch << 32) | cv.u; }
+		else { agg[tile] = tot; __threadfence(); st_flag(flags + tile, (epoch << 2) | 1u); }
+	}
+	// predecessors [0, tile): thread t combines [t * k, (t + 1) * k) in order -- the whole CTA fetches, so up to SCAN_THREADS
+	// predecessors cost ONE round trip to L2 (the loads of a thread are issued back to back and only then tested and re-polled)
+	{
+		const u32 k = (tile + (u32)SCAN_THREADS - 1u) / (u32)SCAN_THREADS;
+		const u32 j0 = (u32)t * k < tile ? (u32)t * k : tile, j1 = j0 + k < tile ? j0 + k : tile;
 		T v = identity; bool have = false;   // (never combine with `identity` on the right: segmented operators only honour it on the left)
 		for (u32 j = j0; j < j1; j += 4) {
 			T x[4];
+			if (ScanPack<T>::value) {
+				u64 wd[4];
 #pragma unroll
-			for (int q = 0; q < 4; q++) {
-				if (j + q < j1) {
-					if (ScanPack<T>::value) {
-						u64 wd;
-						do { wd = *(const volatile u64 *)(pack + j + q); } while ((u32)(wd >> 32) != epoch);
-						union { T t; u32 u; } cv; cv.u = (u32)wd; x[q] = cv.t;
-					} else {
-						u32 f;
-						do { f = *(const volatile u32 *)(flags + j + q); } while ((f >> 2) != epoch);
-						__threadfence();
-						x[q] = ld_cg_t(agg + j + q);
-					}
+				for (int q = 0; q < 4; q++) if (j + q < j1) wd[q] = *(const volatile u64 *)(pack + j + q);
+#pragma unroll
+				for (int q = 0; q < 4; q++) if (j + q < j1) {
+					while ((u32)(wd[q] >> 32) != epoch) wd[q] = *(const volatile u64 *)(pack + j + q);
+					union { T t; u32 u; } cv; cv.u = (u32)wd[q]; x[q] = cv.t;
 				}
+			} else {
+				u32 f[4];
+#pragma unroll
+				for (int q = 0; q < 4; q++) if (j + q < j1) f[q] = *(const volatile u32 *)(flags + j + q);
+#pragma unroll
+				for (int q = 0; q < 4; q++) if (j + q < j1) { while ((f[q] >> 2) != epoch) f[q] = *(const volatile u32 *)(flags + j + q); }
+				__threadfence();      // one fence for the (up to) four values whose flags were seen
+#pragma unroll
+				for (int q = 0; q < 4; q++) if (j + q < j1) x[q] = ld_cg_t(agg + j + q);
 			}
 #pragma unroll
 			for (int q = 0; q < 4; q++) if (j + q < j1) { v = have ? op(v, x[q]) : x[q]; have = true; }
 		}
-		// ordered product over the lanes that hold something (lower lanes = earlier tiles)
+		// ordered product over the lanes that hold something (lower lanes = earlier tiles), then over the warps
 #pragma unroll
 		for (int d = 1; d < 32; d <<= 1) {
 			T y = shfl_up_t(v, d); bool hy = __shfl_up_sync(0xFFFFFFFFu, have ? 1 : 0, d) != 0;
 			if (lane >= d && hy) { v = have ? op(y, v) : y; have = true; }
 		}
-		if (!have) v = identity;
-		if (lane == 31) s_prefix = v;
+		if (lane == 31) { warpPre[w] = v; warpHave[w] = have ? 1u : 0u; }
 	}
 	__syncthreads();
-	T run = s_prefix;
+	T run = identity;
+	{
+		bool hr = false;
+#pragma unroll
+		for (int i = 0; i < SCAN_THREADS / 32; i++) if (warpHave[i]) { run = hr ? op(run, warpPre[i]) : warpPre[i]; hr = true; }
+	}
 	for (int i = 0; i < w; i++) run = op(run, warpTot[i]);
 	T prevLane = shfl_up_t(inc, 1);
 	if (lane > 0) run = op(run, prevLane);
