@@ -1548,18 +1548,21 @@ inline void call_device(Ctx &c, const DevGraph &G, const CallIn &in, const CallO
 			if (!hit) called_[f] = 0;
 		});
 	}
-	Buf<u32> rov0;
-	const u32 R0 = compact_flags(c, called.p, nFl, rov0);
-	out.n_called = R0;
+	// (the number of called regions R0 is not read back here: tier 0 below runs over the upper bound nFl and looks the count up
+	// on the device, so that R0 and the tier-0 counters share one host wait)
+	Buf<u32> rov0, calledPos;
+	u32 R0 = 0;
+	MultiRead mrSel(c);
+	compact_flags(c, called.p, nFl, rov0, &calledPos, &mrSel, &R0);
 	tr.mark("C1 select");
-	if (R0 == 0) return;
 
 	// ------------------------------------------------------------------ C2: vertex order per region
 	// tier 0: thread-private scratch; overflowing regions retry with 16x larger slices of a global arena
-	Buf<u32> J0(c, R0), vtmp(c, (size_t)R0 * 12), cnt(c, 8);
+	Buf<u32> J0(c, nFl), vtmp(c, (size_t)nFl * 12), cnt(c, 8);
 	cnt.zero();
-	u32 *J0_ = J0.p, *vtmp_ = vtmp.p, *cnt_ = cnt.p; const u32 *rov0_ = rov0.p;
-	parallel_for<C_bfs>(c, R0, PV_LAMBDA(size_t r) {
+	u32 *J0_ = J0.p, *vtmp_ = vtmp.p, *cnt_ = cnt.p; const u32 *rov0_ = rov0.p, *R0dev = calledPos.p + nFl;
+	parallel_for<C_bfs>(c, nFl, PV_LAMBDA(size_t r) {
+		if (r >= *R0dev) return;
 		u32 tv[12], es[13], et[32], dg[12], od[12], ov[12];
 		BfsScratch s{12, 32, tv, es, et, dg, od, nullptr, nullptr, 0};
 		u32 f = rov0_[r];
@@ -1569,7 +1572,9 @@ inline void call_device(Ctx &c, const DevGraph &G, const CallIn &in, const CallO
 		if (n == 0) atomic_add(cnt_ + 3, 1u);
 		for (u32 k = 0; k < n; k++) vtmp_[r * 12 + k] = ov[k];
 	});
-	u32 hc[8]; c.d2h(hc, cnt.p, 32);
+	u32 hc[8]; mrSel.add(hc, cnt.p, 32); mrSel.wait();
+	out.n_called = R0;
+	if (R0 == 0) return;
 	// regions that did not fit tier 0 retry in 16x larger slices of a global arena.  The orders stay where the
 	// kernel wrote them (the arenas live until the gather below); only the per-slice result counts go to the host.
 	std::vector<Buf<u32>> arenas;

@@ -204,7 +204,9 @@ PV_DEV void uf_union(u32 *uf, u32 a, u32 b) {
 // Hooking by a hashed priority instead of by index: on chain-shaped graphs (vertex ids ascending along the backbone) hooking
 // by index first builds one long list that every later find has to halve; a random priority keeps the trees shallow.  The
 // root is then an arbitrary member of the component (callers that need the lowest vertex index fix it up afterwards).
-PV_DEV u64 uf_priority(u32 x) { return ((u64)(u32)splitmix64(x) << 32) | x; }
+// (a bijective 32-bit mixer: priorities are unique without a tie-break word, and cost five integer instructions -- the hooking
+// loops below are instruction-bound, the 64-bit splitmix here was most of their time)
+PV_DEV u32 uf_priority(u32 x) { x *= 0x9E3779B1u; x ^= x >> 15; x *= 0x85EBCA6Bu; x ^= x >> 13; x *= 0xC2B2AE35u; x ^= x >> 16; return x; }
 PV_DEV void uf_union_hashed(u32 *uf, u32 a, u32 b) {
 	while (true) {
 		a = uf_find(uf, a); b = uf_find(uf, b);

@@ -215,6 +215,7 @@ struct Session {
 	// from_host: forget the device copy of the whole graph first, so that this call uploads it from the host arrays again
 	void shard(u32 rank, u32 world, bool from_host = false) {
 		const double t0 = now_ms();
+		pv::Trace trs(*c, "session.shard");
 		if (!have_full) {
 			upload_edges(); upload_raw_paths(); c->up_join();
 			if (from_host) ensure_host(true, true, true);
@@ -248,7 +249,9 @@ struct Session {
 		if (full.stepOff.empty()) full.stepOff.assign(1, 0);
 		in.h_stepOff = full.stepOff.data();
 		pv::ShardOut o;
+		trs.mark("whole graph host -> HBM");
 		pv::shard_device(*c, in, rank, world, o);
+		trs.mark("shard_device");
 		// install the share as the session's graph: the big arrays exist only in HBM (ensure_host brings them on demand)
 		c->bg_sync(); c->up_join();
 		invalidate_graph_state();
@@ -264,6 +267,7 @@ struct Session {
 		host_edges = o.E == 0; host_steps = o.S == 0; host_lbl = false;
 		comp_global = o.comp_global; shard_owner = o.owner; n_comp_total = o.n_comp_total;
 		sharded = true;
+		trs.mark("install the share");
 		t_shard_ms = now_ms() - t0;
 	}
 
