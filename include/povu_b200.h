@@ -137,6 +137,20 @@ uint32_t pvgpu_session_tree_count(const pvgpu_session *s);
 uint32_t pvgpu_session_tree_component(const pvgpu_session *s, uint32_t k);
 char *pvgpu_session_pvst_text(const pvgpu_session *s, uint32_t k, size_t *len);
 int pvgpu_session_write_pvst(const pvgpu_session *s, const char *dir);
+/* The reference's two debug surfaces.  With the debug numbering on, decompose also derives -- in parallel, from
+ * the tree it already holds (pv_refnum.cuh) -- the reference's internal numbering: tree-edge indices / ids in creation order, the
+ * new_class() ids of simple_cycle_equiv, capping back edges, top brackets.
+ *   pvgpu_session_hairpin_text           `povu decompose -h`: the "Boundary: b1 b2" lines the reference prints to stderr per component
+ *                                        (/root/reference/src/povu/algorithms/flubbles.cpp:503-719), component order
+ *   pvgpu_session_flubble_debug_frames   one "povu.flubble-debug.frame.v1" JSON line per component (flubbles.cpp:108-213): the content of
+ *                                        the side file <json>.flubble-debug.jsonl that `gfa2vcf --structure-export json` leaves behind
+ *   pvgpu_session_structure_export       after call: writes the "povu.lean4.structure.v1" document of `--structure-export`
+ *                                        (/root/reference/src/mto/to_structure_export.cpp:148-640); frames_jsonl = the side file's content
+ * Texts are malloc'ed (pvgpu_free). */
+int pvgpu_session_set_debug_numbering(pvgpu_session *s, int on);
+char *pvgpu_session_hairpin_text(const pvgpu_session *s, size_t *len);
+char *pvgpu_session_flubble_debug_frames(const pvgpu_session *s, size_t *len);
+int pvgpu_session_structure_export(pvgpu_session *s, const char *json_path, const char *input_name, size_t chunk_size, const char *frames_jsonl);
 int pvgpu_session_read_pvst(pvgpu_session *s, const char *dir);
 /* call against the paths selected by the prefixes (refs.hpp:278-301).  Records stay in the session. */
 int pvgpu_session_call(pvgpu_session *s, const char *const *prefixes, size_t n_prefixes);

@@ -18,7 +18,7 @@
 
 int main(int argc, char **argv)
 {
-	if (argc < 2) { fprintf(stderr, "usage: povu_ref {gfa2vcf|decompose|call} -i gfa [-o dir] [-f dir] [-P prefix]... [-r file] [-t N] [-c N] [-q N] [-v N] [-s] [-h]\n"); return 2; }
+	if (argc < 2) { fprintf(stderr, "usage: povu_ref {gfa2vcf|decompose|call} -i gfa [-o dir] [-f dir] [-P prefix]... [-r file] [-t N] [-c N] [-q N] [-v N] [-s] [-h] [--structure-export json]\n"); return 2; }
 	core::config cfg;
 	std::string task = argv[1];
 	bool have_out = false;
@@ -37,6 +37,7 @@ int main(int argc, char **argv)
 		else if (a == "-g" || a == "--restrict") cfg.set_genomic_region(val());
 		else if (a == "-s" || a == "--subflubbles") cfg.set_subflubbles(true);
 		else if (a == "-h" || a == "--hairpins") cfg.set_hairpins(true);
+		else if (a == "--structure-export") cfg.set_structure_export_path(val());
 		else if (a == "--stdout") { }
 		else { cfg.set_ref_input_format(core::input_format_e::params); cfg.add_ref_name_prefix(a); }
 	}

@@ -7,8 +7,10 @@
 // app/main.cpp:12-44 (a parse error prints the message + usage to stderr and the process then exits 0 without
 // doing anything) and app/subcommand/{gfa2vcf,decompose,call}.cpp (outputs, error text, exit codes).
 // Host code only: all graph work goes through the C ABI of libpovu_b200.so (include/povu_b200.h).
-// Not provided (outside the hot path): info, prune, vcf, --structure-export,
-// -s/--subflubbles -- they fail loudly instead of silently doing something else.
+// -h/--hairpins prints the reference's "Boundary: b1 b2" report to stderr; --structure-export writes the conformance JSON and
+// its <json>.flubble-debug.jsonl side file (to_structure_export.cpp, flubbles.cpp:108-231).
+// Not provided (outside the hot path): info, prune, vcf, -s/--subflubbles -- they fail loudly instead
+// of silently doing something else.
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -125,12 +127,34 @@ struct Dev {
 
 static void unsupported(const Config &c) {
 	if (c.subflubbles) throw Fail{"-s/--subflubbles is not provided by povu_b200 (sub-flubble passes are outside the accelerated hot path)"};
-	if (!c.structure_export.empty()) throw Fail{"--structure-export is not provided by povu_b200"};
-	if (c.hairpins) throw Fail{"-h/--hairpins is not provided by povu_b200 (the reference's stderr report of hairpin boundaries, flubbles.cpp:711-717)"};
+}
+
+// text returned by the library (malloc'ed) -> std::string
+static std::string take(Dev &d, char *p, size_t n) { if (!p) throw Fail{pvgpu_last_error(d.ctx)}; std::string s(p, n); pvgpu_free(p); return s; }
+static std::string sidecar_path(const Config &c) { return c.structure_export + ".flubble-debug.jsonl"; }   // flubbles.cpp:217-220
+static std::string read_file(const std::string &fp) { std::ifstream in(fp, std::ios::binary); return std::string((std::istreambuf_iterator<char>(in)), std::istreambuf_iterator<char>()); }
+static std::string base_name(const std::string &fp) { size_t k = fp.find_last_of('/'); return k == std::string::npos ? fp : fp.substr(k + 1); }
+
+// after decompose: the hairpin report (stderr) and the debug frames of the structure export (appended to the side file)
+static void debug_outputs(const Config &c, Dev &d) {
+	if (c.hairpins) { size_t n = 0; char *p = pvgpu_session_hairpin_text(d.s, &n); std::string t = take(d, p, n); fwrite(t.data(), 1, t.size(), stderr); }
+	if (!c.structure_export.empty()) {
+		size_t n = 0; char *p = pvgpu_session_flubble_debug_frames(d.s, &n); std::string t = take(d, p, n);
+		std::ofstream out(sidecar_path(c), std::ios::app | std::ios::binary);
+		if (!out.is_open()) throw Fail{"could not open flubble debug sidecar: " + sidecar_path(c)};
+		out << t;
+	}
+}
+static void structure_export(const Config &c, Dev &d) {
+	if (c.structure_export.empty()) return;
+	std::string frames = read_file(sidecar_path(c));
+	d.check(pvgpu_session_structure_export(d.s, c.structure_export.c_str(), base_name(c.gfa).c_str(), c.chunk, frames.c_str()));
 }
 
 static void do_decompose(const Config &c, Dev &d, const std::string &out_dir) {
+	pvgpu_session_set_debug_numbering(d.s, c.hairpins);
 	d.check(pvgpu_session_decompose(d.s));
+	debug_outputs(c, d);
 	if (c.verbosity > 1) fprintf(stderr, "INFO [povu::decompose] Found %u components with at least 3 vertices\n", pvgpu_session_tree_count(d.s));
 	d.check(pvgpu_session_write_pvst(d.s, out_dir.c_str()));
 }
@@ -157,6 +181,7 @@ static void write_vcfs(const Config &c, Dev &d, const std::vector<std::string> &
 		fflush(stdout);
 		d.check(pvgpu_session_vcf_write(d.s, c.chunk, 1, nullptr, STDOUT_FILENO, nullptr));
 		if (region_bad) exit(EXIT_FAILURE);
+		structure_export(c, d);
 		return;
 	}
 	mkdir(c.out_dir.c_str(), 0777);   // create_dir_if_not_exists (to_vcf.hpp:83-101)
@@ -169,6 +194,7 @@ static void write_vcfs(const Config &c, Dev &d, const std::vector<std::string> &
 		d.check(rc);
 	}
 	if (region_bad) exit(EXIT_FAILURE);
+	structure_export(c, d);
 }
 
 int main(int argc, char **argv) {
@@ -195,7 +221,10 @@ int main(int argc, char **argv) {
 				double t0 = now_ms();
 				Dev d; d.open(c, true, true);
 				double t1 = now_ms();
+				if (!c.structure_export.empty()) remove(sidecar_path(c).c_str());   // reset_debug_sidecar (gfa2vcf.cpp:46)
+				pvgpu_session_set_debug_numbering(d.s, c.hairpins || !c.structure_export.empty());
 				d.check(pvgpu_session_decompose(d.s));
+				debug_outputs(c, d);
 				if (c.verbosity > 1) fprintf(stderr, "INFO [povu::decompose] Found %u components with at least 3 vertices\n", pvgpu_session_tree_count(d.s));
 				double t2 = now_ms();
 				write_vcfs(c, d, prefixes_of(c));

@@ -2,6 +2,7 @@
 #include "../../include/povu_b200.h"
 #include "pv_engine.hpp"
 #include "pv_ffi.hpp"
+#include "pv_export.hpp"
 #include <cerrno>
 
 struct pvgpu_ctx { pv::Ctx c; std::string err; };
@@ -390,6 +391,16 @@ uint32_t pvgpu_session_tree_count(const pvgpu_session *s) { return (uint32_t)s->
 uint32_t pvgpu_session_tree_component(const pvgpu_session *s, uint32_t k) { return s->s.forest.comp_id[k]; }
 char *pvgpu_session_pvst_text(const pvgpu_session *s, uint32_t k, size_t *len) {
 	try { return dup_text(s->s.pvst_text(k), len); } catch (std::exception &e) { s->x->err = e.what(); return nullptr; }
+}
+int pvgpu_session_set_debug_numbering(pvgpu_session *s, int on) { s->s.debug_numbering = on != 0; return 0; }
+char *pvgpu_session_hairpin_text(const pvgpu_session *s, size_t *len) {
+	try { return dup_text(pve::hairpin_text(s->s), len); } catch (std::exception &e) { s->x->err = e.what(); return nullptr; }
+}
+char *pvgpu_session_flubble_debug_frames(const pvgpu_session *s, size_t *len) {
+	try { return dup_text(pve::flubble_debug_frames(s->s), len); } catch (std::exception &e) { s->x->err = e.what(); return nullptr; }
+}
+int pvgpu_session_structure_export(pvgpu_session *s, const char *json_path, const char *input_name, size_t chunk, const char *frames_jsonl) {
+	PV_TRY(s->x, pve::structure_export(s->s, json_path, input_name ? input_name : "", chunk, frames_jsonl ? frames_jsonl : ""))
 }
 int pvgpu_session_write_pvst(const pvgpu_session *s, const char *dir) { PV_TRY(s->x, s->s.write_pvsts(dir)) }
 int pvgpu_session_read_pvst(pvgpu_session *s, const char *dir) { PV_TRY(s->x, s->s.read_pvsts(dir)) }

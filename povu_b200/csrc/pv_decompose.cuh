@@ -23,6 +23,7 @@
 //      queries; non-laminar components replay the reference's stack machine (one thread each).
 #pragma once
 #include "pv_prims.cuh"
+#include "pv_refnum.cuh"
 
 namespace pv {
 
@@ -40,13 +41,14 @@ struct DecompOut {
 	std::vector<u32> stack_v;       // class stack: vertex idx per position (components concatenated)
 	std::vector<u32> stack_class;   // dense class id per position
 	std::vector<u32> stack_fwd;
+	std::vector<u32> stack_next;    // next stack position of the same class (the position itself when there is none), components concatenated
 	u32 dfs_rounds = 0;
 	u32 arc_rounds = 0;      // rounds of the fired-arc fixpoint (0 = every component laminar; > 64 = the sequential replay ran)
 	u32 collisions = 0;
 	void reset() {   // keeps the (page-locked) capacity of the big arrays
 		comp.clear(); a_v.clear(); z_v.clear(); a_fwd.clear(); z_fwd.clear(); parent.clear(); depth.clear(); fl_base.clear();
 		comp_root.clear(); comp_nv.clear(); comp_nfl.clear(); comp_has_tips.clear(); comp_nonlaminar.clear();
-		stack_v.clear(); stack_class.clear(); stack_fwd.clear(); dfs_rounds = 0; arc_rounds = 0; collisions = 0;
+		stack_v.clear(); stack_class.clear(); stack_fwd.clear(); stack_next.clear(); dfs_rounds = 0; arc_rounds = 0; collisions = 0;
 	}
 };
 
@@ -55,6 +57,7 @@ struct DecompOpts {
 	Buf<u32> *keep_labels = nullptr;   // receives label[v] = lowest vertex index of v's component (what pv_call's component_labels computes)
 	struct DevForest *keep_forest = nullptr;   // receives the flubble table on the device (call reads it there instead of re-uploading)
 	bool async_results = false;        // the big result arrays travel on the context's copy stream; the caller must c.bg_sync() before reading them
+	RefNumOut *refnum = nullptr;       // also derive the reference's internal numbering (pv_refnum.cuh: --hairpins / --structure-export only)
 };
 // the flubble table as decompose left it in HBM
 struct DevForest { Buf<u32> a_v, z_v, parent, depth, comp, fl_base; Buf<u8> a_fwd, z_fwd; u32 n = 0; bool valid = false; };
@@ -676,33 +679,13 @@ inline void decompose_device(Ctx &c, u32 V, u64 E, const u32 *ep1, const u32 *ep
 		u32 p = (u32)pp; u32 v = p >> 1;
 		u32 k = compIdxOfRoot_[gcomp_[v]];
 		u32 myPre = pre_[p];
-		u32 s0 = adjOff_[p], s1 = adjOff_[p + 1];
-		bool isExit = (p & 1u) != entrySide_[v];
-		bool loopDone = false;
-		auto emit = [&](u32 tgtPre, u64 id) {
+		for_each_backedge(p, adjOff_, adjNbr_, pre_, parent_, entrySide_, cNodeBase_[k], M, [&](u32 tgtPre, u64 id, u32) {
 			u64 lo = splitmix64(seed ^ (id * 2)), hi = splitmix64((seed * 0x9E3779B97F4A7C15ull) ^ (id * 2 + 1));
 			atomic_xor(X_ + 2 * (size_t)myPre, lo); atomic_xor(X_ + 2 * (size_t)myPre + 1, hi);
 			atomic_xor(X_ + 2 * (size_t)tgtPre, lo); atomic_xor(X_ + 2 * (size_t)tgtPre + 1, hi);
 			atomic_add((u32 *)cd_ + myPre, 1u); atomic_add((u32 *)cd_ + tgtPre, 0xFFFFFFFFu);
 			atomic_min(minT_ + myPre, tgtPre);
-		};
-		if (s0 == s1) {   // tip side: back edge to the dummy root unless the tree already links them (spanning_tree.cpp:431-438)
-			if (parent_[p] != NONE) emit(cNodeBase_[k], (u64)M + p);
-			return;
-		}
-		for (u32 s = s0; s < s1; s++) {
-			u32 q = adjNbr_[s];
-			if (q == (p ^ 1u)) {   // self-loop: one extra back edge per segment, from the child side (spanning_tree.cpp:387-395)
-				if (isExit && !loopDone) { loopDone = true; emit(pre_[q], s); }
-				continue;
-			}
-			u32 qPre = pre_[q];
-			if (qPre > myPre) continue;            // recorded from the deeper endpoint
-			if (parent_[p] == q) continue;          // the tree edge itself, or parallel to it
-			bool dup = false;
-			for (u32 t = s0; t < s; t++) if (adjNbr_[t] == q) { dup = true; break; }   // parallel edges collapse (spanning_tree.cpp:379-386)
-			if (!dup) emit(qPre, s);
-		}
+		});
 	});
 	// bridges -> simplifying back edges (flubbles.cpp:621-643): v gets one iff no bracket leaves subtree(v)
 	// upwards and no vertex below v got one
@@ -967,6 +950,12 @@ inline void decompose_device(Ctx &c, u32 V, u64 E, const u32 *ep1, const u32 *ep
 		std::vector<u32> es = entrySide.to_host();
 		out.stack_fwd.resize(nS);
 		for (u32 i = 0; i < nS; i++) out.stack_fwd[i] = es[out.stack_v[i]] == 0;
+		out.stack_next = nxt.to_host();
+	}
+	if (opt.refnum) {
+		RefNumIn rn{V, P, N, nComp, nS, M, adjOff_, adjNbr_, treeSlot_, parent_, entrySide_, pre_, sz_, depth_, pre2node_, compIdxOfRoot_, gcomp_, cNodeBase_, cNv_, cHasTips_, cSegBase_,
+			    bridge_, bsum_, PC_, rmq2.view(), minT_, stV_, segComp_};
+		refnum_device(c, rn, *opt.refnum);
 	}
 	tr.mark("results d2h");   // (pack.to_host() above waited for the stream: every copy queued on it before has landed)
 	if (sm.on && sm.n == 9) {

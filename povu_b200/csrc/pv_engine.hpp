@@ -28,6 +28,7 @@ struct Session {
 	pv::DevGraph dg; bool edges_up = false, paths_up = false;
 	pvh::Forest forest; bool forest_ready = false; int forest_subfl = -1; std::vector<u32> tree_label;   // tree_label: component label per tree (call slices the forest by it)   // forest_subfl: does the forest hold sub-flubble families (-1 = not looked yet)
 	pv::DecompOut dec;
+	bool debug_numbering = false; pv::RefNumOut refnum;   // --hairpins / --structure-export: decompose also derives the reference's internal numbering (pv_refnum.cuh)
 	mutable pvh::Records rec;    // binary records + counters of the last call: born in HBM, copied to the host on demand (rec.to_host)
 	std::vector<std::string> prefixes;
 	std::set<u32> ref_ids;
@@ -281,6 +282,8 @@ struct Session {
 		// connectivity pass); on the hot path the host copies of the results additionally travel behind the next phases
 		opt.keep_labels = &d_labels; opt.keep_forest = &dforest;
 		if (want_labels) opt.async_results = true;
+		refnum.reset();
+		if (debug_numbering) { opt.want_stack = true; opt.refnum = &refnum; }
 		pv::Trace tr(*c, "session");
 		pv::decompose_device(*c, g.V(), g.E(), d_ep1.p, d_ep2.p, opt, dec);
 		labels_ready = d_labels.p != nullptr && (want_labels || !paths_up);   // (the hot path rebuilds the index right after)

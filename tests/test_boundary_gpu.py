@@ -16,3 +16,18 @@ def test_gpu_ffi(gpu, tmp_path):
     L = bc.ffi(os.path.join(bc.ROOT, "povu_b200", "libpovu_b200.so"))
     bc.check_ffi_builder(L)
     bc.check_ffi_compute(L, str(tmp_path))
+
+
+def test_gpu_export_golden(gpu, tmp_path):
+    import export_checks as ec
+    ec.check_export_golden(os.path.join(bc.ROOT, "povu_b200", "bin", "povu"), str(tmp_path))
+
+
+def test_gpu_export_vs_reference(gpu, tmp_path):
+    import export_checks as ec
+    cli = os.path.join(bc.ROOT, "povu_b200", "bin", "povu")
+    nb, ne = ec.check_wild_vs_reference(cli, str(tmp_path), range(40))
+    assert nb > 15 and ne > 400
+    nb, ne = ec.check_wild_vs_reference(cli, str(tmp_path), range(500, 504), V=3000)
+    assert ne > 4000
+    ec.check_families_vs_reference(cli, str(tmp_path))
