@@ -361,6 +361,32 @@ class Session:
         s.n_steps = int(off[-1])
         return s
 
+    @classmethod
+    def from_flat(cls, pv, f, with_labels=True):
+        """Session over the flat arrays of synth.tiled_flat (no per-segment Python objects: chromosome-scale components)."""
+        ids = np.ascontiguousarray(f["ids"], dtype=np.uint32)
+        V = len(ids)
+        ep1 = np.ascontiguousarray(f["v1"].astype(np.uint32) * 2 + f["s1"].astype(np.uint32), dtype=np.uint32)
+        ep2 = np.ascontiguousarray(f["v2"].astype(np.uint32) * 2 + f["s2"].astype(np.uint32), dtype=np.uint32)
+        lens = np.ascontiguousarray(f["seg_len"], dtype=np.uint32)
+        lab_off = np.ascontiguousarray(f["lab_off"], dtype=np.uint64) if with_labels else None
+        lab = np.ascontiguousarray(f["lab"], dtype=np.uint8) if with_labels else None
+        H = len(f["names"])
+        if int(f["step_off"][-1]) >= 0xFFFFFFF0:
+            raise RuntimeError("more than 2^32 path steps in one session")
+        names = (C.c_char_p * max(H, 1))(*[n.encode() for n in f["names"]])
+        off = np.ascontiguousarray(f["step_off"], dtype=np.uint32)
+        steps = np.ascontiguousarray(f["steps"], dtype=np.uint32)
+        h = C.c_void_p()
+        rc = pv.lib.pvgpu_session_from_arrays(pv.h, V, ids.ctypes.data, lens.ctypes.data, lab_off.ctypes.data if lab_off is not None else None,
+                                              lab.ctypes.data if lab is not None else None, len(ep1), ep1.ctypes.data, ep2.ctypes.data, H, names,
+                                              off.ctypes.data, steps.ctypes.data, C.byref(h))
+        if rc != 0:
+            raise RuntimeError(pv._err())
+        s = cls(pv, _handle=h)
+        s.n_steps = int(off[-1])
+        return s
+
     def hot_path(self, prefixes, keep_resident=True):
         """decompose -> device index -> call, once.  Returns ms of (upload, decompose, index, call)."""
         arr = (C.c_char_p * len(prefixes))(*[p.encode() for p in prefixes])

@@ -375,6 +375,95 @@ def tiled(templates, n_instances, n_paths, seed=42, n_components=1, comp_weights
     return g
 
 
+def tiled_flat(templates, n_instances, n_paths, seed=42, chrom="chr1", first_id=1, tpl_weights=None):
+    """One chain-shaped component like `tiled`, but built as FLAT numpy arrays only (no Python object per segment or step): the
+    form a chromosome-scale component needs (10^7 segments x 90 walks).  Returns ids, seg_len, lab_off / lab (concatenated
+    sequences), v1 / s1 / v2 / s2, names, step_off and packed steps ((vertex << 1) | strand), inst_base.  Path 0 takes walk 0
+    of every instance.  Not the same random stream as `tiled` (its own graphs: `window_flat` cuts the reference's share)."""
+    rng = _rng(seed)
+    K = len(templates)
+    if tpl_weights is None:
+        tpl = rng.integers(0, K, size=n_instances)
+    else:
+        w_ = np.asarray(tpl_weights, dtype=np.float64)
+        tpl = np.minimum(np.searchsorted(np.cumsum(w_) / w_.sum(), rng.uniform(size=n_instances), side="right"), K - 1)
+    tV = np.array([t["V"] for t in templates], dtype=np.int64)
+    base = np.concatenate([[0], np.cumsum(tV[tpl])])
+    V = int(base[-1])
+    # per-template pools: segment lengths / sequences, links, walks -- all flat
+    t_seglen = [np.array([len(x) for x in t["seqs"]], dtype=np.int64) for t in templates]
+    t_lab = [np.frombuffer("".join(t["seqs"]).encode(), dtype=np.uint8) for t in templates]
+    t_labn = np.array([len(x) for x in t_lab], dtype=np.int64)
+    seg_len = np.empty(V, dtype=np.uint32)
+    lab_base = np.concatenate([[0], np.cumsum(t_labn[tpl])])      # first base of every instance
+    lab = np.empty(int(lab_base[-1]), dtype=np.uint8)
+    links = []
+    for k in range(K):
+        inst = np.nonzero(tpl == k)[0]
+        if len(inst) == 0:
+            continue
+        b = base[inst]
+        seg_len[(b[:, None] + np.arange(tV[k])[None, :]).ravel()] = np.tile(t_seglen[k].astype(np.uint32), len(inst))
+        lab[(lab_base[inst][:, None] + np.arange(t_labn[k])[None, :]).ravel()] = np.tile(t_lab[k], len(inst))
+        L = templates[k]["links"]
+        LL = np.repeat(L[None, :, :], len(inst), axis=0).copy()
+        LL[:, :, 0] += b[:, None]; LL[:, :, 2] += b[:, None]
+        links.append((inst.repeat(len(L)), LL.reshape(-1, 4)))
+    src = np.array([int(t["walks"][0][0][0]) for t in templates]); snk = np.array([int(t["walks"][0][0][-1]) for t in templates])
+    j = np.arange(n_instances - 1)
+    J = np.stack([base[j] + snk[tpl[j]], np.ones(len(j), np.int64), base[j + 1] + src[tpl[j + 1]], np.zeros(len(j), np.int64)], 1)
+    key = np.concatenate([k_ for k_, _ in links] + [j + 0.5])
+    allL = np.concatenate([l_ for _, l_ in links] + [J])
+    allL = allL[np.argsort(key, kind="stable")]
+    del links, key
+    lab_off = np.concatenate([[0], np.cumsum(seg_len, dtype=np.uint64)]).astype(np.uint64)
+    # walks: one flat pool, walk w of template k = pool[wstart[woff[k] + w] : + wlen[..]] (packed (vertex << 1) | strand, template-local)
+    nW = np.array([len(t["walks"]) for t in templates], dtype=np.int64)
+    woff = np.concatenate([[0], np.cumsum(nW)])
+    wlen = np.array([len(wk[0]) for t in templates for wk in t["walks"]], dtype=np.int64)
+    wstart = np.concatenate([[0], np.cumsum(wlen)])[:-1]
+    pool = np.concatenate([(wk[0].astype(np.int64) << 1) | wk[1].astype(np.int64) for t in templates for wk in t["walks"]])
+    names, parts, step_off = [], [], [0]
+    for p in range(n_paths):
+        choice = rng.integers(0, 1 << 30, size=n_instances) % nW[tpl]
+        if p == 0:
+            choice[:] = 0
+        w = woff[tpl] + choice
+        lens = wlen[w]
+        off = np.concatenate([[0], np.cumsum(lens)])
+        tot = int(off[-1])
+        within = np.arange(tot, dtype=np.int64) - np.repeat(off[:-1], lens)
+        st = pool[np.repeat(wstart[w], lens) + within] + (np.repeat(base[:-1], lens) << 1)
+        parts.append(st.astype(np.uint32)); step_off.append(step_off[-1] + tot)
+        names.append(f"S{p // 2 + 1:03d}#{p % 2 + 1}#{chrom}")
+    return {"ids": np.arange(first_id, first_id + V, dtype=np.uint32), "seg_len": seg_len, "lab_off": lab_off, "lab": lab,
+            "v1": allL[:, 0].astype(np.uint32), "s1": allL[:, 1].astype(np.uint8), "v2": allL[:, 2].astype(np.uint32), "s2": allL[:, 3].astype(np.uint8),
+            "names": names, "step_off": np.asarray(step_off, dtype=np.uint64), "steps": np.concatenate(parts) if parts else np.empty(0, np.uint32), "inst_base": base.astype(np.int64)}
+
+
+def window_flat(f, lo, hi):
+    """vertices [lo, hi) of a `tiled_flat` component as an ordinary graph dict (strings and per-path arrays: small), with the
+    original ids -- what `window` does for `tiled` graphs"""
+    keep = (f["v1"] >= lo) & (f["v1"] < hi) & (f["v2"] >= lo) & (f["v2"] < hi)
+    L = np.stack([f["v1"][keep].astype(np.int64) - lo, f["s1"][keep], f["v2"][keep].astype(np.int64) - lo, f["s2"][keep]], 1)
+    lab = f["lab"].tobytes() if len(f["lab"]) < (1 << 26) else None
+    seqs = []
+    for v in range(lo, hi):
+        a, b = int(f["lab_off"][v]), int(f["lab_off"][v + 1])
+        seqs.append((lab[a:b] if lab is not None else f["lab"][a:b].tobytes()).decode())
+    paths = []
+    for k, name in enumerate(f["names"]):
+        st = f["steps"][int(f["step_off"][k]):int(f["step_off"][k + 1])]
+        vtx = st >> 1
+        a, b = int(np.searchsorted(vtx, lo, side="left")), int(np.searchsorted(vtx, hi, side="left"))      # chain-shaped: steps ascend with the instances
+        m = np.nonzero((vtx >= lo) & (vtx < hi))[0] if not (np.all(vtx[a:b] >= lo) and np.all(vtx[a:b] < hi) and (a == 0 or vtx[a - 1] < lo)) else None
+        if m is not None:
+            a, b = (int(m[0]), int(m[-1]) + 1) if len(m) else (0, 0)
+            assert b - a == len(m), "the walk leaves and re-enters the window"
+        paths.append((name, (vtx[a:b].astype(np.int64) - lo).astype(np.uint32), (st[a:b] & 1).astype(np.uint8)))
+    return make_graph(f["ids"][lo:hi], seqs, L, paths)
+
+
 def inversion_unit(seed=0, inner=1):
     """A block that paths may traverse on the reverse strand: u -> [s -> (x | y) -> t] -> v plus the two links of the
     inverted traversal (u+ -> t-, s- -> v+).  A path that walks t-, x-, s- crosses the region (s, t) as a whole-region

@@ -1,0 +1,196 @@
+#!/usr/bin/env python
+"""cfg4 AT ITS STATED SIZE (`wg_100M_25c` -- 25 weakly connected components with sizes proportional to GRCh38
+chr1-22, X, Y, M, ~100 M segments / ~140 M links in total, 90 haplotype paths per component) on 1 / 2 / 4 / 8 B200.
+
+The input arrives the way whole-genome pangenomes are distributed: ONE GRAPH PER CHROMOSOME (component).  Every rank knows the
+25 component weights (here: from the generator's parameters; for files: their sizes), runs the same greedy LPT over them --
+the partition rule of pvgpu_session_reshard, SURVEY 8e -- and ingests only the components it owns; each owned component is one
+session (one decompose -> index -> call per step; no component holds more than 2^32 path steps, the whole graph does).  No
+exchange while computing; the per-rank record counts are summed at the end (the packed-record NCCL gather is bench.py's
+strong-scaling leg; here the records stay where the VCF writer of each rank would consume them).
+
+Timing: per owned component W warm-up steps, then K steps between two CUDA events on the context's stream; a rank's step time is
+the sum over its components, the job's step time the MAX over ranks (all-reduced).  Parity at this size: windows of the rank's
+smallest owned component are cut out with their original ids, run through the UNMODIFIED reference (oracle/_ref/povu_ref) and
+compared byte for byte with the records the device produced for the same regions (POS shifted by the window's offset on the
+reference walk), every record type included.
+
+usage:  python scripts/wg_full.py [--instances N] [--paths 90] [--steps 2] [--warmup 1] [--windows 2]
+        python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29511 scripts/wg_full.py
+result: gpurun_out/wg_full_n<N>.json (rank 0)"""
+import argparse
+import json
+import os
+import re
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402  (GRCH38 weights)
+
+REF = os.path.join(ROOT, "oracle", "_ref", "povu_ref")
+
+
+def templates():
+    from povu_b200 import synth
+    return [synth.template_from(synth.snp_indel_chain(6, n_paths=6, seed=100 + k)) for k in range(18)] + synth.cfg3_templates(seed=7, n_nested=2, tower_depth=0)
+
+
+def lpt(weights, world):
+    """greedy longest-processing-time: heaviest component first onto the lightest rank (ties: lowest rank) -- pv_shard.cuh's rule"""
+    load = [0.0] * world
+    owner = [0] * len(weights)
+    for c in sorted(range(len(weights)), key=lambda c: (-weights[c], c)):
+        r = min(range(world), key=lambda r: (load[r], r))
+        owner[c] = r; load[r] += weights[c]
+    return owner, load
+
+
+def check_windows(f, lines, prefix, n_windows, width=120, margin=2):
+    from povu_b200 import synth
+    base = f["inst_base"]; n_inst = len(base) - 1
+    ids = f["ids"].astype(np.int64)
+    ref_steps = (f["steps"][int(f["step_off"][0]):int(f["step_off"][1])] >> 1).astype(np.int64)
+    ref_cum = np.concatenate([[0], np.cumsum(f["seg_len"][ref_steps].astype(np.int64))])
+    rec_ids = [[int(x) for x in re.findall(r"\d+", l.split("\t", 3)[2])] for l in lines]
+    rec_lo = np.array([min(x) for x in rec_ids], dtype=np.int64); rec_hi = np.array([max(x) for x in rec_ids], dtype=np.int64)
+    out = []
+    for w in range(n_windows):
+        k0 = int((w + 0.5) * n_inst / n_windows - width / 2)
+        k0 = max(0, min(k0, n_inst - width)); k1 = k0 + width
+        lo, hi = int(base[k0]), int(base[k1])
+        sub = synth.window_flat(f, lo, hi)
+        d = tempfile.mkdtemp()
+        gfa = os.path.join(d, "w.gfa")
+        synth.write_gfa_fast(sub, gfa)
+        t0 = time.time()
+        r = subprocess.run([REF, "gfa2vcf", "-i", gfa, "-P", prefix, "-t", "1"], capture_output=True, text=True)
+        t_ref = time.time() - t0
+        subprocess.run(["rm", "-rf", d])
+        assert r.returncode == 0, r.stderr[-500:]
+        in_lo, in_hi = int(ids[base[k0 + margin]]), int(ids[base[k1 - margin]])
+        first = int(np.searchsorted(ref_steps, lo, side="left"))
+        shift = int(ref_cum[first])
+
+        def canon(line, add):
+            x = line.rstrip("\n").split("\t"); x[1] = str(int(x[1]) + add); return "\t".join(x)
+        sel = np.nonzero((rec_lo >= in_lo) & (rec_hi < in_hi))[0]
+        got = sorted(canon(lines[i], 0) for i in sel)
+        want = []
+        for l in r.stdout.splitlines():
+            if l.startswith("#"):
+                continue
+            x = [int(v) for v in re.findall(r"\d+", l.split("\t", 3)[2])]
+            if min(x) >= in_lo and max(x) < in_hi:
+                want.append(canon(l, shift))
+        want.sort()
+        out.append({"window": w, "instances": [k0, k1], "vertices": hi - lo, "records_compared": len(want), "bit_exact": got == want and len(want) > 0, "reference_s": round(t_ref, 2)})
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--instances", type=int, default=2_100_000)      # ~47.6 segments per instance -> ~100 M segments
+    ap.add_argument("--paths", type=int, default=90)
+    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--warmup", type=int, default=1)
+    ap.add_argument("--windows", type=int, default=2)
+    ap.add_argument("--emu", action="store_true", help="host rehearsal library (logic check in the GPU-less container)")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    from povu_b200 import api, synth
+    torch = dist = None
+    if not args.emu:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        if world > 1:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        stream = torch.cuda.Stream()
+        pv = api.Povu(device=local, stream=stream.cuda_stream)
+    else:
+        pv = api.Povu(lib_path=os.path.join(ROOT, "tests", "emu", "libpovu_emu.so"))
+    w = np.asarray(bench.GRCH38, dtype=np.float64)
+    cuts = np.round(np.cumsum(w) / w.sum() * args.instances).astype(np.int64); cuts[-1] = args.instances
+    n_inst = np.diff(np.concatenate([[0], cuts]))
+    owner, load = lpt([float(x) for x in n_inst], world)
+    mine = [c for c in range(len(n_inst)) if owner[c] == rank and n_inst[c] > 0]
+    T = templates()
+    tot = {"V": 0, "E": 0, "S": 0, "flubbles": 0, "records": 0, "ms": 0.0, "gen_s": 0.0, "ingest_s": 0.0}
+    per_comp, wins = [], []
+    smallest = min(mine, key=lambda c: n_inst[c]) if mine else None
+    for c in mine:
+        t0 = time.time()
+        f = synth.tiled_flat(T, int(n_inst[c]), args.paths, seed=1000 + c, chrom=f"chr{c + 1}")
+        t1 = time.time()
+        check = args.windows > 0 and c == smallest
+        sess = api.Session.from_flat(pv, f, with_labels=check)
+        t2 = time.time()
+        V, E, S = len(f["ids"]), len(f["v1"]), int(f["step_off"][-1])
+        prefix = "S001#1"
+        if args.emu:
+            t = time.time(); sess.hot_path([prefix]); ms = (time.time() - t) * 1e3
+        else:
+            with torch.cuda.stream(stream):
+                for _ in range(args.warmup):
+                    sess.hot_path([prefix])
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                for _ in range(args.steps):
+                    sess.hot_path([prefix])
+                e1.record(stream)
+                torch.cuda.synchronize()
+                ms = e0.elapsed_time(e1) / args.steps
+        nrec = int(sess.lib.pvgpu_session_record_count(sess.h)); nfl = int(sess.lib.pvgpu_session_flubble_count(sess.h))
+        st = sess.call_stats()
+        assert st["hard_errors"] == 0 and nrec > 0
+        if check:
+            lines, _ = sess.record_lines()
+            wins = check_windows(f, lines, prefix, args.windows)
+            for x in wins:
+                x["component"] = c + 1
+            del lines
+        sess.close()
+        per_comp.append({"component": c + 1, "segments": V, "links": E, "path_steps": S, "flubbles": nfl, "records": nrec, "ms_per_step": round(ms, 3)})
+        for k, v in (("V", V), ("E", E), ("S", S), ("flubbles", nfl), ("records", nrec), ("ms", ms), ("gen_s", t1 - t0), ("ingest_s", t2 - t1)):
+            tot[k] += v
+        del f
+        print(f"[rank {rank}] component {c + 1}: V={V} E={E} S={S} {ms:.1f} ms/step, {nrec} records (generated in {t1 - t0:.1f} s, ingest {t2 - t1:.1f} s)", file=sys.stderr, flush=True)
+    ok = all(x["bit_exact"] for x in wins)
+    res = {"rank": rank, "components": [p["component"] for p in per_comp], "per_component": per_comp, "windows": wins, **tot, "peak_device_GB": pv.peak_bytes / 1e9}
+    if world > 1:
+        allres = [None] * world
+        dist.all_gather_object(allres, res)
+    else:
+        allres = [res]
+    if rank == 0:
+        job_ms = max(r["ms"] for r in allres)
+        E = sum(r["E"] for r in allres); V = sum(r["V"] for r in allres); S = sum(r["S"] for r in allres)
+        rec = sum(r["records"] for r in allres)
+        allw = [x for r in allres for x in r["windows"]]
+        out = {"workload": f"cfg4 wg_100M_25c at its stated size: 25 components ~ GRCh38 chromosome sizes, {args.instances} template instances, {args.paths} paths per component; one graph per component, LPT by component weight, one session per owned component",
+               "n_gpus": world, "segments": V, "links": E, "path_steps": S, "flubbles": sum(r["flubbles"] for r in allres), "records": rec,
+               "ms_per_step": job_ms, "edges_per_s": E / (job_ms * 1e-3), "records_per_s": rec / (job_ms * 1e-3), "steps": args.steps, "warmup": args.warmup,
+               "rank_ms": [round(r["ms"], 2) for r in allres], "lpt_load_max_over_mean": max(load) / (sum(load) / len(load)),
+               "rank_components": [r["components"] for r in allres], "peak_device_GB_max": max(r["peak_device_GB"] for r in allres),
+               "generation_s_max": max(r["gen_s"] for r in allres), "ingest_s_max": max(r["ingest_s"] for r in allres),
+               "window_check": {"windows": allw, "bit_exact": all(x["bit_exact"] for x in allw), "records_compared": sum(x["records_compared"] for x in allw)},
+               "per_component": sorted((p for r in allres for p in r["per_component"]), key=lambda p: p["component"])}
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        with open(os.path.join(ROOT, "gpurun_out", f"wg_full_n{world}.json"), "w") as fh:
+            json.dump(out, fh, indent=1)
+        print(json.dumps({k: v for k, v in out.items() if k != "per_component"}))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    assert ok, "a window differs from the reference"
+
+
+if __name__ == "__main__":
+    main()
