@@ -100,6 +100,8 @@ def main():
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--warmup", type=int, default=1)
     ap.add_argument("--windows", type=int, default=2)
+    ap.add_argument("--only", default="", help="comma-separated component numbers (diagnostics)")
+    ap.add_argument("--verbose", action="store_true", help="per step: the phases' wall ms and the DFS round count")
     ap.add_argument("--emu", action="store_true", help="host rehearsal library (logic check in the GPU-less container)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -120,6 +122,8 @@ def main():
     n_inst = np.diff(np.concatenate([[0], cuts]))
     owner, load = lpt([float(x) for x in n_inst], world)
     mine = [c for c in range(len(n_inst)) if owner[c] == rank and n_inst[c] > 0]
+    if args.only:
+        mine = [c for c in mine if str(c + 1) in args.only.split(",")]
     T = templates()
     tot = {"V": 0, "E": 0, "S": 0, "flubbles": 0, "records": 0, "ms": 0.0, "gen_s": 0.0, "ingest_s": 0.0}
     per_comp, wins = [], []
@@ -144,7 +148,9 @@ def main():
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record(stream)
                 for _ in range(args.steps):
-                    sess.hot_path([prefix])
+                    parts = sess.hot_path([prefix])
+                    if args.verbose:
+                        print(f"[rank {rank}] component {c + 1}: upload / decompose / index / call = {[round(x, 2) for x in parts]} ms, host waits so far {pv.host_syncs}, launches {pv.launches}", file=sys.stderr, flush=True)
                 e1.record(stream)
                 torch.cuda.synchronize()
                 ms = e0.elapsed_time(e1) / args.steps
