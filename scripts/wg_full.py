@@ -101,6 +101,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=1)
     ap.add_argument("--windows", type=int, default=2)
     ap.add_argument("--only", default="", help="comma-separated component numbers (diagnostics)")
+    ap.add_argument("--profile", action="store_true", help="one extra step per component with per-kernel CUDA-event timing (top kernels to stderr)")
     ap.add_argument("--verbose", action="store_true", help="per step: the phases' wall ms and the DFS round count")
     ap.add_argument("--emu", action="store_true", help="host rehearsal library (logic check in the GPU-less container)")
     args = ap.parse_args()
@@ -125,7 +126,8 @@ def main():
     if args.only:
         mine = [c for c in mine if str(c + 1) in args.only.split(",")]
     T = templates()
-    tot = {"V": 0, "E": 0, "S": 0, "flubbles": 0, "records": 0, "ms": 0.0, "gen_s": 0.0, "ingest_s": 0.0}
+    tot = {"V": 0, "E": 0, "S": 0, "flubbles": 0, "records": 0, "ms": 0.0, "gen_s": 0.0, "ingest_s": 0.0, "e2e_ms": 0.0, "h2d_bytes": 0, "packed_bytes": 0}
+    packed = []      # per owned component: its packed binary records in HBM (what this rank contributes to the final gather)
     per_comp, wins = [], []
     big = [c for c in mine if n_inst[c] >= 480]      # (chrM holds a dozen instances: no room for a window)
     smallest = min(big, key=lambda c: n_inst[c]) if big else None
@@ -154,6 +156,32 @@ def main():
                 e1.record(stream)
                 torch.cuda.synchronize()
                 ms = e0.elapsed_time(e1) / args.steps
+        if args.profile and not args.emu:
+            pv.set_profiling(True)
+            sess.hot_path([prefix])
+            prof = pv.profile()
+            pv.set_profiling(False)
+            tk = sum(k["ms"] for k in prof)
+            print(f"[rank {rank}] component {c + 1}: kernel sum {tk:.2f} ms, {sum(k['launches'] for k in prof)} launches", file=sys.stderr)
+            for k in sorted(prof, key=lambda k: -k["ms"])[:28]:
+                print(f"    {k['name']:<18} x{k['launches']:<4} {k['ms']:8.3f} ms {100 * k['ms'] / tk:5.1f}%  {k['bytes'] / (k['ms'] * 1e-3) / 1e9 if k['ms'] > 0 else 0:8.1f} GB/s", file=sys.stderr)
+        # end to end for this component: raw arrays host -> HBM inside the step (links first, walks behind decompose), decompose,
+        # index, call, the binary records packed into one stream in HBM (host wall clock around a synchronised step)
+        e2e = 0.0
+        if not args.emu:
+            with torch.cuda.stream(stream):
+                sess.hot_path([prefix], keep_resident=False)      # (warm: page-locks the host arrays once)
+                torch.cuda.synchronize()
+                reps = max(1, min(2, args.steps))
+                tw = time.perf_counter()
+                for _ in range(reps):
+                    sess.hot_path([prefix], keep_resident=False)
+                    need = sess.records_packed_bytes()
+                    buf = torch.empty(need, dtype=torch.uint8, device="cuda")
+                    sess.records_pack(buf.data_ptr(), need)
+                torch.cuda.synchronize()
+                e2e = (time.perf_counter() - tw) * 1e3 / reps
+                packed.append(buf)
         nrec = int(sess.lib.pvgpu_session_record_count(sess.h)); nfl = int(sess.lib.pvgpu_session_flubble_count(sess.h))
         st = sess.call_stats()
         assert st["hard_errors"] == 0 and nrec > 0
@@ -165,11 +193,31 @@ def main():
             del lines
         sess.close()
         per_comp.append({"component": c + 1, "segments": V, "links": E, "path_steps": S, "flubbles": nfl, "records": nrec, "ms_per_step": round(ms, 3)})
-        for k, v in (("V", V), ("E", E), ("S", S), ("flubbles", nfl), ("records", nrec), ("ms", ms), ("gen_s", t1 - t0), ("ingest_s", t2 - t1)):
+        for k, v in (("V", V), ("E", E), ("S", S), ("flubbles", nfl), ("records", nrec), ("ms", ms), ("gen_s", t1 - t0), ("ingest_s", t2 - t1), ("e2e_ms", e2e),
+                     ("h2d_bytes", 8 * E + 4 * S + 4 * V), ("packed_bytes", int(packed[-1].numel()) if packed else 0)):
             tot[k] += v
         del f
         print(f"[rank {rank}] component {c + 1}: V={V} E={E} S={S} {ms:.1f} ms/step, {nrec} records (generated in {t1 - t0:.1f} s, ingest {t2 - t1:.1f} s)", file=sys.stderr, flush=True)
+    # the final gather: every rank's packed records to rank 0 over NCCL (sizes first), timed on the host around a synchronise
+    gather_ms = 0.0
+    if not args.emu:
+        mine_bytes = torch.cat(packed) if packed else torch.empty(0, dtype=torch.uint8, device="cuda")
+        del packed
+        if world > 1:
+            for rep in range(2):      # (first pass: NCCL sets its channels up)
+                dist.barrier(); torch.cuda.synchronize()
+                tw = time.perf_counter()
+                sizes = [torch.zeros(1, dtype=torch.int64, device="cuda") for _ in range(world)]
+                dist.all_gather(sizes, torch.tensor([mine_bytes.numel()], dtype=torch.int64, device="cuda"))
+                mx = max(int(x.item()) for x in sizes)
+                send = mine_bytes if mine_bytes.numel() == mx else torch.cat([mine_bytes, torch.empty(mx - mine_bytes.numel(), dtype=torch.uint8, device="cuda")])
+                recv = [torch.empty(mx, dtype=torch.uint8, device="cuda") for _ in range(world)] if rank == 0 else None
+                dist.gather(send, recv, dst=0)
+                torch.cuda.synchronize()
+                gather_ms = (time.perf_counter() - tw) * 1e3
+                del recv, send
     ok = all(x["bit_exact"] for x in wins)
+    tot["gather_ms"] = gather_ms
     res = {"rank": rank, "components": [p["component"] for p in per_comp], "per_component": per_comp, "windows": wins, **tot, "peak_device_GB": pv.peak_bytes / 1e9}
     if world > 1:
         allres = [None] * world
@@ -186,11 +234,15 @@ def main():
                "ms_per_step": job_ms, "edges_per_s": E / (job_ms * 1e-3), "records_per_s": rec / (job_ms * 1e-3), "steps": args.steps, "warmup": args.warmup,
                "rank_ms": [round(r["ms"], 2) for r in allres], "lpt_load_max_over_mean": max(load) / (sum(load) / len(load)),
                "rank_components": [r["components"] for r in allres], "peak_device_GB_max": max(r["peak_device_GB"] for r in allres),
+               "e2e": {"ms_per_step": max(r["e2e_ms"] for r in allres) + max(r["gather_ms"] for r in allres), "edges_per_s": E / (max(1e-9, max(r["e2e_ms"] for r in allres) + max(r["gather_ms"] for r in allres)) * 1e-3),
+                       "rank_hot_path_from_host_ms": [round(r["e2e_ms"], 2) for r in allres], "nccl_gather_ms": round(max(r["gather_ms"] for r in allres), 2),
+                       "h2d_bytes_per_step_all_ranks": sum(r["h2d_bytes"] for r in allres), "gathered_record_bytes": sum(r["packed_bytes"] for r in allres),
+                       "note": "per owned component: links + walks + segment lengths host -> HBM inside the step, decompose, index, call, binary records packed in HBM; then ONE gather of all ranks' record streams on rank 0 over NCCL.  Host wall clock, max over ranks"},
                "generation_s_max": max(r["gen_s"] for r in allres), "ingest_s_max": max(r["ingest_s"] for r in allres),
                "window_check": {"windows": allw, "bit_exact": all(x["bit_exact"] for x in allw), "records_compared": sum(x["records_compared"] for x in allw)},
                "per_component": sorted((p for r in allres for p in r["per_component"]), key=lambda p: p["component"])}
         os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-        with open(os.path.join(ROOT, "gpurun_out", f"wg_full_n{world}.json"), "w") as fh:
+        with open(os.path.join(ROOT, "gpurun_out", f"wg_full_n{world}{'_emu' if args.emu else ''}.json"), "w") as fh:
             json.dump(out, fh, indent=1)
         print(json.dumps({k: v for k, v in out.items() if k != "per_component"}))
     if world > 1:
