@@ -140,6 +140,7 @@ static void debug_outputs(const Config &c, Dev &d) {
 	if (c.hairpins) { size_t n = 0; char *p = pvgpu_session_hairpin_text(d.s, &n); std::string t = take(d, p, n); fwrite(t.data(), 1, t.size(), stderr); }
 	if (!c.structure_export.empty()) {
 		size_t n = 0; char *p = pvgpu_session_flubble_debug_frames(d.s, &n); std::string t = take(d, p, n);
+		if (t.empty()) return;      // (no component reached find_flubbles: the reference never opens the file)
 		std::ofstream out(sidecar_path(c), std::ios::app | std::ios::binary);
 		if (!out.is_open()) throw Fail{"could not open flubble debug sidecar: " + sidecar_path(c)};
 		out << t;

@@ -38,4 +38,5 @@ def test_emu_export_vs_reference(emu_lib, tmp_path):
     assert nb > 60 and ne > 1500
     nb, ne = ec.check_wild_vs_reference(cli, str(tmp_path), range(500, 506), V=600)
     assert ne > 1500
+    ec.check_degenerate_vs_reference(cli, str(tmp_path))
     ec.check_families_vs_reference(cli, str(tmp_path))

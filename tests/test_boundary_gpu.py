@@ -30,4 +30,5 @@ def test_gpu_export_vs_reference(gpu, tmp_path):
     assert nb > 15 and ne > 400
     nb, ne = ec.check_wild_vs_reference(cli, str(tmp_path), range(500, 504), V=3000)
     assert ne > 4000
+    ec.check_degenerate_vs_reference(cli, str(tmp_path))
     ec.check_families_vs_reference(cli, str(tmp_path))
