@@ -49,6 +49,8 @@ def parse_args():
     ap.add_argument("--no-gfa-leg", action="store_true", help="skip the GFA text -> HBM leg (device parser) reported under gfa_text")
     ap.add_argument("--profile-steps", type=int, default=2)
     ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling leg (whole-genome-shaped graph sharded over the ranks)")
+    ap.add_argument("--no-wg-full", action="store_true", help="skip the whole-genome leg at cfg4's stated size (scripts/wg_full.py: ~100 M segments, 90 paths per component; about a minute at N = 1)")
+    ap.add_argument("--wg-full-instances", type=int, default=2_100_000, help="template instances of the full-size whole-genome graph (2.1 M = 100.4 M segments / 142 M links / 2.6 G path steps)")
     ap.add_argument("--wg-instances", type=int, default=300_000, help="template instances of the whole-genome-shaped graph (300 k = 14.3 M segments / 20.2 M links)")
     ap.add_argument("--wg-paths", type=int, default=24, help="haplotype paths per component of that graph")
     return ap.parse_args()
@@ -490,6 +492,24 @@ def run_native(args):
             strong = run_strong(args, pv, stream, rank, world, torch, dist)
         except Exception as ex:      # reported, never fatal for the headline line
             strong = {"error": str(ex)[:300]}
+    # cfg4 at its stated size, one graph per component (scripts/wg_full.py): every rank generates and ingests only the components
+    # the LPT rule gives it; device-timed step = max over ranks of the sum over its components; e2e = the same from host arrays +
+    # one NCCL gather of the packed records.  (The byte-for-byte windows against the reference are that script's own job: bench.py
+    # may run the oracle only as the CPU baseline.)
+    whole = None
+    if not args.no_wg_full:
+        if args.no_strong:
+            sess.close()
+        try:
+            import types
+            sys.path.insert(0, os.path.join(ROOT, "scripts"))
+            import wg_full
+            wa = types.SimpleNamespace(instances=args.wg_full_instances, paths=90, steps=2, warmup=3, windows=0, only="", profile=False, verbose=False, emu=False)
+            whole = wg_full.run_full(wa, pv, stream, rank, world, torch, dist)
+            if whole:
+                whole.pop("window_check", None)
+        except Exception as ex:      # reported, never fatal for the headline line
+            whole = {"error": str(ex)[:300]}
     t_dev = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
     cnt = torch.tensor([n_rec, n_fl], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -554,7 +574,7 @@ def run_native(args):
                         "ms_per_step": e2e_ms_max / e2e_steps, "steps": e2e_steps,
                         "vcf_text": {"bytes": text_bytes, "ms": text_s * 1e3, "note": "record lines written by the device text kernels (X_len, X_write), D2H into a page-locked buffer, write(2) to /dev/null; wall time of one pvgpu_session_vcf_write call, not inside e2e (SURVEY.md 8f2)"}},
                 "gfa_text": gfa_leg, "gpu_launches": int(launches), "host_syncs_per_step": host_syncs / args.steps, "wall_s_timed_region": wall,
-                "clocks": clk, "roofline": roofline, "cpu_baseline": cpu, "strong_scaling": strong, "peak_device_bytes": pv.peak_bytes}
+                "clocks": clk, "roofline": roofline, "cpu_baseline": cpu, "strong_scaling": strong, "whole_genome": whole, "peak_device_bytes": pv.peak_bytes}
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

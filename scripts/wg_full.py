@@ -106,8 +106,8 @@ def main():
     ap.add_argument("--emu", action="store_true", help="host rehearsal library (logic check in the GPU-less container)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
-    from povu_b200 import api, synth
-    torch = dist = None
+    from povu_b200 import api
+    torch = dist = stream = None
     if not args.emu:
         import torch
         import torch.distributed as dist
@@ -118,6 +118,21 @@ def main():
         pv = api.Povu(device=local, stream=stream.cuda_stream)
     else:
         pv = api.Povu(lib_path=os.path.join(ROOT, "tests", "emu", "libpovu_emu.so"))
+    out = run_full(args, pv, stream, rank, world, torch, dist)
+    if rank == 0:
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        with open(os.path.join(ROOT, "gpurun_out", f"wg_full_n{world}{'_emu' if args.emu else ''}.json"), "w") as fh:
+            json.dump(out, fh, indent=1)
+        print(json.dumps({k: v for k, v in out.items() if k != "per_component"}))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    assert out is None or out["window_check"]["bit_exact"], "a window differs from the reference"
+
+
+def run_full(args, pv, stream, rank, world, torch, dist):
+    """args: instances, paths, steps, warmup, windows, only, profile, verbose, emu.  Returns the result dict on rank 0 (None elsewhere)."""
+    from povu_b200 import api, synth
     w = np.asarray(bench.GRCH38, dtype=np.float64)
     cuts = np.round(np.cumsum(w) / w.sum() * args.instances).astype(np.int64); cuts[-1] = args.instances
     n_inst = np.diff(np.concatenate([[0], cuts]))
@@ -184,7 +199,7 @@ def main():
                 packed.append(buf)
         nrec = int(sess.lib.pvgpu_session_record_count(sess.h)); nfl = int(sess.lib.pvgpu_session_flubble_count(sess.h))
         st = sess.call_stats()
-        assert st["hard_errors"] == 0 and nrec > 0
+        assert st["hard_errors"] == 0 and (nrec > 0 or n_inst[c] < 8)
         if check:
             lines, _ = sess.record_lines()
             wins = check_windows(f, lines, prefix, args.windows)
@@ -216,7 +231,6 @@ def main():
                 torch.cuda.synchronize()
                 gather_ms = (time.perf_counter() - tw) * 1e3
                 del recv, send
-    ok = all(x["bit_exact"] for x in wins)
     tot["gather_ms"] = gather_ms
     res = {"rank": rank, "components": [p["component"] for p in per_comp], "per_component": per_comp, "windows": wins, **tot, "peak_device_GB": pv.peak_bytes / 1e9}
     if world > 1:
@@ -224,7 +238,9 @@ def main():
         dist.all_gather_object(allres, res)
     else:
         allres = [res]
-    if rank == 0:
+    if rank != 0:
+        return None
+    if True:
         job_ms = max(r["ms"] for r in allres)
         E = sum(r["E"] for r in allres); V = sum(r["V"] for r in allres); S = sum(r["S"] for r in allres)
         rec = sum(r["records"] for r in allres)
@@ -241,14 +257,7 @@ def main():
                "generation_s_max": max(r["gen_s"] for r in allres), "ingest_s_max": max(r["ingest_s"] for r in allres),
                "window_check": {"windows": allw, "bit_exact": all(x["bit_exact"] for x in allw), "records_compared": sum(x["records_compared"] for x in allw)},
                "per_component": sorted((p for r in allres for p in r["per_component"]), key=lambda p: p["component"])}
-        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-        with open(os.path.join(ROOT, "gpurun_out", f"wg_full_n{world}{'_emu' if args.emu else ''}.json"), "w") as fh:
-            json.dump(out, fh, indent=1)
-        print(json.dumps({k: v for k, v in out.items() if k != "per_component"}))
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
-    assert ok, "a window differs from the reference"
+        return out
 
 
 if __name__ == "__main__":

@@ -57,3 +57,19 @@ def test_gpu_cfg3_mix_with_inversions_windows(gpu):
     assert all(w["bit_exact"] for w in wins), [w for w in wins if not w["bit_exact"]]
     assert sum(w["tangled"] for w in wins) > 0 and sum(w["records_compared"] for w in wins) > 5_000
     assert sum("VARTYPE=SUBR" in l for l in lines) > 0
+
+
+def test_gpu_whole_genome_per_component_windows(gpu):
+    """cfg4's shape through scripts/wg_full.py (one graph per component, one session per owned component) at a tenth of the
+    stated size (10 M segments, 90 paths per component): every component yields records, and two windows of a mid-size component
+    are byte-identical to the compiled reference.  The stated size itself (100 M segments) runs with the same code:
+    profiles/r2_wg_full_*.json."""
+    call_checks.require_ref()
+    import types
+    import torch
+    import wg_full
+    a = types.SimpleNamespace(instances=210_000, paths=90, steps=1, warmup=1, windows=2, only="", profile=False, verbose=False, emu=False)
+    out = wg_full.run_full(a, gpu, torch.cuda.current_stream(), 0, 1, torch, None)
+    assert out["segments"] > 9_500_000 and len(out["per_component"]) == 25 and all(p["records"] > 0 for p in out["per_component"] if p["segments"] > 1000)
+    assert out["window_check"]["bit_exact"] and out["window_check"]["records_compared"] > 500, out["window_check"]
+    assert out["e2e"]["gathered_record_bytes"] > 0
