@@ -45,10 +45,11 @@ struct DecompOut {
 	u32 dfs_rounds = 0;
 	u32 arc_rounds = 0;      // rounds of the fired-arc fixpoint (0 = every component laminar; > 64 = the sequential replay ran)
 	u32 collisions = 0;
+	u32 faithful_classes = 0;   // > 0: the classes were re-derived the reference's way (vertices with >= 3 children reaching above them; pv_refnum.cuh)
 	void reset() {   // keeps the (page-locked) capacity of the big arrays
 		comp.clear(); a_v.clear(); z_v.clear(); a_fwd.clear(); z_fwd.clear(); parent.clear(); depth.clear(); fl_base.clear();
 		comp_root.clear(); comp_nv.clear(); comp_nfl.clear(); comp_has_tips.clear(); comp_nonlaminar.clear();
-		stack_v.clear(); stack_class.clear(); stack_fwd.clear(); stack_next.clear(); dfs_rounds = 0; arc_rounds = 0; collisions = 0;
+		stack_v.clear(); stack_class.clear(); stack_fwd.clear(); stack_next.clear(); dfs_rounds = 0; arc_rounds = 0; collisions = 0; faithful_classes = 0;
 	}
 };
 
@@ -262,8 +263,9 @@ __global__ void __launch_bounds__(UF_THREADS) uf_local_kernel(const u32 *adjOff,
 // prv[i] = previous stack position of i's class or NONE.  fire[i]: 1 = the arc (prv[i], i) fires, 2 = dead or no arc.
 // Returns the number of fixpoint rounds after the laminarity pass (0 = no two arcs cross), -1 if undecided arcs remain after
 // 64 rounds (fire[] then holds 0 for them).  segComp / lamBad (optional): component of every position -> "has crossing arcs".
-// extra_src / extra_dst (optional): one more device word read with the first host wait (the caller's flubble count).
-inline int fired_arcs(Ctx &c, const u32 *prv_, u32 nS, u32 *fire_, const u32 *segComp_, u32 *lamBad_, const u32 *extra_src, u32 *extra_dst) {
+// extra_src / extra_dst, extra2_src / extra2_dst (optional): more device words read with the first host wait (the caller's
+// flubble count, its "reference class naming may differ" flag).
+inline int fired_arcs(Ctx &c, const u32 *prv_, u32 nS, u32 *fire_, const u32 *segComp_, u32 *lamBad_, const u32 *extra_src, u32 *extra_dst, const u32 *extra2_src = nullptr, u32 *extra2_dst = nullptr) {
 	Buf<u32> arcA(c, nS ? nS : 1), fl(c, 1);
 	u32 *arcA_ = arcA.p, *fl_ = fl.p;
 	fl.zero();
@@ -281,7 +283,7 @@ inline int fired_arcs(Ctx &c, const u32 *prv_, u32 nS, u32 *fire_, const u32 *se
 		});
 	}
 	u32 undecided = 0;
-	{ MultiRead mr(c); if (extra_src) mr.add(extra_dst, extra_src, 4); mr.add(&undecided, fl.p, 4); mr.wait(); }
+	{ MultiRead mr(c); if (extra_src) mr.add(extra_dst, extra_src, 4); if (extra2_src) mr.add(extra2_dst, extra2_src, 4); mr.add(&undecided, fl.p, 4); mr.wait(); }
 	int rounds = 0;
 	if (undecided) {
 		Buf<u32> arcF(c, nS);
@@ -802,6 +804,13 @@ inline void decompose_device(Ctx &c, u32 V, u64 E, const u32 *ep1, const u32 *ep
 	// exact verification of every merged pair (bracket sets equal <=> same count, ancestor chain, and no
 	// bracket from subtree(v1) \ subtree(v2) leaves subtree(v1))
 	c.memset0(flag.p, 16);
+	// the reference names classes by (top bracket, list size); with >= 3 children reaching above a vertex its capping edge can be
+	// too short and that naming merges classes that cycle equivalence keeps apart (pv_refnum.cuh: refnum_quirk_flag).  The count
+	// travels with the first host wait of D6; only then are the classes re-derived the reference's way.
+	RefNumIn rn{V, P, N, nComp, nS, M, adjOff_, adjNbr_, treeSlot_, parent_, entrySide_, pre_, sz_, depth_, pre2node_, compIdxOfRoot_, gcomp_, cNodeBase_, cNv_, cHasTips_, cSegBase_,
+		    bridge_, bsum_, PC_, rmq2.view(), minT_, stV_, nullptr};
+	static const bool force_faithful = getenv("POVU_B200_FAITHFUL_CLASSES") != nullptr, never_faithful = getenv("POVU_B200_XOR_CLASSES") != nullptr;
+	if (!never_faithful) refnum_quirk_flag(c, rn, flag.p + 3);
 	{
 		RmqView rv = rmq2.view();
 		parallel_for<K_verify>(c, nS, PV_LAMBDA(size_t i) {
@@ -836,8 +845,31 @@ inline void decompose_device(Ctx &c, u32 V, u64 E, const u32 *ep1, const u32 *ep
 	u32 *open_ = open.p, *flIdx_ = flIdx.p; MP *fn_ = fn.p, *fnS_ = fnS.p;
 	parallel_for<K_fn>(c, (size_t)nS + 1, PV_LAMBDA(size_t i) { open_[i] = i < nS && nxt_[i] > (u32)i + 1 ? 1u : 0u; });
 	exclusive_scan(c, open.p, flIdx.p, (size_t)nS + 1, OpAddU32(), 0u);
-	u32 nFl = 0;
-	const int arcRounds = fired_arcs(c, prv.p, nS, fire.p, segComp.p, lamBad.p, flIdx.p + nS, &nFl);
+	u32 nFl = 0, quirk = 0;
+	int arcRounds = fired_arcs(c, prv.p, nS, fire.p, segComp.p, lamBad.p, flIdx.p + nS, &nFl, flag.p + 3, &quirk);
+	out.faithful_classes = 0;
+	if ((quirk || force_faithful) && !never_faithful) {
+		// classes the reference's way (capping edges, top bracket + list size: pv_refnum.cuh), then next / previous seen by one stable
+		// sort of the stack positions on the class label; everything after this point is unchanged
+		Buf<u32> sc;
+		refnum_device(c, rn, nullptr, &sc);
+		Buf<u32> ckey(c, nS), cord(c, nS);
+		{ u32 *k_ = ckey.p, *o_ = cord.p; const u32 *sc_ = sc.p; parallel_for<K_word>(c, nS, PV_LAMBDA(size_t i) { k_[i] = sc_[i]; o_[i] = (u32)i; }); }
+		radix_sort_pairs(c, ckey, cord, nS, bits_for((u64)N + 1));
+		{
+			const u32 *k_ = ckey.p, *o_ = cord.p;
+			parallel_for<K_seen>(c, nS, PV_LAMBDA(size_t i) {
+				const u32 me = o_[i], k = k_[i];
+				nxt_[me] = (i + 1 < nS && k_[i + 1] == k) ? o_[i + 1] : me;
+				prv_[me] = (i > 0 && k_[i - 1] == k) ? o_[i - 1] : NONE;
+			});
+		}
+		lamBad.zero();
+		parallel_for<K_fn>(c, (size_t)nS + 1, PV_LAMBDA(size_t i) { open_[i] = i < nS && nxt_[i] > (u32)i + 1 ? 1u : 0u; });
+		exclusive_scan(c, open.p, flIdx.p, (size_t)nS + 1, OpAddU32(), 0u);
+		arcRounds = fired_arcs(c, prv.p, nS, fire.p, segComp.p, lamBad.p, flIdx.p + nS, &nFl);
+		out.faithful_classes = quirk ? quirk : 1;
+	}
 	out.arc_rounds = arcRounds < 0 ? 65u : (u32)arcRounds;
 	const bool replay = arcRounds < 0;      // the sequential fallback
 	parallel_for<K_fn>(c, nS, PV_LAMBDA(size_t i) {
@@ -952,11 +984,7 @@ inline void decompose_device(Ctx &c, u32 V, u64 E, const u32 *ep1, const u32 *ep
 		for (u32 i = 0; i < nS; i++) out.stack_fwd[i] = es[out.stack_v[i]] == 0;
 		out.stack_next = nxt.to_host();
 	}
-	if (opt.refnum) {
-		RefNumIn rn{V, P, N, nComp, nS, M, adjOff_, adjNbr_, treeSlot_, parent_, entrySide_, pre_, sz_, depth_, pre2node_, compIdxOfRoot_, gcomp_, cNodeBase_, cNv_, cHasTips_, cSegBase_,
-			    bridge_, bsum_, PC_, rmq2.view(), minT_, stV_, segComp_};
-		refnum_device(c, rn, *opt.refnum);
-	}
+	if (opt.refnum) refnum_device(c, rn, opt.refnum);
 	tr.mark("results d2h");   // (pack.to_host() above waited for the stream: every copy queued on it before has landed)
 	if (sm.on && sm.n == 9) {
 		StageCost &sc = StageCost::inst();

@@ -82,9 +82,37 @@ struct RefNumOut {
 	void reset() { edge_idx.clear(); edge_id.clear(); class_id.clear(); hp_comp.clear(); hp_b1.clear(); hp_b2.clear(); errors = 0; valid = false; }
 };
 
-inline void refnum_device(Ctx &c, const RefNumIn &t, RefNumOut &out) {
+// Can the reference's class naming differ from true cycle equivalence on this tree?  Its capping back edge goes to hi_2 = hi of
+// the FIRST child (ascending index) that is not hi_child and reaches above v (flubbles.cpp:564-573) instead of the second-lowest
+// hi; with three or more such children that bracket can end below brackets of a sibling it should cover, and two tree edges with
+// different bracket sets then share (top bracket, list size) -- the reference gives them one class and reports a flubble that
+// cycle equivalence does not have.  flag[0] += 1 for every vertex with >= 3 children that reach above it.
+PV_KERNEL(R_quirk, 24);
+inline void refnum_quirk_flag(Ctx &c, const RefNumIn &t, u32 *flag) {
+	const u32 P = t.P, N = t.N;
+	const u32 *adjOff_ = t.adjOff, *treeSlot_ = t.treeSlot, *entrySide_ = t.entrySide, *pre_ = t.pre, *sz_ = t.sz, *pre2node_ = t.pre2node;
+	const RmqView hv = t.hiAll;
+	parallel_for<R_quirk>(c, N, PV_LAMBDA(size_t gg) {
+		const u32 g = (u32)gg, node = pre2node_[g];
+		if (node >= P || sz_[node] < 6) return;      // three children need three vertex pairs below
+		const bool isEntry = (node & 1u) == entrySide_[node >> 1];
+		u32 nGray = 0;
+		for (u32 s = adjOff_[node], e = adjOff_[node + 1]; s < e; s++) if (treeSlot_[s] != NONE) nGray++;
+		if (nGray + (isEntry ? 1u : 0u) < 3) return;
+		auto above = [&](u32 ch) -> u32 { u32 gc = pre_[ch]; return hv.query(gc, gc + sz_[ch] - 1) < g ? 1u : 0u; };
+		u32 n = isEntry ? above(node ^ 1u) : 0u;
+		for (u32 s = adjOff_[node], e = adjOff_[node + 1]; s < e; s++) { u32 ch = treeSlot_[s]; if (ch != NONE) n += above(ch); }
+		if (n >= 3) atomic_add(flag, 1u);
+	});
+}
+
+// out (optional): the host-side numbering + hairpin boundaries of the two debug surfaces.  stackClass (optional): receives, on the
+// device, the reference's class of every class-stack position as a label that is unique per class inside the whole forest (what
+// decompose groups by when the quirk above can bite).
+inline void refnum_device(Ctx &c, const RefNumIn &t, RefNumOut *outp, Buf<u32> *stackClass = nullptr) {
+	RefNumOut scratch; RefNumOut &out = outp ? *outp : scratch;
 	out.reset();
-	const u32 P = t.P, N = t.N, nComp = t.nComp, nS = t.nS; const u64 M = t.M;
+	const u32 P = t.P, N = t.N, nS = t.nS; const u64 M = t.M;
 	const u32 *adjOff_ = t.adjOff, *adjNbr_ = t.adjNbr, *treeSlot_ = t.treeSlot, *parent_ = t.parent, *entrySide_ = t.entrySide, *pre_ = t.pre, *sz_ = t.sz, *depth_ = t.depth, *pre2node_ = t.pre2node;
 	const u32 *compIdxOfRoot_ = t.compIdxOfRoot, *gcomp_ = t.gcomp, *cNodeBase_ = t.cNodeBase, *cNv_ = t.cNv, *cHasTips_ = t.cHasTips;
 	const u32 *bridge_ = t.bridge, *bsum_ = t.bsum, *minT_ = t.minT; const i32 *PC_ = t.PC;
@@ -169,7 +197,11 @@ inline void refnum_device(Ctx &c, const RefNumIn &t, RefNumOut &out) {
 	});
 	exclusive_scan(c, cntPost.p, bbase.p, (size_t)N + 1, OpAddU32(), 0u);
 	const u32 NB = bbase.read(N);
-	if (NB == 0) { out.valid = true; out.edge_idx.assign(nS, 0); out.edge_id.assign(nS, 0); out.class_id.assign(nS, 0); return; }
+	if (NB == 0) {
+		out.valid = true; out.edge_idx.assign(nS, 0); out.edge_id.assign(nS, 0); out.class_id.assign(nS, 0);
+		if (stackClass) { *stackClass = Buf<u32>(c, nS ? nS : 1); u32 *sc = stackClass->p; parallel_for<R_out>(c, nS, PV_LAMBDA(size_t i) { sc[i] = (u32)i; }); }
+		return;
+	}
 	Buf<u32> bT(c, NB), bKind(c, NB);
 	u32 *bT_ = bT.p, *bKind_ = bKind.p;
 	parallel_for<R_fill>(c, N, PV_LAMBDA(size_t gg) {
@@ -236,9 +268,18 @@ inline void refnum_device(Ctx &c, const RefNumIn &t, RefNumOut &out) {
 	});
 	parallel_for<R_class>(c, N, PV_LAMBDA(size_t i) { if (skey_[i] < NB) classOf_[sval_[i]] = classNew_[sval_[leadS_[i] - 1]]; });
 
+	const u32 *stV_ = t.stV;
+	if (stackClass) {      // class label = position of the class's opening vertex in the sorted order (unique across components)
+		*stackClass = Buf<u32>(c, nS ? nS : 1);
+		Buf<u32> labOf(c, N);
+		u32 *labOf_ = labOf.p, *sc = stackClass->p;
+		parallel_for<R_class>(c, N, PV_LAMBDA(size_t i) { if (skey_[i] < NB) labOf_[sval_[i]] = leadS_[i]; });
+		parallel_for<R_out>(c, nS, PV_LAMBDA(size_t i) { const u32 v = stV_[i], cx = (2 * v + entrySide_[v]) ^ 1u; sc[i] = labOf_[pre_[cx]]; });
+	}
+	if (!outp) { if (err.read(0)) throw std::runtime_error("decompose: inconsistent bracket lists (internal error)"); return; }
 	// ---- per class-stack position: tree edge index, edge id, class id
 	Buf<u32> oIdx(c, nS ? nS : 1), oId(c, nS ? nS : 1), oCls(c, nS ? nS : 1);
-	u32 *oIdx_ = oIdx.p, *oId_ = oId.p, *oCls_ = oCls.p; const u32 *stV_ = t.stV;
+	u32 *oIdx_ = oIdx.p, *oId_ = oId.p, *oCls_ = oCls.p;
 	parallel_for<R_out>(c, nS, PV_LAMBDA(size_t i) {
 		const u32 v = stV_[i], cx = (2 * v + entrySide_[v]) ^ 1u, gc = pre_[cx], k = gK_[gc];
 		const u32 base = cNodeBase_[k];

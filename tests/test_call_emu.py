@@ -65,3 +65,39 @@ def test_emu_call_matfill_lanes(emu_lib, name, tmp_path, monkeypatch):
     """depth matrix: 32 logical lanes per column stride over the vertex's step list (the many-paths configuration)"""
     monkeypatch.setenv("POVU_B200_MATFILL_LANES", "32")
     cc.check_golden(_ctx(emu_lib, 2), name, str(tmp_path))
+
+
+def test_emu_perturbed_graphs_cli(emu_lib, tmp_path):
+    """nested bubbles + random chords + random-walk haplotypes through the CLI, whole VCF byte for byte vs the compiled reference"""
+    import os
+    n, nrec, ntang, nsubr = cc.check_perturbed_cli(os.path.join(os.path.dirname(emu_lib), "povu_emu"), str(tmp_path), range(300))
+    assert n > 250 and nrec > 3000 and ntang > 300 and nsubr > 300, (n, nrec, ntang, nsubr)
+
+
+def test_emu_reference_class_naming(emu_lib, tmp_path):
+    """Where a DFS-tree vertex has three or more children reaching above it, the reference's (top bracket, list size) class names
+    merge classes that cycle equivalence keeps apart (its capping edge is too short: flubbles.cpp:564-573) and it reports flubbles
+    the XOR labels do not: seeds 860 / 1058 / 2074 of the perturbed family are such graphs.  decompose detects the situation and
+    re-derives the classes the reference's way (pv_refnum.cuh).  Forced on for every graph, that path must give the same results
+    as the label path wherever the two agree: fixtures, LPA, synthetic families, 200 perturbed graphs."""
+    import os
+    import subprocess
+    cli = os.path.join(os.path.dirname(emu_lib), "povu_emu")
+    n, nrec, _, _ = cc.check_perturbed_cli(cli, str(tmp_path), [860, 1058, 2074])
+    assert n == 3 and nrec > 40
+    # the label path alone misses a flubble on those three
+    for seed in (860, 1058, 2074):
+        try:
+            cc.check_perturbed_cli(cli, str(tmp_path), [seed], env={"POVU_B200_XOR_CLASSES": "1"})
+            raise RuntimeError(f"seed {seed}: the label path alone was expected to differ from the reference")
+        except AssertionError:
+            pass
+    force = {"POVU_B200_FAITHFUL_CLASSES": "1"}
+    n, nrec, ntang, nsubr = cc.check_perturbed_cli(cli, str(tmp_path), range(200), env=force)
+    assert n > 170 and nrec > 2000
+    strip = lambda t: "".join(l for l in t.splitlines(True) if not l.startswith("##fileDate"))
+    for name in helpers.POSITIVE + ["LPA"] + helpers.SYNTHETIC:
+        prefix = {"hairpin_inversion_subr": "ref", "LPA": "chm13", "multi_comp": "S001#1#chr1"}.get(name, "S001" if name in helpers.SYNTHETIC else "HG1")
+        r = subprocess.run([cli, "gfa2vcf", "-i", helpers.fixture_path(name, str(tmp_path)), "-t", "1", "-P", prefix], capture_output=True, text=True, env=dict(os.environ, **force))
+        assert r.returncode == 0, (name, r.stderr[-300:])
+        assert strip(r.stdout) == open(os.path.join(helpers.GOLDEN, "expected", name + ".vcf")).read(), name

@@ -74,3 +74,27 @@ def test_gpu_call_many_path_kernels_families(gpu, tmp_path, monkeypatch):
     cc.run_all_synthetic(gpu, str(tmp_path), n_seeds=8)
     cc.run_tangled_vs_reference(gpu, str(tmp_path), n_seeds=10)
     cc.run_inversions_vs_reference(gpu, str(tmp_path), n_seeds=15)
+
+
+def test_gpu_perturbed_graphs_cli(gpu, tmp_path):
+    import os
+    n, nrec, ntang, nsubr = cc.check_perturbed_cli(os.path.join(cc.ROOT, "povu_b200", "bin", "povu"), str(tmp_path), range(300, 380))
+    assert n > 60 and nrec > 600, (n, nrec, ntang, nsubr)
+
+
+def test_gpu_reference_class_naming(gpu, tmp_path):
+    """see test_emu_reference_class_naming: graphs where the reference's class names differ from cycle equivalence, and the
+    re-derived classes forced on for LPA and 80 perturbed graphs"""
+    import os
+    import subprocess
+    cli = os.path.join(cc.ROOT, "povu_b200", "bin", "povu")
+    n, nrec, _, _ = cc.check_perturbed_cli(cli, str(tmp_path), [860, 1058, 2074])
+    assert n == 3 and nrec > 40
+    force = {"POVU_B200_FAITHFUL_CLASSES": "1"}
+    n, nrec, _, _ = cc.check_perturbed_cli(cli, str(tmp_path), range(80), env=force)
+    assert n > 60 and nrec > 600
+    strip = lambda t: "".join(l for l in t.splitlines(True) if not l.startswith("##fileDate"))
+    for name, prefix in (("LPA", "chm13"), ("nested_s1", "S001"), ("hairpin_inversion_subr", "ref")):
+        r = subprocess.run([cli, "gfa2vcf", "-i", helpers.fixture_path(name, str(tmp_path)), "-t", "1", "-P", prefix], capture_output=True, text=True, env=dict(os.environ, **force))
+        assert r.returncode == 0, (name, r.stderr[-300:])
+        assert strip(r.stdout) == open(os.path.join(helpers.GOLDEN, "expected", name + ".vcf")).read(), name
