@@ -160,7 +160,7 @@ inline void graph_build(Ctx &c, u32 V, u64 E, const u32 *ep1, const u32 *ep2, u3
 	g.steps = Buf<u32>(c, S ? S : 1); c.d2d(g.steps.p, d_steps, (size_t)S * 4);
 	g.segLen = Buf<u32>(c, V ? V : 1); c.d2d(g.segLen.p, d_segLen, (size_t)V * 4);
 	g.loci = Buf<u32>(c, S ? S : 1);
-	g.vsOff = Buf<u32>(c, (size_t)V + 1); g.vsStep = Buf<u32>(c, S ? S : 1); g.vsHap = Buf<u32>(c, S ? S : 1);
+	g.vsOff = Buf<u32>(c, (size_t)V + 1); g.vsHap = Buf<u32>(c, S ? S : 1);
 	const u32 *steps_ = g.steps.p, *stepOff_ = g.stepOff.p, *segLen_ = g.segLen.p;
 	{
 		// loci[k] = 1-based start coordinate of step k (liteseq ref_walk::loci).  One u32 scan over all
@@ -174,11 +174,28 @@ inline void graph_build(Ctx &c, u32 V, u64 E, const u32 *ep1, const u32 *ep2, u3
 			loci_[s] = 1u + pre_[s] - pre_[stepOff_[h]];
 		});
 	}
-	// vertex -> steps index = the step indices grouped by vertex, ascending inside a vertex (group_indices, pv_prims.cuh)
+	// vertex -> steps index = the step indices grouped by vertex, ascending inside a vertex (group_indices, pv_prims.cuh).
+	// DENSE walks (hundreds of haplotypes: every vertex owns a long list) skip the small-group machinery altogether: one stable
+	// radix sort of (packed step, step index) on the VERTEX bits of the key -- the strand bit rides along below them, so the
+	// (path, strand) word of every list entry is later formed from the sorted key instead of a random read of steps[].
 	u32 vs_small = 48;
 	if (const char *e = getenv("POVU_B200_VS_SMALL")) vs_small = (u32)strtoul(e, nullptr, 10);   // tests: force the hub path
+	u64 dense_min = 64;
+	if (const char *e = getenv("POVU_B200_DENSE_INDEX")) dense_min = strtoull(e, nullptr, 10);       // tests: 0 forces the dense path
+	const bool dense = S > 0 && (u64)S >= dense_min * (u64)V;
 	const StepVertex SV{steps_};
-	group_begin(c, SV, NoOrd(), S, V, g.vsOff.p, g.vsStep.p, vs_small, gsVs, &mr);
+	Buf<u32> dKey;      // dense: the sorted packed steps
+	if (!dense) { g.vsStep = Buf<u32>(c, S ? S : 1); group_begin(c, SV, NoOrd(), S, V, g.vsOff.p, g.vsStep.p, vs_small, gsVs, &mr); }
+	else {
+		Buf<u32> cnt(c, (size_t)V + 1), vv(c, S);
+		cnt.zero();
+		dKey = Buf<u32>(c, S);
+		u32 *cnt_ = cnt.p, *kk_ = dKey.p, *vv_ = vv.p;
+		parallel_for<K_grp_count>(c, S, PV_LAMBDA(size_t s) { const u32 x = steps_[s]; atomic_add(cnt_ + (x >> 1), 1u); kk_[s] = x; vv_[s] = (u32)s; });
+		exclusive_scan(c, cnt.p, g.vsOff.p, (size_t)V + 1, OpAddU32(), 0u);
+		radix_sort_pairs(c, dKey, vv, S, bits_for(V), 1);
+		g.vsStep = std::move(vv);
+	}
 	// ---- weakly connected components -> the component label of every path
 	if (labels && labels->p && labels->n >= V && V) g.vcomp = std::move(*labels);
 	else { g.vcomp = Buf<u32>(c, V ? V : 1); component_labels(c, V, E, ep1, ep2, g.vcomp.p); }
@@ -204,12 +221,13 @@ inline void graph_build(Ctx &c, u32 V, u64 E, const u32 *ep1, const u32 *ep2, u3
 		});
 	}
 	tr.mark("adjacency");
-	group_finish(c, SV, NoOrd(), gsVs);
+	if (!dense) group_finish(c, SV, NoOrd(), gsVs);
 	{
 		// (path << 1) | strand next to every entry: the depth matrix needs the strand per visit, and reading it here (one pass, the
 		// step index at hand) is cheaper than a random access per matrix cell later
-		u32 *vsStep_ = g.vsStep.p, *vsHap_ = g.vsHap.p;
-		parallel_for<C_vs_hap>(c, S, PV_LAMBDA(size_t i) { u32 st = vsStep_[i]; vsHap_[i] = ((ub_u32(stepOff_, 0, H + 1, st) - 1) << 1) | (steps_[st] & 1u); });
+		u32 *vsStep_ = g.vsStep.p, *vsHap_ = g.vsHap.p; const u32 *dk = dKey.p;
+		if (dense) parallel_for<C_vs_hap>(c, S, PV_LAMBDA(size_t i) { vsHap_[i] = ((ub_u32(stepOff_, 0, H + 1, vsStep_[i]) - 1) << 1) | (dk[i] & 1u); });
+		else parallel_for<C_vs_hap>(c, S, PV_LAMBDA(size_t i) { u32 st = vsStep_[i]; vsHap_[i] = ((ub_u32(stepOff_, 0, H + 1, st) - 1) << 1) | (steps_[st] & 1u); });
 	}
 	tr.mark("loci + vertex->steps");
 	{

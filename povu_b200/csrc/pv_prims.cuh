@@ -385,7 +385,7 @@ template <class T, class Op> inline void inclusive_scan(Ctx &c, const T *in, T *
 static const int RS_THREADS = 256;
 static const int RS_WARPS = RS_THREADS / 32;
 
-__global__ void __launch_bounds__(RS_THREADS) rs_hist_all_kernel(const u32 *keys, size_t n, u32 *ghist, int passes, int vec) {
+__global__ void __launch_bounds__(RS_THREADS) rs_hist_all_kernel(const u32 *keys, size_t n, u32 *ghist, int passes, int vec, int begin) {
 	__shared__ u32 hist[4][256];
 	for (int i = threadIdx.x; i < 4 * 256; i += RS_THREADS) (&hist[0][0])[i] = 0;
 	__syncthreads();
@@ -404,7 +404,7 @@ __global__ void __launch_bounds__(RS_THREADS) rs_hist_all_kernel(const u32 *keys
 			for (int j = 0; j < 16; j++) k[j] = j < m ? keys[base + j] : 0u;
 		}
 		for (int p = 0; p < passes; p++) {
-			int sh = 8 * p;
+			int sh = begin + 8 * p;
 			u32 cur = (k[0] >> sh) & 255u, cnt = 1;
 #pragma unroll
 			for (int j = 1; j < 16; j++) {
@@ -554,13 +554,14 @@ __global__ void __launch_bounds__(RS_THREADS, 4) rs_onesweep_kernel(const u32 *k
 }
 #endif
 
-// Sorts (keys, vals) by key bits [0, bits); on return keys/vals may have been SWAPPED with the internal double buffers
-// (the Buf objects always own the sorted data; raw pointers taken before the call are stale).
-inline void radix_sort_pairs(Ctx &c, Buf<u32> &keys, Buf<u32> &vals, size_t n, int bits) {
+// Sorts (keys, vals) by key bits [begin, begin + bits) -- the bits below `begin` ride along as payload; on return keys/vals may
+// have been SWAPPED with the internal double buffers (the Buf objects always own the sorted data; raw pointers taken before the
+// call are stale).
+inline void radix_sort_pairs(Ctx &c, Buf<u32> &keys, Buf<u32> &vals, size_t n, int bits, int begin = 0) {
 	if (n <= 1 || bits <= 0) return;
 #ifndef PV_EMU
 	if (n >= (1ull << 32)) throw std::runtime_error("radix sort: input too large");
-	if (bits > 32) bits = 32;
+	if (begin + bits > 32) bits = 32 - begin;
 	const int passes = (bits + 7) / 8;
 	Buf<u32> k2(c, keys.n), v2(c, vals.n);
 	Buf<u32> ghist(c, 4 * 256);
@@ -575,15 +576,15 @@ inline void radix_sort_pairs(Ctx &c, Buf<u32> &keys, Buf<u32> &vals, size_t n, i
 		size_t cap = (size_t)c.sm_count * 8;
 		if (blocks > cap) blocks = cap;
 		c.prof_begin("rs_hist", n, n * 4);
-		rs_hist_all_kernel<<<(unsigned)blocks, RS_THREADS, 0, c.stream>>>(keys.p, n, ghist.p, passes, (((uintptr_t)keys.p) & 15u) == 0 ? 1 : 0);
+		rs_hist_all_kernel<<<(unsigned)blocks, RS_THREADS, 0, c.stream>>>(keys.p, n, ghist.p, passes, (((uintptr_t)keys.p) & 15u) == 0 ? 1 : 0, begin);
 		c.prof_end();
 		c.launches++;
 	}
 	for (int p = 0; p < passes; p++) {
 		u32 epoch = c.next_epoch();
 		c.prof_begin("rs_onesweep", n, n * 16);
-		if (small) rs_onesweep_kernel<8><<<(unsigned)ntiles, RS_THREADS, 0, c.stream>>>(keys.p, vals.p, k2.p, v2.p, n, 8 * p, ghist.p + 256 * p, c.rs_status, c.lb_ticket + 1, epoch, (u32)ntiles);
-		else rs_onesweep_kernel<16><<<(unsigned)ntiles, RS_THREADS, 0, c.stream>>>(keys.p, vals.p, k2.p, v2.p, n, 8 * p, ghist.p + 256 * p, c.rs_status, c.lb_ticket + 1, epoch, (u32)ntiles);
+		if (small) rs_onesweep_kernel<8><<<(unsigned)ntiles, RS_THREADS, 0, c.stream>>>(keys.p, vals.p, k2.p, v2.p, n, begin + 8 * p, ghist.p + 256 * p, c.rs_status, c.lb_ticket + 1, epoch, (u32)ntiles);
+		else rs_onesweep_kernel<16><<<(unsigned)ntiles, RS_THREADS, 0, c.stream>>>(keys.p, vals.p, k2.p, v2.p, n, begin + 8 * p, ghist.p + 256 * p, c.rs_status, c.lb_ticket + 1, epoch, (u32)ntiles);
 		c.prof_end();
 		c.launches++;
 		PV_CUDA_CHECK(cudaGetLastError());
@@ -595,7 +596,7 @@ inline void radix_sort_pairs(Ctx &c, Buf<u32> &keys, Buf<u32> &vals, size_t n, i
 	std::iota(idx.begin(), idx.end(), 0u);
 	u32 mask = bits >= 32 ? 0xFFFFFFFFu : ((1u << bits) - 1u);
 	u32 *kp = keys.p, *vp = vals.p;
-	std::stable_sort(idx.begin(), idx.end(), [&](u32 a, u32 b) { return (kp[a] & mask) < (kp[b] & mask); });
+	std::stable_sort(idx.begin(), idx.end(), [&](u32 a, u32 b) { return ((kp[a] >> begin) & mask) < ((kp[b] >> begin) & mask); });
 	// like the device path with an odd number of passes: the result lives in fresh buffers, the old ones are poisoned
 	Buf<u32> k2(c, keys.n), v2(c, vals.n);
 	for (size_t i = 0; i < n; i++) { k2.p[i] = kp[idx[i]]; v2.p[i] = vp[idx[i]]; }
