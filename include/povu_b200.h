@@ -76,6 +76,10 @@ uint32_t pvgpu_flubbles_hash_collisions(const pvgpu_flubbles *f);
 /* rounds of the fired-arc fixpoint that decides which class re-encounters still find their previous occurrence on the reference's
  * stack (0 = every component laminar; more than 64 = the sequential replay ran instead) */
 uint32_t pvgpu_flubbles_arc_rounds(const pvgpu_flubbles *f);
+/* > 0: the tree has vertices with three or more children reaching above them, where the reference's (top bracket, list size) class
+ * names can differ from cycle equivalence (its capping edge, flubbles.cpp:564-573); the classes were then derived the reference's way
+ * (pv_refnum.cuh) instead of from the XOR labels.  The value is the number of such vertices. */
+uint32_t pvgpu_flubbles_faithful_classes(const pvgpu_flubbles *f);
 /* any pointer may be NULL.  a_v/z_v are vertex indices; a_fwd/z_fwd 1 = '>' 0 = '<'. */
 void pvgpu_flubbles_copy(const pvgpu_flubbles *f, uint32_t *comp, uint32_t *a_v, uint8_t *a_fwd, uint32_t *z_v,
 			 uint8_t *z_fwd, uint32_t *parent, uint32_t *depth);

@@ -65,6 +65,8 @@ def load_library(lib_path=None):
     lib.pvgpu_flubbles_hash_collisions.restype = u32
     lib.pvgpu_flubbles_arc_rounds.argtypes = [vp]
     lib.pvgpu_flubbles_arc_rounds.restype = u32
+    lib.pvgpu_flubbles_faithful_classes.argtypes = [vp]
+    lib.pvgpu_flubbles_faithful_classes.restype = u32
     lib.pvgpu_flubbles_copy.argtypes = [vp, P32, P32, P8, P32, P8, P32, P32]
     lib.pvgpu_flubbles_copy_components.argtypes = [vp, P32, P32, P32, P32, P32]
     lib.pvgpu_flubbles_stack_size.argtypes = [vp]
@@ -161,6 +163,7 @@ class Flubbles:
                                           _as_ptr(self.stack_fwd, C.c_uint32))
         self.dfs_rounds = lib.pvgpu_flubbles_dfs_rounds(h)
         self.arc_rounds = lib.pvgpu_flubbles_arc_rounds(h)
+        self.faithful_classes = lib.pvgpu_flubbles_faithful_classes(h)
         self.n = int(n)
 
     def labels(self, ids):

@@ -104,6 +104,7 @@ uint32_t pvgpu_flubbles_component_count(const pvgpu_flubbles *f) { return (uint3
 uint32_t pvgpu_flubbles_dfs_rounds(const pvgpu_flubbles *f) { return f->o.dfs_rounds; }
 uint32_t pvgpu_flubbles_hash_collisions(const pvgpu_flubbles *f) { return f->o.collisions; }
 uint32_t pvgpu_flubbles_arc_rounds(const pvgpu_flubbles *f) { return f->o.arc_rounds; }
+uint32_t pvgpu_flubbles_faithful_classes(const pvgpu_flubbles *f) { return f->o.faithful_classes; }
 void pvgpu_flubbles_copy(const pvgpu_flubbles *f, uint32_t *comp, uint32_t *a_v, uint8_t *a_fwd, uint32_t *z_v, uint8_t *z_fwd, uint32_t *parent, uint32_t *depth) {
 	cp(comp, f->o.comp); cp(a_v, f->o.a_v); cp(a_fwd, f->o.a_fwd); cp(z_v, f->o.z_v); cp(z_fwd, f->o.z_fwd); cp(parent, f->o.parent); cp(depth, f->o.depth);
 }

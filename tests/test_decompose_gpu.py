@@ -92,3 +92,14 @@ def test_gpu_cfg2_full_size_properties(gpu):
     f2 = gpu.decompose(len(g["ids"]), ep1, ep2)
     for k in ("a_v", "z_v", "parent", "depth", "a_fwd", "z_fwd"):
         assert (getattr(f, k) == getattr(f2, k)).all()
+
+
+def test_gpu_reference_class_naming_vs_oracle(gpu):
+    """see test_emu_reference_class_naming_vs_oracle: perturbed graphs, three of them with the reference's short capping edge"""
+    import call_checks as cc
+    hit = 0
+    for seed in [860, 1058, 2074] + list(range(300)):
+        f = _check(gpu, cc.perturbed_graph(seed))
+        hit += 1 if f.faithful_classes else 0
+        assert seed not in (860, 1058, 2074) or f.faithful_classes > 0
+    assert hit >= 3

@@ -90,3 +90,28 @@ def test_emu_hub_ports(emu_lib, order):
             links.append(synth.link(k, "+", 120, "+"))
     g = synth.make_graph(list(range(1, 122)), ["A"] * 121, links, [])
     _check(pv, g)
+
+
+@pytest.mark.parametrize("order", [0, 2])
+def test_emu_reference_class_naming_vs_oracle(emu_lib, order, tmp_path):
+    """Perturbed bubble graphs (chords with arbitrary sides): some have DFS-tree vertices with three or more children reaching
+    above them, where the reference's capping edge is too short and its (top bracket, list size) names merge classes that cycle
+    equivalence keeps apart (seeds 860 / 1058 / 2074: one flubble more than the XOR labels see).  The oracle restates that
+    choice of hi_2 (oracle_decompose.hpp:171-172); it is pinned here against the compiled reference's .pvst on those three,
+    and the device pipeline against the oracle on 150 seeds."""
+    import subprocess
+    import call_checks as cc
+    pv = _ctx(emu_lib, order)
+    hit = 0
+    for seed in [860, 1058, 2074] + list(range(150)):
+        g = cc.perturbed_graph(seed)
+        f = _check(pv, g)
+        hit += 1 if f.faithful_classes else 0
+        if seed in (860, 1058, 2074) and order == 0:
+            assert f.faithful_classes > 0
+            cc.require_ref()
+            gfa = str(tmp_path / f"q{seed}.gfa"); d = str(tmp_path / f"q{seed}"); os.makedirs(d)
+            synth.write_gfa(g, gfa)
+            assert subprocess.run([cc.REF, "decompose", "-i", gfa, "-o", d, "-t", "1"], capture_output=True).returncode == 0
+            assert f.pvst_texts(g["ids"]) == {1: open(os.path.join(d, "1.pvst")).read()}
+    assert hit >= 3
