@@ -175,12 +175,12 @@ inline void graph_build(Ctx &c, u32 V, u64 E, const u32 *ep1, const u32 *ep2, u3
 		});
 	}
 	// vertex -> steps index = the step indices grouped by vertex, ascending inside a vertex (group_indices, pv_prims.cuh).
-	// DENSE walks (hundreds of haplotypes: every vertex owns a long list) skip the small-group machinery altogether: one stable
+	// DENSE walks (dozens to hundreds of haplotypes: every vertex owns a long list) skip the small-group machinery altogether: one stable
 	// radix sort of (packed step, step index) on the VERTEX bits of the key -- the strand bit rides along below them, so the
 	// (path, strand) word of every list entry is later formed from the sorted key instead of a random read of steps[].
 	u32 vs_small = 48;
 	if (const char *e = getenv("POVU_B200_VS_SMALL")) vs_small = (u32)strtoul(e, nullptr, 10);   // tests: force the hub path
-	u64 dense_min = 64;
+	u64 dense_min = 20;      // measured: at 26 steps per vertex (cfg4, 90 paths) the sort path builds the index in 5.6 ms against 9.1 ms; cfg2 (12) and cfg3 (10) keep the small-group path
 	if (const char *e = getenv("POVU_B200_DENSE_INDEX")) dense_min = strtoull(e, nullptr, 10);       // tests: 0 forces the dense path
 	const bool dense = S > 0 && (u64)S >= dense_min * (u64)V;
 	const StepVertex SV{steps_};

@@ -83,10 +83,11 @@ struct RefNumOut {
 };
 
 // Can the reference's class naming differ from true cycle equivalence on this tree?  Its capping back edge goes to hi_2 = hi of
-// the FIRST child (ascending index) that is not hi_child and reaches above v (flubbles.cpp:564-573) instead of the second-lowest
-// hi; with three or more such children that bracket can end below brackets of a sibling it should cover, and two tree edges with
-// different bracket sets then share (top bracket, list size) -- the reference gives them one class and reports a flubble that
-// cycle equivalence does not have.  flag[0] += 1 for every vertex with >= 3 children that reach above it.
+// the FIRST child (ascending index) that is not hi_child and reaches above v (flubbles.cpp:564-573), where cycle equivalence
+// needs the LOWEST hi among those children.  Where the two differ the bracket ends below brackets of a sibling it should cover,
+// and two tree edges with different bracket sets can share (top bracket, list size): the reference gives them one class and
+// reports a flubble that cycle equivalence does not have.  flag[0] += 1 for every vertex where the two choices differ (three or
+// more children must reach above it for that; the usual multi-allelic bubble has them all reach the same vertex and is not counted).
 PV_KERNEL(R_quirk, 24);
 inline void refnum_quirk_flag(Ctx &c, const RefNumIn &t, u32 *flag) {
 	const u32 P = t.P, N = t.N;
@@ -99,10 +100,17 @@ inline void refnum_quirk_flag(Ctx &c, const RefNumIn &t, u32 *flag) {
 		u32 nGray = 0;
 		for (u32 s = adjOff_[node], e = adjOff_[node + 1]; s < e; s++) if (treeSlot_[s] != NONE) nGray++;
 		if (nGray + (isEntry ? 1u : 0u) < 3) return;
-		auto above = [&](u32 ch) -> u32 { u32 gc = pre_[ch]; return hv.query(gc, gc + sz_[ch] - 1) < g ? 1u : 0u; };
-		u32 n = isEntry ? above(node ^ 1u) : 0u;
-		for (u32 s = adjOff_[node], e = adjOff_[node + 1]; s < e; s++) { u32 ch = treeSlot_[s]; if (ch != NONE) n += above(ch); }
-		if (n >= 3) atomic_add(flag, 1u);
+		auto hiOf = [&](u32 ch) -> u32 { u32 gc = pre_[ch]; return hv.query(gc, gc + sz_[ch] - 1); };
+		// hi_child = the first child with the lowest hi (flubbles.cpp:546-562)
+		u32 hi1 = NONE, hiChild = NONE;
+		if (isEntry) { hi1 = hiOf(node ^ 1u); hiChild = node ^ 1u; }
+		for (u32 s = adjOff_[node], e = adjOff_[node + 1]; s < e; s++) { u32 ch = treeSlot_[s]; if (ch == NONE) continue; u32 h = hiOf(ch); if (hiChild == NONE || h < hi1) { hi1 = h; hiChild = ch; } }
+		// among the other children that reach above g: the first one's hi (the reference's hi_2) against the lowest
+		u32 first = NONE, lowest = NONE;
+		auto other = [&](u32 ch) { if (ch == hiChild) return; u32 h = hiOf(ch); if (h >= g) return; if (first == NONE) first = h; if (h < lowest) lowest = h; };
+		if (isEntry) other(node ^ 1u);
+		for (u32 s = adjOff_[node], e = adjOff_[node + 1]; s < e; s++) { u32 ch = treeSlot_[s]; if (ch != NONE) other(ch); }
+		if (first != lowest) atomic_add(flag, 1u);
 	});
 }
 
