@@ -269,7 +269,28 @@ def perturbed_graph(seed):
     return g
 
 
-def check_perturbed_cli(cli, tmp, seeds, env=None):
+def perturbed_graph_big(seed):
+    """the same idea at 3-5 times the size: 10-24 top-level bubbles nested up to 5 deep, 2-11 chords (70 % of them between
+    vertices at most 12 indices apart: local structural variation), 5 template walks + 5 random walks of up to 80 steps"""
+    rng = np.random.default_rng(50_000 + seed)
+    g = synth.nested_bubbles(seed, n_top=10 + seed % 15, max_depth=2 + seed % 4, n_paths=8)
+    V = len(g["ids"])
+    ex = []
+    for _ in range(int(rng.integers(2, 12))):
+        a = int(rng.integers(0, V))
+        b = int(np.clip(a + int(rng.integers(-12, 13)), 0, V - 1)) if rng.uniform() < 0.7 else int(rng.integers(0, V))
+        ex.append((a, int(rng.integers(0, 2)), b, int(rng.integers(0, 2))))
+    L = np.array(ex, dtype=np.int64)
+    g["v1"] = np.concatenate([g["v1"], L[:, 0].astype(np.uint32)]); g["s1"] = np.concatenate([g["s1"], L[:, 1].astype(np.uint8)])
+    g["v2"] = np.concatenate([g["v2"], L[:, 2].astype(np.uint32)]); g["s2"] = np.concatenate([g["s2"], L[:, 3].astype(np.uint8)])
+    paths = list(g["paths"][:5])
+    for i, (st, sr) in enumerate(random_walks(g, rng, 5, 80)):
+        paths.append((f"S{(5 + i) // 2 + 1:03d}#{(5 + i) % 2 + 1}#chr1", st, sr))
+    g["paths"] = paths
+    return g
+
+
+def check_perturbed_cli(cli, tmp, seeds, env=None, build=None):
     """gfa2vcf of `cli` vs the compiled reference, whole output byte for byte (order included).  Seeds on which the reference
     itself crashes are skipped; where the product reports a clamped SUBR slice (the reference reads past the end of a walk
     there: undefined) every other line must still agree.  Returns (graphs compared, records, tangled, SUBR)."""
@@ -277,7 +298,7 @@ def check_perturbed_cli(cli, tmp, seeds, env=None):
     n = nrec = ntang = nsubr = 0
     strip = lambda t: [l for l in t.splitlines() if not l.startswith("##fileDate")]
     for seed in seeds:
-        g = perturbed_graph(seed)
+        g = (build or perturbed_graph)(seed)
         gfa = os.path.join(tmp, f"pert{seed}.gfa")
         synth.write_gfa(g, gfa)
         prefix = g["paths"][0][0].split("#")[0]

@@ -72,6 +72,8 @@ def test_emu_perturbed_graphs_cli(emu_lib, tmp_path):
     import os
     n, nrec, ntang, nsubr = cc.check_perturbed_cli(os.path.join(os.path.dirname(emu_lib), "povu_emu"), str(tmp_path), range(300))
     assert n > 250 and nrec > 3000 and ntang > 300 and nsubr > 300, (n, nrec, ntang, nsubr)
+    n, nrec, ntang, nsubr = cc.check_perturbed_cli(os.path.join(os.path.dirname(emu_lib), "povu_emu"), str(tmp_path), range(150), build=cc.perturbed_graph_big)
+    assert n > 110 and nrec > 4000, (n, nrec, ntang, nsubr)
 
 
 def test_emu_reference_class_naming(emu_lib, tmp_path):

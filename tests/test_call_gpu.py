@@ -80,6 +80,8 @@ def test_gpu_perturbed_graphs_cli(gpu, tmp_path):
     import os
     n, nrec, ntang, nsubr = cc.check_perturbed_cli(os.path.join(cc.ROOT, "povu_b200", "bin", "povu"), str(tmp_path), range(300, 380))
     assert n > 60 and nrec > 600, (n, nrec, ntang, nsubr)
+    n, nrec, ntang, nsubr = cc.check_perturbed_cli(os.path.join(cc.ROOT, "povu_b200", "bin", "povu"), str(tmp_path), range(150, 230), build=cc.perturbed_graph_big)
+    assert n > 55 and nrec > 2000, (n, nrec, ntang, nsubr)
 
 
 def test_gpu_reference_class_naming(gpu, tmp_path):
