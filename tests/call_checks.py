@@ -317,3 +317,34 @@ def check_perturbed_cli(cli, tmp, seeds, env=None, build=None):
         assert a == b, (seed, [l[:120] for l in a if l not in set(b)][:2], [l[:120] for l in b if l not in set(a)][:2])
         n += 1; nrec += sum(1 for l in a if not l.startswith("#")); ntang += sum("TANGLED=T" in l for l in a); nsubr += sum("VARTYPE=SUBR" in l for l in a)
     return n, nrec, ntang, nsubr
+
+
+def check_perturbed_api(pv, tmp, seeds, build=None):
+    """the same comparison through the in-process operators (one CUDA context for all graphs instead of one per CLI run):
+    Session.from_graph -> decompose -> call -> VCF text vs the compiled reference's stdout"""
+    require_ref()
+    n = nrec = 0
+    strip = lambda t: [l for l in t.splitlines() if not l.startswith("##fileDate")]
+    for seed in seeds:
+        g = (build or perturbed_graph)(seed)
+        gfa = os.path.join(tmp, f"perta{seed}.gfa")
+        synth.write_gfa(g, gfa)
+        prefix = g["paths"][0][0].split("#")[0]
+        r = subprocess.run([REF, "gfa2vcf", "-i", gfa, "-t", "1", "-P", prefix], capture_output=True, text=True)
+        if r.returncode != 0:
+            continue
+        s = api.Session.from_graph(pv, g)
+        try:
+            s.decompose(); s.call([prefix])
+            st = s.call_stats()
+            if st["hard_errors"]:
+                continue      # the product refuses (CLI: "the reference aborts on this input")
+            a, b = strip(r.stdout), strip(s.vcf_text(with_date=False))
+            if st["subr_clamped"]:
+                a = [l for l in a if l.startswith("#") or ("VARTYPE=" in l and "VARTYPE=SUBR" not in l)]
+                b = [l for l in b if "VARTYPE=SUBR" not in l]
+            assert a == b, (seed, [l[:120] for l in a if l not in set(b)][:2], [l[:120] for l in b if l not in set(a)][:2])
+        finally:
+            s.close()
+        n += 1; nrec += sum(1 for l in a if not l.startswith("#"))
+    return n, nrec
