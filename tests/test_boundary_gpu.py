@@ -26,8 +26,8 @@ def test_gpu_export_golden(gpu, tmp_path):
 def test_gpu_export_vs_reference(gpu, tmp_path):
     import export_checks as ec
     cli = os.path.join(bc.ROOT, "povu_b200", "bin", "povu")
-    nb, ne = ec.check_wild_vs_reference(cli, str(tmp_path), range(40))
-    assert nb > 15 and ne > 400
+    nb, ne = ec.check_wild_vs_reference(cli, str(tmp_path), range(14))      # (every CLI run creates a CUDA context: the 120-seed sweep is the CPU rehearsal's)
+    assert nb > 4 and ne > 120
     nb, ne = ec.check_wild_vs_reference(cli, str(tmp_path), range(500, 504), V=3000)
     assert ne > 4000
     ec.check_degenerate_vs_reference(cli, str(tmp_path))

@@ -80,10 +80,10 @@ def test_gpu_perturbed_graphs(gpu, tmp_path):
     """perturbed bubble graphs with random-walk haplotypes (tests/call_checks.py), whole VCF vs the compiled reference: through
     the in-process operators (many graphs, one CUDA context) and a few through the CLI binary"""
     import os
-    n, nrec = cc.check_perturbed_api(gpu, str(tmp_path), range(300, 500))
-    assert n > 160 and nrec > 1800, (n, nrec)
-    n, nrec = cc.check_perturbed_api(gpu, str(tmp_path), range(150, 300), build=cc.perturbed_graph_big)
-    assert n > 100 and nrec > 4000, (n, nrec)
+    n, nrec = cc.check_perturbed_api(gpu, str(tmp_path), range(300, 420))
+    assert n > 95 and nrec > 1000, (n, nrec)
+    n, nrec = cc.check_perturbed_api(gpu, str(tmp_path), range(150, 230), build=cc.perturbed_graph_big)
+    assert n > 55 and nrec > 2000, (n, nrec)
     n, nrec, _, _ = cc.check_perturbed_cli(os.path.join(cc.ROOT, "povu_b200", "bin", "povu"), str(tmp_path), range(1000, 1012))
     assert n > 8
 
