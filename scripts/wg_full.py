@@ -98,10 +98,19 @@ def run_full(args, pv, stream, rank, world, torch, dist):
     per_comp, wins = [], []
     big = [c for c in mine if n_inst[c] >= 480]      # (chrM holds a dozen instances: no room for a window)
     smallest = min(big, key=lambda c: n_inst[c]) if big else None
+    # every rank builds all the components it owns first and waits for the others: nobody times kernels while a neighbour's
+    # generator keeps the host cores busy
+    flats = {}
+    gen_s = {}
     for c in mine:
         t0 = time.time()
-        f = synth.tiled_flat(T, int(n_inst[c]), args.paths, seed=1000 + c, chrom=f"chr{c + 1}")
-        t1 = time.time()
+        flats[c] = synth.tiled_flat(T, int(n_inst[c]), args.paths, seed=1000 + c, chrom=f"chr{c + 1}")
+        gen_s[c] = time.time() - t0
+    if world > 1:
+        dist.barrier()
+    for c in mine:
+        f = flats.pop(c)
+        t1 = time.time(); t0 = t1 - gen_s[c]
         check = args.windows > 0 and c == smallest
         sess = api.Session.from_flat(pv, f, with_labels=check)
         t2 = time.time()
