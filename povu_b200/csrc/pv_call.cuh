@@ -755,6 +755,43 @@ inline void overlay_pass(Ctx &c, const DevGraph &G, const GraphView &g, const Ca
 				if (r >= Rc) { if (lane == 0) { recCnt_[r] = 0; grpCnt_[r] = 0; } return; }
 				const u32 b = candOff_[rv.rowBase(r)], e = candOff_[rv.rowBase(r + 1)];
 				u32 *a = cd.hsort + b; u32 nh = 0;
+				if (e - b <= 128u) {
+					// up to four candidates per lane live in registers for the whole grouping: every field is read ONCE (ncu at 90
+					// paths: 2.4 GB read for 0.6 GB of candidates, one sweep of the arrays per head), the head's fields come from its
+					// owner lane by shuffle, membership is a ballot.  Candidate x = b + 32 k + lane: ascending k, then lane, is
+					// ascending x, so "first ungrouped candidate" and "joins the first head it matches" are the sequential rules.
+					u32 fL[4], fR[4], fC[4], fN[4], fS[4]; bool un[4];
+#pragma unroll
+					for (int k = 0; k < 4; k++) {
+						const u32 x = b + 32u * k + lane; const bool v = x < e;
+						fC[k] = v ? cd.cCls[x] : 3u; un[k] = v && fC[k] < 3u;
+						fL[k] = un[k] ? cd.cL[x] : 0u; fR[k] = un[k] ? cd.cR[x] : 0u; fN[k] = un[k] ? cd.cLen[x] : 0u; fS[k] = un[k] ? cd.cStart[x] : 0u;
+					}
+					while (true) {
+						int hk = -1; u32 hm = 0;
+#pragma unroll
+						for (int k = 0; k < 4; k++) { const u32 m = __ballot_sync(0xFFFFFFFFu, un[k]); if (hk < 0 && m) { hk = k; hm = m; } }
+						if (hk < 0) break;
+						const int hl = __ffs((int)hm) - 1;
+						u32 sL = 0, sR = 0, sC = 0, sN = 0, sS = 0;
+#pragma unroll
+						for (int k = 0; k < 4; k++) if (k == hk) { sL = fL[k]; sR = fR[k]; sC = fC[k]; sN = fN[k]; sS = fS[k]; }
+						const u32 hL = __shfl_sync(0xFFFFFFFFu, sL, hl), hR = __shfl_sync(0xFFFFFFFFu, sR, hl), hC = __shfl_sync(0xFFFFFFFFu, sC, hl),
+							  hLen = __shfl_sync(0xFFFFFFFFu, sN, hl), hSt = __shfl_sync(0xFFFFFFFFu, sS, hl);
+						const u32 h = b + 32u * (u32)hk + (u32)hl;
+						u32 mine = 0;
+#pragma unroll
+						for (int k = 0; k < 4; k++) {
+							if (!un[k]) continue;
+							const u32 x = b + 32u * k + lane;
+							if (x == h || (fL[k] == hL && fR[k] == hR && fC[k] == hC && fN[k] == hLen && walk_equal(g.steps, hSt, fS[k], hLen))) { cd.cHead[x] = h; un[k] = false; mine++; }
+						}
+#pragma unroll
+						for (int d = 16; d > 0; d >>= 1) mine += __shfl_xor_sync(0xFFFFFFFFu, mine, d);
+						if (lane == 0) { a[nh] = h; cd.gCount[h] = mine; }
+						nh++;
+					}
+				} else {
 				u32 next = b + lane;          // this lane's first candidate that may still be ungrouped
 				while (true) {
 					while (next < e && (cd.cCls[next] >= 3 || cd.cHead[next] != NONE)) next += 32;
@@ -774,6 +811,8 @@ inline void overlay_pass(Ctx &c, const DevGraph &G, const GraphView &g, const Ca
 					if (lane == 0) { a[nh] = h; cd.gCount[h] = mine; }
 					nh++;
 				}
+				}
+				__syncwarp();      // (lane 0 orders the heads from the arrays: the members' stores above must have landed)
 				if (lane != 0) return;
 				for (u32 st = nh / 2; st-- > 0;) sift_down(g.steps, cd, a, st, nh);
 				for (u32 end = nh; end-- > 1;) { u32 t2 = a[0]; a[0] = a[end]; a[end] = t2; sift_down(g.steps, cd, a, 0, end); }
@@ -1817,18 +1856,11 @@ inline void call_device(Ctx &c, const DevGraph &G, const CallIn &in, const CallO
 				for (u32 j = 0; j < J; j++) {
 					const u32 v = rv.vert(r, j);
 					const u32 a = g.vsOff[v], ee = g.vsOff[v + 1];
-					// 32 consecutive list entries per sweep: the neighbours a lane tests (is my entry the head of its run?  does the
-					// run go on?) sit in the registers of the lanes next to it -- two shuffles instead of two dependent loads
-					// (ncu: 61 % of this kernel's stalls were the long scoreboard behind exactly those loads)
-					for (u32 base = a; base < ee; base += 32) {
-						const u32 e = base + lane; const bool valid = e < ee;
-						const u32 hs = valid ? g.vsHap[e] : 0xFFFFFFFFu; const u32 h = hs >> 1;
-						u32 prevH = __shfl_up_sync(0xFFFFFFFFu, h, 1), nextH = __shfl_down_sync(0xFFFFFFFFu, h, 1);
-						if (lane == 0) prevH = e > a ? (g.vsHap[e - 1] >> 1) : 0x7FFFFFFEu;
-						if (lane == 31) nextH = e + 1 < ee ? (g.vsHap[e + 1] >> 1) : 0x7FFFFFFEu;
-						if (!valid || prevH == h) continue;   // not the head of its run
+					for (u32 e = a + lane; e < ee; e += 32) {   // (the neighbour tests hit the L1 lines the adjacent lanes just loaded: exchanging them by shuffle instead was measured 7 % slower)
+						const u32 hs = g.vsHap[e]; u32 h = hs >> 1;
+						if (e > a && (g.vsHap[e - 1] >> 1) == h) continue;   // not the head of its run
 						u32 first = g.vsStep[e]; u32 n = 1;
-						if (nextH == h) { n = 2; while (e + n < ee && (g.vsHap[e + n] >> 1) == h) n++; }
+						while (e + n < ee && (g.vsHap[e + n] >> 1) == h) n++;
 						if (g.pathComp[h] != comp) continue;   // cannot happen for a connected walk; keeps indexing safe
 						u32 i = g.hapLocal[h];
 						if (n > 0xFFFEu) { atomic_add(cv.errs + 2, 1u); n = 0xFFFEu; }
