@@ -755,7 +755,9 @@ inline void overlay_pass(Ctx &c, const DevGraph &G, const GraphView &g, const Ca
 				if (r >= Rc) { if (lane == 0) { recCnt_[r] = 0; grpCnt_[r] = 0; } return; }
 				const u32 b = candOff_[rv.rowBase(r)], e = candOff_[rv.rowBase(r + 1)];
 				u32 *a = cd.hsort + b; u32 nh = 0;
+				u32 kL = 0, kR = 0, kC = 0, kN = 0, kS = 0, kH = NONE; bool inRegs = false;      // head number `lane` (register path, first 32 heads)
 				if (e - b <= 128u) {
+					inRegs = true;
 					// up to four candidates per lane live in registers for the whole grouping: every field is read ONCE (ncu at 90
 					// paths: 2.4 GB read for 0.6 GB of candidates, one sweep of the arrays per head), the head's fields come from its
 					// owner lane by shuffle, membership is a ballot.  Candidate x = b + 32 k + lane: ascending k, then lane, is
@@ -779,6 +781,7 @@ inline void overlay_pass(Ctx &c, const DevGraph &G, const GraphView &g, const Ca
 						const u32 hL = __shfl_sync(0xFFFFFFFFu, sL, hl), hR = __shfl_sync(0xFFFFFFFFu, sR, hl), hC = __shfl_sync(0xFFFFFFFFu, sC, hl),
 							  hLen = __shfl_sync(0xFFFFFFFFu, sN, hl), hSt = __shfl_sync(0xFFFFFFFFu, sS, hl);
 						const u32 h = b + 32u * (u32)hk + (u32)hl;
+						if (lane == nh) { kL = hL; kR = hR; kC = hC; kN = hLen; kS = hSt; kH = h; }
 						u32 mine = 0;
 #pragma unroll
 						for (int k = 0; k < 4; k++) {
@@ -813,6 +816,28 @@ inline void overlay_pass(Ctx &c, const DevGraph &G, const GraphView &g, const Ca
 				}
 				}
 				__syncwarp();      // (lane 0 orders the heads from the arrays: the members' stores above must have landed)
+				if (inRegs && nh <= 32u) {
+					// the heads' order (context, class, walk: the reference's nested std::maps) by RANKING instead of a heap sort on one
+					// lane: lane j holds head j, meets every other head by shuffle and counts the smaller ones; distinct heads never
+					// compare equal, so the ranks are a permutation.  A head opens a record iff no smaller head shares its context + class.
+					u32 rank = 0; bool prevSame = false;
+					for (u32 j = 0; j < nh; j++) {
+						const u32 oL = __shfl_sync(0xFFFFFFFFu, kL, j), oR = __shfl_sync(0xFFFFFFFFu, kR, j), oC = __shfl_sync(0xFFFFFFFFu, kC, j),
+							  oN = __shfl_sync(0xFFFFFFFFu, kN, j), oS = __shfl_sync(0xFFFFFFFFu, kS, j);
+						if (lane >= nh || j == lane) continue;
+						const bool same = oL == kL && oR == kR && oC == kC;
+						const bool less = oL != kL ? oL < kL : (oR != kR ? oR < kR : (oC != kC ? oC < kC : walk_cmp(g.steps, oS, oN, kS, kN) < 0));
+						if (less) { rank++; if (same) prevSame = true; }
+					}
+					if (lane < nh) a[rank] = kH;
+					const u32 nrec = (u32)__popc(__ballot_sync(0xFFFFFFFFu, lane < nh && !prevSame));
+					if (lane == 0) {
+						recCnt_[r] = nrec; grpCnt_[r] = nh;
+						if (k == 0) cv.hasData[r] = nh ? 1u : 0u;
+						else if (nh == 0 && cv.hasData[r]) atomic_add(cv.errs + 0, 1u);   // std::map::at throws in the reference
+					}
+					return;
+				}
 				if (lane != 0) return;
 				for (u32 st = nh / 2; st-- > 0;) sift_down(g.steps, cd, a, st, nh);
 				for (u32 end = nh; end-- > 1;) { u32 t2 = a[0]; a[0] = a[end]; a[end] = t2; sift_down(g.steps, cd, a, 0, end); }
