@@ -746,7 +746,9 @@ inline void overlay_pass(Ctx &c, const DevGraph &G, const GraphView &g, const Ca
 		// (lanes stride over the candidates, warp minimum), let every lane compare its candidates with it, count the members
 		// with a warp sum.  Heads come out in order of first occurrence and every candidate joins the first head it matches --
 		// exactly the sequential grouping; the few heads are then ordered by lane 0.
-		group_by_warp = (u64)nCand >= 24ull * Rc || getenv("POVU_B200_GROUP_WARP") != nullptr;
+		u64 warp_min = 8;      // candidates per region from which a warp beats a thread (the thread version ran at 17 GB/s with ~20 candidates per region)
+		if (const char *e_ = getenv("POVU_B200_GROUP_WARP_MIN")) warp_min = strtoull(e_, nullptr, 10);
+		group_by_warp = (u64)nCand >= warp_min * Rc || getenv("POVU_B200_GROUP_WARP") != nullptr;
 		if (group_by_warp && !getenv("POVU_B200_GROUP_THREAD")) {
 			u32 *cHead_ = cd.cHead;
 			parallel_for<C_fill16>(c, nC1, PV_LAMBDA(size_t x) { cHead_[x] = NONE; });
