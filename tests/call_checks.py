@@ -290,7 +290,7 @@ def perturbed_graph_big(seed):
     return g
 
 
-def check_perturbed_cli(cli, tmp, seeds, env=None, build=None):
+def check_perturbed_cli(cli, tmp, seeds, env=None, build=None, args=None):
     """gfa2vcf of `cli` vs the compiled reference, whole output byte for byte (order included).  Seeds on which the reference
     itself crashes are skipped; where the product reports a clamped SUBR slice (the reference reads past the end of a walk
     there: undefined) every other line must still agree.  Returns (graphs compared, records, tangled, SUBR)."""
@@ -301,11 +301,11 @@ def check_perturbed_cli(cli, tmp, seeds, env=None, build=None):
         g = (build or perturbed_graph)(seed)
         gfa = os.path.join(tmp, f"pert{seed}.gfa")
         synth.write_gfa(g, gfa)
-        prefix = g["paths"][0][0].split("#")[0]
-        r = subprocess.run([REF, "gfa2vcf", "-i", gfa, "-t", "1", "-P", prefix], capture_output=True, text=True)
+        sel = args or ["-P", g["paths"][0][0].split("#")[0]]
+        r = subprocess.run([REF, "gfa2vcf", "-i", gfa, "-t", "1", *sel], capture_output=True, text=True)
         if r.returncode != 0:
             continue
-        m = subprocess.run([cli, "gfa2vcf", "-i", gfa, "-t", "1", "-P", prefix], capture_output=True, text=True, env=dict(os.environ, **(env or {})))
+        m = subprocess.run([cli, "gfa2vcf", "-i", gfa, "-t", "1", *sel], capture_output=True, text=True, env=dict(os.environ, **(env or {})))
         if m.returncode != 0 and "the reference aborts on this input" in m.stderr:
             continue      # gen_cxt takes front() of an empty vector there (overlay.cpp:307-325): the reference survives by luck, the product refuses
         assert m.returncode == 0, (seed, m.stderr[-300:])

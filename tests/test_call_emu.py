@@ -72,8 +72,15 @@ def test_emu_perturbed_graphs_cli(emu_lib, tmp_path):
     import os
     n, nrec, ntang, nsubr = cc.check_perturbed_cli(os.path.join(os.path.dirname(emu_lib), "povu_emu"), str(tmp_path), range(300))
     assert n > 250 and nrec > 3000 and ntang > 300 and nsubr > 300, (n, nrec, ntang, nsubr)
-    n, nrec, ntang, nsubr = cc.check_perturbed_cli(os.path.join(os.path.dirname(emu_lib), "povu_emu"), str(tmp_path), range(150), build=cc.perturbed_graph_big)
+    cli = os.path.join(os.path.dirname(emu_lib), "povu_emu")
+    n, nrec, ntang, nsubr = cc.check_perturbed_cli(cli, str(tmp_path), range(150), build=cc.perturbed_graph_big)
     assert n > 110 and nrec > 4000, (n, nrec, ntang, nsubr)
+    # several components, two reference samples, one haplotype as the reference with chunks of three regions
+    from povu_b200 import synth
+    n1, r1, _, _ = cc.check_perturbed_cli(cli, str(tmp_path), range(60), build=lambda s: synth.concat_components([cc.perturbed_graph(3 * s + k) for k in range(2 + s % 2)]))
+    n2, r2, _, _ = cc.check_perturbed_cli(cli, str(tmp_path), range(60), build=cc.perturbed_graph_big, args=["-P", "S001", "-P", "S003"])
+    n3, r3, _, _ = cc.check_perturbed_cli(cli, str(tmp_path), range(60), args=["-P", "S002#1", "-c", "3"])
+    assert n1 > 40 and n2 > 40 and n3 > 40 and r1 + r2 + r3 > 600, (n1, r1, n2, r2, n3, r3)
 
 
 def test_emu_reference_class_naming(emu_lib, tmp_path):
