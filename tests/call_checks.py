@@ -348,3 +348,40 @@ def check_perturbed_api(pv, tmp, seeds, build=None):
             s.close()
         n += 1; nrec += sum(1 for l in a if not l.startswith("#"))
     return n, nrec
+
+
+def check_perturbed_files_and_restrict(cli, tmp, seeds):
+    """decompose -> .pvst files (byte-identical to the reference's) -> `call -f dir` on the reference's files, every third
+    graph with a `-g ref:start-end` window over the middle of the reference walk"""
+    import shutil
+    require_ref()
+    n = nrec = 0
+    strip = lambda t: [l for l in t.splitlines() if not l.startswith("##fileDate")]
+    for seed in seeds:
+        g = perturbed_graph_big(seed) if seed % 2 else perturbed_graph(seed)
+        gfa = os.path.join(tmp, f"pf{seed}.gfa")
+        synth.write_gfa(g, gfa)
+        fr, fm = os.path.join(tmp, f"pf{seed}.r"), os.path.join(tmp, f"pf{seed}.m")
+        for d in (fr, fm):
+            shutil.rmtree(d, ignore_errors=True); os.makedirs(d)
+        ref0 = g["paths"][0][0]
+        length = sum(len(g["seqs"][v]) for v in g["paths"][0][1].tolist())
+        if subprocess.run([REF, "decompose", "-i", gfa, "-o", fr, "-t", "1"], capture_output=True).returncode != 0:
+            continue
+        assert subprocess.run([cli, "decompose", "-i", gfa, "-o", fm], capture_output=True).returncode == 0, seed
+        assert {f: open(os.path.join(fr, f)).read() for f in os.listdir(fr)} == {f: open(os.path.join(fm, f)).read() for f in os.listdir(fm)}, (seed, "pvst")
+        sel = ["-P", ref0.split("#")[0]] + (["-g", f"{ref0}:{int(length * 0.2)}-{int(length * 0.7)}"] if seed % 3 == 0 else [])
+        r = subprocess.run([REF, "call", "-i", gfa, "-f", fr, "-t", "1", *sel], capture_output=True, text=True)
+        if r.returncode != 0:
+            continue
+        m = subprocess.run([cli, "call", "-i", gfa, "-f", fr, "-t", "1", *sel], capture_output=True, text=True)
+        if m.returncode != 0 and "the reference aborts on this input" in m.stderr:
+            continue
+        assert m.returncode == 0, (seed, m.stderr[-300:])
+        a, b = strip(r.stdout), strip(m.stdout)
+        if "SUBR records had a merged length past the end of a walk" in m.stderr:
+            a = [l for l in a if l.startswith("#") or ("VARTYPE=" in l and "VARTYPE=SUBR" not in l)]
+            b = [l for l in b if "VARTYPE=SUBR" not in l]
+        assert a == b, (seed, sel)
+        n += 1; nrec += sum(1 for l in a if not l.startswith("#"))
+    return n, nrec

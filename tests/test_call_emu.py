@@ -110,3 +110,9 @@ def test_emu_reference_class_naming(emu_lib, tmp_path):
         r = subprocess.run([cli, "gfa2vcf", "-i", helpers.fixture_path(name, str(tmp_path)), "-t", "1", "-P", prefix], capture_output=True, text=True, env=dict(os.environ, **force))
         assert r.returncode == 0, (name, r.stderr[-300:])
         assert strip(r.stdout) == open(os.path.join(helpers.GOLDEN, "expected", name + ".vcf")).read(), name
+
+
+def test_emu_perturbed_files_and_restrict(emu_lib, tmp_path):
+    import os
+    n, nrec = cc.check_perturbed_files_and_restrict(os.path.join(os.path.dirname(emu_lib), "povu_emu"), str(tmp_path), range(90))
+    assert n > 70 and nrec > 1200, (n, nrec)
