@@ -385,3 +385,45 @@ def check_perturbed_files_and_restrict(cli, tmp, seeds):
         assert a == b, (seed, sel)
         n += 1; nrec += sum(1 for l in a if not l.startswith("#"))
     return n, nrec
+
+
+def hub_graph(seed):
+    """nested bubbles plus 1-3 hubs (one vertex side linked to 3-8 random vertex sides) and a few more chords: DFS-tree vertices
+    with many children whose brackets reach different heights -- where the reference's choice of capping edge matters most
+    (about three graphs in four take the re-derived classes of pv_refnum.cuh).  No haplotypes: a decompose family."""
+    rng = np.random.default_rng(90_000 + seed)
+    g = synth.nested_bubbles(seed, n_top=6 + seed % 10, max_depth=1 + seed % 4, n_paths=2)
+    V = len(g["ids"])
+    ex = []
+    for _ in range(1 + seed % 3):
+        h, hs = int(rng.integers(0, V)), int(rng.integers(0, 2))
+        for _ in range(int(rng.integers(3, 9))):
+            ex.append((h, hs, int(rng.integers(0, V)), int(rng.integers(0, 2))))
+    for _ in range(int(rng.integers(0, 5))):
+        ex.append((int(rng.integers(0, V)), int(rng.integers(0, 2)), int(rng.integers(0, V)), int(rng.integers(0, 2))))
+    L = np.array(ex, dtype=np.int64)
+    g["v1"] = np.concatenate([g["v1"], L[:, 0].astype(np.uint32)]); g["s1"] = np.concatenate([g["s1"], L[:, 1].astype(np.uint8)])
+    g["v2"] = np.concatenate([g["v2"], L[:, 2].astype(np.uint32)]); g["s2"] = np.concatenate([g["s2"], L[:, 3].astype(np.uint8)])
+    return g
+
+
+def check_hub_graphs(pv, tmp, seeds, ref_every=4):
+    """decompose vs the oracle on every graph and vs the compiled reference's .pvst on every `ref_every`-th"""
+    import oracle_binding as ob
+    require_ref()
+    n = faithful = nref = 0
+    for seed in seeds:
+        g = hub_graph(seed)
+        ep1, ep2 = api.edge_ports(g)
+        f = pv.decompose(len(g["ids"]), ep1, ep2)
+        assert ob.flubble_rows(f, g["ids"]) == ob.oracle_decompose(g), seed
+        n += 1; faithful += 1 if f.faithful_classes else 0
+        if seed % ref_every == 0:
+            gfa = os.path.join(tmp, f"hub{seed}.gfa"); d = os.path.join(tmp, f"hub{seed}.d")
+            os.makedirs(d, exist_ok=True)
+            synth.write_gfa(g, gfa)
+            if subprocess.run([REF, "decompose", "-i", gfa, "-o", d, "-t", "1"], capture_output=True).returncode != 0:
+                continue
+            assert f.pvst_texts(g["ids"]) == {int(x[:-5]): open(os.path.join(d, x)).read() for x in os.listdir(d)}, seed
+            nref += 1
+    return n, faithful, nref

@@ -115,3 +115,9 @@ def test_emu_reference_class_naming_vs_oracle(emu_lib, order, tmp_path):
             assert subprocess.run([cc.REF, "decompose", "-i", gfa, "-o", d, "-t", "1"], capture_output=True).returncode == 0
             assert f.pvst_texts(g["ids"]) == {1: open(os.path.join(d, "1.pvst")).read()}
     assert hit >= 3
+
+
+def test_emu_hub_graphs_reference_classes(emu_lib, tmp_path):
+    import call_checks as cc
+    n, faithful, nref = cc.check_hub_graphs(_ctx(emu_lib, 1), str(tmp_path), range(240))
+    assert n == 240 and faithful > 120 and nref > 50, (n, faithful, nref)
