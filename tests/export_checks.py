@@ -71,6 +71,15 @@ def check_export_golden(cli, tmp):
         r = run(cli, "decompose", "-i", gfa, "-h", "-o", d)
         assert r.returncode == 0, (name, r.stderr[-400:])
         assert "".join(l + "\n" for l in boundaries(r.stderr)) == read(os.path.join(EXPORT, name + ".hairpins.txt")), name
+    # the reference's own integration test for this surface (tests/integration_tests/gfa2vcf_tests.cc:137-166,
+    # StructureExportIncludesFlubbleDebugFrame): exit 0, the four keys in the document, the side file exists
+    gfa = helpers.fixture_path("insertion_flubble"); js = os.path.join(tmp, "ref_test.json")
+    r = run(cli, "gfa2vcf", "-i", gfa, "-t", "1", "-P", "HG1", "--structure-export", js)
+    assert r.returncode == 0, r.stderr
+    text = read(js)
+    for key in ('"flubble_debug"', '"stack_entries"', '"next_seen_table"', '"diagnostic":"ok"'):
+        assert key in text, key
+    assert os.path.exists(js + ".flubble-debug.jsonl")
     # the VCF on stdout is not disturbed by the export, and a second run replaces (not appends to) the side file
     gfa = helpers.fixture_path("nested_deletion"); js = os.path.join(tmp, "twice.json")
     a = run(cli, "gfa2vcf", "-i", gfa, "-P", "HG1", "--structure-export", js)
