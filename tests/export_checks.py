@@ -88,6 +88,29 @@ def check_export_golden(cli, tmp):
     assert a.stdout == b.stdout == c.stdout and read(js + ".flubble-debug.jsonl") == read(os.path.join(EXPORT, "nested_deletion.frames.jsonl"))
 
 
+def check_cycle_tables(cli, tmp):
+    """the reference's conformance harness reads the debug frames of `--structure-export` and checks six hand-written cycle tables
+    (tests/lean4_conformance/src/main.rs:1594-1622, transcribed in tests/golden/cycle_oracle.json): tree-edge ids in one group
+    share a class, ids of different groups do not.  Here the same check on the product's frames."""
+    tables = helpers.load_json("cycle_oracle.json")
+    for name, groups in tables.items():
+        if name.startswith("_"):
+            continue
+        js = os.path.join(tmp, "cyc_" + name + ".json")
+        r = run(cli, "gfa2vcf", "-i", helpers.fixture_path(name), "-t", "1", "-P", "HG1", "--structure-export", js)
+        assert r.returncode == 0, (name, r.stderr[-300:])
+        frame = json.loads(read(js))["flubble_debug"]["frames"][0]
+        cls = {e["tree_edge_id"]: e["class_id"] for e in frame["stack_entries"]}
+        assert all(e["diagnostic"] == "ok" for e in frame["stack_entries"]), name
+        seen = {}
+        for gi, grp in enumerate(groups):
+            ids = {cls[t] for t in grp}
+            assert len(ids) == 1, (name, grp, "one class expected")
+            c = ids.pop()
+            assert c not in seen, (name, grp, "distinct groups must not share a class")
+            seen[c] = gi
+
+
 def canon(doc):
     """tree numbers -> names that do not depend on the order the trees were read in"""
     d = json.loads(doc)

@@ -21,6 +21,7 @@ def test_gpu_ffi(gpu, tmp_path):
 def test_gpu_export_golden(gpu, tmp_path):
     import export_checks as ec
     ec.check_export_golden(os.path.join(bc.ROOT, "povu_b200", "bin", "povu"), str(tmp_path))
+    ec.check_cycle_tables(os.path.join(bc.ROOT, "povu_b200", "bin", "povu"), str(tmp_path))
 
 
 def test_gpu_export_vs_reference(gpu, tmp_path):
