@@ -134,6 +134,7 @@ inline void structure_export(Session &S, const std::string &path, const std::str
 		o += "{\"order\":" + std::to_string(v) + ",\"id\":" + std::to_string(g.ids[v]) + ",\"sequence\":";
 		if (g.has_labels) json_str(o, g.lbl.data() + g.lblOff[v], (size_t)(g.lblOff[v + 1] - g.lblOff[v])); else o += "\"\"";
 		o += '}';
+		if (o.size() > (8u << 20)) { out << o; o.clear(); }
 	}
 	o += "],\"links\":[";
 	for (u64 e = 0; e < g.E(); e++) {
@@ -141,6 +142,7 @@ inline void structure_export(Session &S, const std::string &path, const std::str
 		const u32 a = g.ep1[e], b = g.ep2[e];
 		o += "{\"order\":" + std::to_string(e) + ",\"from\":" + std::to_string(g.ids[a >> 1]) + ",\"from_orient\":\"" + ((a & 1u) ? "+" : "-") + "\",\"to\":" + std::to_string(g.ids[b >> 1]) +
 		     ",\"to_orient\":\"" + ((b & 1u) ? "-" : "+") + "\",\"overlap\":\"0M\"}";
+		if (o.size() > (8u << 20)) { out << o; o.clear(); }
 	}
 	o += "],\"paths\":[";
 	for (u32 h = 0; h < g.H(); h++) {
