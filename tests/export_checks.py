@@ -111,6 +111,39 @@ def check_cycle_tables(cli, tmp):
             seen[c] = gi
 
 
+def check_hierarchy_spans(cli, tmp):
+    """the conformance harness's hierarchy rule (tests/lean4_conformance/src/main.rs:1490-1571), restated: every class-stack
+    span (an entry and the next later entry of its class, more than one position apart) names a PVST flubble node by its
+    canonical boundary id, and that node's parent is the node of the smallest strictly containing span, else the tree's root."""
+    cases = [(n, "ref" if n == "hairpin_inversion_subr" else "HG1") for n in helpers.POSITIVE] + [("nested_s1", "S001"), ("nested_s2_shuffled", "S001"), ("chain_s3", "S001")]
+    checked = 0
+    for name, prefix in cases:
+        js = os.path.join(tmp, "hier_" + name + ".json")
+        r = run(cli, "gfa2vcf", "-i", helpers.fixture_path(name), "-t", "1", "-P", prefix, "--structure-export", js)
+        assert r.returncode == 0, (name, r.stderr[-300:])
+        d = json.loads(read(js))
+        by_boundary = {n["boundary"]: n for n in d["pvst_nodes"] if n["family"] == "flubble"}
+        assert len(by_boundary) == sum(1 for n in d["pvst_nodes"] if n["family"] == "flubble"), (name, "duplicate boundary id")
+        for frame in d["flubble_debug"]["frames"]:
+            ent = frame["stack_entries"]
+            spans = []
+            for i, e in enumerate(ent):
+                close = next((j for j in range(i + 1, len(ent)) if ent[j]["class_id"] == e["class_id"]), None)
+                if close is None or i + 1 >= close:
+                    continue
+                c = ent[close]
+                bid = f">{c['boundary_vertex_id']}>{e['boundary_vertex_id']}" if e["orientation"] == "<" and c["orientation"] == "<" else \
+                    f"{e['orientation']}{e['boundary_vertex_id']}{c['orientation']}{c['boundary_vertex_id']}"
+                assert bid in by_boundary, (name, bid, "a stack span without a PVST flubble node")
+                spans.append((e["order"], c["order"], by_boundary[bid]))
+            for a, b, node in spans:
+                cont = [(b2 - a2, n2["node_id"]) for a2, b2, n2 in spans if n2["node_id"] != node["node_id"] and a2 <= a and b <= b2 and (a2 < a or b < b2)]
+                want = min(cont)[1] if cont else node["node_id"].split(":")[0] + ":0"
+                assert node["parent"] == want, (name, node["node_id"], node["parent"], want)
+                checked += 1
+    assert checked > 100, checked
+
+
 def canon(doc):
     """tree numbers -> names that do not depend on the order the trees were read in"""
     d = json.loads(doc)
