@@ -15,6 +15,7 @@ def test_emu_ffi_builder(emu_lib):
 
 def test_emu_ffi_compute(emu_lib, tmp_path):
     bc.check_ffi_compute(bc.ffi(emu_lib), str(tmp_path))
+    assert bc.check_ffi_perturbed(bc.ffi(emu_lib), str(tmp_path), range(60)) > 45
 
 
 def test_cuda_library_ffi_builder_without_gpu(built):
