@@ -16,13 +16,11 @@ def test_gpu_ffi(gpu, tmp_path):
     L = bc.ffi(os.path.join(bc.ROOT, "povu_b200", "libpovu_b200.so"))
     bc.check_ffi_builder(L)
     bc.check_ffi_compute(L, str(tmp_path))
-    assert bc.check_ffi_perturbed(L, str(tmp_path), range(60, 100)) > 30
 
 
 def test_gpu_export_golden(gpu, tmp_path):
     import export_checks as ec
     ec.check_export_golden(os.path.join(bc.ROOT, "povu_b200", "bin", "povu"), str(tmp_path))
-    ec.check_cycle_tables(os.path.join(bc.ROOT, "povu_b200", "bin", "povu"), str(tmp_path))
 
 
 def test_gpu_export_vs_reference(gpu, tmp_path):

@@ -103,10 +103,3 @@ def test_gpu_reference_class_naming_vs_oracle(gpu):
         hit += 1 if f.faithful_classes else 0
         assert seed not in (860, 1058, 2074) or f.faithful_classes > 0
     assert hit >= 3
-
-
-def test_gpu_hub_graphs_reference_classes(gpu, tmp_path):
-    """hubs + chords on nested bubbles: most of these take the classes re-derived the reference's way (call_checks.hub_graph)"""
-    import call_checks as cc
-    n, faithful, nref = cc.check_hub_graphs(gpu, str(tmp_path), range(240, 400))
-    assert n == 160 and faithful > 80 and nref > 30, (n, faithful, nref)
