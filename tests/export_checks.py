@@ -34,6 +34,29 @@ def read(p):
         return f.read()
 
 
+def check_call_export(cli, tmp):
+    """`povu call --structure-export` (no decompose in the run): the frames are whatever the side file already holds
+    (to_structure_export.cpp:146-170) -- none without one, its lines verbatim with one"""
+    assert os.path.exists(REF)
+    gfa = helpers.fixture_path("nested_deletion")
+    d = os.path.join(tmp, "callexp"); os.makedirs(d)
+    assert run(REF, "decompose", "-i", gfa, "-o", d, "-t", "1").returncode == 0
+    rj, mj = os.path.join(tmp, "callexp.r.json"), os.path.join(tmp, "callexp.m.json")
+    for side in (None, '{"schema":"anything"}\n'):
+        for j in (rj, mj):
+            if side is None:
+                if os.path.exists(j + ".flubble-debug.jsonl"):
+                    os.remove(j + ".flubble-debug.jsonl")
+            else:
+                with open(j + ".flubble-debug.jsonl", "w") as f:
+                    f.write(side)
+        r = run(REF, "call", "-i", gfa, "-f", d, "-t", "1", "-P", "HG1", "--structure-export", rj)
+        m = run(cli, "call", "-i", gfa, "-f", d, "-t", "1", "-P", "HG1", "--structure-export", mj)
+        assert r.returncode == 0 and m.returncode == 0, m.stderr[-300:]
+        assert trim_steps(read(rj), gfa) == read(mj)
+        assert len(json.loads(read(mj))["flubble_debug"]["frames"]) == (0 if side is None else 1)
+
+
 def trim_steps(doc, gfa):
     """The reference lists `hap_len` (base pairs) entries of a path's step arrays instead of `step_count`
     (to_structure_export.cpp:319-328: `step_idx < ref.get_length()`), i.e. it reads past the end of the walk whenever a

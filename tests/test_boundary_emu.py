@@ -30,6 +30,7 @@ def test_emu_export_golden(emu_lib, tmp_path):
     ec.check_export_golden(os.path.join(os.path.dirname(emu_lib), "povu_emu"), str(tmp_path))
     ec.check_cycle_tables(os.path.join(os.path.dirname(emu_lib), "povu_emu"), str(tmp_path))
     ec.check_hierarchy_spans(os.path.join(os.path.dirname(emu_lib), "povu_emu"), str(tmp_path))
+    ec.check_call_export(os.path.join(os.path.dirname(emu_lib), "povu_emu"), str(tmp_path))
 
 
 def test_emu_export_vs_reference(emu_lib, tmp_path):

@@ -22,6 +22,7 @@ def test_gpu_cycle_tables_and_hierarchy_spans(gpu, tmp_path):
     """the conformance harness's expectations (main.rs:1490-1622) on the CUDA build's structure export"""
     ec.check_cycle_tables(CLI, str(tmp_path))
     ec.check_hierarchy_spans(CLI, str(tmp_path))
+    ec.check_call_export(CLI, str(tmp_path))
 
 
 def test_gpu_ffi_builder_on_perturbed_graphs(gpu, tmp_path):
