@@ -1,7 +1,9 @@
 // povu_b200 -- the reference's INTERNAL NUMBERING of the cycle-equivalence pass, derived in parallel from the arrays decompose
-// already holds (exact DFS tree in preorder, back edges, simplifying edges).  Only the two debug surfaces of the reference read
-// it: `--hairpins` (stderr "Boundary: b1 b2", /root/reference/src/povu/algorithms/flubbles.cpp:503-719) and the per-component
-// "povu.flubble-debug.frame.v1" frames of `--structure-export` (flubbles.cpp:108-213).  The hot path never runs this.
+// already holds (exact DFS tree in preorder, back edges, simplifying edges).  Two users: (1) the debug surfaces of the reference,
+// `--hairpins` (stderr "Boundary: b1 b2", /root/reference/src/povu/algorithms/flubbles.cpp:503-719) and the per-component
+// "povu.flubble-debug.frame.v1" frames of `--structure-export` (flubbles.cpp:108-213); (2) decompose itself, on the rare trees
+// where the reference's class names are not cycle equivalence (refnum_quirk_flag below): the classes then come from here.
+// On every named benchmark configuration the hot path never runs this.
 //
 // What the reference computes sequentially, vertex by vertex in descending DFS index, and what stands in for it here:
 //   * bracket list of v (std::list, children spliced on top in ascending index order, own pushes on top of those)
