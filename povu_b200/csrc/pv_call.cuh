@@ -605,7 +605,8 @@ struct ChunkView {
 
 	PV_DEV Lap lap(u32 row) const { u32 s = lapStart[row]; return Lap{s, s + lapLen[row]}; }
 };
-struct CandView { u32 *cL, *cR, *cStart, *cLen, *cRS, *cRL, *cHap, *cCls, *cHead, *gCount, *hsort, *pinCount; };
+struct CandView { u32 *cL, *cR, *cStart, *cLen, *cRS, *cRL, *cHap, *cCls, *cHead, *gCount, *hsort, *pinCount;
+		  u32 *evald; };   // evald[region]: a context of this ref was looked at (what makes trek::has_data() true, see overlay_pass)
 
 // comp_bounds + is_inverted over one (region, ref path, other path) pair (overlay.cpp:84-149); with
 // fill = true also gen_cxt, the two hap slices and the classification of every context
@@ -632,6 +633,7 @@ PV_DEV u32 scan_pair_ri(const ChunkView &cv, u32 refLocal, u32 k, u32 r, u32 i, 
 		if (ok) {
 			if (prev != NONE && diff) {
 				if (fill) {
+					cd.evald[r] = 1;      // tk.get_min_rov(ref) default-inserts the ref's map for EVERY context, before the pin / equal-slice tests (overlay.cpp:478-479)
 					u32 u = rv.vert(r, prev), v = rv.vert(r, j);
 					Lap rl = cv.lap(rv.rowBase(r) + refLocal), al = cv.lap(row);
 					u32 fu = g.occ_first(u, rl.lo, rl.hi), lv = g.occ_last(v, rl.lo, rl.hi);
@@ -726,7 +728,11 @@ inline void overlay_pass(Ctx &c, const DevGraph &G, const GraphView &g, const Ca
 		const size_t nC1 = nCand ? nCand : 1;
 		Buf<u32> cL(c, nC1), cR(c, nC1), cStart(c, nC1), cLen(c, nC1), cRS(c, nC1), cRL(c, nC1), cHap(c, nC1), cCls(c, nC1), cHead(c, nC1), gCount(c, nC1), hsort(c, nC1);
 		Buf<u32> pinCount(c, 1); pinCount.zero();
-		const CandView cd{cL.p, cR.p, cStart.p, cLen.p, cRS.p, cRL.p, cHap.p, cCls.p, cHead.p, gCount.p, hsort.p, pinCount.p};
+		// has_data() of the reference's trek is "some ref's map exists", and a ref's map comes into being with the first context that is
+		// looked at for it -- also when that context ends as an inversion pin pair or an equal slice and leaves no record.  Regions
+		// whose first ref only produced such contexts therefore DO go on to the next ref (a whole-row inversion does not count).
+		Buf<u32> evald(c, (size_t)Rc + 1); evald.zero();
+		const CandView cd{cL.p, cR.p, cStart.p, cLen.p, cRS.p, cRL.p, cHap.p, cCls.p, cHead.p, gCount.p, hsort.p, pinCount.p, evald.p};
 		// ---- C5b: slices per context, classification
 		// one thread per candidate slot; the thread of a row's FIRST slot fills the whole row.  Rows without a context
 		// (most paths carry the ref allele) cost nothing and the working lanes of a warp are consecutive busy rows.
@@ -835,8 +841,8 @@ inline void overlay_pass(Ctx &c, const DevGraph &G, const GraphView &g, const Ca
 					const u32 nrec = (u32)__popc(__ballot_sync(0xFFFFFFFFu, lane < nh && !prevSame));
 					if (lane == 0) {
 						recCnt_[r] = nrec; grpCnt_[r] = nh;
-						if (k == 0) cv.hasData[r] = nh ? 1u : 0u;
-						else if (nh == 0 && cv.hasData[r]) atomic_add(cv.errs + 0, 1u);   // std::map::at throws in the reference
+						if (k == 0) cv.hasData[r] = cd.evald[r];
+						else if (!cd.evald[r] && cv.hasData[r]) atomic_add(cv.errs + 0, 1u);   // std::map::at throws in the reference
 					}
 					return;
 				}
@@ -846,8 +852,8 @@ inline void overlay_pass(Ctx &c, const DevGraph &G, const GraphView &g, const Ca
 				u32 nrec = 0;
 				for (u32 q = 0; q < nh; q++) if (q == 0 || !same_record(cd, a[q - 1], a[q])) nrec++;
 				recCnt_[r] = nrec; grpCnt_[r] = nh;
-				if (k == 0) cv.hasData[r] = nh ? 1u : 0u;
-				else if (nh == 0 && cv.hasData[r]) atomic_add(cv.errs + 0, 1u);   // std::map::at throws in the reference
+				if (k == 0) cv.hasData[r] = cd.evald[r];
+				else if (!cd.evald[r] && cv.hasData[r]) atomic_add(cv.errs + 0, 1u);   // std::map::at throws in the reference
 			});
 		} else group_by_warp = false;
 #endif
@@ -872,8 +878,8 @@ inline void overlay_pass(Ctx &c, const DevGraph &G, const GraphView &g, const Ca
 			u32 nrec = 0;
 			for (u32 t = 0; t < nh; t++) if (t == 0 || !same_record(cd, a[t - 1], a[t])) nrec++;
 			recCnt_[r] = nrec; grpCnt_[r] = nh;
-			if (k == 0) cv.hasData[r] = nh ? 1u : 0u;
-			else if (nh == 0 && cv.hasData[r]) atomic_add(cv.errs + 0, 1u);   // std::map::at throws in the reference
+			if (k == 0) cv.hasData[r] = cd.evald[r];
+			else if (!cd.evald[r] && cv.hasData[r]) atomic_add(cv.errs + 0, 1u);   // std::map::at throws in the reference
 		});
 		exclusive_scan(c, recCnt.p, recOff.p, (size_t)Rc + 1, OpAddU32(), 0u);
 		exclusive_scan(c, grpCnt.p, grpOff.p, (size_t)Rc + 1, OpAddU32(), 0u);

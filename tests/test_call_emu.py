@@ -71,6 +71,10 @@ def test_emu_perturbed_graphs_cli(emu_lib, tmp_path):
     """nested bubbles + random chords + random-walk haplotypes through the CLI, whole VCF byte for byte vs the compiled reference"""
     import os
     n, nrec, ntang, nsubr = cc.check_perturbed_cli(os.path.join(os.path.dirname(emu_lib), "povu_emu"), str(tmp_path), range(300))
+    # seed 6706: the first reference path only meets an inversion pin pair in region >1>9; the reference's trek still "has data"
+    # (get_min_rov default-inserts the ref's map for every context it looks at, overlay.cpp:478-479) and goes on to the second
+    # reference path, which yields a record
+    assert cc.check_perturbed_cli(os.path.join(os.path.dirname(emu_lib), "povu_emu"), str(tmp_path), [6706])[1] == 3
     assert n > 250 and nrec > 3000 and ntang > 300 and nsubr > 300, (n, nrec, ntang, nsubr)
     cli = os.path.join(os.path.dirname(emu_lib), "povu_emu")
     n, nrec, ntang, nsubr = cc.check_perturbed_cli(cli, str(tmp_path), range(150), build=cc.perturbed_graph_big)

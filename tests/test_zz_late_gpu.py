@@ -28,3 +28,9 @@ def test_gpu_cycle_tables_and_hierarchy_spans(gpu, tmp_path):
 def test_gpu_ffi_builder_on_perturbed_graphs(gpu, tmp_path):
     L = bc.ffi(os.path.join(bc.ROOT, "povu_b200", "libpovu_b200.so"))
     assert bc.check_ffi_perturbed(L, str(tmp_path), range(60, 100)) > 30
+
+
+def test_gpu_has_data_after_pin_pair_only(gpu, tmp_path):
+    """perturbed seed 6706 (see test_emu_perturbed_graphs_cli): a region whose first reference path only yields an inversion pin pair
+    still goes on to the second reference path"""
+    assert cc.check_perturbed_cli(CLI, str(tmp_path), [6706])[1] == 3
