@@ -294,7 +294,7 @@ struct Session {
 		// Components with < 3 vertices own no flubbles and get no tree (decompose.cpp:135-142).
 		forest.a_v.swap(dec.a_v); forest.z_v.swap(dec.z_v); forest.a_fwd.swap(dec.a_fwd); forest.z_fwd.swap(dec.z_fwd);
 		forest.parent.swap(dec.parent); forest.height.swap(dec.depth); forest.flBase.swap(dec.fl_base);
-		forest.family.assign(forest.a_v.size(), 'F');
+		forest.family.assign(forest.a_v.size(), 'F'); forest.orphan.clear();
 		forest.comp_id.clear(); forest.treeOff.assign(1, 0);
 		u32 base = 0;
 		for (u32 k = 0; k < dec.comp_nv.size(); k++) {
@@ -383,9 +383,11 @@ struct Session {
 		if (!forest_ready) throw std::runtime_error("call: no PVST forest (run decompose or read .pvst files first)");
 		upload_paths();
 		std::vector<u32> refs(ref_ids.begin(), ref_ids.end());
-		// sub-flubble families and everything below them are never selected (color.cpp:117-125)
+		// the sub-flubble CLAN -- concealed, smothered, midi (pvst.hpp:110-125) -- and everything below such a vertex is never
+		// selected (color.cpp:117-125); tiny (T) and parallel (O) vertices are flubble-like and are called like flubbles
 		std::vector<u8> excl;
-		if (forest_subfl < 0) { forest_subfl = 0; for (char f : forest.family) if (f != 'F') { forest_subfl = 1; break; } }   // once per forest, not per call
+		auto subfl = [](char f) { return f == 'C' || f == 'S' || f == 'M'; };
+		if (forest_subfl < 0) { forest_subfl = forest.orphan.empty() ? 0 : 1; for (char f : forest.family) if (subfl(f)) { forest_subfl = 1; break; } }   // once per forest, not per call
 		const bool any_excl = forest_subfl == 1;
 		if (any_excl) {
 			excl.assign(forest.n(), 0);
@@ -394,7 +396,7 @@ struct Session {
 			std::stable_sort(ord.begin(), ord.end(), [&](u32 a, u32 b) { return forest.height[a] < forest.height[b]; });
 			for (u32 f : ord) {
 				u32 p = forest.parent[f];
-				if (forest.family[f] != 'F' || (p != 0 && excl[forest.flBase[f] + p - 1])) excl[f] = 1;
+				if (subfl(forest.family[f]) || (f < forest.orphan.size() && forest.orphan[f]) || (p != 0 && excl[forest.flBase[f] + p - 1])) excl[f] = 1;   // (orphans: vertices the file's children lists never reach from the root)
 			}
 		}
 		pv::CallIn in;

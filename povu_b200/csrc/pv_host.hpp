@@ -266,6 +266,7 @@ struct Forest {
 	std::vector<u32> treeOff;                  // per tree: first flubble (size = trees + 1)
 	pv::hvec<u32> a_v, z_v, parent, height, flBase; pv::hvec<u8> a_fwd, z_fwd;   // per flubble; parent/height in PVST indices (page-locked: they are copied to the device)
 	pv::hvec<char> family;                  // 'F', 'T', 'O', 'C', 'S', 'M'
+	std::vector<u8> orphan;                 // 1 = not reachable from the tree's root through the children lists of the file (empty: none)
 	u32 n() const { return (u32)a_v.size(); }
 };
 
@@ -310,6 +311,7 @@ inline void read_pvst(const std::string &fp, const HostGraph &g, u32 comp_id, Fo
 		F.parent.push_back(0); F.height.push_back(1); F.flBase.push_back(base); F.family.push_back(r.typ);
 		file2pvst[r.id] = nv; row2pvst[i] = nv++;
 	}
+	std::vector<std::vector<u32>> kidsOf(nv);      // children lists as listed (a vertex may be listed under several parents)
 	for (size_t i = 0; i < rows.size(); i++) {
 		if (rows[i].kids == "." || row2pvst[i] == NONE32) continue;
 		const std::string &s = rows[i].kids;
@@ -319,10 +321,20 @@ inline void read_pvst(const std::string &fp, const HostGraph &g, u32 comp_id, Fo
 			size_t a = 0, z = t.size();
 			while (a < z && isspace((unsigned char)t[a])) a++;
 			while (z > a && isspace((unsigned char)t[z - 1])) z--;
-			if (z > a) { char *end = nullptr; std::string tt = t.substr(a, z - a); long v = strtol(tt.c_str(), &end, 10); if (end != tt.c_str()) { auto it = file2pvst.find((u32)v); if (it != file2pvst.end() && it->second > 0) F.parent[base + it->second - 1] = row2pvst[i]; } }
+			if (z > a) { char *end = nullptr; std::string tt = t.substr(a, z - a); long v = strtol(tt.c_str(), &end, 10); if (end != tt.c_str()) { auto it = file2pvst.find((u32)v); if (it != file2pvst.end() && it->second > 0) { F.parent[base + it->second - 1] = row2pvst[i]; kidsOf[row2pvst[i]].push_back(it->second); } } }
 			if (comma == std::string::npos) break;
 			pos = comma + 1;
 		}
+	}
+	// The reference only ever looks at vertices it reaches from the root through the children lists (color.cpp:104-163).  Its
+	// sub-flubble passes leave vertices that no list names (`decompose -s`: flubbles whose edge to the parent was deleted and
+	// re-added the wrong way round): those are never called.
+	{
+		std::vector<u8> seen(nv, 0); std::vector<u32> st(1, 0); seen[0] = 1;
+		while (!st.empty()) { u32 x = st.back(); st.pop_back(); for (u32 k : kidsOf[x]) if (!seen[k]) { seen[k] = 1; st.push_back(k); } }
+		bool any = false;
+		for (u32 j = 1; j < nv; j++) if (!seen[j]) any = true;
+		if (any || !F.orphan.empty()) { F.orphan.resize(F.n(), 0); for (u32 j = 1; j < nv; j++) if (!seen[j]) F.orphan[base + j - 1] = 1; }
 	}
 	// heights: root 0, child = parent + 1 (pvst.hpp:807-836); parents precede children in creation order only for
 	// files we wrote ourselves, so resolve iteratively

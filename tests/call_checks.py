@@ -427,3 +427,44 @@ def check_hub_graphs(pv, tmp, seeds, ref_every=4):
             assert f.pvst_texts(g["ids"]) == {int(x[:-5]): open(os.path.join(d, x)).read() for x in os.listdir(d)}, seed
             nref += 1
     return n, faithful, nref
+
+
+def check_subflubble_forests(cli, tmp, seeds, with_lpa=True):
+    """`call -f` on forests written by the REFERENCE's `decompose -s`: tiny (T) and parallel (O) vertices are flubble-like and are
+    called, the concealed / smothered / midi clan and everything below it is not (pvst.hpp:110-125, color.cpp:117-125), and
+    vertices that no children list reaches from the root -- the sub-flubble passes leave some -- are never looked at"""
+    import shutil
+    require_ref()
+    n = nrec = 0
+    fams = {}
+    strip = lambda t: [l for l in t.splitlines() if not l.startswith("##fileDate")]
+    cases = []
+    for seed in seeds:
+        g = perturbed_graph_big(seed) if seed % 2 else perturbed_graph(seed)
+        gfa = os.path.join(tmp, f"sf{seed}.gfa")
+        synth.write_gfa(g, gfa)
+        cases.append((gfa, g["paths"][0][0].split("#")[0]))
+    if with_lpa:
+        cases.append((helpers.fixture_path("LPA", tmp), "chm13"))
+    for gfa, prefix in cases:
+        d = gfa + ".forest"
+        shutil.rmtree(d, ignore_errors=True); os.makedirs(d)
+        if subprocess.run([REF, "decompose", "-i", gfa, "-o", d, "-t", "1", "-s"], capture_output=True).returncode != 0:
+            continue
+        for f in os.listdir(d):
+            for l in open(os.path.join(d, f)):
+                fams[l[0]] = fams.get(l[0], 0) + 1
+        r = subprocess.run([REF, "call", "-i", gfa, "-f", d, "-t", "1", "-P", prefix], capture_output=True, text=True)
+        if r.returncode != 0:
+            continue
+        m = subprocess.run([cli, "call", "-i", gfa, "-f", d, "-t", "1", "-P", prefix], capture_output=True, text=True)
+        if m.returncode != 0 and "the reference aborts on this input" in m.stderr:
+            continue
+        assert m.returncode == 0, (gfa, m.stderr[-300:])
+        a, b = strip(r.stdout), strip(m.stdout)
+        if "SUBR records had a merged length past the end of a walk" in m.stderr:
+            a = [l for l in a if l.startswith("#") or ("VARTYPE=" in l and "VARTYPE=SUBR" not in l)]
+            b = [l for l in b if "VARTYPE=SUBR" not in l]
+        assert a == b, gfa
+        n += 1; nrec += sum(1 for l in a if not l.startswith("#"))
+    return n, nrec, fams

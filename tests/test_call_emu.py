@@ -120,3 +120,9 @@ def test_emu_perturbed_files_and_restrict(emu_lib, tmp_path):
     import os
     n, nrec = cc.check_perturbed_files_and_restrict(os.path.join(os.path.dirname(emu_lib), "povu_emu"), str(tmp_path), range(90))
     assert n > 70 and nrec > 1200, (n, nrec)
+
+
+def test_emu_call_on_subflubble_forests(emu_lib, tmp_path):
+    import os
+    n, nrec, fams = cc.check_subflubble_forests(os.path.join(os.path.dirname(emu_lib), "povu_emu"), str(tmp_path), range(80))
+    assert n > 60 and nrec > 3000 and fams.get("T", 0) > 3000 and fams.get("C", 0) > 20, (n, nrec, fams)

@@ -34,3 +34,9 @@ def test_gpu_has_data_after_pin_pair_only(gpu, tmp_path):
     """perturbed seed 6706 (see test_emu_perturbed_graphs_cli): a region whose first reference path only yields an inversion pin pair
     still goes on to the second reference path"""
     assert cc.check_perturbed_cli(CLI, str(tmp_path), [6706])[1] == 3
+
+
+def test_gpu_call_on_subflubble_forests(gpu, tmp_path):
+    """see test_emu_call_on_subflubble_forests (host-side forest handling; a few graphs through the CUDA CLI)"""
+    n, nrec, fams = cc.check_subflubble_forests(CLI, str(tmp_path), range(12), with_lpa=True)
+    assert n > 8 and nrec > 2000, (n, nrec, fams)
