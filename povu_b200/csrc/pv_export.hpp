@@ -121,6 +121,10 @@ inline std::vector<PvstNode> parse_pvst_nodes(const std::string &text) {
 
 // the whole document.  Runs after call(); `input_name` = file name of the GFA; chunk_size = -c of the CLI (record order).
 inline void structure_export(Session &S, const std::string &path, const std::string &input_name, size_t chunk_size, const std::string &frames_jsonl) {
+	// forests written by the reference's `decompose -s` name vertices under several parents or under none; the tables below are
+	// rebuilt from one parent per vertex and would not reproduce that -- refuse instead of writing something else
+	for (char f : S.forest.family) if (f == 'C' || f == 'S' || f == 'M') throw std::runtime_error("structure export: forests with concealed / smothered / midi vertices (decompose -s) are not supported");
+	if (!S.forest.orphan.empty()) throw std::runtime_error("structure export: the forest has vertices that no children list reaches (decompose -s); not supported");
 	std::ofstream out(path, std::ios::binary);
 	if (!out.is_open()) throw std::runtime_error("could not open structure export path: " + path);
 	S.ensure_host(true, true, true);
